@@ -1,0 +1,312 @@
+/* ref_harness.c — TEST INFRASTRUCTURE ONLY.  Serves the xo_* oracle API (oracle/src/xo.h) with the
+ * UNMODIFIED reference: it is compiled against the headers under S/ and linked to oracle/_ref/libx264ref.so
+ * (the reference's own .c files built in place, see oracle/Makefile).  Nothing here computes pixels: every
+ * xo_* function only marshals buffers into the reference's structures and calls the reference's function.
+ * Exists only in the build container (S/ is absent on the GPU box; the built .so travels with the snapshot). */
+#include <stdlib.h>
+#include <string.h>
+#include "common/common.h"
+#include "encoder/me.h"
+#include "src/xo.h"
+
+extern int16_t *g_cost_mv[52];                 /* S/encoder/analyse.c:179 (this fork's exported copy) */
+extern uint16_t *x264_cost_mv_fpel[52][4];     /* S/encoder/analyse.c:177 */
+
+const char *xo_backend(void) { return "reference"; }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* encoder handles, keyed by what shapes the function tables and frame layout                        */
+typedef struct {
+    int width, height, me_method, subme_tables, sub8x8, lowres;
+    x264_t *h;
+    x264_frame_t *fenc;
+} hkey;
+static hkey g_h[64];
+static int g_nh;
+
+static x264_t *get_h(int width, int height, int me_method, int subme_tables, int sub8x8, int lowres, x264_frame_t **fenc)
+{
+    for (int i = 0; i < g_nh; i++)
+        if (g_h[i].width == width && g_h[i].height == height && g_h[i].me_method == me_method &&
+            g_h[i].subme_tables == subme_tables && g_h[i].sub8x8 == sub8x8 && g_h[i].lowres == lowres) {
+            if (fenc) *fenc = g_h[i].fenc;
+            return g_h[i].h;
+        }
+    x264_param_t p;
+    x264_param_default(&p);
+    p.i_width = width;
+    p.i_height = height;
+    p.i_threads = 1;
+    p.i_log_level = X264_LOG_NONE;
+    p.rc.i_rc_method = X264_RC_CQP;
+    p.rc.i_qp_constant = 26;
+    p.analyse.i_me_method = me_method;
+    p.analyse.i_me_range = 16;
+    p.analyse.i_subpel_refine = subme_tables;
+    p.analyse.b_psnr = 0;
+    p.analyse.b_ssim = 0;
+    if (sub8x8) p.analyse.inter |= X264_ANALYSE_PSUB8x8 | X264_ANALYSE_PSUB16x16;
+    if (lowres) { p.i_bframe = 3; p.i_bframe_adaptive = X264_B_ADAPT_FAST; }
+    x264_t *h = x264_encoder_open(&p);
+    if (!h || g_nh == 64) abort();
+    hkey *k = &g_h[g_nh++];
+    k->width = width; k->height = height; k->me_method = me_method; k->subme_tables = subme_tables;
+    k->sub8x8 = sub8x8; k->lowres = lowres; k->h = h;
+    k->fenc = x264_frame_new(h);
+    h->fenc = k->fenc;
+    if (fenc) *fenc = k->fenc;
+    return h;
+}
+
+/* make the reference build its own MV cost tables for qp: run its real encoder for I+P at --qp qp --me esa */
+static void ensure_costs(int qp)
+{
+    if (g_cost_mv[qp] && x264_cost_mv_fpel[qp][0])
+        return;
+    x264_param_t p;
+    x264_param_default(&p);
+    p.i_width = 32; p.i_height = 32; p.i_threads = 1; p.i_log_level = X264_LOG_NONE;
+    p.rc.i_rc_method = X264_RC_CQP;
+    p.rc.i_qp_constant = qp;
+    p.rc.f_ip_factor = 1.0; p.rc.f_pb_factor = 1.0;
+    p.analyse.i_me_method = X264_ME_ESA;
+    p.analyse.i_subpel_refine = 1;
+    p.i_bframe = 0;
+    p.i_scenecut_threshold = -1;
+    x264_t *h = x264_encoder_open(&p);
+    x264_picture_t pic, out;
+    x264_nal_t *nal; int nnal;
+    x264_picture_alloc(&pic, X264_CSP_I420, 32, 32);
+    for (int f = 0; f < 3; f++) {
+        for (int i = 0; i < 32 * 32; i++) pic.img.plane[0][i] = (uint8_t)((i * 7 + f * 13) ^ (i >> 5));
+        memset(pic.img.plane[1], 128, 16 * 16); memset(pic.img.plane[2], 128, 16 * 16);
+        pic.i_type = X264_TYPE_AUTO; pic.i_qpplus1 = 0; pic.i_pts = f;
+        x264_encoder_encode(h, &nal, &nnal, &pic, &out);
+    }
+    x264_picture_clean(&pic);
+    /* NOT closing h: this fork frees g_cost_mv[] in x264_encoder_close (S/encoder/encoder.c:2136-2145) */
+    if (!g_cost_mv[qp] || !x264_cost_mv_fpel[qp][0]) abort();
+}
+
+int xo_lambda(int qp) { extern const int x264_lambda_tab[52]; return x264_lambda_tab[qp]; }
+
+void xo_cost_mv_table(int qp, int16_t *out)
+{
+    ensure_costs(qp);
+    memcpy(out, g_cost_mv[qp], (4 * 4 * 2048 + 1) * sizeof(int16_t));
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+static x264_pixel_function_t g_pixf;
+static x264_mc_functions_t g_mc;
+static x264_dct_function_t g_dctf;
+static x264_quant_function_t g_quantf;
+static int g_tables;
+static void tables(void)
+{
+    if (g_tables) return;
+    x264_pixel_init(0, &g_pixf);
+    x264_mc_init(0, &g_mc);
+    x264_dct_init(0, &g_dctf);
+    x264_quant_init(NULL, 0, &g_quantf);
+    g_tables = 1;
+}
+
+int xo_pixel_cmp(int metric, int i_pixel, const uint8_t *p1, int s1, const uint8_t *p2, int s2)
+{
+    tables();
+    switch (metric) {
+    case XO_SAD:  return g_pixf.sad[i_pixel]((uint8_t *)p1, s1, (uint8_t *)p2, s2);
+    case XO_SSD:  return g_pixf.ssd[i_pixel]((uint8_t *)p1, s1, (uint8_t *)p2, s2);
+    case XO_SATD: return g_pixf.satd[i_pixel]((uint8_t *)p1, s1, (uint8_t *)p2, s2);
+    case XO_SA8D: return g_pixf.sa8d[i_pixel]((uint8_t *)p1, s1, (uint8_t *)p2, s2);
+    }
+    return -1;
+}
+int xo_pixel_var(int i_pixel, const uint8_t *pix, int stride) { tables(); return g_pixf.var[i_pixel]((uint8_t *)pix, stride); }
+uint64_t xo_pixel_hadamard_ac(int i_pixel, const uint8_t *pix, int stride) { tables(); return g_pixf.hadamard_ac[i_pixel]((uint8_t *)pix, stride); }
+int xo_pixel_ads(int i_pixel, const int enc_dc[4], const uint16_t *sums, int delta, const uint16_t *cost_mvx,
+                 int16_t *mvs, int width, int thresh)
+{
+    tables();
+    return g_pixf.ads[i_pixel]((int *)enc_dc, (uint16_t *)sums, delta, (uint16_t *)cost_mvx, mvs, width, thresh);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+void xo_geometry(int width, int height, xo_geom *g)
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(width, height, X264_ME_ESA, 1, 0, 1, &f);
+    memset(g, 0, sizeof(*g));
+    g->width = width; g->height = height;
+    g->mb_width = h->sps->i_mb_width; g->mb_height = h->sps->i_mb_height;
+    g->stride = f->i_stride[0]; g->lines = f->i_lines[0];
+    g->plane_size = g->stride * (g->lines + 2 * PADV);
+    g->origin = g->stride * PADV + PADH;
+    g->stride_lowres = f->i_stride_lowres; g->width_lowres = f->i_width_lowres; g->lines_lowres = f->i_lines_lowres;
+    g->plane_size_lowres = g->stride_lowres * (g->lines_lowres + 2 * PADV);
+    g->origin_lowres = g->stride_lowres * PADV + PADH;
+}
+
+/* copy a caller plane (pointer at pixel 0,0, padded all around) into/out of a reference frame plane */
+static void put_plane(uint8_t *dst00, const uint8_t *src00, int stride, int lines)
+{
+    memcpy(dst00 - stride * PADV - PADH, src00 - stride * PADV - PADH, (size_t)stride * (lines + 2 * PADV));
+}
+
+void xo_frame_expand_border(const xo_geom *g, uint8_t *plane)
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, X264_ME_ESA, 1, 0, 0, &f);
+    put_plane(f->plane[0], plane, g->stride, g->lines);
+    x264_frame_expand_border_mod16(h, f);
+    x264_frame_expand_border(h, f, 0, 1);
+    put_plane(plane, f->plane[0], g->stride, g->lines);
+}
+
+void xo_frame_filter(const xo_geom *g, const uint8_t *plane, uint8_t *dsth, uint8_t *dstv, uint8_t *dstc,
+                     uint16_t *integral, int b_sub8x8)
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, X264_ME_ESA, 1, b_sub8x8, 0, &f);
+    size_t isz = (size_t)g->stride * (g->lines + 2 * PADV) * sizeof(uint16_t) << b_sub8x8;
+    put_plane(f->plane[0], plane, g->stride, g->lines);
+    if (integral) memcpy(f->buffer[3], integral - g->stride * PADV - PADH, isz);
+    uint16_t *keep = f->integral;
+    if (!integral) f->integral = NULL;
+    x264_frame_filter(h, f, 0, 1);
+    x264_frame_expand_border_filtered(h, f, 0, 1);
+    f->integral = keep;
+    put_plane(dsth, f->filtered[1], g->stride, g->lines);
+    put_plane(dstv, f->filtered[2], g->stride, g->lines);
+    put_plane(dstc, f->filtered[3], g->stride, g->lines);
+    if (integral) memcpy(integral - g->stride * PADV - PADH, f->buffer[3], isz);
+}
+
+void xo_frame_init_lowres(const xo_geom *g, uint8_t *plane, uint8_t *l0, uint8_t *lh, uint8_t *lv, uint8_t *lc)
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, X264_ME_ESA, 1, 0, 1, &f);
+    put_plane(f->plane[0], plane, g->stride, g->lines);
+    x264_frame_init_lowres(h, f);
+    put_plane(plane, f->plane[0], g->stride, g->lines);
+    uint8_t *o[4] = { l0, lh, lv, lc };
+    for (int i = 0; i < 4; i++)
+        put_plane(o[i], f->lowres[i], g->stride_lowres, g->lines_lowres);
+}
+
+void xo_mc_luma(uint8_t *dst, int dst_stride, const uint8_t *const src[4], int src_stride, int mvx, int mvy, int w, int hgt)
+{
+    tables();
+    g_mc.mc_luma(dst, dst_stride, (uint8_t **)src, src_stride, mvx, mvy, w, hgt);
+}
+void xo_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride, int mvx, int mvy, int w, int hgt)
+{
+    tables();
+    g_mc.mc_chroma(dst, dst_stride, (uint8_t *)src, src_stride, mvx, mvy, w, hgt);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+static void run_search(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref[4], const uint16_t *integral,
+                       const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    /* the function tables depend on (me method, user subme>1): open the encoder the way the CLI would */
+    int tables_subme = in->fpel_satd || mbcmp_satd ? 7 : 1;
+    int tables_me = in->fpel_satd ? X264_ME_TESA : in->me_method;
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, tables_me, tables_subme, in->b_sub8x8, 0, &f);
+    DECLARE_ALIGNED_16(uint8_t fenc[16 * 16]);
+    x264_me_t m;
+    DECLARE_ALIGNED_4(int16_t mvc[16][2]);
+    ensure_costs(in->qp);
+    memset(&m, 0, sizeof(m));
+    for (int y = 0; y < x264_pixel_size[in->i_pixel].h; y++)
+        memcpy(fenc + 16 * y, fenc_plane + (in->by + y) * g->stride + in->bx, x264_pixel_size[in->i_pixel].w);
+    memcpy(mvc, in->mvc, sizeof(mvc));
+    h->fenc = f;
+    h->param.analyse.i_me_range = in->me_range;
+    h->mb.i_me_method = in->me_method;
+    h->mb.i_subpel_refine = subme;
+    h->mb.b_chroma_me = 0;
+    h->mb.i_qp = in->qp;
+    for (int k = 0; k < 2; k++) {
+        h->mb.mv_min_fpel[k] = in->mv_min_fpel[k]; h->mb.mv_max_fpel[k] = in->mv_max_fpel[k];
+        h->mb.mv_min_spel[k] = in->mv_min_spel[k]; h->mb.mv_max_spel[k] = in->mv_max_spel[k];
+    }
+    m.i_pixel = in->i_pixel;
+    m.p_cost_mv = g_cost_mv[in->qp] + 2 * 4 * 2048;
+    m.i_stride[0] = g->stride;
+    m.p_fenc[0] = fenc;
+    for (int k = 0; k < 4; k++)
+        m.p_fref[k] = fref[k] ? (uint8_t *)fref[k] + in->by * g->stride + in->bx : NULL;
+    m.integral = integral ? (uint16_t *)integral + in->by * g->stride + in->bx : NULL;
+    m.mvp[0] = in->mvp[0]; m.mvp[1] = in->mvp[1];
+    x264_me_search_ref(h, &m, mvc, in->i_mvc, NULL);
+    memset(out, 0, sizeof(*out));
+    out->mv[0] = m.mv[0]; out->mv[1] = m.mv[1];
+    out->cost = m.cost; out->cost_mv = m.cost_mv;
+    /* the reference does not expose its internal full-pel state; report what can be derived */
+    out->bmx = out->bmy = out->bcost = out->seed_mx = out->seed_my = out->seed_cost = -1;
+}
+
+void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
+                       const uint16_t *integral, const xo_me_in *in, xo_me_out *out)
+{
+    const uint8_t *planes[4] = { fref_plane, NULL, NULL, NULL };
+    run_search(g, fenc_plane, planes, integral, in, 1, 0, out);
+}
+void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
+                         const uint16_t *integral, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    run_search(g, fenc_plane, fref_planes, integral, in, subme, mbcmp_satd, out);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+void xo_sub4x4_dct(int16_t dct[16], const uint8_t *p1, const uint8_t *p2) { tables(); g_dctf.sub4x4_dct((void *)dct, (uint8_t *)p1, (uint8_t *)p2); }
+void xo_add4x4_idct(uint8_t *dst, int16_t dct[16]) { tables(); g_dctf.add4x4_idct(dst, (void *)dct); }
+void xo_sub8x8_dct8(int16_t dct[64], const uint8_t *p1, const uint8_t *p2) { tables(); g_dctf.sub8x8_dct8((void *)dct, (uint8_t *)p1, (uint8_t *)p2); }
+void xo_add8x8_idct8(uint8_t *dst, int16_t dct[64]) { tables(); g_dctf.add8x8_idct8(dst, (void *)dct); }
+void xo_dct4x4dc(int16_t d[16]) { tables(); g_dctf.dct4x4dc((void *)d); }
+void xo_idct4x4dc(int16_t d[16]) { tables(); g_dctf.idct4x4dc((void *)d); }
+void xo_add_idct_dc(uint8_t *dst, const int16_t *dc, int n)
+{
+    tables();
+    if (n == 4) g_dctf.add8x8_idct_dc(dst, (void *)dc);
+    else g_dctf.add16x16_idct_dc(dst, (void *)dc);
+}
+
+/* quantiser tables straight out of x264_cqm_init (run by x264_encoder_open) */
+static x264_t *g_cqm_h[2];
+static x264_t *cqm_h(int cqm)
+{
+    if (!g_cqm_h[cqm]) {
+        x264_param_t p;
+        x264_param_default(&p);
+        p.i_width = 32; p.i_height = 32; p.i_threads = 1; p.i_log_level = X264_LOG_NONE;
+        p.rc.i_rc_method = X264_RC_CQP; p.rc.i_qp_constant = 26;
+        p.analyse.b_transform_8x8 = 1;
+        p.i_cqm_preset = cqm ? X264_CQM_JVT : X264_CQM_FLAT;
+        g_cqm_h[cqm] = x264_encoder_open(&p);
+        if (!g_cqm_h[cqm]) abort();
+    }
+    return g_cqm_h[cqm];
+}
+void xo_quant4_tables(int cqm, int list, int qp, uint16_t mf[16], uint16_t bias[16])
+{
+    x264_t *h = cqm_h(cqm);
+    memcpy(mf, h->quant4_mf[list][qp], 32); memcpy(bias, h->quant4_bias[list][qp], 32);
+}
+void xo_quant8_tables(int cqm, int list, int qp, uint16_t mf[64], uint16_t bias[64])
+{
+    x264_t *h = cqm_h(cqm);
+    memcpy(mf, h->quant8_mf[list][qp], 128); memcpy(bias, h->quant8_bias[list][qp], 128);
+}
+void xo_dequant4_table(int cqm, int list, int dequant_mf[6][16]) { memcpy(dequant_mf, cqm_h(cqm)->dequant4_mf[list], 6 * 16 * sizeof(int)); }
+void xo_dequant8_table(int cqm, int list, int dequant_mf[6][64]) { memcpy(dequant_mf, cqm_h(cqm)->dequant8_mf[list], 6 * 64 * sizeof(int)); }
+int xo_quant_4x4(int16_t dct[16], const uint16_t mf[16], const uint16_t bias[16]) { tables(); return g_quantf.quant_4x4((void *)dct, (uint16_t *)mf, (uint16_t *)bias); }
+int xo_quant_8x8(int16_t dct[64], const uint16_t mf[64], const uint16_t bias[64]) { tables(); return g_quantf.quant_8x8((void *)dct, (uint16_t *)mf, (uint16_t *)bias); }
+int xo_quant_4x4_dc(int16_t dct[16], int mf, int bias) { tables(); return g_quantf.quant_4x4_dc((void *)dct, mf, bias); }
+int xo_quant_2x2_dc(int16_t dct[4], int mf, int bias) { tables(); return g_quantf.quant_2x2_dc((void *)dct, mf, bias); }
+void xo_dequant_4x4(int16_t dct[16], const int dequant_mf[6][16], int qp) { tables(); g_quantf.dequant_4x4((void *)dct, (void *)dequant_mf, qp); }
+void xo_dequant_8x8(int16_t dct[64], const int dequant_mf[6][64], int qp) { tables(); g_quantf.dequant_8x8((void *)dct, (void *)dequant_mf, qp); }
+void xo_dequant_4x4_dc(int16_t dct[16], const int dequant_mf[6][16], int qp) { tables(); g_quantf.dequant_4x4_dc((void *)dct, (void *)dequant_mf, qp); }

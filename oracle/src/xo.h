@@ -1,0 +1,136 @@
+/* xo.h — ORACLE API.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, single-threaded restatement of the data-parallel core of x264-snapshot-20090216-2245
+ * (S/ = /root/reference/x264-snapshot-20090216-2245/).  Every function cites the S/file:line it follows.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library; the product (libx264_cuda.so) never links or calls it.
+ *
+ * The SAME symbol set is exported by oracle/_ref/libref_harness.so, where each xo_* call is served by
+ * the UNMODIFIED reference code compiled from S/ (see oracle/ref_harness.c).  Tests run both and
+ * require identical bytes, which is how this restatement is pinned (the reference ships no golden
+ * vectors: SURVEY.md §4 / §8c).
+ */
+#ifndef XO_H
+#define XO_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* partition ids, S/common/pixel.h:30-42 */
+enum { XO_16x16 = 0, XO_16x8, XO_8x16, XO_8x8, XO_8x4, XO_4x8, XO_4x4 };
+/* metric ids for xo_pixel_cmp */
+enum { XO_SAD = 0, XO_SSD = 1, XO_SATD = 2, XO_SA8D = 3 };
+/* motion-search methods, S/x264.h:100-104 */
+enum { XO_ME_DIA = 0, XO_ME_HEX = 1, XO_ME_UMH = 2, XO_ME_ESA = 3, XO_ME_TESA = 4 };
+
+#define XO_PADH 32 /* S/common/frame.h:28-29 */
+#define XO_PADV 32
+#define XO_FENC_STRIDE 16 /* S/common/common.h:464-465 */
+#define XO_FDEC_STRIDE 32
+#define XO_COST_MAX (1 << 28) /* S/encoder/me.h:27 */
+
+const char *xo_backend(void); /* "port" (restatement) or "reference" (harness over S/) */
+
+/* ---------------- pixel metrics: S/common/pixel.c ---------------- */
+int xo_pixel_cmp(int metric, int i_pixel, const uint8_t *pix1, int stride1, const uint8_t *pix2, int stride2);
+int xo_pixel_var(int i_pixel /* XO_16x16 | XO_8x8 */, const uint8_t *pix, int stride);
+uint64_t xo_pixel_hadamard_ac(int i_pixel /* 16x16..8x8 */, const uint8_t *pix, int stride);
+/* S/common/pixel.c:515-559; i_pixel selects ads4/ads2/ads1 as x264_pixel_init does (:591-594, :793-796) */
+int xo_pixel_ads(int i_pixel, const int enc_dc[4], const uint16_t *sums, int delta, const uint16_t *cost_mvx,
+                 int16_t *mvs, int width, int thresh);
+
+/* ---------------- cost tables: S/encoder/analyse.c:140-218 ---------------- */
+int xo_lambda(int qp);
+/* fills out[0 .. 4*4*2048] ; the centre (mvd 0) is out[2*4*2048] exactly like p_cost_mv */
+void xo_cost_mv_table(int qp, int16_t *out);
+
+/* ---------------- frame geometry: S/common/frame.c:29-152 (cpu=0 -> align 16) ---------------- */
+typedef struct {
+    int width, height;       /* picture size as given by the user */
+    int mb_width, mb_height; /* in macroblocks */
+    int stride, lines;       /* luma stride / mod16 lines */
+    int plane_size;          /* stride*(lines+2*PADV) */
+    int origin;              /* offset of pixel (0,0) inside a plane buffer: stride*PADV+PADH */
+    int stride_lowres, width_lowres, lines_lowres, plane_size_lowres, origin_lowres;
+} xo_geom;
+void xo_geometry(int width, int height, xo_geom *g);
+
+/* ---------------- whole-frame filters ---------------- */
+/* S/common/frame.c:304-331 then :240-267 (luma only): pad the picture to mod16, replicate 32-px borders.
+ * plane points at pixel (0,0). */
+void xo_frame_expand_border(const xo_geom *g, uint8_t *plane);
+/* S/common/mc.c:404-463 with (mb_y=0,b_end=1) + S/common/frame.c:269-295: hpel planes h,v,c and the
+ * integral image(s).  Pointers address pixel (0,0) of their plane buffers; integral may be NULL.
+ * integral has room for stride*(lines+2*PADV) uint16 (twice that when sub8x8). */
+void xo_frame_filter(const xo_geom *g, const uint8_t *plane, uint8_t *dsth, uint8_t *dstv, uint8_t *dstc,
+                     uint16_t *integral, int b_sub8x8);
+/* S/common/mc.c:306-357 + S/common/frame.c:297-302; note: writes plane[width] column / lines row first,
+ * exactly like the reference (:315-317), hence plane is not const. */
+void xo_frame_init_lowres(const xo_geom *g, uint8_t *plane, uint8_t *l0, uint8_t *lh, uint8_t *lv, uint8_t *lc);
+
+/* S/common/mc.c:157-202: qpel sample fetch from the 4 hpel planes into dst (stride dst_stride) */
+void xo_mc_luma(uint8_t *dst, int dst_stride, const uint8_t *const src[4], int src_stride, int mvx, int mvy, int w, int h);
+/* S/common/mc.c:205-236 */
+void xo_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride, int mvx, int mvy, int w, int h);
+
+/* ---------------- full-pel motion search: S/encoder/me.c:156-631 with i_subpel_refine = 1 ----------------
+ * One call == one x264_me_search_ref() on a block, stopping before sub-pel refinement.
+ * Planes are whole padded frames; (bx,by) is the block's pixel position. */
+typedef struct {
+    int me_method;         /* XO_ME_* (DIA, HEX, ESA, TESA supported) */
+    int me_range;          /* h->param.analyse.i_me_range */
+    int qp;                /* selects lambda / p_cost_mv */
+    int fpel_satd;         /* 1: fpelcmp = SATD (subme>1 && TESA, S/encoder/encoder.c:608-618), 0: SAD */
+    int i_pixel;           /* XO_16x16 .. XO_4x4 */
+    int bx, by;            /* block position in pixels */
+    int mv_min_fpel[2], mv_max_fpel[2]; /* h->mb.mv_{min,max}_fpel */
+    int mv_min_spel[2], mv_max_spel[2]; /* h->mb.mv_{min,max}_spel (me.c:629, :699-700) */
+    int16_t mvp[2];        /* qpel predictor */
+    int i_mvc;             /* number of extra predictors */
+    int16_t mvc[16][2];
+    int b_sub8x8;          /* integral has the 4x4 plane */
+} xo_me_in;
+typedef struct {
+    int16_t mv[2];         /* qpel units */
+    int cost, cost_mv;
+    /* full-pel state right after the search loop (before "-> qpel mv"): what a device kernel must reproduce */
+    int bmx, bmy, bcost;
+    /* the same, right BEFORE the ESA/TESA/DIA/HEX loop (after predictors and (0,0)): the seed */
+    int seed_mx, seed_my, seed_cost;
+} xo_me_out;
+void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
+                       const uint16_t *integral, const xo_me_in *in, xo_me_out *out);
+/* the same search followed by refine_subpel (me.c:622-628): subme = h->mb.i_subpel_refine used by the
+ * search, mbcmp_satd = whether mbcmp is SATD (user subme>1).  fref_planes = {full, h, v, c}. */
+void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
+                         const uint16_t *integral, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out);
+
+/* ---------------- transforms: S/common/dct.c, quant: S/common/quant.c, tables: S/common/set.c ---------------- */
+void xo_sub4x4_dct(int16_t dct[16], const uint8_t *pix1 /*stride 16*/, const uint8_t *pix2 /*stride 32*/);
+void xo_add4x4_idct(uint8_t *dst /*stride 32*/, int16_t dct[16]);
+void xo_sub8x8_dct8(int16_t dct[64], const uint8_t *pix1, const uint8_t *pix2);
+void xo_add8x8_idct8(uint8_t *dst, int16_t dct[64]);
+void xo_dct4x4dc(int16_t d[16]);
+void xo_idct4x4dc(int16_t d[16]);
+void xo_add_idct_dc(uint8_t *dst, const int16_t *dc, int n /* 4: add8x8_idct_dc, 16: add16x16_idct_dc */);
+
+/* cqm: 0 = flat16, 1 = JVT.  Tables as built by x264_cqm_init (S/common/set.c:68-174) with default deadzones 21/11.
+ * list ids: 0 CQM_4IY 1 CQM_4PY 2 CQM_4IC 3 CQM_4PC (4x4), 0 CQM_8IY 1 CQM_8PY (8x8). */
+void xo_quant4_tables(int cqm, int list, int qp, uint16_t mf[16], uint16_t bias[16]);
+void xo_quant8_tables(int cqm, int list, int qp, uint16_t mf[64], uint16_t bias[64]);
+void xo_dequant4_table(int cqm, int list, int dequant_mf[6][16]);
+void xo_dequant8_table(int cqm, int list, int dequant_mf[6][64]);
+int xo_quant_4x4(int16_t dct[16], const uint16_t mf[16], const uint16_t bias[16]);
+int xo_quant_8x8(int16_t dct[64], const uint16_t mf[64], const uint16_t bias[64]);
+int xo_quant_4x4_dc(int16_t dct[16], int mf, int bias);
+int xo_quant_2x2_dc(int16_t dct[4], int mf, int bias);
+void xo_dequant_4x4(int16_t dct[16], const int dequant_mf[6][16], int qp);
+void xo_dequant_8x8(int16_t dct[64], const int dequant_mf[6][64], int qp);
+void xo_dequant_4x4_dc(int16_t dct[16], const int dequant_mf[6][16], int qp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,354 @@
+/* xo_me.c — ORACLE (test infrastructure only): MV cost tables and the integer/sub-pel motion search of
+ * S/encoder/me.c (x264_me_search_ref :156-631, refine_subpel :680-778), restated with whole padded planes
+ * as inputs.  UMH is not restated (outside SURVEY.md §8).  The ESA branch is written as the plain raster
+ * argmin that SURVEY.md App. D1 proved byte-identical to the SEA code; the TESA branch reproduces the
+ * ADS/SAD threshold list exactly because its result depends on it. */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "xo.h"
+
+static const int blk_w[7] = { 16, 16, 8, 8, 8, 4, 4 };
+static const int blk_h[7] = { 16, 8, 16, 8, 4, 8, 4 };
+
+static inline int clip3(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+/* S/encoder/analyse.c:140-148: lambda = 2^(qp/6-2) rounded by hand */
+int xo_lambda(int qp)
+{
+    static const uint8_t tab[52] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4,
+                                     5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 23, 25, 29, 32, 36, 40, 45,
+                                     51, 57, 64, 72, 81, 91 };
+    return tab[qp];
+}
+
+/* S/encoder/analyse.c:40,192-203.  The reference evaluates, in this exact mixed float/double form,
+ *   lambda * ( ((float)log(i+1)) / log(2) * 2 + 0.718f + !!i ) + .5f   truncated to int16.
+ * Same compiler and -ffast-math as the reference build; equality with the reference's
+ * own g_cost_mv[] is asserted for all 52 qps in tests/test_oracle_vs_ref.py. */
+void xo_cost_mv_table(int qp, int16_t *out)
+{
+    int lambda = xo_lambda(qp);
+    int16_t *c = out + 2 * 4 * 2048;
+    for (int i = 0; i <= 2 * 4 * 2048; i++)
+        c[-i] = c[i] = lambda * (((float)log((double)(i + 1))) / (log((double)2)) * 2 + 0.718f + !!i) + .5f;
+}
+
+/* per-process cache of the 52 tables */
+static int16_t *g_tab[52];
+static const int16_t *cost_table(int qp)
+{
+    if (!g_tab[qp]) {
+        int16_t *t = malloc((4 * 4 * 2048 + 1) * sizeof(int16_t));
+        xo_cost_mv_table(qp, t);
+        g_tab[qp] = t;
+    }
+    return g_tab[qp] + 2 * 4 * 2048;
+}
+
+typedef struct {
+    const xo_geom *g;
+    const xo_me_in *in;
+    uint8_t fenc[16 * 16];       /* stride-16 copy of the block, like h->mb.pic.p_fenc */
+    const uint8_t *fref[4];      /* block-positioned pointers into full/h/v/c planes */
+    const int16_t *cmx, *cmy;    /* p_cost_mv - mvp[k] */
+    int bw, bh, stride;
+    int fpel_metric, sub_metric; /* XO_SAD / XO_SATD */
+} me_ctx;
+
+static int fpel_cost(const me_ctx *c, int mx, int my)
+{
+    return xo_pixel_cmp(c->fpel_metric, c->in->i_pixel, c->fenc, 16, c->fref[0] + my * c->stride + mx, c->stride) +
+           c->cmx[mx << 2] + c->cmy[my << 2];
+}
+#define TRY_FPEL(mx_, my_) do { int cst_ = fpel_cost(c, (mx_), (my_)); \
+    if (cst_ < bcost) { bcost = cst_; bmx = (mx_); bmy = (my_); } } while (0)
+
+/* qpel-position block compare through the 4 hpel planes (COST_MV_HPEL me.c:65-72, COST_MV_SAD/SATD :646-677) */
+static int qpel_cost(const me_ctx *c, int metric, int mx, int my)
+{
+    uint8_t tmp[16 * 16];
+    xo_mc_luma(tmp, 16, c->fref, c->stride, mx, my, c->bw, c->bh);
+    return xo_pixel_cmp(metric, c->in->i_pixel, c->fenc, 16, tmp, 16) + c->cmx[mx] + c->cmy[my];
+}
+
+static const int8_t hex_ring[8][2] = { { -1, -2 }, { -2, 0 }, { -1, 2 }, { 1, 2 }, { 2, 0 }, { 1, -2 }, { -1, -2 }, { -2, 0 } };
+static const int8_t prev_of[8] = { 5, 0, 1, 2, 3, 4, 5, 0 }; /* (x-1)%6, me.c:46-47 */
+
+typedef struct { int sad; int16_t mx, my; } cand_t;
+
+/* extended input for sub-pel: subme level, mbcmp metric and the hpel planes */
+typedef struct {
+    int subme;      /* h->mb.i_subpel_refine */
+    int mbcmp_satd; /* mbcmp == satd (user subme>1) */
+} me_sub;
+
+static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
+                    const uint16_t *integral, const xo_me_in *in, const me_sub *sub, xo_me_out *out)
+{
+    me_ctx cx, *c = &cx;
+    const int stride = g->stride, range = in->me_range;
+    const int x_min = in->mv_min_fpel[0], y_min = in->mv_min_fpel[1];
+    const int x_max = in->mv_max_fpel[0], y_max = in->mv_max_fpel[1];
+    const int16_t *tab = cost_table(in->qp);
+    int bmx, bmy, bcost, pmx, pmy;
+    int bpred_mx = 0, bpred_my = 0, bpred_cost = XO_COST_MAX;
+
+    c->g = g; c->in = in; c->stride = stride;
+    c->bw = blk_w[in->i_pixel]; c->bh = blk_h[in->i_pixel];
+    c->fpel_metric = in->fpel_satd ? XO_SATD : XO_SAD;
+    c->sub_metric = sub->mbcmp_satd ? XO_SATD : XO_SAD;
+    c->cmx = tab - in->mvp[0];
+    c->cmy = tab - in->mvp[1];
+    for (int y = 0; y < c->bh; y++)
+        memcpy(c->fenc + 16 * y, fenc_plane + (in->by + y) * stride + in->bx, c->bw);
+    for (int k = 0; k < 4; k++)
+        c->fref[k] = fref_planes[k] ? fref_planes[k] + in->by * stride + in->bx : NULL;
+
+    /* me.c:182-186 */
+    bmx = clip3(in->mvp[0], x_min * 4, x_max * 4);
+    bmy = clip3(in->mvp[1], y_min * 4, y_max * 4);
+    pmx = (bmx + 2) >> 2;
+    pmy = (bmy + 2) >> 2;
+    bcost = XO_COST_MAX;
+
+    if (sub->subme >= 3) { /* me.c:189-205: predictors compared at qpel precision with fpelcmp */
+        uint32_t bmv = ((uint32_t)(uint16_t)bmx) | ((uint32_t)bmy << 16);
+#define TRY_PRED(mx_, my_) do { int cst_ = qpel_cost(c, c->fpel_metric, (mx_), (my_)); \
+        if (cst_ < bpred_cost) { bpred_cost = cst_; bpred_mx = (mx_); bpred_my = (my_); } } while (0)
+        TRY_PRED(bmx, bmy);
+        for (int i = 0; i < in->i_mvc; i++) {
+            uint32_t v = ((uint32_t)(uint16_t)in->mvc[i][0]) | ((uint32_t)(uint16_t)in->mvc[i][1] << 16);
+            if (v && (bmv - v)) {
+                int mx = clip3(in->mvc[i][0], x_min * 4, x_max * 4);
+                int my = clip3(in->mvc[i][1], y_min * 4, y_max * 4);
+                TRY_PRED(mx, my);
+            }
+        }
+        bmx = (bpred_mx + 2) >> 2;
+        bmy = (bpred_my + 2) >> 2;
+        TRY_FPEL(bmx, bmy);
+    } else { /* me.c:207-227 */
+        TRY_FPEL(pmx, pmy);
+        bcost -= c->cmx[pmx << 2] + c->cmy[pmy << 2];
+        for (int i = 0; i < in->i_mvc; i++) {
+            int mx = (in->mvc[i][0] + 2) >> 2;
+            int my = (in->mvc[i][1] + 2) >> 2;
+            if ((mx | my) && ((mx - bmx) | (my - bmy))) {
+                mx = clip3(mx, x_min, x_max);
+                my = clip3(my, y_min, y_max);
+                TRY_FPEL(mx, my);
+            }
+        }
+    }
+    TRY_FPEL(0, 0); /* me.c:229 */
+    out->seed_mx = bmx; out->seed_my = bmy; out->seed_cost = bcost;
+
+#define IN_RANGE(mx_, my_) ((mx_) >= x_min && (mx_) <= x_max && (my_) >= y_min && (my_) <= y_max)
+    switch (in->me_method) {
+    case XO_ME_DIA: { /* me.c:233-244 */
+        int i = 0;
+        do {
+            int ox = bmx, oy = bmy;
+            TRY_FPEL(ox, oy - 1); TRY_FPEL(ox, oy + 1); TRY_FPEL(ox - 1, oy); TRY_FPEL(ox + 1, oy);
+            if (bmx == ox && bmy == oy) break;
+            if (!IN_RANGE(bmx, bmy)) break;
+        } while (++i < range);
+        break;
+    }
+    case XO_ME_HEX: { /* me.c:246-305 (the de-duplicated form) */
+        int costs[6], dir = -2;
+        static const int8_t first[6][2] = { { -2, 0 }, { -1, 2 }, { 1, 2 }, { 2, 0 }, { 1, -2 }, { -1, -2 } };
+        for (int k = 0; k < 6; k++)
+            costs[k] = fpel_cost(c, bmx + first[k][0], bmy + first[k][1]);
+        for (int k = 0; k < 6; k++)
+            if (costs[k] < bcost) { bcost = costs[k]; dir = k; }
+        if (dir != -2) {
+            bmx += hex_ring[dir + 1][0];
+            bmy += hex_ring[dir + 1][1];
+            for (int i = 1; i < range / 2 && IN_RANGE(bmx, bmy); i++) {
+                int odir = prev_of[dir + 1];
+                for (int k = 0; k < 3; k++)
+                    costs[k] = fpel_cost(c, bmx + hex_ring[odir + k][0], bmy + hex_ring[odir + k][1]);
+                dir = -2;
+                for (int k = 0; k < 3; k++)
+                    if (costs[k] < bcost) { bcost = costs[k]; dir = odir - 1 + k; }
+                if (dir == -2) break;
+                bmx += hex_ring[dir + 1][0];
+                bmy += hex_ring[dir + 1][1];
+            }
+        }
+        { /* square refine, me.c:301-304 */
+            int ox = bmx, oy = bmy;
+            static const int8_t sq[8][2] = { { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 }, { -1, -1 }, { -1, 1 }, { 1, -1 }, { 1, 1 } };
+            for (int k = 0; k < 8; k++)
+                TRY_FPEL(ox + sq[k][0], oy + sq[k][1]);
+        }
+        break;
+    }
+    case XO_ME_ESA:
+    case XO_ME_TESA: { /* me.c:449-600 */
+        const int min_x = bmx - range > x_min ? bmx - range : x_min;
+        const int min_y = bmy - range > y_min ? bmy - range : y_min;
+        const int max_x = bmx + range < x_max ? bmx + range : x_max;
+        const int max_y = bmy + range < y_max ? bmy + range : y_max;
+        const int width = (max_x - min_x + 3) & ~3;
+        if (in->me_method == XO_ME_ESA) {
+            /* ADS only removes candidates whose cost lower bound is >= bcost, so the survivors' scan in
+             * raster order with strict '<' equals this loop. */
+            for (int my = min_y; my <= max_y; my++)
+                for (int mx = min_x; mx < min_x + width; mx++)
+                    TRY_FPEL(mx, my);
+        } else {
+            /* me.c:469-489: DC of the fenc sub-blocks */
+            int enc_dc[4];
+            const int sad_size = in->i_pixel <= XO_8x8 ? XO_8x8 : XO_4x4;
+            int delta = blk_w[sad_size];
+            const uint16_t *sums_base = integral + in->by * stride + in->bx;
+            static const uint8_t zero[8 * 16];
+            uint16_t *row_cost = malloc((width + 16) * sizeof(uint16_t));
+            int16_t *xs = malloc((width + 16) * sizeof(int16_t));
+            cand_t *list = malloc(sizeof(cand_t) * (size_t)(width + 4) * (max_y - min_y + 2));
+            int n = 0, limit;
+            const int sad_thresh = range <= 16 ? 10 : range <= 24 ? 11 : 12;
+            enc_dc[0] = xo_pixel_cmp(XO_SAD, sad_size, zero, 16, c->fenc, 16);
+            enc_dc[1] = xo_pixel_cmp(XO_SAD, sad_size, zero, 16, c->fenc + delta, 16);
+            enc_dc[2] = xo_pixel_cmp(XO_SAD, sad_size, zero, 16, c->fenc + delta * 16, 16);
+            enc_dc[3] = xo_pixel_cmp(XO_SAD, sad_size, zero, 16, c->fenc + delta + delta * 16, 16);
+            if (delta == 4)
+                sums_base += stride * (g->lines + XO_PADV * 2);
+            if (in->i_pixel == XO_16x16 || in->i_pixel == XO_8x16 || in->i_pixel == XO_4x8)
+                delta *= stride;
+            if (in->i_pixel == XO_8x16 || in->i_pixel == XO_4x8)
+                enc_dc[1] = enc_dc[2];
+            for (int i = 0; i < width; i++)
+                row_cost[i] = (uint16_t)c->cmx[(min_x + i) << 2];
+
+            int bsad = xo_pixel_cmp(XO_SAD, in->i_pixel, c->fenc, 16, c->fref[0] + bmy * stride + bmx, stride) +
+                       c->cmx[bmx << 2] + c->cmy[bmy << 2];
+            for (int my = min_y; my <= max_y; my++) {
+                int ycost = c->cmy[my << 2];
+                if (bsad <= ycost)
+                    continue;
+                bsad -= ycost;
+                int xn = xo_pixel_ads(in->i_pixel, enc_dc, sums_base + min_x + my * stride, delta, row_cost, xs,
+                                      width, bsad * 17 / 16);
+                for (int i = 0; i < xn; i++) {
+                    int mx = min_x + xs[i];
+                    /* NB me.c:518,531: the reference indexes cost_fpel_mvx by xs[i] WITHOUT min_x here (while ADS
+                     * got cost_fpel_mvx+min_x, :505): the SAD-stage x cost is that of mx = xs[i].  Reproduced. */
+                    int sad = xo_pixel_cmp(XO_SAD, in->i_pixel, c->fenc, 16, c->fref[0] + mx + my * stride, stride) +
+                              (uint16_t)c->cmx[xs[i] << 2];
+                    if (sad < bsad * sad_thresh >> 3) {
+                        if (sad < bsad) bsad = sad;
+                        list[n].sad = sad + ycost;
+                        list[n].mx = mx;
+                        list[n].my = my;
+                        n++;
+                    }
+                }
+                bsad += ycost;
+            }
+            limit = range / 2;
+            if (n > limit * 2) { /* me.c:543-558 */
+                int i, j;
+                bsad = bsad * (sad_thresh + 8) >> 4;
+                for (i = 0; i < n && list[i].sad <= bsad; i++);
+                for (j = i; j < n; j++)
+                    if (list[j].sad <= bsad)
+                        list[i++] = list[j];
+                n = i;
+            }
+            if (n > limit) { /* me.c:559-576: partial selection sort, first index wins ties */
+                for (int i = 0; i < limit; i++) {
+                    int bj = i, bs = list[bj].sad;
+                    for (int j = i + 1; j < n; j++)
+                        if (list[j].sad < bs) { bs = list[j].sad; bj = j; }
+                    if (bj > i) { cand_t t = list[i]; list[i] = list[bj]; list[bj] = t; }
+                }
+                n = limit;
+            }
+            for (int i = 0; i < n; i++)
+                TRY_FPEL(list[i].mx, list[i].my);
+            free(row_cost); free(xs); free(list);
+        }
+        break;
+    }
+    default:
+        break;
+    }
+    out->bmx = bmx; out->bmy = bmy; out->bcost = bcost;
+
+    /* me.c:603-620 */
+    int mvx, mvy, cost;
+    if (bpred_cost < bcost) { mvx = bpred_mx; mvy = bpred_my; cost = bpred_cost; }
+    else { mvx = bmx << 2; mvy = bmy << 2; cost = bcost; }
+    int cost_mv = c->cmx[mvx] + c->cmy[mvy];
+    if (bmx == pmx && bmy == pmy && sub->subme < 3)
+        cost += cost_mv;
+
+    if (sub->subme >= 2) {
+        /* refine_subpel(h, m, hpel, qpel, NULL, 0): me.c:680-778 */
+        static const int8_t iters[10][4] = { { 0, 0, 0, 0 }, { 1, 1, 0, 0 }, { 0, 1, 1, 0 }, { 0, 2, 1, 0 }, { 0, 2, 1, 1 },
+                                             { 0, 2, 1, 2 }, { 0, 0, 2, 2 }, { 0, 0, 2, 2 }, { 0, 0, 4, 10 }, { 0, 0, 4, 10 } };
+        int hpel_iters = iters[sub->subme][2], qpel_iters = iters[sub->subme][3];
+        int sbmx = mvx, sbmy = mvy, sbcost = cost, odir = -1, bdir;
+        const int spel_y_max = in->mv_max_spel[1];
+        if (hpel_iters && sub->subme < 3) {
+            int mx = clip3(in->mvp[0], in->mv_min_spel[0], in->mv_max_spel[0]);
+            int my = clip3(in->mvp[1], in->mv_min_spel[1], in->mv_max_spel[1]);
+            if ((mx - sbmx) | (my - sbmy)) {
+                int cst = qpel_cost(c, c->fpel_metric, mx, my);
+                if (cst < sbcost) { sbcost = cst; sbmx = mx; sbmy = my; }
+            }
+        }
+        for (int i = hpel_iters; i > 0; i--) { /* me.c:710-727: fpelcmp on the 4 half-pel neighbours */
+            int ox = sbmx, oy = sbmy, cst;
+            cst = qpel_cost(c, c->fpel_metric, ox, oy - 2); if (cst < sbcost) { sbcost = cst; sbmy = oy - 2; }
+            cst = qpel_cost(c, c->fpel_metric, ox, oy + 2); if (cst < sbcost) { sbcost = cst; sbmy = oy + 2; }
+            cst = qpel_cost(c, c->fpel_metric, ox - 2, oy); if (cst < sbcost) { sbcost = cst; sbmx = ox - 2; sbmy = oy; }
+            cst = qpel_cost(c, c->fpel_metric, ox + 2, oy); if (cst < sbcost) { sbcost = cst; sbmx = ox + 2; sbmy = oy; }
+            if (sbmx == ox && sbmy == oy) break;
+        }
+        /* !b_refine_qpel: me.c:729-736 */
+        if (sbmy > spel_y_max) sbmy = spel_y_max;
+        sbcost = qpel_cost(c, c->sub_metric, sbmx, sbmy);
+        bdir = -1;
+        for (int i = qpel_iters; i > 0; i--) { /* me.c:755-767 */
+            int ox = sbmx, oy = sbmy;
+            static const int8_t d[4][2] = { { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 } };
+            odir = bdir;
+            for (int k = 0; k < 4; k++)
+                if ((k ^ 1) != odir) {
+                    int cst = qpel_cost(c, c->sub_metric, ox + d[k][0], oy + d[k][1]);
+                    if (cst < sbcost) { sbcost = cst; sbmx = ox + d[k][0]; sbmy = oy + d[k][1]; bdir = k; }
+                }
+            if (sbmx == ox && sbmy == oy) break;
+        }
+        if (sbmy > spel_y_max) { /* me.c:770-775 */
+            sbmy = spel_y_max;
+            sbcost = qpel_cost(c, c->sub_metric, sbmx, sbmy);
+        }
+        mvx = sbmx; mvy = sbmy; cost = sbcost;
+        cost_mv = c->cmx[mvx] + c->cmy[mvy];
+    } else if (mvy > in->mv_max_spel[1]) {
+        mvy = in->mv_max_spel[1]; /* me.c:629-630 */
+    }
+    out->mv[0] = mvx; out->mv[1] = mvy; out->cost = cost; out->cost_mv = cost_mv;
+}
+
+void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
+                       const uint16_t *integral, const xo_me_in *in, xo_me_out *out)
+{
+    const uint8_t *planes[4] = { fref_plane, NULL, NULL, NULL };
+    me_sub sub = { 1, 0 };
+    me_core(g, fenc_plane, planes, integral, in, &sub, out);
+}
+
+/* full search incl. sub-pel refinement; subme = h->mb.i_subpel_refine, mbcmp_satd = (user subme > 1) */
+void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
+                         const uint16_t *integral, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    me_sub sub = { subme, mbcmp_satd };
+    me_core(g, fenc_plane, fref_planes, integral, in, &sub, out);
+}

@@ -1,0 +1,183 @@
+"""ctypes binding of the ORACLE api (oracle/src/xo.h).  Test infrastructure only.
+
+Two shared objects export this same symbol set:
+  oracle/liboracle.so            -- our C restatement ("port")
+  oracle/_ref/libref_harness.so  -- the unmodified reference compiled from /root/reference ("reference");
+                                    present only when built in the container (it travels to the GPU box
+                                    inside the gpurun snapshot).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PORT_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+
+PADH = PADV = 32
+SAD, SSD, SATD, SA8D = 0, 1, 2, 3
+P16x16, P16x8, P8x16, P8x8, P8x4, P4x8, P4x4 = range(7)
+BLK_W = [16, 16, 8, 8, 8, 4, 4]
+BLK_H = [16, 8, 16, 8, 4, 8, 4]
+ME_DIA, ME_HEX, ME_UMH, ME_ESA, ME_TESA = range(5)
+COST_MAX = 1 << 28
+
+
+class Geom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "width", "height", "mb_width", "mb_height", "stride", "lines", "plane_size", "origin",
+        "stride_lowres", "width_lowres", "lines_lowres", "plane_size_lowres", "origin_lowres")]
+
+
+class MeIn(C.Structure):
+    _fields_ = [("me_method", C.c_int), ("me_range", C.c_int), ("qp", C.c_int), ("fpel_satd", C.c_int),
+                ("i_pixel", C.c_int), ("bx", C.c_int), ("by", C.c_int),
+                ("mv_min_fpel", C.c_int * 2), ("mv_max_fpel", C.c_int * 2),
+                ("mv_min_spel", C.c_int * 2), ("mv_max_spel", C.c_int * 2),
+                ("mvp", C.c_int16 * 2), ("i_mvc", C.c_int), ("mvc", (C.c_int16 * 2) * 16), ("b_sub8x8", C.c_int)]
+
+
+class MeOut(C.Structure):
+    _fields_ = [("mv", C.c_int16 * 2), ("cost", C.c_int), ("cost_mv", C.c_int),
+                ("bmx", C.c_int), ("bmy", C.c_int), ("bcost", C.c_int),
+                ("seed_mx", C.c_int), ("seed_my", C.c_int), ("seed_cost", C.c_int)]
+
+
+u8p = C.POINTER(C.c_uint8)
+u16p = C.POINTER(C.c_uint16)
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int)
+
+
+def _ptr(a, ty=u8p, off=0):
+    """pointer to element `off` of a contiguous numpy array"""
+    assert a.flags["C_CONTIGUOUS"]
+    return C.cast(a.ctypes.data + off * a.itemsize, ty)
+
+
+class Oracle:
+    def __init__(self, path):
+        self.lib = L = C.CDLL(path)
+        L.xo_backend.restype = C.c_char_p
+        L.xo_pixel_cmp.argtypes = [C.c_int, C.c_int, u8p, C.c_int, u8p, C.c_int]
+        L.xo_pixel_var.argtypes = [C.c_int, u8p, C.c_int]
+        L.xo_pixel_hadamard_ac.argtypes = [C.c_int, u8p, C.c_int]
+        L.xo_pixel_hadamard_ac.restype = C.c_uint64
+        L.xo_pixel_ads.argtypes = [C.c_int, i32p, u16p, C.c_int, u16p, i16p, C.c_int, C.c_int]
+        L.xo_cost_mv_table.argtypes = [C.c_int, i16p]
+        L.xo_geometry.argtypes = [C.c_int, C.c_int, C.POINTER(Geom)]
+        L.xo_frame_expand_border.argtypes = [C.POINTER(Geom), u8p]
+        L.xo_frame_filter.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, u8p, u16p, C.c_int]
+        L.xo_frame_init_lowres.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, u8p, u8p]
+        L.xo_mc_luma.argtypes = [u8p, C.c_int, C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.xo_mc_chroma.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.xo_me_search_fpel.argtypes = [C.POINTER(Geom), u8p, u8p, u16p, C.POINTER(MeIn), C.POINTER(MeOut)]
+        L.xo_me_search_subpel.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), u16p, C.POINTER(MeIn), C.c_int,
+                                          C.c_int, C.POINTER(MeOut)]
+        for n in ("xo_sub4x4_dct", "xo_sub8x8_dct8"):
+            getattr(L, n).argtypes = [i16p, u8p, u8p]
+        for n in ("xo_add4x4_idct", "xo_add8x8_idct8"):
+            getattr(L, n).argtypes = [u8p, i16p]
+        L.xo_dct4x4dc.argtypes = [i16p]
+        L.xo_idct4x4dc.argtypes = [i16p]
+        L.xo_add_idct_dc.argtypes = [u8p, i16p, C.c_int]
+        L.xo_quant4_tables.argtypes = [C.c_int, C.c_int, C.c_int, u16p, u16p]
+        L.xo_quant8_tables.argtypes = [C.c_int, C.c_int, C.c_int, u16p, u16p]
+        L.xo_dequant4_table.argtypes = [C.c_int, C.c_int, i32p]
+        L.xo_dequant8_table.argtypes = [C.c_int, C.c_int, i32p]
+        L.xo_quant_4x4.argtypes = [i16p, u16p, u16p]
+        L.xo_quant_8x8.argtypes = [i16p, u16p, u16p]
+        L.xo_quant_4x4_dc.argtypes = [i16p, C.c_int, C.c_int]
+        L.xo_quant_2x2_dc.argtypes = [i16p, C.c_int, C.c_int]
+        for n in ("xo_dequant_4x4", "xo_dequant_8x8", "xo_dequant_4x4_dc"):
+            getattr(L, n).argtypes = [i16p, i32p, C.c_int]
+        self.backend = L.xo_backend().decode()
+
+    # ---- convenience wrappers (numpy in / numpy out) ----
+    def geometry(self, w, h):
+        g = Geom()
+        self.lib.xo_geometry(w, h, C.byref(g))
+        return g
+
+    def pixel_cmp(self, metric, i_pixel, a, sa, b, sb, offa=0, offb=0):
+        return self.lib.xo_pixel_cmp(metric, i_pixel, _ptr(a, u8p, offa), sa, _ptr(b, u8p, offb), sb)
+
+    def cost_mv_table(self, qp):
+        t = np.zeros(4 * 4 * 2048 + 1, np.int16)
+        self.lib.xo_cost_mv_table(qp, _ptr(t, i16p))
+        return t
+
+    def new_plane(self, g, fill=0):
+        """padded luma plane buffer; pixel (0,0) is at flat index g.origin"""
+        return np.full(g.plane_size, fill, np.uint8)
+
+    def plane_from_picture(self, g, pic):
+        """pic: (height,width) uint8 -> padded plane with mod16 + 32px border replication done by the oracle"""
+        p = self.new_plane(g)
+        v = p[g.origin - 0:].view()
+        for y in range(g.height):
+            o = g.origin + y * g.stride
+            p[o:o + g.width] = pic[y]
+        self.lib.xo_frame_expand_border(C.byref(g), _ptr(p, u8p, g.origin))
+        return p
+
+    def frame_filter(self, g, plane, sub8x8=0, want_integral=True):
+        h = np.zeros(g.plane_size, np.uint8)
+        v = np.zeros(g.plane_size, np.uint8)
+        c = np.zeros(g.plane_size, np.uint8)
+        integ = np.zeros(g.plane_size << sub8x8, np.uint16) if want_integral else None
+        self.lib.xo_frame_filter(C.byref(g), _ptr(plane, u8p, g.origin), _ptr(h, u8p, g.origin), _ptr(v, u8p, g.origin),
+                                 _ptr(c, u8p, g.origin), _ptr(integ, u16p, g.origin) if want_integral else None, sub8x8)
+        return h, v, c, integ
+
+    def init_lowres(self, g, plane):
+        outs = [np.zeros(g.plane_size_lowres, np.uint8) for _ in range(4)]
+        self.lib.xo_frame_init_lowres(C.byref(g), _ptr(plane, u8p, g.origin), *[_ptr(o, u8p, g.origin_lowres) for o in outs])
+        return outs
+
+    def me_search_fpel(self, g, fenc, fref, integral, mi):
+        out = MeOut()
+        self.lib.xo_me_search_fpel(C.byref(g), _ptr(fenc, u8p, g.origin), _ptr(fref, u8p, g.origin),
+                                   _ptr(integral, u16p, g.origin) if integral is not None else None, C.byref(mi), C.byref(out))
+        return out
+
+    def me_search_subpel(self, g, fenc, planes4, integral, mi, subme, mbcmp_satd):
+        out = MeOut()
+        arr = (u8p * 4)(*[_ptr(p, u8p, g.origin) for p in planes4])
+        self.lib.xo_me_search_subpel(C.byref(g), _ptr(fenc, u8p, g.origin), arr,
+                                     _ptr(integral, u16p, g.origin) if integral is not None else None, C.byref(mi),
+                                     subme, mbcmp_satd, C.byref(out))
+        return out
+
+
+_cache = {}
+
+
+def port():
+    if "port" not in _cache:
+        _cache["port"] = Oracle(PORT_SO)
+    return _cache["port"]
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    if "ref" not in _cache:
+        _cache["ref"] = Oracle(REF_SO)
+    return _cache["ref"]
+
+
+def mv_limits_fpel(g, mb_x, mb_y, mv_range=512):
+    """h->mb.mv_{min,max}_{spel,fpel} for a progressive, single-thread encode (S/encoder/analyse.c:258-304)."""
+    fr = 4 * mv_range
+    clip = lambda v: max(-fr, min(fr - 1, v))
+    mn = [4 * (-16 * mb_x - 24), 4 * (-16 * mb_y - 24)]
+    mx = [4 * (16 * (g.mb_width - mb_x - 1) + 24), 4 * (16 * (g.mb_height - mb_y - 1) + 24)]
+    min_spel = [clip(mn[0]), max(mn[1], max(4 * (-512 + 8), -fr))]
+    min_spel[1] = min(min_spel[1], fr)
+    max_spel = [clip(mx[0]), clip(mx[1])]
+    min_fpel = [(min_spel[0] >> 2) + 5, (min_spel[1] >> 2) + 5]
+    max_fpel = [(max_spel[0] >> 2) - 5, (max_spel[1] >> 2) - 5]
+    return min_fpel, max_fpel, min_spel, max_spel
