@@ -1,0 +1,148 @@
+/* x264_cuda.h — C ABI of the B200 (sm_100a) back-end for the data-parallel core of x264 (core build 66,
+ * snapshot 20090216-2245; S/ = the reference tree).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Two layers:
+ *  1. frame-batched entry points  x264_cuda_*      — the performance path.  Each one replaces a loop the
+ *     reference runs per macroblock / per row with one (or a few) kernel launches over a whole frame.
+ *  2. plugin-table fillers        x264_*_init_cuda — declared in x264_cuda_tables.h; they fill the reference's
+ *     x264_pixel/mc/dct/quant function tables so the library is a drop-in behind *_init(cpu).
+ *
+ * Error convention (S/encoder/encoder.c:634-645, S/x264.c:759-762): functions return 0 on success, -1 on
+ * failure; x264_cuda_error() gives the message a caller would pass to x264_log(h, X264_LOG_ERROR, ...).
+ * There is NO CPU fallback: without a usable CUDA device every entry point fails.
+ *
+ * Threading (S/common/common.h:50, S/encoder/encoder.c:780): one x264_cuda_t per x264_t thread context; a
+ * context owns one CUDA stream and is not re-entrant; different contexts may be used concurrently.
+ */
+#ifndef X264_CUDA_H
+#define X264_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X264_CUDA_API __attribute__((visibility("default")))
+
+typedef struct x264_cuda_t x264_cuda_t;             /* device context */
+typedef struct x264_cuda_frame_t x264_cuda_frame_t; /* device mirror of the planes of one x264_frame_t */
+
+/* partition ids == enum in S/common/pixel.h:30-42 */
+enum { X264_CUDA_PIXEL_16x16 = 0, X264_CUDA_PIXEL_16x8, X264_CUDA_PIXEL_8x16, X264_CUDA_PIXEL_8x8,
+       X264_CUDA_PIXEL_8x4, X264_CUDA_PIXEL_4x8, X264_CUDA_PIXEL_4x4 };
+
+/* ------------------------------------------------------------------ context ------------------------ */
+/* hook: x264_encoder_open, next to x264_pixel_init..x264_quant_init (S/encoder/encoder.c:731-745) */
+X264_CUDA_API int x264_cuda_open(x264_cuda_t **ctx, int device);
+X264_CUDA_API void x264_cuda_close(x264_cuda_t *ctx);
+X264_CUDA_API const char *x264_cuda_error(const x264_cuda_t *ctx); /* ctx may be NULL: last open() error */
+/* run on a caller-provided cudaStream_t (e.g. the framework's current stream); NULL restores the own stream */
+X264_CUDA_API int x264_cuda_set_stream(x264_cuda_t *ctx, void *cuda_stream);
+X264_CUDA_API void *x264_cuda_get_stream(x264_cuda_t *ctx);
+X264_CUDA_API int x264_cuda_synchronize(x264_cuda_t *ctx);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+X264_CUDA_API long long x264_cuda_launch_count(const x264_cuda_t *ctx);
+X264_CUDA_API int x264_cuda_sm_count(const x264_cuda_t *ctx);
+
+/* ------------------------------------------------------------------ frames ------------------------- */
+/* Mirrors x264_frame_new (S/common/frame.c:29-152): a luma plane with PADH=PADV=32 borders, optionally the
+ * three half-pel planes (filtered[1..3]), the integral image(s) and the four half-resolution planes.
+ * Device layout: same padded geometry as the reference, stride rounded up to 128 bytes. */
+#define X264_CUDA_FRAME_HPEL      1 /* filtered[1..3]: i_subpel_refine > 0 (frame.c:70-77) */
+#define X264_CUDA_FRAME_INTEGRAL  2 /* me >= ESA (frame.c:99-104) */
+#define X264_CUDA_FRAME_INTEGRAL4 4 /* + 4x4 sums: b_have_sub8x8_esa */
+#define X264_CUDA_FRAME_LOWRES    8 /* b_have_lowres (frame.c:79-97) */
+
+typedef struct x264_cuda_geom_t {
+    int width, height;       /* picture size */
+    int mb_width, mb_height; /* macroblocks */
+    int stride, lines;       /* DEVICE luma stride (bytes), mod-16 lines */
+    int stride_lowres, width_lowres, lines_lowres;
+    int flags;
+} x264_cuda_geom_t;
+
+enum { X264_CUDA_PLANE_FULL = 0, X264_CUDA_PLANE_H = 1, X264_CUDA_PLANE_V = 2, X264_CUDA_PLANE_C = 3, /* filtered[0..3] */
+       X264_CUDA_PLANE_LOWRES = 4, /* +0..3: lowres[0..3] */
+       X264_CUDA_PLANE_INTEGRAL = 8, X264_CUDA_PLANE_INTEGRAL4 = 9 };
+
+X264_CUDA_API x264_cuda_frame_t *x264_cuda_frame_new(x264_cuda_t *ctx, int width, int height, int flags);
+X264_CUDA_API void x264_cuda_frame_delete(x264_cuda_frame_t *frame);
+X264_CUDA_API void x264_cuda_frame_geometry(const x264_cuda_frame_t *frame, x264_cuda_geom_t *g);
+/* device address of pixel (0,0) of a plane (NULL if the frame lacks it) — for zero-copy producers/consumers */
+X264_CUDA_API void *x264_cuda_frame_plane(const x264_cuda_frame_t *frame, int plane);
+
+/* host -> device copy of a cols x rows luma rectangle anchored at pixel (0,0); src points at pixel (0,0) of
+ * the host plane (e.g. x264_frame_t.plane[0]).  No border handling. */
+X264_CUDA_API int x264_cuda_frame_upload(x264_cuda_t *ctx, x264_cuda_frame_t *frame, const uint8_t *src, int src_stride,
+                                         int cols, int rows);
+/* the same from a device-resident source (pitch-linear) */
+X264_CUDA_API int x264_cuda_frame_upload_dev(x264_cuda_t *ctx, x264_cuda_frame_t *frame, const void *dsrc, int src_stride,
+                                             int cols, int rows);
+/* device -> host copy of a whole padded plane: dst points at the host buffer start (row -32, col -32);
+ * elem size 1 (pixel planes) or 2 (integral).  dst_stride in elements. */
+X264_CUDA_API int x264_cuda_frame_download(x264_cuda_t *ctx, const x264_cuda_frame_t *frame, int plane, void *dst,
+                                           int dst_stride);
+
+/* ≡ x264_frame_expand_border_mod16 + x264_frame_expand_border, luma (S/common/frame.c:304-331, :240-267) */
+X264_CUDA_API int x264_cuda_frame_expand_border(x264_cuda_t *ctx, x264_cuda_frame_t *frame);
+/* ≡ x264_frame_filter(h, frame, 0, 1) + x264_frame_expand_border_filtered(h, frame, 0, 1): the three half-pel
+ * planes and the integral image(s) of a whole (border-expanded) frame (S/common/mc.c:404-463,
+ * S/common/frame.c:269-295).  Hook: x264_fdec_filter_row, S/encoder/encoder.c:1016-1023. */
+X264_CUDA_API int x264_cuda_frame_filter(x264_cuda_t *ctx, x264_cuda_frame_t *frame);
+/* ≡ x264_frame_init_lowres pixel work (S/common/mc.c:306-321 + frame.c:297-302). Hook: encoder.c:1418. */
+X264_CUDA_API int x264_cuda_frame_init_lowres(x264_cuda_t *ctx, x264_cuda_frame_t *frame);
+
+/* ------------------------------------------------------------------ MV cost tables ------------------ */
+/* Upload the HOST-computed lambda*bits table of one qp: p_cost_mv as built by x264_mb_analyse_load_costs
+ * (S/encoder/analyse.c:182-203), `table` = the malloc base, 4*4*2048+1 int16 entries (centre at +2*4*2048).
+ * Float-derived on the host — never recomputed on the device. */
+X264_CUDA_API int x264_cuda_set_cost_mv(x264_cuda_t *ctx, int qp, const int16_t *table);
+/* host-side mirror of that table builder for standalone use (tests, bench): fills table[4*4*2048+1] */
+X264_CUDA_API void x264_cuda_host_cost_mv(int qp, int16_t *table);
+X264_CUDA_API int x264_cuda_host_lambda(int qp);
+
+/* ------------------------------------------------------------------ motion search ------------------- */
+/* One job == one x264_me_search_ref() call (S/encoder/me.c:156-631) up to and including the ESA/TESA loop,
+ * for i_subpel_refine < 3 (full-pel predictor stage, me.c:207-229).  Jobs are independent; the reference's
+ * sequential neighbour-predictor order lives in how the caller derives mvp/mvc. */
+#define X264_CUDA_ME_MAX_MVC 12
+#define X264_CUDA_ME_SEEDED 1 /* skip the predictor stage: (seed_mv, seed_cost) are bmx,bmy,bcost at me.c:229 */
+#define X264_CUDA_ME_TESA   2 /* TESA candidate thresholds + final fpelcmp pass (me.c:491-578) */
+#define X264_CUDA_ME_FPEL_SATD 4 /* fpelcmp is SATD (mbcmp_init, S/encoder/encoder.c:608-618) */
+typedef struct x264_cuda_me_job_t {
+    int16_t bx, by;              /* block position in luma pixels */
+    uint8_t i_pixel;             /* X264_CUDA_PIXEL_* */
+    uint8_t qp;                  /* h->mb.i_qp: selects the cost table */
+    uint8_t i_mvc;               /* number of entries used in mvc[] */
+    uint8_t flags;               /* X264_CUDA_ME_* */
+    int16_t mvp[2];              /* m->mvp (qpel) */
+    int16_t mv_min_fpel[2];      /* h->mb.mv_min_fpel */
+    int16_t mv_max_fpel[2];      /* h->mb.mv_max_fpel */
+    int16_t seed_mv[2];          /* only with X264_CUDA_ME_SEEDED */
+    int32_t seed_cost;
+    int16_t mvc[X264_CUDA_ME_MAX_MVC][2]; /* extra predictors (qpel) */
+} x264_cuda_me_job_t;            /* 76 bytes */
+
+typedef struct x264_cuda_me_result_t {
+    int16_t bmx, bmy;            /* full-pel winner at me.c:601 */
+    int32_t bcost;
+    int16_t seed_mx, seed_my;    /* bmx,bmy,bcost entering the ESA loop (me.c:229) */
+    int32_t seed_cost;
+} x264_cuda_me_result_t;         /* 16 bytes */
+
+/* host arrays in, host arrays out (H2D of jobs, launch, D2H of results, stream-synchronised on return) */
+X264_CUDA_API int x264_cuda_me_search(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                      int me_range, const x264_cuda_me_job_t *jobs, int n_jobs,
+                                      x264_cuda_me_result_t *results);
+/* device arrays in/out, asynchronous on the context's stream */
+X264_CUDA_API int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                          int me_range, const void *d_jobs, int n_jobs, void *d_results);
+/* m->mv / m->cost / m->cost_mv from a result, i.e. me.c:603-630 for i_subpel_refine < 2 (host arithmetic) */
+X264_CUDA_API void x264_cuda_me_finish(const x264_cuda_me_job_t *job, const x264_cuda_me_result_t *res,
+                                       const int16_t *cost_table, int mv_max_spel_y, int16_t mv[2], int *cost, int *cost_mv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

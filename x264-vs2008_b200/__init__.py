@@ -1,0 +1,181 @@
+"""x264-vs2008_b200 — Python face of the B200 back-end (ctypes over lib/libx264_cuda.so, the C ABI of
+include/x264_cuda.h).  Used by tests/ and bench.py; the product itself is the shared library.
+
+No fallback of any kind: if the library or a CUDA device is missing, calls raise."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libx264_cuda.so")
+
+PADH = PADV = 32
+FRAME_HPEL, FRAME_INTEGRAL, FRAME_INTEGRAL4, FRAME_LOWRES = 1, 2, 4, 8
+PLANE_FULL, PLANE_H, PLANE_V, PLANE_C, PLANE_LOWRES, PLANE_INTEGRAL, PLANE_INTEGRAL4 = 0, 1, 2, 3, 4, 8, 9
+ME_SEEDED, ME_TESA, ME_FPEL_SATD = 1, 2, 4
+ME_MAX_MVC = 12
+
+
+class Geom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "mb_width", "mb_height", "stride", "lines",
+                                       "stride_lowres", "width_lowres", "lines_lowres", "flags")]
+
+
+# numpy mirrors of x264_cuda_me_job_t / x264_cuda_me_result_t (include/x264_cuda.h)
+ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1"), ("i_mvc", "u1"), ("flags", "u1"),
+                   ("mvp", "<i2", (2,)), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
+                   ("seed_mv", "<i2", (2,)), ("seed_cost", "<i4"), ("mvc", "<i2", (ME_MAX_MVC, 2))], align=True)
+ME_RESULT = np.dtype([("bmx", "<i2"), ("bmy", "<i2"), ("bcost", "<i4"), ("seed_mx", "<i2"), ("seed_my", "<i2"),
+                      ("seed_cost", "<i4")], align=True)
+assert ME_JOB.itemsize == 76 and ME_RESULT.itemsize == 16
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libx264_cuda.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, ip = C.c_void_p, C.c_int
+        L.x264_cuda_open.argtypes = [C.POINTER(vp), ip]
+        L.x264_cuda_close.argtypes = [vp]
+        L.x264_cuda_error.argtypes = [vp]
+        L.x264_cuda_error.restype = C.c_char_p
+        L.x264_cuda_set_stream.argtypes = [vp, vp]
+        L.x264_cuda_get_stream.argtypes = [vp]
+        L.x264_cuda_get_stream.restype = vp
+        L.x264_cuda_synchronize.argtypes = [vp]
+        L.x264_cuda_launch_count.argtypes = [vp]
+        L.x264_cuda_launch_count.restype = C.c_longlong
+        L.x264_cuda_sm_count.argtypes = [vp]
+        L.x264_cuda_frame_new.argtypes = [vp, ip, ip, ip]
+        L.x264_cuda_frame_new.restype = vp
+        L.x264_cuda_frame_delete.argtypes = [vp]
+        L.x264_cuda_frame_geometry.argtypes = [vp, C.POINTER(Geom)]
+        L.x264_cuda_frame_plane.argtypes = [vp, ip]
+        L.x264_cuda_frame_plane.restype = vp
+        L.x264_cuda_frame_upload.argtypes = [vp, vp, vp, ip, ip, ip]
+        L.x264_cuda_frame_upload_dev.argtypes = [vp, vp, vp, ip, ip, ip]
+        L.x264_cuda_frame_download.argtypes = [vp, vp, ip, vp, ip]
+        for n in ("x264_cuda_frame_expand_border", "x264_cuda_frame_filter", "x264_cuda_frame_init_lowres"):
+            if hasattr(L, n):
+                getattr(L, n).argtypes = [vp, vp]
+        L.x264_cuda_set_cost_mv.argtypes = [vp, ip, vp]
+        L.x264_cuda_host_cost_mv.argtypes = [ip, vp]
+        L.x264_cuda_host_lambda.argtypes = [ip]
+        L.x264_cuda_me_search.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_me_search_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        _lib = L
+    return _lib
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def host_cost_mv(qp):
+    t = np.zeros(4 * 4 * 2048 + 1, np.int16)
+    lib().x264_cuda_host_cost_mv(qp, t.ctypes.data)
+    return t
+
+
+class Frame:
+    def __init__(self, ctx, width, height, flags):
+        self.ctx = ctx
+        self.h = lib().x264_cuda_frame_new(ctx.h, width, height, flags)
+        if not self.h:
+            raise CudaError(ctx.error())
+        self.g = Geom()
+        lib().x264_cuda_frame_geometry(self.h, C.byref(self.g))
+
+    def close(self):
+        if self.h:
+            lib().x264_cuda_frame_delete(self.h)
+            self.h = None
+
+    def plane_ptr(self, plane):
+        return lib().x264_cuda_frame_plane(self.h, plane)
+
+    def upload(self, pic, cols=None, rows=None):
+        """pic: 2-D uint8 numpy array whose [0,0] is pixel (0,0) (host memory)"""
+        assert pic.dtype == np.uint8 and pic.strides[1] == 1
+        rows = pic.shape[0] if rows is None else rows
+        cols = pic.shape[1] if cols is None else cols
+        self.ctx.check(lib().x264_cuda_frame_upload(self.ctx.h, self.h, pic.ctypes.data, pic.strides[0], cols, rows))
+
+    def upload_dev(self, dptr, stride, cols, rows):
+        self.ctx.check(lib().x264_cuda_frame_upload_dev(self.ctx.h, self.h, dptr, stride, cols, rows))
+
+    def expand_border(self):
+        self.ctx.check(lib().x264_cuda_frame_expand_border(self.ctx.h, self.h))
+
+    def filter(self):
+        self.ctx.check(lib().x264_cuda_frame_filter(self.ctx.h, self.h))
+
+    def init_lowres(self):
+        self.ctx.check(lib().x264_cuda_frame_init_lowres(self.ctx.h, self.h))
+
+    def download(self, plane):
+        """whole padded plane as a 2-D array (rows -32.., cols -32..)"""
+        g = self.g
+        lowres = PLANE_LOWRES <= plane < PLANE_LOWRES + 4
+        lines = g.lines_lowres if lowres else g.lines
+        w = (g.width_lowres if lowres else g.mb_width * 16) + 2 * PADH
+        out = np.zeros((lines + 2 * PADV, w), np.uint16 if plane >= PLANE_INTEGRAL else np.uint8)
+        self.ctx.check(lib().x264_cuda_frame_download(self.ctx.h, self.h, plane, out.ctypes.data, w))
+        return out
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        if lib().x264_cuda_open(C.byref(self.h), device) != 0:
+            raise CudaError(lib().x264_cuda_error(None).decode())
+        self._qps = set()
+
+    def close(self):
+        if self.h:
+            lib().x264_cuda_close(self.h)
+            self.h = C.c_void_p()
+
+    def error(self):
+        return lib().x264_cuda_error(self.h).decode()
+
+    def check(self, rc):
+        if rc != 0:
+            raise CudaError(self.error())
+
+    def set_stream(self, s):
+        self.check(lib().x264_cuda_set_stream(self.h, s))
+
+    def synchronize(self):
+        self.check(lib().x264_cuda_synchronize(self.h))
+
+    def launches(self):
+        return lib().x264_cuda_launch_count(self.h)
+
+    def sm_count(self):
+        return lib().x264_cuda_sm_count(self.h)
+
+    def frame(self, width, height, flags=0):
+        return Frame(self, width, height, flags)
+
+    def set_cost_mv(self, qp, table=None):
+        t = host_cost_mv(qp) if table is None else np.ascontiguousarray(table, np.int16)
+        self.check(lib().x264_cuda_set_cost_mv(self.h, qp, t.ctypes.data))
+        self._qps.add(qp)
+
+    def me_search(self, fenc, fref, me_range, jobs):
+        """jobs: numpy array of ME_JOB (host) -> numpy array of ME_RESULT"""
+        jobs = np.ascontiguousarray(jobs, ME_JOB)
+        for qp in np.unique(jobs["qp"]):
+            if int(qp) not in self._qps:
+                self.set_cost_mv(int(qp))
+        res = np.zeros(len(jobs), ME_RESULT)
+        self.check(lib().x264_cuda_me_search(self.h, fenc.h, fref.h, me_range, jobs.ctypes.data, len(jobs), res.ctypes.data))
+        return res
+
+    def me_search_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
+        self.check(lib().x264_cuda_me_search_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

@@ -1,0 +1,57 @@
+// common.cuh — internal declarations shared by the sm_100a translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/x264_cuda.h"
+
+#define PADH 32
+#define PADV 32
+#define COST_MAX (1 << 28)
+
+struct x264_cuda_t {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;          // the stream every launch goes to
+    long long launches;
+    char err[256];
+    int16_t *d_cost_mv[52];       // device copies of p_cost_mv (base pointers, 4*4*2048+1 entries)
+    void *d_cost_ptrs;            // device array of the 52 pointers above
+    int cost_ptrs_dirty;
+    // staging for the host-pointer entry points
+    void *d_stage; size_t d_stage_size;
+    void *h_stage; size_t h_stage_size; // pinned
+};
+
+struct x264_cuda_frame_t {
+    x264_cuda_t *ctx;
+    x264_cuda_geom_t g;
+    size_t plane_size;            // stride*(lines+2*PADV)
+    size_t plane_size_lowres;
+    uint8_t *buf;                 // 1 or 4 luma planes, contiguous (frame.c:66-77)
+    uint8_t *plane[4];            // pixel (0,0) of filtered[0..3]
+    uint8_t *buf_lowres;
+    uint8_t *lowres[4];
+    uint16_t *buf_integral;
+    uint16_t *integral;           // element (0,0) of the 8x8-sum plane; the 4x4 plane follows
+};
+
+int x264_cuda_fail(x264_cuda_t *ctx, const char *what, cudaError_t e);
+int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes);
+int x264_cuda_cost_tables(x264_cuda_t *ctx, const int16_t *const **d_ptrs); // device array of 52 table pointers
+
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return x264_cuda_fail((ctx), #call, e_); } while (0)
+#define LAUNCH_CHECK(ctx, name) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); \
+    if (e_ != cudaSuccess) return x264_cuda_fail((ctx), name, e_); } while (0)
+
+// ---- device helpers ----
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc)
+{
+    uint32_t r; // VABSDIFF4.U8.ACC : sum of |a.b[i]-b.b[i]| + acc, one ALU-pipe instruction on sm_100a
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(acc));
+    return r;
+}
+__device__ __forceinline__ int clip3i(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int clip_u8(int v) { return min(max(v, 0), 255); }

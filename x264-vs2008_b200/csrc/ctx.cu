@@ -1,0 +1,232 @@
+// ctx.cu — context, device frames, host<->device plumbing of the x264_cuda C ABI (include/x264_cuda.h).
+#include "common.cuh"
+#include <cmath>
+#include <cstdlib>
+
+static char g_open_error[256] = "";
+
+int x264_cuda_fail(x264_cuda_t *ctx, const char *what, cudaError_t e)
+{
+    char *dst = ctx ? ctx->err : g_open_error;
+    snprintf(dst, 256, "x264_cuda: %s failed: %s", what, cudaGetErrorString(e));
+    return -1;
+}
+
+extern "C" const char *x264_cuda_error(const x264_cuda_t *ctx) { return ctx ? ctx->err : g_open_error; }
+
+extern "C" int x264_cuda_open(x264_cuda_t **pctx, int device)
+{
+    *pctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_open_error, 256, "x264_cuda: no CUDA device (%s); this back-end has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+        return -1;
+    }
+    if (device < 0 || device >= n) {
+        snprintf(g_open_error, 256, "x264_cuda: device %d out of range (0..%d)", device, n - 1);
+        return -1;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return x264_cuda_fail(nullptr, "cudaSetDevice", e);
+    if (prop.major != 10) {
+        snprintf(g_open_error, 256, "x264_cuda: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                 prop.major, prop.minor);
+        return -1;
+    }
+    x264_cuda_t *ctx = (x264_cuda_t *)calloc(1, sizeof(x264_cuda_t));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        free(ctx);
+        return x264_cuda_fail(nullptr, "cudaStreamCreate", e);
+    }
+    ctx->stream = ctx->own_stream;
+    *pctx = ctx;
+    return 0;
+}
+
+extern "C" void x264_cuda_close(x264_cuda_t *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 52; i++) cudaFree(ctx->d_cost_mv[i]);
+    cudaFree(ctx->d_cost_ptrs);
+    cudaFree(ctx->d_stage);
+    cudaFreeHost(ctx->h_stage);
+    cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+extern "C" int x264_cuda_set_stream(x264_cuda_t *ctx, void *s)
+{
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return 0;
+}
+extern "C" void *x264_cuda_get_stream(x264_cuda_t *ctx) { return (void *)ctx->stream; }
+extern "C" int x264_cuda_synchronize(x264_cuda_t *ctx)
+{
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" long long x264_cuda_launch_count(const x264_cuda_t *ctx) { return ctx->launches; }
+extern "C" int x264_cuda_sm_count(const x264_cuda_t *ctx) { return ctx->sm_count; }
+
+int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes)
+{
+    if (dev_bytes > ctx->d_stage_size) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_stage);
+        ctx->d_stage = nullptr; ctx->d_stage_size = 0;
+        size_t sz = dev_bytes + dev_bytes / 2;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_stage, sz));
+        ctx->d_stage_size = sz;
+    }
+    if (host_bytes > ctx->h_stage_size) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_size = 0;
+        size_t sz = host_bytes + host_bytes / 2;
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->h_stage, sz));
+        ctx->h_stage_size = sz;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ frames
+static inline int align_up(int x, int a) { return (x + a - 1) & ~(a - 1); }
+
+extern "C" x264_cuda_frame_t *x264_cuda_frame_new(x264_cuda_t *ctx, int width, int height, int flags)
+{
+    if (width <= 0 || height <= 0) {
+        snprintf(ctx->err, 256, "x264_cuda: invalid frame size %dx%d", width, height);
+        return nullptr;
+    }
+    cudaSetDevice(ctx->device);
+    x264_cuda_frame_t *f = (x264_cuda_frame_t *)calloc(1, sizeof(*f));
+    f->ctx = ctx;
+    x264_cuda_geom_t &g = f->g;
+    g.width = width; g.height = height;
+    g.mb_width = (width + 15) / 16; g.mb_height = (height + 15) / 16;
+    g.lines = g.mb_height * 16;
+    g.stride = align_up(g.mb_width * 16 + 2 * PADH, 128);
+    g.width_lowres = g.mb_width * 8;
+    g.lines_lowres = g.lines / 2;
+    g.stride_lowres = align_up(g.width_lowres + 2 * PADH, 128);
+    g.flags = flags;
+    f->plane_size = (size_t)g.stride * (g.lines + 2 * PADV);
+    f->plane_size_lowres = (size_t)g.stride_lowres * (g.lines_lowres + 2 * PADV);
+    int nplanes = (flags & X264_CUDA_FRAME_HPEL) ? 4 : 1;
+    // +256 slack: kernels read whole aligned words/vectors that may straddle the last row's end
+    cudaError_t e = cudaMalloc(&f->buf, nplanes * f->plane_size + 256);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->buf, 0, nplanes * f->plane_size + 256, ctx->stream);
+    for (int i = 0; i < nplanes && e == cudaSuccess; i++)
+        f->plane[i] = f->buf + i * f->plane_size + (size_t)g.stride * PADV + PADH;
+    if (e == cudaSuccess && (flags & X264_CUDA_FRAME_LOWRES)) {
+        e = cudaMalloc(&f->buf_lowres, 4 * f->plane_size_lowres + 256);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->buf_lowres, 0, 4 * f->plane_size_lowres + 256, ctx->stream);
+        for (int i = 0; i < 4; i++)
+            f->lowres[i] = f->buf_lowres + i * f->plane_size_lowres + (size_t)g.stride_lowres * PADV + PADH;
+    }
+    if (e == cudaSuccess && (flags & (X264_CUDA_FRAME_INTEGRAL | X264_CUDA_FRAME_INTEGRAL4))) {
+        size_t n = f->plane_size * ((flags & X264_CUDA_FRAME_INTEGRAL4) ? 2 : 1);
+        e = cudaMalloc(&f->buf_integral, n * sizeof(uint16_t) + 256);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->buf_integral, 0, n * sizeof(uint16_t) + 256, ctx->stream);
+        f->integral = f->buf_integral + (size_t)g.stride * PADV + PADH;
+    }
+    if (e != cudaSuccess) {
+        x264_cuda_fail(ctx, "frame allocation", e);
+        x264_cuda_frame_delete(f);
+        return nullptr;
+    }
+    return f;
+}
+
+extern "C" void x264_cuda_frame_delete(x264_cuda_frame_t *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->buf);
+    cudaFree(f->buf_lowres);
+    cudaFree(f->buf_integral);
+    free(f);
+}
+
+extern "C" void x264_cuda_frame_geometry(const x264_cuda_frame_t *f, x264_cuda_geom_t *g) { *g = f->g; }
+
+extern "C" void *x264_cuda_frame_plane(const x264_cuda_frame_t *f, int plane)
+{
+    if (plane >= 0 && plane < 4) return f->plane[plane];
+    if (plane >= X264_CUDA_PLANE_LOWRES && plane < X264_CUDA_PLANE_LOWRES + 4) return f->lowres[plane - X264_CUDA_PLANE_LOWRES];
+    if (plane == X264_CUDA_PLANE_INTEGRAL) return f->integral;
+    if (plane == X264_CUDA_PLANE_INTEGRAL4)
+        return (f->g.flags & X264_CUDA_FRAME_INTEGRAL4) ? f->integral + f->plane_size : nullptr;
+    return nullptr;
+}
+
+extern "C" int x264_cuda_frame_upload(x264_cuda_t *ctx, x264_cuda_frame_t *f, const uint8_t *src, int src_stride,
+                                      int cols, int rows)
+{
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, src, src_stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+extern "C" int x264_cuda_frame_upload_dev(x264_cuda_t *ctx, x264_cuda_frame_t *f, const void *dsrc, int src_stride,
+                                          int cols, int rows)
+{
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, dsrc, src_stride, cols, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int x264_cuda_frame_download(x264_cuda_t *ctx, const x264_cuda_frame_t *f, int plane, void *dst, int dst_stride)
+{
+    const x264_cuda_geom_t &g = f->g;
+    const void *p00 = x264_cuda_frame_plane(f, plane);
+    if (!p00) {
+        snprintf(ctx->err, 256, "x264_cuda: frame has no plane %d", plane);
+        return -1;
+    }
+    bool lowres = plane >= X264_CUDA_PLANE_LOWRES && plane < X264_CUDA_PLANE_LOWRES + 4;
+    bool integ = plane >= X264_CUDA_PLANE_INTEGRAL;
+    int es = integ ? 2 : 1;
+    int stride = lowres ? g.stride_lowres : g.stride;
+    int lines = lowres ? g.lines_lowres : g.lines;
+    int w = lowres ? g.width_lowres : g.mb_width * 16;
+    const uint8_t *src = (const uint8_t *)p00 - ((size_t)stride * PADV + PADH) * es;
+    int cols = w + 2 * PADH;
+    if (cols > dst_stride) cols = dst_stride;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)dst_stride * es, src, (size_t)stride * es, (size_t)cols * es, lines + 2 * PADV,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ MV cost tables
+extern "C" int x264_cuda_set_cost_mv(x264_cuda_t *ctx, int qp, const int16_t *table)
+{
+    if (qp < 0 || qp > 51) { snprintf(ctx->err, 256, "x264_cuda: qp %d out of range", qp); return -1; }
+    const size_t n = (4 * 4 * 2048 + 1) * sizeof(int16_t);
+    if (!ctx->d_cost_mv[qp]) CUDA_TRY(ctx, cudaMalloc(&ctx->d_cost_mv[qp], n + 16));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cost_mv[qp], table, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // `table` may be pageable and short-lived
+    ctx->cost_ptrs_dirty = 1;
+    return 0;
+}
+
+int x264_cuda_cost_tables(x264_cuda_t *ctx, const int16_t *const **d_ptrs)
+{
+    if (!ctx->d_cost_ptrs) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_cost_ptrs, 52 * sizeof(void *)));
+        ctx->cost_ptrs_dirty = 1;
+    }
+    if (ctx->cost_ptrs_dirty) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cost_ptrs, ctx->d_cost_mv, 52 * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->cost_ptrs_dirty = 0;
+    }
+    *d_ptrs = (const int16_t *const *)ctx->d_cost_ptrs;
+    return 0;
+}
