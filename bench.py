@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark (BASELINE.json: "1080p ESA ME Gcand/s ...").
+
+Workload (BASELINE.json configs[1]): full-resolution exhaustive motion search (--me esa --merange 16) of one
+1080p P-frame against one reference frame: for each of the 8160 macroblocks the nine partition searches the
+reference's analyse stage can issue (1x16x16, 2x16x8, 2x8x16, 4x8x8), each an independent
+x264_me_search_ref job with its own predictor (mvp) and candidate predictors (mvc).  One *step* = one frame pair.
+Synthetic seeded content; inputs cycle through a ring of frame pairs larger than L2 (126 MB).
+
+  value : Gcand/s with frames, jobs and results resident in HBM (kernel time only, CUDA events)
+  e2e   : the same through the host-buffer C ABI: H2D of both pictures and the job list, border replication,
+          search, D2H of the results — everything a caller of x264_cuda_* pays per frame
+  cand  : one (partition block, integer MV) evaluation of the reference's search space: rows*width per job with
+          width=(max_x-min_x+3)&~3 (S/encoder/me.c:452-457), counted exactly from each job's window.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref = unmodified x264 C compiled in place;
+falls back to the oracle port) of the same jobs on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, ME_RANGE, QP = 1920, 1080, 16, 26
+RING_PAIRS = 32  # 64 padded planes x 2.36 MB = 151 MB > 126 MB L2
+
+
+def build_jobs(pkg, mb_w, mb_h, seed=2024, motion=(5, 3)):
+    """nine searches per macroblock with seeded predictors around the true global motion (qpel units)"""
+    import xo_api as X
+    rng = np.random.default_rng(seed)
+    parts = [(0, 0, 0), (1, 0, 0), (1, 0, 8), (2, 0, 0), (2, 8, 0), (3, 0, 0), (3, 8, 0), (3, 0, 8), (3, 8, 8)]
+    n = mb_w * mb_h * len(parts)
+    jobs = np.zeros(n, pkg.ME_JOB)
+    g = type("G", (), dict(mb_width=mb_w, mb_height=mb_h))
+    k = 0
+    for mby in range(mb_h):
+        for mbx in range(mb_w):
+            mnf, mxf, _, _ = X.mv_limits_fpel(g, mbx, mby)
+            for ip, ox, oy in parts:
+                j = jobs[k]
+                j["bx"], j["by"], j["i_pixel"], j["qp"] = mbx * 16 + ox, mby * 16 + oy, ip, QP
+                j["mv_min_fpel"], j["mv_max_fpel"] = mnf, mxf
+                k += 1
+    jit = lambda s, size: rng.integers(-s, s + 1, size)
+    jobs["mvp"][:, 0] = -4 * motion[0] + jit(6, n)
+    jobs["mvp"][:, 1] = -4 * motion[1] + jit(6, n)
+    jobs["i_mvc"] = 3
+    for c in range(3):
+        jobs["mvc"][:, c, 0] = -4 * motion[0] + jit(10, n)
+        jobs["mvc"][:, c, 1] = -4 * motion[1] + jit(10, n)
+    return jobs
+
+
+def count_cands(jobs, res, me_range):
+    """exact size of each job's search space from its seed (window centre) and MV limits"""
+    bmx, bmy = res["seed_mx"].astype(np.int64), res["seed_my"].astype(np.int64)
+    mn, mx = jobs["mv_min_fpel"].astype(np.int64), jobs["mv_max_fpel"].astype(np.int64)
+    min_x, max_x = np.maximum(bmx - me_range, mn[:, 0]), np.minimum(bmx + me_range, mx[:, 0])
+    min_y, max_y = np.maximum(bmy - me_range, mn[:, 1]), np.minimum(bmy + me_range, mx[:, 1])
+    width = (max_x - min_x + 3) & ~3
+    cands = width * (max_y - min_y + 1)
+    blk = np.array([64, 32, 32, 16, 8, 8, 4])[jobs["i_pixel"]]  # 4-byte SAD ops per candidate
+    return int(cands.sum()), int((cands * blk).sum())
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------- CPU arms
+def _cpu_worker(args):
+    """times a slice of jobs through the oracle API (reference harness if built, else the port) in one process"""
+    lo, hi, use_ref, reps = args
+    import xo_api as X
+    import __graft_entry__ as ge
+    pkg = ge.load_pkg()
+    from x264_vs2008_b200 import synth
+    o = X.ref() if use_ref else X.port()
+    g = o.geometry(W, H)
+    clip = synth.Clip(W, H, seed=1)
+    pe, pr = o.plane_from_picture(g, clip.luma(1)), o.plane_from_picture(g, clip.luma(0))
+    _, _, _, integ = o.frame_filter(g, pr, 0)
+    jobs = build_jobs(pkg, g.mb_width, g.mb_height)[lo:hi]
+    arr = (X.MeIn * len(jobs))()
+    _, _, mns, mxs = None, None, None, None
+    for i, j in enumerate(jobs):
+        m = arr[i]
+        m.me_method, m.me_range, m.qp, m.i_pixel = X.ME_ESA, ME_RANGE, int(j["qp"]), int(j["i_pixel"])
+        m.bx, m.by, m.i_mvc = int(j["bx"]), int(j["by"]), int(j["i_mvc"])
+        for k in range(2):
+            m.mv_min_fpel[k], m.mv_max_fpel[k], m.mvp[k] = int(j["mv_min_fpel"][k]), int(j["mv_max_fpel"][k]), int(j["mvp"][k])
+            m.mv_max_spel[k] = 1 << 20
+        for c in range(m.i_mvc):
+            m.mvc[c][0], m.mvc[c][1] = int(j["mvc"][c][0]), int(j["mvc"][c][1])
+    o.me_search_fpel_batch(g, pe, pr, integ, arr[:64] if len(jobs) > 64 else arr)  # warm tables/caches
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        outs = o.me_search_fpel_batch(g, pe, pr, integ, arr)
+    dt = time.perf_counter() - t0
+    res = np.zeros(len(jobs), pkg.ME_RESULT)
+    if use_ref:  # the harness hides the seed: recompute it with the port to count the search space
+        outs = X.port().me_search_fpel_batch(g, pe, pr, integ, arr)
+    for i, r in enumerate(outs):
+        res[i]["seed_mx"], res[i]["seed_my"] = r.seed_mx, r.seed_my
+    cands, _ = count_cands(jobs, res, ME_RANGE)
+    return cands * reps, dt
+
+
+def cpu_rate(n_procs, jobs_per_proc, reps, stride_start=0):
+    """(cands/s aggregate, kind, cores, sample description)"""
+    import xo_api as X
+    use_ref = X.have_ref()
+    total_jobs = (W // 16) * ((H + 15) // 16) * 9
+    slices = []
+    for p in range(n_procs):
+        lo = (stride_start + p * jobs_per_proc) % max(1, total_jobs - jobs_per_proc)
+        slices.append((lo, lo + jobs_per_proc, use_ref, reps))
+    if n_procs == 1:
+        outs = [_cpu_worker(slices[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(n_procs) as pool:
+            outs = pool.map(_cpu_worker, slices)
+    cands = sum(o[0] for o in outs)
+    wall = max(o[1] for o in outs)
+    kind = "reference" if use_ref else "port"
+    sample = "%d jobs x %d passes per process (ESA merange 16, 1080p, same job list as the GPU arm)" % (jobs_per_proc, reps)
+    return cands / wall, kind, n_procs, sample, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for s in range(args.warmup + args.steps):
+        rate, kind, n, sample, wall = cpu_rate(cores, 9 * 120 * 16, 1, stride_start=s * 997)
+        if s >= args.warmup:
+            vals.append((rate, wall))
+    rate = float(np.mean([v[0] for v in vals]))
+    ms = float(np.mean([v[1] for v in vals])) * 1e3
+    line = {"impl": "reference", "metric": "1080p ESA ME Gcand/s", "value": rate / 1e9, "unit": "Gcand/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "1080p --me esa --merange 16, 9 partition searches per MB (bounded sample per step)",
+                       "me_range": ME_RANGE, "qp": QP},
+            "cpu_baseline": {"value": rate / 1e9, "unit": "Gcand/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": rate / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_pkg()
+    from x264_vs2008_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pkg.Context(local)
+    stream = torch.cuda.Stream()  # a real (non-legacy-default) stream: events and kernels share it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_cost_mv(QP)
+
+    # ---- inputs: a ring of frame pairs (each rank gets its own seeded content: frames shard across GPUs)
+    clip = synth.Clip(W, H, seed=1 + rank)
+    n_frames = 2 * RING_PAIRS
+    host_pics = torch.empty((n_frames, H, W), dtype=torch.uint8).pin_memory()
+    base = [clip.luma(i) for i in range(8)]
+    for i in range(n_frames):  # 8 generated frames, re-used with whole-pel shifts to fill the ring cheaply
+        host_pics[i].copy_(torch.from_numpy(np.roll(base[i % 8], (i // 8) * 3, axis=1)))
+    frames = [ctx.frame(W, H, 0) for _ in range(n_frames)]
+    for f, pic in zip(frames, host_pics):
+        f.upload(pic.numpy()); f.expand_border()
+    g = frames[0].g
+    jobs = build_jobs(pkg, g.mb_width, g.mb_height)
+    n_jobs = len(jobs)
+    h_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).pin_memory()
+    d_jobs = h_jobs.cuda()
+    d_res = torch.zeros(n_jobs * pkg.ME_RESULT.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        p = i % RING_PAIRS
+        ctx.me_search_dev(frames[2 * p + 1], frames[2 * p], ME_RANGE, d_jobs.data_ptr(), n_jobs, d_res.data_ptr())
+
+    # search-space size (identical for every pair up to the seed positions; count it on pair 0 .. RING_PAIRS-1 exactly)
+    cands_per_pair, sadops_per_pair = [], []
+    for p in range(RING_PAIRS):
+        step_resident(p)
+        res = d_res.cpu().numpy().view(pkg.ME_RESULT)
+        c, s = count_cands(jobs, res, ME_RANGE)
+        cands_per_pair.append(c); sadops_per_pair.append(s)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- integer-pipe peak under load clocks (roofline denominator for the SAD kernel)
+    int_peak = ctx.measure_int_pipe()
+
+    # ---- value: resident inputs, kernel only
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ctx.launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        evs[i][0].record(stream)
+        step_resident(args.warmup + i)
+        evs[i][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = ctx.launches() - l0
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(kernel_ms))
+    cands = sum(cands_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
+    sadops = sum(sadops_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    fe, fr = ctx.frame(W, H, 0), ctx.frame(W, H, 0)
+    h_res = torch.zeros(n_jobs * pkg.ME_RESULT.itemsize, dtype=torch.uint8).pin_memory()
+
+    def step_e2e(i):
+        p = i % RING_PAIRS
+        fe.upload(host_pics[2 * p + 1].numpy()); fe.expand_border()
+        fr.upload(host_pics[2 * p].numpy()); fr.expand_border()
+        pkg.lib().x264_cuda_me_search(ctx.h, fe.h, fr.h, ME_RANGE, h_jobs.data_ptr(), n_jobs, h_res.data_ptr())
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    h2d = 2 * W * H + n_jobs * pkg.ME_JOB.itemsize
+    d2h = n_jobs * pkg.ME_RESULT.itemsize
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([cands, sadops], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cands_all, sadops_all = float(c[0]), float(c[1])
+    else:
+        cands_all, sadops_all = float(cands), float(sadops)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        per_launch_ms = float(sum(kernel_ms)) / max(1, len(kernel_ms))
+        # algorithmic bytes of one launch: both padded luma planes read once + job list + results
+        alg_bytes = 2 * g.stride * (g.lines + 64) + n_jobs * (pkg.ME_JOB.itemsize + pkg.ME_RESULT.itemsize)
+        hbm_ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        int_ach = (sadops / args.steps) / (per_launch_ms * 1e-3)
+        line = {
+            "metric": "1080p ESA ME Gcand/s", "value": cands_all / (total_ms * 1e-3) / 1e9, "unit": "Gcand/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "1080p --me esa --merange 16: 8160 MB x 9 partition searches (73440 x264_me_search_ref jobs) per frame pair",
+                       "width": W, "height": H, "me_range": ME_RANGE, "qp": QP, "jobs_per_step": n_jobs,
+                       "cands_per_step": cands // args.steps,
+                       "l2": "inputs cycle through a %d-pair ring of padded planes (%.0f MB) > 126 MB L2" % (RING_PAIRS, n_frames * g.stride * (g.lines + 64) / 1e6)},
+            "e2e": {"value": cands_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                         "traffic": None, "kernel": "me_search_kernel", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "note": "this kernel is integer-ALU-pipe bound by design (64 4-byte SADs per 16x16 candidate, ~1 B of HBM traffic per 10k ops); see int_pipe"},
+            "int_pipe": {"bound": "int_pipe", "op": "VABSDIFF4.U8.ACC (4-byte SAD-accumulate)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
+                         "unit": "Tsad4/s", "frac": int_ach / int_peak, "peak_source": "x264_cuda_measure_int_pipe, measured in this run"},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            rate, kind, cores, sample, _ = cpu_rate(1, 9 * 120 * 8, 2)
+            line["cpu_baseline"] = {"value": rate / 1e9, "unit": "Gcand/s", "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    for f in frames:
+        f.close()
+    fe.close(); fr.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

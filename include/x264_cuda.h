@@ -44,6 +44,8 @@ X264_CUDA_API int x264_cuda_synchronize(x264_cuda_t *ctx);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 X264_CUDA_API long long x264_cuda_launch_count(const x264_cuda_t *ctx);
 X264_CUDA_API int x264_cuda_sm_count(const x264_cuda_t *ctx);
+/* roofline denominator for the SAD kernels: measured whole-GPU rate of VABSDIFF4.U8.ACC (thread-ops / second) */
+X264_CUDA_API int x264_cuda_measure_int_pipe(x264_cuda_t *ctx, double *sad4_per_sec);
 
 /* ------------------------------------------------------------------ frames ------------------------- */
 /* Mirrors x264_frame_new (S/common/frame.c:29-152): a luma plane with PADH=PADV=32 borders, optionally the
@@ -141,6 +143,37 @@ X264_CUDA_API int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_fram
 /* m->mv / m->cost / m->cost_mv from a result, i.e. me.c:603-630 for i_subpel_refine < 2 (host arithmetic) */
 X264_CUDA_API void x264_cuda_me_finish(const x264_cuda_me_job_t *job, const x264_cuda_me_result_t *res,
                                        const int16_t *cost_table, int mv_max_spel_y, int16_t mv[2], int *cost, int *cost_mv);
+
+/* ------------------------------------------------------------------ macroblock-batched motion search - */
+/* One job == ALL inter partition searches of one macroblock against one reference: 16x16, 2x16x8, 2x8x16,
+ * 4x8x8 (the x264_me_search_ref calls of x264_mb_analyse_inter_p16x16/p8x8/p16x8/p8x16, S/encoder/analyse.c:
+ * 1077-1371), each with its own mvp/mvc, hence its own seed and its own +-me_range window.  The kernel walks the
+ * union of the windows once, evaluates the four 8x8 SADs of the macroblock per candidate position and derives
+ * all nine partition costs from them (PIXEL_SAD_C is a plain sum: S/common/pixel.c:40-56), so nine searches
+ * cost about one.  Results are identical to nine x264_cuda_me_search jobs. */
+#define X264_CUDA_ME_MB_PARTS 9 /* 0: 16x16 | 1,2: 16x8 top,bottom | 3,4: 8x16 left,right | 5..8: 8x8 TL,TR,BL,BR */
+#define X264_CUDA_ME_MB_MVC 4
+typedef struct x264_cuda_me_mb_job_t {
+    int16_t mb_x, mb_y;              /* macroblock coordinates */
+    uint16_t part_mask;              /* bit p: search partition p */
+    uint8_t qp, flags;               /* flags: X264_CUDA_ME_SEEDED */
+    int16_t mv_min_fpel[2], mv_max_fpel[2];
+    uint8_t i_mvc[X264_CUDA_ME_MB_PARTS];
+    uint8_t reserved[3];
+    int16_t mvp[X264_CUDA_ME_MB_PARTS][2];
+    int16_t mvc[X264_CUDA_ME_MB_PARTS][X264_CUDA_ME_MB_MVC][2];
+    int16_t seed_mv[X264_CUDA_ME_MB_PARTS][2]; /* only with X264_CUDA_ME_SEEDED */
+    int32_t seed_cost[X264_CUDA_ME_MB_PARTS];
+} x264_cuda_me_mb_job_t;             /* 280 bytes */
+typedef struct x264_cuda_me_mb_result_t {
+    x264_cuda_me_result_t part[X264_CUDA_ME_MB_PARTS];
+} x264_cuda_me_mb_result_t;          /* 144 bytes */
+
+X264_CUDA_API int x264_cuda_me_search_mb(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                         int me_range, const x264_cuda_me_mb_job_t *jobs, int n_jobs,
+                                         x264_cuda_me_mb_result_t *results);
+X264_CUDA_API int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                             int me_range, const void *d_jobs, int n_jobs, void *d_results);
 
 #ifdef __cplusplus
 }

@@ -260,6 +260,12 @@ void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint
 {
     run_search(g, fenc_plane, fref_planes, integral, in, subme, mbcmp_satd, out);
 }
+void xo_me_search_fpel_batch(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
+                             const uint16_t *integral, const xo_me_in *in, int n, xo_me_out *out)
+{
+    for (int i = 0; i < n; i++)
+        xo_me_search_fpel(g, fenc_plane, fref_plane, integral, in + i, out + i);
+}
 
 /* ------------------------------------------------------------------------------------------------ */
 void xo_sub4x4_dct(int16_t dct[16], const uint8_t *p1, const uint8_t *p2) { tables(); g_dctf.sub4x4_dct((void *)dct, (uint8_t *)p1, (uint8_t *)p2); }

@@ -102,6 +102,9 @@ typedef struct {
 } xo_me_out;
 void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
                        const uint16_t *integral, const xo_me_in *in, xo_me_out *out);
+/* n independent searches in one call (C loop; used to time the CPU path without per-call binding overhead) */
+void xo_me_search_fpel_batch(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
+                             const uint16_t *integral, const xo_me_in *in, int n, xo_me_out *out);
 /* the same search followed by refine_subpel (me.c:622-628): subme = h->mb.i_subpel_refine used by the
  * search, mbcmp_satd = whether mbcmp is SATD (user subme>1).  fref_planes = {full, h, v, c}. */
 void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],

@@ -352,3 +352,10 @@ void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint
     me_sub sub = { subme, mbcmp_satd };
     me_core(g, fenc_plane, fref_planes, integral, in, &sub, out);
 }
+
+void xo_me_search_fpel_batch(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,
+                             const uint16_t *integral, const xo_me_in *in, int n, xo_me_out *out)
+{
+    for (int i = 0; i < n; i++)
+        xo_me_search_fpel(g, fenc_plane, fref_plane, integral, in + i, out + i);
+}

@@ -62,3 +62,63 @@ def oracle_me(o, g, fenc, fref, integral, mis):
         r = o.me_search_fpel(g, fenc, fref, integral, mi)
         out.append((r.bmx, r.bmy, r.bcost))
     return out
+
+
+def make_mb_jobs(pkg, g, seed, n, qp, mvp_spread=40, mvc_spread=60, centre=(0, 0), mask_random=True):
+    """n seeded macroblock jobs (nine partition searches each) -> (ME_MB_JOB array)"""
+    rng = np.random.default_rng(seed)
+    jobs = np.zeros(n, pkg.ME_MB_JOB)
+    for i in range(n):
+        j = jobs[i]
+        mbx, mby = int(rng.integers(0, g.mb_width)), int(rng.integers(0, g.mb_height))
+        mnf, mxf, _, _ = X.mv_limits_fpel(g, mbx, mby)
+        j["mb_x"], j["mb_y"] = mbx, mby
+        j["qp"] = qp if isinstance(qp, int) else int(qp[int(rng.integers(0, len(qp)))])
+        j["part_mask"] = int(rng.integers(1, 512)) if (mask_random and i % 4 == 0) else 511
+        j["mv_min_fpel"], j["mv_max_fpel"] = mnf, mxf
+        base = [int(rng.integers(-mvp_spread, mvp_spread + 1)) + centre[0], int(rng.integers(-mvp_spread, mvp_spread + 1)) + centre[1]]
+        for p in range(pkg.ME_MB_PARTS):
+            # partitions of one MB have correlated predictors (as in the encoder) with occasional outliers
+            jit = 6 if rng.integers(0, 6) else 70
+            j["mvp"][p] = [base[0] + int(rng.integers(-jit, jit + 1)), base[1] + int(rng.integers(-jit, jit + 1))]
+            nm = int(rng.integers(0, pkg.ME_MB_MVC + 1))
+            j["i_mvc"][p] = nm
+            for k in range(nm):
+                v = [base[0] + int(rng.integers(-mvc_spread, mvc_spread + 1)), base[1] + int(rng.integers(-mvc_spread, mvc_spread + 1))]
+                if rng.integers(0, 8) == 0:
+                    v = [0, 0]
+                j["mvc"][p][k] = v
+    return jobs
+
+
+def mb_jobs_to_block_jobs(pkg, mbjobs):
+    """expand macroblock jobs into the equivalent per-block ME_JOB list (masked partitions skipped);
+    returns (ME_JOB array, list of (mb index, partition))"""
+    out, idx = [], []
+    for i, mj in enumerate(mbjobs):
+        for p, (ip, ox, oy) in enumerate(pkg.ME_MB_PART_GEOM):
+            if not (int(mj["part_mask"]) >> p) & 1:
+                continue
+            j = np.zeros((), pkg.ME_JOB)
+            j["bx"], j["by"], j["i_pixel"], j["qp"] = int(mj["mb_x"]) * 16 + ox, int(mj["mb_y"]) * 16 + oy, ip, mj["qp"]
+            j["i_mvc"] = mj["i_mvc"][p]
+            j["mvp"] = mj["mvp"][p]
+            j["mv_min_fpel"], j["mv_max_fpel"] = mj["mv_min_fpel"], mj["mv_max_fpel"]
+            j["mvc"][:pkg.ME_MB_MVC] = mj["mvc"][p]
+            out.append(j)
+            idx.append((i, p))
+    return np.array(out, pkg.ME_JOB), idx
+
+
+def block_jobs_to_mis(jobs, me_range, method=X.ME_ESA):
+    arr = (X.MeIn * len(jobs))()
+    for i, j in enumerate(jobs):
+        m = arr[i]
+        m.me_method, m.me_range, m.qp, m.i_pixel = method, me_range, int(j["qp"]), int(j["i_pixel"])
+        m.bx, m.by, m.i_mvc = int(j["bx"]), int(j["by"]), int(j["i_mvc"])
+        for k in range(2):
+            m.mv_min_fpel[k], m.mv_max_fpel[k], m.mvp[k] = int(j["mv_min_fpel"][k]), int(j["mv_max_fpel"][k]), int(j["mvp"][k])
+            m.mv_max_spel[k] = 1 << 20
+        for c in range(m.i_mvc):
+            m.mvc[c][0], m.mvc[c][1] = int(j["mvc"][c][0]), int(j["mvc"][c][1])
+    return arr

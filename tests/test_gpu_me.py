@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 import xo_api as X
-from helpers import make_me_jobs, oracle_me
+from helpers import make_me_jobs, oracle_me, make_mb_jobs, mb_jobs_to_block_jobs, block_jobs_to_mis
 
 pytestmark = pytest.mark.gpu
 
@@ -112,4 +112,31 @@ def test_esa_1080p_full_frame_property(pkg, ctx, port):
             mi.mv_min_fpel[k], mi.mv_max_fpel[k] = int(jobs[i]["mv_min_fpel"][k]), int(jobs[i]["mv_max_fpel"][k])
         o = port.me_search_fpel(g, pe, pr, None, mi)
         assert (int(res[i]["bmx"]), int(res[i]["bmy"]), int(res[i]["bcost"])) == (o.bmx, o.bmy, o.bcost)
+    fenc.close(); fref.close()
+
+
+@pytest.mark.parametrize("w,h,me_range", [(352, 288, 16), (352, 288, 8), (352, 288, 24), (128, 96, 16), (100, 70, 16), (640, 360, 40)])
+def test_mb_search_matches_oracle_and_block_search(pkg, ctx, port, w, h, me_range):
+    """macroblock-batched search (nine partitions, union window) == nine independent x264_me_search_ref"""
+    g, fenc, fref, pe, pr = _setup(pkg, ctx, port, w, h, seed=3 * w + me_range)
+    mbjobs = make_mb_jobs(pkg, g, seed=me_range, n=250, qp=(12, 26, 38))
+    res = ctx.me_search_mb(fenc, fref, me_range, mbjobs)
+    bjobs, idx = mb_jobs_to_block_jobs(pkg, mbjobs)
+    outs = port.me_search_fpel_batch(g, pe, pr, None, block_jobs_to_mis(bjobs, me_range))
+    bres = ctx.me_search(fenc, fref, me_range, bjobs)
+    bad = []
+    for k, (i, p) in enumerate(idx):
+        r = res[i]["part"][p]
+        got = (int(r["bmx"]), int(r["bmy"]), int(r["bcost"]), int(r["seed_mx"]), int(r["seed_my"]), int(r["seed_cost"]))
+        o = outs[k]
+        want = (o.bmx, o.bmy, o.bcost, o.seed_mx, o.seed_my, o.seed_cost)
+        blk = bres[k]
+        if got != want or got[:3] != (int(blk["bmx"]), int(blk["bmy"]), int(blk["bcost"])):
+            bad.append((i, p, got, want))
+    assert not bad, (len(bad), bad[:5])
+    # masked-out partitions are flagged
+    for i, mj in enumerate(mbjobs):
+        for p in range(9):
+            if not (int(mj["part_mask"]) >> p) & 1:
+                assert int(res[i]["part"][p]["bcost"]) == -1
     fenc.close(); fref.close()

@@ -72,6 +72,7 @@ class Oracle:
         L.xo_mc_luma.argtypes = [u8p, C.c_int, C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.xo_mc_chroma.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.xo_me_search_fpel.argtypes = [C.POINTER(Geom), u8p, u8p, u16p, C.POINTER(MeIn), C.POINTER(MeOut)]
+        L.xo_me_search_fpel_batch.argtypes = [C.POINTER(Geom), u8p, u8p, u16p, C.POINTER(MeIn), C.c_int, C.POINTER(MeOut)]
         L.xo_me_search_subpel.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), u16p, C.POINTER(MeIn), C.c_int,
                                           C.c_int, C.POINTER(MeOut)]
         for n in ("xo_sub4x4_dct", "xo_sub8x8_dct8"):
@@ -140,6 +141,15 @@ class Oracle:
         self.lib.xo_me_search_fpel(C.byref(g), _ptr(fenc, u8p, g.origin), _ptr(fref, u8p, g.origin),
                                    _ptr(integral, u16p, g.origin) if integral is not None else None, C.byref(mi), C.byref(out))
         return out
+
+    def me_search_fpel_batch(self, g, fenc, fref, integral, mis):
+        """mis: ctypes array (MeIn * n) or list of MeIn"""
+        n = len(mis)
+        arr = mis if isinstance(mis, C.Array) else (MeIn * n)(*mis)
+        outs = (MeOut * n)()
+        self.lib.xo_me_search_fpel_batch(C.byref(g), _ptr(fenc, u8p, g.origin), _ptr(fref, u8p, g.origin),
+                                         _ptr(integral, u16p, g.origin) if integral is not None else None, arr, n, outs)
+        return outs
 
     def me_search_subpel(self, g, fenc, planes4, integral, mi, subme, mbcmp_satd):
         out = MeOut()

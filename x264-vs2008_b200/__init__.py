@@ -27,7 +27,16 @@ ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1")
                    ("seed_mv", "<i2", (2,)), ("seed_cost", "<i4"), ("mvc", "<i2", (ME_MAX_MVC, 2))], align=True)
 ME_RESULT = np.dtype([("bmx", "<i2"), ("bmy", "<i2"), ("bcost", "<i4"), ("seed_mx", "<i2"), ("seed_my", "<i2"),
                       ("seed_cost", "<i4")], align=True)
+ME_MB_PARTS, ME_MB_MVC = 9, 4
+# partition p of a macroblock job: (i_pixel, x offset, y offset)
+ME_MB_PART_GEOM = [(0, 0, 0), (1, 0, 0), (1, 0, 8), (2, 0, 0), (2, 8, 0), (3, 0, 0), (3, 8, 0), (3, 0, 8), (3, 8, 8)]
+ME_MB_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("part_mask", "<u2"), ("qp", "u1"), ("flags", "u1"),
+                      ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)), ("i_mvc", "u1", (ME_MB_PARTS,)),
+                      ("reserved", "u1", (3,)), ("mvp", "<i2", (ME_MB_PARTS, 2)), ("mvc", "<i2", (ME_MB_PARTS, ME_MB_MVC, 2)),
+                      ("seed_mv", "<i2", (ME_MB_PARTS, 2)), ("seed_cost", "<i4", (ME_MB_PARTS,))], align=True)
+ME_MB_RESULT = np.dtype([("part", ME_RESULT, (ME_MB_PARTS,))], align=True)
 assert ME_JOB.itemsize == 76 and ME_RESULT.itemsize == 16
+assert ME_MB_JOB.itemsize == 280 and ME_MB_RESULT.itemsize == 144
 
 _lib = None
 
@@ -50,6 +59,7 @@ def lib():
         L.x264_cuda_launch_count.argtypes = [vp]
         L.x264_cuda_launch_count.restype = C.c_longlong
         L.x264_cuda_sm_count.argtypes = [vp]
+        L.x264_cuda_measure_int_pipe.argtypes = [vp, C.POINTER(C.c_double)]
         L.x264_cuda_frame_new.argtypes = [vp, ip, ip, ip]
         L.x264_cuda_frame_new.restype = vp
         L.x264_cuda_frame_delete.argtypes = [vp]
@@ -67,6 +77,8 @@ def lib():
         L.x264_cuda_host_lambda.argtypes = [ip]
         L.x264_cuda_me_search.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_search_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_me_search_mb.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_me_search_mb_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         _lib = L
     return _lib
 
@@ -156,6 +168,11 @@ class Context:
     def launches(self):
         return lib().x264_cuda_launch_count(self.h)
 
+    def measure_int_pipe(self):
+        v = C.c_double()
+        self.check(lib().x264_cuda_measure_int_pipe(self.h, C.byref(v)))
+        return v.value
+
     def sm_count(self):
         return lib().x264_cuda_sm_count(self.h)
 
@@ -176,6 +193,19 @@ class Context:
         res = np.zeros(len(jobs), ME_RESULT)
         self.check(lib().x264_cuda_me_search(self.h, fenc.h, fref.h, me_range, jobs.ctypes.data, len(jobs), res.ctypes.data))
         return res
+
+    def me_search_mb(self, fenc, fref, me_range, jobs):
+        """jobs: numpy array of ME_MB_JOB (host) -> numpy array of ME_MB_RESULT"""
+        jobs = np.ascontiguousarray(jobs, ME_MB_JOB)
+        for qp in np.unique(jobs["qp"]):
+            if int(qp) not in self._qps:
+                self.set_cost_mv(int(qp))
+        res = np.zeros(len(jobs), ME_MB_RESULT)
+        self.check(lib().x264_cuda_me_search_mb(self.h, fenc.h, fref.h, me_range, jobs.ctypes.data, len(jobs), res.ctypes.data))
+        return res
+
+    def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
+        self.check(lib().x264_cuda_me_search_mb_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))
 
     def me_search_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
         self.check(lib().x264_cuda_me_search_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

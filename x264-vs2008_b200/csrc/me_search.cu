@@ -18,72 +18,152 @@ namespace {
 
 struct Geo { const uint8_t *fenc; const uint8_t *fref; int stride; };
 
+#define ME_WARPS_PER_BLOCK 4
+#define ME_ROW_CHUNK 64 // rows of partial SADs kept in shared memory between the two column passes of 16-wide blocks
+
 template <int NW>
-__device__ __forceinline__ void load_row(uint32_t (&dst)[NW], const uint32_t *p, int sh)
+__device__ __forceinline__ void load_row(uint32_t (&dst)[NW], const uint8_t *p, int sh)
 {
     uint32_t w[NW + 1];
 #pragma unroll
-    for (int i = 0; i <= NW; i++) w[i] = __ldg(p + i);
+    for (int i = 0; i <= NW; i++) w[i] = __ldg((const uint32_t *)p + i);
 #pragma unroll
     for (int i = 0; i < NW; i++) dst[i] = __funnelshift_r(w[i], w[i + 1], sh);
 }
 
-// SAD of the register block F (BH x NW words) against the block at byte address `a` (any alignment)
-template <int BW, int BH>
-__device__ __forceinline__ int sad_block_at(const uint32_t (&F)[BH][BW / 4], const uint8_t *a, int stride)
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// One lane walks its candidate column top-down over `nrows` rows.  mode 0: complete block (cost -> best key);
+// mode 1: left half of a 16-wide block (SAD -> partial[]); mode 2: right half (adds partial[], cost -> best key).
+// The ring R keeps the BH reference rows under the block; slot s holds the row r with r % BH == s, which is
+// static after unrolling by BH.  key = cost<<12 | row: min() == strict '<' with the earlier row winning ties.
+template <int NW, int BH>
+__device__ __noinline__ void scan_column(const uint8_t *fe, const uint8_t *p, int sh, int stride, int nrows, int mode,
+                                         int cost_x, const int16_t *cmy_row, uint16_t *partial, int row0, uint32_t &best_key)
 {
-    constexpr int NW = BW / 4;
-    const int sh = ((uintptr_t)a & 3) * 8;
-    const uint32_t *p = (const uint32_t *)((uintptr_t)a & ~(uintptr_t)3);
+    uint32_t F[BH][NW], R[BH][NW];
+#pragma unroll
+    for (int y = 0; y < BH; y++)
+#pragma unroll
+        for (int w = 0; w < NW; w++) F[y][w] = __ldg((const uint32_t *)(fe + (size_t)y * stride) + w);
+#pragma unroll
+    for (int y = 0; y < BH - 1; y++) load_row<NW>(R[y], p + (size_t)y * stride, sh);
+    int cy = cmy_row[0];
+    for (int base = 0; base < nrows; base += BH) {
+#pragma unroll
+        for (int j = 0; j < BH; j++) {
+            const int r = base + j;
+            if (r >= nrows) break; // warp-uniform
+            load_row<NW>(R[(j + BH - 1) % BH], p + (size_t)(r + BH - 1) * stride, sh);
+            const int cy_next = cmy_row[4 * (r + 1)]; // one row ahead: hides the L1 latency (the table has slack)
+            uint32_t acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+            for (int y = 0; y < BH; y++)
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    const int k = (y * NW + w) & 3;
+                    acc[k] = sad4_acc(F[y][w], R[(j + y) % BH][w], acc[k]);
+                }
+            uint32_t sad = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            if (mode == 1) {
+                partial[r * 32] = (uint16_t)sad;
+            } else {
+                if (mode == 2) sad += partial[r * 32];
+                const uint32_t key = ((sad + cost_x + cy) << 12) | (uint32_t)(row0 + r);
+                best_key = min(best_key, key);
+            }
+            cy = cy_next;
+        }
+    }
+}
+
+// SAD of the BH x (4*NW*npass) fenc block against the reference block at byte address `a`
+template <int NW, int BH>
+__device__ __noinline__ int sad_block_at(const uint8_t *fe, const uint8_t *a, int stride, int npass)
+{
     uint32_t acc0 = 0, acc1 = 0;
+    for (int h = 0; h < npass; h++, fe += 4 * NW, a += 4 * NW) {
+        const int sh = ((uintptr_t)a & 3) * 8;
+        const uint8_t *p = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
 #pragma unroll
-    for (int y = 0; y < BH; y++) {
-        uint32_t r[NW];
-        load_row<NW>(r, (const uint32_t *)((const uint8_t *)p + (size_t)y * stride), sh);
+        for (int y = 0; y < BH; y++) {
+            uint32_t r[NW];
+            load_row<NW>(r, p + (size_t)y * stride, sh);
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-            if ((y + w) & 1) acc1 = sad4_acc(F[y][w], r[w], acc1);
-            else acc0 = sad4_acc(F[y][w], r[w], acc0);
+            for (int w = 0; w < NW; w++) {
+                const uint32_t f = __ldg((const uint32_t *)(fe + (size_t)y * stride) + w);
+                if ((y + w) & 1) acc1 = sad4_acc(f, r[w], acc1);
+                else acc0 = sad4_acc(f, r[w], acc0);
+            }
         }
     }
     return (int)(acc0 + acc1);
 }
 
-__device__ __forceinline__ int tab_at(const int16_t *tab, int i)
+// NW words per column pass; 16-wide blocks (npass == 2) take two 8-wide passes, which halves the registers and
+// lets 16x16/8x16 (and 16x8/8x8) share one instantiation — the hot loops of a frame's job mix fit the I-cache.
+// variant -> (NW, BH) instantiation shared by several partition shapes
+__device__ __forceinline__ void scan_dispatch(int variant, const uint8_t *fe, const uint8_t *p, int sh, int stride, int nrows,
+                                              int mode, int cost_x, const int16_t *cmy_row, uint16_t *partial, int row0,
+                                              uint32_t &key)
 {
-    // p_cost_mv is defined for |i| <= 2*4*2048 (analyse.c:196-203); x264's mv range keeps indices inside
-    return tab[max(-2 * 4 * 2048, min(2 * 4 * 2048, i))];
+    switch (variant) {
+    case 0: scan_column<2, 16>(fe, p, sh, stride, nrows, mode, cost_x, cmy_row, partial, row0, key); break;
+    case 1: scan_column<2, 8>(fe, p, sh, stride, nrows, mode, cost_x, cmy_row, partial, row0, key); break;
+    case 2: scan_column<2, 4>(fe, p, sh, stride, nrows, mode, cost_x, cmy_row, partial, row0, key); break;
+    case 3: scan_column<1, 8>(fe, p, sh, stride, nrows, mode, cost_x, cmy_row, partial, row0, key); break;
+    default: scan_column<1, 4>(fe, p, sh, stride, nrows, mode, cost_x, cmy_row, partial, row0, key); break;
+    }
+}
+__device__ __forceinline__ int sad_dispatch(int variant, const uint8_t *fe, const uint8_t *a, int stride, int npass)
+{
+    switch (variant) {
+    case 0: return sad_block_at<2, 16>(fe, a, stride, npass);
+    case 1: return sad_block_at<2, 8>(fe, a, stride, npass);
+    case 2: return sad_block_at<2, 4>(fe, a, stride, npass);
+    case 3: return sad_block_at<1, 8>(fe, a, stride, npass);
+    default: return sad_block_at<1, 4>(fe, a, stride, npass);
+    }
 }
 
-template <int BW, int BH>
 __device__ void search_job(const Geo &geo, const x264_cuda_me_job_t &job, const int16_t *tab, int me_range,
-                           x264_cuda_me_result_t *res, int lane)
+                           x264_cuda_me_result_t *res, int lane, uint16_t *partial)
 {
-    constexpr int NW = BW / 4;
+    // i_pixel -> {variant, passes}: 16x16 8x16 share <2,16>, 16x8 8x8 share <2,8>
+    const int ip = min((int)job.i_pixel, 6);
+    const int variant = ip == X264_CUDA_PIXEL_16x16 || ip == X264_CUDA_PIXEL_8x16 ? 0
+                      : ip == X264_CUDA_PIXEL_16x8 || ip == X264_CUDA_PIXEL_8x8 ? 1
+                      : ip == X264_CUDA_PIXEL_8x4 ? 2 : ip == X264_CUDA_PIXEL_4x8 ? 3 : 4;
+    const int npass = ip <= X264_CUDA_PIXEL_16x8 ? 2 : 1;
+    const int NW = variant <= 2 ? 2 : 1;
+    const int BH = variant == 0 ? 16 : (variant == 1 || variant == 3) ? 8 : 4;
+    const int BW = 4 * NW * npass;
     const int stride = geo.stride;
     const int16_t *cmx = tab - job.mvp[0]; // p_cost_mvx, me.c:179-180
     const int16_t *cmy = tab - job.mvp[1];
     const int x_min = job.mv_min_fpel[0], y_min = job.mv_min_fpel[1];
     const int x_max = job.mv_max_fpel[0], y_max = job.mv_max_fpel[1];
 
-    // ---- fenc block -> registers (uniform across the warp)
-    uint32_t F[BH][NW];
+    // every table index this job can form must stay inside p_cost_mv's +-2*4*2048 (analyse.c:196-203)
     {
-        const uint8_t *fe = geo.fenc + (size_t)job.by * stride + job.bx;
-#pragma unroll
-        for (int y = 0; y < BH; y++)
-#pragma unroll
-            for (int w = 0; w < NW; w++) F[y][w] = __ldg((const uint32_t *)(fe + (size_t)y * stride) + w);
+        const int lim = 2 * 4 * 2048 - 8;
+        const int ax = max(abs(4 * x_min - job.mvp[0]), abs(4 * x_max - job.mvp[0]));
+        const int ay = max(abs(4 * y_min - job.mvp[1]), abs(4 * y_max - job.mvp[1]));
+        if (ax > lim || ay > lim || x_min > 0 || x_max < 0 || y_min > 0 || y_max < 0) {
+            if (lane == 0) { x264_cuda_me_result_t r = { 0, 0, -1, 0, 0, -1 }; *res = r; } // rejected job
+            return;
+        }
     }
+    const uint8_t *fe = geo.fenc + (size_t)job.by * stride + job.bx;   // m->p_fenc[0] (in place, plane stride)
     const uint8_t *ref0 = geo.fref + (size_t)job.by * stride + job.bx; // m->p_fref[0]
 
     // ---- predictor stage, me.c:182-229 (i_subpel_refine < 3): lane i evaluates candidate i
     int bmx, bmy, bcost;
-    const int pmx = (clip3i(job.mvp[0], x_min * 4, x_max * 4) + 2) >> 2;
-    const int pmy = (clip3i(job.mvp[1], y_min * 4, y_max * 4) + 2) >> 2;
     if (job.flags & X264_CUDA_ME_SEEDED) {
-        bmx = job.seed_mv[0]; bmy = job.seed_mv[1]; bcost = job.seed_cost;
+        bmx = clip3i(job.seed_mv[0], x_min, x_max); bmy = clip3i(job.seed_mv[1], y_min, y_max); bcost = job.seed_cost;
     } else {
+        const int pmx = (clip3i(job.mvp[0], x_min * 4, x_max * 4) + 2) >> 2;
+        const int pmy = (clip3i(job.mvp[1], y_min * 4, y_max * 4) + 2) >> 2;
         const int n_mvc = min((int)job.i_mvc, X264_CUDA_ME_MAX_MVC);
         int cx = 0, cy = 0, valid = 0;
         if (lane == 0) { cx = pmx; cy = pmy; valid = 1; }
@@ -94,13 +174,13 @@ __device__ void search_job(const Geo &geo, const x264_cuda_me_job_t &job, const 
         } else if (lane == n_mvc + 1) { cx = 0; cy = 0; valid = 1; }
         int cost = COST_MAX + 1;
         if (valid) {
-            cost = sad_block_at<BW, BH>(F, ref0 + (ptrdiff_t)cy * stride + cx, stride);
-            if (lane != 0) cost += tab_at(cmx, cx << 2) + tab_at(cmy, cy << 2); // me.c:217: mvp cost is removed again
+            cost = sad_dispatch(variant, fe, ref0 + (ptrdiff_t)cy * stride + cx, stride, npass);
+            if (lane != 0) cost += cmx[cx << 2] + cmy[cy << 2]; // me.c:217: the mvp's own MV cost is removed again
         }
         // sequential strict '<' over the list == min over (cost, list index).  Skipping "same as current best"
         // candidates (me.c:222) never changes the outcome: such a candidate cannot be strictly better.
-        unsigned key = __reduce_min_sync(0xffffffffu, (unsigned)cost);
-        unsigned who = __reduce_min_sync(0xffffffffu, (unsigned)cost == key ? (unsigned)lane : 0xffu);
+        const unsigned key = __reduce_min_sync(0xffffffffu, (unsigned)cost);
+        const unsigned who = __reduce_min_sync(0xffffffffu, (unsigned)cost == key ? (unsigned)lane : 0xffu);
         bcost = (int)key;
         bmx = __shfl_sync(0xffffffffu, cx, who);
         bmy = __shfl_sync(0xffffffffu, cy, who);
@@ -113,53 +193,47 @@ __device__ void search_job(const Geo &geo, const x264_cuda_me_job_t &job, const 
     const int width = (max_x - min_x + 3) & ~3;
     const int rows = max_y - min_y + 1;
 
-    unsigned long long best_key = ~0ull;
+    unsigned long long best = ~0ull; // (cost<<12|row) << 12 | col
     for (int c0 = 0; c0 < width; c0 += 32) {
         const int col = c0 + lane;
         const bool active = col < width;
         const int mx = min_x + (active ? col : 0);
-        const uint8_t *a = ref0 + (ptrdiff_t)min_y * stride + mx;
-        const int sh = ((uintptr_t)a & 3) * 8;
-        const uint8_t *p = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
-        const int cost_x = tab_at(cmx, mx << 2);
-        uint32_t R[BH][NW]; // ring: slot s holds reference row r with r % BH == s
-#pragma unroll
-        for (int y = 0; y < BH - 1; y++) load_row<NW>(R[y], (const uint32_t *)(p + (size_t)y * stride), sh);
-        int lane_best = 0x7fffffff, lane_my = 0;
-        for (int base = 0; base < rows; base += BH) {
-#pragma unroll
-            for (int j = 0; j < BH; j++) {
-                const int my_idx = base + j;
-                if (my_idx >= rows) break; // warp-uniform
-                load_row<NW>(R[(j + BH - 1) % BH], (const uint32_t *)(p + (size_t)(my_idx + BH - 1) * stride), sh);
-                uint32_t acc[4] = { 0, 0, 0, 0 };
-#pragma unroll
-                for (int y = 0; y < BH; y++)
-#pragma unroll
-                    for (int w = 0; w < NW; w++) {
-                        const int k = (y * NW + w) & 3;
-                        acc[k] = sad4_acc(F[y][w], R[(j + y) % BH][w], acc[k]);
-                    }
-                const int cost = (int)(acc[0] + acc[1] + acc[2] + acc[3]) + cost_x + tab_at(cmy, (min_y + my_idx) << 2);
-                if (cost < lane_best) { lane_best = cost; lane_my = my_idx; }
+        const int cost_x = cmx[mx << 2];
+        for (int row0 = 0; row0 < rows; row0 += ME_ROW_CHUNK) {
+            const int nrows = min(ME_ROW_CHUNK, rows - row0);
+            const uint8_t *a = ref0 + (ptrdiff_t)(min_y + row0) * stride + mx;
+            // pull the warp's whole window tile into L1 up front: later row loads are L1 hits consumed a full
+            // row-step after issue.  The tile is (nrows+BH-1) rows x (32+BW+3) bytes, i.e. at most 2 lines a row.
+            {
+                const uint8_t *t0 = ref0 + (ptrdiff_t)(min_y + row0) * stride + min_x + c0;
+                for (int r = lane; r < nrows + BH - 1; r += 32) {
+                    prefetch_l1(t0 + (size_t)r * stride);
+                    prefetch_l1(t0 + (size_t)r * stride + 32 + BW);
+                }
             }
-        }
-        if (active) {
-            unsigned long long key = ((unsigned long long)(unsigned)lane_best << 24) | ((unsigned)lane_my << 12) | (unsigned)col;
-            best_key = min(best_key, key);
+            const int sh = ((uintptr_t)a & 3) * 8;
+            const uint8_t *p = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
+            const int16_t *cmy_row = cmy + 4 * (min_y + row0);
+            uint32_t key = 0xffffffffu;
+            if (npass == 1) {
+                scan_dispatch(variant, fe, p, sh, stride, nrows, 0, cost_x, cmy_row, partial + lane, row0, key);
+            } else {
+                scan_dispatch(variant, fe, p, sh, stride, nrows, 1, cost_x, cmy_row, partial + lane, row0, key);
+                __syncwarp();
+                scan_dispatch(variant, fe + 4 * NW, p + 4 * NW, sh, stride, nrows, 2, cost_x, cmy_row, partial + lane, row0, key);
+                __syncwarp();
+            }
+            if (active) best = min(best, ((unsigned long long)key << 12) | (unsigned)col);
         }
     }
-    // warp argmin of (cost, my, mx)
+    // warp argmin of (cost, my, mx): first candidate in raster order among the minima
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o);
-        best_key = min(best_key, other);
-    }
-    const int w_cost = (int)(best_key >> 24);
-    if (best_key != ~0ull && w_cost < bcost) {
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    const int w_cost = (int)(best >> 24);
+    if (best != ~0ull && w_cost < bcost) {
         bcost = w_cost;
-        bmy = min_y + (int)((best_key >> 12) & 0xfff);
-        bmx = min_x + (int)(best_key & 0xfff);
+        bmy = min_y + (int)((best >> 12) & 0xfff);
+        bmx = min_x + (int)(best & 0xfff);
     }
     if (lane == 0) {
         x264_cuda_me_result_t r;
@@ -169,24 +243,23 @@ __device__ void search_job(const Geo &geo, const x264_cuda_me_job_t &job, const 
     }
 }
 
-__global__ void __launch_bounds__(128) me_search_kernel(Geo geo, const x264_cuda_me_job_t *__restrict__ jobs, int n_jobs,
-                                                        const int16_t *const *__restrict__ cost_tabs, int me_range,
-                                                        x264_cuda_me_result_t *__restrict__ results)
+__global__ void __launch_bounds__(ME_WARPS_PER_BLOCK * 32, 4)
+me_search_kernel(Geo geo, const x264_cuda_me_job_t *__restrict__ jobs, int n_jobs, const int16_t *const *__restrict__ cost_tabs,
+                 int me_range, x264_cuda_me_result_t *__restrict__ results)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint16_t s_partial[ME_WARPS_PER_BLOCK][ME_ROW_CHUNK * 32];
+    __shared__ x264_cuda_me_job_t s_job[ME_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_jobs; j += warps_per_grid) {
-        const x264_cuda_me_job_t job = jobs[j];
-        const int16_t *tab = cost_tabs[job.qp] + 2 * 4 * 2048;
-        switch (job.i_pixel) {
-        case X264_CUDA_PIXEL_16x16: search_job<16, 16>(geo, job, tab, me_range, results + j, lane); break;
-        case X264_CUDA_PIXEL_16x8:  search_job<16, 8>(geo, job, tab, me_range, results + j, lane); break;
-        case X264_CUDA_PIXEL_8x16:  search_job<8, 16>(geo, job, tab, me_range, results + j, lane); break;
-        case X264_CUDA_PIXEL_8x8:   search_job<8, 8>(geo, job, tab, me_range, results + j, lane); break;
-        case X264_CUDA_PIXEL_8x4:   search_job<8, 4>(geo, job, tab, me_range, results + j, lane); break;
-        case X264_CUDA_PIXEL_4x8:   search_job<4, 8>(geo, job, tab, me_range, results + j, lane); break;
-        default:                    search_job<4, 4>(geo, job, tab, me_range, results + j, lane); break;
-        }
+        // stage the 76-byte job through shared memory (19 words, one per lane)
+        __syncwarp();
+        if (lane < (int)(sizeof(x264_cuda_me_job_t) / 4)) ((uint32_t *)&s_job[wid])[lane] = __ldg((const uint32_t *)(jobs + j) + lane);
+        __syncwarp();
+        const x264_cuda_me_job_t &job = s_job[wid];
+        const int16_t *tab = cost_tabs[job.qp > 51 ? 51 : job.qp] + 2 * 4 * 2048;
+        uint16_t *partial = s_partial[wid];
+        search_job(geo, job, tab, me_range, results + j, lane, partial);
     }
 }
 
@@ -207,7 +280,7 @@ extern "C" int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_frame_t
     const int16_t *const *d_tabs;
     if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
     Geo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
-    const int warps_per_block = 4;
+    const int warps_per_block = ME_WARPS_PER_BLOCK;
     int blocks = (n_jobs + warps_per_block - 1) / warps_per_block;
     me_search_kernel<<<blocks, warps_per_block * 32, 0, ctx->stream>>>(geo, (const x264_cuda_me_job_t *)d_jobs, n_jobs, d_tabs,
                                                                         me_range, (x264_cuda_me_result_t *)d_results);

@@ -1,0 +1,307 @@
+// me_search_mb.cu — macroblock-batched exhaustive search: the nine inter-partition ESA searches of one
+// macroblock (16x16, 2x16x8, 2x8x16, 4x8x8) in ONE pass over the union of their windows.
+//
+// ONE WARP PER MACROBLOCK.  Lane l owns candidate column x0+l of the union window and walks the rows top-down with
+// a 16-row register ring of its 16-byte reference strip (5 aligned loads + 4 funnel shifts per row).  Per candidate
+// position the warp issues the 64 VABSDIFF4.U8.ACC of the whole macroblock into four accumulators — the 8x8
+// quadrant SADs TL,TR,BL,BR — and every partition cost is a sum of those (S/common/pixel.c:40-56), plus that
+// partition's own lambda*bits(mv - mvp) (S/encoder/me.c:54-63).  A partition only accepts positions inside ITS
+// window (seed +- me_range clipped to the MV limits, width rounded up to 4: me.c:451-457); outside it the cost is
+// forced above every real cost.  Keys (cost<<12|row) make min() the reference's strict-'<' raster-order update.
+//
+// Roofline class: integer ALU pipe.  Per candidate position: 64 SAD ops + ~30 ALU ops of bookkeeping serve nine
+// (partition, mv) candidates of the reference's search space.
+#include "common.cuh"
+
+namespace {
+
+struct Geo { const uint8_t *fenc; const uint8_t *fref; int stride; };
+
+#define MB_WARPS 4
+#define MB_ROW_CHUNK 64
+#define NP X264_CUDA_ME_MB_PARTS
+#define NCAND (X264_CUDA_ME_MB_MVC + 2)
+#define INVALID_COST 0x3ffff // above any real cost (<= 65280 + 2*~2.6k), small enough that 3 of them << 12 fit 32 bits
+
+struct __align__(16) WarpSmem {
+    uint32_t F[16][4];                       // fenc macroblock, 256 B (read as uint4 rows: keep 16-byte aligned)
+    uint32_t cyt[MB_ROW_CHUNK][12];          // per row: 9 partition y-costs (+3 pad) -> three 16-byte broadcast loads
+    x264_cuda_me_mb_job_t job;               // 280 B
+    int pc_cost[NP * NCAND], pc_x[NP * NCAND], pc_y[NP * NCAND]; // predictor stage scratch
+    int seed[NP][3];                         // bmx, bmy, bcost per partition
+    int win[NP][4];                          // min_x, min_y, width, rows per partition
+};
+
+__device__ __forceinline__ void load_row16(uint32_t (&dst)[4], const uint8_t *p, int sh)
+{
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = __ldg((const uint32_t *)p + i);
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// partition geometry inside the macroblock
+__device__ __forceinline__ void part_geom(int p, int &ox, int &oy, int &bw, int &bh)
+{
+    ox = (p == 4 || p == 6 || p == 8) ? 8 : 0;
+    oy = (p == 2 || p == 7 || p == 8) ? 8 : 0;
+    bw = (p <= 2) ? 16 : 8;
+    bh = (p == 0 || p == 3 || p == 4) ? 16 : 8;
+}
+
+// plain SAD of a bw x bh block (bw in {8,16}) of fenc (from the shared copy) vs reference bytes at `a`
+__device__ int sad_part(const uint32_t (*F)[4], int ox, int oy, int bw, int bh, const uint8_t *a, int stride)
+{
+    const int sh = ((uintptr_t)a & 3) * 8;
+    const uint8_t *p = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
+    uint32_t acc = 0;
+    const int nw = bw >> 2, w0 = ox >> 2;
+    for (int y = 0; y < bh; y++) {
+        const uint32_t *row = (const uint32_t *)(p + (size_t)y * stride);
+        uint32_t lo = __ldg(row);
+        for (int w = 0; w < nw; w++) {
+            const uint32_t hi = __ldg(row + w + 1);
+            acc = sad4_acc(F[oy + y][w0 + w], __funnelshift_r(lo, hi, sh), acc);
+            lo = hi;
+        }
+    }
+    return (int)acc;
+}
+
+__global__ void __launch_bounds__(MB_WARPS * 32, 3)
+me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int n_jobs,
+                    const int16_t *const *__restrict__ cost_tabs, int me_range, x264_cuda_me_mb_result_t *__restrict__ results)
+{
+    __shared__ __align__(16) WarpSmem s_all[MB_WARPS];
+    const int lane = threadIdx.x & 31;
+    WarpSmem &S = s_all[threadIdx.x >> 5];
+    const int stride = geo.stride;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jb < n_jobs; jb += warps_per_grid) {
+        __syncwarp();
+        for (int i = lane; i < (int)(sizeof(x264_cuda_me_mb_job_t) / 4); i += 32)
+            ((uint32_t *)&S.job)[i] = __ldg((const uint32_t *)(jobs + jb) + i);
+        __syncwarp();
+        const x264_cuda_me_mb_job_t &job = S.job;
+        const int16_t *tab = cost_tabs[job.qp > 51 ? 51 : job.qp] + 2 * 4 * 2048;
+        const int x_min = job.mv_min_fpel[0], y_min = job.mv_min_fpel[1];
+        const int x_max = job.mv_max_fpel[0], y_max = job.mv_max_fpel[1];
+        const unsigned mask = job.part_mask & ((1u << NP) - 1);
+        x264_cuda_me_result_t *out = results[jb].part;
+
+        // reject jobs whose table indices could leave p_cost_mv's +-2*4*2048 (analyse.c:196-203) or with bad limits
+        int bad = x_min > 0 || x_max < 0 || y_min > 0 || y_max < 0;
+        if (lane < NP && (mask >> lane & 1)) {
+            const int lim = 2 * 4 * 2048 - 8;
+            bad |= max(abs(4 * x_min - job.mvp[lane][0]), abs(4 * x_max - job.mvp[lane][0])) > lim;
+            bad |= max(abs(4 * y_min - job.mvp[lane][1]), abs(4 * y_max - job.mvp[lane][1])) > lim;
+        }
+        if (__any_sync(0xffffffffu, bad) || !mask) {
+            if (lane < NP) { x264_cuda_me_result_t r = { 0, 0, -1, 0, 0, -1 }; out[lane] = r; }
+            continue;
+        }
+        const uint8_t *fe = geo.fenc + (size_t)job.mb_y * 16 * stride + job.mb_x * 16;
+        const uint8_t *ref0 = geo.fref + (size_t)job.mb_y * 16 * stride + job.mb_x * 16;
+        for (int i = lane; i < 64; i += 32) S.F[i >> 2][i & 3] = __ldg((const uint32_t *)(fe + (size_t)(i >> 2) * stride) + (i & 3));
+        __syncwarp();
+
+        // ---- predictor stage per partition (me.c:207-229), one (partition, candidate) per lane, two rounds
+        if (!(job.flags & X264_CUDA_ME_SEEDED)) {
+            for (int idx = lane; idx < NP * NCAND; idx += 32) {
+                const int p = idx / NCAND, c = idx % NCAND;
+                int cost = COST_MAX + 1, cx = 0, cy = 0;
+                if (mask >> p & 1) {
+                    int valid = 1;
+                    const int n_mvc = min((int)job.i_mvc[p], X264_CUDA_ME_MB_MVC);
+                    if (c == 0) {
+                        cx = (clip3i(job.mvp[p][0], x_min * 4, x_max * 4) + 2) >> 2;
+                        cy = (clip3i(job.mvp[p][1], y_min * 4, y_max * 4) + 2) >> 2;
+                    } else if (c <= X264_CUDA_ME_MB_MVC) {
+                        const int mx = (job.mvc[p][c - 1][0] + 2) >> 2, my = (job.mvc[p][c - 1][1] + 2) >> 2;
+                        valid = (c - 1 < n_mvc) && (mx | my) != 0;
+                        cx = clip3i(mx, x_min, x_max); cy = clip3i(my, y_min, y_max);
+                    }
+                    if (valid) {
+                        int ox, oy, bw, bh;
+                        part_geom(p, ox, oy, bw, bh);
+                        cost = sad_part(S.F, ox, oy, bw, bh, ref0 + (ptrdiff_t)(oy + cy) * stride + ox + cx, stride);
+                        if (c != 0) cost += tab[(cx << 2) - job.mvp[p][0]] + tab[(cy << 2) - job.mvp[p][1]];
+                    }
+                }
+                S.pc_cost[idx] = cost; S.pc_x[idx] = cx; S.pc_y[idx] = cy;
+            }
+            __syncwarp();
+            if (lane < NP) {
+                int bc = COST_MAX + 1, bx = 0, by = 0; // sequential strict '<' in candidate order
+                for (int c = 0; c < NCAND; c++) {
+                    const int v = S.pc_cost[lane * NCAND + c];
+                    if (v < bc) { bc = v; bx = S.pc_x[lane * NCAND + c]; by = S.pc_y[lane * NCAND + c]; }
+                }
+                S.seed[lane][0] = bx; S.seed[lane][1] = by; S.seed[lane][2] = bc;
+            }
+        } else if (lane < NP) {
+            S.seed[lane][0] = clip3i(job.seed_mv[lane][0], x_min, x_max);
+            S.seed[lane][1] = clip3i(job.seed_mv[lane][1], y_min, y_max);
+            S.seed[lane][2] = job.seed_cost[lane];
+        }
+        __syncwarp();
+
+        // ---- per-partition windows (me.c:451-457) and their union
+        int ux0 = 1 << 20, uy0 = 1 << 20, ux1 = -(1 << 20), uy1 = -(1 << 20);
+        if (lane < NP && (mask >> lane & 1)) {
+            const int bmx = S.seed[lane][0], bmy = S.seed[lane][1];
+            const int min_x = max(bmx - me_range, x_min), min_y = max(bmy - me_range, y_min);
+            const int max_x = min(bmx + me_range, x_max), max_y = min(bmy + me_range, y_max);
+            const int width = (max_x - min_x + 3) & ~3, rows = max_y - min_y + 1;
+            S.win[lane][0] = min_x; S.win[lane][1] = min_y; S.win[lane][2] = width; S.win[lane][3] = rows;
+            ux0 = min_x; uy0 = min_y; ux1 = min_x + width; uy1 = min_y + rows;
+        } else if (lane < NP) {
+            S.win[lane][0] = 0; S.win[lane][1] = 0; S.win[lane][2] = 0; S.win[lane][3] = 0; // empty window
+        }
+        ux0 = __reduce_min_sync(0xffffffffu, ux0); uy0 = __reduce_min_sync(0xffffffffu, uy0);
+        ux1 = __reduce_max_sync(0xffffffffu, ux1); uy1 = __reduce_max_sync(0xffffffffu, uy1);
+        __syncwarp();
+        const int uwidth = ux1 - ux0, urows = uy1 - uy0;
+
+        uint32_t best[NP], bcol[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) { best[p] = 0xffffffffu; bcol[p] = 0; }
+
+        for (int c0 = 0; c0 < uwidth; c0 += 32) {
+            const int col = c0 + lane;
+            const int mx = ux0 + min(col, uwidth - 1);
+            uint32_t cxp[NP]; // this lane's x-cost per partition, INVALID outside the partition's column range
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const int wx0 = S.win[p][0], ww = S.win[p][2];
+                const bool in = col < uwidth && mx >= wx0 && mx < wx0 + ww;
+                cxp[p] = in ? (uint32_t)tab[(mx << 2) - job.mvp[p][0]] : INVALID_COST;
+            }
+            for (int row0 = 0; row0 < urows; row0 += MB_ROW_CHUNK) {
+                const int nrows = min(MB_ROW_CHUNK, urows - row0);
+                // y-cost table of this row chunk: cyt[r][p]
+                __syncwarp();
+                for (int i = lane; i < nrows * 12; i += 32) {
+                    const int r = i / 12, p = i - r * 12;
+                    uint32_t v = INVALID_COST;
+                    if (p < NP) {
+                        const int my = uy0 + row0 + r;
+                        if (my >= S.win[p][1] && my < S.win[p][1] + S.win[p][3]) v = (uint32_t)tab[(my << 2) - job.mvp[p][1]];
+                    }
+                    S.cyt[r][p] = v;
+                }
+                // pull the window tile into L1: (nrows+15) rows x 51 bytes, at most two 128-byte lines per row
+                const uint8_t *t0 = ref0 + (ptrdiff_t)(uy0 + row0) * stride + ux0 + c0;
+                for (int r = lane; r < nrows + 15; r += 32) {
+                    prefetch_l1(t0 + (size_t)r * stride);
+                    prefetch_l1(t0 + (size_t)r * stride + 48);
+                }
+                __syncwarp();
+                const uint8_t *a = ref0 + (ptrdiff_t)(uy0 + row0) * stride + mx;
+                const int sh = ((uintptr_t)a & 3) * 8;
+                const uint8_t *pr = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
+                uint32_t R[16][4];
+#pragma unroll
+                for (int y = 0; y < 15; y++) load_row16(R[y], pr + (size_t)y * stride, sh);
+                uint32_t kb[NP]; // best key of this chunk per partition (cost<<12 | row)
+#pragma unroll
+                for (int p = 0; p < NP; p++) kb[p] = 0xffffffffu;
+                const uint4 *F4 = (const uint4 *)&S.F[0][0];
+                for (int base = 0; base < nrows; base += 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int r = base + j;
+                        if (r >= nrows) break; // warp-uniform
+                        load_row16(R[(j + 15) % 16], pr + (size_t)(r + 15) * stride, sh);
+                        const uint4 *cy4 = (const uint4 *)&S.cyt[r][0];
+                        const uint4 ca = cy4[0], cb = cy4[1], cc = cy4[2];
+                        uint32_t tl = 0, tr = 0, bl = 0, br = 0;
+#pragma unroll
+                        for (int y = 0; y < 8; y++) {
+                            const uint4 f = F4[y];
+                            tl = sad4_acc(f.x, R[(j + y) % 16][0], tl); tr = sad4_acc(f.z, R[(j + y) % 16][2], tr);
+                            tl = sad4_acc(f.y, R[(j + y) % 16][1], tl); tr = sad4_acc(f.w, R[(j + y) % 16][3], tr);
+                        }
+#pragma unroll
+                        for (int y = 8; y < 16; y++) {
+                            const uint4 f = F4[y];
+                            bl = sad4_acc(f.x, R[(j + y) % 16][0], bl); br = sad4_acc(f.z, R[(j + y) % 16][2], br);
+                            bl = sad4_acc(f.y, R[(j + y) % 16][1], bl); br = sad4_acc(f.w, R[(j + y) % 16][3], br);
+                        }
+                        const uint32_t top = tl + tr, bot = bl + br, lft = tl + bl, rgt = tr + br, all = top + bot;
+                        const uint32_t rowid = (uint32_t)(row0 + r);
+#define UPD(p, sad, cy) kb[p] = min(kb[p], (((sad) + cxp[p] + (cy)) << 12) | rowid)
+                        UPD(0, all, ca.x); UPD(1, top, ca.y); UPD(2, bot, ca.z); UPD(3, lft, ca.w); UPD(4, rgt, cb.x);
+                        UPD(5, tl, cb.y); UPD(6, tr, cb.z); UPD(7, bl, cb.w); UPD(8, br, cc.x);
+#undef UPD
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (kb[p] < best[p]) { best[p] = kb[p]; bcol[p] = (uint32_t)col; } // later chunks only win strictly
+            }
+        }
+        // ---- warp argmin per partition: min key (cost,row), then the lowest column among the lanes holding it
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
+            const uint32_t c = __reduce_min_sync(0xffffffffu, best[p] == k ? bcol[p] : 0xffffffffu);
+            if (lane == p) { best[0] = k; bcol[0] = c; } // lane p keeps partition p's winner
+        }
+        if (lane < NP) {
+            x264_cuda_me_result_t r;
+            int bmx = S.seed[lane][0], bmy = S.seed[lane][1], bcost = S.seed[lane][2];
+            r.seed_mx = (int16_t)bmx; r.seed_my = (int16_t)bmy; r.seed_cost = bcost;
+            const int w_cost = (int)(best[0] >> 12);
+            if ((mask >> lane & 1) && w_cost < INVALID_COST && w_cost < bcost) {
+                bcost = w_cost; bmy = uy0 + (int)(best[0] & 0xfff); bmx = ux0 + (int)bcol[0];
+            }
+            if (!(mask >> lane & 1)) { bmx = bmy = 0; bcost = -1; r.seed_mx = r.seed_my = 0; r.seed_cost = -1; }
+            r.bmx = (int16_t)bmx; r.bmy = (int16_t)bmy; r.bcost = bcost;
+            out[lane] = r;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                          int me_range, const void *d_jobs, int n_jobs, void *d_results)
+{
+    if (n_jobs <= 0) return 0;
+    if (fenc->g.stride != fref->g.stride || fenc->g.lines != fref->g.lines) {
+        snprintf(ctx->err, 256, "x264_cuda_me_search_mb: fenc/fref geometry mismatch");
+        return -1;
+    }
+    if (me_range < 1 || me_range > 1024) {
+        snprintf(ctx->err, 256, "x264_cuda_me_search_mb: me_range %d out of range", me_range);
+        return -1;
+    }
+    const int16_t *const *d_tabs;
+    if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
+    Geo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
+    const int blocks = (n_jobs + MB_WARPS - 1) / MB_WARPS;
+    me_search_mb_kernel<<<blocks, MB_WARPS * 32, 0, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
+                                                                   (x264_cuda_me_mb_result_t *)d_results);
+    LAUNCH_CHECK(ctx, "me_search_mb_kernel");
+    return 0;
+}
+
+extern "C" int x264_cuda_me_search_mb(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int me_range,
+                                      const x264_cuda_me_mb_job_t *jobs, int n_jobs, x264_cuda_me_mb_result_t *results)
+{
+    if (n_jobs <= 0) return 0;
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_me_mb_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_me_mb_result_t);
+    const size_t jb_al = (jb + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, jb_al + rb, jb_al + rb)) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    memcpy(hs, jobs, jb);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds, hs, jb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x264_cuda_me_search_mb_dev(ctx, fenc, fref, me_range, ds, n_jobs, ds + jb_al)) return -1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs + jb_al, ds + jb_al, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(results, hs + jb_al, rb);
+    return 0;
+}
