@@ -18,16 +18,24 @@ namespace {
 struct Geo { const uint8_t *fenc; const uint8_t *fref; int stride; };
 
 #define MB_WARPS 4
-#define MB_ROW_CHUNK 64
+#define MB_MAX_RANGE 64   // larger ranges go through the per-block kernel (x264_cuda_me_search)
+#define MB_MAX_UW 128     // union window limits; beyond them partitions are searched one at a time
+#define MB_MAX_UR 192
 #define NP X264_CUDA_ME_MB_PARTS
 #define NCAND (X264_CUDA_ME_MB_MVC + 2)
-#define INVALID_COST 0x3ffff // above any real cost (<= 65280 + 2*~2.6k), small enough that 3 of them << 12 fit 32 bits
+#define INVALID_COST 0x3ffff // above any real cost (<= 65280 + 2*~2.6k); three of them still fit the key's 20 cost bits
+
+// key layout: cost (up to 20 bits) << 10 | row (8 bits) << 2 | column chunk (2 bits).  min() over keys is the
+// reference's strict-'<' update in raster order at column-chunk granularity; the column inside the chunk is the
+// lane's own, resolved by the final warp reduction.
+#define KEY_SHIFT 10
 
 struct __align__(16) WarpSmem {
     uint32_t F[16][4];                       // fenc macroblock, 256 B (read as uint4 rows: keep 16-byte aligned)
-    uint32_t cyt[MB_ROW_CHUNK][12];          // per row: 9 partition y-costs (+3 pad) -> three 16-byte broadcast loads
+    uint32_t cyt[MB_MAX_UR + 4][12];         // per union row: 9 partition y-costs, pre-shifted, | row<<2 (+3 pad)
     x264_cuda_me_mb_job_t job;               // 280 B
-    int pc_cost[NP * NCAND], pc_x[NP * NCAND], pc_y[NP * NCAND]; // predictor stage scratch
+    int quad[NP * NCAND][4];                 // predictor stage: 8x8 quadrant SADs of every (partition, candidate)
+    int pc_x[NP * NCAND], pc_y[NP * NCAND];
     int seed[NP][3];                         // bmx, bmy, bcost per partition
     int win[NP][4];                          // min_x, min_y, width, rows per partition
 };
@@ -42,32 +50,104 @@ __device__ __forceinline__ void load_row16(uint32_t (&dst)[4], const uint8_t *p,
 }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// partition geometry inside the macroblock
-__device__ __forceinline__ void part_geom(int p, int &ox, int &oy, int &bw, int &bh)
+// quadrants (bit q: TL,TR,BL,BR) making up partition p
+__device__ __forceinline__ unsigned part_quads(int p)
 {
-    ox = (p == 4 || p == 6 || p == 8) ? 8 : 0;
-    oy = (p == 2 || p == 7 || p == 8) ? 8 : 0;
-    bw = (p <= 2) ? 16 : 8;
-    bh = (p == 0 || p == 3 || p == 4) ? 16 : 8;
+    return (unsigned)(0x8421a5c3full >> (4 * p)) & 15; // p0:1111 p1:0011 p2:1100 p3:0101 p4:1010 p5:0001 p6:0010 p7:0100 p8:1000
 }
 
-// plain SAD of a bw x bh block (bw in {8,16}) of fenc (from the shared copy) vs reference bytes at `a`
-__device__ int sad_part(const uint32_t (*F)[4], int ox, int oy, int bw, int bh, const uint8_t *a, int stride)
+// SAD of the 8x8 fenc quadrant q against the reference bytes at `a` (any alignment); fully unrolled, uniform work
+__device__ __forceinline__ int sad_quad(const uint32_t (*F)[4], int q, const uint8_t *a, int stride)
 {
     const int sh = ((uintptr_t)a & 3) * 8;
     const uint8_t *p = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
-    uint32_t acc = 0;
-    const int nw = bw >> 2, w0 = ox >> 2;
-    for (int y = 0; y < bh; y++) {
+    const int w0 = (q & 1) * 2, y0 = (q >> 1) * 8;
+    uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
         const uint32_t *row = (const uint32_t *)(p + (size_t)y * stride);
-        uint32_t lo = __ldg(row);
-        for (int w = 0; w < nw; w++) {
-            const uint32_t hi = __ldg(row + w + 1);
-            acc = sad4_acc(F[oy + y][w0 + w], __funnelshift_r(lo, hi, sh), acc);
-            lo = hi;
+        const uint32_t a0 = __ldg(row), a1 = __ldg(row + 1), a2 = __ldg(row + 2);
+        acc0 = sad4_acc(F[y0 + y][w0], __funnelshift_r(a0, a1, sh), acc0);
+        acc1 = sad4_acc(F[y0 + y][w0 + 1], __funnelshift_r(a1, a2, sh), acc1);
+    }
+    return (int)(acc0 + acc1);
+}
+
+// The exhaustive pass over the union window of the partitions in `mask`.  Returns per-lane best keys in best[].
+__device__ __forceinline__ void scan_union(WarpSmem &S, const int16_t *tab, const uint8_t *ref0, int stride, unsigned mask,
+                                           int ux0, int uy0, int uwidth, int urows, int lane, uint32_t (&best)[NP])
+{
+    const x264_cuda_me_mb_job_t &job = S.job;
+    // y-cost table for the whole union: cyt[r][p] = (cost_y << KEY_SHIFT) | r << 2, INVALID outside p's row range
+    __syncwarp();
+    for (int i = lane; i < (urows + 3) * 12; i += 32) {
+        const int r = i / 12, p = i - r * 12;
+        uint32_t v = INVALID_COST;
+        if (p < NP && r < urows && (mask >> p & 1)) {
+            const int my = uy0 + r;
+            if (my >= S.win[p][1] && my < S.win[p][1] + S.win[p][3]) v = (uint32_t)tab[(my << 2) - job.mvp[p][1]];
+        }
+        S.cyt[r][p] = (v << KEY_SHIFT) | ((uint32_t)min(r, 255) << 2);
+    }
+    __syncwarp();
+    const uint4 *F4 = (const uint4 *)&S.F[0][0];
+    for (int c0 = 0, chunk = 0; c0 < uwidth; c0 += 32, chunk++) {
+        // lane tiling of this column chunk: a full chunk is 32 columns x 1 row segment; a narrow tail chunk is
+        // folded to 16x2 or 8x4 (columns x row segments) so that all 32 lanes stay busy
+        const int rem = uwidth - c0;
+        const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8, segs = 32 / cw;
+        const int lcol = lane & (cw - 1), seg = lane / cw;
+        const int col = c0 + lcol;
+        const int mx = ux0 + min(col, uwidth - 1);
+        const int seg_rows = (urows + segs - 1) / segs;
+        uint32_t cxp[NP]; // (x-cost << KEY_SHIFT) | chunk, INVALID outside the partition's column range
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const int wx0 = S.win[p][0], ww = S.win[p][2];
+            const bool in = (mask >> p & 1) && col < uwidth && mx >= wx0 && mx < wx0 + ww;
+            cxp[p] = ((in ? (uint32_t)tab[(mx << 2) - job.mvp[p][0]] : INVALID_COST) << KEY_SHIFT) | (uint32_t)chunk;
+        }
+        // pull the window tile into L1: (urows+15+pad) rows x <=51 bytes, at most two 128-byte lines per row
+        const uint8_t *t0 = ref0 + (ptrdiff_t)uy0 * stride + ux0 + c0;
+        for (int r = lane; r < seg_rows * segs + 15; r += 32) {
+            prefetch_l1(t0 + (size_t)r * stride);
+            prefetch_l1(t0 + (size_t)r * stride + cw + 16);
+        }
+        const int rbeg = seg * seg_rows;
+        const uint8_t *a = ref0 + (ptrdiff_t)(uy0 + rbeg) * stride + mx;
+        const int sh = ((uintptr_t)a & 3) * 8;
+        const uint8_t *pr = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
+        uint32_t R[16][4];
+#pragma unroll
+        for (int y = 0; y < 15; y++) load_row16(R[y], pr + (size_t)y * stride, sh);
+        for (int base = 0; base < seg_rows; base += 16) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int r = base + j;
+                if (r >= seg_rows) break; // warp-uniform
+                load_row16(R[(j + 15) % 16], pr + (size_t)(r + 15) * stride, sh);
+                const uint4 *cy4 = (const uint4 *)&S.cyt[rbeg + r][0];
+                const uint4 ca = cy4[0], cb = cy4[1], cc = cy4[2];
+                // eight independent accumulator chains (two per 8x8 quadrant) keep the ALU pipe fed
+                uint32_t tl = 0, tr = 0, bl = 0, br = 0, tl2 = 0, tr2 = 0, bl2 = 0, br2 = 0;
+#pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    const uint4 f = F4[y], g = F4[y + 8];
+                    tl = sad4_acc(f.x, R[(j + y) % 16][0], tl); tr = sad4_acc(f.z, R[(j + y) % 16][2], tr);
+                    bl = sad4_acc(g.x, R[(j + y + 8) % 16][0], bl); br = sad4_acc(g.z, R[(j + y + 8) % 16][2], br);
+                    tl2 = sad4_acc(f.y, R[(j + y) % 16][1], tl2); tr2 = sad4_acc(f.w, R[(j + y) % 16][3], tr2);
+                    bl2 = sad4_acc(g.y, R[(j + y + 8) % 16][1], bl2); br2 = sad4_acc(g.w, R[(j + y + 8) % 16][3], br2);
+                }
+                tl += tl2; tr += tr2; bl += bl2; br += br2;
+                const uint32_t top = tl + tr, bot = bl + br, lft = tl + bl, rgt = tr + br, all = top + bot;
+                // key = sad*2^KEY_SHIFT + (cx<<KEY_SHIFT|chunk) + (cy<<KEY_SHIFT|row<<2): one IMAD (FMA pipe) + IADD + MIN
+#define UPD(p, sad, cy) best[p] = min(best[p], __umul24((sad), 1u << KEY_SHIFT) + cxp[p] + (cy))
+                UPD(0, all, ca.x); UPD(1, top, ca.y); UPD(2, bot, ca.z); UPD(3, lft, ca.w); UPD(4, rgt, cb.x);
+                UPD(5, tl, cb.y); UPD(6, tr, cb.z); UPD(7, bl, cb.w); UPD(8, br, cc.x);
+#undef UPD
+            }
         }
     }
-    return (int)acc;
 }
 
 __global__ void __launch_bounds__(MB_WARPS * 32, 3)
@@ -107,37 +187,40 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
         for (int i = lane; i < 64; i += 32) S.F[i >> 2][i & 3] = __ldg((const uint32_t *)(fe + (size_t)(i >> 2) * stride) + (i & 3));
         __syncwarp();
 
-        // ---- predictor stage per partition (me.c:207-229), one (partition, candidate) per lane, two rounds
+        // ---- predictor stage per partition (me.c:207-229).  Every (partition, candidate) cost is a sum of 8x8
+        // quadrant SADs at that candidate's position: 54 items x up to 4 quadrants, one uniform 8x8 SAD per lane.
         if (!(job.flags & X264_CUDA_ME_SEEDED)) {
-            for (int idx = lane; idx < NP * NCAND; idx += 32) {
-                const int p = idx / NCAND, c = idx % NCAND;
-                int cost = COST_MAX + 1, cx = 0, cy = 0;
-                if (mask >> p & 1) {
-                    int valid = 1;
-                    const int n_mvc = min((int)job.i_mvc[p], X264_CUDA_ME_MB_MVC);
-                    if (c == 0) {
-                        cx = (clip3i(job.mvp[p][0], x_min * 4, x_max * 4) + 2) >> 2;
-                        cy = (clip3i(job.mvp[p][1], y_min * 4, y_max * 4) + 2) >> 2;
-                    } else if (c <= X264_CUDA_ME_MB_MVC) {
-                        const int mx = (job.mvc[p][c - 1][0] + 2) >> 2, my = (job.mvc[p][c - 1][1] + 2) >> 2;
-                        valid = (c - 1 < n_mvc) && (mx | my) != 0;
-                        cx = clip3i(mx, x_min, x_max); cy = clip3i(my, y_min, y_max);
-                    }
-                    if (valid) {
-                        int ox, oy, bw, bh;
-                        part_geom(p, ox, oy, bw, bh);
-                        cost = sad_part(S.F, ox, oy, bw, bh, ref0 + (ptrdiff_t)(oy + cy) * stride + ox + cx, stride);
-                        if (c != 0) cost += tab[(cx << 2) - job.mvp[p][0]] + tab[(cy << 2) - job.mvp[p][1]];
-                    }
+            for (int idx = lane; idx < NP * NCAND; idx += 32) { // candidate positions
+                const int p = idx / NCAND, c = idx - p * NCAND;
+                int cx = 0, cy = 0, valid = (mask >> p & 1);
+                const int n_mvc = min((int)job.i_mvc[p], X264_CUDA_ME_MB_MVC);
+                if (c == 0) {
+                    cx = (clip3i(job.mvp[p][0], x_min * 4, x_max * 4) + 2) >> 2;
+                    cy = (clip3i(job.mvp[p][1], y_min * 4, y_max * 4) + 2) >> 2;
+                } else if (c <= X264_CUDA_ME_MB_MVC) {
+                    const int mx = (job.mvc[p][c - 1][0] + 2) >> 2, my = (job.mvc[p][c - 1][1] + 2) >> 2;
+                    valid = valid && (c - 1 < n_mvc) && (mx | my) != 0; // zero predictors: covered by the (0,0) test
+                    cx = clip3i(mx, x_min, x_max); cy = clip3i(my, y_min, y_max);
                 }
-                S.pc_cost[idx] = cost; S.pc_x[idx] = cx; S.pc_y[idx] = cy;
+                S.pc_x[idx] = cx; S.pc_y[idx] = valid ? cy : (1 << 20); // pc_y == 1<<20 marks "skip"
+            }
+            __syncwarp();
+            for (int t = lane; t < NP * NCAND * 4; t += 32) { // (item, quadrant) tasks
+                const int idx = t >> 2, q = t & 3, p = idx / NCAND;
+                int v = 0;
+                if (S.pc_y[idx] != (1 << 20) && (part_quads(p) >> q & 1))
+                    v = sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + S.pc_y[idx]) * stride + (q & 1) * 8 + S.pc_x[idx], stride);
+                S.quad[idx][q] = v;
             }
             __syncwarp();
             if (lane < NP) {
                 int bc = COST_MAX + 1, bx = 0, by = 0; // sequential strict '<' in candidate order
                 for (int c = 0; c < NCAND; c++) {
-                    const int v = S.pc_cost[lane * NCAND + c];
-                    if (v < bc) { bc = v; bx = S.pc_x[lane * NCAND + c]; by = S.pc_y[lane * NCAND + c]; }
+                    const int idx = lane * NCAND + c;
+                    if (S.pc_y[idx] == (1 << 20)) continue;
+                    int v = S.quad[idx][0] + S.quad[idx][1] + S.quad[idx][2] + S.quad[idx][3];
+                    if (c != 0) v += tab[(S.pc_x[idx] << 2) - job.mvp[lane][0]] + tab[(S.pc_y[idx] << 2) - job.mvp[lane][1]];
+                    if (v < bc) { bc = v; bx = S.pc_x[idx]; by = S.pc_y[idx]; }
                 }
                 S.seed[lane][0] = bx; S.seed[lane][1] = by; S.seed[lane][2] = bc;
             }
@@ -148,116 +231,61 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
         }
         __syncwarp();
 
-        // ---- per-partition windows (me.c:451-457) and their union
-        int ux0 = 1 << 20, uy0 = 1 << 20, ux1 = -(1 << 20), uy1 = -(1 << 20);
-        if (lane < NP && (mask >> lane & 1)) {
-            const int bmx = S.seed[lane][0], bmy = S.seed[lane][1];
-            const int min_x = max(bmx - me_range, x_min), min_y = max(bmy - me_range, y_min);
-            const int max_x = min(bmx + me_range, x_max), max_y = min(bmy + me_range, y_max);
-            const int width = (max_x - min_x + 3) & ~3, rows = max_y - min_y + 1;
+        // ---- per-partition windows (me.c:451-457)
+        if (lane < NP) {
+            int min_x = 0, min_y = 0, width = 0, rows = 0;
+            if (mask >> lane & 1) {
+                const int bmx = S.seed[lane][0], bmy = S.seed[lane][1];
+                min_x = max(bmx - me_range, x_min); min_y = max(bmy - me_range, y_min);
+                const int max_x = min(bmx + me_range, x_max), max_y = min(bmy + me_range, y_max);
+                width = (max_x - min_x + 3) & ~3; rows = max_y - min_y + 1;
+            }
             S.win[lane][0] = min_x; S.win[lane][1] = min_y; S.win[lane][2] = width; S.win[lane][3] = rows;
-            ux0 = min_x; uy0 = min_y; ux1 = min_x + width; uy1 = min_y + rows;
-        } else if (lane < NP) {
-            S.win[lane][0] = 0; S.win[lane][1] = 0; S.win[lane][2] = 0; S.win[lane][3] = 0; // empty window
         }
-        ux0 = __reduce_min_sync(0xffffffffu, ux0); uy0 = __reduce_min_sync(0xffffffffu, uy0);
-        ux1 = __reduce_max_sync(0xffffffffu, ux1); uy1 = __reduce_max_sync(0xffffffffu, uy1);
         __syncwarp();
-        const int uwidth = ux1 - ux0, urows = uy1 - uy0;
 
-        uint32_t best[NP], bcol[NP];
+        // ---- exhaustive pass(es): all partitions over the union of their windows when it is compact, else one by one
+        unsigned todo = mask;
+        int my_bmx = 0, my_bmy = 0, my_cost = INVALID_COST; // lane p keeps partition p's window winner
+        while (todo) {
+            int ux0 = 1 << 20, uy0 = 1 << 20, ux1 = -(1 << 20), uy1 = -(1 << 20);
+            if (lane < NP && (todo >> lane & 1)) {
+                ux0 = S.win[lane][0]; uy0 = S.win[lane][1]; ux1 = ux0 + S.win[lane][2]; uy1 = uy0 + S.win[lane][3];
+            }
+            ux0 = __reduce_min_sync(0xffffffffu, ux0); uy0 = __reduce_min_sync(0xffffffffu, uy0);
+            ux1 = __reduce_max_sync(0xffffffffu, ux1); uy1 = __reduce_max_sync(0xffffffffu, uy1);
+            unsigned group = todo;
+            if (ux1 - ux0 > MB_MAX_UW || uy1 - uy0 > MB_MAX_UR) { // scattered predictors: search the lowest partition alone
+                const int p = __ffs(todo) - 1;
+                group = 1u << p;
+                ux0 = S.win[p][0]; uy0 = S.win[p][1]; ux1 = ux0 + S.win[p][2]; uy1 = uy0 + S.win[p][3];
+            }
+            todo &= ~group;
+            uint32_t best[NP];
 #pragma unroll
-        for (int p = 0; p < NP; p++) { best[p] = 0xffffffffu; bcol[p] = 0; }
-
-        for (int c0 = 0; c0 < uwidth; c0 += 32) {
-            const int col = c0 + lane;
-            const int mx = ux0 + min(col, uwidth - 1);
-            uint32_t cxp[NP]; // this lane's x-cost per partition, INVALID outside the partition's column range
+            for (int p = 0; p < NP; p++) best[p] = 0xffffffffu;
+            scan_union(S, tab, ref0, stride, group, ux0, uy0, ux1 - ux0, uy1 - uy0, lane, best);
+            // warp argmin per partition: min key (cost,row,chunk), then the lowest in-chunk column among its holders
+            const int uwidth = ux1 - ux0;
 #pragma unroll
             for (int p = 0; p < NP; p++) {
-                const int wx0 = S.win[p][0], ww = S.win[p][2];
-                const bool in = col < uwidth && mx >= wx0 && mx < wx0 + ww;
-                cxp[p] = in ? (uint32_t)tab[(mx << 2) - job.mvp[p][0]] : INVALID_COST;
+                if (!(group >> p & 1)) continue; // warp-uniform
+                const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
+                const int chunk = k & 3, rem = uwidth - chunk * 32;
+                const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8;
+                const uint32_t c = __reduce_min_sync(0xffffffffu, best[p] == k ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
+                if (lane == p) {
+                    my_cost = (int)(k >> KEY_SHIFT);
+                    my_bmy = uy0 + (int)((k >> 2) & 255);
+                    my_bmx = ux0 + chunk * 32 + (int)c;
+                }
             }
-            for (int row0 = 0; row0 < urows; row0 += MB_ROW_CHUNK) {
-                const int nrows = min(MB_ROW_CHUNK, urows - row0);
-                // y-cost table of this row chunk: cyt[r][p]
-                __syncwarp();
-                for (int i = lane; i < nrows * 12; i += 32) {
-                    const int r = i / 12, p = i - r * 12;
-                    uint32_t v = INVALID_COST;
-                    if (p < NP) {
-                        const int my = uy0 + row0 + r;
-                        if (my >= S.win[p][1] && my < S.win[p][1] + S.win[p][3]) v = (uint32_t)tab[(my << 2) - job.mvp[p][1]];
-                    }
-                    S.cyt[r][p] = v;
-                }
-                // pull the window tile into L1: (nrows+15) rows x 51 bytes, at most two 128-byte lines per row
-                const uint8_t *t0 = ref0 + (ptrdiff_t)(uy0 + row0) * stride + ux0 + c0;
-                for (int r = lane; r < nrows + 15; r += 32) {
-                    prefetch_l1(t0 + (size_t)r * stride);
-                    prefetch_l1(t0 + (size_t)r * stride + 48);
-                }
-                __syncwarp();
-                const uint8_t *a = ref0 + (ptrdiff_t)(uy0 + row0) * stride + mx;
-                const int sh = ((uintptr_t)a & 3) * 8;
-                const uint8_t *pr = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
-                uint32_t R[16][4];
-#pragma unroll
-                for (int y = 0; y < 15; y++) load_row16(R[y], pr + (size_t)y * stride, sh);
-                uint32_t kb[NP]; // best key of this chunk per partition (cost<<12 | row)
-#pragma unroll
-                for (int p = 0; p < NP; p++) kb[p] = 0xffffffffu;
-                const uint4 *F4 = (const uint4 *)&S.F[0][0];
-                for (int base = 0; base < nrows; base += 16) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int r = base + j;
-                        if (r >= nrows) break; // warp-uniform
-                        load_row16(R[(j + 15) % 16], pr + (size_t)(r + 15) * stride, sh);
-                        const uint4 *cy4 = (const uint4 *)&S.cyt[r][0];
-                        const uint4 ca = cy4[0], cb = cy4[1], cc = cy4[2];
-                        uint32_t tl = 0, tr = 0, bl = 0, br = 0;
-#pragma unroll
-                        for (int y = 0; y < 8; y++) {
-                            const uint4 f = F4[y];
-                            tl = sad4_acc(f.x, R[(j + y) % 16][0], tl); tr = sad4_acc(f.z, R[(j + y) % 16][2], tr);
-                            tl = sad4_acc(f.y, R[(j + y) % 16][1], tl); tr = sad4_acc(f.w, R[(j + y) % 16][3], tr);
-                        }
-#pragma unroll
-                        for (int y = 8; y < 16; y++) {
-                            const uint4 f = F4[y];
-                            bl = sad4_acc(f.x, R[(j + y) % 16][0], bl); br = sad4_acc(f.z, R[(j + y) % 16][2], br);
-                            bl = sad4_acc(f.y, R[(j + y) % 16][1], bl); br = sad4_acc(f.w, R[(j + y) % 16][3], br);
-                        }
-                        const uint32_t top = tl + tr, bot = bl + br, lft = tl + bl, rgt = tr + br, all = top + bot;
-                        const uint32_t rowid = (uint32_t)(row0 + r);
-#define UPD(p, sad, cy) kb[p] = min(kb[p], (((sad) + cxp[p] + (cy)) << 12) | rowid)
-                        UPD(0, all, ca.x); UPD(1, top, ca.y); UPD(2, bot, ca.z); UPD(3, lft, ca.w); UPD(4, rgt, cb.x);
-                        UPD(5, tl, cb.y); UPD(6, tr, cb.z); UPD(7, bl, cb.w); UPD(8, br, cc.x);
-#undef UPD
-                    }
-                }
-#pragma unroll
-                for (int p = 0; p < NP; p++)
-                    if (kb[p] < best[p]) { best[p] = kb[p]; bcol[p] = (uint32_t)col; } // later chunks only win strictly
-            }
-        }
-        // ---- warp argmin per partition: min key (cost,row), then the lowest column among the lanes holding it
-#pragma unroll
-        for (int p = 0; p < NP; p++) {
-            const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
-            const uint32_t c = __reduce_min_sync(0xffffffffu, best[p] == k ? bcol[p] : 0xffffffffu);
-            if (lane == p) { best[0] = k; bcol[0] = c; } // lane p keeps partition p's winner
         }
         if (lane < NP) {
             x264_cuda_me_result_t r;
             int bmx = S.seed[lane][0], bmy = S.seed[lane][1], bcost = S.seed[lane][2];
             r.seed_mx = (int16_t)bmx; r.seed_my = (int16_t)bmy; r.seed_cost = bcost;
-            const int w_cost = (int)(best[0] >> 12);
-            if ((mask >> lane & 1) && w_cost < INVALID_COST && w_cost < bcost) {
-                bcost = w_cost; bmy = uy0 + (int)(best[0] & 0xfff); bmx = ux0 + (int)bcol[0];
-            }
+            if ((mask >> lane & 1) && my_cost < INVALID_COST && my_cost < bcost) { bcost = my_cost; bmy = my_bmy; bmx = my_bmx; }
             if (!(mask >> lane & 1)) { bmx = bmy = 0; bcost = -1; r.seed_mx = r.seed_my = 0; r.seed_cost = -1; }
             r.bmx = (int16_t)bmx; r.bmy = (int16_t)bmy; r.bcost = bcost;
             out[lane] = r;
@@ -275,8 +303,9 @@ extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_fram
         snprintf(ctx->err, 256, "x264_cuda_me_search_mb: fenc/fref geometry mismatch");
         return -1;
     }
-    if (me_range < 1 || me_range > 1024) {
-        snprintf(ctx->err, 256, "x264_cuda_me_search_mb: me_range %d out of range", me_range);
+    if (me_range < 1 || me_range > MB_MAX_RANGE) {
+        snprintf(ctx->err, 256, "x264_cuda_me_search_mb: me_range %d not in 1..%d (use x264_cuda_me_search for larger ranges)", me_range,
+                 MB_MAX_RANGE);
         return -1;
     }
     const int16_t *const *d_tabs;
