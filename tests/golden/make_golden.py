@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libref_harness.so, i.e. the x264
+snapshot's own C compiled in place).  Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors, so these are its outputs on seeded inputs; the
+not-gpu tests require the oracle port to reproduce every byte, the gpu tests require the CUDA path to."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+import xo_api as X  # noqa: E402
+import __graft_entry__ as ge  # noqa: E402
+
+pkg = ge.load_pkg()
+from x264_vs2008_b200 import synth  # noqa: E402
+from helpers import make_me_jobs  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    r = X.ref()
+    assert r.backend == "reference"
+    out = {}
+    # ---- pixel metrics on seeded blocks + the max-difference patterns of checkasm.c:246-256
+    rng = np.random.default_rng(2009)
+    a = rng.integers(0, 256, (48, 64), dtype=np.uint8)
+    b = rng.integers(0, 256, (48, 64), dtype=np.uint8)
+    yy, xx = np.mgrid[0:48, 0:64]
+    pats = [(a, b), (np.zeros_like(a), np.full_like(a, 255)), ((((xx + yy) & 1) * 255).astype(np.uint8), (((xx + yy + 1) & 1) * 255).astype(np.uint8)),
+            (((xx & 1) * 255).astype(np.uint8), ((yy & 1) * 255).astype(np.uint8))]
+    offs = rng.integers(0, 32, (40, 4))
+    vals = []
+    for pa, pb in pats:
+        for m in range(4):
+            for ip in range(7):
+                if m == X.SA8D and ip not in (0, 3):
+                    continue
+                for o in offs:
+                    vals.append(r.pixel_cmp(m, ip, pa, 64, pb, 64, int(o[0]) * 64 + int(o[1]), int(o[2]) * 64 + int(o[3])))
+    out["pixel_a"], out["pixel_b"], out["pixel_offs"], out["pixel_vals"] = a, b, offs, np.array(vals, np.int64)
+    # ---- MV cost tables: sha256 of all 52 (the tables themselves are 1.7 MB)
+    out["cost_mv_sha"] = np.array([sha(r.cost_mv_table(q)) for q in range(52)])
+    out["cost_mv_qp26_head"] = r.cost_mv_table(26)[2 * 4 * 2048:2 * 4 * 2048 + 256]
+    # ---- frame filters on a small picture (non-mod16 size on purpose) and CIF (checksums)
+    for name, (w, h) in (("small", (76, 52)), ("cif", (352, 288))):
+        g = r.geometry(w, h)
+        pic = synth.Clip(w, h, seed=5).luma(2)
+        plane = r.plane_from_picture(g, pic)
+        for s8 in (0, 1):
+            fh, fv, fc, integ = r.frame_filter(g, plane, s8)
+            if name == "small":
+                out["small_pic"] = pic
+                out["small_plane"], out["small_h"], out["small_v"], out["small_c"] = plane, fh, fv, fc
+                out["small_integral%d" % s8] = integ
+            out["%s_filter_sha_s8%d" % (name, s8)] = np.array([sha(plane), sha(fh), sha(fv), sha(fc), sha(integ)])
+        if g.mb_width % 2 == 0:
+            lows = r.init_lowres(g, plane.copy())
+            out["%s_lowres_sha" % name] = np.array([sha(x) for x in lows])
+    # ---- motion search (ESA, TESA, DIA, HEX; sub-pel) on a 160x128 pair
+    w, h = 160, 128
+    g = r.geometry(w, h)
+    clip = synth.Clip(w, h, seed=21)
+    pe, pr = r.plane_from_picture(g, clip.luma(1)), r.plane_from_picture(g, clip.luma(0))
+    fh, fv, fc, integ = r.frame_filter(g, pr, 1)
+    res = []
+    for method in (X.ME_DIA, X.ME_HEX, X.ME_ESA, X.ME_TESA):
+        for fpel_satd in ((0, 1) if method == X.ME_TESA else (0,)):
+            jobs, mis = make_me_jobs(pkg, g, seed=100 + method, n=120, me_range=16, qp=(12, 26, 40), pixels=(0, 1, 2, 3, 4, 5, 6),
+                                     tesa=(method == X.ME_TESA), fpel_satd=bool(fpel_satd))
+            for mi in mis:
+                mi.me_method = method
+                mi.b_sub8x8 = 1
+                o = r.me_search_fpel(g, pe, pr, integ, mi)
+                res.append((method, fpel_satd, o.mv[0], o.mv[1], o.cost, o.cost_mv))
+            for subme in (2, 4, 6):
+                for mi in mis[:40]:
+                    mi.i_pixel = mi.i_pixel % 4
+                    mi.bx, mi.by = (mi.bx // 16) * 16, (mi.by // 16) * 16
+                    mi.fpel_satd = 1 if (method == X.ME_TESA) else 0
+                    o = r.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
+                    res.append((method, 10 + subme, o.mv[0], o.mv[1], o.cost, o.cost_mv))
+    out["me_results"] = np.array(res, np.int32)
+    np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
+    print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+"""not-gpu: oracle port vs the unmodified reference, live (only where oracle/_ref is built), on fresh seeded inputs —
+the checkasm-style differential test (S/tools/checkasm.c) with the reference as the other side."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import xo_api as X
+
+
+def test_cost_tables_all_qps(port, ref):
+    for q in range(52):
+        assert np.array_equal(port.cost_mv_table(q), ref.cost_mv_table(q)), q
+
+
+def test_pixel_metrics_random(port, ref):
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 256, (64, 64), dtype=np.uint8)
+    b = rng.integers(0, 256, (64, 64), dtype=np.uint8)
+    for m in range(4):
+        for ip in range(7):
+            if m == X.SA8D and ip not in (0, 3):
+                continue
+            for _ in range(64):  # 64 misalignments like checkasm.c:227
+                oa, ob = int(rng.integers(0, 32)) * 64 + int(rng.integers(0, 32)), int(rng.integers(0, 32)) * 64 + int(rng.integers(0, 32))
+                assert port.pixel_cmp(m, ip, a, 64, b, 64, oa, ob) == ref.pixel_cmp(m, ip, a, 64, b, 64, oa, ob)
+    for ip in (0, 3):
+        assert port.lib.xo_pixel_var(ip, X._ptr(a), 64) == ref.lib.xo_pixel_var(ip, X._ptr(a), 64)
+    for ip in range(4):
+        assert port.lib.xo_pixel_hadamard_ac(ip, X._ptr(a), 64) == ref.lib.xo_pixel_hadamard_ac(ip, X._ptr(a), 64)
+
+
+def test_ads(port, ref):
+    """checkasm.c:433-464: 100 trials, sums[72], dc 14-bit, width 28, delta 32"""
+    rng = np.random.default_rng(9)
+    for ip in range(7):
+        for _ in range(100):
+            sums = rng.integers(0, 1 << 14, 72, dtype=np.uint16)
+            dc = (C.c_int * 4)(*[int(x) for x in rng.integers(0, 1 << 14, 4)])
+            cost = rng.integers(0, 1 << 10, 32, dtype=np.uint16)
+            thresh = int(rng.integers(0, 1 << 15))
+            m1, m2 = np.zeros(32, np.int16), np.zeros(32, np.int16)
+            n1 = port.lib.xo_pixel_ads(ip, dc, X._ptr(sums, X.u16p), 32, X._ptr(cost, X.u16p), X._ptr(m1, X.i16p), 28, thresh)
+            n2 = ref.lib.xo_pixel_ads(ip, dc, X._ptr(sums, X.u16p), 32, X._ptr(cost, X.u16p), X._ptr(m2, X.i16p), 28, thresh)
+            assert n1 == n2 and np.array_equal(m1[:n1], m2[:n2])
+
+
+def test_frame_ops(pkg, port, ref):
+    from x264_vs2008_b200 import synth
+    for (w, h) in ((64, 48), (100, 70), (352, 288)):
+        g = port.geometry(w, h)
+        gr = ref.geometry(w, h)
+        assert all(getattr(g, f[0]) == getattr(gr, f[0]) for f in g._fields_)
+        pic = synth.Clip(w, h, seed=w).luma(0)
+        pp, pr = port.plane_from_picture(g, pic), ref.plane_from_picture(g, pic)
+        assert np.array_equal(pp, pr)
+        for s8 in (0, 1):
+            for x, y in zip(port.frame_filter(g, pp, s8), ref.frame_filter(g, pr, s8)):
+                assert np.array_equal(x, y)
+        la, lb = port.init_lowres(g, pp.copy()), ref.init_lowres(g, pr.copy())
+        for x, y in zip(la, lb):
+            x2, y2 = x.reshape(-1, g.stride_lowres), y.reshape(-1, g.stride_lowres)
+            # odd mb_width: columns >= width_lowres (+ right border) are never written by the reference
+            # (stale memory of a recycled frame buffer) -> only the defined area is comparable
+            c1 = g.stride_lowres if g.mb_width % 2 == 0 else X.PADH + g.width_lowres
+            assert np.array_equal(x2[:, :c1], y2[:, :c1])
+
+
+def test_dct_quant(port, ref):
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        p1 = rng.integers(0, 256, 16 * 16, dtype=np.uint8)
+        p2 = rng.integers(0, 256, 32 * 16, dtype=np.uint8)
+        if trial % 10 == 0:
+            p1[:], p2[:] = 255 * (trial % 20 == 0), 255 * (trial % 20 != 0)
+        for fn, n in (("xo_sub4x4_dct", 16), ("xo_sub8x8_dct8", 64)):
+            d1, d2 = np.zeros(n, np.int16), np.zeros(n, np.int16)
+            getattr(port.lib, fn)(X._ptr(d1, X.i16p), X._ptr(p1), X._ptr(p2))
+            getattr(ref.lib, fn)(X._ptr(d2, X.i16p), X._ptr(p1), X._ptr(p2))
+            assert np.array_equal(d1, d2)
+            for cqm in (0, 1):
+                qp = int(rng.integers(0, 52))
+                lst = int(rng.integers(0, 4 if n == 16 else 2))
+                mf1, b1, mf2, b2 = (np.zeros(n, np.uint16) for _ in range(4))
+                tfn = "xo_quant4_tables" if n == 16 else "xo_quant8_tables"
+                getattr(port.lib, tfn)(cqm, lst, qp, X._ptr(mf1, X.u16p), X._ptr(b1, X.u16p))
+                getattr(ref.lib, tfn)(cqm, lst, qp, X._ptr(mf2, X.u16p), X._ptr(b2, X.u16p))
+                assert np.array_equal(mf1, mf2) and np.array_equal(b1, b2), (cqm, lst, qp)
+                dq1, dq2 = np.zeros(6 * n, np.int32), np.zeros(6 * n, np.int32)
+                dfn = "xo_dequant4_table" if n == 16 else "xo_dequant8_table"
+                getattr(port.lib, dfn)(cqm, lst, X._ptr(dq1, X.i32p))
+                getattr(ref.lib, dfn)(cqm, lst, X._ptr(dq2, X.i32p))
+                assert np.array_equal(dq1, dq2)
+                q1, q2 = d1.copy(), d1.copy()
+                qfn = "xo_quant_4x4" if n == 16 else "xo_quant_8x8"
+                nz1 = getattr(port.lib, qfn)(X._ptr(q1, X.i16p), X._ptr(mf1, X.u16p), X._ptr(b1, X.u16p))
+                nz2 = getattr(ref.lib, qfn)(X._ptr(q2, X.i16p), X._ptr(mf1, X.u16p), X._ptr(b1, X.u16p))
+                assert nz1 == nz2 and np.array_equal(q1, q2)
+                dfn2 = "xo_dequant_4x4" if n == 16 else "xo_dequant_8x8"
+                getattr(port.lib, dfn2)(X._ptr(q1, X.i16p), X._ptr(dq1, X.i32p), qp)
+                getattr(ref.lib, dfn2)(X._ptr(q2, X.i16p), X._ptr(dq1, X.i32p), qp)
+                assert np.array_equal(q1, q2)
+                r1, r2 = p2.copy(), p2.copy()
+                ifn = "xo_add4x4_idct" if n == 16 else "xo_add8x8_idct8"
+                getattr(port.lib, ifn)(X._ptr(r1), X._ptr(q1, X.i16p))
+                getattr(ref.lib, ifn)(X._ptr(r2), X._ptr(q2, X.i16p))
+                assert np.array_equal(r1, r2) and np.array_equal(q1, q2)
+        # DC paths: +-4080 extremes and 13-bit random (checkasm.c:577-589)
+        dc = rng.integers(-4096, 4096, 16).astype(np.int16) if trial % 3 else np.full(16, 4080 * (1 - 2 * (trial % 2)), np.int16)
+        a, b = dc.copy(), dc.copy()
+        port.lib.xo_dct4x4dc(X._ptr(a, X.i16p)); ref.lib.xo_dct4x4dc(X._ptr(b, X.i16p))
+        assert np.array_equal(a, b)
+        qp = int(rng.integers(0, 52))
+        mf, bias = int(rng.integers(100, 30000)), int(rng.integers(0, 30000))
+        assert port.lib.xo_quant_4x4_dc(X._ptr(a, X.i16p), mf, bias) == ref.lib.xo_quant_4x4_dc(X._ptr(b, X.i16p), mf, bias)
+        assert np.array_equal(a, b)
+        a2, b2 = a[:4].copy(), a[:4].copy()
+        assert port.lib.xo_quant_2x2_dc(X._ptr(a2, X.i16p), mf, bias) == ref.lib.xo_quant_2x2_dc(X._ptr(b2, X.i16p), mf, bias)
+        assert np.array_equal(a2, b2)
+        port.lib.xo_idct4x4dc(X._ptr(a, X.i16p)); ref.lib.xo_idct4x4dc(X._ptr(b, X.i16p))
+        assert np.array_equal(a, b)
+        dq = np.zeros(6 * 16, np.int32)
+        port.lib.xo_dequant4_table(0, 0, X._ptr(dq, X.i32p))
+        port.lib.xo_dequant_4x4_dc(X._ptr(a, X.i16p), X._ptr(dq, X.i32p), qp); ref.lib.xo_dequant_4x4_dc(X._ptr(b, X.i16p), X._ptr(dq, X.i32p), qp)
+        assert np.array_equal(a, b)
+        for n in (4, 16):
+            r1, r2 = p2.copy(), p2.copy()
+            port.lib.xo_add_idct_dc(X._ptr(r1), X._ptr(a, X.i16p), n); ref.lib.xo_add_idct_dc(X._ptr(r2), X._ptr(a, X.i16p), n)
+            assert np.array_equal(r1, r2)
