@@ -55,6 +55,7 @@ X264_CUDA_API int x264_cuda_measure_int_pipe(x264_cuda_t *ctx, double *sad4_per_
 #define X264_CUDA_FRAME_INTEGRAL  2 /* me >= ESA (frame.c:99-104) */
 #define X264_CUDA_FRAME_INTEGRAL4 4 /* + 4x4 sums: b_have_sub8x8_esa */
 #define X264_CUDA_FRAME_LOWRES    8 /* b_have_lowres (frame.c:79-97) */
+#define X264_CUDA_FRAME_CHROMA   16 /* plane[1], plane[2] (4:2:0), 16-px borders (frame.c:61-65) */
 
 typedef struct x264_cuda_geom_t {
     int width, height;       /* picture size */
@@ -66,7 +67,7 @@ typedef struct x264_cuda_geom_t {
 
 enum { X264_CUDA_PLANE_FULL = 0, X264_CUDA_PLANE_H = 1, X264_CUDA_PLANE_V = 2, X264_CUDA_PLANE_C = 3, /* filtered[0..3] */
        X264_CUDA_PLANE_LOWRES = 4, /* +0..3: lowres[0..3] */
-       X264_CUDA_PLANE_INTEGRAL = 8, X264_CUDA_PLANE_INTEGRAL4 = 9 };
+       X264_CUDA_PLANE_INTEGRAL = 8, X264_CUDA_PLANE_INTEGRAL4 = 9, X264_CUDA_PLANE_CB = 10, X264_CUDA_PLANE_CR = 11 };
 
 X264_CUDA_API x264_cuda_frame_t *x264_cuda_frame_new(x264_cuda_t *ctx, int width, int height, int flags);
 X264_CUDA_API void x264_cuda_frame_delete(x264_cuda_frame_t *frame);
@@ -78,6 +79,9 @@ X264_CUDA_API void *x264_cuda_frame_plane(const x264_cuda_frame_t *frame, int pl
  * the host plane (e.g. x264_frame_t.plane[0]).  No border handling. */
 X264_CUDA_API int x264_cuda_frame_upload(x264_cuda_t *ctx, x264_cuda_frame_t *frame, const uint8_t *src, int src_stride,
                                          int cols, int rows);
+/* chroma: plane = X264_CUDA_PLANE_CB / _CR, cols x rows in chroma samples */
+X264_CUDA_API int x264_cuda_frame_upload_chroma(x264_cuda_t *ctx, x264_cuda_frame_t *frame, int plane, const uint8_t *src,
+                                                int src_stride, int cols, int rows);
 /* the same from a device-resident source (pitch-linear) */
 X264_CUDA_API int x264_cuda_frame_upload_dev(x264_cuda_t *ctx, x264_cuda_frame_t *frame, const void *dsrc, int src_stride,
                                              int cols, int rows);
@@ -143,6 +147,57 @@ X264_CUDA_API int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_fram
 /* m->mv / m->cost / m->cost_mv from a result, i.e. me.c:603-630 for i_subpel_refine < 2 (host arithmetic) */
 X264_CUDA_API void x264_cuda_me_finish(const x264_cuda_me_job_t *job, const x264_cuda_me_result_t *res,
                                        const int16_t *cost_table, int mv_max_spel_y, int16_t mv[2], int *cost, int *cost_mv);
+
+/* ------------------------------------------------------------------ transform / quantisation --------- */
+/* Quantiser tables exactly as x264_cqm_init leaves them in x264_t (S/common/set.c:68-174, S/common/common.h:294-304):
+ * quant4_mf[list] -> uint16[52][16], quant4_bias likewise, dequant4_mf[list] -> int[6][16] (lists CQM_4IY,4PY,4IC,4PC),
+ * quant8_mf[list] -> uint16[52][64], quant8_bias, dequant8_mf[list] -> int[6][64] (lists CQM_8IY, 8PY; may be NULL). */
+X264_CUDA_API int x264_cuda_set_quant_tables(x264_cuda_t *ctx, const uint16_t *const quant4_mf[4], const uint16_t *const quant4_bias[4],
+                                             const int *const dequant4_mf[4], const uint16_t *const quant8_mf[2],
+                                             const uint16_t *const quant8_bias[2], const int *const dequant8_mf[2]);
+/* host-side mirror of x264_cqm_init for standalone use: cqm_preset 0 flat / 1 JVT, default deadzones 21/11.
+ * Output arrays are laid out as above (caller-allocated, contiguous over lists). */
+X264_CUDA_API void x264_cuda_host_cqm_tables(int cqm_preset, uint16_t q4mf[4][52][16], uint16_t q4bias[4][52][16], int dq4[4][6][16],
+                                             uint16_t q8mf[2][52][64], uint16_t q8bias[2][52][64], int dq8[2][6][64]);
+/* convenience: build with x264_cuda_host_cqm_tables and upload */
+X264_CUDA_API int x264_cuda_set_quant_preset(x264_cuda_t *ctx, int cqm_preset);
+
+/* Function-level batches over PACKED blocks (host arrays; the checkasm-style entry points, S/tools/checkasm.c:469-688,
+ * :976-1291).  kind 0: 4x4 blocks (16 samples / coefficients each), kind 1: 8x8 (64).  For block i:
+ *   dct   = sub4x4_dct | sub8x8_dct8 (fenc_i - pred_i)                  (S/common/dct.c:122-155, :265-285)   -> dct_out
+ *   nz    = quant_4x4 | quant_8x8 (dct, mf[cat_i][qp_i], bias[..])      (S/common/quant.c:33-58)             -> level_out, nz_out
+ *   recon = pred_i + idct(dequant(level))                                (quant.c:76-146, dct.c:174-216, :322-341) -> recon_out
+ * cat_i = CQM list id.  Any output pointer may be NULL. */
+X264_CUDA_API int x264_cuda_block_residual(x264_cuda_t *ctx, int kind, int n, const uint8_t *fenc, const uint8_t *pred,
+                                           const uint8_t *qp, const uint8_t *cat, int16_t *dct_out, int16_t *level_out,
+                                           uint8_t *nz_out, uint8_t *recon_out);
+/* DC chains on packed blocks of 16 (kind 0: dct4x4dc -> quant_4x4_dc -> idct4x4dc -> dequant_4x4_dc, the luma-DC path of
+ * x264_mb_encode_i16x16, S/encoder/macroblock.c:246-262) : fwd_out / level_out / deq_out, nz_out. */
+X264_CUDA_API int x264_cuda_block_dc(x264_cuda_t *ctx, int n, const int16_t *dc_in, const uint8_t *qp, const uint8_t *cat,
+                                     int16_t *fwd_out, int16_t *level_out, uint8_t *nz_out, int16_t *deq_out);
+
+/* Frame-batched residual coding of INTER macroblocks: the non-trellis, non-lossless inter branch of x264_macroblock_encode
+ * (S/encoder/macroblock.c:596-742) + x264_mb_encode_8x8_chroma (:272-363).  fdec holds the motion-compensated
+ * prediction of the listed macroblocks on entry (luma + chroma planes) and their reconstruction on return;
+ * coefficient output mirrors h->dct / non_zero_count / cbp of each macroblock. */
+#define X264_CUDA_RESID_8x8DCT   1 /* h->mb.b_transform_8x8 */
+#define X264_CUDA_RESID_DECIMATE 2 /* B slice or param.analyse.b_dct_decimate */
+typedef struct x264_cuda_resid_job_t {
+    int16_t mb_x, mb_y;
+    uint8_t qp, chroma_qp; /* h->mb.i_qp, h->mb.i_chroma_qp */
+    uint8_t flags, reserved;
+} x264_cuda_resid_job_t;     /* 8 bytes */
+typedef struct x264_cuda_mb_coeffs_t {
+    int16_t luma[256];       /* h->dct.luma4x4[0..15] (zigzag, block order) or h->dct.luma8x8[0..3] with 8x8dct; 0 where uncoded */
+    int16_t chroma_ac[8][16];/* h->dct.luma4x4[16..23] */
+    int16_t chroma_dc[2][4]; /* h->dct.chroma_dc */
+    uint8_t nnz[27];         /* non_zero_count[x264_scan8[0..26]] */
+    uint8_t cbp_luma, cbp_chroma, reserved[3];
+} x264_cuda_mb_coeffs_t;     /* 816 bytes */
+X264_CUDA_API int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
+                                           const x264_cuda_resid_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_t *coeffs);
+X264_CUDA_API int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
+                                               const void *d_jobs, int n_jobs, void *d_coeffs);
 
 /* ------------------------------------------------------------------ macroblock-batched motion search - */
 /* One job == ALL inter partition searches of one macroblock against one reference: 16x16, 2x16x8, 2x8x16,

@@ -316,3 +316,79 @@ int xo_quant_2x2_dc(int16_t dct[4], int mf, int bias) { tables(); return g_quant
 void xo_dequant_4x4(int16_t dct[16], const int dequant_mf[6][16], int qp) { tables(); g_quantf.dequant_4x4((void *)dct, (void *)dequant_mf, qp); }
 void xo_dequant_8x8(int16_t dct[64], const int dequant_mf[6][64], int qp) { tables(); g_quantf.dequant_8x8((void *)dct, (void *)dequant_mf, qp); }
 void xo_dequant_4x4_dc(int16_t dct[16], const int dequant_mf[6][16], int qp) { tables(); g_quantf.dequant_4x4_dc((void *)dct, (void *)dequant_mf, qp); }
+
+/* ------------------------------------------------------------------------------------------------ */
+void xo_zigzag_scan_4x4(int16_t level[16], const int16_t dct[16])
+{
+    x264_zigzag_function_t z; x264_zigzag_init(0, &z, 0);
+    z.scan_4x4(level, (void *)dct);
+}
+void xo_zigzag_scan_8x8(int16_t level[64], const int16_t dct[64])
+{
+    x264_zigzag_function_t z; x264_zigzag_init(0, &z, 0);
+    z.scan_8x8(level, (void *)dct);
+}
+int xo_decimate_score(const int16_t *dct, int i_max)
+{
+    tables();
+    return i_max == 15 ? g_quantf.decimate_score15((int16_t *)dct) : i_max == 16 ? g_quantf.decimate_score16((int16_t *)dct)
+                                                                                   : g_quantf.decimate_score64((int16_t *)dct);
+}
+
+/* drives the reference's own x264_macroblock_encode on a hand-loaded inter macroblock (prediction already in
+ * p_fdec, b_skip_mc = 1) */
+#include "encoder/macroblock.h"
+static x264_t *g_res_h[2][2];
+void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                          uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out)
+{
+    x264_t **ph = &g_res_h[!!in->cqm][!!in->b_transform_8x8], *h;
+    if (!*ph) {
+        x264_param_t p;
+        x264_param_default(&p);
+        p.i_width = 64; p.i_height = 64; p.i_threads = 1; p.i_log_level = X264_LOG_NONE;
+        p.rc.i_rc_method = X264_RC_CQP; p.rc.i_qp_constant = 26;
+        p.analyse.b_transform_8x8 = 1; /* tables for both paths */
+        p.analyse.i_trellis = 0; p.analyse.i_noise_reduction = 0;
+        p.i_cqm_preset = in->cqm ? X264_CQM_JVT : X264_CQM_FLAT;
+        *ph = x264_encoder_open(&p);
+        if (!*ph) abort();
+    }
+    h = *ph;
+    h->sh.i_type = SLICE_TYPE_P;
+    h->sh.b_mbaff = 0;
+    h->param.analyse.b_dct_decimate = in->b_decimate;
+    h->mb.i_type = P_L0; h->mb.i_partition = D_16x16;
+    h->mb.b_lossless = 0; h->mb.b_trellis = 0; h->mb.b_noise_reduction = 0; h->mb.b_skip_mc = 1;
+    h->mb.b_transform_8x8 = in->b_transform_8x8;
+    h->mb.i_qp = in->qp; h->mb.i_chroma_qp = in->chroma_qp;
+    h->mb.i_mb_xy = 0; h->mb.i_mb_x = h->mb.i_mb_y = 0;
+    /* make the final P_SKIP test fail so i_type stays P_L0 */
+    h->mb.cache.mv[0][x264_scan8[0]][0] = 4; h->mb.cache.mv[0][x264_scan8[0]][1] = 0;
+    h->mb.cache.pskip_mv[0] = 0; h->mb.cache.pskip_mv[1] = 0;
+    h->mb.cache.ref[0][x264_scan8[0]] = 0;
+    memset(&h->dct, 0, sizeof(h->dct));
+    memset(h->mb.cache.non_zero_count, 0, sizeof(h->mb.cache.non_zero_count));
+    for (int y = 0; y < 16; y++) {
+        memcpy(h->mb.pic.p_fenc[0] + FENC_STRIDE * y, fenc_y + 16 * y, 16);
+        memcpy(h->mb.pic.p_fdec[0] + FDEC_STRIDE * y, rec_y + 16 * y, 16);
+    }
+    for (int y = 0; y < 8; y++) {
+        memcpy(h->mb.pic.p_fenc[1] + FENC_STRIDE * y, fenc_u + 8 * y, 8);
+        memcpy(h->mb.pic.p_fenc[2] + FENC_STRIDE * y, fenc_v + 8 * y, 8);
+        memcpy(h->mb.pic.p_fdec[1] + FDEC_STRIDE * y, rec_u + 8 * y, 8);
+        memcpy(h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, rec_v + 8 * y, 8);
+    }
+    x264_macroblock_encode(h);
+    memset(out, 0, sizeof(*out));
+    memcpy(out->luma4x4, h->dct.luma4x4, sizeof(out->luma4x4));
+    memcpy(out->luma8x8, h->dct.luma8x8, sizeof(out->luma8x8));
+    memcpy(out->chroma_dc, h->dct.chroma_dc, sizeof(out->chroma_dc));
+    for (int i = 0; i < 27; i++) out->nnz[i] = h->mb.cache.non_zero_count[x264_scan8[i]];
+    out->cbp_luma = h->mb.i_cbp_luma; out->cbp_chroma = h->mb.i_cbp_chroma;
+    for (int y = 0; y < 16; y++) memcpy(rec_y + 16 * y, h->mb.pic.p_fdec[0] + FDEC_STRIDE * y, 16);
+    for (int y = 0; y < 8; y++) {
+        memcpy(rec_u + 8 * y, h->mb.pic.p_fdec[1] + FDEC_STRIDE * y, 8);
+        memcpy(rec_v + 8 * y, h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, 8);
+    }
+}

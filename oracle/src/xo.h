@@ -133,6 +133,30 @@ void xo_dequant_4x4(int16_t dct[16], const int dequant_mf[6][16], int qp);
 void xo_dequant_8x8(int16_t dct[64], const int dequant_mf[6][64], int qp);
 void xo_dequant_4x4_dc(int16_t dct[16], const int dequant_mf[6][16], int qp);
 
+/* zigzag (frame) scans, S/common/dct.c:488-560; decimation scores, S/common/quant.c:203-252 (i_max 15|16|64) */
+void xo_zigzag_scan_4x4(int16_t level[16], const int16_t dct[16]);
+void xo_zigzag_scan_8x8(int16_t level[64], const int16_t dct[64]);
+int xo_decimate_score(const int16_t *dct, int i_max);
+
+/* ---------------- residual path of one inter macroblock: S/encoder/macroblock.c:596-742 + :272-363 ----------------
+ * fenc_* packed (16x16, 8x8, 8x8); rec_* hold the prediction on entry and the reconstruction on return. */
+typedef struct {
+    int qp, chroma_qp;
+    int b_transform_8x8;
+    int b_decimate; /* h->sh.i_type == SLICE_TYPE_B || h->param.analyse.b_dct_decimate */
+    int cqm;        /* 0 flat, 1 JVT */
+} xo_resid_in;
+typedef struct {
+    int16_t luma4x4[24][16]; /* h->dct.luma4x4: 16 luma + 8 chroma AC blocks, zigzag order; zero where nothing was coded */
+    int16_t luma8x8[4][64];
+    int16_t chroma_dc[2][4];
+    uint8_t nnz[27];         /* non_zero_count[x264_scan8[i]]: 0..15 luma, 16..23 chroma AC, 24 luma DC, 25/26 chroma DC */
+    uint8_t pad;
+    int cbp_luma, cbp_chroma;
+} xo_resid_out;
+void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                          uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out);
+
 #ifdef __cplusplus
 }
 #endif

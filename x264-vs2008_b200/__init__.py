@@ -10,8 +10,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libx264_cuda.so")
 
 PADH = PADV = 32
-FRAME_HPEL, FRAME_INTEGRAL, FRAME_INTEGRAL4, FRAME_LOWRES = 1, 2, 4, 8
-PLANE_FULL, PLANE_H, PLANE_V, PLANE_C, PLANE_LOWRES, PLANE_INTEGRAL, PLANE_INTEGRAL4 = 0, 1, 2, 3, 4, 8, 9
+FRAME_HPEL, FRAME_INTEGRAL, FRAME_INTEGRAL4, FRAME_LOWRES, FRAME_CHROMA = 1, 2, 4, 8, 16
+PLANE_FULL, PLANE_H, PLANE_V, PLANE_C, PLANE_LOWRES, PLANE_INTEGRAL, PLANE_INTEGRAL4, PLANE_CB, PLANE_CR = 0, 1, 2, 3, 4, 8, 9, 10, 11
+RESID_8x8DCT, RESID_DECIMATE = 1, 2
+RESID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("qp", "u1"), ("chroma_qp", "u1"), ("flags", "u1"), ("reserved", "u1")], align=True)
+MB_COEFFS = np.dtype([("luma", "<i2", (256,)), ("chroma_ac", "<i2", (8, 16)), ("chroma_dc", "<i2", (2, 4)), ("nnz", "u1", (27,)),
+                      ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("reserved", "u1", (3,))], align=True)
+assert RESID_JOB.itemsize == 8 and MB_COEFFS.itemsize == 816
 ME_SEEDED, ME_TESA, ME_FPEL_SATD = 1, 2, 4
 ME_MAX_MVC = 12
 
@@ -68,6 +73,12 @@ def lib():
         L.x264_cuda_frame_plane.restype = vp
         L.x264_cuda_frame_upload.argtypes = [vp, vp, vp, ip, ip, ip]
         L.x264_cuda_frame_upload_dev.argtypes = [vp, vp, vp, ip, ip, ip]
+        L.x264_cuda_frame_upload_chroma.argtypes = [vp, vp, ip, vp, ip, ip, ip]
+        L.x264_cuda_set_quant_preset.argtypes = [vp, ip]
+        L.x264_cuda_block_residual.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_block_dc.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_residual_inter.argtypes = [vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_residual_inter_dev.argtypes = [vp, vp, vp, vp, ip, vp]
         L.x264_cuda_frame_download.argtypes = [vp, vp, ip, vp, ip]
         for n in ("x264_cuda_frame_expand_border", "x264_cuda_frame_filter", "x264_cuda_frame_init_lowres"):
             if hasattr(L, n):
@@ -117,6 +128,12 @@ class Frame:
         cols = pic.shape[1] if cols is None else cols
         self.ctx.check(lib().x264_cuda_frame_upload(self.ctx.h, self.h, pic.ctypes.data, pic.strides[0], cols, rows))
 
+    def upload_chroma(self, cb, cr):
+        for plane, pic in ((PLANE_CB, cb), (PLANE_CR, cr)):
+            assert pic.dtype == np.uint8 and pic.strides[1] == 1
+            self.ctx.check(lib().x264_cuda_frame_upload_chroma(self.ctx.h, self.h, plane, pic.ctypes.data, pic.strides[0],
+                                                               pic.shape[1], pic.shape[0]))
+
     def upload_dev(self, dptr, stride, cols, rows):
         self.ctx.check(lib().x264_cuda_frame_upload_dev(self.ctx.h, self.h, dptr, stride, cols, rows))
 
@@ -133,9 +150,11 @@ class Frame:
         """whole padded plane as a 2-D array (rows -32.., cols -32..)"""
         g = self.g
         lowres = PLANE_LOWRES <= plane < PLANE_LOWRES + 4
-        lines = g.lines_lowres if lowres else g.lines
-        w = (g.width_lowres if lowres else g.mb_width * 16) + 2 * PADH
-        out = np.zeros((lines + 2 * PADV, w), np.uint16 if plane >= PLANE_INTEGRAL else np.uint8)
+        chroma = plane in (PLANE_CB, PLANE_CR)
+        lines = g.lines_lowres if lowres else g.lines // 2 if chroma else g.lines
+        pad = 16 if chroma else PADH
+        w = (g.width_lowres if lowres else g.mb_width * 8 if chroma else g.mb_width * 16) + 2 * pad
+        out = np.zeros((lines + 2 * pad, w), np.uint16 if plane in (PLANE_INTEGRAL, PLANE_INTEGRAL4) else np.uint8)
         self.ctx.check(lib().x264_cuda_frame_download(self.ctx.h, self.h, plane, out.ctypes.data, w))
         return out
 
@@ -193,6 +212,34 @@ class Context:
         res = np.zeros(len(jobs), ME_RESULT)
         self.check(lib().x264_cuda_me_search(self.h, fenc.h, fref.h, me_range, jobs.ctypes.data, len(jobs), res.ctypes.data))
         return res
+
+    def set_quant_preset(self, cqm):
+        self.check(lib().x264_cuda_set_quant_preset(self.h, cqm))
+
+    def block_residual(self, kind, fenc, pred, qp, cat):
+        """packed blocks (n, 16|64) uint8 -> dict(dct, level, nz, recon)"""
+        n, bs = fenc.shape[0], 64 if kind else 16
+        fenc, pred = np.ascontiguousarray(fenc, np.uint8), np.ascontiguousarray(pred, np.uint8)
+        qp, cat = np.ascontiguousarray(qp, np.uint8), np.ascontiguousarray(cat, np.uint8)
+        dct, level = np.zeros((n, bs), np.int16), np.zeros((n, bs), np.int16)
+        nz, recon = np.zeros(n, np.uint8), np.zeros((n, bs), np.uint8)
+        self.check(lib().x264_cuda_block_residual(self.h, kind, n, fenc.ctypes.data, pred.ctypes.data, qp.ctypes.data, cat.ctypes.data,
+                                                  dct.ctypes.data, level.ctypes.data, nz.ctypes.data, recon.ctypes.data))
+        return dict(dct=dct, level=level, nz=nz, recon=recon)
+
+    def block_dc(self, dc, qp, cat):
+        n = dc.shape[0]
+        dc, qp, cat = np.ascontiguousarray(dc, np.int16), np.ascontiguousarray(qp, np.uint8), np.ascontiguousarray(cat, np.uint8)
+        fwd, level, deq, nz = np.zeros((n, 16), np.int16), np.zeros((n, 16), np.int16), np.zeros((n, 16), np.int16), np.zeros(n, np.uint8)
+        self.check(lib().x264_cuda_block_dc(self.h, n, dc.ctypes.data, qp.ctypes.data, cat.ctypes.data, fwd.ctypes.data, level.ctypes.data,
+                                            nz.ctypes.data, deq.ctypes.data))
+        return dict(fwd=fwd, level=level, nz=nz, deq=deq)
+
+    def residual_inter(self, fenc, fdec, jobs):
+        jobs = np.ascontiguousarray(jobs, RESID_JOB)
+        out = np.zeros(len(jobs), MB_COEFFS)
+        self.check(lib().x264_cuda_residual_inter(self.h, fenc.h, fdec.h, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
 
     def me_search_mb(self, fenc, fref, me_range, jobs):
         """jobs: numpy array of ME_MB_JOB (host) -> numpy array of ME_MB_RESULT"""

@@ -18,11 +18,20 @@ struct x264_cuda_t {
     long long launches;
     char err[256];
     int16_t *d_cost_mv[52];       // device copies of p_cost_mv (base pointers, 4*4*2048+1 entries)
+    struct QuantTables *d_qt;     // device quantiser tables (x264_cuda_set_quant_tables)
+    int have_qt8;
     void *d_cost_ptrs;            // device array of the 52 pointers above
     int cost_ptrs_dirty;
     // staging for the host-pointer entry points
     void *d_stage; size_t d_stage_size;
     void *h_stage; size_t h_stage_size; // pinned
+};
+
+struct QuantTables {
+    uint16_t q4mf[4][52][16], q4bias[4][52][16];
+    int dq4[4][6][16];
+    uint16_t q8mf[2][52][64], q8bias[2][52][64];
+    int dq8[2][6][64];
 };
 
 struct x264_cuda_frame_t {
@@ -34,6 +43,9 @@ struct x264_cuda_frame_t {
     uint8_t *plane[4];            // pixel (0,0) of filtered[0..3]
     uint8_t *buf_lowres;
     uint8_t *lowres[4];
+    uint8_t *buf_chroma;          // U then V, each stride_c*(lines/2+2*16)
+    uint8_t *chroma[2];           // pixel (0,0) of U, V
+    int stride_c;
     uint16_t *buf_integral;
     uint16_t *integral;           // element (0,0) of the 8x8-sum plane; the 4x4 plane follows
 };

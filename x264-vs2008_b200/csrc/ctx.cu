@@ -55,6 +55,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 52; i++) cudaFree(ctx->d_cost_mv[i]);
     cudaFree(ctx->d_cost_ptrs);
+    cudaFree(ctx->d_qt);
     cudaFree(ctx->d_stage);
     cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->own_stream);
@@ -131,6 +132,13 @@ extern "C" x264_cuda_frame_t *x264_cuda_frame_new(x264_cuda_t *ctx, int width, i
         for (int i = 0; i < 4; i++)
             f->lowres[i] = f->buf_lowres + i * f->plane_size_lowres + (size_t)g.stride_lowres * PADV + PADH;
     }
+    if (e == cudaSuccess && (flags & X264_CUDA_FRAME_CHROMA)) {
+        f->stride_c = g.stride / 2;
+        const size_t csz = (size_t)f->stride_c * (g.lines / 2 + 2 * 16);
+        e = cudaMalloc(&f->buf_chroma, 2 * csz + 256);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->buf_chroma, 0, 2 * csz + 256, ctx->stream);
+        for (int i = 0; i < 2; i++) f->chroma[i] = f->buf_chroma + i * csz + (size_t)f->stride_c * 16 + 16;
+    }
     if (e == cudaSuccess && (flags & (X264_CUDA_FRAME_INTEGRAL | X264_CUDA_FRAME_INTEGRAL4))) {
         size_t n = f->plane_size * ((flags & X264_CUDA_FRAME_INTEGRAL4) ? 2 : 1);
         e = cudaMalloc(&f->buf_integral, n * sizeof(uint16_t) + 256);
@@ -152,6 +160,7 @@ extern "C" void x264_cuda_frame_delete(x264_cuda_frame_t *f)
     cudaStreamSynchronize(f->ctx->stream);
     cudaFree(f->buf);
     cudaFree(f->buf_lowres);
+    cudaFree(f->buf_chroma);
     cudaFree(f->buf_integral);
     free(f);
 }
@@ -162,6 +171,7 @@ extern "C" void *x264_cuda_frame_plane(const x264_cuda_frame_t *f, int plane)
 {
     if (plane >= 0 && plane < 4) return f->plane[plane];
     if (plane >= X264_CUDA_PLANE_LOWRES && plane < X264_CUDA_PLANE_LOWRES + 4) return f->lowres[plane - X264_CUDA_PLANE_LOWRES];
+    if (plane == X264_CUDA_PLANE_CB || plane == X264_CUDA_PLANE_CR) return f->chroma[plane - X264_CUDA_PLANE_CB];
     if (plane == X264_CUDA_PLANE_INTEGRAL) return f->integral;
     if (plane == X264_CUDA_PLANE_INTEGRAL4)
         return (f->g.flags & X264_CUDA_FRAME_INTEGRAL4) ? f->integral + f->plane_size : nullptr;
@@ -172,6 +182,17 @@ extern "C" int x264_cuda_frame_upload(x264_cuda_t *ctx, x264_cuda_frame_t *f, co
                                       int cols, int rows)
 {
     CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, src, src_stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+extern "C" int x264_cuda_frame_upload_chroma(x264_cuda_t *ctx, x264_cuda_frame_t *f, int plane, const uint8_t *src, int src_stride,
+                                             int cols, int rows)
+{
+    if (!f->buf_chroma || (plane != X264_CUDA_PLANE_CB && plane != X264_CUDA_PLANE_CR)) {
+        snprintf(ctx->err, 256, "x264_cuda_frame_upload_chroma: frame has no chroma plane %d", plane);
+        return -1;
+    }
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(f->chroma[plane - X264_CUDA_PLANE_CB], f->stride_c, src, src_stride, cols, rows,
+                                    cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
 extern "C" int x264_cuda_frame_upload_dev(x264_cuda_t *ctx, x264_cuda_frame_t *f, const void *dsrc, int src_stride,
@@ -190,15 +211,17 @@ extern "C" int x264_cuda_frame_download(x264_cuda_t *ctx, const x264_cuda_frame_
         return -1;
     }
     bool lowres = plane >= X264_CUDA_PLANE_LOWRES && plane < X264_CUDA_PLANE_LOWRES + 4;
-    bool integ = plane >= X264_CUDA_PLANE_INTEGRAL;
+    bool chroma = plane == X264_CUDA_PLANE_CB || plane == X264_CUDA_PLANE_CR;
+    bool integ = plane == X264_CUDA_PLANE_INTEGRAL || plane == X264_CUDA_PLANE_INTEGRAL4;
     int es = integ ? 2 : 1;
-    int stride = lowres ? g.stride_lowres : g.stride;
-    int lines = lowres ? g.lines_lowres : g.lines;
-    int w = lowres ? g.width_lowres : g.mb_width * 16;
-    const uint8_t *src = (const uint8_t *)p00 - ((size_t)stride * PADV + PADH) * es;
-    int cols = w + 2 * PADH;
+    int stride = lowres ? g.stride_lowres : chroma ? f->stride_c : g.stride;
+    int lines = lowres ? g.lines_lowres : chroma ? g.lines / 2 : g.lines;
+    int w = lowres ? g.width_lowres : chroma ? g.mb_width * 8 : g.mb_width * 16;
+    int padh = chroma ? 16 : PADH, padv = chroma ? 16 : PADV;
+    const uint8_t *src = (const uint8_t *)p00 - ((size_t)stride * padv + padh) * es;
+    int cols = w + 2 * padh;
     if (cols > dst_stride) cols = dst_stride;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)dst_stride * es, src, (size_t)stride * es, (size_t)cols * es, lines + 2 * PADV,
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)dst_stride * es, src, (size_t)stride * es, (size_t)cols * es, lines + 2 * padv,
                                     cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -1,0 +1,640 @@
+// residual.cu — batched H.264 integer transforms and (de)quantisation: S/common/dct.c, S/common/quant.c and the
+// inter-macroblock sequencing of S/encoder/macroblock.c:596-742 (+ chroma :272-363).
+//
+// Roofline class: HBM (80 B of traffic per 4x4 block, 320 B per 8x8 block against a few hundred integer ops).
+// Layout conventions follow the reference: coefficient blocks are stored TRANSPOSED (dct[i][k], dct.c:131-154),
+// every intermediate that the reference keeps in an int16_t array is narrowed to int16 at the same point.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int s16(int v) { return (int)(int16_t)v; }
+
+// ---- 4x4 core transform (dct.c:122-155).  d: 16 residuals row-major; out: coefficient block, reference layout
+__device__ __forceinline__ void fwd4x4(const int (&d)[16], int (&o)[16])
+{
+    int t[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int s03 = d[i * 4] + d[i * 4 + 3], s12 = d[i * 4 + 1] + d[i * 4 + 2];
+        const int d03 = d[i * 4] - d[i * 4 + 3], d12 = d[i * 4 + 1] - d[i * 4 + 2];
+        t[0 * 4 + i] = s03 + s12; t[1 * 4 + i] = 2 * d03 + d12; t[2 * 4 + i] = s03 - s12; t[3 * 4 + i] = d03 - 2 * d12;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int s03 = t[i * 4] + t[i * 4 + 3], s12 = t[i * 4 + 1] + t[i * 4 + 2];
+        const int d03 = t[i * 4] - t[i * 4 + 3], d12 = t[i * 4 + 1] - t[i * 4 + 2];
+        o[i * 4 + 0] = s03 + s12; o[i * 4 + 1] = 2 * d03 + d12; o[i * 4 + 2] = s03 - s12; o[i * 4 + 3] = d03 - 2 * d12;
+    }
+}
+// inverse (dct.c:174-216): returns the 16 residuals to add, row-major (d[y][x])
+__device__ __forceinline__ void inv4x4(const int (&c)[16], int (&r)[16])
+{
+    int t[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int s02 = c[0 * 4 + i] + c[2 * 4 + i], d02 = c[0 * 4 + i] - c[2 * 4 + i];
+        const int s13 = c[1 * 4 + i] + (c[3 * 4 + i] >> 1), d13 = (c[1 * 4 + i] >> 1) - c[3 * 4 + i];
+        t[i * 4 + 0] = s16(s02 + s13); t[i * 4 + 1] = s16(d02 + d13); t[i * 4 + 2] = s16(d02 - d13); t[i * 4 + 3] = s16(s02 - s13);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int s02 = t[0 * 4 + i] + t[2 * 4 + i], d02 = t[0 * 4 + i] - t[2 * 4 + i];
+        const int s13 = t[1 * 4 + i] + (t[3 * 4 + i] >> 1), d13 = (t[1 * 4 + i] >> 1) - t[3 * 4 + i];
+        r[0 * 4 + i] = s16((s02 + s13 + 32) >> 6); r[1 * 4 + i] = s16((d02 + d13 + 32) >> 6);
+        r[2 * 4 + i] = s16((d02 - d13 + 32) >> 6); r[3 * 4 + i] = s16((s02 - s13 + 32) >> 6);
+    }
+}
+// quant.c:33-40 on one coefficient
+__device__ __forceinline__ int quant1(int c, int mf, int f) { return s16(c > 0 ? ((f + c) * mf >> 16) : -((f - c) * mf >> 16)); }
+// quant.c:76-109 / :111-146 on one coefficient
+__device__ __forceinline__ int dequant1(int c, int dmf, int qbits)
+{
+    return qbits >= 0 ? s16((c * dmf) << qbits) : s16((c * dmf + (1 << (-qbits - 1))) >> (-qbits));
+}
+
+// ---- 8-point transforms (dct.c:238-263, :295-320)
+__device__ __forceinline__ void fwd8(const int (&s)[8], int (&o)[8])
+{
+    const int s07 = s[0] + s[7], s16_ = s[1] + s[6], s25 = s[2] + s[5], s34 = s[3] + s[4];
+    const int a0 = s07 + s34, a1 = s16_ + s25, a2 = s07 - s34, a3 = s16_ - s25;
+    const int d07 = s[0] - s[7], d16 = s[1] - s[6], d25 = s[2] - s[5], d34 = s[3] - s[4];
+    const int a4 = d16 + d25 + (d07 + (d07 >> 1)), a5 = d07 - d34 - (d25 + (d25 >> 1));
+    const int a6 = d07 + d34 - (d16 + (d16 >> 1)), a7 = d16 - d25 + (d34 + (d34 >> 1));
+    o[0] = a0 + a1; o[1] = a4 + (a7 >> 2); o[2] = a2 + (a3 >> 1); o[3] = a5 + (a6 >> 2);
+    o[4] = a0 - a1; o[5] = a6 - (a5 >> 2); o[6] = (a2 >> 1) - a3; o[7] = (a4 >> 2) - a7;
+}
+__device__ __forceinline__ void inv8(const int (&s)[8], int (&o)[8])
+{
+    const int a0 = s[0] + s[4], a2 = s[0] - s[4], a4 = (s[2] >> 1) - s[6], a6 = (s[6] >> 1) + s[2];
+    const int b0 = a0 + a6, b2 = a2 + a4, b4 = a2 - a4, b6 = a0 - a6;
+    const int a1 = -s[3] + s[5] - s[7] - (s[7] >> 1), a3 = s[1] + s[7] - s[3] - (s[3] >> 1);
+    const int a5 = -s[1] + s[7] + s[5] + (s[5] >> 1), a7 = s[3] + s[5] + s[1] + (s[1] >> 1);
+    const int b1 = (a7 >> 2) + a1, b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5, b7 = a7 - (a1 >> 2);
+    o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1;
+    o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+// sub8x8_dct8 (dct.c:265-285): d row-major residuals -> c in reference layout (c[x*8+i])
+__device__ void fwd8x8(int *d /*64, clobbered*/, int *c)
+{
+    for (int i = 0; i < 8; i++) { // columns, in place
+        int s[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = d[k * 8 + i];
+        fwd8(s, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k * 8 + i] = s16(o[k]);
+    }
+    for (int i = 0; i < 8; i++) { // rows, written transposed
+        int s[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = d[i * 8 + k];
+        fwd8(s, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k * 8 + i] = s16(o[k]);
+    }
+}
+// add8x8_idct8 (dct.c:322-341): c (clobbered) -> r residuals with r[k*8+i] added to pixel (row k, col i)
+__device__ void inv8x8(int *c, int *r)
+{
+    c[0] = s16(c[0] + 32);
+    for (int i = 0; i < 8; i++) {
+        int s[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = c[k * 8 + i];
+        inv8(s, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k * 8 + i] = s16(o[k]);
+    }
+    for (int i = 0; i < 8; i++) {
+        int s[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = c[i * 8 + k];
+        inv8(s, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k * 8 + i] = o[k] >> 6; // dst[i + k*FDEC_STRIDE]
+    }
+}
+
+// ---- zig-zag (frame) orders as flat indices into the reference's transposed blocks (dct.c:488-560)
+__constant__ uint8_t c_zz4[16] = { 0, 4, 1, 2, 5, 8, 12, 9, 6, 3, 7, 10, 13, 14, 11, 15 };
+__constant__ uint8_t c_zz8[64] = { 0,  8,  1,  2,  9,  16, 24, 17, 10, 3,  4,  11, 18, 25, 32, 40, 33, 26, 19, 12, 5,  6,
+                                   13, 20, 27, 34, 41, 48, 56, 49, 42, 35, 28, 21, 14, 7,  15, 22, 29, 36, 43, 50, 57, 58,
+                                   51, 44, 37, 30, 23, 31, 38, 45, 52, 59, 60, 53, 46, 39, 47, 54, 61, 62, 55, 63 };
+__constant__ uint8_t c_dec4[16] = { 3, 2, 2, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+__constant__ uint8_t c_dec8[64] = { 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };
+
+// quant.c:219-252 on a zig-zag ordered block in local memory/registers; first = 1 skips the DC (score15)
+__device__ int decimate_score(const int16_t *lv, int first, int n)
+{
+    const uint8_t *tab = n == 64 ? c_dec8 : c_dec4;
+    int idx = n - 1, score = 0;
+    while (idx >= first && lv[idx] == 0) idx--;
+    while (idx >= first) {
+        if ((unsigned)(lv[idx--] + 1) > 2) return 9;
+        int run = 0;
+        while (idx >= first && lv[idx] == 0) { idx--; run++; }
+        score += tab[run];
+    }
+    return score;
+}
+
+// =========================================================================================================
+// function-level batches over packed blocks
+__global__ void __launch_bounds__(128) block_residual4_kernel(const QuantTables *__restrict__ qt, int n, const uint8_t *__restrict__ fenc,
+                                                              const uint8_t *__restrict__ pred, const uint8_t *__restrict__ qp,
+                                                              const uint8_t *__restrict__ cat, int16_t *dct_out, int16_t *level_out,
+                                                              uint8_t *nz_out, uint8_t *recon_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 fe = __ldg((const uint4 *)fenc + i), pr = __ldg((const uint4 *)pred + i);
+    const uint32_t fw[4] = { fe.x, fe.y, fe.z, fe.w }, pw[4] = { pr.x, pr.y, pr.z, pr.w };
+    int d[16], c[16], p[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        p[k] = (pw[k >> 2] >> (8 * (k & 3))) & 255;
+        d[k] = (int)((fw[k >> 2] >> (8 * (k & 3))) & 255) - p[k];
+    }
+    fwd4x4(d, c);
+    if (dct_out)
+#pragma unroll
+        for (int k = 0; k < 16; k++) dct_out[i * 16 + k] = (int16_t)c[k];
+    const int q = min((int)qp[i], 51), l = cat[i] & 3;
+    const uint16_t *mf = qt->q4mf[l][q], *bias = qt->q4bias[l][q];
+    int nz = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+    if (level_out)
+#pragma unroll
+        for (int k = 0; k < 16; k++) level_out[i * 16 + k] = (int16_t)c[k];
+    if (nz_out) nz_out[i] = nz != 0;
+    if (recon_out) {
+        if (nz) {
+            const int *dmf = qt->dq4[l][q % 6];
+            const int qbits = q / 6 - 4;
+            int r[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+            inv4x4(c, r);
+#pragma unroll
+            for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + r[k]);
+        }
+        uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[k >> 2] |= (uint32_t)p[k] << (8 * (k & 3));
+        ((uint4 *)recon_out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+__global__ void __launch_bounds__(64) block_residual8_kernel(const QuantTables *__restrict__ qt, int n, const uint8_t *__restrict__ fenc,
+                                                             const uint8_t *__restrict__ pred, const uint8_t *__restrict__ qp,
+                                                             const uint8_t *__restrict__ cat, int16_t *dct_out, int16_t *level_out,
+                                                             uint8_t *nz_out, uint8_t *recon_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d[64], c[64];
+    for (int k = 0; k < 64; k++) d[k] = (int)fenc[(size_t)i * 64 + k] - (int)pred[(size_t)i * 64 + k];
+    fwd8x8(d, c);
+    if (dct_out) for (int k = 0; k < 64; k++) dct_out[(size_t)i * 64 + k] = (int16_t)c[k];
+    const int q = min((int)qp[i], 51), l = cat[i] & 1;
+    const uint16_t *mf = qt->q8mf[l][q], *bias = qt->q8bias[l][q];
+    int nz = 0;
+    for (int k = 0; k < 64; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+    if (level_out) for (int k = 0; k < 64; k++) level_out[(size_t)i * 64 + k] = (int16_t)c[k];
+    if (nz_out) nz_out[i] = nz != 0;
+    if (recon_out) {
+        if (nz) {
+            const int *dmf = qt->dq8[l][q % 6];
+            const int qbits = q / 6 - 6;
+            for (int k = 0; k < 64; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+            inv8x8(c, d);
+            for (int k = 0; k < 64; k++) recon_out[(size_t)i * 64 + k] = (uint8_t)clip_u8((int)pred[(size_t)i * 64 + k] + d[k]);
+        } else
+            for (int k = 0; k < 64; k++) recon_out[(size_t)i * 64 + k] = pred[(size_t)i * 64 + k];
+    }
+}
+
+// dct4x4dc / idct4x4dc (dct.c:39-105)
+__device__ __forceinline__ void hadamard_dc(int (&d)[16], bool fwd)
+{
+    int t[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int s01 = d[i * 4] + d[i * 4 + 1], d01 = d[i * 4] - d[i * 4 + 1];
+        const int s23 = d[i * 4 + 2] + d[i * 4 + 3], d23 = d[i * 4 + 2] - d[i * 4 + 3];
+        t[0 * 4 + i] = s16(s01 + s23); t[1 * 4 + i] = s16(s01 - s23); t[2 * 4 + i] = s16(d01 - d23); t[3 * 4 + i] = s16(d01 + d23);
+    }
+    const int r = fwd ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int s01 = t[i * 4] + t[i * 4 + 1], d01 = t[i * 4] - t[i * 4 + 1];
+        const int s23 = t[i * 4 + 2] + t[i * 4 + 3], d23 = t[i * 4 + 2] - t[i * 4 + 3];
+        d[i * 4 + 0] = s16((s01 + s23 + r) >> r); d[i * 4 + 1] = s16((s01 - s23 + r) >> r);
+        d[i * 4 + 2] = s16((d01 - d23 + r) >> r); d[i * 4 + 3] = s16((d01 + d23 + r) >> r);
+    }
+}
+
+__global__ void __launch_bounds__(128) block_dc_kernel(const QuantTables *__restrict__ qt, int n, const int16_t *__restrict__ dc_in,
+                                                       const uint8_t *__restrict__ qp, const uint8_t *__restrict__ cat, int16_t *fwd_out,
+                                                       int16_t *level_out, uint8_t *nz_out, int16_t *deq_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = dc_in[i * 16 + k];
+    hadamard_dc(d, true);
+    if (fwd_out)
+#pragma unroll
+        for (int k = 0; k < 16; k++) fwd_out[i * 16 + k] = (int16_t)d[k];
+    const int q = min((int)qp[i], 51), l = cat[i] & 3;
+    const int mf = qt->q4mf[l][q][0] >> 1, bias = qt->q4bias[l][q][0] << 1; // macroblock.c:250
+    int nz = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { d[k] = quant1(d[k], mf, bias); nz |= d[k]; }
+    if (level_out)
+#pragma unroll
+        for (int k = 0; k < 16; k++) level_out[i * 16 + k] = (int16_t)d[k];
+    if (nz_out) nz_out[i] = nz != 0;
+    if (deq_out) {
+        hadamard_dc(d, false);
+        const int qbits = q / 6 - 6, dmf0 = qt->dq4[l][q % 6][0]; // quant.c:148-178
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            d[k] = qbits >= 0 ? s16(d[k] * (dmf0 << qbits)) : s16((d[k] * dmf0 + (1 << (-qbits - 1))) >> (-qbits));
+#pragma unroll
+        for (int k = 0; k < 16; k++) deq_out[i * 16 + k] = (int16_t)d[k];
+    }
+}
+
+// =========================================================================================================
+// Inter macroblock residual: ONE WARP PER MACROBLOCK.  Lanes 0..15 own the luma 4x4 blocks in the reference's
+// block order (block_idx_x/y, S/common/macroblock.h:195-202) — or lanes 0..3 the four 8x8 blocks with 8x8dct —
+// and lanes 16..23 the chroma AC blocks (U0..3, V0..3).  Decimation sums and the chroma 2x2 DC travel by shuffles.
+struct FrameRefs { const uint8_t *fe_y, *fe_u, *fe_v; uint8_t *fd_y, *fd_u, *fd_v; int stride, stride_c; };
+
+__device__ __forceinline__ void load4x4(const uint8_t *p, int stride, int (&v)[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const uint32_t w = *(const uint32_t *)(p + (size_t)y * stride);
+#pragma unroll
+        for (int x = 0; x < 4; x++) v[y * 4 + x] = (w >> (8 * x)) & 255;
+    }
+}
+__device__ __forceinline__ void store4x4(uint8_t *p, int stride, const int (&v)[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+        *(uint32_t *)(p + (size_t)y * stride) = (uint32_t)v[y * 4] | ((uint32_t)v[y * 4 + 1] << 8) | ((uint32_t)v[y * 4 + 2] << 16) |
+                                                ((uint32_t)v[y * 4 + 3] << 24);
+}
+
+__global__ void __launch_bounds__(128) residual_inter_kernel(const QuantTables *__restrict__ qt, FrameRefs fr,
+                                                             const x264_cuda_resid_job_t *__restrict__ jobs, int n_jobs,
+                                                             x264_cuda_mb_coeffs_t *__restrict__ outs)
+{
+    const int lane = threadIdx.x & 31;
+    const int jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (jb >= n_jobs) return;
+    const x264_cuda_resid_job_t job = jobs[jb];
+    x264_cuda_mb_coeffs_t *out = outs + jb;
+    const int qp = min((int)job.qp, 51), cqp = min((int)job.chroma_qp, 51);
+    const bool dct8 = job.flags & X264_CUDA_RESID_8x8DCT, decim = job.flags & X264_CUDA_RESID_DECIMATE;
+    const unsigned FULL = 0xffffffffu;
+
+    // zero the coefficient record first (uncoded blocks read as zero, like a cleared h->dct)
+    for (int i = lane; i < (int)(sizeof(x264_cuda_mb_coeffs_t) / 4); i += 32) ((uint32_t *)out)[i] = 0;
+    __syncwarp();
+
+    int cbp_luma = 0;
+    // ------------------------------------------------------------------ luma
+    if (!dct8) { // macroblock.c:678-742
+        int nz = 0, score = 0;
+        int c[16], p[16];
+        const int bx = (lane & 1) + ((lane >> 2) & 1) * 2, by = ((lane >> 1) & 1) + ((lane >> 3) & 1) * 2; // block_idx_x/y
+        uint8_t *dst = fr.fd_y + ((size_t)job.mb_y * 16 + by * 4) * fr.stride + job.mb_x * 16 + bx * 4;
+        if (lane < 16) {
+            int f[16], d[16];
+            load4x4(fr.fe_y + ((size_t)job.mb_y * 16 + by * 4) * fr.stride + job.mb_x * 16 + bx * 4, fr.stride, f);
+            load4x4(dst, fr.stride, p);
+#pragma unroll
+            for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
+            fwd4x4(d, c);
+            const uint16_t *mf = qt->q4mf[1][qp], *bias = qt->q4bias[1][qp]; // CQM_4PY
+#pragma unroll
+            for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+            nz = nz != 0;
+            if (nz) {
+                int16_t lv[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) *(uint32_t *)&out->luma[lane * 16 + k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
+                if (decim) score = decimate_score(lv, 0, 16);
+                const int *dmf = qt->dq4[1][qp % 6];
+                const int qbits = qp / 6 - 4;
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+            }
+        }
+        // per 8x8: i_decimate_8x8 accumulates the scores of its blocks in order while it is still < 6 (macroblock.c:704-705)
+        const int base = lane & ~3;
+        int dec8 = 0, any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int s = __shfl_sync(FULL, score, base + k), z = __shfl_sync(FULL, nz, base + k);
+            if (z && dec8 < 6) dec8 += s;
+            any |= z;
+        }
+        int keep8 = decim ? (dec8 >= 4) : any; // this 8x8's cbp bit before the MB-level test
+        int dec_mb = 0, cbp = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            dec_mb += __shfl_sync(FULL, dec8, 4 * k);
+            cbp |= __shfl_sync(FULL, keep8, 4 * k) << k;
+        }
+        if (decim && dec_mb < 6) cbp = 0;
+        cbp_luma = cbp;
+        if (lane < 16) {
+            const int coded = (cbp >> (lane >> 2)) & 1;
+            // nnz: the quant result, cleared for decimated 8x8s / decimated MBs (STORE_8x8_NNZ, :717; :731-735)
+            out->nnz[lane] = (uint8_t)((decim ? coded : 1) && nz);
+            if (coded && nz) { // add8x8_idct adds every block of a coded 8x8; all-zero blocks add nothing
+                int r[16];
+                inv4x4(c, r);
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + r[k]);
+                store4x4(dst, fr.stride, p);
+            }
+        }
+    } else { // macroblock.c:627-677
+        int nz = 0, score = 0;
+        int c[64];
+        uint8_t *dst = fr.fd_y + ((size_t)job.mb_y * 16 + (lane >> 1) * 8) * fr.stride + job.mb_x * 16 + (lane & 1) * 8;
+        if (lane < 4) {
+            int d[64];
+            const uint8_t *src = fr.fe_y + ((size_t)job.mb_y * 16 + (lane >> 1) * 8) * fr.stride + job.mb_x * 16 + (lane & 1) * 8;
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) d[y * 8 + x] = (int)src[(size_t)y * fr.stride + x] - (int)dst[(size_t)y * fr.stride + x];
+            fwd8x8(d, c);
+            const uint16_t *mf = qt->q8mf[1][qp], *bias = qt->q8bias[1][qp]; // CQM_8PY
+            for (int k = 0; k < 64; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+            nz = nz != 0;
+            if (nz) {
+                int16_t lv[64];
+                for (int k = 0; k < 64; k++) lv[k] = (int16_t)c[c_zz8[k]];
+                for (int k = 0; k < 64; k++) out->luma[lane * 64 + k] = lv[k];
+                if (decim) score = decimate_score(lv, 0, 64);
+            }
+        }
+        int dec_mb = 0, cbp = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int s = __shfl_sync(FULL, score, k), z = __shfl_sync(FULL, nz, k);
+            if (z) { dec_mb += decim ? s : 0; if (!decim || s >= 4) cbp |= 1 << k; }
+        }
+        if (decim && dec_mb < 6) cbp = 0;
+        cbp_luma = cbp;
+        if (lane < 4 && ((cbp >> lane) & 1)) {
+            int r[64];
+            const int *dmf = qt->dq8[1][qp % 6];
+            const int qbits = qp / 6 - 6;
+            for (int k = 0; k < 64; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+            inv8x8(c, r);
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) dst[(size_t)y * fr.stride + x] = (uint8_t)clip_u8((int)dst[(size_t)y * fr.stride + x] + r[y * 8 + x]);
+        }
+        if (lane < 16) out->nnz[lane] = (uint8_t)((cbp >> (lane >> 2)) & 1); // STORE_8x8_NNZ
+    }
+
+    // ------------------------------------------------------------------ chroma (b_inter = 1), macroblock.c:272-363
+    {
+        const int cl = lane - 16;                 // 0..7 on the chroma lanes
+        const bool mine = lane >= 16 && lane < 24;
+        const int ch = (cl >> 2) & 1, bi = cl & 3;
+        int c[16], p[16], nz = 0, score = 0, dc0 = 0;
+        const uint8_t *fe = (ch ? fr.fe_v : fr.fe_u) + ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * fr.stride_c + job.mb_x * 8 + (bi & 1) * 4;
+        uint8_t *dst = (ch ? fr.fd_v : fr.fd_u) + ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * fr.stride_c + job.mb_x * 8 + (bi & 1) * 4;
+        if (mine) {
+            int f[16], d[16];
+            load4x4(fe, fr.stride_c, f);
+            load4x4(dst, fr.stride_c, p);
+#pragma unroll
+            for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
+            fwd4x4(d, c);
+            dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
+            const uint16_t *mf = qt->q4mf[3][cqp], *bias = qt->q4bias[3][cqp]; // CQM_4PC
+#pragma unroll
+            for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+            nz = nz != 0;
+            if (nz) {
+                int16_t lv[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
+#pragma unroll
+                for (int k = 0; k < 16; k += 2)
+                    *(uint32_t *)&out->chroma_ac[cl][k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
+                if (decim) score = decimate_score(lv, 1, 16);
+                const int *dmf = qt->dq4[3][cqp % 6];
+                const int qbits = cqp / 6 - 4;
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+            }
+        }
+        // gather the four DCs / scores / nz of this lane's channel
+        const int cb = 16 + ch * 4;
+        const int b0 = __shfl_sync(FULL, dc0, cb), b1 = __shfl_sync(FULL, dc0, cb + 1), b2 = __shfl_sync(FULL, dc0, cb + 2),
+                  b3 = __shfl_sync(FULL, dc0, cb + 3);
+        int tot = 0, nz_ac = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { tot += __shfl_sync(FULL, score, cb + k); nz_ac |= __shfl_sync(FULL, nz, cb + k); }
+        // dct2x2dc: d[0][0], d[1][0], d[0][1], d[1][1] (macroblock.c:72-80), flat order d[0][0],d[0][1],d[1][0],d[1][1]
+        const int e0 = b0 + b1, e1 = b2 + b3, e2 = b0 - b1, e3 = b2 - b3;
+        int dc[4] = { s16(e0 + e1), s16(e0 - e1), s16(e2 + e3), s16(e2 - e3) };
+        const int mf0 = qt->q4mf[3][cqp][0] >> 1, bias0 = qt->q4bias[3][cqp][0] << 1;
+        int nz_dc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { dc[k] = quant1(dc[k], mf0, bias0); nz_dc |= dc[k]; }
+        nz_dc = nz_dc != 0;
+        // IDCT_DEQUANT_START (macroblock.c:42-53)
+        const int g0 = dc[0] + dc[1], g1 = dc[2] + dc[3], g2 = dc[0] - dc[1], g3 = dc[2] - dc[3];
+        int dmf = qt->dq4[3][cqp % 6][0], qbits = cqp / 6 - 5;
+        if (qbits > 0) { dmf <<= qbits; qbits = 0; }
+        const int o4[4] = { s16((g0 + g1) * dmf >> -qbits), s16((g0 - g1) * dmf >> -qbits), s16((g2 + g3) * dmf >> -qbits),
+                            s16((g2 - g3) * dmf >> -qbits) };
+        const bool dc_only = (decim && tot < 7) || !nz_ac;
+        if (mine) {
+            out->nnz[16 + cl] = (uint8_t)(dc_only ? 0 : nz);
+            if (bi == 0) {
+                out->nnz[25 + ch] = (uint8_t)nz_dc;
+                if (nz_dc) { // zigzag_scan_2x2_dc: level[i] = dct[x][y]
+                    out->chroma_dc[ch][0] = (int16_t)dc[0]; out->chroma_dc[ch][1] = (int16_t)dc[2];
+                    out->chroma_dc[ch][2] = (int16_t)dc[1]; out->chroma_dc[ch][3] = (int16_t)dc[3];
+                }
+            }
+            if (dc_only) {
+                if (nz_dc) { // add8x8_idct_dc: block bi gets dct[bi>>1][bi&1] == o4[bi]
+                    const int v = s16((o4[bi] + 32) >> 6);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + v);
+                    store4x4(dst, fr.stride_c, p);
+                }
+            } else {
+                if (nz_dc) c[0] = o4[bi]; // idct_dequant_2x2_dc -> dct4x4[bi][0][0]
+                int r[16];
+                inv4x4(c, r);
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + r[k]);
+                store4x4(dst, fr.stride_c, p);
+            }
+        }
+        const int ac_u = __shfl_sync(FULL, (int)!dc_only, 16), ac_v = __shfl_sync(FULL, (int)!dc_only, 20);
+        const int dcn_u = __shfl_sync(FULL, nz_dc, 16), dcn_v = __shfl_sync(FULL, nz_dc, 20);
+        if (lane == 0) {
+            out->cbp_luma = (uint8_t)cbp_luma;
+            out->cbp_chroma = (uint8_t)((ac_u | ac_v) ? 2 : (dcn_u | dcn_v) ? 1 : 0);
+        }
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int x264_cuda_set_quant_tables(x264_cuda_t *ctx, const uint16_t *const q4mf[4], const uint16_t *const q4bias[4],
+                                          const int *const dq4[4], const uint16_t *const q8mf[2], const uint16_t *const q8bias[2],
+                                          const int *const dq8[2])
+{
+    QuantTables *h = (QuantTables *)calloc(1, sizeof(QuantTables));
+    for (int l = 0; l < 4; l++) {
+        memcpy(h->q4mf[l], q4mf[l], sizeof(h->q4mf[l]));
+        memcpy(h->q4bias[l], q4bias[l], sizeof(h->q4bias[l]));
+        memcpy(h->dq4[l], dq4[l], sizeof(h->dq4[l]));
+    }
+    ctx->have_qt8 = q8mf && q8mf[0] && q8bias && dq8;
+    if (ctx->have_qt8)
+        for (int l = 0; l < 2; l++) {
+            memcpy(h->q8mf[l], q8mf[l], sizeof(h->q8mf[l]));
+            memcpy(h->q8bias[l], q8bias[l], sizeof(h->q8bias[l]));
+            memcpy(h->dq8[l], dq8[l], sizeof(h->dq8[l]));
+        }
+    cudaError_t e = cudaSuccess;
+    if (!ctx->d_qt) e = cudaMalloc(&ctx->d_qt, sizeof(QuantTables));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_qt, h, sizeof(QuantTables), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    free(h);
+    if (e != cudaSuccess) return x264_cuda_fail(ctx, "x264_cuda_set_quant_tables", e);
+    return 0;
+}
+
+extern "C" int x264_cuda_set_quant_preset(x264_cuda_t *ctx, int cqm_preset)
+{
+    QuantTables *h = (QuantTables *)calloc(1, sizeof(QuantTables));
+    x264_cuda_host_cqm_tables(cqm_preset, h->q4mf, h->q4bias, h->dq4, h->q8mf, h->q8bias, h->dq8);
+    const uint16_t *a[4], *b[4], *e[2], *f[2];
+    const int *c[4], *g[2];
+    for (int l = 0; l < 4; l++) { a[l] = &h->q4mf[l][0][0]; b[l] = &h->q4bias[l][0][0]; c[l] = &h->dq4[l][0][0]; }
+    for (int l = 0; l < 2; l++) { e[l] = &h->q8mf[l][0][0]; f[l] = &h->q8bias[l][0][0]; g[l] = &h->dq8[l][0][0]; }
+    int rc = x264_cuda_set_quant_tables(ctx, a, b, c, e, f, g);
+    free(h);
+    return rc;
+}
+
+static int need_tables(x264_cuda_t *ctx, bool want8)
+{
+    if (!ctx->d_qt || (want8 && !ctx->have_qt8)) {
+        snprintf(ctx->err, 256, "x264_cuda: quantiser tables not set (x264_cuda_set_quant_tables)%s", want8 ? " for the 8x8 transform" : "");
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int x264_cuda_block_residual(x264_cuda_t *ctx, int kind, int n, const uint8_t *fenc, const uint8_t *pred, const uint8_t *qp,
+                                        const uint8_t *cat, int16_t *dct_out, int16_t *level_out, uint8_t *nz_out, uint8_t *recon_out)
+{
+    if (n <= 0) return 0;
+    if (need_tables(ctx, kind == 1)) return -1;
+    const size_t bs = kind ? 64 : 16;
+    // device layout: fenc | pred | qp | cat | dct | level | nz | recon
+    size_t off[9], sz[8] = { n * bs, n * bs, (size_t)n, (size_t)n, n * bs * 2, n * bs * 2, (size_t)n, n * bs };
+    off[0] = 0;
+    for (int i = 0; i < 8; i++) off[i + 1] = (off[i] + sz[i] + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, off[8], off[8])) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    memcpy(hs + off[0], fenc, sz[0]); memcpy(hs + off[1], pred, sz[1]); memcpy(hs + off[2], qp, sz[2]); memcpy(hs + off[3], cat, sz[3]);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds, hs, off[4], cudaMemcpyHostToDevice, ctx->stream));
+    if (kind == 0)
+        block_residual4_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_qt, n, ds + off[0], ds + off[1], ds + off[2], ds + off[3],
+                                                                         (int16_t *)(ds + off[4]), (int16_t *)(ds + off[5]), ds + off[6], ds + off[7]);
+    else
+        block_residual8_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_qt, n, ds + off[0], ds + off[1], ds + off[2], ds + off[3],
+                                                                      (int16_t *)(ds + off[4]), (int16_t *)(ds + off[5]), ds + off[6], ds + off[7]);
+    LAUNCH_CHECK(ctx, "block_residual_kernel");
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs + off[4], ds + off[4], off[8] - off[4], cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dct_out) memcpy(dct_out, hs + off[4], sz[4]);
+    if (level_out) memcpy(level_out, hs + off[5], sz[5]);
+    if (nz_out) memcpy(nz_out, hs + off[6], sz[6]);
+    if (recon_out) memcpy(recon_out, hs + off[7], sz[7]);
+    return 0;
+}
+
+extern "C" int x264_cuda_block_dc(x264_cuda_t *ctx, int n, const int16_t *dc_in, const uint8_t *qp, const uint8_t *cat, int16_t *fwd_out,
+                                  int16_t *level_out, uint8_t *nz_out, int16_t *deq_out)
+{
+    if (n <= 0) return 0;
+    if (need_tables(ctx, false)) return -1;
+    size_t off[8], sz[7] = { (size_t)n * 32, (size_t)n, (size_t)n, (size_t)n * 32, (size_t)n * 32, (size_t)n, (size_t)n * 32 };
+    off[0] = 0;
+    for (int i = 0; i < 7; i++) off[i + 1] = (off[i] + sz[i] + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, off[7], off[7])) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    memcpy(hs + off[0], dc_in, sz[0]); memcpy(hs + off[1], qp, sz[1]); memcpy(hs + off[2], cat, sz[2]);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds, hs, off[3], cudaMemcpyHostToDevice, ctx->stream));
+    block_dc_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_qt, n, (const int16_t *)(ds + off[0]), ds + off[1], ds + off[2],
+                                                              (int16_t *)(ds + off[3]), (int16_t *)(ds + off[4]), ds + off[5], (int16_t *)(ds + off[6]));
+    LAUNCH_CHECK(ctx, "block_dc_kernel");
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs + off[3], ds + off[3], off[7] - off[3], cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (fwd_out) memcpy(fwd_out, hs + off[3], sz[3]);
+    if (level_out) memcpy(level_out, hs + off[4], sz[4]);
+    if (nz_out) memcpy(nz_out, hs + off[5], sz[5]);
+    if (deq_out) memcpy(deq_out, hs + off[6], sz[6]);
+    return 0;
+}
+
+extern "C" int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec, const void *d_jobs,
+                                            int n_jobs, void *d_coeffs)
+{
+    if (n_jobs <= 0) return 0;
+    if (need_tables(ctx, true)) return -1;
+    if (!fenc->buf_chroma || !fdec->buf_chroma || fenc->g.stride != fdec->g.stride) {
+        snprintf(ctx->err, 256, "x264_cuda_residual_inter: frames need X264_CUDA_FRAME_CHROMA and equal geometry");
+        return -1;
+    }
+    FrameRefs fr = { fenc->plane[0], fenc->chroma[0], fenc->chroma[1], fdec->plane[0], fdec->chroma[0], fdec->chroma[1], fenc->g.stride,
+                     fenc->stride_c };
+    residual_inter_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_qt, fr, (const x264_cuda_resid_job_t *)d_jobs, n_jobs,
+                                                                     (x264_cuda_mb_coeffs_t *)d_coeffs);
+    LAUNCH_CHECK(ctx, "residual_inter_kernel");
+    return 0;
+}
+
+extern "C" int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
+                                        const x264_cuda_resid_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_t *coeffs)
+{
+    if (n_jobs <= 0) return 0;
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_resid_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_mb_coeffs_t);
+    const size_t jb_al = (jb + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, jb_al + rb, jb_al + rb)) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    memcpy(hs, jobs, jb);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds, hs, jb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x264_cuda_residual_inter_dev(ctx, fenc, fdec, ds, n_jobs, ds + jb_al)) return -1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs + jb_al, ds + jb_al, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(coeffs, hs + jb_al, rb);
+    return 0;
+}

@@ -25,3 +25,59 @@ void x264_cuda_host_cost_mv(int qp, int16_t *table)
         centre[i] = centre[-i] = lambda * (l2 / (log((double)2)) * 2 + 0.718f + !!i) + .5f;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Quantiser tables as x264_cqm_init builds them (S/common/set.c:28-66 constants, :68-174 derivation), for the
+ * flat and JVT presets with the default deadzones (inter 21, intra 11: S/common/common.c:129-130).  In a drop-in
+ * integration the tables of the live x264_t are uploaded instead (x264_cuda_set_quant_tables). */
+static const uint8_t k_dequant4[6][3] = { { 10, 13, 16 }, { 11, 14, 18 }, { 13, 16, 20 }, { 14, 18, 23 }, { 16, 20, 25 }, { 18, 23, 29 } };
+static const uint16_t k_quant4[6][3] = { { 13107, 8066, 5243 }, { 11916, 7490, 4660 }, { 10082, 6554, 4194 },
+                                         { 9362, 5825, 3647 },  { 8192, 5243, 3355 },  { 7282, 4559, 2893 } };
+static const uint8_t k_scan8[16] = { 0, 3, 4, 3, 3, 1, 5, 1, 4, 5, 2, 5, 3, 1, 5, 1 };
+static const uint8_t k_dequant8[6][6] = { { 20, 18, 32, 19, 25, 24 }, { 22, 19, 35, 21, 28, 26 }, { 26, 23, 42, 24, 33, 31 },
+                                          { 28, 25, 45, 26, 35, 33 }, { 32, 28, 51, 30, 40, 38 }, { 36, 32, 58, 34, 46, 43 } };
+static const uint16_t k_quant8[6][6] = { { 13107, 11428, 20972, 12222, 16777, 15481 }, { 11916, 10826, 19174, 11058, 14980, 14290 },
+                                         { 10082, 8943, 15978, 9675, 12710, 11985 },   { 9362, 8228, 14913, 8931, 11984, 11259 },
+                                         { 8192, 7346, 13159, 7740, 10486, 9777 },     { 7282, 6428, 11570, 6830, 9118, 8640 } };
+/* JVT default matrices (S/common/set.h:168-203) */
+static const uint8_t k_jvt4i[16] = { 6, 13, 20, 28, 13, 20, 28, 32, 20, 28, 32, 37, 28, 32, 37, 42 };
+static const uint8_t k_jvt4p[16] = { 10, 14, 20, 24, 14, 20, 24, 27, 20, 24, 27, 30, 24, 27, 30, 34 };
+static const uint8_t k_jvt8i[64] = { 6,  10, 13, 16, 18, 23, 25, 27, 10, 11, 16, 18, 23, 25, 27, 29, 13, 16, 18, 23, 25, 27,
+                                     29, 31, 16, 18, 23, 25, 27, 29, 31, 33, 18, 23, 25, 27, 29, 31, 33, 36, 23, 25, 27, 29,
+                                     31, 33, 36, 38, 25, 27, 29, 31, 33, 36, 38, 40, 27, 29, 31, 33, 36, 38, 40, 42 };
+static const uint8_t k_jvt8p[64] = { 9,  13, 15, 17, 19, 21, 22, 24, 13, 13, 17, 19, 21, 22, 24, 25, 15, 17, 19, 21, 22, 24,
+                                     25, 27, 17, 19, 21, 22, 24, 25, 27, 28, 19, 21, 22, 24, 25, 27, 28, 30, 21, 22, 24, 25,
+                                     27, 28, 30, 32, 22, 24, 25, 27, 28, 30, 32, 33, 24, 25, 27, 28, 30, 32, 33, 35 };
+
+static int round_div(int n, int d) { return (n + (d >> 1)) / d; }
+static int round_shift(int x, int s) { return s < 0 ? x << -s : s == 0 ? x : (x + (1 << (s - 1))) >> s; }
+
+void x264_cuda_host_cqm_tables(int cqm_preset, uint16_t q4mf[4][52][16], uint16_t q4bias[4][52][16], int dq4[4][6][16],
+                               uint16_t q8mf[2][52][64], uint16_t q8bias[2][52][64], int dq8[2][6][64])
+{
+    static const int deadzone[4] = { 32 - 11, 32 - 21, 32 - 11, 32 - 21 }; /* 4IY, 4PY, 4IC, 4PC (set.c:77-79) */
+    for (int list = 0; list < 4; list++)
+        for (int i = 0; i < 16; i++) {
+            const int sl = cqm_preset ? ((list & 1) ? k_jvt4p[i] : k_jvt4i[i]) : 16;
+            const int k = (i & 1) + ((i >> 2) & 1);
+            for (int q = 0; q < 6; q++) dq4[list][q][i] = k_dequant4[q][k] * sl;
+            for (int qp = 0; qp < 52; qp++) {
+                const int j = round_shift(round_div(k_quant4[qp % 6][k] * 16, sl), qp / 6 - 1);
+                const int b = round_div(deadzone[list] << 10, j), cap = (1 << 15) / j;
+                q4mf[list][qp][i] = (uint16_t)j;
+                q4bias[list][qp][i] = (uint16_t)(b < cap ? b : cap);
+            }
+        }
+    for (int list = 0; list < 2; list++)
+        for (int i = 0; i < 64; i++) {
+            const int sl = cqm_preset ? (list ? k_jvt8p[i] : k_jvt8i[i]) : 16;
+            const int k = k_scan8[((i >> 1) & 12) | (i & 3)];
+            for (int q = 0; q < 6; q++) dq8[list][q][i] = k_dequant8[q][k] * sl;
+            for (int qp = 0; qp < 52; qp++) {
+                const int j = round_shift(round_div(k_quant8[qp % 6][k] * 16, sl), qp / 6);
+                const int b = round_div(deadzone[list] << 10, j), cap = (1 << 15) / j;
+                q8mf[list][qp][i] = (uint16_t)j;
+                q8bias[list][qp][i] = (uint16_t)(b < cap ? b : cap);
+            }
+        }
+}
