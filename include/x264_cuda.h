@@ -116,6 +116,7 @@ X264_CUDA_API int x264_cuda_host_lambda(int qp);
 #define X264_CUDA_ME_SEEDED 1 /* skip the predictor stage: (seed_mv, seed_cost) are bmx,bmy,bcost at me.c:229 */
 #define X264_CUDA_ME_TESA   2 /* TESA candidate thresholds + final fpelcmp pass (me.c:491-578) */
 #define X264_CUDA_ME_FPEL_SATD 4 /* fpelcmp is SATD (mbcmp_init, S/encoder/encoder.c:608-618) */
+#define X264_CUDA_ME_MBCMP_SATD 8 /* mbcmp is SATD (user subme > 1) */
 typedef struct x264_cuda_me_job_t {
     int16_t bx, by;              /* block position in luma pixels */
     uint8_t i_pixel;             /* X264_CUDA_PIXEL_* */
@@ -128,7 +129,9 @@ typedef struct x264_cuda_me_job_t {
     int16_t seed_mv[2];          /* only with X264_CUDA_ME_SEEDED */
     int32_t seed_cost;
     int16_t mvc[X264_CUDA_ME_MAX_MVC][2]; /* extra predictors (qpel) */
-} x264_cuda_me_job_t;            /* 76 bytes */
+    int16_t mv_min_spel[2];      /* h->mb.mv_min_spel / mv_max_spel: used by x264_cuda_me_search_small (sub-pel stages) */
+    int16_t mv_max_spel[2];
+} x264_cuda_me_job_t;            /* 84 bytes */
 
 typedef struct x264_cuda_me_result_t {
     int16_t bmx, bmy;            /* full-pel winner at me.c:601 */
@@ -147,6 +150,35 @@ X264_CUDA_API int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_fram
 /* m->mv / m->cost / m->cost_mv from a result, i.e. me.c:603-630 for i_subpel_refine < 2 (host arithmetic) */
 X264_CUDA_API void x264_cuda_me_finish(const x264_cuda_me_job_t *job, const x264_cuda_me_result_t *res,
                                        const int16_t *cost_table, int mv_max_spel_y, int16_t mv[2], int *cost, int *cost_mv);
+
+/* ------------------------------------------------------------------ iterative + sub-pel search -------- */
+/* One job == one complete x264_me_search_ref() (S/encoder/me.c:156-631) for the small iterative methods, or the tail
+ * of one for ESA/TESA:
+ *   method X264_CUDA_ME_METHOD_DIA / _HEX : predictor stage (full-pel for subme < 3, quarter-pel via get_ref for
+ *       subme >= 3: me.c:188-229), the search loop (me.c:233-305), "-> qpel mv" (:603-620), refine_subpel (:622-628,
+ *       :680-778; b_chroma_me = 0);
+ *   method X264_CUDA_ME_METHOD_SEEDED     : job.seed_mv/seed_cost carry the full-pel winner of x264_cuda_me_search
+ *       (ESA/TESA, subme < 3 predictor stage) and only ":603-631" runs.
+ * fref must have the half-pel planes (X264_CUDA_FRAME_HPEL, x264_cuda_frame_filter) when subme >= 2. */
+enum { X264_CUDA_ME_METHOD_DIA = 0, X264_CUDA_ME_METHOD_HEX = 1, X264_CUDA_ME_METHOD_SEEDED = 8 };
+typedef struct x264_cuda_me_final_t {
+    int16_t mv[2];               /* m->mv (qpel) */
+    int32_t cost;                /* m->cost */
+    int32_t cost_mv;             /* m->cost_mv */
+    int16_t bmx, bmy;            /* full-pel winner before the sub-pel stages */
+} x264_cuda_me_final_t;          /* 16 bytes */
+X264_CUDA_API int x264_cuda_me_search_small(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                            int method, int me_range, int subme, const x264_cuda_me_job_t *jobs, int n_jobs,
+                                            x264_cuda_me_final_t *results);
+X264_CUDA_API int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                                int method, int me_range, int subme, const void *d_jobs, int n_jobs,
+                                                void *d_results);
+
+/* Function-level block metrics over PACKED operands (checkasm-style, S/tools/checkasm.c:222-295): block i of pix1 and
+ * pix2 is a 16x16 byte tile (stride 16) whose top-left w x h corner is compared.  metric: 0 SAD, 1 SSD, 2 SATD, 3 SA8D
+ * (16x16 and 8x8 only, like the reference table). */
+X264_CUDA_API int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel, int n, const uint8_t *pix1, const uint8_t *pix2,
+                                      int *out);
 
 /* ------------------------------------------------------------------ transform / quantisation --------- */
 /* Quantiser tables exactly as x264_cqm_init leaves them in x264_t (S/common/set.c:68-174, S/common/common.h:294-304):

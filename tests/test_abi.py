@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol(pkg):
 
 
 def test_struct_sizes_match_header(pkg):
-    assert pkg.ME_JOB.itemsize == 76 and pkg.ME_RESULT.itemsize == 16
+    assert pkg.ME_JOB.itemsize == 84 and pkg.ME_RESULT.itemsize == 16 and pkg.ME_FINAL.itemsize == 16
+    assert pkg.ME_MB_JOB.itemsize == 280 and pkg.MB_COEFFS.itemsize == 816 and pkg.RESID_JOB.itemsize == 8
 
 
 def test_host_cost_table_matches_oracle(pkg, port):

@@ -1,0 +1,88 @@
+"""gpu: DIA / HEX searches, '-> qpel mv' and refine_subpel (x264_cuda_me_search_small) and the packed block metrics,
+vs the oracle, bit-exact"""
+import numpy as np
+import pytest
+import xo_api as X
+from helpers import make_me_jobs
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(pkg, ctx, port, w, h, seed):
+    from x264_vs2008_b200 import synth
+    clip = synth.Clip(w, h, seed=seed)
+    g = port.geometry(w, h)
+    fenc, fref = ctx.frame(w, h, 0), ctx.frame(w, h, pkg.FRAME_HPEL)
+    fenc.upload(clip.luma(1)); fenc.expand_border()
+    fref.upload(clip.luma(0)); fref.expand_border(); fref.filter()
+    pe, pr = port.plane_from_picture(g, clip.luma(1)), port.plane_from_picture(g, clip.luma(0))
+    fh, fv, fc, _ = port.frame_filter(g, pr, 0, want_integral=False)
+    return g, fenc, fref, pe, [pr, fh, fv, fc]
+
+
+def _fill_spel(jobs, mis):
+    for j, mi in zip(jobs, mis):
+        j["mv_min_spel"] = [mi.mv_min_spel[0], mi.mv_min_spel[1]]
+        j["mv_max_spel"] = [mi.mv_max_spel[0], mi.mv_max_spel[1]]
+
+
+@pytest.mark.parametrize("method", [X.ME_DIA, X.ME_HEX])
+@pytest.mark.parametrize("subme", [1, 2, 3, 4, 5, 7])
+def test_small_search(pkg, ctx, port, method, subme):
+    w, h = 320, 192
+    g, fenc, fref, pe, planes = _setup(pkg, ctx, port, w, h, seed=40 + subme)
+    for mbcmp_satd in (0, 1):
+        jobs, mis = make_me_jobs(pkg, g, seed=100 * method + subme, n=400, me_range=16, qp=(12, 26, 38), pixels=(0, 1, 2, 3, 4, 5, 6),
+                                 mvp_spread=40)
+        _fill_spel(jobs, mis)
+        jobs["flags"] = pkg.ME_MBCMP_SATD if mbcmp_satd else 0
+        res = ctx.me_search_small(fenc, fref, method, 16, subme, jobs)
+        bad = []
+        for i, mi in enumerate(mis):
+            mi.me_method = method
+            o = port.me_search_subpel(g, pe, planes, None, mi, subme, mbcmp_satd)
+            got = (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"]), int(res[i]["bmx"]), int(res[i]["bmy"]))
+            want = (o.mv[0], o.mv[1], o.cost, o.cost_mv, o.bmx, o.bmy)
+            if got != want:
+                bad.append((i, mi.i_pixel, got, want))
+        assert not bad, (mbcmp_satd, len(bad), bad[:4])
+    fenc.close(); fref.close()
+
+
+@pytest.mark.parametrize("subme", [1, 2])
+def test_esa_then_subpel(pkg, ctx, port, subme):
+    """full x264_me_search_ref for --me esa: ESA kernel -> seeded small-search kernel (me.c:603-631)"""
+    w, h = 320, 192
+    g, fenc, fref, pe, planes = _setup(pkg, ctx, port, w, h, seed=77)
+    jobs, mis = make_me_jobs(pkg, g, seed=5, n=400, me_range=16, qp=(20, 30), pixels=(0, 1, 2, 3))
+    _fill_spel(jobs, mis)
+    jobs["flags"] = pkg.ME_MBCMP_SATD
+    fp = ctx.me_search(fenc, fref, 16, jobs)
+    j2 = jobs.copy()
+    j2["seed_mv"][:, 0], j2["seed_mv"][:, 1], j2["seed_cost"] = fp["bmx"], fp["bmy"], fp["bcost"]
+    res = ctx.me_search_small(fenc, fref, pkg.ME_METHOD_SEEDED, 16, subme, j2)
+    for i, mi in enumerate(mis):
+        o = port.me_search_subpel(g, pe, planes, None, mi, subme, 1)
+        assert (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"])) == (o.mv[0], o.mv[1], o.cost, o.cost_mv), i
+    fenc.close(); fref.close()
+
+
+def test_block_cmp(pkg, ctx, port):
+    """checkasm-style (checkasm.c:222-295): random tiles + the max-difference 'overflow' patterns"""
+    rng = np.random.default_rng(8)
+    n = 600
+    a = rng.integers(0, 256, (n, 16, 16), dtype=np.uint8)
+    b = rng.integers(0, 256, (n, 16, 16), dtype=np.uint8)
+    yy, xx = np.mgrid[0:16, 0:16]
+    a[0], b[0] = 0, 255
+    a[1], b[1] = ((xx + yy) & 1) * 255, ((xx + yy + 1) & 1) * 255
+    a[2], b[2] = (xx & 1) * 255, (yy & 1) * 255
+    a[3], b[3] = ((xx >> 1) & 1) * 255, ((yy >> 2) & 1) * 255
+    a[4] = b[4]
+    for metric in range(4):
+        for ip in range(7):
+            if metric == X.SA8D and ip not in (0, 3):
+                continue
+            got = ctx.block_cmp(metric, ip, a, b)
+            want = [port.pixel_cmp(metric, ip, a[i], 16, b[i], 16) for i in range(n)]
+            assert list(got) == want, (metric, ip)

@@ -29,7 +29,11 @@ class Geom(C.Structure):
 # numpy mirrors of x264_cuda_me_job_t / x264_cuda_me_result_t (include/x264_cuda.h)
 ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1"), ("i_mvc", "u1"), ("flags", "u1"),
                    ("mvp", "<i2", (2,)), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
-                   ("seed_mv", "<i2", (2,)), ("seed_cost", "<i4"), ("mvc", "<i2", (ME_MAX_MVC, 2))], align=True)
+                   ("seed_mv", "<i2", (2,)), ("seed_cost", "<i4"), ("mvc", "<i2", (ME_MAX_MVC, 2)),
+                   ("mv_min_spel", "<i2", (2,)), ("mv_max_spel", "<i2", (2,))], align=True)
+ME_FINAL = np.dtype([("mv", "<i2", (2,)), ("cost", "<i4"), ("cost_mv", "<i4"), ("bmx", "<i2"), ("bmy", "<i2")], align=True)
+ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_SEEDED = 0, 1, 8
+ME_MBCMP_SATD = 8
 ME_RESULT = np.dtype([("bmx", "<i2"), ("bmy", "<i2"), ("bcost", "<i4"), ("seed_mx", "<i2"), ("seed_my", "<i2"),
                       ("seed_cost", "<i4")], align=True)
 ME_MB_PARTS, ME_MB_MVC = 9, 4
@@ -40,7 +44,7 @@ ME_MB_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("part_mask", "<u2"), ("
                       ("reserved", "u1", (3,)), ("mvp", "<i2", (ME_MB_PARTS, 2)), ("mvc", "<i2", (ME_MB_PARTS, ME_MB_MVC, 2)),
                       ("seed_mv", "<i2", (ME_MB_PARTS, 2)), ("seed_cost", "<i4", (ME_MB_PARTS,))], align=True)
 ME_MB_RESULT = np.dtype([("part", ME_RESULT, (ME_MB_PARTS,))], align=True)
-assert ME_JOB.itemsize == 76 and ME_RESULT.itemsize == 16
+assert ME_JOB.itemsize == 84 and ME_RESULT.itemsize == 16 and ME_FINAL.itemsize == 16
 assert ME_MB_JOB.itemsize == 280 and ME_MB_RESULT.itemsize == 144
 
 _lib = None
@@ -89,6 +93,9 @@ def lib():
         L.x264_cuda_me_search.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_search_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_search_mb.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_me_search_small.argtypes = [vp, vp, vp, ip, ip, ip, vp, ip, vp]
+        L.x264_cuda_me_search_small_dev.argtypes = [vp, vp, vp, ip, ip, ip, vp, ip, vp]
+        L.x264_cuda_block_cmp.argtypes = [vp, ip, ip, ip, vp, vp, vp]
         L.x264_cuda_me_search_mb_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         _lib = L
     return _lib
@@ -239,6 +246,23 @@ class Context:
         jobs = np.ascontiguousarray(jobs, RESID_JOB)
         out = np.zeros(len(jobs), MB_COEFFS)
         self.check(lib().x264_cuda_residual_inter(self.h, fenc.h, fdec.h, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
+
+    def me_search_small(self, fenc, fref, method, me_range, subme, jobs):
+        jobs = np.ascontiguousarray(jobs, ME_JOB)
+        for qp in np.unique(jobs["qp"]):
+            if int(qp) not in self._qps:
+                self.set_cost_mv(int(qp))
+        res = np.zeros(len(jobs), ME_FINAL)
+        self.check(lib().x264_cuda_me_search_small(self.h, fenc.h, fref.h, method, me_range, subme, jobs.ctypes.data, len(jobs),
+                                                   res.ctypes.data))
+        return res
+
+    def block_cmp(self, metric, i_pixel, pix1, pix2):
+        """pix1, pix2: (n, 16, 16) uint8 tiles -> int32[n]"""
+        pix1, pix2 = np.ascontiguousarray(pix1, np.uint8), np.ascontiguousarray(pix2, np.uint8)
+        out = np.zeros(pix1.shape[0], np.int32)
+        self.check(lib().x264_cuda_block_cmp(self.h, metric, i_pixel, pix1.shape[0], pix1.ctypes.data, pix2.ctypes.data, out.ctypes.data))
         return out
 
     def me_search_mb(self, fenc, fref, me_range, jobs):
