@@ -86,3 +86,34 @@ def test_block_cmp(pkg, ctx, port):
             got = ctx.block_cmp(metric, ip, a, b)
             want = [port.pixel_cmp(metric, ip, a[i], 16, b[i], 16) for i in range(n)]
             assert list(got) == want, (metric, ip)
+
+
+@pytest.mark.parametrize("me_range,subme,fpel_satd", [(16, 1, 0), (16, 2, 1), (16, 7, 1), (8, 1, 0), (24, 2, 1), (32, 1, 0)])
+def test_tesa(pkg, ctx, port, me_range, subme, fpel_satd):
+    """--me tesa end to end on the device: ADS/SAD thresholds, keeper list, SATD on the keepers, sub-pel tail"""
+    from x264_vs2008_b200 import synth
+    w, h = 320, 192
+    clip = synth.Clip(w, h, seed=61)
+    g = port.geometry(w, h)
+    fenc = ctx.frame(w, h, 0)
+    fref = ctx.frame(w, h, pkg.FRAME_HPEL | pkg.FRAME_INTEGRAL | pkg.FRAME_INTEGRAL4)
+    fenc.upload(clip.luma(1)); fenc.expand_border()
+    fref.upload(clip.luma(0)); fref.expand_border(); fref.filter()
+    pe, pr = port.plane_from_picture(g, clip.luma(1)), port.plane_from_picture(g, clip.luma(0))
+    fh, fv, fc, integ = port.frame_filter(g, pr, 1)
+    jobs, mis = make_me_jobs(pkg, g, seed=me_range + subme, n=400, me_range=me_range, qp=(12, 26, 38), pixels=(0, 1, 2, 3, 4, 5, 6),
+                             tesa=True, fpel_satd=bool(fpel_satd))
+    _fill_spel(jobs, mis)
+    mbs = 1 if subme > 1 else 0
+    jobs["flags"] = (pkg.ME_FPEL_SATD if fpel_satd else 0) | (pkg.ME_MBCMP_SATD if mbs else 0)
+    res = ctx.me_search_small(fenc, fref, pkg.ME_METHOD_TESA, me_range, subme, jobs)
+    bad = []
+    for i, mi in enumerate(mis):
+        mi.b_sub8x8 = 1
+        o = port.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, mbs)
+        got = (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"]), int(res[i]["bmx"]), int(res[i]["bmy"]))
+        want = (o.mv[0], o.mv[1], o.cost, o.cost_mv, o.bmx, o.bmy)
+        if got != want:
+            bad.append((i, mi.i_pixel, got, want))
+    assert not bad, (len(bad), bad[:4])
+    fenc.close(); fref.close()

@@ -23,6 +23,7 @@ struct x264_cuda_t {
     void *d_cost_ptrs;            // device array of the 52 pointers above
     int cost_ptrs_dirty;
     // staging for the host-pointer entry points
+    void *d_scratch; size_t d_scratch_size; // kernel-private scratch (TESA candidate lists)
     void *d_stage; size_t d_stage_size;
     void *h_stage; size_t h_stage_size; // pinned
 };

@@ -57,6 +57,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_cost_ptrs);
     cudaFree(ctx->d_qt);
     cudaFree(ctx->d_stage);
+    cudaFree(ctx->d_scratch);
     cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->own_stream);
     free(ctx);

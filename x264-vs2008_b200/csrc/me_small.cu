@@ -18,6 +18,11 @@ struct SearchCtx {
     int bw, bh, U, units;         // block size, lanes per candidate (pow2), units in the block
     const int16_t *cmx, *cmy;     // p_cost_mv - mvp
     bool fpel_satd, mbcmp_satd;
+    // TESA only
+    const uint16_t *sums8, *sums4; // integral planes at the block origin (8x8 and 4x4 box sums)
+    int lines_pad;                 // unused
+    int2 *list; int list_cap;      // candidate list scratch: (sad, mx | my << 16)
+    int i_pixel;
 };
 
 // cost of THIS lane's candidate (qpel mv), identical on all lanes of the group; invalid candidates return COST_MAX+1
@@ -62,6 +67,149 @@ __device__ __forceinline__ int scan_fpel(const SearchCtx &c, int lane, const Tab
         }
     }
     return best_k;
+}
+
+// candidate-list accessors: the list is written and read by DIFFERENT lanes of the warp between __syncwarp()s; volatile
+// keeps every access a real memory operation (no register caching across the barriers)
+__device__ __forceinline__ int2 list_get(const int2 *l, int i) { const volatile int *p = (const volatile int *)(l + i); return make_int2(p[0], p[1]); }
+__device__ __forceinline__ void list_put(int2 *l, int i, int2 v) { volatile int *p = (volatile int *)(l + i); p[0] = v.x; p[1] = v.y; }
+
+// ---- TESA candidate selection, me.c:491-578: ADS threshold, SAD threshold, keep the best few, fpelcmp on those.
+// Kept __noinline__ on purpose: when inlined into warp_search, ptxas (12.9, -O1 and up) produced code that dropped the
+// second ADS term for 4x8 blocks (caught by tests/test_gpu_me_small.py::test_tesa; -Xptxas -O0 and the out-of-line
+// form are both correct).
+__device__ __noinline__ void tesa_search(const SearchCtx &c, const x264_cuda_me_job_t &job, int me_range, int lane, int &bcost, int &bmx, int &bmy)
+{
+    const int x_min = job.mv_min_fpel[0], y_min = job.mv_min_fpel[1], x_max = job.mv_max_fpel[0], y_max = job.mv_max_fpel[1];
+    const int min_x = max(bmx - me_range, x_min), min_y = max(bmy - me_range, y_min);
+    const int max_x = min(bmx + me_range, x_max), max_y = min(bmy + me_range, y_max);
+    const int width = (max_x - min_x + 3) & ~3;
+    const int stride = c.stride, ip = c.i_pixel;
+    // enc_dc: pixel sums of the fenc sub-blocks (sad_x4 against zero, me.c:481-489)
+    const int small = ip > X264_CUDA_PIXEL_8x8;         // 4x4 sums
+    const int d = small ? 4 : 8;
+    const int terms = ip == X264_CUDA_PIXEL_16x16 ? 4 : (ip == X264_CUDA_PIXEL_8x8 || ip == X264_CUDA_PIXEL_4x4) ? 1 : 2;
+    const bool vertical2 = ip == X264_CUDA_PIXEL_8x16 || ip == X264_CUDA_PIXEL_4x8; // second term below, not beside
+    int dc0, dc1, dc2, dc3;
+    {
+        // lane l < 4 sums sub-block l (only the ones inside the block are ever used)
+        int v = 0;
+        const int sx = (lane & 1) * d, sy = ((lane >> 1) & 1) * d;
+        if (lane < 4 && sx < c.bw && sy < c.bh)
+            for (int y = 0; y < d; y++)
+                for (int x = 0; x < d; x += 4) v = (int)sad4_acc(__ldg((const uint32_t *)(c.fe + (size_t)(sy + y) * stride + sx + x)), 0u, (uint32_t)v);
+        __syncwarp();
+        dc0 = __shfl_sync(0xffffffffu, v, 0);
+        const int v1 = __shfl_sync(0xffffffffu, v, 1);
+        dc2 = __shfl_sync(0xffffffffu, v, 2);
+        dc3 = __shfl_sync(0xffffffffu, v, 3);
+        dc1 = vertical2 ? dc2 : v1; // me.c:488-489
+    }
+    const uint16_t *sums_base = small ? c.sums4 : c.sums8;
+    const int delta = (ip == X264_CUDA_PIXEL_16x16 || vertical2) ? d * stride : d;
+    const int n_extra = terms - 1;                                  // 0, 1 or 3 box sums besides the first
+    const int off1 = terms == 4 ? 8 : delta, off2 = delta, off3 = delta + 8;
+    const int sad_thresh = me_range <= 16 ? 10 : me_range <= 24 ? 11 : 12;
+    const uint8_t *ref0 = c.planes[0];
+    int nmv = 0;
+    // bsad = plain SAD at the seed + its MV bits (me.c:497-498)
+    int bsad = eval_round(c, false, lane, true, bmx << 2, bmy << 2);
+    for (int my = min_y; my <= max_y; my++) {
+        const int ycost = c.cmy[my << 2];
+        if (bsad <= ycost) continue;
+        bsad -= ycost;
+        const int thresh = bsad * 17 / 16;
+        for (int c0 = 0; c0 < width; c0 += 32) {
+            const int i = c0 + lane;
+            bool surv = false;
+            if (i < width) {
+                const uint16_t *sp = sums_base + (ptrdiff_t)my * stride + min_x + i;
+                // pixf.ads[i_pixel]: ads4 / ads2 / ads1 (pixel.c:515-559); offsets of the extra box sums precomputed per job
+                const int s0 = __ldg(sp), s1 = __ldg(sp + off1), s2 = __ldg(sp + off2), s3 = __ldg(sp + off3);
+                int ads = max(dc0 - s0, s0 - dc0) + (int)(uint16_t)c.cmx[(min_x + i) << 2];
+                if (n_extra >= 1) ads += max(dc1 - s1, s1 - dc1);
+                if (n_extra == 3) ads += max(dc2 - s2, s2 - dc2) + max(dc3 - s3, s3 - dc3);
+                surv = ads < thresh;
+            }
+            if (!__any_sync(0xffffffffu, surv)) continue;
+            // plain SAD of every survivor (one lane each), + the x cost indexed WITHOUT min_x as the reference does
+            // (me.c:518,531: cost_fpel_mvx[xs[i]])
+            int sad = 0x3fffffff;
+            if (surv) {
+                const uint8_t *a = ref0 + (ptrdiff_t)my * stride + min_x + i;
+                uint32_t acc = 0;
+                for (int y = 0; y < c.bh; y++)
+                    for (int x = 0; x < c.bw; x += 4)
+                        acc = sad4_acc(__ldg((const uint32_t *)(c.fe + (size_t)y * stride + x)), ldg4(a + (size_t)y * stride + x), acc);
+                sad = (int)acc + (int)(uint16_t)c.cmx[i << 2];
+            }
+
+            // bsad seen by lane j = min(bsad, sads of the survivors before it): exclusive prefix-min over the lanes
+            int pm = sad;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, pm, o);
+                if (lane >= o) pm = min(pm, t);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, pm, 1);
+            excl = lane == 0 ? bsad : min(excl, bsad);
+            const bool acc_ = surv && sad < ((excl * sad_thresh) >> 3);
+            const unsigned m = __ballot_sync(0xffffffffu, acc_);
+            if (acc_) {
+                const int pos = nmv + __popc(m & ((1u << lane) - 1));
+                if (pos < c.list_cap) list_put(c.list, pos, make_int2(sad + ycost, ((min_x + i) & 0xffff) | (my << 16)));
+            }
+            nmv += __popc(m);
+            bsad = min(bsad, __shfl_sync(0xffffffffu, pm, 31));
+        }
+        bsad += ycost;
+    }
+    __threadfence_block();
+    __syncwarp();
+    nmv = min(nmv, c.list_cap);
+    const int limit = me_range / 2;
+    if (nmv > limit * 2) { // stable filter by sad <= bsad*(sad_thresh+8)>>4, me.c:543-558
+        const int cut = bsad * (sad_thresh + 8) >> 4;
+        int w = 0;
+        for (int b0 = 0; b0 < nmv; b0 += 32) {
+            const int j = b0 + lane;
+            int2 e = make_int2(0, 0);
+            bool keep = false;
+            if (j < nmv) { e = list_get(c.list, j); keep = e.x <= cut; }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) list_put(c.list, w + __popc(m & ((1u << lane) - 1)), e);
+            w += __popc(m);
+            __syncwarp();
+        }
+        nmv = w;
+    }
+    if (nmv > limit) { // partial selection sort, first index wins ties, me.c:559-576
+        for (int i = 0; i < limit; i++) {
+            unsigned long long best = ~0ull;
+            for (int j = i + lane; j < nmv; j += 32) best = min(best, ((unsigned long long)(unsigned)list_get(c.list, j).x << 32) | (unsigned)j);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            const int bj = (int)(best & 0xffffffffu);
+            if (lane == 0 && bj > i) { const int2 t = list_get(c.list, i); list_put(c.list, i, list_get(c.list, bj)); list_put(c.list, bj, t); }
+            __threadfence_block();
+            __syncwarp();
+        }
+        nmv = limit;
+    }
+    // COST_MV with fpelcmp on the keepers, in list order (me.c:577-578)
+    const int per = 32 / c.U;
+    for (int k0 = 0; k0 < nmv; k0 += per) {
+        const int k = k0 + lane / c.U;
+        const bool valid = k < nmv;
+        int mx = 0, my = 0;
+        if (valid) { const int2 e = list_get(c.list, k); mx = (int)(int16_t)(e.y & 0xffff); my = e.y >> 16; }
+        const int cost = eval_round(c, c.fpel_satd, lane, valid, mx << 2, my << 2);
+        for (int j = 0; j < per && k0 + j < nmv; j++) {
+            const int cj = cand_cost(c, cost, j);
+            if (cj < bcost) { bcost = cj; bmx = __shfl_sync(0xffffffffu, mx, j * c.U); bmy = __shfl_sync(0xffffffffu, my, j * c.U); }
+        }
+    }
 }
 
 __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, int method, int me_range, int subme, int lane,
@@ -154,6 +302,8 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
         ox = bmx; oy = bmy; // square refine, me.c:301-304
         scan_fpel(c, lane, c_square1, 0, 8, ox, oy, bcost, bmx, bmy);
     }
+    else if (method == X264_CUDA_ME_METHOD_TESA)
+        tesa_search(c, job, me_range, lane, bcost, bmx, bmy);
     const int fbmx = bmx, fbmy = bmy;
 
     // ---- "-> qpel mv", me.c:603-620
@@ -220,7 +370,7 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
     }
 }
 
-struct Planes { const uint8_t *fenc; const uint8_t *ref[4]; int stride; };
+struct Planes { const uint8_t *fenc; const uint8_t *ref[4]; int stride; const uint16_t *sums8, *sums4; int2 *scratch; int list_cap; };
 
 __global__ void __launch_bounds__(128) me_small_kernel(Planes pl, const x264_cuda_me_job_t *__restrict__ jobs, int n_jobs,
                                                        const int16_t *const *__restrict__ cost_tabs, int method, int me_range, int subme,
@@ -228,8 +378,9 @@ __global__ void __launch_bounds__(128) me_small_kernel(Planes pl, const x264_cud
 {
     __shared__ x264_cuda_me_job_t s_job[4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n_jobs) return;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int j = gw; j < n_jobs; j += warps_per_grid) {
+    __syncwarp();
     if (lane < (int)(sizeof(x264_cuda_me_job_t) / 4)) ((uint32_t *)&s_job[wid])[lane] = __ldg((const uint32_t *)(jobs + j) + lane);
     __syncwarp();
     const x264_cuda_me_job_t &job = s_job[wid];
@@ -241,7 +392,7 @@ __global__ void __launch_bounds__(128) me_small_kernel(Planes pl, const x264_cud
         const int ay = max(abs(4 * job.mv_min_fpel[1] - job.mvp[1]), abs(4 * job.mv_max_fpel[1] - job.mvp[1])) + 40;
         if (ax > lim || ay > lim || job.mv_min_fpel[0] > 0 || job.mv_max_fpel[0] < 0 || job.mv_min_fpel[1] > 0 || job.mv_max_fpel[1] < 0) {
             if (lane == 0) { x264_cuda_me_final_t r = { { 0, 0 }, -1, -1, 0, 0 }; results[j] = r; }
-            return;
+            continue;
         }
     }
     const int ip = min((int)job.i_pixel, 6);
@@ -257,7 +408,15 @@ __global__ void __launch_bounds__(128) me_small_kernel(Planes pl, const x264_cud
     for (int k = 0; k < 4; k++) c.planes[k] = pl.ref[k] ? pl.ref[k] + off : pl.ref[0] + off;
     c.cmx = tab - job.mvp[0]; c.cmy = tab - job.mvp[1];
     c.fpel_satd = job.flags & X264_CUDA_ME_FPEL_SATD; c.mbcmp_satd = job.flags & X264_CUDA_ME_MBCMP_SATD;
+    c.i_pixel = ip;
+    c.sums8 = pl.sums8 ? pl.sums8 + off : nullptr; c.sums4 = pl.sums4 ? pl.sums4 + off : nullptr;
+    c.list = pl.scratch ? pl.scratch + (size_t)gw * pl.list_cap : nullptr; c.list_cap = pl.list_cap; c.lines_pad = 0;
+    if (method == X264_CUDA_ME_METHOD_TESA && (!c.list || !(ip > X264_CUDA_PIXEL_8x8 ? c.sums4 : c.sums8))) {
+        if (lane == 0) { x264_cuda_me_final_t r = { { 0, 0 }, -1, -1, 0, 0 }; results[j] = r; } // no integral plane for this block size
+        continue;
+    }
     warp_search(c, job, method, me_range, subme, lane, results + j);
+  }
 }
 
 // ---- function-level block metrics over packed 16x16 tiles: one thread per block
@@ -309,8 +468,9 @@ extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_f
         snprintf(ctx->err, 256, "x264_cuda_me_search_small: fenc/fref geometry mismatch");
         return -1;
     }
-    if (subme < 0 || subme > 9 || me_range < 1 || (method != X264_CUDA_ME_METHOD_DIA && method != X264_CUDA_ME_METHOD_HEX &&
-                                                   method != X264_CUDA_ME_METHOD_SEEDED)) {
+    if (subme < 0 || subme > 9 || me_range < 1 || me_range > 64 ||
+        (method != X264_CUDA_ME_METHOD_DIA && method != X264_CUDA_ME_METHOD_HEX && method != X264_CUDA_ME_METHOD_SEEDED &&
+         method != X264_CUDA_ME_METHOD_TESA)) {
         snprintf(ctx->err, 256, "x264_cuda_me_search_small: bad method %d / subme %d / me_range %d", method, subme, me_range);
         return -1;
     }
@@ -320,8 +480,28 @@ extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_f
     }
     const int16_t *const *d_tabs;
     if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
-    Planes pl = { fenc->plane[0], { fref->plane[0], fref->plane[1], fref->plane[2], fref->plane[3] }, fenc->g.stride };
-    me_small_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(pl, (const x264_cuda_me_job_t *)d_jobs, n_jobs, d_tabs, method, me_range, subme,
+    Planes pl = { fenc->plane[0], { fref->plane[0], fref->plane[1], fref->plane[2], fref->plane[3] }, fenc->g.stride, nullptr, nullptr, nullptr, 0 };
+    int blocks = (n_jobs + 3) / 4;
+    if (method == X264_CUDA_ME_METHOD_TESA) {
+        if (!fref->integral) {
+            snprintf(ctx->err, 256, "x264_cuda_me_search_small: TESA needs the integral image (X264_CUDA_FRAME_INTEGRAL + x264_cuda_frame_filter)");
+            return -1;
+        }
+        pl.sums8 = fref->integral;
+        pl.sums4 = (fref->g.flags & X264_CUDA_FRAME_INTEGRAL4) ? fref->integral + fref->plane_size : nullptr;
+        // candidate list scratch: one (2R+1) x (2R+4) list per resident warp (persistent grid-stride warps)
+        pl.list_cap = (2 * me_range + 1) * ((2 * me_range + 4) & ~3);
+        blocks = min(blocks, ctx->sm_count * 8);
+        const size_t need = (size_t)blocks * 4 * pl.list_cap * sizeof(int2);
+        if (need > ctx->d_scratch_size) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->d_scratch_size = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_scratch, need));
+            ctx->d_scratch_size = need;
+        }
+        pl.scratch = (int2 *)ctx->d_scratch;
+    }
+    me_small_kernel<<<blocks, 128, 0, ctx->stream>>>(pl, (const x264_cuda_me_job_t *)d_jobs, n_jobs, d_tabs, method, me_range, subme,
                                                                 (x264_cuda_me_final_t *)d_results);
     LAUNCH_CHECK(ctx, "me_small_kernel");
     return 0;
