@@ -1,0 +1,216 @@
+"""gpu: the reference's plugin tables filled by x264_*_init_cuda — checkasm-style (S/tools/checkasm.c): every overridden
+entry is called through its C function pointer on host buffers and compared with the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import xo_api as X
+
+pytestmark = pytest.mark.gpu
+
+u8p, i16p, u16p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_uint16), C.POINTER(C.c_int)
+CMP = C.CFUNCTYPE(C.c_int, u8p, C.c_int, u8p, C.c_int)
+CMP3 = C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, C.c_int, i32p)
+CMP4 = C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, u8p, C.c_int, i32p)
+VP = C.c_void_p
+
+
+class PixelTable(C.Structure):
+    _fields_ = [("sad", CMP * 7), ("ssd", CMP * 7), ("satd", CMP * 7), ("ssim", CMP * 7), ("sa8d", CMP * 4), ("mbcmp", CMP * 7),
+                ("mbcmp_unaligned", CMP * 7), ("fpelcmp", CMP * 7), ("fpelcmp_x3", CMP3 * 7), ("fpelcmp_x4", CMP4 * 7),
+                ("sad_aligned", CMP * 7), ("var", VP * 4), ("hadamard_ac", VP * 4), ("ssim_4x4x2_core", VP), ("ssim_end4", VP),
+                ("sad_x3", CMP3 * 7), ("sad_x4", CMP4 * 7), ("satd_x3", CMP3 * 7), ("satd_x4", CMP4 * 7),
+                ("ads", C.CFUNCTYPE(C.c_int, i32p, u16p, C.c_int, u16p, i16p, C.c_int, C.c_int) * 7), ("intra", VP * 6)]
+
+
+class DctTable(C.Structure):
+    _fields_ = [(n, t) for n, t in [
+        ("sub4x4_dct", C.CFUNCTYPE(None, i16p, u8p, u8p)), ("add4x4_idct", C.CFUNCTYPE(None, u8p, i16p)),
+        ("sub8x8_dct", C.CFUNCTYPE(None, i16p, u8p, u8p)), ("add8x8_idct", C.CFUNCTYPE(None, u8p, i16p)),
+        ("add8x8_idct_dc", C.CFUNCTYPE(None, u8p, i16p)), ("sub16x16_dct", C.CFUNCTYPE(None, i16p, u8p, u8p)),
+        ("add16x16_idct", C.CFUNCTYPE(None, u8p, i16p)), ("add16x16_idct_dc", C.CFUNCTYPE(None, u8p, i16p)),
+        ("sub8x8_dct8", C.CFUNCTYPE(None, i16p, u8p, u8p)), ("add8x8_idct8", C.CFUNCTYPE(None, u8p, i16p)),
+        ("sub16x16_dct8", C.CFUNCTYPE(None, i16p, u8p, u8p)), ("add16x16_idct8", C.CFUNCTYPE(None, u8p, i16p)),
+        ("dct4x4dc", C.CFUNCTYPE(None, i16p)), ("idct4x4dc", C.CFUNCTYPE(None, i16p))]]
+
+
+class QuantTable(C.Structure):
+    _fields_ = [("quant_8x8", C.CFUNCTYPE(C.c_int, i16p, u16p, u16p)), ("quant_4x4", C.CFUNCTYPE(C.c_int, i16p, u16p, u16p)),
+                ("quant_4x4_dc", C.CFUNCTYPE(C.c_int, i16p, C.c_int, C.c_int)), ("quant_2x2_dc", C.CFUNCTYPE(C.c_int, i16p, C.c_int, C.c_int)),
+                ("dequant_8x8", C.CFUNCTYPE(None, i16p, i32p, C.c_int)), ("dequant_4x4", C.CFUNCTYPE(None, i16p, i32p, C.c_int)),
+                ("dequant_4x4_dc", C.CFUNCTYPE(None, i16p, i32p, C.c_int)), ("rest", VP * 15)]
+
+
+class McTable(C.Structure):
+    _fields_ = [("mc_luma", C.CFUNCTYPE(None, u8p, C.c_int, C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)),
+                ("get_ref", C.CFUNCTYPE(u8p, u8p, C.POINTER(C.c_int), C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)),
+                ("mc_chroma", VP), ("avg", VP * 10), ("copy", VP * 7), ("copy_16x16_unaligned", VP), ("plane_copy", VP),
+                ("hpel_filter", C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, i16p)),
+                ("prefetch_fenc", VP), ("prefetch_ref", VP), ("memcpy_aligned", VP), ("memzero_aligned", VP),
+                ("integral", VP * 4),
+                ("frame_init_lowres_core", C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int))]
+
+
+def P(a, off=0, ty=u8p):
+    return C.cast(a.ctypes.data + off * a.itemsize, ty)
+
+
+@pytest.fixture(scope="module")
+def L(pkg, ctx):
+    return pkg.lib()
+
+
+def test_pixel_table(pkg, L, port):
+    t = PixelTable()
+    assert L.x264_pixel_init_cuda(C.byref(t)) == 0
+    assert not t.var[0] and not t.ssim_end4 and not t.intra[0]  # entries outside the hot path are left to the C table
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (48, 64), dtype=np.uint8)
+    b = rng.integers(0, 256, (48, 64), dtype=np.uint8)
+    fenc = np.ascontiguousarray(rng.integers(0, 256, (16, 16), dtype=np.uint8))
+    for ip in range(7):
+        for name, metric in (("sad", X.SAD), ("sad_aligned", X.SAD), ("ssd", X.SSD), ("satd", X.SATD)):
+            for _ in range(6):
+                oa, ob = int(rng.integers(0, 32)) * 64 + int(rng.integers(0, 32)), int(rng.integers(0, 32)) * 64 + int(rng.integers(0, 32))
+                assert getattr(t, name)[ip](P(a, oa), 64, P(b, ob), 64) == port.pixel_cmp(metric, ip, a, 64, b, 64, oa, ob), (name, ip)
+        offs = [int(rng.integers(0, 32)) * 64 + int(rng.integers(0, 32)) for _ in range(4)]
+        for name, metric in (("sad", X.SAD), ("satd", X.SATD)):
+            s3, s4 = (C.c_int * 3)(), (C.c_int * 4)()
+            getattr(t, name + "_x3")[ip](P(fenc), P(b, offs[0]), P(b, offs[1]), P(b, offs[2]), 64, s3)
+            getattr(t, name + "_x4")[ip](P(fenc), P(b, offs[0]), P(b, offs[1]), P(b, offs[2]), P(b, offs[3]), 64, s4)
+            want = [port.pixel_cmp(metric, ip, fenc, 16, b, 64, 0, o) for o in offs]
+            assert list(s3) == want[:3] and list(s4) == want, (name, ip)
+    for ip in (0, 3):
+        assert t.sa8d[ip](P(a, 65), 64, P(b, 130), 64) == port.pixel_cmp(X.SA8D, ip, a, 64, b, 64, 65, 130)
+    assert not t.sa8d[1] and not t.sa8d[2]
+    # ads: checkasm.c:433-464
+    for ip in range(7):
+        for _ in range(25):
+            sums = rng.integers(0, 1 << 14, 72, dtype=np.uint16)
+            dc = (C.c_int * 4)(*[int(x) for x in rng.integers(0, 1 << 14, 4)])
+            cost = rng.integers(0, 1 << 10, 32, dtype=np.uint16)
+            thresh = int(rng.integers(0, 1 << 15))
+            m1, m2 = np.zeros(32, np.int16), np.zeros(32, np.int16)
+            n1 = t.ads[ip](dc, P(sums, 0, u16p), 32, P(cost, 0, u16p), P(m1, 0, i16p), 28, thresh)
+            n2 = port.lib.xo_pixel_ads(ip, dc, X._ptr(sums, X.u16p), 32, X._ptr(cost, X.u16p), X._ptr(m2, X.i16p), 28, thresh)
+            assert n1 == n2 and np.array_equal(m1[:n1], m2[:n2]), ip
+
+
+def test_dct_and_quant_tables(pkg, L, port):
+    d, q = DctTable(), QuantTable()
+    assert L.x264_dct_init_cuda(C.byref(d)) == 0 and L.x264_quant_init_cuda(C.byref(q)) == 0
+    rng = np.random.default_rng(2)
+    o = port.lib
+    for trial in range(12):
+        fe = rng.integers(0, 256, 16 * 16, dtype=np.uint8)
+        fd = rng.integers(0, 256, 32 * 16, dtype=np.uint8)
+        # forward transforms: 4x4-family and 8x8-family over 16x16
+        got = np.zeros(256, np.int16)
+        d.sub16x16_dct(P(got, 0, i16p), P(fe), P(fd))
+        want = np.zeros(256, np.int16)
+        for b in range(16):
+            x = ((b >> 2) & 1) * 8 + (b & 1) * 4
+            y = (b >> 3) * 8 + ((b >> 1) & 1) * 4
+            o.xo_sub4x4_dct(X._ptr(want, X.i16p, b * 16), X._ptr(fe, X.u8p, y * 16 + x), X._ptr(fd, X.u8p, y * 32 + x))
+        assert np.array_equal(got, want)
+        g1 = np.zeros(16, np.int16); d.sub4x4_dct(P(g1, 0, i16p), P(fe), P(fd)); assert np.array_equal(g1, want[:16])
+        g4 = np.zeros(64, np.int16); d.sub8x8_dct(P(g4, 0, i16p), P(fe), P(fd)); assert np.array_equal(g4, want[:64])
+        got8, want8 = np.zeros(256, np.int16), np.zeros(256, np.int16)
+        d.sub16x16_dct8(P(got8, 0, i16p), P(fe), P(fd))
+        for b in range(4):
+            o.xo_sub8x8_dct8(X._ptr(want8, X.i16p, b * 64), X._ptr(fe, X.u8p, (b >> 1) * 8 * 16 + (b & 1) * 8), X._ptr(fd, X.u8p, (b >> 1) * 8 * 32 + (b & 1) * 8))
+        assert np.array_equal(got8, want8)
+        g8 = np.zeros(64, np.int16); d.sub8x8_dct8(P(g8, 0, i16p), P(fe), P(fd)); assert np.array_equal(g8, want8[:64])
+        # quant / dequant with real tables, then inverse transforms
+        qp, cqm = int(rng.integers(0, 52)), int(rng.integers(0, 2))
+        mf, bias, dq = np.zeros(16, np.uint16), np.zeros(16, np.uint16), np.zeros(96, np.int32)
+        o.xo_quant4_tables(cqm, 1, qp, X._ptr(mf, X.u16p), X._ptr(bias, X.u16p)); o.xo_dequant4_table(cqm, 1, X._ptr(dq, X.i32p))
+        a, b2 = want[:16].copy(), want[:16].copy()
+        assert q.quant_4x4(P(a, 0, i16p), P(mf, 0, u16p), P(bias, 0, u16p)) == o.xo_quant_4x4(X._ptr(b2, X.i16p), X._ptr(mf, X.u16p), X._ptr(bias, X.u16p))
+        assert np.array_equal(a, b2)
+        q.dequant_4x4(P(a, 0, i16p), P(dq, 0, i32p), qp); o.xo_dequant_4x4(X._ptr(b2, X.i16p), X._ptr(dq, X.i32p), qp)
+        assert np.array_equal(a, b2)
+        r1, r2 = fd.copy(), fd.copy()
+        d.add4x4_idct(P(r1), P(a, 0, i16p)); o.xo_add4x4_idct(X._ptr(r2), X._ptr(b2, X.i16p))
+        assert np.array_equal(r1, r2)
+        mf8, bias8, dq8 = np.zeros(64, np.uint16), np.zeros(64, np.uint16), np.zeros(384, np.int32)
+        o.xo_quant8_tables(cqm, 1, qp, X._ptr(mf8, X.u16p), X._ptr(bias8, X.u16p)); o.xo_dequant8_table(cqm, 1, X._ptr(dq8, X.i32p))
+        a, b2 = want8[:64].copy(), want8[:64].copy()
+        assert q.quant_8x8(P(a, 0, i16p), P(mf8, 0, u16p), P(bias8, 0, u16p)) == o.xo_quant_8x8(X._ptr(b2, X.i16p), X._ptr(mf8, X.u16p), X._ptr(bias8, X.u16p))
+        assert np.array_equal(a, b2)
+        q.dequant_8x8(P(a, 0, i16p), P(dq8, 0, i32p), qp); o.xo_dequant_8x8(X._ptr(b2, X.i16p), X._ptr(dq8, X.i32p), qp)
+        assert np.array_equal(a, b2)
+        r1, r2 = fd.copy(), fd.copy()
+        d.add8x8_idct8(P(r1), P(a.copy(), 0, i16p)); o.xo_add8x8_idct8(X._ptr(r2), X._ptr(b2.copy(), X.i16p))
+        assert np.array_equal(r1, r2)
+        # 16x16 inverse (4x4 family) on the quantised+dequantised full macroblock
+        full = want.copy()
+        for b in range(16):
+            o.xo_quant_4x4(X._ptr(full, X.i16p, b * 16), X._ptr(mf, X.u16p), X._ptr(bias, X.u16p))
+            o.xo_dequant_4x4(X._ptr(full, X.i16p, b * 16), X._ptr(dq, X.i32p), qp)
+        r1, r2 = fd.copy(), fd.copy()
+        d.add16x16_idct(P(r1), P(full, 0, i16p))
+        for b in range(16):
+            x = ((b >> 2) & 1) * 8 + (b & 1) * 4
+            y = (b >> 3) * 8 + ((b >> 1) & 1) * 4
+            o.xo_add4x4_idct(X._ptr(r2, X.u8p, y * 32 + x), X._ptr(full.copy(), X.i16p, b * 16))
+        assert np.array_equal(r1, r2)
+        # DC paths
+        dc = rng.integers(-4096, 4096, 16).astype(np.int16)
+        a, b2 = dc.copy(), dc.copy()
+        d.dct4x4dc(P(a, 0, i16p)); o.xo_dct4x4dc(X._ptr(b2, X.i16p)); assert np.array_equal(a, b2)
+        m, bs = int(mf[0]) >> 1, int(bias[0]) << 1
+        assert q.quant_4x4_dc(P(a, 0, i16p), m, bs) == o.xo_quant_4x4_dc(X._ptr(b2, X.i16p), m, bs) and np.array_equal(a, b2)
+        a2, b3 = a[:4].copy(), a[:4].copy()
+        assert q.quant_2x2_dc(P(a2, 0, i16p), m, bs) == o.xo_quant_2x2_dc(X._ptr(b3, X.i16p), m, bs) and np.array_equal(a2, b3)
+        d.idct4x4dc(P(a, 0, i16p)); o.xo_idct4x4dc(X._ptr(b2, X.i16p)); assert np.array_equal(a, b2)
+        q.dequant_4x4_dc(P(a, 0, i16p), P(dq, 0, i32p), qp); o.xo_dequant_4x4_dc(X._ptr(b2, X.i16p), X._ptr(dq, X.i32p), qp)
+        assert np.array_equal(a, b2)
+        for fn, n in ((d.add8x8_idct_dc, 4), (d.add16x16_idct_dc, 16)):
+            r1, r2 = fd.copy(), fd.copy()
+            fn(P(r1), P(a, 0, i16p)); o.xo_add_idct_dc(X._ptr(r2), X._ptr(a, X.i16p), n)
+            assert np.array_equal(r1, r2)
+
+
+def test_mc_table(pkg, L, port):
+    m = McTable()
+    assert L.x264_mc_init_cuda(C.byref(m)) == 0
+    from x264_vs2008_b200 import synth
+    w, h = 96, 64
+    g = port.geometry(w, h)
+    plane = port.plane_from_picture(g, synth.Clip(w, h, seed=2).luma(0))
+    fh, fv, fc, _ = port.frame_filter(g, plane, 0, want_integral=False)
+    # hpel_filter on a 48x10 window (checkasm.c:822-850 compares bytes 2..44 of each row; we compare all the C body defines)
+    dh, dv, dc = np.zeros_like(plane), np.zeros_like(plane), np.zeros_like(plane)
+    o0 = g.origin + 8 * g.stride + 8
+    m.hpel_filter(P(dh, o0), P(dv, o0), P(dc, o0), P(plane, o0), g.stride, 48, 10, None)
+    for y in range(10):
+        r = o0 + y * g.stride
+        assert np.array_equal(dh[r:r + 48], fh[r:r + 48]) and np.array_equal(dc[r:r + 48], fc[r:r + 48])
+        assert np.array_equal(dv[r - 2:r + 51], fv[r - 2:r + 51])
+    # frame_init_lowres_core w=40 (checkasm.c:852-881)
+    outs = [np.zeros(64 * 24, np.uint8) for _ in range(4)]
+    m.frame_init_lowres_core(P(plane, g.origin), P(outs[0]), P(outs[1]), P(outs[2]), P(outs[3]), g.stride, 64, 40, 20)
+    want = port.init_lowres(g, plane.copy())
+    for k in range(4):
+        for y in range(20):
+            assert np.array_equal(outs[k][y * 64:y * 64 + 40], want[k][g.origin_lowres + y * g.stride_lowres:][:40])
+    # mc_luma / get_ref at random qpel vectors (checkasm.c:702-746)
+    rng = np.random.default_rng(4)
+    planes = [plane, fh, fv, fc]
+    arr = (u8p * 4)(*[P(p, g.origin + 20 * g.stride + 30) for p in planes])
+    arr_o = (X.u8p * 4)(*[X._ptr(p, X.u8p, g.origin + 20 * g.stride + 30) for p in planes])
+    for (bw, bh) in ((16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4), (20, 18), (12, 10)):
+        for _ in range(8):
+            mvx, mvy = int(rng.integers(-40, 41)), int(rng.integers(-40, 41))
+            d1, d2 = np.zeros(32 * 20, np.uint8), np.zeros(32 * 20, np.uint8)
+            m.mc_luma(P(d1), 32, arr, g.stride, mvx, mvy, bw, bh)
+            port.lib.xo_mc_luma(X._ptr(d2), 32, arr_o, g.stride, mvx, mvy, bw, bh)
+            assert np.array_equal(d1, d2), (bw, bh, mvx, mvy)
+            st = C.c_int(32)
+            d3 = np.zeros(32 * 20, np.uint8)
+            res = m.get_ref(P(d3), C.byref(st), arr, g.stride, mvx, mvy, bw, bh)
+            got = np.ctypeslib.as_array(res, shape=(20 * st.value,))
+            for y in range(bh):
+                assert np.array_equal(got[y * st.value:y * st.value + bw], d2[y * 32:y * 32 + bw])
+    L.x264_cuda_tables_shutdown()
