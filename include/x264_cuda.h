@@ -183,6 +183,22 @@ X264_CUDA_API int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cud
 X264_CUDA_API int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel, int n, const uint8_t *pix1, const uint8_t *pix2,
                                       int *out);
 
+/* ------------------------------------------------------------------ motion compensation -------------- */
+/* Frame-batched x264_mb_mc_0xywh (S/common/macroblock.c:462-486): for each job the w x h luma block at (bx,by) is
+ * predicted from fref at quarter-pel mv (mc_luma, S/common/mc.c:160-179) and, when both frames carry chroma planes, the
+ * two w/2 x h/2 chroma blocks by 1/8-pel bilinear interpolation (mc_chroma, mc.c:205-236); results are written into fdec.
+ * fref must be border-expanded and filtered (X264_CUDA_FRAME_HPEL); chroma borders are the caller's to upload. */
+typedef struct x264_cuda_mc_job_t {
+    int16_t bx, by;   /* luma position */
+    int16_t mvx, mvy; /* quarter-pel */
+    uint8_t w, h;     /* luma size: 4, 8 or 16 */
+    uint8_t reserved[2];
+} x264_cuda_mc_job_t; /* 12 bytes */
+X264_CUDA_API int x264_cuda_mc_blocks(x264_cuda_t *ctx, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec,
+                                      const x264_cuda_mc_job_t *jobs, int n_jobs);
+X264_CUDA_API int x264_cuda_mc_blocks_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec,
+                                          const void *d_jobs, int n_jobs);
+
 /* ------------------------------------------------------------------ transform / quantisation --------- */
 /* Quantiser tables exactly as x264_cqm_init leaves them in x264_t (S/common/set.c:68-174, S/common/common.h:294-304):
  * quant4_mf[list] -> uint16[52][16], quant4_bias likewise, dequant4_mf[list] -> int[6][16] (lists CQM_4IY,4PY,4IC,4PC),

@@ -13,6 +13,8 @@ PADH = PADV = 32
 FRAME_HPEL, FRAME_INTEGRAL, FRAME_INTEGRAL4, FRAME_LOWRES, FRAME_CHROMA = 1, 2, 4, 8, 16
 PLANE_FULL, PLANE_H, PLANE_V, PLANE_C, PLANE_LOWRES, PLANE_INTEGRAL, PLANE_INTEGRAL4, PLANE_CB, PLANE_CR = 0, 1, 2, 3, 4, 8, 9, 10, 11
 RESID_8x8DCT, RESID_DECIMATE = 1, 2
+MC_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("mvx", "<i2"), ("mvy", "<i2"), ("w", "u1"), ("h", "u1"), ("reserved", "u1", (2,))], align=True)
+assert MC_JOB.itemsize == 12
 RESID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("qp", "u1"), ("chroma_qp", "u1"), ("flags", "u1"), ("reserved", "u1")], align=True)
 MB_COEFFS = np.dtype([("luma", "<i2", (256,)), ("chroma_ac", "<i2", (8, 16)), ("chroma_dc", "<i2", (2, 4)), ("nnz", "u1", (27,)),
                       ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("reserved", "u1", (3,))], align=True)
@@ -79,6 +81,8 @@ def lib():
         L.x264_cuda_frame_upload_dev.argtypes = [vp, vp, vp, ip, ip, ip]
         L.x264_cuda_frame_upload_chroma.argtypes = [vp, vp, ip, vp, ip, ip, ip]
         L.x264_cuda_set_quant_preset.argtypes = [vp, ip]
+        L.x264_cuda_mc_blocks.argtypes = [vp, vp, vp, vp, ip]
+        L.x264_cuda_mc_blocks_dev.argtypes = [vp, vp, vp, vp, ip]
         L.x264_cuda_block_residual.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_block_dc.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_residual_inter.argtypes = [vp, vp, vp, vp, ip, vp]
@@ -219,6 +223,10 @@ class Context:
         res = np.zeros(len(jobs), ME_RESULT)
         self.check(lib().x264_cuda_me_search(self.h, fenc.h, fref.h, me_range, jobs.ctypes.data, len(jobs), res.ctypes.data))
         return res
+
+    def mc_blocks(self, fref, fdec, jobs):
+        jobs = np.ascontiguousarray(jobs, MC_JOB)
+        self.check(lib().x264_cuda_mc_blocks(self.h, fref.h, fdec.h, jobs.ctypes.data, len(jobs)))
 
     def set_quant_preset(self, cqm):
         self.check(lib().x264_cuda_set_quant_preset(self.h, cqm))
