@@ -392,3 +392,116 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
         memcpy(rec_v + 8 * y, h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, 8);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* lowres lookahead through the reference's own x264_rc_analyse_slice -> x264_slicetype_frame_cost   */
+#include "common/predict.h"
+static x264_frame_t *g_la_frames[3];
+static x264_t *g_la_h;
+static int g_la_key[6];
+
+void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                          const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                          const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out)
+{
+    int key[6] = { g->width, g->height, in->me_method, in->mbcmp_satd, in->fpel_satd, in->b_weighted_bipred };
+    if (!g_la_h || memcmp(key, g_la_key, sizeof(key))) {
+        x264_param_t p;
+        x264_param_default(&p);
+        p.i_width = g->width; p.i_height = g->height; p.i_threads = 1; p.i_log_level = X264_LOG_NONE;
+        p.rc.i_rc_method = X264_RC_CQP; p.rc.i_qp_constant = 26;
+        p.analyse.i_me_method = in->fpel_satd ? X264_ME_TESA : in->me_method;
+        p.analyse.i_subpel_refine = in->mbcmp_satd ? 7 : 1;
+        p.analyse.b_weighted_bipred = in->b_weighted_bipred;
+        p.i_bframe = 3; p.i_bframe_adaptive = X264_B_ADAPT_FAST;
+        g_la_h = x264_encoder_open(&p);
+        if (!g_la_h) abort();
+        for (int i = 0; i < 3; i++) g_la_frames[i] = x264_frame_new(g_la_h);
+        memcpy(g_la_key, key, sizeof(key));
+    }
+    x264_t *h = g_la_h;
+    h->param.analyse.i_me_range = in->me_range;
+    const int n_mb = g->mb_width * g->mb_height;
+    x264_frame_t *f0 = g_la_frames[0], *f1 = g_la_frames[1], *fb = g_la_frames[2];
+    const int b_bidir = in->b < in->p1;
+    const uint8_t *const *src[3] = { fref0, fref1, fenc };
+    x264_frame_t *dst[3] = { f0, f1, fb };
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < 4; i++)
+            if (src[k] && src[k][i]) put_plane(dst[k]->lowres[i], src[k][i], g->stride_lowres, g->lines_lowres);
+    const int d0 = in->b - in->p0 - 1, d1 = in->p1 - in->b - 1;
+    memset(fb->i_cost_est, -1, sizeof(fb->i_cost_est));
+    if (in->b != in->p0) {
+        memcpy(fb->lowres_mvs[0][d0], mvs0, n_mb * 4); memcpy(fb->lowres_mv_costs[0][d0], costs0, n_mb * 4);
+        if (in->do_search[0]) fb->lowres_mvs[0][d0][0][0] = 0x7FFF;
+    }
+    if (b_bidir) {
+        memcpy(fb->lowres_mvs[1][d1], mvs1, n_mb * 4); memcpy(fb->lowres_mv_costs[1][d1], costs1, n_mb * 4);
+        if (in->do_search[1]) fb->lowres_mvs[1][d1][0][0] = 0x7FFF;
+        memcpy(f1->lowres_mvs[0][in->p1 - in->p0 - 1], ref1_mvs, n_mb * 4);
+    }
+    memcpy(fb->i_intra_cost, intra_cost, n_mb * 2);
+    fb->b_intra_calculated = in->b_intra_calculated;
+    /* drive x264_rc_analyse_slice (slicetype.c:638-679) so that it evaluates exactly (p0,p1,b) */
+    h->fenc = fb; h->fdec = g_la_frames[0]; /* fdec only receives copies of row satds */
+    h->fref0[0] = f0; h->fref1[0] = f1;
+    h->frames.current[0] = NULL;
+    if (in->p0 == in->p1 && in->p0 == in->b) fb->i_type = X264_TYPE_I;
+    else if (!b_bidir) {
+        fb->i_type = X264_TYPE_P;
+        /* p1 = 1 + number of leading B frames in h->frames.current: fake (p1-1) B entries */
+        static x264_frame_t bf;
+        bf.i_type = X264_TYPE_B;
+        int i;
+        for (i = 0; i < in->p1 - 1; i++) h->frames.current[i] = &bf;
+        h->frames.current[i] = NULL;
+    } else {
+        fb->i_type = X264_TYPE_B;
+        f0->i_poc = 0; f1->i_poc = 2 * in->p1; fb->i_poc = 2 * in->p1 - 2 * (in->p1 - in->b); /* p1=(poc1-poc0)/2, b as slicetype.c:664 */
+        fb->i_poc = f1->i_poc - 2 * in->b; /* the reference computes b = (poc1 - poc_enc)/2 */
+    }
+    x264_rc_analyse_slice(h);
+    h->frames.current[0] = NULL;
+    int score = fb->i_cost_est[in->b - in->p0][in->p1 - in->b];
+    (void)score;
+    if (in->b != in->p0) { memcpy(mvs0, fb->lowres_mvs[0][d0], n_mb * 4); memcpy(costs0, fb->lowres_mv_costs[0][d0], n_mb * 4); }
+    if (b_bidir) { memcpy(mvs1, fb->lowres_mvs[1][d1], n_mb * 4); memcpy(costs1, fb->lowres_mv_costs[1][d1], n_mb * 4); }
+    memcpy(intra_cost, fb->i_intra_cost, n_mb * 2);
+    memset(out, 0, sizeof(*out));
+    out->score = fb->i_cost_est[in->b - in->p0][in->p1 - in->b]; /* NB: B scores arrive scaled by 100/(120+bias) (slicetype.c:338) */
+    out->score_aq = fb->i_cost_est_aq[in->b - in->p0][in->p1 - in->b];
+    out->intra_mbs = fb->i_intra_mbs[in->b - in->p0];
+    out->intra_cost_sum = fb->i_cost_est[0][0];
+}
+
+void xo_lowres_intra_pred(int mode, const uint8_t *l0, int stride, int bx, int by, uint8_t out[64])
+{
+    static x264_predict_t p8c[7];
+    static x264_predict8x8_t p8[12];
+    static int init;
+    static x264_predict_8x8_filter_t filt;
+    if (!init) { x264_predict_8x8c_init(0, p8c); x264_predict_8x8_init(0, p8, &filt); init = 1; }
+    DECLARE_ALIGNED_16(uint8_t buf[9 * FDEC_STRIDE]);
+    DECLARE_ALIGNED_16(uint8_t edge[33]);
+    const uint8_t *src = l0 + by * stride + bx - 1;
+    uint8_t *pix = &buf[8 + FDEC_STRIDE - 1];
+    memcpy(pix - FDEC_STRIDE, src - stride, 17);
+    for (int i = 0; i < 8; i++) pix[i * FDEC_STRIDE] = src[i * stride];
+    pix++;
+    if (mode < 4) p8c[mode](pix);
+    else { x264_predict_8x8_filter(pix, edge, ALL_NEIGHBORS, ALL_NEIGHBORS); p8[mode - 1](pix, edge); }
+    for (int y = 0; y < 8; y++) memcpy(out + 8 * y, pix + y * FDEC_STRIDE, 8);
+}
+int xo_lowres_intra_cost(const uint8_t *l0, int stride, int bx, int by, int mbcmp_satd)
+{
+    uint8_t pred[64], pp[8 * 16], fenc[8 * 16];
+    int best = 1 << 30;
+    for (int y = 0; y < 8; y++) memcpy(fenc + 16 * y, l0 + (by + y) * stride + bx, 8);
+    for (int m = 0; m < 10; m++) {
+        xo_lowres_intra_pred(m, l0, stride, bx, by, pred);
+        for (int y = 0; y < 8; y++) memcpy(pp + 16 * y, pred + 8 * y, 8);
+        int c = xo_pixel_cmp(mbcmp_satd ? XO_SATD : XO_SAD, XO_8x8, pp, 16, fenc, 16);
+        if (c < best) best = c;
+    }
+    return best + 5;
+}

@@ -157,6 +157,30 @@ typedef struct {
 void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
                           uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out);
 
+/* ---------------- lowres lookahead: S/encoder/slicetype.c:43-355 (non-VBV, no AQ) ----------------
+ * Planes are the four half-resolution planes (pixel 0,0 pointers, stride g->stride_lowres).  mvs/costs are the frame's
+ * lowres_mvs[l][dist-1] / lowres_mv_costs[l][dist-1] arrays (mb_width*mb_height entries, updated in place when
+ * do_search[l]); ref1_mvs = frames[p1]->lowres_mvs[0][p1-p0-1] (B evaluations only); intra_cost = i_intra_cost.
+ * out->score is the plain sum before the B-frame scaling of slicetype.c:338-339. */
+typedef struct {
+    int p0, p1, b;
+    int me_method;         /* user's --me; the lookahead uses min(HEX, me) (slicetype.c:38) */
+    int me_range;          /* h->param.analyse.i_me_range */
+    int mbcmp_satd;        /* user subme > 1 */
+    int fpel_satd;         /* user subme > 1 && --me tesa */
+    int b_weighted_bipred;
+    int do_search[2];
+    int b_intra_calculated;
+} xo_lowres_in;
+typedef struct { int score, score_aq, intra_mbs, intra_cost_sum; } xo_lowres_out;
+void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                          const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                          const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out);
+/* one of the ten 8x8 predictions used by the lookahead (0..3: predict_8x8c DC,H,V,P; 4..9: predict_8x8 DDL,DDR,VR,HD,VL,HU
+ * on the filtered edge), S/common/predict.c:234-336, :499-748 */
+void xo_lowres_intra_pred(int mode, const uint8_t *l0, int stride, int bx, int by, uint8_t out[64]);
+int xo_lowres_intra_cost(const uint8_t *l0, int stride, int bx, int by, int mbcmp_satd);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,7 +87,7 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
                     const uint16_t *integral, const xo_me_in *in, const me_sub *sub, xo_me_out *out)
 {
     me_ctx cx, *c = &cx;
-    const int stride = g->stride, range = in->me_range;
+    const int stride = g->stride > 0 ? g->stride : -g->stride, range = in->me_range; /* negative: explicit stride (lowres) */
     const int x_min = in->mv_min_fpel[0], y_min = in->mv_min_fpel[1];
     const int x_max = in->mv_max_fpel[0], y_max = in->mv_max_fpel[1];
     const int16_t *tab = cost_table(in->qp);
@@ -358,4 +358,16 @@ void xo_me_search_fpel_batch(const xo_geom *g, const uint8_t *fenc_plane, const 
 {
     for (int i = 0; i < n; i++)
         xo_me_search_fpel(g, fenc_plane, fref_plane, integral, in + i, out + i);
+}
+
+/* same search on planes of an explicit stride (the half-resolution lookahead planes) */
+void xo_me_search_subpel_strided(int stride, int lines_unused, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
+                                 const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    xo_geom g;
+    memset(&g, 0, sizeof(g));
+    g.stride = stride;
+    (void)lines_unused;
+    me_sub sub = { subme, mbcmp_satd };
+    me_core(&g, fenc_plane, fref_planes, NULL, in, &sub, out);
 }
