@@ -183,6 +183,43 @@ X264_CUDA_API int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cud
 X264_CUDA_API int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel, int n, const uint8_t *pix1, const uint8_t *pix2,
                                       int *out);
 
+/* ------------------------------------------------------------------ lowres lookahead ------------------ */
+/* One call == one x264_slicetype_frame_cost(h, a, frames, p0, p1, b) evaluation (S/encoder/slicetype.c:256-355) in its
+ * default (non-VBV, non-AQ) form: every interior 8x8 block of the half-resolution frame b gets
+ * x264_slicetype_mb_cost (:43-248) — bidirectional direct-like try, one DIA/HEX + subme-4 search per list with the
+ * reverse-raster neighbour predictors, bidirectional retry, intra (ten 8x8 predictions) — and the block costs are
+ * summed.  Blocks run as an anti-diagonal wavefront (x+2y descending) inside one launch; the per-frame
+ * state the reference keeps in x264_frame_t (lowres_mvs, lowres_mv_costs, i_intra_cost) lives on the device with the
+ * frame.  Call order and do_search/b_intra_calculated bookkeeping stay with the host, as in the reference.
+ * fenc = frames[b], fref0 = frames[p0], fref1 = frames[p1] (may equal fref0 when b == p1); all three need
+ * X264_CUDA_FRAME_LOWRES + x264_cuda_frame_init_lowres. */
+#define X264_CUDA_LOWRES_WEIGHTED_BIPRED 16 /* param.analyse.b_weighted_bipred; other flag bits: X264_CUDA_ME_MBCMP_SATD / _FPEL_SATD */
+typedef struct x264_cuda_lowres_params_t {
+    int p0, p1, b;
+    int me_method;          /* the user's --me (X264_ME_*: 0 dia, 1 hex, ...); the lookahead uses min(HEX, me) */
+    int me_range;
+    int flags;
+    int do_search[2];       /* slicetype.c:279-282 */
+    int b_intra_calculated; /* frames[b]->b_intra_calculated */
+} x264_cuda_lowres_params_t;
+typedef struct x264_cuda_lowres_result_t {
+    int score;              /* sum of block costs BEFORE the B-frame scaling of slicetype.c:338-339 */
+    int intra_mbs;          /* i_intra_mbs[b-p0]   (b == p1 only) */
+    int intra_cost_sum;     /* i_cost_est[0][0]    (b == p1 only) */
+    int reserved;
+} x264_cuda_lowres_result_t;
+/* (re)allocates the lookahead state of a frame: n_dist = i_bframe + 1 distances per list, zero-filled like frame.c:92-98 */
+X264_CUDA_API int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame_t *frame, int n_dist);
+/* host access to lowres_mvs[list][dist] (int16[mb][2]) / lowres_mv_costs[list][dist] (int[mb]) / i_intra_cost (uint16[mb]);
+ * NULL pointers are skipped */
+X264_CUDA_API int x264_cuda_frame_lookahead_get(x264_cuda_t *ctx, const x264_cuda_frame_t *frame, int list, int dist, int16_t *mvs,
+                                                int *costs, uint16_t *intra_cost);
+X264_CUDA_API int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_frame_t *frame, int list, int dist, const int16_t *mvs,
+                                                const int *costs, const uint16_t *intra_cost);
+X264_CUDA_API int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
+                                              const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *params,
+                                              x264_cuda_lowres_result_t *result);
+
 /* ------------------------------------------------------------------ motion compensation -------------- */
 /* Frame-batched x264_mb_mc_0xywh (S/common/macroblock.c:462-486): for each job the w x h luma block at (bx,by) is
  * predicted from fref at quarter-pel mv (mc_luma, S/common/mc.c:160-179) and, when both frames carry chroma planes, the

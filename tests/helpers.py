@@ -122,3 +122,63 @@ def block_jobs_to_mis(jobs, me_range, method=X.ME_ESA):
         for c in range(m.i_mvc):
             m.mvc[c][0], m.mvc[c][1] = int(j["mvc"][c][0]), int(j["mvc"][c][1])
     return arr
+
+
+# ---------------- lowres lookahead (S/encoder/slicetype.c:43-355) ----------------
+# The evaluation schedule the slicetype decision produces for a 3-frame window: I cost of frame 0 and 1, P(0->1), P(0->2),
+# B(0,1,2) with searches, then the same B again with cached vectors (do_search 0) and P(0->1) with cached intra costs.
+LOOKAHEAD_SCHEDULE = (
+    # (name, fenc, p0, p1, b, do_search, b_intra_calculated)
+    ("I0", 0, 0, 0, 0, (0, 0), 0),
+    ("P01", 1, 0, 1, 1, (1, 0), 0),
+    ("P02", 2, 0, 2, 2, (1, 0), 0),
+    ("B012", 1, 0, 2, 1, (0, 1), 1),   # list0 vectors of frame 1 at distance 1 are cached from P01
+    ("B012_cached", 1, 0, 2, 1, (0, 0), 1),
+    ("P01_cached", 1, 0, 1, 1, (0, 0), 1),
+)
+
+
+def lowres_planes(o, g, clip, n_frames):
+    """[frame][4] padded lowres planes built by oracle `o` from synthetic luma"""
+    out = []
+    for i in range(n_frames):
+        p = o.plane_from_picture(g, clip.luma(i))
+        out.append(o.init_lowres(g, p))
+    return out
+
+
+def oracle_lookahead(o, g, planes, me_method=X.ME_HEX, me_range=16, mbcmp_satd=1, weighted=0, is_ref=False):
+    """runs LOOKAHEAD_SCHEDULE on oracle `o`; returns list of (name, score, intra_mbs, intra_cost_sum, mvs0, costs0, mvs1, costs1, intra).
+    Frame state: per frame, per (list, dist) arrays, as x264_frame_t keeps them (S/common/frame.h:65-74)."""
+    n = g.mb_width * g.mb_height
+    st = [{"mvs": np.zeros((2, 3, n, 2), np.int16), "costs": np.zeros((2, 3, n), np.int32), "intra": np.zeros(n, np.uint16)} for _ in planes]
+    res = []
+    for name, fe, p0, p1, b, ds, bic in LOOKAHEAD_SCHEDULE:
+        d0, d1 = max(b - p0 - 1, 0), max(p1 - b - 1, 0)
+        s = st[fe]
+        state = {"mvs0": s["mvs"][0, d0], "costs0": s["costs"][0, d0], "mvs1": s["mvs"][1, d1], "costs1": s["costs"][1, d1],
+                 "intra": s["intra"], "ref1_mvs": st[p1]["mvs"][0, max(p1 - p0 - 1, 0)].copy()}
+        out = o.lowres_frame_cost(g, planes[b], planes[p0], planes[p1], p0, p1, b, state, me_method=me_method, me_range=me_range,
+                                  mbcmp_satd=mbcmp_satd, weighted=weighted, do_search=ds, b_intra_calculated=bic)
+        score = out.score
+        if not is_ref and b < p1:
+            score = score * 100 // 120   # the reference stores B scores scaled (slicetype.c:338-339, i_bframe_bias 0)
+        res.append((name, score, out.intra_mbs if b == p1 else 0, out.intra_cost_sum if (b == p1 and p0 != p1) else 0,  # for I the reference overwrites i_cost_est[0][0] with the score
+                   
+                    state["mvs0"].copy(), state["costs0"].copy(), state["mvs1"].copy(), state["costs1"].copy(), s["intra"].copy()))
+    return res
+
+
+def lookahead_digest(res, g):
+    """compact, comparable form: scores + interior arrays"""
+    W, H = g.mb_width, g.mb_height
+    small = W <= 2 or H <= 2
+    m = np.zeros((H, W), bool)
+    if small:
+        m[:] = True
+    else:
+        m[1:H - 1, 1:W - 1] = True
+    m = m.ravel()
+    scal = np.array([(r[1], r[2], r[3]) for r in res], np.int64)
+    arrs = [np.concatenate([r[4][m].ravel().astype(np.int64), r[5][m], r[6][m].ravel().astype(np.int64), r[7][m], r[8][m].astype(np.int64)]) for r in res]
+    return scal, np.stack(arrs)

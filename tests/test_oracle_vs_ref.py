@@ -126,3 +126,20 @@ def test_dct_quant(port, ref):
             r1, r2 = p2.copy(), p2.copy()
             port.lib.xo_add_idct_dc(X._ptr(r1), X._ptr(a, X.i16p), n); ref.lib.xo_add_idct_dc(X._ptr(r2), X._ptr(a, X.i16p), n)
             assert np.array_equal(r1, r2)
+
+
+@pytest.mark.parametrize("size,method,satd,weighted", [((176, 144), X.ME_HEX, 1, 0), ((176, 144), X.ME_DIA, 0, 0), ((208, 112), X.ME_HEX, 1, 1),
+                                                       ((32, 64), X.ME_HEX, 1, 0)])
+def test_lowres_lookahead(pkg, port, ref, size, method, satd, weighted):
+    """x264_slicetype_frame_cost through the reference's x264_rc_analyse_slice vs the port, whole evaluation schedule"""
+    from x264_vs2008_b200 import synth
+    from helpers import lowres_planes, oracle_lookahead, lookahead_digest
+    w, h = size
+    g = port.geometry(w, h)
+    planes = lowres_planes(ref, g, synth.Clip(w, h, seed=31), 3)
+    a = oracle_lookahead(port, g, planes, method, 16, satd, weighted)
+    b = oracle_lookahead(ref, g, planes, method, 16, satd, weighted, is_ref=True)
+    sa, xa = lookahead_digest(a, g)
+    sb, xb = lookahead_digest(b, g)
+    assert np.array_equal(sa, sb), (sa, sb)
+    assert np.array_equal(xa, xb)

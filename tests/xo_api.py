@@ -43,6 +43,16 @@ class MeOut(C.Structure):
                 ("seed_mx", C.c_int), ("seed_my", C.c_int), ("seed_cost", C.c_int)]
 
 
+class LowresIn(C.Structure):
+    _fields_ = [("p0", C.c_int), ("p1", C.c_int), ("b", C.c_int), ("me_method", C.c_int), ("me_range", C.c_int),
+                ("mbcmp_satd", C.c_int), ("fpel_satd", C.c_int), ("b_weighted_bipred", C.c_int),
+                ("do_search", C.c_int * 2), ("b_intra_calculated", C.c_int)]
+
+
+class LowresOut(C.Structure):
+    _fields_ = [("score", C.c_int), ("score_aq", C.c_int), ("intra_mbs", C.c_int), ("intra_cost_sum", C.c_int)]
+
+
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
 i16p = C.POINTER(C.c_int16)
@@ -92,6 +102,10 @@ class Oracle:
         L.xo_quant_2x2_dc.argtypes = [i16p, C.c_int, C.c_int]
         for n in ("xo_dequant_4x4", "xo_dequant_8x8", "xo_dequant_4x4_dc"):
             getattr(L, n).argtypes = [i16p, i32p, C.c_int]
+        L.xo_lowres_frame_cost.argtypes = [C.POINTER(Geom), C.POINTER(LowresIn), C.POINTER(u8p), C.POINTER(u8p), C.POINTER(u8p),
+                                           i16p, i32p, i16p, i32p, i16p, u16p, C.POINTER(LowresOut)]
+        L.xo_lowres_intra_pred.argtypes = [C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
+        L.xo_lowres_intra_cost.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         self.backend = L.xo_backend().decode()
 
     # ---- convenience wrappers (numpy in / numpy out) ----
@@ -158,6 +172,26 @@ class Oracle:
                                      _ptr(integral, u16p, g.origin) if integral is not None else None, C.byref(mi),
                                      subme, mbcmp_satd, C.byref(out))
         return out
+
+
+    def lowres_frame_cost(self, g, fenc4, fref0_4, fref1_4, p0, p1, b, state, me_method=ME_HEX, me_range=16, mbcmp_satd=1,
+                          fpel_satd=0, weighted=0, do_search=(1, 1), b_intra_calculated=0):
+        """x264_slicetype_frame_cost on lowres planes.  state: dict of per-frame lookahead arrays that persist between calls —
+        'mvs0','mvs1' int16[n_mb,2]; 'costs0','costs1' int32[n_mb]; 'intra' uint16[n_mb]; 'ref1_mvs' int16[n_mb,2] (B only).
+        Updated in place.  Returns LowresOut (score is the raw sum for the port; the reference scales B scores, see xo.h)."""
+        li = LowresIn(p0, p1, b, me_method, me_range, mbcmp_satd, fpel_satd, weighted, (C.c_int * 2)(*do_search), b_intra_calculated)
+        mk = lambda planes: (u8p * 4)(*[_ptr(p, u8p, g.origin_lowres) for p in planes])
+        out = LowresOut()
+        self.lib.xo_lowres_frame_cost(C.byref(g), C.byref(li), mk(fenc4), mk(fref0_4), mk(fref1_4),
+                                      _ptr(state["mvs0"], i16p), _ptr(state["costs0"], i32p), _ptr(state["mvs1"], i16p),
+                                      _ptr(state["costs1"], i32p), _ptr(state["ref1_mvs"], i16p), _ptr(state["intra"], u16p), C.byref(out))
+        return out
+
+
+def lowres_state(g):
+    n = g.mb_width * g.mb_height
+    return {"mvs0": np.zeros((n, 2), np.int16), "mvs1": np.zeros((n, 2), np.int16), "costs0": np.zeros(n, np.int32),
+            "costs1": np.zeros(n, np.int32), "intra": np.zeros(n, np.uint16), "ref1_mvs": np.zeros((n, 2), np.int16)}
 
 
 _cache = {}

@@ -36,6 +36,7 @@ ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1")
 ME_FINAL = np.dtype([("mv", "<i2", (2,)), ("cost", "<i4"), ("cost_mv", "<i4"), ("bmx", "<i2"), ("bmy", "<i2")], align=True)
 ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_TESA, ME_METHOD_SEEDED = 0, 1, 4, 8
 ME_MBCMP_SATD = 8
+LOWRES_WEIGHTED_BIPRED = 16
 ME_RESULT = np.dtype([("bmx", "<i2"), ("bmy", "<i2"), ("bcost", "<i4"), ("seed_mx", "<i2"), ("seed_my", "<i2"),
                       ("seed_cost", "<i4")], align=True)
 ME_MB_PARTS, ME_MB_MVC = 9, 4
@@ -101,6 +102,10 @@ def lib():
         L.x264_cuda_me_search_small_dev.argtypes = [vp, vp, vp, ip, ip, ip, vp, ip, vp]
         L.x264_cuda_block_cmp.argtypes = [vp, ip, ip, ip, vp, vp, vp]
         L.x264_cuda_me_search_mb_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_frame_lookahead_alloc.argtypes = [vp, vp, ip]
+        L.x264_cuda_frame_lookahead_get.argtypes = [vp, vp, ip, ip, vp, vp, vp]
+        L.x264_cuda_frame_lookahead_set.argtypes = [vp, vp, ip, ip, vp, vp, vp]
+        L.x264_cuda_lowres_frame_cost.argtypes = [vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -156,6 +161,20 @@ class Frame:
 
     def init_lowres(self):
         self.ctx.check(lib().x264_cuda_frame_init_lowres(self.ctx.h, self.h))
+
+    def lookahead_alloc(self, n_dist):
+        """lowres_mvs / lowres_mv_costs / i_intra_cost of this frame (S/common/frame.c:85-98), zero-filled"""
+        self.ctx.check(lib().x264_cuda_frame_lookahead_alloc(self.ctx.h, self.h, n_dist))
+
+    def lookahead_get(self, lst, dist):
+        n = self.g.mb_width * self.g.mb_height
+        mvs, costs, intra = np.zeros((n, 2), np.int16), np.zeros(n, np.int32), np.zeros(n, np.uint16)
+        self.ctx.check(lib().x264_cuda_frame_lookahead_get(self.ctx.h, self.h, lst, dist, mvs.ctypes.data, costs.ctypes.data, intra.ctypes.data))
+        return mvs, costs, intra
+
+    def lookahead_set(self, lst, dist, mvs=None, costs=None, intra=None):
+        a = [None if x is None else np.ascontiguousarray(x, t) for x, t in ((mvs, np.int16), (costs, np.int32), (intra, np.uint16))]
+        self.ctx.check(lib().x264_cuda_frame_lookahead_set(self.ctx.h, self.h, lst, dist, *[None if x is None else x.ctypes.data for x in a]))
 
     def download(self, plane):
         """whole padded plane as a 2-D array (rows -32.., cols -32..)"""
@@ -282,6 +301,14 @@ class Context:
         res = np.zeros(len(jobs), ME_MB_RESULT)
         self.check(lib().x264_cuda_me_search_mb(self.h, fenc.h, fref.h, me_range, jobs.ctypes.data, len(jobs), res.ctypes.data))
         return res
+
+    def lowres_frame_cost(self, fenc, fref0, fref1, p0, p1, b, me_method=1, me_range=16, flags=ME_MBCMP_SATD, do_search=(1, 1),
+                          b_intra_calculated=0):
+        """x264_slicetype_frame_cost (S/encoder/slicetype.c:248-355) -> (score, intra_mbs, intra_cost_sum); score is the raw sum"""
+        pm = np.array([p0, p1, b, me_method, me_range, flags, do_search[0], do_search[1], b_intra_calculated], np.int32)
+        res = np.zeros(4, np.int32)
+        self.check(lib().x264_cuda_lowres_frame_cost(self.h, fenc.h, fref0.h, fref1.h, pm.ctypes.data, res.ctypes.data))
+        return int(res[0]), int(res[1]), int(res[2])
 
     def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
         self.check(lib().x264_cuda_me_search_mb_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

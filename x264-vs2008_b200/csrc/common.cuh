@@ -23,6 +23,7 @@ struct x264_cuda_t {
     void *d_cost_ptrs;            // device array of the 52 pointers above
     int cost_ptrs_dirty;
     // staging for the host-pointer entry points
+    int *d_la_order; int la_w, la_h, la_n; int la_epoch; int *d_la_sums; // lookahead wavefront order + result cells
     void *d_scratch; size_t d_scratch_size; // kernel-private scratch (TESA candidate lists)
     void *d_stage; size_t d_stage_size;
     void *h_stage; size_t h_stage_size; // pinned
@@ -47,6 +48,8 @@ struct x264_cuda_frame_t {
     uint8_t *buf_chroma;          // U then V, each stride_c*(lines/2+2*16)
     uint8_t *chroma[2];           // pixel (0,0) of U, V
     int stride_c;
+    // lookahead state (x264_cuda_frame_lookahead_alloc): lowres_mvs[2][n_dist][mb], lowres_mv_costs[2][n_dist][mb], i_intra_cost[mb]
+    int la_dist; int16_t *la_mvs; int *la_costs; int *la_intra; int *la_done;
     uint16_t *buf_integral;
     uint16_t *integral;           // element (0,0) of the 8x8-sum plane; the 4x4 plane follows
 };

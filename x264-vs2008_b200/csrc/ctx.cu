@@ -58,6 +58,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_qt);
     cudaFree(ctx->d_stage);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums);
     cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->own_stream);
     free(ctx);
@@ -162,6 +163,7 @@ extern "C" void x264_cuda_frame_delete(x264_cuda_frame_t *f)
     cudaFree(f->buf);
     cudaFree(f->buf_lowres);
     cudaFree(f->buf_chroma);
+    cudaFree(f->la_mvs); cudaFree(f->la_costs); cudaFree(f->la_intra); cudaFree(f->la_done);
     cudaFree(f->buf_integral);
     free(f);
 }

@@ -544,3 +544,394 @@ extern "C" int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel, in
     memcpy(out, hs + 2 * tb, ob);
     return 0;
 }
+
+// =====================================================================================================================
+// Lowres lookahead: x264_slicetype_frame_cost / x264_slicetype_mb_cost (S/encoder/slicetype.c:43-355)
+// =====================================================================================================================
+namespace {
+
+#define LA_F1(a, b) (((a) + (b) + 1) >> 1)
+#define LA_F2(a, b, c) (((a) + 2 * (b) + (c) + 2) >> 2)
+
+// one of the ten predictions of slicetype.c:205-229 at pixel (x,y) of the 8x8 block; tp[-1..15] row above, lf[0..7] left
+// column (raw), l[]/t[]/lt the filtered edge of x264_predict_8x8_filter (S/common/predict.c:499-540)
+struct Edge { int tp[17]; int lf[8]; int l[8]; int t[16]; int lt; int dc[4]; int pb, pc, pi00; };
+__device__ __forceinline__ int EL(const Edge &e, int k) { return k < 8 ? e.l[7 - k] : k == 8 ? e.lt : e.t[k - 9]; } // l7..l0, lt, t0..t7
+__device__ int intra_px(const Edge &e, int mode, int x, int y)
+{
+    switch (mode) {
+    case 0: return e.dc[(y >> 2) * 2 + (x >> 2)];                                  // predict_8x8c_dc, predict.c:234-277
+    case 1: return e.lf[y];                                                        // _h
+    case 2: return e.tp[x + 1];                                                    // _v
+    case 3: return clip_u8((e.pi00 + e.pc * y + e.pb * x) >> 5);                   // _p, predict.c:305-336
+    case 4: { const int k = x + y; return k == 14 ? LA_F2(e.t[14], e.t[15], e.t[15]) : LA_F2(e.t[k], e.t[k + 1], e.t[k + 2]); } // ddl
+    case 5: { const int k = 8 + x - y; return LA_F2(EL(e, k - 1), EL(e, k), EL(e, k + 1)); }                                   // ddr
+    case 6: { const int z = 2 * x - y;                                                                                        // vr
+              if (z >= 0) { const int k = 8 + x - (y >> 1); return (z & 1) ? LA_F2(EL(e, k - 1), EL(e, k), EL(e, k + 1)) : LA_F1(EL(e, k), EL(e, k + 1)); }
+              if (z == -1) return LA_F2(e.l[0], e.lt, e.t[0]);
+              const int k = y - 2 * x - 1; return LA_F2(e.l[k], e.l[k - 1], k - 2 >= 0 ? e.l[k - 2] : e.lt); }
+    case 7: { const int z = 2 * y - x;                                                                                        // hd
+              if (z >= 0) { const int k = 8 - y + (x >> 1); return (z & 1) ? LA_F2(EL(e, k - 1), EL(e, k), EL(e, k + 1)) : LA_F1(EL(e, k - 1), EL(e, k)); }
+              if (z == -1) return LA_F2(e.l[0], e.lt, e.t[0]);
+              const int k = x - 2 * y - 1; return LA_F2(e.t[k], e.t[k - 1], k - 2 >= 0 ? e.t[k - 2] : e.lt); }
+    case 8: { const int k = x + (y >> 1); return (y & 1) ? LA_F2(e.t[k], e.t[k + 1], e.t[k + 2]) : LA_F1(e.t[k], e.t[k + 1]); } // vl
+    default: { const int z = x + 2 * y;                                                                                       // hu
+               if (z > 13) return e.l[7];
+               if (z == 13) return LA_F2(e.l[6], e.l[7], e.l[7]);
+               const int k = y + (x >> 1); return (z & 1) ? LA_F2(e.l[k], e.l[k + 1], e.l[k + 2]) : LA_F1(e.l[k], e.l[k + 1]); }
+    }
+}
+
+// intra cost of every block (fully parallel, no dependencies): one thread per block, all threads of a warp walk the ten
+// modes together.  slicetype.c:192-233: min over the predictions of mbcmp(pred, fenc) + 5.
+__global__ void __launch_bounds__(64) lowres_intra_kernel(const uint8_t *__restrict__ l0, int stride, int W, int H, int satd, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const int mx = i % W, my = i / W;
+    const uint8_t *src = l0 + (size_t)(8 * my) * stride + 8 * mx;
+    Edge e;
+    for (int k = 0; k < 17; k++) e.tp[k] = src[-stride - 1 + k];
+    for (int k = 0; k < 8; k++) e.lf[k] = src[(ptrdiff_t)k * stride - 1];
+    const int *top = e.tp + 1;
+    e.lt = LA_F2(top[0], top[-1], e.lf[0]);
+    e.l[0] = LA_F2(top[-1], e.lf[0], e.lf[1]);
+    for (int y = 1; y < 7; y++) e.l[y] = LA_F2(e.lf[y - 1], e.lf[y], e.lf[y + 1]);
+    e.l[7] = (e.lf[6] + 3 * e.lf[7] + 2) >> 2;
+    e.t[0] = LA_F2(top[-1], top[0], top[1]);
+    for (int x = 1; x < 15; x++) e.t[x] = LA_F2(top[x - 1], top[x], top[x + 1]);
+    e.t[15] = (top[14] + 3 * top[15] + 2) >> 2;
+    {
+        int s0 = 0, s1 = 0, s2 = 0, s3 = 0, Hh = 0, V = 0;
+        for (int k = 0; k < 4; k++) {
+            s0 += top[k]; s1 += top[k + 4]; s2 += e.lf[k]; s3 += e.lf[k + 4];
+            Hh += (k + 1) * (top[4 + k] - top[2 - k]);
+            V += (k + 1) * (e.lf[4 + k] - (2 - k >= 0 ? e.lf[2 - k] : top[-1]));
+        }
+        e.dc[0] = (s0 + s2 + 4) >> 3; e.dc[1] = (s1 + 2) >> 2; e.dc[2] = (s3 + 2) >> 2; e.dc[3] = (s1 + s3 + 4) >> 3;
+        const int a = 16 * (e.lf[7] + top[7]);
+        e.pb = (17 * Hh + 16) >> 5; e.pc = (17 * V + 16) >> 5; e.pi00 = a - 3 * e.pb - 3 * e.pc + 16;
+    }
+    uint2 f[8];
+    for (int y = 0; y < 8; y++) f[y] = ldg8(src + (size_t)y * stride);
+    int best = 1 << 30;
+    for (int mode = 0; mode < 10; mode++) {
+        uint2 p[8];
+        for (int y = 0; y < 8; y++) {
+            uint32_t lo = 0, hi = 0;
+            for (int x = 0; x < 4; x++) { lo |= (uint32_t)intra_px(e, mode, x, y) << (8 * x); hi |= (uint32_t)intra_px(e, mode, x + 4, y) << (8 * x); }
+            p[y] = make_uint2(lo, hi);
+        }
+        int c;
+        if (satd) {
+            const uint2 fa[4] = { f[0], f[1], f[2], f[3] }, fb[4] = { f[4], f[5], f[6], f[7] };
+            const uint2 pa[4] = { p[0], p[1], p[2], p[3] }, pb[4] = { p[4], p[5], p[6], p[7] };
+            c = satd_8x4_rows(pa, fa) + satd_8x4_rows(pb, fb);
+        } else {
+            uint32_t acc = 0;
+            for (int y = 0; y < 8; y++) { acc = sad4_acc(p[y].x, f[y].x, acc); acc = sad4_acc(p[y].y, f[y].y, acc); }
+            c = (int)acc;
+        }
+        best = min(best, c);
+    }
+    out[i] = best + 5;
+}
+
+struct LaArgs {
+    const uint8_t *fenc[4], *ref[2][4];
+    int stride, W, H;
+    int16_t *mvs[2]; int *costs[2]; const int16_t *ref1_mvs; int *intra; int *done; const int *order; int n_order;
+    int *ticket, *sums; // sums: score, intra_mbs, intra_cost_sum
+    int epoch, b_bidir, b_any_inter, dsf, weight, method, me_range, do_search0, do_search1, mbcmp_satd, fpel_satd;
+    const int16_t *tab; // p_cost_mv (qp 12) centre
+};
+
+__device__ __forceinline__ int ld_vol(const int *p) { return *(const volatile int *)p; }
+
+// TRY_BIDIR (slicetype.c:96-112): lanes 0/1 own the two 8x4 units of the block
+__device__ int bidir_cost(const LaArgs &a, const uint8_t *fe, size_t off, int mv0x, int mv0y, int mv1x, int mv1y, int lane)
+{
+    int v = 0;
+    if (lane < 2) {
+        const uint8_t *const p0[4] = { a.ref[0][0] + off, a.ref[0][1] + off, a.ref[0][2] + off, a.ref[0][3] + off };
+        const uint8_t *const p1[4] = { a.ref[1][0] + off, a.ref[1][1] + off, a.ref[1][2] + off, a.ref[1][3] + off };
+        const QpelSrc s0 = qpel_src(p0, a.stride, mv0x, mv0y), s1 = qpel_src(p1, a.stride, mv1x, mv1y);
+        uint2 f[4], r[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const ptrdiff_t o = (ptrdiff_t)(4 * lane + y) * a.stride;
+            f[y] = ldg8(fe + o);
+            const uint2 x0 = qpel_row8(s0, o), x1 = qpel_row8(s1, o);
+            if (a.weight == 32) r[y] = make_uint2(__vavgu4(x0.x, x1.x), __vavgu4(x0.y, x1.y)); // pixel_avg_wxh, mc.c:52-62
+            else { // pixel_avg_weight_wxh, mc.c:64-97
+                uint32_t w[2] = { 0, 0 };
+                const uint32_t xa[2] = { x0.x, x0.y }, xb[2] = { x1.x, x1.y };
+                for (int k = 0; k < 8; k++) {
+                    const int pa = (xa[k >> 2] >> (8 * (k & 3))) & 255, pb = (xb[k >> 2] >> (8 * (k & 3))) & 255;
+                    w[k >> 2] |= (uint32_t)clip_u8((pa * a.weight + pb * (64 - a.weight) + 32) >> 6) << (8 * (k & 3));
+                }
+                r[y] = make_uint2(w[0], w[1]);
+            }
+        }
+        if (a.mbcmp_satd) v = satd_8x4_rows(f, r);
+        else {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int y = 0; y < 4; y++) { acc = sad4_acc(f[y].x, r[y].x, acc); acc = sad4_acc(f[y].y, r[y].y, acc); }
+            v = (int)acc;
+        }
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+__global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
+{
+    __shared__ x264_cuda_me_job_t s_job[4];
+    __shared__ x264_cuda_me_final_t s_fin[4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.n_order) return;
+        const int xy = a.order[t], mx = xy % a.W, my = xy / a.W;
+        const size_t off = (size_t)(8 * my) * a.stride + 8 * mx;
+        const uint8_t *fe = a.fenc[0] + off;
+        int bcost = COST_MAX;
+        if (a.b_any_inter) {
+            // wait for the blocks whose vectors this one predicts from: right, below, below-left, below-right (slicetype.c:153-166)
+            if (a.do_search0 | a.do_search1) {
+                if (lane < 4) {
+                    const int dx = lane == 0 ? 1 : lane == 1 ? 0 : lane == 2 ? -1 : 1, dy = lane == 0 ? 0 : 1;
+                    const int nx = mx + dx, ny = my + dy;
+                    // only blocks evaluated in this call carry a flag: the interior ones (or all of them for tiny frames)
+                    const bool small = a.W <= 2 || a.H <= 2;
+                    const bool inside = small ? (nx >= 0 && nx < a.W && ny >= 0 && ny < a.H) : (nx >= 1 && nx <= a.W - 2 && ny >= 1 && ny <= a.H - 2);
+                    if (inside) while (ld_vol(a.done + nx + ny * a.W) != a.epoch) __nanosleep(40);
+                }
+                __syncwarp();
+                __threadfence();
+            }
+            const int fx_min = -8 * mx - 4, fx_max = 8 * (a.W - mx - 1) + 4, fy_min = -8 * my - 4, fy_max = 8 * (a.H - my - 1) + 4; // slicetype.c:75-85
+            const int sx_min = 4 * (fx_min - 8), sx_max = 4 * (fx_max + 8), sy_min = 4 * (fy_min - 8), sy_max = 4 * (fy_max + 8);
+            int mvx[2] = { 0, 0 }, mvy[2] = { 0, 0 };
+            if (a.b_bidir) { // slicetype.c:121-142
+                const int rx = a.ref1_mvs[2 * xy], ry = a.ref1_mvs[2 * xy + 1];
+                int d0x = (rx * a.dsf + 128) >> 8, d0y = (ry * a.dsf + 128) >> 8;
+                int d1x = d0x - rx, d1y = d0y - ry;
+                d0x = clip3i(d0x, sx_min, sx_max); d0y = clip3i(d0y, sy_min, sy_max);
+                d1x = clip3i(d1x, sx_min, sx_max); d1y = clip3i(d1y, sy_min, sy_max);
+                bcost = min(bcost, bidir_cost(a, fe, off, d0x, d0y, d1x, d1y, lane));
+                if (d0x | d0y | d1x | d1y) bcost = min(bcost, bidir_cost(a, fe, off, 0, 0, 0, 0, lane));
+            }
+            for (int l = 0; l < 1 + a.b_bidir; l++) {
+                int cost;
+                if (l ? a.do_search1 : a.do_search0) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        x264_cuda_me_job_t &j = s_job[wid];
+                        const volatile int16_t *fm = a.mvs[l] + 2 * xy; // written by other warps of this launch: no caching
+                        int n = 0;
+                        int16_t c[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+#define LA_MVC(o) { c[n][0] = fm[2 * (o)]; c[n][1] = fm[2 * (o) + 1]; n++; }
+                        if (mx < a.W - 1) LA_MVC(1);
+                        if (my < a.H - 1) {
+                            LA_MVC(a.W);
+                            if (mx > 0) LA_MVC(a.W - 1);
+                            if (mx < a.W - 1) LA_MVC(a.W + 1);
+                        }
+#undef LA_MVC
+                        j.bx = 8 * mx; j.by = 8 * my; j.i_pixel = X264_CUDA_PIXEL_8x8; j.qp = 12; j.i_mvc = n;
+                        j.flags = (a.fpel_satd ? X264_CUDA_ME_FPEL_SATD : 0) | (a.mbcmp_satd ? X264_CUDA_ME_MBCMP_SATD : 0);
+                        for (int k = 0; k < 2; k++) { // x264_median_mv(mvc[0], mvc[1], mvc[2])
+                            const int p = c[0][k], q = c[1][k], r = c[2][k];
+                            j.mvp[k] = (int16_t)max(min(p, q), min(max(p, q), r));
+                        }
+                        for (int k = 0; k < 4; k++) { j.mvc[k][0] = c[k][0]; j.mvc[k][1] = c[k][1]; }
+                        j.mv_min_fpel[0] = fx_min; j.mv_max_fpel[0] = fx_max; j.mv_min_fpel[1] = fy_min; j.mv_max_fpel[1] = fy_max;
+                        j.mv_min_spel[0] = sx_min; j.mv_max_spel[0] = sx_max; j.mv_min_spel[1] = sy_min; j.mv_max_spel[1] = sy_max;
+                    }
+                    __syncwarp();
+                    const x264_cuda_me_job_t &job = s_job[wid];
+                    SearchCtx c;
+                    c.stride = a.stride; c.bw = 8; c.bh = 8; c.units = 2; c.U = 2; c.fe = fe;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) c.planes[k] = a.ref[l][k] + off;
+                    c.cmx = a.tab - job.mvp[0]; c.cmy = a.tab - job.mvp[1];
+                    c.fpel_satd = a.fpel_satd; c.mbcmp_satd = a.mbcmp_satd;
+                    c.i_pixel = X264_CUDA_PIXEL_8x8; c.sums8 = c.sums4 = nullptr; c.list = nullptr; c.list_cap = 0; c.lines_pad = 0;
+                    warp_search(c, job, a.method, a.me_range, 4, lane, &s_fin[wid]);
+                    __syncwarp();
+                    const x264_cuda_me_final_t fin = s_fin[wid];
+                    cost = fin.cost - 2;                                  // slicetype.c:169-171
+                    if (fin.mv[0] | fin.mv[1]) cost += 5;
+                    mvx[l] = fin.mv[0]; mvy[l] = fin.mv[1];
+                    if (lane == 0) {
+                        *(volatile int *)(a.mvs[l] + 2 * xy) = (int)(((uint32_t)(uint16_t)fin.mv[0]) | ((uint32_t)(uint16_t)fin.mv[1] << 16));
+                        a.costs[l][xy] = cost;
+                    }
+                } else {
+                    mvx[l] = a.mvs[l][2 * xy]; mvy[l] = a.mvs[l][2 * xy + 1]; cost = a.costs[l][xy];
+                }
+                bcost = min(bcost, cost);
+            }
+            if (a.b_bidir && (mvx[0] | mvy[0] | mvx[1] | mvy[1])) bcost = min(bcost, 5 + bidir_cost(a, fe, off, mvx[0], mvy[0], mvx[1], mvy[1], lane));
+        }
+        int b_intra = 0, icost = 0;
+        if (!a.b_bidir) { // slicetype.c:189-245
+            icost = a.intra[xy];
+            b_intra = icost < bcost;
+            if (b_intra) bcost = icost;
+        }
+        if (lane == 0) {
+            __threadfence();
+            *(volatile int *)(a.done + xy) = a.epoch;
+            atomicAdd(a.sums + 0, bcost);
+            if (!a.b_bidir && mx > 0 && mx < a.W - 1 && my > 0 && my < a.H - 1) { atomicAdd(a.sums + 1, b_intra); atomicAdd(a.sums + 2, icost); }
+        }
+    }
+}
+
+} // namespace
+
+extern "C" int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame_t *f, int n_dist)
+{
+    if (!(f->g.flags & X264_CUDA_FRAME_LOWRES) || n_dist < 1 || n_dist > 17) {
+        snprintf(ctx->err, 256, "x264_cuda_frame_lookahead_alloc: frame needs X264_CUDA_FRAME_LOWRES and 1 <= n_dist <= 17");
+        return -1;
+    }
+    const size_t n_mb = (size_t)f->g.mb_width * f->g.mb_height;
+    cudaFree(f->la_mvs); cudaFree(f->la_costs); cudaFree(f->la_intra); cudaFree(f->la_done);
+    f->la_mvs = nullptr; f->la_costs = nullptr; f->la_intra = nullptr; f->la_done = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&f->la_mvs, 2 * n_dist * n_mb * 4));
+    CUDA_TRY(ctx, cudaMalloc(&f->la_costs, 2 * n_dist * n_mb * 4));
+    CUDA_TRY(ctx, cudaMalloc(&f->la_intra, n_mb * 4));
+    CUDA_TRY(ctx, cudaMalloc(&f->la_done, n_mb * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->la_mvs, 0, 2 * n_dist * n_mb * 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->la_costs, 0, 2 * n_dist * n_mb * 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->la_intra, 0, n_mb * 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->la_done, 0, n_mb * 4, ctx->stream));
+    f->la_dist = n_dist;
+    return 0;
+}
+
+static int la_check(x264_cuda_t *ctx, const x264_cuda_frame_t *f, int list, int dist)
+{
+    if (!f->la_mvs || list < 0 || list > 1 || dist < 0 || dist >= f->la_dist) {
+        snprintf(ctx->err, 256, "x264_cuda lookahead: no state for list %d distance %d (x264_cuda_frame_lookahead_alloc)", list, dist);
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int x264_cuda_frame_lookahead_get(x264_cuda_t *ctx, const x264_cuda_frame_t *f, int list, int dist, int16_t *mvs, int *costs,
+                                             uint16_t *intra_cost)
+{
+    if (la_check(ctx, f, list, dist)) return -1;
+    const size_t n_mb = (size_t)f->g.mb_width * f->g.mb_height, o = ((size_t)list * f->la_dist + dist) * n_mb;
+    if (mvs) CUDA_TRY(ctx, cudaMemcpyAsync(mvs, f->la_mvs + 2 * o, n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (costs) CUDA_TRY(ctx, cudaMemcpyAsync(costs, f->la_costs + o, n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (intra_cost) {
+        int *tmp = (int *)malloc(n_mb * 4);
+        cudaError_t e = cudaMemcpy(tmp, f->la_intra, n_mb * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < n_mb; i++) intra_cost[i] = (uint16_t)tmp[i];
+        free(tmp);
+        if (e != cudaSuccess) return x264_cuda_fail(ctx, "lookahead_get", e);
+    }
+    return 0;
+}
+
+extern "C" int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_frame_t *f, int list, int dist, const int16_t *mvs, const int *costs,
+                                             const uint16_t *intra_cost)
+{
+    if (la_check(ctx, f, list, dist)) return -1;
+    const size_t n_mb = (size_t)f->g.mb_width * f->g.mb_height, o = ((size_t)list * f->la_dist + dist) * n_mb;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (mvs) CUDA_TRY(ctx, cudaMemcpy(f->la_mvs + 2 * o, mvs, n_mb * 4, cudaMemcpyHostToDevice));
+    if (costs) CUDA_TRY(ctx, cudaMemcpy(f->la_costs + o, costs, n_mb * 4, cudaMemcpyHostToDevice));
+    if (intra_cost) {
+        int *tmp = (int *)malloc(n_mb * 4);
+        for (size_t i = 0; i < n_mb; i++) tmp[i] = intra_cost[i];
+        cudaError_t e = cudaMemcpy(f->la_intra, tmp, n_mb * 4, cudaMemcpyHostToDevice);
+        free(tmp);
+        if (e != cudaSuccess) return x264_cuda_fail(ctx, "lookahead_set", e);
+    }
+    return 0;
+}
+
+extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
+                                           const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *pm, x264_cuda_lowres_result_t *result)
+{
+    const x264_cuda_geom_t &g = fenc->g;
+    const int W = g.mb_width, H = g.mb_height, b_bidir = pm->b < pm->p1, any = !(pm->p0 == pm->p1 && pm->p0 == pm->b);
+    if (!fenc->lowres[0] || !fref0->lowres[0] || !fref1->lowres[0] || fref0->g.stride_lowres != g.stride_lowres || fref1->g.stride_lowres != g.stride_lowres) {
+        snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: frames need X264_CUDA_FRAME_LOWRES and equal geometry");
+        return -1;
+    }
+    const int d0 = pm->b - pm->p0 - 1, d1 = pm->p1 - pm->b - 1;
+    if (!fenc->la_mvs || (any && (d0 < 0 || d0 >= fenc->la_dist)) || (b_bidir && (d1 < 0 || d1 >= fenc->la_dist || !fref1->la_mvs || pm->p1 - pm->p0 - 1 >= fref1->la_dist))) {
+        snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: lookahead state missing or distance out of range");
+        return -1;
+    }
+    const int16_t *const *d_tabs;
+    if (!ctx->d_cost_mv[12]) { // the lookahead always works at qp 12 (slicetype.c:35)
+        int16_t *t = (int16_t *)malloc((4 * 4 * 2048 + 1) * sizeof(int16_t));
+        x264_cuda_host_cost_mv(12, t);
+        int rc = x264_cuda_set_cost_mv(ctx, 12, t);
+        free(t);
+        if (rc) return -1;
+    }
+    if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
+    // wavefront order: interior blocks (all blocks for tiny frames) by x + 2y descending
+    if (ctx->la_w != W || ctx->la_h != H) {
+        const bool small = W <= 2 || H <= 2;
+        int *ord = (int *)malloc((size_t)W * H * sizeof(int)), n = 0;
+        for (int v = (W - 1) + 2 * (H - 1); v >= 0; v--)
+            for (int y = H - 1; y >= 0; y--) {
+                const int x = v - 2 * y;
+                if (x < 0 || x >= W) continue;
+                if (!small && (x < 1 || x > W - 2 || y < 1 || y > H - 2)) continue;
+                ord[n++] = x + y * W;
+            }
+        cudaFree(ctx->d_la_order); ctx->d_la_order = nullptr;
+        if (!ctx->d_la_sums) CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_sums, 8 * sizeof(int)));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_order, (size_t)W * H * sizeof(int)));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_la_order, ord, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        free(ord);
+        ctx->la_w = W; ctx->la_h = H; ctx->la_n = n;
+    }
+    const size_t n_mb = (size_t)W * H;
+    if (!b_bidir && !pm->b_intra_calculated) {
+        lowres_intra_kernel<<<(int)((n_mb + 63) / 64), 64, 0, ctx->stream>>>(fenc->lowres[0], g.stride_lowres, W, H, !!(pm->flags & X264_CUDA_ME_MBCMP_SATD), fenc->la_intra);
+        LAUNCH_CHECK(ctx, "lowres_intra_kernel");
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_la_sums, 0, 8 * sizeof(int), ctx->stream));
+    LaArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int k = 0; k < 4; k++) { a.fenc[k] = fenc->lowres[k]; a.ref[0][k] = fref0->lowres[k]; a.ref[1][k] = fref1->lowres[k]; }
+    a.stride = g.stride_lowres; a.W = W; a.H = H;
+    a.mvs[0] = fenc->la_mvs + 2 * ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb; a.costs[0] = fenc->la_costs + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
+    a.mvs[1] = fenc->la_mvs + 2 * ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb; a.costs[1] = fenc->la_costs + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
+    a.ref1_mvs = b_bidir ? fref1->la_mvs + 2 * ((size_t)(pm->p1 - pm->p0 - 1)) * n_mb : nullptr;
+    a.intra = fenc->la_intra; a.done = fenc->la_done; a.order = ctx->d_la_order; a.n_order = ctx->la_n;
+    a.ticket = ctx->d_la_sums + 4; a.sums = ctx->d_la_sums;
+    a.epoch = ++ctx->la_epoch; a.b_bidir = b_bidir; a.b_any_inter = any;
+    a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
+    a.weight = (pm->flags & X264_CUDA_LOWRES_WEIGHTED_BIPRED) ? 64 - (a.dsf >> 2) : 32;                          // slicetype.c:57
+    a.method = pm->me_method < 1 ? X264_CUDA_ME_METHOD_DIA : X264_CUDA_ME_METHOD_HEX;                            // min(HEX, me), slicetype.c:38
+    a.me_range = pm->me_range; a.do_search0 = pm->do_search[0]; a.do_search1 = pm->do_search[1];
+    a.mbcmp_satd = !!(pm->flags & X264_CUDA_ME_MBCMP_SATD); a.fpel_satd = !!(pm->flags & X264_CUDA_ME_FPEL_SATD);
+    a.tab = ctx->d_cost_mv[12] + 2 * 4 * 2048;
+    // persistent warps pulling tickets in wavefront order: every ticket's dependencies hold smaller tickets, so a waiting
+    // warp only ever waits for warps that are already running (no co-residency assumption beyond one CTA per SM slot)
+    const int blocks = min((ctx->la_n + 3) / 4, ctx->sm_count * 2);
+    lowres_cost_kernel<<<blocks, 128, 0, ctx->stream>>>(a);
+    LAUNCH_CHECK(ctx, "lowres_cost_kernel");
+    int sums[8];
+    CUDA_TRY(ctx, cudaMemcpyAsync(sums, ctx->d_la_sums, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    result->score = sums[0]; result->intra_mbs = sums[1]; result->intra_cost_sum = sums[2]; result->reserved = 0;
+    return 0;
+}
