@@ -21,7 +21,11 @@ import __graft_entry__ as ge  # noqa: E402
 
 pkg = ge.load_pkg()
 from x264_vs2008_b200 import synth  # noqa: E402
-from helpers import make_me_jobs  # noqa: E402
+from helpers import make_me_jobs, lowres_planes, oracle_lookahead, lookahead_digest  # noqa: E402
+
+
+LOOKAHEAD_GOLDEN = (("qcif_hex_satd", (176, 144), X.ME_HEX, 1, 0), ("qcif_dia_sad", (176, 144), X.ME_DIA, 0, 0),
+                    ("w208_hex_satd_wb", (208, 112), X.ME_HEX, 1, 1), ("tiny", (32, 64), X.ME_HEX, 1, 0))
 
 
 def sha(a):
@@ -91,6 +95,12 @@ def main():
                     o = r.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
                     res.append((method, 10 + subme, o.mv[0], o.mv[1], o.cost, o.cost_mv))
     out["me_results"] = np.array(res, np.int32)
+    # ---- lowres lookahead schedule (I, P, P dist 2, B, cached) through the reference's x264_rc_analyse_slice
+    for tag, (w, h), method, satd, weighted in LOOKAHEAD_GOLDEN:
+        g = r.geometry(w, h)
+        planes = lowres_planes(r, g, synth.Clip(w, h, seed=31), 3)
+        scal, arrs = lookahead_digest(oracle_lookahead(r, g, planes, method, 16, satd, weighted, is_ref=True), g)
+        out["la_%s_scalars" % tag], out["la_%s_arrays" % tag] = scal, arrs.astype(np.int32)
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")), "bytes")
 
