@@ -243,8 +243,12 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
     ctx.set_cost_mv(QP)
 
-    # ---- inputs: a ring of frame pairs (each rank gets its own seeded content: frames shard across GPUs)
-    clip = synth.Clip(W, H, seed=1 + rank)
+    # ---- inputs: the job is world x RING_PAIRS frame pairs; each rank owns a contiguous shard of them (weak scaling:
+    # per-GPU work is fixed, no data-path collective — x264-vs2008_b200/shard.py)
+    from x264_vs2008_b200 import shard
+    pair_lo, pair_hi = shard.frame_shard(world * RING_PAIRS, world, rank)
+    assert pair_hi - pair_lo == RING_PAIRS
+    clip = synth.Clip(W, H, seed=1 + pair_lo // RING_PAIRS)
     n_frames = 2 * RING_PAIRS
     host_pics = torch.empty((n_frames, H, W), dtype=torch.uint8).pin_memory()
     base = [clip.luma(i) for i in range(8)]
@@ -307,7 +311,7 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall
     launches = ctx.launches() - l0
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(kernel_ms))
+    total_ms = float(evs[0][0].elapsed_time(evs[-1][1]))  # the whole K-step bracket on the device (gaps included)
     cands = sum(cands_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
     sadops = sum(sadops_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
 
@@ -346,15 +350,7 @@ def run_ours(args):
     d2h = n_jobs * pkg.ME_RESULT.itemsize
 
     # ---- max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
-        c = torch.tensor([cands, sadops], device="cuda", dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        cands_all, sadops_all = float(c[0]), float(c[1])
-    else:
-        cands_all, sadops_all = float(cands), float(sadops)
+    (total_ms, e2e_ms), (cands_all, sadops_all) = shard.reduce_job(dist if world > 1 else None, "cuda", [total_ms, e2e_ms], [cands, sadops])
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
