@@ -315,26 +315,66 @@ def run_ours(args):
     cands = sum(cands_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
     sadops = sum(sadops_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region
-    fe, fr = ctx.frame(W, H, 0), ctx.frame(W, H, 0)
-    h_res = torch.zeros(n_jobs * pkg.ME_RESULT.itemsize, dtype=torch.uint8).pin_memory()
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  Every step uploads its two pictures from
+    # pinned host memory, expands their borders, uploads the job list, searches, and reads all results back to the host.
+    # (a) serial: one host thread, one context, each call waits for its results before the next picture is sent;
+    # (b) pipelined: T host threads, each with its own context + stream + frame pair, i.e. T frames in flight — the
+    #     reference's own frame-threading model (one x264_t per frame in flight, S/encoder/encoder.c:1569-1608), which
+    #     lets copies of one frame overlap the search of another.  The headline e2e.value is (b); (a) is reported beside it.
+    import threading
+    T = max(1, args.e2e_threads)
+    lanes = []
+    for t in range(T):
+        c = ctx if t == 0 else pkg.Context(local)
+        st = stream if t == 0 else torch.cuda.Stream()
+        if t:
+            c.set_stream(st.cuda_stream)
+            c.set_cost_mv(QP)
+        lanes.append({"ctx": c, "stream": st, "fe": c.frame(W, H, 0), "fr": c.frame(W, H, 0),
+                      "res": torch.zeros(n_jobs * pkg.ME_RESULT.itemsize, dtype=torch.uint8).pin_memory()})
+    L = pkg.lib()
 
-    def step_e2e(i):
+    def step_e2e(ln, i):
         p = i % RING_PAIRS
-        fe.upload(host_pics[2 * p + 1].numpy()); fe.expand_border()
-        fr.upload(host_pics[2 * p].numpy()); fr.expand_border()
-        pkg.lib().x264_cuda_me_search_mb(ctx.h, fe.h, fr.h, ME_RANGE, h_mbjobs.data_ptr(), n_mb, h_res.data_ptr())
+        c = ln["ctx"]
+        ln["fe"].upload(host_pics[2 * p + 1].numpy()); ln["fe"].expand_border()
+        ln["fr"].upload(host_pics[2 * p].numpy()); ln["fr"].expand_border()
+        c.check(L.x264_cuda_me_search_mb(c.h, ln["fe"].h, ln["fr"].h, ME_RANGE, h_mbjobs.data_ptr(), n_mb, ln["res"].data_ptr()))
 
     for i in range(args.warmup):
-        step_e2e(i)
+        for ln in lanes:
+            step_e2e(ln, i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
-        step_e2e(args.warmup + i)
+        step_e2e(lanes[0], args.warmup + i)
+    e1.record(stream)
+    barrier()
+    e2e_serial_ms = e0.elapsed_time(e1)
+
+    def lane_loop(t):
+        for i in range(t, args.steps, T):
+            step_e2e(lanes[t], args.warmup + i)
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ths = [threading.Thread(target=lane_loop, args=(t,)) for t in range(T)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()  # every call is synchronous: when the threads are done, so are all copies and kernels
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    # the e2e path must return what the resident path computes for the same pair (checked on every lane's last step)
+    for t in range(min(T, args.steps)):
+        i_last = ((args.steps - 1 - t) // T) * T + t
+        step_resident(args.warmup + i_last)
+        torch.cuda.synchronize()
+        if not np.array_equal(d_res.cpu().numpy(), lanes[t]["res"].numpy()):
+            raise SystemExit("bench.py: e2e results differ from the resident-path results (lane %d)" % t)
     clocks = sampler.stop()
     # secondary: the same searches as 73440 independent per-block jobs (x264_cuda_me_search, no SAD sharing)
     for i in range(3):
@@ -371,7 +411,9 @@ def run_ours(args):
                        "cands_per_step": cands // args.steps,
                        "l2": "inputs cycle through a %d-pair ring of padded planes (%.0f MB) > 126 MB L2" % (RING_PAIRS, n_frames * g.stride * (g.lines + 64) / 1e6)},
             "e2e": {"value": cands_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps, "frames_in_flight": T,
+                    "serial": {"value": cands / (e2e_serial_ms * 1e-3) / 1e9, "ms_per_step": e2e_serial_ms / args.steps,
+                               "note": "one host thread, each call waits for its results before the next picture is sent (this rank)"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
@@ -389,7 +431,11 @@ def run_ours(args):
         print(json.dumps(line))
     for f in frames:
         f.close()
-    fe.close(); fr.close(); ctx.close()
+    for ln in lanes:
+        ln["fe"].close(); ln["fr"].close()
+        if ln["ctx"] is not ctx:
+            ln["ctx"].close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -397,10 +443,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="frames in flight (host threads, one context each) in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

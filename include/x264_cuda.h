@@ -47,6 +47,14 @@ X264_CUDA_API int x264_cuda_sm_count(const x264_cuda_t *ctx);
 /* roofline denominator for the SAD kernels: measured whole-GPU rate of VABSDIFF4.U8.ACC (thread-ops / second) */
 X264_CUDA_API int x264_cuda_measure_int_pipe(x264_cuda_t *ctx, double *sad4_per_sec);
 
+/* Page-locked host memory.  Every entry point accepts ordinary (pageable) host pointers; job lists, result arrays and picture
+ * planes that live in memory from x264_cuda_host_alloc (a drop-in for x264_malloc, S/common/common.c:700-721) or registered
+ * with x264_cuda_host_register are DMA'd directly instead of being copied through the context's staging buffer. */
+X264_CUDA_API void *x264_cuda_host_alloc(size_t bytes);
+X264_CUDA_API void x264_cuda_host_free(void *p);
+X264_CUDA_API int x264_cuda_host_register(void *p, size_t bytes);
+X264_CUDA_API int x264_cuda_host_unregister(void *p);
+
 /* ------------------------------------------------------------------ frames ------------------------- */
 /* Mirrors x264_frame_new (S/common/frame.c:29-152): a luma plane with PADH=PADV=32 borders, optionally the
  * three half-pel planes (filtered[1..3]), the integral image(s) and the four half-resolution planes.

@@ -56,6 +56,10 @@ struct x264_cuda_frame_t {
 
 int x264_cuda_fail(x264_cuda_t *ctx, const char *what, cudaError_t e);
 int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes);
+// caller memory <-> device.  Page-locked caller memory (x264_cuda_host_alloc / x264_cuda_host_register) is DMA'd directly;
+// pageable memory goes through the pinned stage at `hs`.  results_out also waits for the stream (the call's completion point).
+int x264_cuda_jobs_in(x264_cuda_t *ctx, void *d, const void *h, void *hs, size_t n);
+int x264_cuda_results_out(x264_cuda_t *ctx, void *h, const void *d, void *hs, size_t n);
 int x264_cuda_cost_tables(x264_cuda_t *ctx, const int16_t *const **d_ptrs); // device array of 52 table pointers
 
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return x264_cuda_fail((ctx), #call, e_); } while (0)

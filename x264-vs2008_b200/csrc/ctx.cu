@@ -99,6 +99,44 @@ int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes)
     return 0;
 }
 
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+int x264_cuda_jobs_in(x264_cuda_t *ctx, void *d, const void *h, void *hs, size_t n)
+{
+    if (!is_pinned(h)) { memcpy(hs, h, n); h = hs; }
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int x264_cuda_results_out(x264_cuda_t *ctx, void *h, const void *d, void *hs, size_t n)
+{
+    const bool direct = is_pinned(h);
+    CUDA_TRY(ctx, cudaMemcpyAsync(direct ? h : hs, d, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!direct) memcpy(h, hs, n);
+    return 0;
+}
+extern "C" void *x264_cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void x264_cuda_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int x264_cuda_host_register(void *p, size_t bytes)
+{
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+extern "C" int x264_cuda_host_unregister(void *p)
+{
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+
 // ------------------------------------------------------------------ frames
 static inline int align_up(int x, int a) { return (x + a - 1) & ~(a - 1); }
 

@@ -67,8 +67,7 @@ extern "C" int x264_cuda_mc_blocks(x264_cuda_t *ctx, const x264_cuda_frame_t *fr
     if (n_jobs <= 0) return 0;
     const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_mc_job_t);
     if (x264_cuda_stage(ctx, jb, jb)) return -1;
-    memcpy(ctx->h_stage, jobs, jb);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, jb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x264_cuda_jobs_in(ctx, ctx->d_stage, jobs, ctx->h_stage, jb)) return -1;
     if (x264_cuda_mc_blocks_dev(ctx, fref, fdec, ctx->d_stage, n_jobs)) return -1;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

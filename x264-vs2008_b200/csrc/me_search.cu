@@ -296,12 +296,9 @@ extern "C" int x264_cuda_me_search(x264_cuda_t *ctx, const x264_cuda_frame_t *fe
     const size_t jb_al = (jb + 255) & ~(size_t)255;
     if (x264_cuda_stage(ctx, jb_al + rb, jb_al + rb)) return -1;
     uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
-    memcpy(hs, jobs, jb); // pageable caller memory -> pinned staging, so the copies below are truly asynchronous
-    CUDA_TRY(ctx, cudaMemcpyAsync(ds, hs, jb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x264_cuda_jobs_in(ctx, ds, jobs, hs, jb)) return -1;
     if (x264_cuda_me_search_dev(ctx, fenc, fref, me_range, ds, n_jobs, ds + jb_al)) return -1;
-    CUDA_TRY(ctx, cudaMemcpyAsync(hs + jb_al, ds + jb_al, rb, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(results, hs + jb_al, rb);
+    if (x264_cuda_results_out(ctx, results, ds + jb_al, hs + jb_al, rb)) return -1;
     return 0;
 }
 
