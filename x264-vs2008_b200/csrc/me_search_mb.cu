@@ -20,7 +20,7 @@ struct Geo { const uint8_t *fenc; const uint8_t *fref; int stride; };
 #define MB_WARPS 4
 #define MB_MAX_RANGE 64   // larger ranges go through the per-block kernel (x264_cuda_me_search)
 #define MB_MAX_UW 128     // union window limits; beyond them partitions are searched one at a time
-#define MB_MAX_UR 192
+#define MB_UNION_SLACK 31 // rows the union may exceed a single window's 2*me_range+1 by (the y-cost table is sized for that)
 #define NP X264_CUDA_ME_MB_PARTS
 #define NCAND (X264_CUDA_ME_MB_MVC + 2)
 #define INVALID_COST 0x3ffff // above any real cost (<= 65280 + 2*~2.6k); three of them still fit the key's 20 cost bits
@@ -32,7 +32,6 @@ struct Geo { const uint8_t *fenc; const uint8_t *fref; int stride; };
 
 struct __align__(16) WarpSmem {
     uint32_t F[16][4];                       // fenc macroblock, 256 B (read as uint4 rows: keep 16-byte aligned)
-    uint32_t cyt[MB_MAX_UR + 4][12];         // per union row: 9 partition y-costs, pre-shifted, | row<<2 (+3 pad)
     x264_cuda_me_mb_job_t job;               // 280 B
     int quad[NP * NCAND][4];                 // predictor stage: 8x8 quadrant SADs of every (partition, candidate)
     int pc_x[NP * NCAND], pc_y[NP * NCAND];
@@ -49,6 +48,7 @@ __device__ __forceinline__ void load_row16(uint32_t (&dst)[4], const uint8_t *p,
     for (int i = 0; i < 4; i++) dst[i] = __funnelshift_r(w[i], w[i + 1], sh);
 }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // quadrants (bit q: TL,TR,BL,BR) making up partition p
 __device__ __forceinline__ unsigned part_quads(int p)
@@ -74,20 +74,33 @@ __device__ __forceinline__ int sad_quad(const uint32_t (*F)[4], int q, const uin
 }
 
 // The exhaustive pass over the union window of the partitions in `mask`.  Returns per-lane best keys in best[].
-__device__ __forceinline__ void scan_union(WarpSmem &S, const int16_t *tab, const uint8_t *ref0, int stride, unsigned mask,
+// cyt: per union row the 9 partition y-costs, pre-shifted, | row<<2 (+3 pad) — dynamic smem of 2*me_range+1+MB_UNION_SLACK+4
+// rows (a small table leaves the L1 to the window tiles)
+__device__ __forceinline__ void scan_union(WarpSmem &S, uint32_t (*cyt)[12], const int16_t *tab, const uint8_t *ref0, int stride, unsigned mask,
                                            int ux0, int uy0, int uwidth, int urows, int lane, uint32_t (&best)[NP])
 {
     const x264_cuda_me_mb_job_t &job = S.job;
-    // y-cost table for the whole union: cyt[r][p] = (cost_y << KEY_SHIFT) | r << 2, INVALID outside p's row range
+    // y-cost table for the whole union: cyt[r][p] = (cost_y << KEY_SHIFT) | r << 2, INVALID outside p's row range.
+    // Lane -> (partition p = lane % 9, row phase lane / 9); four rows per trip so that the table loads overlap.
     __syncwarp();
-    for (int i = lane; i < (urows + 3) * 12; i += 32) {
-        const int r = i / 12, p = i - r * 12;
-        uint32_t v = INVALID_COST;
-        if (p < NP && r < urows && (mask >> p & 1)) {
-            const int my = uy0 + r;
-            if (my >= S.win[p][1] && my < S.win[p][1] + S.win[p][3]) v = (uint32_t)tab[(my << 2) - job.mvp[p][1]];
+    if (lane < 27) {
+        const int p = lane % 9, ph = lane / 9;
+        const bool on = mask >> p & 1;
+        const int wy0 = S.win[p][1] - uy0, wy1 = wy0 + S.win[p][3];
+        const int16_t *ty = tab + ((uy0 << 2) - job.mvp[p][1]);
+        for (int r0 = ph; r0 < urows + 3; r0 += 12) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = r0 + 3 * k;
+                v[k] = (on && r >= wy0 && r < wy1) ? (uint32_t)ty[r << 2] : INVALID_COST;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = r0 + 3 * k;
+                if (r < urows + 3) cyt[r][p] = (v[k] << KEY_SHIFT) | ((uint32_t)min(r, 255) << 2);
+            }
         }
-        S.cyt[r][p] = (v << KEY_SHIFT) | ((uint32_t)min(r, 255) << 2);
     }
     __syncwarp();
     const uint4 *F4 = (const uint4 *)&S.F[0][0];
@@ -126,7 +139,7 @@ __device__ __forceinline__ void scan_union(WarpSmem &S, const int16_t *tab, cons
                 const int r = base + j;
                 if (r >= seg_rows) break; // warp-uniform
                 load_row16(R[(j + 15) % 16], pr + (size_t)(r + 15) * stride, sh);
-                const uint4 *cy4 = (const uint4 *)&S.cyt[rbeg + r][0];
+                const uint4 *cy4 = (const uint4 *)&cyt[rbeg + r][0];
                 const uint4 ca = cy4[0], cb = cy4[1], cc = cy4[2];
                 // eight independent accumulator chains (two per 8x8 quadrant) keep the ALU pipe fed
                 uint32_t tl = 0, tr = 0, bl = 0, br = 0, tl2 = 0, tr2 = 0, bl2 = 0, br2 = 0;
@@ -152,17 +165,28 @@ __device__ __forceinline__ void scan_union(WarpSmem &S, const int16_t *tab, cons
 
 __global__ void __launch_bounds__(MB_WARPS * 32, 3)
 me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int n_jobs,
-                    const int16_t *const *__restrict__ cost_tabs, int me_range, x264_cuda_me_mb_result_t *__restrict__ results)
+                    const int16_t *const *__restrict__ cost_tabs, int me_range, int max_ur, int prefetch_dist,
+                    x264_cuda_me_mb_result_t *__restrict__ results)
 {
     __shared__ __align__(16) WarpSmem s_all[MB_WARPS];
+    extern __shared__ __align__(16) uint32_t s_cyt[]; // MB_WARPS x (max_ur + 4) x 12
     const int lane = threadIdx.x & 31;
     WarpSmem &S = s_all[threadIdx.x >> 5];
+    uint32_t (*cyt)[12] = (uint32_t (*)[12])(s_cyt + (size_t)(threadIdx.x >> 5) * (max_ur + 4) * 12);
     const int stride = geo.stride;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jb < n_jobs; jb += warps_per_grid) {
         __syncwarp();
         for (int i = lane; i < (int)(sizeof(x264_cuda_me_mb_job_t) / 4); i += 32)
             ((uint32_t *)&S.job)[i] = __ldg((const uint32_t *)(jobs + jb) + i);
+        // the macroblock that will run in this warp's slot roughly one residency later: pull its job and pixels into L2
+        // now (first-touch HBM latency is the main cost of the short phases before the scan)
+        const int jn = jb + prefetch_dist;
+        uint32_t next_pos = 0xffffffffu; // mb_x | mb_y << 16 of that job
+        if (jn < n_jobs) {
+            next_pos = __ldg((const uint32_t *)(jobs + jn));
+            if (lane < 3) prefetch_l2((const uint8_t *)(jobs + jn) + 128 * lane);
+        }
         __syncwarp();
         const x264_cuda_me_mb_job_t &job = S.job;
         const int16_t *tab = cost_tabs[job.qp > 51 ? 51 : job.qp] + 2 * 4 * 2048;
@@ -205,12 +229,19 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
                 S.pc_x[idx] = cx; S.pc_y[idx] = valid ? cy : (1 << 20); // pc_y == 1<<20 marks "skip"
             }
             __syncwarp();
-            for (int t = lane; t < NP * NCAND * 4; t += 32) { // (item, quadrant) tasks
-                const int idx = t >> 2, q = t & 3, p = idx / NCAND;
-                int v = 0;
-                if (S.pc_y[idx] != (1 << 20) && (part_quads(p) >> q & 1))
-                    v = sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + S.pc_y[idx]) * stride + (q & 1) * 8 + S.pc_x[idx], stride);
-                S.quad[idx][q] = v;
+            // (item, quadrant) tasks, two per trip so that their 48 row loads are in flight together
+            for (int t0 = lane; t0 < NP * NCAND * 4; t0 += 64) {
+                int v[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int t = t0 + 32 * u, idx = min(t >> 2, NP * NCAND - 1), q = t & 3, p = idx / NCAND;
+                    v[u] = 0;
+                    if (t < NP * NCAND * 4 && S.pc_y[idx] != (1 << 20) && (part_quads(p) >> q & 1))
+                        v[u] = sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + S.pc_y[idx]) * stride + (q & 1) * 8 + S.pc_x[idx], stride);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                    if (t0 + 32 * u < NP * NCAND * 4) S.quad[(t0 + 32 * u) >> 2][(t0 + 32 * u) & 3] = v[u];
             }
             __syncwarp();
             if (lane < NP) {
@@ -244,6 +275,14 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
         }
         __syncwarp();
 
+        // ---- that later macroblock: fenc rows and a reference tile displaced like this macroblock's first window
+        if (next_pos != 0xffffffffu) {
+            const size_t o = (size_t)(next_pos >> 16) * 16 * stride + (next_pos & 0xffff) * 16;
+            if (lane < 16) prefetch_l2(geo.fenc + o + (size_t)lane * stride);
+            const uint8_t *t = geo.fref + o + (ptrdiff_t)(S.seed[0][1] - me_range) * stride + (S.seed[0][0] - me_range);
+            for (int r = lane; r < 2 * me_range + 16; r += 32) { prefetch_l2(t + (size_t)r * stride); prefetch_l2(t + (size_t)r * stride + 2 * me_range + 15); }
+        }
+
         // ---- exhaustive pass(es): all partitions over the union of their windows when it is compact, else one by one
         unsigned todo = mask;
         int my_bmx = 0, my_bmy = 0, my_cost = INVALID_COST; // lane p keeps partition p's window winner
@@ -255,7 +294,7 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
             ux0 = __reduce_min_sync(0xffffffffu, ux0); uy0 = __reduce_min_sync(0xffffffffu, uy0);
             ux1 = __reduce_max_sync(0xffffffffu, ux1); uy1 = __reduce_max_sync(0xffffffffu, uy1);
             unsigned group = todo;
-            if (ux1 - ux0 > MB_MAX_UW || uy1 - uy0 > MB_MAX_UR) { // scattered predictors: search the lowest partition alone
+            if (ux1 - ux0 > MB_MAX_UW || uy1 - uy0 > max_ur) { // scattered predictors: search the lowest partition alone
                 const int p = __ffs(todo) - 1;
                 group = 1u << p;
                 ux0 = S.win[p][0]; uy0 = S.win[p][1]; ux1 = ux0 + S.win[p][2]; uy1 = uy0 + S.win[p][3];
@@ -264,7 +303,7 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
             uint32_t best[NP];
 #pragma unroll
             for (int p = 0; p < NP; p++) best[p] = 0xffffffffu;
-            scan_union(S, tab, ref0, stride, group, ux0, uy0, ux1 - ux0, uy1 - uy0, lane, best);
+            scan_union(S, cyt, tab, ref0, stride, group, ux0, uy0, ux1 - ux0, uy1 - uy0, lane, best);
             // warp argmin per partition: min key (cost,row,chunk), then the lowest in-chunk column among its holders
             const int uwidth = ux1 - ux0;
 #pragma unroll
@@ -311,9 +350,12 @@ extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_fram
     const int16_t *const *d_tabs;
     if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
     Geo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
+    const int max_ur = 2 * me_range + 1 + MB_UNION_SLACK;
+    const size_t dyn = (size_t)MB_WARPS * (max_ur + 4) * 12 * sizeof(uint32_t);
     const int blocks = (n_jobs + MB_WARPS - 1) / MB_WARPS;
-    me_search_mb_kernel<<<blocks, MB_WARPS * 32, 0, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
-                                                                   (x264_cuda_me_mb_result_t *)d_results);
+    const int prefetch_dist = MB_WARPS * 3 * ctx->sm_count; // warps resident at once (168 registers: three CTAs per SM)
+    me_search_mb_kernel<<<blocks, MB_WARPS * 32, dyn, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
+                                                                     max_ur, prefetch_dist, (x264_cuda_me_mb_result_t *)d_results);
     LAUNCH_CHECK(ctx, "me_search_mb_kernel");
     return 0;
 }
