@@ -228,6 +228,27 @@ X264_CUDA_API int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_
                                               const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *params,
                                               x264_cuda_lowres_result_t *result);
 
+/* ------------------------------------------------------------------ in-loop deblocking ---------------- */
+/* x264_frame_deblock (S/common/frame.c:794-799 -> x264_frame_deblock_row :621-792) of one progressive frame, in place on the
+ * device frame's luma and chroma planes (X264_CUDA_FRAME_CHROMA).  The per-macroblock arrays are the reference's own, in its
+ * layouts (S/common/common.h:420-436, i_mb_stride == mb_width): h->mb.type, h->mb.qp, h->mb.mb_transform_size,
+ * h->mb.non_zero_count ([mb][16+4+4]), h->mb.ref[l] (8x8 grid, stride 2*mb_width), h->mb.mv[l] (4x4 grid, stride 4*mb_width);
+ * list-1 arrays may be NULL unless b_slice_b.  MBAFF (sh.b_mbaff) is not supported.  Called where the reference calls
+ * x264_frame_deblock_row for the last row of a frame (S/encoder/encoder.c:1009-1014, single-thread schedule). */
+typedef struct x264_cuda_deblock_params_t {
+    int alpha_c0_offset, beta_offset;   /* h->sh.i_alpha_c0_offset, h->sh.i_beta_offset */
+    int chroma_qp_offset;               /* h->pps->i_chroma_qp_index_offset */
+    int b_slice_b;                      /* h->sh.i_type == SLICE_TYPE_B */
+    int b_psub8x8;                      /* h->param.analyse.inter & X264_ANALYSE_PSUB8x8 */
+    int b_cavlc_8x8dct;                 /* !h->pps->b_cabac && h->pps->b_transform_8x8_mode (nnz munging, frame.c:334-373) */
+} x264_cuda_deblock_params_t;
+X264_CUDA_API int x264_cuda_frame_deblock(x264_cuda_t *ctx, x264_cuda_frame_t *fdec, const x264_cuda_deblock_params_t *params,
+                                          const int8_t *type, const int8_t *qp, const int8_t *transform8x8, const uint8_t (*nnz)[24],
+                                          const int8_t *ref0, const int16_t (*mv0)[2], const int8_t *ref1, const int16_t (*mv1)[2]);
+X264_CUDA_API int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_t *fdec, const x264_cuda_deblock_params_t *params,
+                                              const int8_t *d_type, const int8_t *d_qp, const int8_t *d_transform8x8, const uint8_t *d_nnz,
+                                              const int8_t *d_ref0, const int16_t *d_mv0, const int8_t *d_ref1, const int16_t *d_mv1);
+
 /* ------------------------------------------------------------------ motion compensation -------------- */
 /* Frame-batched x264_mb_mc_0xywh (S/common/macroblock.c:462-486): for each job the w x h luma block at (bx,by) is
  * predicted from fref at quarter-pel mv (mc_luma, S/common/mc.c:160-179) and, when both frames carry chroma planes, the

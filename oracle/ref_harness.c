@@ -505,3 +505,47 @@ int xo_lowres_intra_cost(const uint8_t *l0, int stride, int bx, int by, int mbcm
     }
     return best + 5;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* deblocking through the reference's own x264_frame_deblock_row (S/common/frame.c:621-792)          */
+void xo_frame_deblock(const xo_geom *g, const xo_deblock_in *d, uint8_t *py, uint8_t *pu, uint8_t *pv, int stride_c)
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, X264_ME_ESA, 1, 0, 1, &f); /* the i_bframe > 0 handle: its frames carry list-1 mv/ref arrays */
+    static x264_t *fd_h[64];
+    static x264_frame_t *fd_f[64];
+    int k = 0;
+    while (k < 63 && fd_h[k] && fd_h[k] != h) k++;
+    if (!fd_h[k]) { fd_h[k] = h; fd_f[k] = x264_frame_new(h); } /* fdec is only attached by x264_encoder_encode: give it one */
+    x264_frame_t *fd = fd_f[k];
+    h->fdec = fd;
+    /* x264_macroblock_slice_init (S/common/macroblock.c:777-781): per-macroblock state lives in the frame being decoded */
+    h->mb.mv[0] = fd->mv[0]; h->mb.mv[1] = fd->mv[1]; h->mb.ref[0] = fd->ref[0]; h->mb.ref[1] = fd->ref[1]; h->mb.type = fd->mb_type;
+    const int n = g->mb_width * g->mb_height;
+    for (int y = 0; y < g->lines; y++) memcpy(fd->plane[0] + y * fd->i_stride[0], py + y * g->stride, 16 * g->mb_width);
+    for (int y = 0; y < g->lines / 2; y++) {
+        memcpy(fd->plane[1] + y * fd->i_stride[1], pu + y * stride_c, 8 * g->mb_width);
+        memcpy(fd->plane[2] + y * fd->i_stride[2], pv + y * stride_c, 8 * g->mb_width);
+    }
+    const int save_inter = h->param.analyse.inter, save_off = h->param.analyse.i_chroma_qp_offset;
+    h->sh.i_alpha_c0_offset = d->alpha_c0_offset; h->sh.i_beta_offset = d->beta_offset; h->sh.b_mbaff = 0;
+    h->sh.i_type = d->b_slice_b ? SLICE_TYPE_B : SLICE_TYPE_P;
+    h->param.analyse.i_chroma_qp_offset = d->chroma_qp_offset;
+    h->chroma_qp_table = i_chroma_qp_table + 12 + d->chroma_qp_offset;
+    h->param.analyse.inter = d->b_psub8x8 ? (save_inter | X264_ANALYSE_PSUB8x8) : (save_inter & ~X264_ANALYSE_PSUB8x8);
+    x264_pps_t *pps = (x264_pps_t *)h->pps;
+    const int save_cabac = pps->b_cabac, save_t8 = pps->b_transform_8x8_mode;
+    if (d->b_cavlc_8x8dct) { pps->b_cabac = 0; pps->b_transform_8x8_mode = 1; } else pps->b_cabac = 1;
+    memcpy(h->mb.type, d->type, n); memcpy(h->mb.qp, d->qp, n); memcpy(h->mb.mb_transform_size, d->transform8x8, n);
+    memcpy(h->mb.non_zero_count, d->nnz, (size_t)n * 24);
+    for (int l = 0; l < 2; l++) { memcpy(h->mb.ref[l], d->ref[l], (size_t)n * 4); memcpy(h->mb.mv[l], d->mv[l], (size_t)n * 16 * 4); }
+    for (int mb_y = 0; mb_y < g->mb_height; mb_y++) x264_frame_deblock_row(h, mb_y);
+    for (int y = 0; y < g->lines; y++) memcpy(py + y * g->stride, fd->plane[0] + y * fd->i_stride[0], 16 * g->mb_width);
+    for (int y = 0; y < g->lines / 2; y++) {
+        memcpy(pu + y * stride_c, fd->plane[1] + y * fd->i_stride[1], 8 * g->mb_width);
+        memcpy(pv + y * stride_c, fd->plane[2] + y * fd->i_stride[2], 8 * g->mb_width);
+    }
+    h->param.analyse.inter = save_inter; h->param.analyse.i_chroma_qp_offset = save_off;
+    h->chroma_qp_table = i_chroma_qp_table + 12 + save_off;
+    pps->b_cabac = save_cabac; pps->b_transform_8x8_mode = save_t8;
+}

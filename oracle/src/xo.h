@@ -181,6 +181,24 @@ void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_
 void xo_lowres_intra_pred(int mode, const uint8_t *l0, int stride, int bx, int by, uint8_t out[64]);
 int xo_lowres_intra_cost(const uint8_t *l0, int stride, int bx, int by, int mbcmp_satd);
 
+/* ---------------- in-loop deblocking of one progressive frame: S/common/frame.c:376-800 ----------------
+ * Arrays use the reference's own layouts (S/common/common.h:420-436) with i_mb_stride = mb_width: type/qp/transform8x8
+ * per macroblock; nnz[mb][24] (first 16 = luma 4x4 blocks, raster x+4y); ref[l] per 8x8 block on the frame-wide 8x8 grid
+ * (stride 2*mb_width); mv[l] per 4x4 block on the frame-wide 4x4 grid (stride 4*mb_width).  Planes are filtered in place
+ * (pixel 0,0 pointers; luma stride g->stride). */
+typedef struct {
+    int alpha_c0_offset, beta_offset;   /* sh.i_alpha_c0_offset, sh.i_beta_offset (= 2 x the --deblock arguments) */
+    int chroma_qp_offset;               /* pps->i_chroma_qp_index_offset == param.analyse.i_chroma_qp_offset */
+    int b_slice_b;                      /* sh.i_type == SLICE_TYPE_B */
+    int b_psub8x8;                      /* param.analyse.inter & X264_ANALYSE_PSUB8x8 */
+    int b_cavlc_8x8dct;                 /* !pps->b_cabac && pps->b_transform_8x8_mode */
+    const int8_t *type, *qp, *transform8x8;
+    const uint8_t (*nnz)[24];
+    const int8_t *ref[2];
+    const int16_t (*mv[2])[2];
+} xo_deblock_in;
+void xo_frame_deblock(const xo_geom *g, const xo_deblock_in *d, uint8_t *py, uint8_t *pu, uint8_t *pv, int stride_c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,3 +182,87 @@ def lookahead_digest(res, g):
     scal = np.array([(r[1], r[2], r[3]) for r in res], np.int64)
     arrs = [np.concatenate([r[4][m].ravel().astype(np.int64), r[5][m], r[6][m].ravel().astype(np.int64), r[7][m], r[8][m].astype(np.int64)]) for r in res]
     return scal, np.stack(arrs)
+
+
+# ---------------- deblocking (S/common/frame.c:621-792) ----------------
+def make_deblock_info(g, seed, slice_b=0, psub8x8=1, cavlc_8x8dct=0, alpha=0, beta=0, chroma_off=0, chaos=False, qp_centre=30):
+    """per-macroblock state in the reference's layouts (h->mb.type/qp/mb_transform_size/non_zero_count/ref/mv).
+    chaos=False: what an encoder produces (vectors constant per partition, refs -1 for intra ...);
+    chaos=True: every array independently random — the filter's decisions must match for ANY contents."""
+    rng = np.random.default_rng(seed)
+    W, H = g.mb_width, g.mb_height
+    n = W * H
+    if slice_b:
+        types = np.array([0, 2, 7, 8, 12, 16, 17, 18], np.int8)
+        tp = np.array([.05, .05, .1, .25, .15, .15, .1, .15])
+    else:
+        types = np.array([0, 1, 2, 4, 5, 6], np.int8)
+        tp = np.array([.06, .04, .06, .44, .15, .25])
+    mtype = rng.choice(types, n, p=tp).astype(np.int8)
+    qp = np.clip(rng.normal(qp_centre, 7, n).round(), 0, 51).astype(np.int8)
+    qp[rng.random(n) < 0.05] = rng.integers(0, 16)
+    intra = mtype <= 3
+    skip = (mtype == 6) | (mtype == 18)
+    t8 = ((rng.random(n) < 0.3) & ~skip & (mtype != 2)).astype(np.int8)
+    t8[mtype == 1] = 1
+    nnz = np.zeros((n, 24), np.uint8)
+    dense = rng.random(n) < 0.5
+    nnz[:] = (rng.random((n, 24)) < np.where(dense, 0.5, 0.08)[:, None]) * rng.integers(1, 17, (n, 24))
+    nnz[skip] = 0
+    ref = [np.zeros((2 * H, 2 * W), np.int8) for _ in range(2)]
+    mv = [np.zeros((4 * H, 4 * W, 2), np.int16) for _ in range(2)]
+    base = np.array([-20, -12]) + rng.integers(-3, 4, 2)
+    for mb in range(n):
+        my, mx = divmod(mb, W)
+        for l in range(2):
+            if intra[mb] or (l == 1 and not slice_b):
+                ref[l][2 * my:2 * my + 2, 2 * mx:2 * mx + 2] = -1
+                continue
+            r8 = rng.integers(0, 2, (2, 2)) if rng.random() < 0.15 else np.full((2, 2), rng.integers(0, 2) if rng.random() < 0.2 else 0)
+            if slice_b and rng.random() < 0.3:
+                r8 = np.full((2, 2), -1)  # list unused by this macroblock
+            ref[l][2 * my:2 * my + 2, 2 * mx:2 * mx + 2] = r8
+            v16 = base + rng.integers(-5, 6, 2)
+            blk = np.broadcast_to(v16, (4, 4, 2)).copy()
+            if mtype[mb] in (5, 17):  # 8x8 partitions, optionally 4x4 sub-partitions
+                for by in range(2):
+                    for bx in range(2):
+                        blk[2 * by:2 * by + 2, 2 * bx:2 * bx + 2] = v16 + rng.integers(-4, 5, 2)
+                        if psub8x8 and rng.random() < 0.4:
+                            blk[2 * by:2 * by + 2, 2 * bx:2 * bx + 2] += rng.integers(-4, 5, (2, 2, 2))
+            elif rng.random() < 0.3:  # 16x8 / 8x16
+                if rng.random() < 0.5:
+                    blk[2:] = v16 + rng.integers(-6, 7, 2)
+                else:
+                    blk[:, 2:] = v16 + rng.integers(-6, 7, 2)
+            mv[l][4 * my:4 * my + 4, 4 * mx:4 * mx + 4] = blk
+    if chaos:
+        mtype = rng.integers(0, 19, n).astype(np.int8)
+        t8 = rng.integers(0, 2, n).astype(np.int8)
+        nnz = (rng.integers(0, 3, (n, 24)) * (rng.random((n, 24)) < 0.4)).astype(np.uint8)
+        ref = [rng.integers(-1, 2, (2 * H, 2 * W)).astype(np.int8) for _ in range(2)]
+        mv = [(base + rng.integers(-5, 6, (4 * H, 4 * W, 2))).astype(np.int16) for _ in range(2)]
+    return {"alpha_c0_offset": alpha, "beta_offset": beta, "chroma_qp_offset": chroma_off, "b_slice_b": slice_b, "b_psub8x8": psub8x8,
+            "b_cavlc_8x8dct": cavlc_8x8dct, "type": np.ascontiguousarray(mtype), "qp": np.ascontiguousarray(qp),
+            "transform8x8": np.ascontiguousarray(t8), "nnz": np.ascontiguousarray(nnz),
+            "ref0": np.ascontiguousarray(ref[0]), "ref1": np.ascontiguousarray(ref[1]),
+            "mv0": np.ascontiguousarray(mv[0]), "mv1": np.ascontiguousarray(mv[1])}
+
+
+def blocky_recon(clip, g, frame=0, seed=0):
+    """a 'reconstructed' picture with coding artefacts: synthetic content quantised per 4x4/8x8 block (DC steps + noise)"""
+    rng = np.random.default_rng(seed)
+    y, u, v = clip.yuv420(frame)
+    W16, H16 = 16 * g.mb_width, 16 * g.mb_height
+    def pad(a, w, h):
+        out = np.zeros((h, w), np.uint8)
+        out[:a.shape[0], :a.shape[1]] = a
+        out[a.shape[0]:, :a.shape[1]] = a[-1:, :]
+        out[:, a.shape[1]:] = out[:, a.shape[1] - 1:a.shape[1]]
+        return out
+    y, u, v = pad(y, W16, H16), pad(u, W16 // 2, H16 // 2), pad(v, W16 // 2, H16 // 2)
+    def blockify(a, bs):
+        h, w = a.shape
+        off = rng.integers(-6, 7, (h // bs, w // bs))
+        return np.clip(a.astype(np.int32) + np.kron(off, np.ones((bs, bs), np.int32)) + rng.integers(-1, 2, a.shape), 0, 255).astype(np.uint8)
+    return blockify(y, 4), blockify(u, 2), blockify(v, 2)

@@ -143,3 +143,28 @@ def test_lowres_lookahead(pkg, port, ref, size, method, satd, weighted):
     sb, xb = lookahead_digest(b, g)
     assert np.array_equal(sa, sb), (sa, sb)
     assert np.array_equal(xa, xb)
+
+
+@pytest.mark.parametrize("size,kw", [((176, 144), dict()), ((176, 144), dict(slice_b=1)), ((208, 112), dict(cavlc_8x8dct=1, alpha=-2, beta=2, chroma_off=3)),
+                                     ((64, 48), dict(chaos=True)), ((96, 80), dict(chaos=True, slice_b=1, cavlc_8x8dct=1, alpha=6, beta=-4, chroma_off=-5)),
+                                     ((176, 144), dict(psub8x8=0, qp_centre=18, alpha=-6, beta=-6)), ((32, 16), dict(qp_centre=45, alpha=12, beta=12))])
+def test_deblock(pkg, port, ref, size, kw):
+    """x264_frame_deblock_row over a whole frame: reference vs port, encoder-like and fully random macroblock state"""
+    from x264_vs2008_b200 import synth
+    from helpers import make_deblock_info, blocky_recon
+    w, h = size
+    g = port.geometry(w, h)
+    for seed in range(3):
+        info = make_deblock_info(g, seed=100 + seed, **kw)
+        y, u, v = blocky_recon(synth.Clip(w, h, seed=5), g, seed=seed)
+        outs = []
+        for o in (port, ref):
+            py = o.new_plane(g)
+            pad = py.reshape(-1, g.stride)
+            pad[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]] = y
+            uu, vv = u.copy(), v.copy()
+            o.frame_deblock(g, info, py, uu, vv)
+            outs.append((py.copy(), uu, vv))
+        assert not np.array_equal(outs[0][0].reshape(-1, g.stride)[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]], y)  # something was filtered
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)

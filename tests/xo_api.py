@@ -53,6 +53,13 @@ class LowresOut(C.Structure):
     _fields_ = [("score", C.c_int), ("score_aq", C.c_int), ("intra_mbs", C.c_int), ("intra_cost_sum", C.c_int)]
 
 
+class DeblockIn(C.Structure):
+    _fields_ = [("alpha_c0_offset", C.c_int), ("beta_offset", C.c_int), ("chroma_qp_offset", C.c_int), ("b_slice_b", C.c_int),
+                ("b_psub8x8", C.c_int), ("b_cavlc_8x8dct", C.c_int),
+                ("type", C.c_void_p), ("qp", C.c_void_p), ("transform8x8", C.c_void_p), ("nnz", C.c_void_p),
+                ("ref", C.c_void_p * 2), ("mv", C.c_void_p * 2)]
+
+
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
 i16p = C.POINTER(C.c_int16)
@@ -106,6 +113,7 @@ class Oracle:
                                            i16p, i32p, i16p, i32p, i16p, u16p, C.POINTER(LowresOut)]
         L.xo_lowres_intra_pred.argtypes = [C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
         L.xo_lowres_intra_cost.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.xo_frame_deblock.argtypes = [C.POINTER(Geom), C.POINTER(DeblockIn), u8p, u8p, u8p, C.c_int]
         self.backend = L.xo_backend().decode()
 
     # ---- convenience wrappers (numpy in / numpy out) ----
@@ -174,6 +182,11 @@ class Oracle:
         return out
 
 
+    def frame_deblock(self, g, info, y, u, v):
+        """y: padded luma plane (flat, pixel 0,0 at g.origin); u, v: 2-D chroma arrays (contiguous).  Filtered in place."""
+        d = deblock_in(info)
+        self.lib.xo_frame_deblock(C.byref(g), C.byref(d), _ptr(y, u8p, g.origin), _ptr(u), _ptr(v), u.shape[1])
+
     def lowres_frame_cost(self, g, fenc4, fref0_4, fref1_4, p0, p1, b, state, me_method=ME_HEX, me_range=16, mbcmp_satd=1,
                           fpel_satd=0, weighted=0, do_search=(1, 1), b_intra_calculated=0):
         """x264_slicetype_frame_cost on lowres planes.  state: dict of per-frame lookahead arrays that persist between calls —
@@ -186,6 +199,16 @@ class Oracle:
                                       _ptr(state["mvs0"], i16p), _ptr(state["costs0"], i32p), _ptr(state["mvs1"], i16p),
                                       _ptr(state["costs1"], i32p), _ptr(state["ref1_mvs"], i16p), _ptr(state["intra"], u16p), C.byref(out))
         return out
+
+
+def deblock_in(info):
+    """info: dict from helpers.make_deblock_info -> (DeblockIn, keepalive)"""
+    d = DeblockIn(info["alpha_c0_offset"], info["beta_offset"], info["chroma_qp_offset"], info["b_slice_b"], info["b_psub8x8"],
+                  info["b_cavlc_8x8dct"])
+    d.type, d.qp, d.transform8x8, d.nnz = (info[k].ctypes.data for k in ("type", "qp", "transform8x8", "nnz"))
+    d.ref[0], d.ref[1] = info["ref0"].ctypes.data, info["ref1"].ctypes.data
+    d.mv[0], d.mv[1] = info["mv0"].ctypes.data, info["mv1"].ctypes.data
+    return d
 
 
 def lowres_state(g):

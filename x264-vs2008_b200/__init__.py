@@ -106,6 +106,13 @@ def lib():
         L.x264_cuda_frame_lookahead_get.argtypes = [vp, vp, ip, ip, vp, vp, vp]
         L.x264_cuda_frame_lookahead_set.argtypes = [vp, vp, ip, ip, vp, vp, vp]
         L.x264_cuda_lowres_frame_cost.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_frame_deblock.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_frame_deblock_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_host_alloc.argtypes = [C.c_size_t]
+        L.x264_cuda_host_alloc.restype = vp
+        L.x264_cuda_host_free.argtypes = [vp]
+        L.x264_cuda_host_register.argtypes = [vp, C.c_size_t]
+        L.x264_cuda_host_unregister.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -309,6 +316,16 @@ class Context:
         res = np.zeros(4, np.int32)
         self.check(lib().x264_cuda_lowres_frame_cost(self.h, fenc.h, fref0.h, fref1.h, pm.ctypes.data, res.ctypes.data))
         return int(res[0]), int(res[1]), int(res[2])
+
+    def frame_deblock(self, fdec, info):
+        """x264_frame_deblock (S/common/frame.c:621-799) in place on fdec's luma + chroma planes.  info: dict with the reference's
+        per-macroblock arrays (type, qp, transform8x8, nnz[n,24], ref0/ref1 [2H,2W], mv0/mv1 [4H,4W,2]) and the slice parameters."""
+        pm = np.array([info["alpha_c0_offset"], info["beta_offset"], info["chroma_qp_offset"], info["b_slice_b"], info["b_psub8x8"],
+                       info["b_cavlc_8x8dct"]], np.int32)
+        arr = {k: np.ascontiguousarray(info[k], t) for k, t in (("type", np.int8), ("qp", np.int8), ("transform8x8", np.int8), ("nnz", np.uint8),
+                                                               ("ref0", np.int8), ("mv0", np.int16), ("ref1", np.int8), ("mv1", np.int16))}
+        self.check(lib().x264_cuda_frame_deblock(self.h, fdec.h, pm.ctypes.data, *[arr[k].ctypes.data for k in
+                                                 ("type", "qp", "transform8x8", "nnz", "ref0", "mv0", "ref1", "mv1")]))
 
     def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
         self.check(lib().x264_cuda_me_search_mb_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

@@ -38,7 +38,8 @@ class Clip:
         for r in self.rects:
             x0 = (r["x"] + n * r["vx"]) % max(1, self.w - r["w"])
             y0 = (r["y"] + n * r["vy"]) % max(1, self.h - r["h"])
-            y[y0:y0 + r["h"], x0:x0 + r["w"]] = r["tex"]
+            sub = y[y0:y0 + r["h"], x0:x0 + r["w"]]
+            sub[...] = r["tex"][:sub.shape[0], :sub.shape[1]]  # (cropped only for pictures smaller than a rectangle)
         if self.noise:
             rng = np.random.default_rng(self.seed * 1000003 + n)
             y = y + rng.integers(-self.noise, self.noise + 1, y.shape, dtype=np.int16)
