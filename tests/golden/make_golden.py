@@ -21,11 +21,16 @@ import __graft_entry__ as ge  # noqa: E402
 
 pkg = ge.load_pkg()
 from x264_vs2008_b200 import synth  # noqa: E402
-from helpers import make_me_jobs, lowres_planes, oracle_lookahead, lookahead_digest  # noqa: E402
+from helpers import make_me_jobs, lowres_planes, oracle_lookahead, lookahead_digest, make_deblock_info, blocky_recon  # noqa: E402
 
 
 LOOKAHEAD_GOLDEN = (("qcif_hex_satd", (176, 144), X.ME_HEX, 1, 0), ("qcif_dia_sad", (176, 144), X.ME_DIA, 0, 0),
                     ("w208_hex_satd_wb", (208, 112), X.ME_HEX, 1, 1), ("tiny", (32, 64), X.ME_HEX, 1, 0))
+
+
+DEBLOCK_GOLDEN = (("qcif_p", (176, 144), dict()), ("qcif_b", (176, 144), dict(slice_b=1)),
+                  ("w208_cavlc8", (208, 112), dict(cavlc_8x8dct=1, alpha=-2, beta=2, chroma_off=3)),
+                  ("chaos_b", (96, 80), dict(chaos=True, slice_b=1, cavlc_8x8dct=1, alpha=6, beta=-4, chroma_off=-5)), ("cif_p", (352, 288), dict(qp_centre=34)))
 
 
 def sha(a):
@@ -101,6 +106,15 @@ def main():
         planes = lowres_planes(r, g, synth.Clip(w, h, seed=31), 3)
         scal, arrs = lookahead_digest(oracle_lookahead(r, g, planes, method, 16, satd, weighted, is_ref=True), g)
         out["la_%s_scalars" % tag], out["la_%s_arrays" % tag] = scal, arrs.astype(np.int32)
+    # ---- deblocking: sha256 of the three filtered planes for seeded macroblock state (x264_frame_deblock_row)
+    for tag, (w, h), kw in DEBLOCK_GOLDEN:
+        g = r.geometry(w, h)
+        info = make_deblock_info(g, seed=100, **kw)
+        y, u, v = blocky_recon(synth.Clip(w, h, seed=5), g, seed=0)
+        py = r.new_plane(g)
+        py.reshape(-1, g.stride)[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]] = y
+        r.frame_deblock(g, info, py, u, v)
+        out["deblock_%s_sha" % tag] = np.array([sha(py.reshape(-1, g.stride)[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]]), sha(u), sha(v)])
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")), "bytes")
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One 1080p frame through every frame-batched kernel (for ncu launch lists / per-kernel profiles and device timing):
-upload -> border -> hpel+integral -> lowres -> MB-batched ESA -> sub-pel refine -> MC -> inter residual."""
+upload -> border -> hpel+integral -> lowres -> MB-batched ESA -> sub-pel refine -> MC -> inter residual -> deblock -> lowres frame cost."""
 import argparse
 import os
 import sys
@@ -39,6 +39,11 @@ def main():
     rj = np.zeros(g.mb_width * g.mb_height, pkg.RESID_JOB)
     rj["mb_x"], rj["mb_y"] = np.tile(np.arange(g.mb_width), g.mb_height), np.repeat(np.arange(g.mb_height), g.mb_width)
     rj["qp"], rj["chroma_qp"], rj["flags"] = 26, 26, pkg.RESID_DECIMATE
+    from helpers import make_deblock_info
+    dinfo = make_deblock_info(g, seed=7)
+    fref.init_lowres()
+    for f in (fenc, fref):
+        f.lookahead_alloc(2)
     stages = {}
 
     def timed(name, fn):
@@ -66,6 +71,8 @@ def main():
         mc["bx"], mc["by"], mc["mvx"], mc["mvy"], mc["w"], mc["h"] = jobs["bx"][0::9], jobs["by"][0::9], f16["mv"][:, 0], f16["mv"][:, 1], 16, 16
         timed("mc_blocks (8160 MB)", lambda: ctx.mc_blocks(fref, fdec, mc))
         timed("residual_inter (8160 MB)", lambda: ctx.residual_inter(fenc, fdec, rj))
+        timed("deblock (wavefront, P slice)", lambda: ctx.frame_deblock(fdec, dinfo))
+        timed("lowres intra+P cost (x264_slicetype_frame_cost b=p1=1)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)))
     ctx.synchronize()
     if a.time:
         for k, v in stages.items():

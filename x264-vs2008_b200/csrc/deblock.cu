@@ -7,6 +7,8 @@
 // and (x+1,y-1) are done.  ONE WARP PER MACROBLOCK ROW sweeps left to right; the left dependency never leaves the warp
 // (the previous macroblock's right columns stay in shared memory), the upper dependency is a per-row progress counter in
 // global memory.  Lanes 0-15 own the 16 luma lines across the current edge, lanes 16-31 the 8+8 chroma lines.
+// Everything that does not depend on pixels — bS of all 8 edges of every macroblock, alpha/beta/tc0 lookups — is done
+// beforehand by a fully parallel kernel (one thread per macroblock edge) so that the dependent chain only filters.
 //
 // Roofline class: latency (W + 2H dependent steps per frame); HBM traffic is one read + one write of the planes.
 #include "common.cuh"
@@ -36,8 +38,6 @@ __device__ __forceinline__ int chroma_qp(int q) { return c_chroma_qp[clip3i(q, 0
 struct MbInfo {            // what the filter needs of one macroblock, unpacked from the reference's arrays
     int type, qp, t8;
     unsigned nz;           // bit x+4y: 4x4 block has coefficients, as the deblocker sees it (munge_cavlc_nnz_row, frame.c:336-352)
-    int8_t ref[2][4];      // [list][8x8 block]
-    int16_t mv[2][16][2];  // [list][4x4 block x+4y]
 };
 
 struct DeblockArgs {
@@ -53,67 +53,105 @@ struct DeblockArgs {
 
 #define LT_STRIDE 32 // luma tile: rows -4..15, columns -4..15 at byte 16 + c (column 0 on a 16-byte boundary)
 #define CT_STRIDE 16 // chroma tile: rows -2..7, columns -2..7 at byte 8 + c
-struct RowSmem {
-    __align__(16) uint8_t L[20][LT_STRIDE];
-    __align__(16) uint8_t C[2][10][CT_STRIDE];
-    MbInfo cur, left, top;
+
+// what the wavefront needs to know about one edge (dir*4 + edge) of one macroblock: 16 bytes
+struct __align__(16) EdgeRec {
+    uint8_t mode;          // 0: edge not filtered, 1: bS < 4 filters, 2: bS 4 (intra macroblock edge) filters
+    uint8_t alpha, beta;   // luma thresholds (0 disables, like the reference's early return)
+    uint8_t alpha_c, beta_c;
+    uint8_t tc[4];         // luma tc0 per 4-line group, 0xff = bS 0
+    uint8_t tc_c[4];       // chroma tc (tc0 + 1) per 2-line group, 0 = bS 0
+    uint8_t pad[3];
 };
 
-__device__ void load_info(const DeblockArgs &a, int mb_x, int mb_y, MbInfo &m, int lane)
+__device__ void read_info(const DeblockArgs &a, int mb_x, int mb_y, MbInfo &m)
 {
     const int mb = mb_y * a.W + mb_x;
-    if (lane == 0) {
-        m.type = a.type[mb]; m.qp = a.qp[mb]; m.t8 = a.t8[mb];
-        unsigned nz = 0;
-        const uint8_t *n = a.nnz + (size_t)mb * 24;
-        for (int i = 0; i < 16; i++) nz |= (unsigned)(n[i] != 0) << i;
-        if (a.cavlc8 && m.t8) { // per-8x8 "any coefficient"
-            unsigned o = 0;
-            for (int b = 0; b < 4; b++) {
-                const int s = (b & 1) * 2 + (b >> 1) * 8;
-                if (nz & (0x33u << s)) o |= 0x33u << s;
-            }
-            nz = o;
+    m.type = a.type[mb]; m.qp = a.qp[mb]; m.t8 = a.t8[mb];
+    const uint2 *n2 = (const uint2 *)(a.nnz + (size_t)mb * 24); // 24-byte rows: 8-byte aligned
+    const uint2 n0 = n2[0], n1 = n2[1];
+    const uint32_t w[4] = { n0.x, n0.y, n1.x, n1.y };
+    unsigned nz = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) nz |= (unsigned)(((w[i >> 2] >> (8 * (i & 3))) & 255) != 0) << i;
+    if (a.cavlc8 && m.t8) { // per-8x8 "any coefficient"
+        unsigned o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int s = (b & 1) * 2 + (b >> 1) * 8;
+            if (nz & (0x33u << s)) o |= 0x33u << s;
         }
-        m.nz = nz;
+        nz = o;
     }
-    if (lane < 8) { // ref: 2 lists x 2 rows x 2 entries
-        const int l = lane >> 2, k = lane & 3;
-        m.ref[l][k] = (l == 0 || a.slice_b) ? a.ref[l][(size_t)(2 * mb_y + (k >> 1)) * 2 * a.W + 2 * mb_x + (k & 1)] : (int8_t)0;
-    }
-    { // mv: 2 lists x 16 blocks, one 32-bit (x,y) pair per lane
-        const int l = lane >> 4, k = lane & 15;
-        uint32_t v = 0;
-        if (l == 0 || a.slice_b) v = ((const uint32_t *)a.mv[l])[(size_t)(4 * mb_y + (k >> 2)) * 4 * a.W + 4 * mb_x + (k & 3)];
-        *(uint32_t *)m.mv[l][k] = v;
-    }
+    m.nz = nz;
 }
 
-// bS of the four 4-line groups of one edge (frame.c:697-741); every lane computes all four (they chain)
-__device__ unsigned edge_bs(const DeblockArgs &a, const MbInfo &c, const MbInfo &n, int dir, int edge, int no_sub8x8)
+// one thread per (macroblock, direction, edge): frame.c:644-657 (which edges), :697-741 (bS), :588-604 (thresholds)
+__global__ void __launch_bounds__(256) deblock_prep_kernel(DeblockArgs a, EdgeRec *__restrict__ recs)
 {
-    unsigned out = 0;
-    int prev = 0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.W * a.H * 8) return;
+    const int mb = t >> 3, dir = (t >> 2) & 1, edge = t & 3, mb_x = mb % a.W, mb_y = mb / a.W;
+    EdgeRec r;
+    *(uint4 *)&r = make_uint4(0, 0, 0, 0);
+    MbInfo c;
+    read_info(a, mb_x, mb_y, c);
+    const int intra = c.type >= 0 && c.type <= 3;
+    int edge_end = c.type == 6 ? 1 : 4;                       // P_SKIP
+    const int no_sub8x8 = c.type != 5 || !a.psub8x8;          // P_8x8
+    if (c.qp <= 15 - min(a.alpha_off, a.beta_off) - max(0, a.chroma_off)) edge_end = 1;
+    const bool has_nb = dir ? mb_y > 0 : mb_x > 0;
+    const bool on = edge == 0 ? has_nb : (edge < edge_end && !(c.t8 && (edge & 1)));
+    if (on) {
+        const int nx = mb_x - (edge == 0 && dir == 0), ny = mb_y - (edge == 0 && dir == 1);
+        MbInfo n;
+        read_info(a, nx, ny, n);
+        const int n_intra = n.type >= 0 && n.type <= 3;
+        unsigned bsv = 0;
+        if (edge == 0 && (intra | n_intra)) r.mode = 2;
+        else if (intra | n_intra) bsv = 0xff;
+        else {
+            int prev = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int x = dir == 0 ? edge : i, y = dir == 0 ? i : edge;
-        const int xn = dir == 0 ? (x - 1) & 3 : x, yn = dir == 0 ? y : (y - 1) & 3;
-        int bs = 0;
-        if ((c.nz >> (x + 4 * y) & 1) | (n.nz >> (xn + 4 * yn) & 1)) bs = 2;
-        else if (!(edge & no_sub8x8)) {
-            if ((i & no_sub8x8) && prev != 2) bs = prev;
-            else {
-                const int bp = x + 4 * y, bq = xn + 4 * yn, rp = (x >> 1) + (y >> 1) * 2, rq = (xn >> 1) + (yn >> 1) * 2;
-                bool diff = c.ref[0][rp] != n.ref[0][rq] || abs(c.mv[0][bp][0] - n.mv[0][bq][0]) >= 4 || abs(c.mv[0][bp][1] - n.mv[0][bq][1]) >= 4;
-                if (!diff && a.slice_b)
-                    diff = c.ref[1][rp] != n.ref[1][rq] || abs(c.mv[1][bp][0] - n.mv[1][bq][0]) >= 4 || abs(c.mv[1][bp][1] - n.mv[1][bq][1]) >= 4;
-                bs = diff;
+            for (int i = 0; i < 4; i++) {
+                const int x = dir == 0 ? edge : i, y = dir == 0 ? i : edge;
+                const int xn = dir == 0 ? (x - 1) & 3 : x, yn = dir == 0 ? y : (y - 1) & 3;
+                int bs = 0;
+                if ((c.nz >> (x + 4 * y) & 1) | (n.nz >> (xn + 4 * yn) & 1)) bs = 2;
+                else if (!(edge & no_sub8x8)) {
+                    if ((i & no_sub8x8) && prev != 2) bs = prev;
+                    else {
+                        bool diff = false;
+                        for (int l = 0; l < 1 + a.slice_b && !diff; l++) {
+                            const int rp = a.ref[l][(size_t)(2 * mb_y + (y >> 1)) * 2 * a.W + 2 * mb_x + (x >> 1)];
+                            const int rq = a.ref[l][(size_t)(2 * ny + (yn >> 1)) * 2 * a.W + 2 * nx + (xn >> 1)];
+                            const uint32_t vp = ((const uint32_t *)a.mv[l])[(size_t)(4 * mb_y + y) * 4 * a.W + 4 * mb_x + x];
+                            const uint32_t vq = ((const uint32_t *)a.mv[l])[(size_t)(4 * ny + yn) * 4 * a.W + 4 * nx + xn];
+                            diff = rp != rq || abs((int16_t)(vp & 0xffff) - (int16_t)(vq & 0xffff)) >= 4 || abs((int16_t)(vp >> 16) - (int16_t)(vq >> 16)) >= 4;
+                        }
+                        bs = diff;
+                    }
+                }
+                prev = bs;
+                bsv |= (unsigned)bs << (2 * i);
             }
         }
-        prev = bs;
-        out |= (unsigned)bs << (2 * i);
+        if (r.mode == 2 || bsv) {
+            if (!r.mode) r.mode = 1;
+            const int ql = (c.qp + n.qp + 1) >> 1, ia = ql + a.alpha_off;
+            r.alpha = (uint8_t)alpha_of(ia); r.beta = (uint8_t)beta_of(ql + a.beta_off);
+            const int qc = (chroma_qp(c.qp + a.chroma_off) + chroma_qp(n.qp + a.chroma_off) + 1) >> 1, iac = qc + a.alpha_off;
+            r.alpha_c = (uint8_t)alpha_of(iac); r.beta_c = (uint8_t)beta_of(qc + a.beta_off);
+            if (edge & 1) r.alpha_c = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int bs = (bsv >> (2 * i)) & 3;
+                r.tc[i] = bs ? (uint8_t)tc0_of(ia, bs) : (uint8_t)0xff;
+                r.tc_c[i] = bs ? (uint8_t)(tc0_of(iac, bs) + 1) : (uint8_t)0;
+            }
+        }
     }
-    return out;
+    *(uint4 *)&recs[t] = *(const uint4 *)&r;
 }
 
 // one line across an edge; p points at q0, xs = byte step across the edge.  bs 4 = the intra macroblock-edge filter.
@@ -163,76 +201,73 @@ __device__ void filter_chroma(uint8_t *p, int xs, int alpha, int beta, int bs, i
     }
 }
 
-__global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a)
+struct RowSmem {
+    __align__(16) uint8_t L[20][LT_STRIDE];
+    __align__(16) uint8_t C[2][10][CT_STRIDE];
+    __align__(16) EdgeRec rec[8];
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a, const EdgeRec *__restrict__ recs)
 {
     __shared__ RowSmem S;
     const int lane = threadIdx.x, mb_y = blockIdx.x;
-    const int qp_thresh = 15 - min(a.alpha_off, a.beta_off) - max(0, a.chroma_off);
     uint8_t *rowy = a.y + (size_t)16 * mb_y * a.stride, *rowu = a.u + (size_t)8 * mb_y * a.stride_c, *rowv = a.v + (size_t)8 * mb_y * a.stride_c;
+    const uint4 *rrow = (const uint4 *)(recs + (size_t)mb_y * a.W * 8);
+    // this row's own pixels and edge records never depend on the row above: always one macroblock ahead, in registers
+    uint4 ly = make_uint4(0, 0, 0, 0), rc = make_uint4(0, 0, 0, 0);
+    uint2 lc = make_uint2(0, 0);
+    if (lane < 16) {
+        ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride));
+        lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c));
+    }
+    if (lane < 8) rc = __ldg(rrow + lane);
     for (int mb_x = 0; mb_x < a.W; mb_x++) {
-        // ---- this macroblock's own pixels and state do not depend on the row above: fetch them before waiting
-        uint4 ly = make_uint4(0, 0, 0, 0);
-        uint2 lc = make_uint2(0, 0);
         if (lane < 16) {
-            ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride + 16 * mb_x));
-            lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * mb_x));
+            *(uint4 *)&S.L[4 + lane][16] = ly;
+            *(uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8] = lc;
         }
-        load_info(a, mb_x, mb_y, S.cur, lane);
+        if (lane < 8) *(uint4 *)&S.rec[lane] = rc;
+        if (mb_x + 1 < a.W) {
+            if (lane < 16) {
+                ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride + 16 * (mb_x + 1)));
+                lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * (mb_x + 1)));
+            }
+            if (lane < 8) rc = __ldg(rrow + (size_t)(mb_x + 1) * 8 + lane);
+        }
         if (mb_y > 0) {
-            load_info(a, mb_x, mb_y - 1, S.top, lane);
             if (lane == 0) {
                 const int need = min(mb_x + 2, a.W);
-                while (*(volatile int *)(a.progress + mb_y - 1) < need) __nanosleep(100);
+                while (ld_acquire(a.progress + mb_y - 1) < need) { }
             }
             __syncwarp();
-            __threadfence();
             if (lane < 4) *(uint4 *)&S.L[lane][16] = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * mb_x));
             else if (lane < 8) {
                 const int pl = (lane - 4) >> 1, r = (lane - 4) & 1; // chroma rows -2, -1 of both planes
                 *(uint2 *)&S.C[pl][r][8] = __ldcg((const uint2 *)((pl ? rowv : rowu) - (size_t)(2 - r) * a.stride_c + 8 * mb_x));
             }
         }
-        if (lane < 16) {
-            *(uint4 *)&S.L[4 + lane][16] = ly;
-            *(uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8] = lc;
-        }
         __syncwarp();
 
-        const MbInfo &c = S.cur;
-        const int intra = c.type >= 0 && c.type <= 3;
-        int edge_end = c.type == 6 ? 1 : 4;                       // P_SKIP
-        const int no_sub8x8 = c.type != 5 || !a.psub8x8;          // P_8x8
-        if (c.qp <= qp_thresh) edge_end = 1;
-        for (int dir = 0; dir < 2; dir++) {
-            int edge = dir ? mb_y == 0 : mb_x == 0;
-            if (edge) edge += c.t8;
-            for (; edge < edge_end; edge += c.t8 + 1) {
-                const MbInfo &n = edge ? c : dir == 0 ? S.left : S.top;
-                const int n_intra = n.type >= 0 && n.type <= 3;
-                unsigned bsv;
-                if (edge == 0 && (intra | n_intra)) bsv = 0x100; // marks the bS-4 filters
-                else if (intra | n_intra) bsv = 0xff;            // bS 3 on all four groups
-                else bsv = edge_bs(a, c, n, dir, edge, no_sub8x8);
-                if (!bsv) continue;                               // warp-uniform
-                const bool chroma_lane = lane >= 16;
-                const bool active = !(chroma_lane && (edge & 1)); // chroma has edges 0 and 2 only
-                const int qa = chroma_lane ? (chroma_qp(c.qp + a.chroma_off) + chroma_qp(n.qp + a.chroma_off) + 1) >> 1 : (c.qp + n.qp + 1) >> 1;
-                const int ia = qa + a.alpha_off, alpha = alpha_of(ia), beta = beta_of(qa + a.beta_off);
-                if (active && alpha && beta) {
-                    if (!chroma_lane) {
-                        const int bs = bsv == 0x100 ? 4 : (bsv >> (2 * (lane >> 2))) & 3;
-                        uint8_t *p = dir == 0 ? &S.L[4 + lane][16 + 4 * edge] : &S.L[4 + 4 * edge][16 + lane];
-                        if (bs) filter_luma(p, dir == 0 ? 1 : LT_STRIDE, alpha, beta, bs, bs < 4 ? tc0_of(ia, bs) : 0);
-                    } else {
-                        const int pl = (lane - 16) >> 3, i = lane & 7;
-                        const int bs = bsv == 0x100 ? 4 : (bsv >> (2 * (i >> 1))) & 3;
-                        uint8_t *p = dir == 0 ? &S.C[pl][2 + i][8 + 2 * edge] : &S.C[pl][2 + 2 * edge][8 + i];
-                        if (bs) filter_chroma(p, dir == 0 ? 1 : CT_STRIDE, alpha, beta, bs, bs < 4 ? tc0_of(ia, bs) + 1 : 0);
-                    }
+#pragma unroll
+        for (int de = 0; de < 8; de++) {
+            const int dir = de >> 2, edge = de & 3;
+            const EdgeRec &r = S.rec[de];
+            if (r.mode) { // warp-uniform
+                if (lane < 16) {
+                    const int tc0 = r.mode == 2 ? 0 : r.tc[lane >> 2];
+                    uint8_t *p = dir == 0 ? &S.L[4 + lane][16 + 4 * edge] : &S.L[4 + 4 * edge][16 + lane];
+                    if (tc0 != 0xff) filter_luma(p, dir == 0 ? 1 : LT_STRIDE, r.alpha, r.beta, r.mode == 2 ? 4 : 1, tc0);
+                } else if (!(edge & 1)) {
+                    const int pl = (lane - 16) >> 3, i = lane & 7;
+                    const int tc = r.mode == 2 ? 1 : r.tc_c[i >> 1];
+                    uint8_t *p = dir == 0 ? &S.C[pl][2 + i][8 + 2 * edge] : &S.C[pl][2 + 2 * edge][8 + i];
+                    if (tc) filter_chroma(p, dir == 0 ? 1 : CT_STRIDE, r.alpha_c, r.beta_c, r.mode == 2 ? 4 : 1, tc);
                 }
                 __syncwarp();
             }
-            __syncwarp();
         }
 
         // ---- write back: this macroblock, the 3 (chroma: 1) columns of the left neighbour and rows of the upper one it touched
@@ -243,20 +278,16 @@ __global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a)
             uint8_t *dc = (lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * mb_x;
             *(uint2 *)dc = *(const uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8];
             if (mb_x > 0) *(uint16_t *)(dc - 2) = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6];
+            // the right columns stay in shared memory as the next macroblock's left neighbour
+            *(uint32_t *)&S.L[4 + lane][12] = *(const uint32_t *)&S.L[4 + lane][28];
+            *(uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6] = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][14];
         } else if (mb_y > 0) {
             if (lane < 19) *(uint4 *)(rowy - (size_t)(19 - lane) * a.stride + 16 * mb_x) = *(const uint4 *)&S.L[lane - 15][16]; // rows -3..-1
             else if (lane < 21) *(uint2 *)((lane == 19 ? rowu : rowv) - a.stride_c + 8 * mb_x) = *(const uint2 *)&S.C[lane - 19][1][8];
         }
+        __threadfence(); // every lane's pixel stores are visible device-wide before lane 0 publishes the progress
         __syncwarp();
-        // ---- the right columns stay in shared memory as the next macroblock's left neighbour
-        if (lane < 16) {
-            *(uint32_t *)&S.L[4 + lane][12] = *(const uint32_t *)&S.L[4 + lane][28];
-            *(uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6] = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][14];
-        }
-        for (int i = lane; i < (int)(sizeof(MbInfo) / 4); i += 32) ((uint32_t *)&S.left)[i] = ((const uint32_t *)&S.cur)[i];
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) *(volatile int *)(a.progress + mb_y) = mb_x + 1;
+        if (lane == 0) st_release(a.progress + mb_y, mb_x + 1);
     }
 }
 
@@ -282,6 +313,13 @@ extern "C" int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_t *
         ctx->deblock_rows = H;
     }
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_deblock_progress, 0, (size_t)H * sizeof(int), ctx->stream));
+    const size_t n_edges = (size_t)fdec->g.mb_width * H * 8;
+    if (n_edges * sizeof(EdgeRec) > ctx->d_deblock_recs_size) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_deblock_recs); ctx->d_deblock_recs = nullptr; ctx->d_deblock_recs_size = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_deblock_recs, n_edges * sizeof(EdgeRec)));
+        ctx->d_deblock_recs_size = n_edges * sizeof(EdgeRec);
+    }
     DeblockArgs a;
     a.y = fdec->plane[0]; a.u = fdec->chroma[0]; a.v = fdec->chroma[1];
     a.stride = fdec->g.stride; a.stride_c = fdec->stride_c; a.W = fdec->g.mb_width; a.H = H;
@@ -292,7 +330,9 @@ extern "C" int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_t *
     a.progress = ctx->d_deblock_progress;
     // one single-warp CTA per macroblock row; all of them are resident at once (<= a few hundred), so a row can always
     // wait for the row above
-    deblock_rows_kernel<<<H, 32, 0, ctx->stream>>>(a);
+    deblock_prep_kernel<<<(int)((n_edges + 255) / 256), 256, 0, ctx->stream>>>(a, (EdgeRec *)ctx->d_deblock_recs);
+    LAUNCH_CHECK(ctx, "deblock_prep_kernel");
+    deblock_rows_kernel<<<H, 32, 0, ctx->stream>>>(a, (const EdgeRec *)ctx->d_deblock_recs);
     LAUNCH_CHECK(ctx, "deblock_rows_kernel");
     return 0;
 }
