@@ -154,53 +154,6 @@ __global__ void __launch_bounds__(256) deblock_prep_kernel(DeblockArgs a, EdgeRe
     *(uint4 *)&recs[t] = *(const uint4 *)&r;
 }
 
-// one line across an edge; p points at q0, xs = byte step across the edge.  bs 4 = the intra macroblock-edge filter.
-__device__ void filter_luma(uint8_t *p, int xs, int alpha, int beta, int bs, int tc0)
-{
-    const int p2 = p[-3 * xs], p1 = p[-2 * xs], p0 = p[-xs], q0 = p[0], q1 = p[xs], q2 = p[2 * xs];
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    if (bs < 4) { // frame.c:424-467
-        int tc = tc0;
-        const int avg = (p0 + q0 + 1) >> 1;
-        if (abs(p2 - p0) < beta) { p[-2 * xs] = (uint8_t)(p1 + clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0)); tc++; }
-        if (abs(q2 - q0) < beta) { p[xs] = (uint8_t)(q1 + clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0)); tc++; }
-        const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-        p[-xs] = (uint8_t)clip_u8(p0 + delta);
-        p[0] = (uint8_t)clip_u8(q0 - delta);
-    } else if (abs(p0 - q0) < ((alpha >> 2) + 2)) { // frame.c:507-552
-        if (abs(p2 - p0) < beta) {
-            const int p3 = p[-4 * xs];
-            p[-xs] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-            p[-2 * xs] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-            p[-3 * xs] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-        } else
-            p[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        if (abs(q2 - q0) < beta) {
-            const int q3 = p[3 * xs];
-            p[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-            p[xs] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-            p[2 * xs] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-        } else
-            p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    } else {
-        p[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    }
-}
-__device__ void filter_chroma(uint8_t *p, int xs, int alpha, int beta, int bs, int tc)
-{
-    const int p1 = p[-2 * xs], p0 = p[-xs], q0 = p[0], q1 = p[xs];
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    if (bs < 4) { // frame.c:470-497
-        const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-        p[-xs] = (uint8_t)clip_u8(p0 + delta);
-        p[0] = (uint8_t)clip_u8(q0 - delta);
-    } else { // frame.c:562-580
-        p[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    }
-}
-
 struct RowSmem {
     __align__(16) uint8_t L[20][LT_STRIDE];
     __align__(16) uint8_t C[2][10][CT_STRIDE];
@@ -210,20 +163,104 @@ struct RowSmem {
 __device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+// One line across a luma edge held in two packed words: P = p3,p2,p1,p0 (byte 0..3), Q = q0,q1,q2,q3.
+// strong = the bS 4 filter of intra macroblock edges (frame.c:507-552), else the bS < 4 filter (frame.c:424-467).
+__device__ __forceinline__ void filter_luma_w(uint32_t &P, uint32_t &Q, int alpha, int beta, bool strong, int tc0)
+{
+    const int p3 = P & 255, p2 = (P >> 8) & 255, p1 = (P >> 16) & 255, p0 = P >> 24;
+    const int q0 = Q & 255, q1 = (Q >> 8) & 255, q2 = (Q >> 16) & 255, q3 = Q >> 24;
+    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+    int n2 = p2, n1 = p1, n0 = p0, m0 = q0, m1 = q1, m2 = q2;
+    if (!strong) {
+        int tc = tc0;
+        const int avg = (p0 + q0 + 1) >> 1;
+        if (abs(p2 - p0) < beta) { n1 = p1 + clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0); tc++; }
+        if (abs(q2 - q0) < beta) { m1 = q1 + clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0); tc++; }
+        const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
+        n0 = clip_u8(p0 + delta);
+        m0 = clip_u8(q0 - delta);
+    } else if (abs(p0 - q0) < ((alpha >> 2) + 2)) {
+        if (abs(p2 - p0) < beta) {
+            n0 = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+            n1 = (p2 + p1 + p0 + q0 + 2) >> 2;
+            n2 = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+        } else
+            n0 = (2 * p1 + p0 + q1 + 2) >> 2;
+        if (abs(q2 - q0) < beta) {
+            m0 = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+            m1 = (p0 + q0 + q1 + q2 + 2) >> 2;
+            m2 = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+        } else
+            m0 = (2 * q1 + q0 + p1 + 2) >> 2;
+    } else {
+        n0 = (2 * p1 + p0 + q1 + 2) >> 2;
+        m0 = (2 * q1 + q0 + p1 + 2) >> 2;
+    }
+    P = (uint32_t)p3 | (uint32_t)n2 << 8 | (uint32_t)n1 << 16 | (uint32_t)n0 << 24;
+    Q = (uint32_t)m0 | (uint32_t)m1 << 8 | (uint32_t)m2 << 16 | (uint32_t)q3 << 24;
+}
+// chroma (frame.c:470-497, :562-580): P = x,x,p1,p0; Q = q0,q1,x,x
+__device__ __forceinline__ void filter_chroma_w(uint32_t &P, uint32_t &Q, int alpha, int beta, bool strong, int tc)
+{
+    const int p1 = (P >> 16) & 255, p0 = P >> 24, q0 = Q & 255, q1 = (Q >> 8) & 255;
+    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+    int n0, m0;
+    if (!strong) {
+        const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
+        n0 = clip_u8(p0 + delta);
+        m0 = clip_u8(q0 - delta);
+    } else {
+        n0 = (2 * p1 + p0 + q1 + 2) >> 2;
+        m0 = (2 * q1 + q0 + p1 + 2) >> 2;
+    }
+    P = (P & 0x00ffffffu) | (uint32_t)n0 << 24;
+    Q = (Q & 0xffffff00u) | (uint32_t)m0;
+}
+
+// the four (luma) / two (chroma) edges of one direction on the line this lane holds in registers
+__device__ __forceinline__ void filter_line(uint32_t (&w)[5], const EdgeRec *rec, int dir, int lane)
+{
+    if (lane < 16) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const EdgeRec &r = rec[dir * 4 + e];
+            if (!r.mode) continue; // warp-uniform
+            const int tc0 = r.mode == 2 ? 0 : r.tc[lane >> 2];
+            if (tc0 != 0xff) filter_luma_w(w[e], w[e + 1], r.alpha, r.beta, r.mode == 2, tc0);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            const EdgeRec &r = rec[dir * 4 + e];
+            if (!r.mode) continue;
+            const int tc = r.mode == 2 ? 1 : r.tc_c[(lane & 7) >> 1];
+            if (tc) filter_chroma_w(w[e >> 1], w[(e >> 1) + 1], r.alpha_c, r.beta_c, r.mode == 2, tc);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a, const EdgeRec *__restrict__ recs)
 {
     __shared__ RowSmem S;
     const int lane = threadIdx.x, mb_y = blockIdx.x;
     uint8_t *rowy = a.y + (size_t)16 * mb_y * a.stride, *rowu = a.u + (size_t)8 * mb_y * a.stride_c, *rowv = a.v + (size_t)8 * mb_y * a.stride_c;
     const uint4 *rrow = (const uint4 *)(recs + (size_t)mb_y * a.W * 8);
+    const int *above = a.progress + mb_y - 1;
+    // chroma lanes: plane and line inside the plane
+    const int cpl = (lane >> 3) & 1, cln = lane & 7;
     // this row's own pixels and edge records never depend on the row above: always one macroblock ahead, in registers
-    uint4 ly = make_uint4(0, 0, 0, 0), rc = make_uint4(0, 0, 0, 0);
-    uint2 lc = make_uint2(0, 0);
+    uint4 ly = make_uint4(0, 0, 0, 0), rc = make_uint4(0, 0, 0, 0), tl = make_uint4(0, 0, 0, 0);
+    uint2 lc = make_uint2(0, 0), tc2 = make_uint2(0, 0);
     if (lane < 16) {
         ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride));
         lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c));
     }
     if (lane < 8) rc = __ldg(rrow + lane);
+    // the rows above (4 luma, 2+2 chroma) depend on the upper row's progress.  `seen` caches the last value read; when it
+    // already covers the NEXT macroblock its top rows are fetched a whole step early (have_top), so a row that trails the
+    // one above by a few macroblocks never waits for memory.
+    int seen = 0;
+    bool have_top = false;
     for (int mb_x = 0; mb_x < a.W; mb_x++) {
         if (lane < 16) {
             *(uint4 *)&S.L[4 + lane][16] = ly;
@@ -237,38 +274,75 @@ __global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a, const E
             }
             if (lane < 8) rc = __ldg(rrow + (size_t)(mb_x + 1) * 8 + lane);
         }
+        int flag_probe = -1; // a non-blocking read of the upper row's progress, consumed at the end of the step
         if (mb_y > 0) {
-            if (lane == 0) {
+            if (!have_top) {
                 const int need = min(mb_x + 2, a.W);
-                while (ld_acquire(a.progress + mb_y - 1) < need) { }
+                while (seen < need) seen = ld_acquire(above); // every lane reads the same word: one request
+                if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * mb_x));
+                else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * mb_x));
             }
-            __syncwarp();
-            if (lane < 4) *(uint4 *)&S.L[lane][16] = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * mb_x));
-            else if (lane < 8) {
-                const int pl = (lane - 4) >> 1, r = (lane - 4) & 1; // chroma rows -2, -1 of both planes
-                *(uint2 *)&S.C[pl][r][8] = __ldcg((const uint2 *)((pl ? rowv : rowu) - (size_t)(2 - r) * a.stride_c + 8 * mb_x));
+            if (lane < 4) *(uint4 *)&S.L[lane][16] = tl;
+            else if (lane < 8) *(uint2 *)&S.C[(lane - 4) >> 1][(lane - 4) & 1][8] = tc2;
+            have_top = false;
+            if (mb_x + 1 < a.W) {
+                if (seen >= min(mb_x + 3, a.W)) {
+                    if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * (mb_x + 1)));
+                    else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * (mb_x + 1)));
+                    have_top = true;
+                } else
+                    flag_probe = ld_acquire(above);
             }
         }
         __syncwarp();
 
-#pragma unroll
-        for (int de = 0; de < 8; de++) {
-            const int dir = de >> 2, edge = de & 3;
-            const EdgeRec &r = S.rec[de];
-            if (r.mode) { // warp-uniform
-                if (lane < 16) {
-                    const int tc0 = r.mode == 2 ? 0 : r.tc[lane >> 2];
-                    uint8_t *p = dir == 0 ? &S.L[4 + lane][16 + 4 * edge] : &S.L[4 + 4 * edge][16 + lane];
-                    if (tc0 != 0xff) filter_luma(p, dir == 0 ? 1 : LT_STRIDE, r.alpha, r.beta, r.mode == 2 ? 4 : 1, tc0);
-                } else if (!(edge & 1)) {
-                    const int pl = (lane - 16) >> 3, i = lane & 7;
-                    const int tc = r.mode == 2 ? 1 : r.tc_c[i >> 1];
-                    uint8_t *p = dir == 0 ? &S.C[pl][2 + i][8 + 2 * edge] : &S.C[pl][2 + 2 * edge][8 + i];
-                    if (tc) filter_chroma(p, dir == 0 ? 1 : CT_STRIDE, r.alpha_c, r.beta_c, r.mode == 2 ? 4 : 1, tc);
-                }
-                __syncwarp();
-            }
+        // ---- vertical edges: the lane's line (luma row / chroma row) lives in registers across all of them
+        uint32_t w[5];
+        if (lane < 16) {
+            w[0] = *(const uint32_t *)&S.L[4 + lane][12];
+            const uint4 v = *(const uint4 *)&S.L[4 + lane][16];
+            w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w;
+        } else {
+            w[0] = *(const uint32_t *)&S.C[cpl][2 + cln][4];
+            const uint2 v = *(const uint2 *)&S.C[cpl][2 + cln][8];
+            w[1] = v.x; w[2] = v.y; w[3] = w[4] = 0;
         }
+        filter_line(w, S.rec, 0, lane);
+        if (lane < 16) {
+            *(uint32_t *)&S.L[4 + lane][12] = w[0];
+            *(uint4 *)&S.L[4 + lane][16] = make_uint4(w[1], w[2], w[3], w[4]);
+        } else {
+            *(uint32_t *)&S.C[cpl][2 + cln][4] = w[0];
+            *(uint2 *)&S.C[cpl][2 + cln][8] = make_uint2(w[1], w[2]);
+        }
+        __syncwarp();
+        // ---- horizontal edges: the lane's column, gathered from the tile
+        if (lane < 16) {
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                w[k] = (uint32_t)S.L[4 * k][16 + lane] | (uint32_t)S.L[4 * k + 1][16 + lane] << 8 | (uint32_t)S.L[4 * k + 2][16 + lane] << 16 |
+                       (uint32_t)S.L[4 * k + 3][16 + lane] << 24;
+        } else {
+            w[0] = (uint32_t)S.C[cpl][0][8 + cln] << 16 | (uint32_t)S.C[cpl][1][8 + cln] << 24;
+#pragma unroll
+            for (int k = 1; k < 3; k++)
+                w[k] = (uint32_t)S.C[cpl][4 * k - 2][8 + cln] | (uint32_t)S.C[cpl][4 * k - 1][8 + cln] << 8 | (uint32_t)S.C[cpl][4 * k][8 + cln] << 16 |
+                       (uint32_t)S.C[cpl][4 * k + 1][8 + cln] << 24;
+        }
+        filter_line(w, S.rec, 1, lane);
+        if (lane < 16) {
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+#pragma unroll
+                for (int b = (k == 0 ? 1 : 0); b < (k == 4 ? 3 : 4); b++) S.L[4 * k + b][16 + lane] = (uint8_t)(w[k] >> (8 * b)); // p3 of the first and q3 of the last edge never change
+        } else {
+            S.C[cpl][1][8 + cln] = (uint8_t)(w[0] >> 24);
+#pragma unroll
+            for (int k = 1; k < 3; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) S.C[cpl][4 * k - 2 + b][8 + cln] = (uint8_t)(w[k] >> (8 * b));
+        }
+        __syncwarp();
 
         // ---- write back: this macroblock, the 3 (chroma: 1) columns of the left neighbour and rows of the upper one it touched
         if (lane < 16) {
@@ -280,14 +354,23 @@ __global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a, const E
             if (mb_x > 0) *(uint16_t *)(dc - 2) = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6];
             // the right columns stay in shared memory as the next macroblock's left neighbour
             *(uint32_t *)&S.L[4 + lane][12] = *(const uint32_t *)&S.L[4 + lane][28];
-            *(uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6] = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][14];
+            *(uint32_t *)&S.C[lane >> 3][2 + (lane & 7)][4] = *(const uint32_t *)&S.C[lane >> 3][2 + (lane & 7)][12];
         } else if (mb_y > 0) {
             if (lane < 19) *(uint4 *)(rowy - (size_t)(19 - lane) * a.stride + 16 * mb_x) = *(const uint4 *)&S.L[lane - 15][16]; // rows -3..-1
             else if (lane < 21) *(uint2 *)((lane == 19 ? rowu : rowv) - a.stride_c + 8 * mb_x) = *(const uint2 *)&S.C[lane - 19][1][8];
         }
-        __threadfence(); // every lane's pixel stores are visible device-wide before lane 0 publishes the progress
+        // __syncwarp orders every lane's pixel stores before lane 0's release store; release is cumulative, so a row that
+        // acquires the new progress value sees all of them (no per-lane __threadfence on the critical path)
         __syncwarp();
         if (lane == 0) st_release(a.progress + mb_y, mb_x + 1);
+        if (flag_probe >= 0) {
+            seen = max(seen, flag_probe);
+            if (seen >= min(mb_x + 3, a.W)) { // became ready during this step: start the fetch now, it overlaps the next step's prologue
+                if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * (mb_x + 1)));
+                else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * (mb_x + 1)));
+                have_top = true;
+            }
+        }
     }
 }
 
