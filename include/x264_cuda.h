@@ -125,6 +125,10 @@ X264_CUDA_API int x264_cuda_host_lambda(int qp);
 #define X264_CUDA_ME_TESA   2 /* TESA candidate thresholds + final fpelcmp pass (me.c:491-578) */
 #define X264_CUDA_ME_FPEL_SATD 4 /* fpelcmp is SATD (mbcmp_init, S/encoder/encoder.c:608-618) */
 #define X264_CUDA_ME_MBCMP_SATD 8 /* mbcmp is SATD (user subme > 1) */
+#define X264_CUDA_ME_CHROMA 32    /* h->mb.b_chroma_me (P slices, subme >= 5, --chroma-me): the sub-pel SATD cost of partitions >= 8x8 adds
+                                   * mc_chroma + mbcmp of U and V (S/encoder/me.c:655-677); honoured by x264_cuda_me_search_small when fenc
+                                   * and fref both carry chroma planes (X264_CUDA_FRAME_CHROMA, borders expanded), else the job is rejected
+                                   * (cost -1) */
 typedef struct x264_cuda_me_job_t {
     int16_t bx, by;              /* block position in luma pixels */
     uint8_t i_pixel;             /* X264_CUDA_PIXEL_* */

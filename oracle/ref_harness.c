@@ -207,8 +207,8 @@ void xo_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int src_stri
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-static void run_search(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref[4], const uint16_t *integral,
-                       const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+static void run_search_c(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref[4], const uint16_t *integral,
+                         const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
 {
     /* the function tables depend on (me method, user subme>1): open the encoder the way the CLI would */
     int tables_subme = in->fpel_satd || mbcmp_satd ? 7 : 1;
@@ -227,7 +227,7 @@ static void run_search(const xo_geom *g, const uint8_t *fenc_plane, const uint8_
     h->param.analyse.i_me_range = in->me_range;
     h->mb.i_me_method = in->me_method;
     h->mb.i_subpel_refine = subme;
-    h->mb.b_chroma_me = 0;
+    h->mb.b_chroma_me = ch != NULL;
     h->mb.i_qp = in->qp;
     for (int k = 0; k < 2; k++) {
         h->mb.mv_min_fpel[k] = in->mv_min_fpel[k]; h->mb.mv_max_fpel[k] = in->mv_max_fpel[k];
@@ -241,12 +241,34 @@ static void run_search(const xo_geom *g, const uint8_t *fenc_plane, const uint8_
         m.p_fref[k] = fref[k] ? (uint8_t *)fref[k] + in->by * g->stride + in->bx : NULL;
     m.integral = integral ? (uint16_t *)integral + in->by * g->stride + in->bx : NULL;
     m.mvp[0] = in->mvp[0]; m.mvp[1] = in->mvp[1];
+    DECLARE_ALIGNED_16(uint8_t fenc_c[2][16 * 8]);
+    if (ch) { /* fenc chroma at FENC_STRIDE like h->mb.pic.p_fenc[1,2]; reference chroma planes as m->p_fref[4,5] */
+        const uint8_t *fe[2] = { ch->fenc_u, ch->fenc_v }, *fr[2] = { ch->fref_u, ch->fref_v };
+        for (int pl = 0; pl < 2; pl++) {
+            for (int y = 0; y < x264_pixel_size[in->i_pixel].h / 2; y++)
+                memcpy(fenc_c[pl] + 16 * y, fe[pl] + (in->by / 2 + y) * ch->stride_c + in->bx / 2, x264_pixel_size[in->i_pixel].w / 2);
+            m.p_fenc[1 + pl] = fenc_c[pl];
+            m.p_fref[4 + pl] = (uint8_t *)fr[pl] + (in->by / 2) * ch->stride_c + in->bx / 2;
+        }
+        m.i_stride[1] = ch->stride_c;
+    }
     x264_me_search_ref(h, &m, mvc, in->i_mvc, NULL);
     memset(out, 0, sizeof(*out));
     out->mv[0] = m.mv[0]; out->mv[1] = m.mv[1];
     out->cost = m.cost; out->cost_mv = m.cost_mv;
     /* the reference does not expose its internal full-pel state; report what can be derived */
     out->bmx = out->bmy = out->bcost = out->seed_mx = out->seed_my = out->seed_cost = -1;
+}
+
+static void run_search(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref[4], const uint16_t *integral,
+                       const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    run_search_c(g, fenc_plane, fref, integral, NULL, in, subme, mbcmp_satd, out);
+}
+void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const uint16_t *integral,
+                                const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    run_search_c(g, fenc_plane, fref_planes, integral, ch, in, subme, mbcmp_satd, out);
 }
 
 void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,

@@ -157,6 +157,11 @@ typedef struct {
 void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
                           uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out);
 
+/* chroma planes for b_chroma_me (pixel (0,0) pointers; borders expanded by 16 like x264_frame_expand_border does for planes 1,2) */
+typedef struct { const uint8_t *fenc_u, *fenc_v, *fref_u, *fref_v; int stride_c; } xo_chroma;
+void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const uint16_t *integral,
+                                const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out);
+
 /* ---------------- lowres lookahead: S/encoder/slicetype.c:43-355 (non-VBV, no AQ) ----------------
  * Planes are the four half-resolution planes (pixel 0,0 pointers, stride g->stride_lowres).  mvs/costs are the frame's
  * lowres_mvs[l][dist-1] / lowres_mv_costs[l][dist-1] arrays (mb_width*mb_height entries, updated in place when

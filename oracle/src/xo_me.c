@@ -54,6 +54,11 @@ typedef struct {
     const int16_t *cmx, *cmy;    /* p_cost_mv - mvp[k] */
     int bw, bh, stride;
     int fpel_metric, sub_metric; /* XO_SAD / XO_SATD */
+    /* b_chroma_me (h->mb.b_chroma_me && i_pixel <= PIXEL_8x8): stride-16 copies of the fenc chroma blocks, block-positioned
+     * reference chroma planes (m->p_fref[4], [5]) */
+    int chroma_me, stride_c;
+    uint8_t fenc_c[2][16 * 8];
+    const uint8_t *fref_c[2];
 } me_ctx;
 
 static int fpel_cost(const me_ctx *c, int mx, int my)
@@ -72,6 +77,22 @@ static int qpel_cost(const me_ctx *c, int metric, int mx, int my)
     return xo_pixel_cmp(metric, c->in->i_pixel, c->fenc, 16, tmp, 16) + c->cmx[mx] + c->cmy[my];
 }
 
+/* COST_MV_SATD (me.c:655-677): mbcmp of the luma block, plus — only while the candidate still beats bcost — the two chroma
+ * blocks predicted by mc_chroma and compared with mbcmp[i_pixel+3] */
+static int satd_cost(const me_ctx *c, int mx, int my, int bcost)
+{
+    int cost = qpel_cost(c, c->sub_metric, mx, my);
+    if (c->chroma_me && cost < bcost) {
+        uint8_t pix[8 * 8];
+        for (int pl = 0; pl < 2; pl++) {
+            xo_mc_chroma(pix, 8, c->fref_c[pl], c->stride_c, mx, my, c->bw / 2, c->bh / 2);
+            cost += xo_pixel_cmp(c->sub_metric, c->in->i_pixel + 3, c->fenc_c[pl], 16, pix, 8);
+            if (cost >= bcost) break;
+        }
+    }
+    return cost;
+}
+
 static const int8_t hex_ring[8][2] = { { -1, -2 }, { -2, 0 }, { -1, 2 }, { 1, 2 }, { 2, 0 }, { 1, -2 }, { -1, -2 }, { -2, 0 } };
 static const int8_t prev_of[8] = { 5, 0, 1, 2, 3, 4, 5, 0 }; /* (x-1)%6, me.c:46-47 */
 
@@ -81,6 +102,7 @@ typedef struct { int sad; int16_t mx, my; } cand_t;
 typedef struct {
     int subme;      /* h->mb.i_subpel_refine */
     int mbcmp_satd; /* mbcmp == satd (user subme>1) */
+    const xo_chroma *ch; /* non-NULL: h->mb.b_chroma_me */
 } me_sub;
 
 static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
@@ -104,6 +126,17 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
         memcpy(c->fenc + 16 * y, fenc_plane + (in->by + y) * stride + in->bx, c->bw);
     for (int k = 0; k < 4; k++)
         c->fref[k] = fref_planes[k] ? fref_planes[k] + in->by * stride + in->bx : NULL;
+    c->chroma_me = sub->ch && in->i_pixel <= 3; /* me.c:686 */
+    if (c->chroma_me) {
+        const xo_chroma *ch = sub->ch;
+        const uint8_t *fe[2] = { ch->fenc_u, ch->fenc_v }, *fr[2] = { ch->fref_u, ch->fref_v };
+        c->stride_c = ch->stride_c;
+        for (int pl = 0; pl < 2; pl++) {
+            for (int y = 0; y < c->bh / 2; y++)
+                memcpy(c->fenc_c[pl] + 16 * y, fe[pl] + (in->by / 2 + y) * ch->stride_c + in->bx / 2, c->bw / 2);
+            c->fref_c[pl] = fr[pl] + (in->by / 2) * ch->stride_c + in->bx / 2;
+        }
+    }
 
     /* me.c:182-186 */
     bmx = clip3(in->mvp[0], x_min * 4, x_max * 4);
@@ -312,7 +345,7 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
         }
         /* !b_refine_qpel: me.c:729-736 */
         if (sbmy > spel_y_max) sbmy = spel_y_max;
-        sbcost = qpel_cost(c, c->sub_metric, sbmx, sbmy);
+        sbcost = satd_cost(c, sbmx, sbmy, XO_COST_MAX);
         bdir = -1;
         for (int i = qpel_iters; i > 0; i--) { /* me.c:755-767 */
             int ox = sbmx, oy = sbmy;
@@ -320,14 +353,14 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
             odir = bdir;
             for (int k = 0; k < 4; k++)
                 if ((k ^ 1) != odir) {
-                    int cst = qpel_cost(c, c->sub_metric, ox + d[k][0], oy + d[k][1]);
+                    int cst = satd_cost(c, ox + d[k][0], oy + d[k][1], sbcost);
                     if (cst < sbcost) { sbcost = cst; sbmx = ox + d[k][0]; sbmy = oy + d[k][1]; bdir = k; }
                 }
             if (sbmx == ox && sbmy == oy) break;
         }
         if (sbmy > spel_y_max) { /* me.c:770-775 */
             sbmy = spel_y_max;
-            sbcost = qpel_cost(c, c->sub_metric, sbmx, sbmy);
+            sbcost = satd_cost(c, sbmx, sbmy, XO_COST_MAX);
         }
         mvx = sbmx; mvy = sbmy; cost = sbcost;
         cost_mv = c->cmx[mvx] + c->cmy[mvy];
@@ -341,7 +374,7 @@ void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_
                        const uint16_t *integral, const xo_me_in *in, xo_me_out *out)
 {
     const uint8_t *planes[4] = { fref_plane, NULL, NULL, NULL };
-    me_sub sub = { 1, 0 };
+    me_sub sub = { 1, 0, NULL };
     me_core(g, fenc_plane, planes, integral, in, &sub, out);
 }
 
@@ -349,7 +382,15 @@ void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_
 void xo_me_search_subpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
                          const uint16_t *integral, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
 {
-    me_sub sub = { subme, mbcmp_satd };
+    me_sub sub = { subme, mbcmp_satd, NULL };
+    me_core(g, fenc_plane, fref_planes, integral, in, &sub, out);
+}
+
+/* the same with chroma in the sub-pel cost (P-slices, subme >= 5, --chroma-me: S/encoder/analyse.c b_chroma_me) */
+void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const uint16_t *integral,
+                                const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
+{
+    me_sub sub = { subme, mbcmp_satd, ch };
     me_core(g, fenc_plane, fref_planes, integral, in, &sub, out);
 }
 
@@ -368,6 +409,6 @@ void xo_me_search_subpel_strided(int stride, int lines_unused, const uint8_t *fe
     memset(&g, 0, sizeof(g));
     g.stride = stride;
     (void)lines_unused;
-    me_sub sub = { subme, mbcmp_satd };
+    me_sub sub = { subme, mbcmp_satd, NULL };
     me_core(&g, fenc_plane, fref_planes, NULL, in, &sub, out);
 }

@@ -266,3 +266,13 @@ def blocky_recon(clip, g, frame=0, seed=0):
         off = rng.integers(-6, 7, (h // bs, w // bs))
         return np.clip(a.astype(np.int32) + np.kron(off, np.ones((bs, bs), np.int32)) + rng.integers(-1, 2, a.shape), 0, 255).astype(np.uint8)
     return blockify(y, 4), blockify(u, 2), blockify(v, 2)
+
+
+def padded_chroma(g, c):
+    """(h/2, w/2) chroma picture -> plane with mod16 padding and 16-px replicated borders (x264_frame_expand_border, planes 1/2)"""
+    H, W = g.lines // 2, g.mb_width * 8
+    out = np.zeros((H + 32, W + 32), np.uint8)
+    ys = np.clip(np.arange(-16, H + 16), 0, c.shape[0] - 1)
+    xs = np.clip(np.arange(-16, W + 16), 0, c.shape[1] - 1)
+    out[:] = c[np.ix_(ys, xs)]
+    return out

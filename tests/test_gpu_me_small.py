@@ -117,3 +117,43 @@ def test_tesa(pkg, ctx, port, me_range, subme, fpel_satd):
             bad.append((i, mi.i_pixel, got, want))
     assert not bad, (len(bad), bad[:4])
     fenc.close(); fref.close()
+
+
+@pytest.mark.parametrize("method", [X.ME_DIA, X.ME_HEX])
+@pytest.mark.parametrize("subme", [5, 6, 7])
+def test_chroma_me(pkg, ctx, port, method, subme):
+    """b_chroma_me: COST_MV_SATD adds mc_chroma + mbcmp[i_pixel+3] of U and V (me.c:655-677) for partitions >= 8x8; also exercises
+    the device-side chroma border expansion (frame.c:229-236)"""
+    from x264_vs2008_b200 import synth
+    from helpers import padded_chroma
+    w, h = 320, 192
+    clip = synth.Clip(w, h, seed=60 + subme)
+    g = port.geometry(w, h)
+    (y1, u1, v1), (y0, u0, v0) = clip.yuv420(1), clip.yuv420(0)
+    fenc, fref = ctx.frame(w, h, pkg.FRAME_CHROMA), ctx.frame(w, h, pkg.FRAME_HPEL | pkg.FRAME_CHROMA)
+    fenc.upload(y1); fenc.upload_chroma(u1, v1); fenc.expand_border()
+    fref.upload(y0); fref.upload_chroma(u0, v0); fref.expand_border(); fref.filter()
+    chroma = [padded_chroma(g, c) for c in (u1, v1, u0, v0)]
+    for k, pl in enumerate((pkg.PLANE_CB, pkg.PLANE_CR)):  # device border expansion of the chroma planes
+        assert np.array_equal(fref.download(pl), chroma[2 + k])
+    pe, pr = port.plane_from_picture(g, y1), port.plane_from_picture(g, y0)
+    fh, fv, fc, _ = port.frame_filter(g, pr, 0, want_integral=False)
+    jobs, mis = make_me_jobs(pkg, g, seed=200 * method + subme, n=400, me_range=16, qp=(12, 26, 38), pixels=(0, 1, 2, 3, 4, 5, 6), mvp_spread=40)
+    _fill_spel(jobs, mis)
+    for j, mi in zip(jobs, mis):  # chroma needs even block positions; partitions >= 8x8 sit on multiples of 8 anyway
+        j["bx"], j["by"] = (int(j["bx"]) // 8) * 8, (int(j["by"]) // 8) * 8
+        mi.bx, mi.by = int(j["bx"]), int(j["by"])
+    jobs["flags"] = pkg.ME_MBCMP_SATD | pkg.ME_CHROMA
+    res = ctx.me_search_small(fenc, fref, method, 16, subme, jobs)
+    bad, n_differs = [], 0
+    for i, mi in enumerate(mis):
+        mi.me_method = method
+        o = port.me_search_subpel_chroma(g, pe, [pr, fh, fv, fc], None, chroma, mi, subme, 1)
+        plain = port.me_search_subpel(g, pe, [pr, fh, fv, fc], None, mi, subme, 1)
+        n_differs += (plain.cost != o.cost)
+        got = (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"]))
+        if got != (o.mv[0], o.mv[1], o.cost, o.cost_mv):
+            bad.append((i, mi.i_pixel, got, (o.mv[0], o.mv[1], o.cost, o.cost_mv)))
+    assert not bad, (len(bad), bad[:4])
+    assert n_differs > 100
+    fenc.close(); fref.close()

@@ -168,3 +168,29 @@ def test_deblock(pkg, port, ref, size, kw):
         assert not np.array_equal(outs[0][0].reshape(-1, g.stride)[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]], y)  # something was filtered
         for a, b in zip(*outs):
             assert np.array_equal(a, b)
+
+
+def test_chroma_me(pkg, port, ref):
+    """refine_subpel with b_chroma_me (P slices, subme >= 5): COST_MV_SATD adds mc_chroma + mbcmp[i_pixel+3] of U and V (me.c:655-677)"""
+    from x264_vs2008_b200 import synth
+    from helpers import make_me_jobs, padded_chroma
+    w, h = 160, 128
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=21)
+    (y1, u1, v1), (y0, u0, v0) = clip.yuv420(1), clip.yuv420(0)
+    pe, pr = port.plane_from_picture(g, y1), port.plane_from_picture(g, y0)
+    fh, fv, fc, integ = port.frame_filter(g, pr, 1)
+    chroma = [padded_chroma(g, c) for c in (u1, v1, u0, v0)]
+    n_diff = 0
+    for method in (X.ME_DIA, X.ME_HEX, X.ME_ESA):
+        _, mis = make_me_jobs(pkg, g, seed=300 + method, n=60, me_range=16, qp=(12, 26, 40), pixels=(0, 1, 2, 3))
+        for subme in (5, 6, 7):
+            for mi in mis:
+                mi.me_method = method
+                mi.bx, mi.by = (mi.bx // 16) * 16, (mi.by // 16) * 16
+                a = port.me_search_subpel_chroma(g, pe, [pr, fh, fv, fc], integ, chroma, mi, subme, 1)
+                b = ref.me_search_subpel_chroma(g, pe, [pr, fh, fv, fc], integ, chroma, mi, subme, 1)
+                assert (a.mv[0], a.mv[1], a.cost, a.cost_mv) == (b.mv[0], b.mv[1], b.cost, b.cost_mv)
+                c = port.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
+                n_diff += (c.mv[0], c.mv[1]) != (a.mv[0], a.mv[1]) or c.cost != a.cost
+    assert n_diff > 50  # the chroma term really changes costs/decisions on this content

@@ -53,6 +53,10 @@ class LowresOut(C.Structure):
     _fields_ = [("score", C.c_int), ("score_aq", C.c_int), ("intra_mbs", C.c_int), ("intra_cost_sum", C.c_int)]
 
 
+class Chroma(C.Structure):
+    _fields_ = [("fenc_u", C.c_void_p), ("fenc_v", C.c_void_p), ("fref_u", C.c_void_p), ("fref_v", C.c_void_p), ("stride_c", C.c_int)]
+
+
 class DeblockIn(C.Structure):
     _fields_ = [("alpha_c0_offset", C.c_int), ("beta_offset", C.c_int), ("chroma_qp_offset", C.c_int), ("b_slice_b", C.c_int),
                 ("b_psub8x8", C.c_int), ("b_cavlc_8x8dct", C.c_int),
@@ -113,6 +117,8 @@ class Oracle:
                                            i16p, i32p, i16p, i32p, i16p, u16p, C.POINTER(LowresOut)]
         L.xo_lowres_intra_pred.argtypes = [C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
         L.xo_lowres_intra_cost.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.xo_me_search_subpel_chroma.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), u16p, C.POINTER(Chroma), C.POINTER(MeIn), C.c_int,
+                                                 C.c_int, C.POINTER(MeOut)]
         L.xo_frame_deblock.argtypes = [C.POINTER(Geom), C.POINTER(DeblockIn), u8p, u8p, u8p, C.c_int]
         self.backend = L.xo_backend().decode()
 
@@ -181,6 +187,17 @@ class Oracle:
                                      subme, mbcmp_satd, C.byref(out))
         return out
 
+
+    def me_search_subpel_chroma(self, g, fenc, planes4, integral, chroma, mi, subme, mbcmp_satd):
+        """chroma: (fenc_u, fenc_v, fref_u, fref_v) 2-D padded chroma planes (16-px borders, as Frame.download(PLANE_CB) returns them)"""
+        out = MeOut()
+        arr = (u8p * 4)(*[_ptr(p, u8p, g.origin) for p in planes4])
+        sc = chroma[0].shape[1]
+        ch = Chroma(*[a.ctypes.data + 16 * sc + 16 for a in chroma], sc)
+        self.lib.xo_me_search_subpel_chroma(C.byref(g), _ptr(fenc, u8p, g.origin), arr,
+                                            _ptr(integral, u16p, g.origin) if integral is not None else None, C.byref(ch), C.byref(mi),
+                                            subme, mbcmp_satd, C.byref(out))
+        return out
 
     def frame_deblock(self, g, info, y, u, v):
         """y: padded luma plane (flat, pixel 0,0 at g.origin); u, v: 2-D chroma arrays (contiguous).  Filtered in place."""

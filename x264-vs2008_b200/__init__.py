@@ -36,6 +36,7 @@ ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1")
 ME_FINAL = np.dtype([("mv", "<i2", (2,)), ("cost", "<i4"), ("cost_mv", "<i4"), ("bmx", "<i2"), ("bmy", "<i2")], align=True)
 ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_TESA, ME_METHOD_SEEDED = 0, 1, 4, 8
 ME_MBCMP_SATD = 8
+ME_CHROMA = 32
 LOWRES_WEIGHTED_BIPRED = 16
 ME_RESULT = np.dtype([("bmx", "<i2"), ("bmy", "<i2"), ("bcost", "<i4"), ("seed_mx", "<i2"), ("seed_my", "<i2"),
                       ("seed_cost", "<i4")], align=True)

@@ -201,8 +201,13 @@ extern "C" int x264_cuda_frame_expand_border(x264_cuda_t *ctx, x264_cuda_frame_t
     const x264_cuda_geom_t &g = f->g;
     uint8_t *planes[1] = { f->plane[0] };
     // mod16 padding and the 32-px borders are both replications of the picture edge (frame.c:304-331, :218-267)
-    return launch_border(ctx, planes, 1, g.stride, 0, g.width - 1, 0, g.height - 1, -PADH, g.mb_width * 16 + PADH, -PADV,
-                         g.lines + PADV);
+    if (launch_border(ctx, planes, 1, g.stride, 0, g.width - 1, 0, g.height - 1, -PADH, g.mb_width * 16 + PADH, -PADV, g.lines + PADV)) return -1;
+    if (f->buf_chroma) { // planes 1 and 2: half size, half padding (frame.c:229-236)
+        uint8_t *cp[2] = { f->chroma[0], f->chroma[1] };
+        return launch_border(ctx, cp, 2, f->stride_c, 0, g.width / 2 - 1, 0, g.height / 2 - 1, -PADH / 2, g.mb_width * 8 + PADH / 2, -PADV / 2,
+                             g.lines / 2 + PADV / 2);
+    }
+    return 0;
 }
 
 extern "C" int x264_cuda_frame_filter(x264_cuda_t *ctx, x264_cuda_frame_t *f)

@@ -23,6 +23,10 @@ struct SearchCtx {
     int lines_pad;                 // unused
     int2 *list; int list_cap;      // candidate list scratch: (sad, mx | my << 16)
     int i_pixel;
+    // b_chroma_me (me.c:686): chroma planes of fenc / fref at the block's chroma origin
+    const uint8_t *fe_c[2], *ref_c[2];
+    int stride_c;
+    bool chroma_me;
 };
 
 // cost of THIS lane's candidate (qpel mv), identical on all lanes of the group; invalid candidates return COST_MAX+1
@@ -41,6 +45,68 @@ __device__ __forceinline__ int eval_round(const SearchCtx &c, bool satd, int lan
     return add_mv_cost ? v + c.cmx[mx] + c.cmy[my] : v;
 }
 __device__ __forceinline__ int cand_cost(const SearchCtx &c, int cost, int k) { return __shfl_sync(0xffffffffu, cost, k * c.U); }
+
+// The chroma term of COST_MV_SATD (me.c:655-677): mc_chroma (mc.c:205-236) of the bw/2 x bh/2 blocks of U and V at the luma
+// qpel mv, compared with mbcmp[i_pixel+3].  Chroma units (8x4 for 16-wide partitions, 4x4 for 8-wide ones) are spread over
+// the lanes of the candidate's group like the luma units; there are never more of them than luma units.  The reference
+// adds U and V only while the candidate still beats bcost — the decision is the same as with the full sum (costs are >= 0).
+__device__ __forceinline__ int chroma_unit_cost(const SearchCtx &c, bool satd, int u, int mx, int my)
+{
+    const bool wide = c.bw == 16;                 // chroma block 8 wide, else 4
+    const int per_plane = c.bh >> 3;              // units per plane: bh/2 rows in units of 4 rows
+    if (u >= 2 * per_plane) return 0;
+    const int pl = u / per_plane, cy0 = (u - pl * per_plane) * 4;
+    const int d8x = mx & 7, d8y = my & 7;
+    const int cA = (8 - d8x) * (8 - d8y), cB = d8x * (8 - d8y), cC = (8 - d8x) * d8y, cD = d8x * d8y;
+    const uint8_t *s = c.ref_c[pl] + (ptrdiff_t)((my >> 3) + cy0) * c.stride_c + (mx >> 3);
+    const uint8_t *f = c.fe_c[pl] + (ptrdiff_t)cy0 * c.stride_c;
+    const int w = wide ? 8 : 4;
+    uint32_t pr[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    int top[9];
+#pragma unroll
+    for (int x = 0; x < 9; x++) top[x] = x <= w ? s[x] : 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int bot[9];
+#pragma unroll
+        for (int x = 0; x < 9; x++) bot[x] = x <= w ? s[(ptrdiff_t)(y + 1) * c.stride_c + x] : 0;
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+            if (x < w) pr[y][x >> 2] |= (uint32_t)((cA * top[x] + cB * top[x + 1] + cC * bot[x] + cD * bot[x + 1] + 32) >> 6) << (8 * (x & 3));
+#pragma unroll
+        for (int x = 0; x < 9; x++) top[x] = bot[x];
+    }
+    if (wide) {
+        uint2 fr[4], rr[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) { fr[y] = ldg8(f + (ptrdiff_t)y * c.stride_c); rr[y] = make_uint2(pr[y][0], pr[y][1]); }
+        if (satd) return satd_8x4_rows(fr, rr);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int y = 0; y < 4; y++) { acc = sad4_acc(fr[y].x, rr[y].x, acc); acc = sad4_acc(fr[y].y, rr[y].y, acc); }
+        return (int)acc;
+    }
+    uint32_t fr[4], rr[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) { fr[y] = ldg4(f + (ptrdiff_t)y * c.stride_c); rr[y] = pr[y][0]; }
+    if (satd) return satd_4x4_rows(fr, rr);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++) acc = sad4_acc(fr[y], rr[y], acc);
+    return (int)acc;
+}
+
+// COST_MV_SATD: mbcmp of the luma block (+ mv cost) + the chroma term when b_chroma_me
+__device__ __forceinline__ int eval_round_satd(const SearchCtx &c, int lane, bool valid, int mx, int my)
+{
+    int v = eval_round(c, c.mbcmp_satd, lane, valid, mx, my);
+    if (c.chroma_me) { // warp-uniform
+        int cv = valid ? chroma_unit_cost(c, c.mbcmp_satd, lane & (c.U - 1), mx, my) : 0;
+        for (int o = c.U >> 1; o > 0; o >>= 1) cv += __shfl_xor_sync(0xffffffffu, cv, o);
+        if (valid) v += cv;
+    }
+    return v;
+}
 
 __constant__ int8_t c_hex2[8][2] = { { -1, -2 }, { -2, 0 }, { -1, 2 }, { 1, 2 }, { 2, 0 }, { 1, -2 }, { -1, -2 }, { -2, 0 } };
 __constant__ int8_t c_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };
@@ -313,7 +379,7 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
     int cost_mv = c.cmx[mvx] + c.cmy[mvy];
     if (bmx == pmx && bmy == pmy && subme < 3) cost += cost_mv;
 
-    // ---- refine_subpel(h, m, hpel, qpel, NULL, 0), me.c:680-778 (b_chroma_me == 0)
+    // ---- refine_subpel(h, m, hpel, qpel, NULL, 0), me.c:680-778
     if (subme >= 2) {
         const int hpel_iters = c_subpel_iters[subme][2], qpel_iters = c_subpel_iters[subme][3];
         int sx = mvx, sy = mvy, sc = cost;
@@ -339,14 +405,14 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
             if (sx == ox && sy == oy) break;
         }
         if (sy > spel_ymax) sy = spel_ymax; // !b_refine_qpel, me.c:729-736
-        sc = eval_round(c, c.mbcmp_satd, lane, true, sx, sy);
+        sc = eval_round_satd(c, lane, true, sx, sy);
         int bdir = -1;
         for (int i = qpel_iters; i > 0; i--) { // quarter-pel diamond with mbcmp, me.c:755-767
             const int odir = bdir, ox = sx, oy = sy;
             const int k = lane / c.U;
             const int dx = k == 2 ? -1 : k == 3 ? 1 : 0, dy = k == 0 ? -1 : k == 1 ? 1 : 0;
             const bool valid = k < 4 && (k ^ 1) != odir;
-            const int v = eval_round(c, c.mbcmp_satd, lane, valid, ox + dx, oy + dy);
+            const int v = eval_round_satd(c, lane, valid, ox + dx, oy + dy);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int vj = cand_cost(c, v, j);
@@ -357,7 +423,7 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
             }
             if (sx == ox && sy == oy) break;
         }
-        if (sy > spel_ymax) { sy = spel_ymax; sc = eval_round(c, c.mbcmp_satd, lane, true, sx, sy); } // me.c:770-775
+        if (sy > spel_ymax) { sy = spel_ymax; sc = eval_round_satd(c, lane, true, sx, sy); } // me.c:770-775
         mvx = sx; mvy = sy; cost = sc;
         cost_mv = c.cmx[mvx] + c.cmy[mvy];
     } else if (mvy > job.mv_max_spel[1]) {
@@ -370,7 +436,10 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
     }
 }
 
-struct Planes { const uint8_t *fenc; const uint8_t *ref[4]; int stride; const uint16_t *sums8, *sums4; int2 *scratch; int list_cap; };
+struct Planes {
+    const uint8_t *fenc; const uint8_t *ref[4]; int stride; const uint16_t *sums8, *sums4; int2 *scratch; int list_cap;
+    const uint8_t *fenc_c[2], *ref_c[2]; int stride_c; // chroma planes (NULL without X264_CUDA_FRAME_CHROMA on both frames)
+};
 
 __global__ void __launch_bounds__(128) me_small_kernel(Planes pl, const x264_cuda_me_job_t *__restrict__ jobs, int n_jobs,
                                                        const int16_t *const *__restrict__ cost_tabs, int method, int me_range, int subme,
@@ -409,6 +478,16 @@ __global__ void __launch_bounds__(128) me_small_kernel(Planes pl, const x264_cud
     c.cmx = tab - job.mvp[0]; c.cmy = tab - job.mvp[1];
     c.fpel_satd = job.flags & X264_CUDA_ME_FPEL_SATD; c.mbcmp_satd = job.flags & X264_CUDA_ME_MBCMP_SATD;
     c.i_pixel = ip;
+    c.chroma_me = (job.flags & X264_CUDA_ME_CHROMA) && ip <= X264_CUDA_PIXEL_8x8; // me.c:686
+    if (c.chroma_me && !pl.ref_c[0]) {
+        if (lane == 0) { x264_cuda_me_final_t r = { { 0, 0 }, -1, -1, 0, 0 }; results[j] = r; } // frames without chroma planes
+        continue;
+    }
+    c.stride_c = pl.stride_c;
+    {
+        const size_t offc = (size_t)(job.by >> 1) * pl.stride_c + (job.bx >> 1);
+        c.fe_c[0] = pl.fenc_c[0] + offc; c.fe_c[1] = pl.fenc_c[1] + offc; c.ref_c[0] = pl.ref_c[0] + offc; c.ref_c[1] = pl.ref_c[1] + offc;
+    }
     c.sums8 = pl.sums8 ? pl.sums8 + off : nullptr; c.sums4 = pl.sums4 ? pl.sums4 + off : nullptr;
     c.list = pl.scratch ? pl.scratch + (size_t)gw * pl.list_cap : nullptr; c.list_cap = pl.list_cap; c.lines_pad = 0;
     if (method == X264_CUDA_ME_METHOD_TESA && (!c.list || !(ip > X264_CUDA_PIXEL_8x8 ? c.sums4 : c.sums8))) {
@@ -480,7 +559,12 @@ extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_f
     }
     const int16_t *const *d_tabs;
     if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
-    Planes pl = { fenc->plane[0], { fref->plane[0], fref->plane[1], fref->plane[2], fref->plane[3] }, fenc->g.stride, nullptr, nullptr, nullptr, 0 };
+    Planes pl = { fenc->plane[0], { fref->plane[0], fref->plane[1], fref->plane[2], fref->plane[3] }, fenc->g.stride, nullptr, nullptr, nullptr, 0,
+                  { nullptr, nullptr }, { nullptr, nullptr }, 0 };
+    if (fenc->buf_chroma && fref->buf_chroma && fenc->stride_c == fref->stride_c) {
+        pl.fenc_c[0] = fenc->chroma[0]; pl.fenc_c[1] = fenc->chroma[1]; pl.ref_c[0] = fref->chroma[0]; pl.ref_c[1] = fref->chroma[1];
+        pl.stride_c = fenc->stride_c;
+    }
     int blocks = (n_jobs + 3) / 4;
     if (method == X264_CUDA_ME_METHOD_TESA) {
         if (!fref->integral) {
@@ -757,6 +841,7 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
                     for (int k = 0; k < 4; k++) c.planes[k] = a.ref[l][k] + off;
                     c.cmx = a.tab - job.mvp[0]; c.cmy = a.tab - job.mvp[1];
                     c.fpel_satd = a.fpel_satd; c.mbcmp_satd = a.mbcmp_satd;
+                    c.chroma_me = false; // the lookahead has no chroma planes
                     c.i_pixel = X264_CUDA_PIXEL_8x8; c.sums8 = c.sums4 = nullptr; c.list = nullptr; c.list_cap = 0; c.lines_pad = 0;
                     warp_search(c, job, a.method, a.me_range, 4, lane, &s_fin[wid]);
                     __syncwarp();
