@@ -253,6 +253,26 @@ X264_CUDA_API int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_
                                               const int8_t *d_type, const int8_t *d_qp, const int8_t *d_transform8x8, const uint8_t *d_nnz,
                                               const int8_t *d_ref0, const int16_t *d_mv0, const int8_t *d_ref1, const int16_t *d_mv1);
 
+/* ------------------------------------------------------------------ whole-frame analysis metrics ------ */
+/* per-frame / per-macroblock measures without inter-macroblock dependencies.  The device computes the
+ * integer parts; the float tails stay on the host (x264_cuda_host_*) because their results depend on float evaluation order.
+ * plane: X264_CUDA_PLANE_FULL / _CB / _CR (or a half-pel plane id). */
+/* x264_pixel_ssd_wxh (S/common/pixel.c:98-136) over the top-left width x height pixels of one plane of two frames: PSNR input
+ * (S/encoder/encoder.c:1034-1046) */
+X264_CUDA_API int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int width, int height,
+                                      int64_t *ssd);
+/* ssim_4x4x2_core (pixel.c:435-460) for every 4x4 block of the region: sums[(height/4)*(width/4)][4] = s1, s2, ss, s12;
+ * x264_cuda_host_ssim_end then gives x264_pixel_ssim_wxh's value (pixel.c:462-509) */
+X264_CUDA_API int x264_cuda_frame_ssim_sums(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int width, int height,
+                                            int (*sums)[4]);
+X264_CUDA_API float x264_cuda_host_ssim_end(const int (*sums)[4], int w4, int h4);
+/* ac_energy_mb (S/encoder/ratecontrol.c:171-191) of every macroblock (frame needs X264_CUDA_FRAME_CHROMA): energy[mb_width*mb_height];
+ * x264_cuda_host_aq then is x264_adaptive_quant_frame (:233-249): f_qp_offset[mb] and (optional) i_inv_qscale_factor[mb] */
+X264_CUDA_API int x264_cuda_frame_mb_energy(x264_cuda_t *ctx, const x264_cuda_frame_t *frame, uint32_t *energy);
+X264_CUDA_API void x264_cuda_host_aq(const uint32_t *energy, int n_mb, float aq_strength, float *qp_offset, uint16_t *inv_qscale);
+/* x264_pixel_hadamard_ac_16x16 (pixel.c:306-358) of every macroblock of the luma plane (psy-rd source energy): out[mb] */
+X264_CUDA_API int x264_cuda_frame_mb_hadamard_ac(x264_cuda_t *ctx, const x264_cuda_frame_t *frame, uint64_t *out);
+
 /* ------------------------------------------------------------------ motion compensation -------------- */
 /* Frame-batched x264_mb_mc_0xywh (S/common/macroblock.c:462-486): for each job the w x h luma block at (bx,by) is
  * predicted from fref at quarter-pel mv (mc_luma, S/common/mc.c:160-179) and, when both frames carry chroma planes, the

@@ -571,3 +571,78 @@ void xo_frame_deblock(const xo_geom *g, const xo_deblock_in *d, uint8_t *py, uin
     h->chroma_qp_table = i_chroma_qp_table + 12 + save_off;
     pps->b_cabac = save_cabac; pps->b_transform_8x8_mode = save_t8;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* whole-frame metrics through the reference's own functions                                          */
+int64_t xo_frame_ssd(const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height)
+{
+    tables();
+    return x264_pixel_ssd_wxh(&g_pixf, (uint8_t *)p1, s1, (uint8_t *)p2, s2, width, height);
+}
+float xo_frame_ssim(const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height)
+{
+    tables();
+    void *buf = malloc(8 * (width / 4 + 3) * sizeof(int));
+    float r = x264_pixel_ssim_wxh(&g_pixf, (uint8_t *)p1, s1, (uint8_t *)p2, s2, width, height, buf);
+    free(buf);
+    return r;
+}
+void xo_frame_ssim_sums(const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height, int (*sums)[4])
+{
+    tables();
+    const int w4 = width >> 2, h4 = height >> 2;
+    for (int by = 0; by < h4; by++)
+        for (int bx = 0; bx + 1 < w4 + (w4 & 1); bx += 2) {
+            int t[2][4];
+            g_pixf.ssim_4x4x2_core(p1 + 4 * by * s1 + 4 * bx, s1, p2 + 4 * by * s2 + 4 * bx, s2, t);
+            memcpy(sums[by * w4 + bx], t[0], 16);
+            if (bx + 1 < w4) memcpy(sums[by * w4 + bx + 1], t[1], 16);
+        }
+}
+void xo_frame_mb_energy(const xo_geom *g, const uint8_t *py, const uint8_t *pu, const uint8_t *pv, int stride_c, uint32_t *out)
+{
+    /* ac_energy_mb is static in ratecontrol.c: same three table calls; xo_frame_aq below goes through the real function */
+    tables();
+    for (int mb_y = 0; mb_y < g->mb_height; mb_y++)
+        for (int mb_x = 0; mb_x < g->mb_width; mb_x++) {
+            unsigned int var = g_pixf.var[PIXEL_16x16]((uint8_t *)py + 16 * (mb_x + mb_y * g->stride), g->stride);
+            var += g_pixf.var[PIXEL_8x8]((uint8_t *)pu + 8 * (mb_x + mb_y * stride_c), stride_c);
+            var += g_pixf.var[PIXEL_8x8]((uint8_t *)pv + 8 * (mb_x + mb_y * stride_c), stride_c);
+            out[mb_x + mb_y * g->mb_width] = X264_MAX(var, 1);
+        }
+}
+void xo_frame_mb_hadamard_ac(const xo_geom *g, const uint8_t *py, uint64_t *out)
+{
+    tables();
+    for (int mb_y = 0; mb_y < g->mb_height; mb_y++)
+        for (int mb_x = 0; mb_x < g->mb_width; mb_x++)
+            out[mb_x + mb_y * g->mb_width] = g_pixf.hadamard_ac[PIXEL_16x16]((uint8_t *)py + 16 * (mb_x + mb_y * g->stride), g->stride);
+}
+void xo_aq_from_energy(const uint32_t *energy, int n, float aq_strength, float *qp_offset, uint16_t *inv_qscale)
+{
+    (void)energy; (void)n; (void)aq_strength; (void)qp_offset; (void)inv_qscale;
+    abort(); /* the reference has no such entry point: use xo_frame_aq */
+}
+void xo_frame_aq(const xo_geom *g, const uint8_t *py, const uint8_t *pu, const uint8_t *pv, int stride_c, float aq_strength, float *qp_offset,
+                 uint16_t *inv_qscale)
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, X264_ME_ESA, 1, 0, 1, &f); /* the lowres handle: frames carry i_inv_qscale_factor */
+    for (int y = 0; y < g->lines; y++) memcpy(f->plane[0] + y * f->i_stride[0], py + y * g->stride, 16 * g->mb_width);
+    for (int y = 0; y < g->lines / 2; y++) {
+        memcpy(f->plane[1] + y * f->i_stride[1], pu + y * stride_c, 8 * g->mb_width);
+        memcpy(f->plane[2] + y * f->i_stride[2], pv + y * stride_c, 8 * g->mb_width);
+    }
+    const int n_mb = g->mb_width * g->mb_height;
+    /* CQP handles switch AQ off (encoder.c:429), so their frames lack the two arrays (frame.c:137-142): give them some */
+    if (!f->f_qp_offset) f->f_qp_offset = x264_malloc(n_mb * sizeof(float));
+    if (!f->i_inv_qscale_factor) f->i_inv_qscale_factor = x264_malloc(n_mb * sizeof(uint16_t));
+    const float save = h->param.rc.f_aq_strength;
+    h->param.rc.f_aq_strength = aq_strength;
+    h->mb.b_interlaced = 0;
+    x264_adaptive_quant_frame(h, f);
+    h->param.rc.f_aq_strength = save;
+    const int n = g->mb_width * g->mb_height;
+    memcpy(qp_offset, f->f_qp_offset, n * sizeof(float));
+    if (h->frames.b_have_lowres) memcpy(inv_qscale, f->i_inv_qscale_factor, n * sizeof(uint16_t));
+}

@@ -204,6 +204,18 @@ typedef struct {
 } xo_deblock_in;
 void xo_frame_deblock(const xo_geom *g, const xo_deblock_in *d, uint8_t *py, uint8_t *pu, uint8_t *pv, int stride_c);
 
+/* ---------------- whole-frame analysis metrics (no inter-macroblock dependencies) ---------------- */
+int64_t xo_frame_ssd(const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height);                 /* pixel.c:98-136 */
+void xo_frame_mb_energy(const xo_geom *g, const uint8_t *py, const uint8_t *pu, const uint8_t *pv, int stride_c, uint32_t *out); /* ratecontrol.c:171-191 */
+void xo_frame_mb_hadamard_ac(const xo_geom *g, const uint8_t *py, uint64_t *out);                                  /* pixel.c:306-358 */
+void xo_frame_ssim_sums(const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height, int (*sums)[4]); /* pixel.c:435-460 */
+float xo_frame_ssim(const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height);                 /* pixel.c:484-509 */
+/* x264_adaptive_quant_frame (ratecontrol.c:233-249) given the energies: f_qp_offset[mb], i_inv_qscale_factor[mb] */
+void xo_aq_from_energy(const uint32_t *energy, int n, float aq_strength, float *qp_offset, uint16_t *inv_qscale);
+/* the same through the frame: energies + float formula in one go (reference: x264_adaptive_quant_frame itself) */
+void xo_frame_aq(const xo_geom *g, const uint8_t *py, const uint8_t *pu, const uint8_t *pv, int stride_c, float aq_strength, float *qp_offset,
+                 uint16_t *inv_qscale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,3 +194,59 @@ def test_chroma_me(pkg, port, ref):
                 c = port.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
                 n_diff += (c.mv[0], c.mv[1]) != (a.mv[0], a.mv[1]) or c.cost != a.cost
     assert n_diff > 50  # the chroma term really changes costs/decisions on this content
+
+
+def _metric_inputs(port, w, h, seed):
+    from x264_vs2008_b200 import synth
+    from helpers import blocky_recon
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=seed)
+    y, u, v = clip.yuv420(1)
+    ry, ru, rv = blocky_recon(clip, g, frame=1, seed=seed)  # a "reconstruction" of the same picture
+    H16, W16 = 16 * g.mb_height, 16 * g.mb_width
+    def pad(a, hh, ww):
+        out = np.zeros((hh, ww), np.uint8)
+        out[:a.shape[0], :a.shape[1]] = a
+        return out
+    return g, (pad(y, H16, W16), pad(u, H16 // 2, W16 // 2), pad(v, H16 // 2, W16 // 2)), (ry, ru, rv)
+
+
+@pytest.mark.parametrize("size", [(176, 144), (100, 70), (352, 288), (20, 12)])
+def test_frame_metrics(pkg, port, ref, size):
+    """x264_pixel_ssd_wxh, x264_pixel_ssim_wxh, ac_energy_mb / x264_adaptive_quant_frame, hadamard_ac: reference vs port, and the
+    product's host-side float tails (x264_cuda_host_ssim_end, x264_cuda_host_aq) vs the reference"""
+    w, h = size
+    g, (y, u, v), (ry, ru, rv) = _metric_inputs(port, w, h, seed=9)
+    for (a, b, ww, hh) in ((y, ry, w, h), (u, ru, w // 2, h // 2), (v, rv, w // 2, h // 2), (y, ry, w - 3, h - 5)):
+        assert port.frame_ssd(a, b, ww, hh) == ref.frame_ssd(a, b, ww, hh) > 0
+        if ww >= 8 and hh >= 8:
+            s_ref = ref.frame_ssim(a, b, ww, hh)
+            assert port.frame_ssim(a, b, ww, hh) == s_ref
+            sums = port.frame_ssim_sums(a, b, ww, hh)
+            assert np.array_equal(sums, ref.frame_ssim_sums(a, b, ww, hh))
+            assert float(pkg.lib().x264_cuda_host_ssim_end(sums.ctypes.data, ww // 4, hh // 4)) == s_ref
+    py = port.new_plane(g)
+    py.reshape(-1, g.stride)[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]] = y
+    e = port.frame_mb_energy(g, py, u, v)
+    assert np.array_equal(e, ref.frame_mb_energy(g, py, u, v))
+    assert np.array_equal(port.frame_mb_hadamard_ac(g, py), ref.frame_mb_hadamard_ac(g, py))
+    for strength in (1.0, 0.6, 2.5):
+        q_ref, i_ref = ref.frame_aq(g, py, u, v, strength)
+        q_port, i_port = port.frame_aq(g, py, u, v, strength)
+        q_host, i_host = pkg.host_aq(e, strength)
+        assert np.array_equal(q_ref, q_port) and np.array_equal(i_ref, i_port)
+        assert np.array_equal(q_ref, q_host) and np.array_equal(i_ref, i_host)
+
+
+def test_aq_tables_all_energies(pkg, port, ref):
+    """every leading-zero count and every 7-bit mantissa of the log2 table, through x264_adaptive_quant_frame on crafted pictures
+    is impractical; instead sweep the host helper against the port over a dense set of energies (both rebuild the tables from
+    log2/exp2), and pin the port to the reference on real pictures above"""
+    e = np.unique(np.concatenate([np.arange(1, 70000, 7), (np.arange(128, 256)[:, None] << np.arange(0, 24)[None, :]).ravel(),
+                                  np.array([1, 2, 3, 0x7fffffff, 0xffffffff])]).astype(np.uint64)).astype(np.uint32)
+    for strength in (1.0, 3.0):
+        q, i = pkg.host_aq(e, strength)
+        q2, i2 = np.zeros(len(e), np.float32), np.zeros(len(e), np.uint16)
+        port.lib.xo_aq_from_energy(e.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint32)), len(e), __import__("ctypes").c_float(strength),
+                                   q2.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)), X._ptr(i2, X.u16p))
+        assert np.array_equal(q, q2) and np.array_equal(i, i2)

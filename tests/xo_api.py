@@ -119,6 +119,14 @@ class Oracle:
         L.xo_lowres_intra_cost.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.xo_me_search_subpel_chroma.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), u16p, C.POINTER(Chroma), C.POINTER(MeIn), C.c_int,
                                                  C.c_int, C.POINTER(MeOut)]
+        L.xo_frame_ssd.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+        L.xo_frame_ssd.restype = C.c_int64
+        L.xo_frame_ssim.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+        L.xo_frame_ssim.restype = C.c_float
+        L.xo_frame_ssim_sums.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, i32p]
+        L.xo_frame_mb_energy.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, C.c_int, C.POINTER(C.c_uint32)]
+        L.xo_frame_mb_hadamard_ac.argtypes = [C.POINTER(Geom), u8p, C.POINTER(C.c_uint64)]
+        L.xo_frame_aq.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, C.c_int, C.c_float, C.POINTER(C.c_float), u16p]
         L.xo_frame_deblock.argtypes = [C.POINTER(Geom), C.POINTER(DeblockIn), u8p, u8p, u8p, C.c_int]
         self.backend = L.xo_backend().decode()
 
@@ -198,6 +206,35 @@ class Oracle:
                                             _ptr(integral, u16p, g.origin) if integral is not None else None, C.byref(ch), C.byref(mi),
                                             subme, mbcmp_satd, C.byref(out))
         return out
+
+    # whole-frame metrics; a, b: 2-D uint8 arrays (row stride = shape[1])
+    def frame_ssd(self, a, b, width, height):
+        return int(self.lib.xo_frame_ssd(_ptr(a), a.shape[1], _ptr(b), b.shape[1], width, height))
+
+    def frame_ssim(self, a, b, width, height):
+        return float(self.lib.xo_frame_ssim(_ptr(a), a.shape[1], _ptr(b), b.shape[1], width, height))
+
+    def frame_ssim_sums(self, a, b, width, height):
+        sums = np.zeros((height // 4, width // 4, 4), np.int32)
+        self.lib.xo_frame_ssim_sums(_ptr(a), a.shape[1], _ptr(b), b.shape[1], width, height, _ptr(sums, i32p))
+        return sums
+
+    def frame_mb_energy(self, g, y, u, v):
+        """y: padded luma plane (flat); u, v: 2-D chroma"""
+        out = np.zeros(g.mb_width * g.mb_height, np.uint32)
+        self.lib.xo_frame_mb_energy(C.byref(g), _ptr(y, u8p, g.origin), _ptr(u), _ptr(v), u.shape[1], out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return out
+
+    def frame_mb_hadamard_ac(self, g, y):
+        out = np.zeros(g.mb_width * g.mb_height, np.uint64)
+        self.lib.xo_frame_mb_hadamard_ac(C.byref(g), _ptr(y, u8p, g.origin), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return out
+
+    def frame_aq(self, g, y, u, v, strength):
+        n = g.mb_width * g.mb_height
+        qp, inv = np.zeros(n, np.float32), np.zeros(n, np.uint16)
+        self.lib.xo_frame_aq(C.byref(g), _ptr(y, u8p, g.origin), _ptr(u), _ptr(v), u.shape[1], strength, qp.ctypes.data_as(C.POINTER(C.c_float)), _ptr(inv, u16p))
+        return qp, inv
 
     def frame_deblock(self, g, info, y, u, v):
         """y: padded luma plane (flat, pixel 0,0 at g.origin); u, v: 2-D chroma arrays (contiguous).  Filtered in place."""

@@ -109,6 +109,13 @@ def lib():
         L.x264_cuda_lowres_frame_cost.argtypes = [vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_frame_ssd.argtypes = [vp, vp, vp, ip, ip, ip, vp]
+        L.x264_cuda_frame_ssim_sums.argtypes = [vp, vp, vp, ip, ip, ip, vp]
+        L.x264_cuda_host_ssim_end.argtypes = [vp, ip, ip]
+        L.x264_cuda_host_ssim_end.restype = C.c_float
+        L.x264_cuda_frame_mb_energy.argtypes = [vp, vp, vp]
+        L.x264_cuda_host_aq.argtypes = [vp, ip, C.c_float, vp, vp]
+        L.x264_cuda_frame_mb_hadamard_ac.argtypes = [vp, vp, vp]
         L.x264_cuda_host_alloc.argtypes = [C.c_size_t]
         L.x264_cuda_host_alloc.restype = vp
         L.x264_cuda_host_free.argtypes = [vp]
@@ -120,6 +127,14 @@ def lib():
 
 class CudaError(RuntimeError):
     pass
+
+
+def host_aq(energy, aq_strength=1.0):
+    """x264_adaptive_quant_frame's float part -> (f_qp_offset, i_inv_qscale_factor)"""
+    e = np.ascontiguousarray(energy, np.uint32)
+    qp, inv = np.zeros(len(e), np.float32), np.zeros(len(e), np.uint16)
+    lib().x264_cuda_host_aq(e.ctypes.data, len(e), aq_strength, qp.ctypes.data, inv.ctypes.data)
+    return qp, inv
 
 
 def host_cost_mv(qp):
@@ -327,6 +342,27 @@ class Context:
                                                                ("ref0", np.int8), ("mv0", np.int16), ("ref1", np.int8), ("mv1", np.int16))}
         self.check(lib().x264_cuda_frame_deblock(self.h, fdec.h, pm.ctypes.data, *[arr[k].ctypes.data for k in
                                                  ("type", "qp", "transform8x8", "nnz", "ref0", "mv0", "ref1", "mv1")]))
+
+    def frame_ssd(self, a, b, plane, width, height):
+        out = np.zeros(1, np.int64)
+        self.check(lib().x264_cuda_frame_ssd(self.h, a.h, b.h, plane, width, height, out.ctypes.data))
+        return int(out[0])
+
+    def frame_ssim(self, a, b, plane, width, height):
+        """-> (x264_pixel_ssim_wxh value, sums[h4, w4, 4])"""
+        sums = np.zeros((height // 4, width // 4, 4), np.int32)
+        self.check(lib().x264_cuda_frame_ssim_sums(self.h, a.h, b.h, plane, width, height, sums.ctypes.data))
+        return float(lib().x264_cuda_host_ssim_end(sums.ctypes.data, width // 4, height // 4)), sums
+
+    def frame_mb_energy(self, f):
+        out = np.zeros(f.g.mb_width * f.g.mb_height, np.uint32)
+        self.check(lib().x264_cuda_frame_mb_energy(self.h, f.h, out.ctypes.data))
+        return out
+
+    def frame_mb_hadamard_ac(self, f):
+        out = np.zeros(f.g.mb_width * f.g.mb_height, np.uint64)
+        self.check(lib().x264_cuda_frame_mb_hadamard_ac(self.h, f.h, out.ctypes.data))
+        return out
 
     def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
         self.check(lib().x264_cuda_me_search_mb_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

@@ -81,3 +81,66 @@ void x264_cuda_host_cqm_tables(int cqm_preset, uint16_t q4mf[4][52][16], uint16_
             }
         }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Float tails of the frame metrics.  They run on the host with the reference's compiler flags because their results depend
+ * on float evaluation order; the device supplies the integer inputs (csrc/metrics.cu). */
+
+/* x264_pixel_ssim_wxh's accumulation (S/common/pixel.c:462-509) over the per-4x4 sums of x264_cuda_frame_ssim_sums: windows of
+ * 2x2 blocks, evaluated four at a time per row pair, each group summed on its own before it joins the total. */
+static float ssim_window(int s1, int s2, int ss, int s12)
+{
+    static const int c1 = (int)(.01 * .01 * 255 * 255 * 64 + .5);
+    static const int c2 = (int)(.03 * .03 * 255 * 255 * 64 * 63 + .5);
+    const int vars = ss * 64 - s1 * s1 - s2 * s2;
+    const int covar = s12 * 64 - s1 * s2;
+    return (float)(2 * s1 * s2 + c1) * (float)(2 * covar + c2) / ((float)(s1 * s1 + s2 * s2 + c1) * (float)(vars + c2));
+}
+float x264_cuda_host_ssim_end(const int (*sums)[4], int w4, int h4)
+{
+    float total = 0.0;
+    for (int y = 1; y < h4; y++) {
+        const int (*cur)[4] = sums + (size_t)y * w4, (*up)[4] = sums + (size_t)(y - 1) * w4;
+        for (int x = 0; x < w4 - 1; x += 4) {
+            const int n = w4 - x - 1 < 4 ? w4 - x - 1 : 4;
+            float group = 0.0;
+            for (int i = x; i < x + n; i++)
+                group += ssim_window(cur[i][0] + cur[i + 1][0] + up[i][0] + up[i + 1][0], cur[i][1] + cur[i + 1][1] + up[i][1] + up[i + 1][1],
+                                     cur[i][2] + cur[i + 1][2] + up[i][2] + up[i + 1][2], cur[i][3] + cur[i + 1][3] + up[i][3] + up[i + 1][3]);
+            total += group;
+        }
+    }
+    return total;
+}
+
+/* x264_adaptive_quant_frame (S/encoder/ratecontrol.c:233-249) from the macroblock energies of x264_cuda_frame_mb_energy:
+ * qp_offset[mb] = strength*1.0397*(log2(energy) - 14.427...) via the reference's 7-bit log2 table, inv_qscale[mb] = 2^(-qp/6)
+ * in .8 fixed point via its 6-bit exp2 table (x264_exp2fix8).  Both tables are five-decimal / integer roundings of the
+ * functions and are rebuilt here rather than transcribed. */
+static float aq_log2[128];
+static uint8_t aq_exp2[64];
+static void aq_init(void)
+{
+    if (aq_exp2[63]) return;
+    for (int i = 0; i < 128; i++) aq_log2[i] = (float)(floor(log2(1.0 + i / 128.0) * 1e5 + 0.5) / 1e5);
+    for (int i = 0; i < 64; i++) aq_exp2[i] = (uint8_t)floor((pow(2.0, (i + 0.5) / 64.0) - 1.0) * 256.0 + 0.5);
+}
+void x264_cuda_host_aq(const uint32_t *energy, int n_mb, float aq_strength, float *qp_offset, uint16_t *inv_qscale)
+{
+    aq_init();
+    const float strength = aq_strength * 1.0397;
+    for (int k = 0; k < n_mb; k++) {
+        const uint32_t e = energy[k];
+        const int lz = __builtin_clz(e);
+        const float adj = strength * (aq_log2[(e << lz >> 24) & 0x7f] - lz + 16.573f);
+        qp_offset[k] = adj;
+        if (inv_qscale) {
+            float x = adj * (-1.f / 6.f) + 8;
+            int v;
+            if (x <= 0) v = 0;
+            else if (x >= 16) v = 0xffff;
+            else { const int i = x; const int f = (x - i) * 64; v = (aq_exp2[f] + 256) << i >> 8; }
+            inv_qscale[k] = (uint16_t)v;
+        }
+    }
+}
