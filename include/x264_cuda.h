@@ -257,14 +257,15 @@ X264_CUDA_API int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_
 /* per-frame / per-macroblock measures without inter-macroblock dependencies.  The device computes the
  * integer parts; the float tails stay on the host (x264_cuda_host_*) because their results depend on float evaluation order.
  * plane: X264_CUDA_PLANE_FULL / _CB / _CR (or a half-pel plane id). */
-/* x264_pixel_ssd_wxh (S/common/pixel.c:98-136) over the top-left width x height pixels of one plane of two frames: PSNR input
- * (S/encoder/encoder.c:1034-1046) */
-X264_CUDA_API int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int width, int height,
-                                      int64_t *ssd);
-/* ssim_4x4x2_core (pixel.c:435-460) for every 4x4 block of the region: sums[(height/4)*(width/4)][4] = s1, s2, ss, s12;
- * x264_cuda_host_ssim_end then gives x264_pixel_ssim_wxh's value (pixel.c:462-509) */
-X264_CUDA_API int x264_cuda_frame_ssim_sums(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int width, int height,
-                                            int (*sums)[4]);
+/* x264_pixel_ssd_wxh (S/common/pixel.c:98-136) over the width x height pixels at (x0,y0) of one plane of two frames: PSNR input
+ * (S/encoder/encoder.c:1034-1046; the reference's per-row slabs add up to one whole-frame call) */
+X264_CUDA_API int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int x0, int y0, int width,
+                                      int height, int64_t *ssd);
+/* ssim_4x4x2_core (pixel.c:435-460) for every 4x4 block of the region at (x0,y0): sums[(height/4)*(width/4)][4] = s1, s2, ss, s12;
+ * x264_cuda_host_ssim_end then gives x264_pixel_ssim_wxh's value (pixel.c:462-509).  The encoder evaluates SSIM in row slabs
+ * starting at x0 = 2 (encoder.c:1047-1056): pass the same (2, min_y, i_width-2, max_y-min_y) per slab for the identical float. */
+X264_CUDA_API int x264_cuda_frame_ssim_sums(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int x0, int y0, int width,
+                                            int height, int (*sums)[4]);
 X264_CUDA_API float x264_cuda_host_ssim_end(const int (*sums)[4], int w4, int h4);
 /* ac_energy_mb (S/encoder/ratecontrol.c:171-191) of every macroblock (frame needs X264_CUDA_FRAME_CHROMA): energy[mb_width*mb_height];
  * x264_cuda_host_aq then is x264_adaptive_quant_frame (:233-249): f_qp_offset[mb] and (optional) i_inv_qscale_factor[mb] */

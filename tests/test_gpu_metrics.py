@@ -22,6 +22,12 @@ def test_frame_metrics(pkg, ctx, port, size):
             val, sums = ctx.frame_ssim(fa, fb, plane, ww, hh)
             assert np.array_equal(sums, port.frame_ssim_sums(a, b, ww, hh))
             assert val == port.frame_ssim(a, b, ww, hh)
+    if h >= 48:  # the encoder's SSIM slabs: x0 = 2, rows [min_y, max_y) (encoder.c:1047-1056)
+        for (y0, hh) in ((2, 22), (10, 32), (h - 30, 30)):
+            val, sums = ctx.frame_ssim(fa, fb, pkg.PLANE_FULL, w - 2, hh, x0=2, y0=y0)
+            a, b = np.ascontiguousarray(y[y0:, 2:]), np.ascontiguousarray(ry[y0:, 2:])
+            assert np.array_equal(sums, port.frame_ssim_sums(a, b, w - 2, hh)) and val == port.frame_ssim(a, b, w - 2, hh)
+            assert ctx.frame_ssd(fa, fb, pkg.PLANE_FULL, w - 2, hh, x0=2, y0=y0) == port.frame_ssd(a, b, w - 2, hh)
     py = port.new_plane(g)
     py.reshape(-1, g.stride)[X.PADV:X.PADV + y.shape[0], X.PADH:X.PADH + y.shape[1]] = y
     e = ctx.frame_mb_energy(fa)

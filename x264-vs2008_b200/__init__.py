@@ -109,8 +109,8 @@ def lib():
         L.x264_cuda_lowres_frame_cost.argtypes = [vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-        L.x264_cuda_frame_ssd.argtypes = [vp, vp, vp, ip, ip, ip, vp]
-        L.x264_cuda_frame_ssim_sums.argtypes = [vp, vp, vp, ip, ip, ip, vp]
+        L.x264_cuda_frame_ssd.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
+        L.x264_cuda_frame_ssim_sums.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
         L.x264_cuda_host_ssim_end.argtypes = [vp, ip, ip]
         L.x264_cuda_host_ssim_end.restype = C.c_float
         L.x264_cuda_frame_mb_energy.argtypes = [vp, vp, vp]
@@ -343,15 +343,15 @@ class Context:
         self.check(lib().x264_cuda_frame_deblock(self.h, fdec.h, pm.ctypes.data, *[arr[k].ctypes.data for k in
                                                  ("type", "qp", "transform8x8", "nnz", "ref0", "mv0", "ref1", "mv1")]))
 
-    def frame_ssd(self, a, b, plane, width, height):
+    def frame_ssd(self, a, b, plane, width, height, x0=0, y0=0):
         out = np.zeros(1, np.int64)
-        self.check(lib().x264_cuda_frame_ssd(self.h, a.h, b.h, plane, width, height, out.ctypes.data))
+        self.check(lib().x264_cuda_frame_ssd(self.h, a.h, b.h, plane, x0, y0, width, height, out.ctypes.data))
         return int(out[0])
 
-    def frame_ssim(self, a, b, plane, width, height):
+    def frame_ssim(self, a, b, plane, width, height, x0=0, y0=0):
         """-> (x264_pixel_ssim_wxh value, sums[h4, w4, 4])"""
         sums = np.zeros((height // 4, width // 4, 4), np.int32)
-        self.check(lib().x264_cuda_frame_ssim_sums(self.h, a.h, b.h, plane, width, height, sums.ctypes.data))
+        self.check(lib().x264_cuda_frame_ssim_sums(self.h, a.h, b.h, plane, x0, y0, width, height, sums.ctypes.data))
         return float(lib().x264_cuda_host_ssim_end(sums.ctypes.data, width // 4, height // 4)), sums
 
     def frame_mb_energy(self, f):

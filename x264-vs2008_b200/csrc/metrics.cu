@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) ssd_kernel(const uint8_t *__restrict__ p1
     unsigned long long total = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(i / wpr), x = (int)(i - (long long)y * wpr) * 4;
-        uint32_t a = *(const uint32_t *)(p1 + (size_t)y * s1 + x), b = *(const uint32_t *)(p2 + (size_t)y * s2 + x);
+        uint32_t a = ldg4(p1 + (size_t)y * s1 + x), b = ldg4(p2 + (size_t)y * s2 + x); // any alignment (regions may start at odd x)
         if (x + 4 > width) { const uint32_t m = 0xffffffffu >> (8 * (x + 4 - width)); a &= m; b &= m; }
         total += sq4(a, b, 0);
     }
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) ssim_sums_kernel(const uint8_t *__restric
     uint32_t a1 = 0, a2 = 0, ss = 0, s12 = 0;
 #pragma unroll
     for (int y = 0; y < 4; y++) {
-        const uint32_t a = __ldg((const uint32_t *)(p1 + (size_t)(4 * by + y) * s1 + 4 * bx)), b = __ldg((const uint32_t *)(p2 + (size_t)(4 * by + y) * s2 + 4 * bx));
+        const uint32_t a = ldg4(p1 + (size_t)(4 * by + y) * s1 + 4 * bx), b = ldg4(p2 + (size_t)(4 * by + y) * s2 + 4 * bx);
         a1 = __dp4a(a, 0x01010101u, a1); a2 = __dp4a(b, 0x01010101u, a2);
         ss = __dp4a(a, a, ss); ss = __dp4a(b, b, ss); s12 = __dp4a(a, b, s12);
     }
@@ -135,10 +135,12 @@ const uint8_t *plane00(const x264_cuda_frame_t *f, int plane, int *stride)
 
 } // namespace
 
-extern "C" int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int width, int height, int64_t *ssd)
+extern "C" int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int x0, int y0, int width,
+                                   int height, int64_t *ssd)
 {
     int s1 = 0, s2 = 0;
     const uint8_t *p1 = plane00(a, plane, &s1), *p2 = plane00(b, plane, &s2);
+    if (p1 && p2) { p1 += (ptrdiff_t)y0 * s1 + x0; p2 += (ptrdiff_t)y0 * s2 + x0; }
     if (!p1 || !p2 || width < 1 || height < 1) { snprintf(ctx->err, 256, "x264_cuda_frame_ssd: frames lack plane %d or empty region", plane); return -1; }
     if (x264_cuda_stage(ctx, 256, 256)) return -1;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_stage, 0, 8, ctx->stream));
@@ -168,11 +170,12 @@ extern "C" int x264_cuda_frame_mb_hadamard_ac(x264_cuda_t *ctx, const x264_cuda_
     return x264_cuda_results_out(ctx, out, ctx->d_stage, ctx->h_stage, (size_t)n * 8);
 }
 
-extern "C" int x264_cuda_frame_ssim_sums(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int width, int height,
-                                         int (*sums)[4])
+extern "C" int x264_cuda_frame_ssim_sums(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int x0, int y0, int width,
+                                         int height, int (*sums)[4])
 {
     int s1 = 0, s2 = 0;
     const uint8_t *p1 = plane00(a, plane, &s1), *p2 = plane00(b, plane, &s2);
+    if (p1 && p2) { p1 += (ptrdiff_t)y0 * s1 + x0; p2 += (ptrdiff_t)y0 * s2 + x0; }
     const int w4 = width >> 2, h4 = height >> 2;
     if (!p1 || !p2 || w4 < 1 || h4 < 1) { snprintf(ctx->err, 256, "x264_cuda_frame_ssim_sums: frames lack plane %d or region smaller than 4x4", plane); return -1; }
     const size_t bytes = (size_t)w4 * h4 * 16;
