@@ -56,6 +56,9 @@ struct x264_cuda_frame_t {
 };
 
 int x264_cuda_fail(x264_cuda_t *ctx, const char *what, cudaError_t e);
+// Every public entry point starts with this: the calling host thread may never have touched CUDA (the reference runs one
+// pthread per frame in flight, S/encoder/encoder.c:1569-1608) and would otherwise launch on device 0 with another device's stream.
+static inline void x264_cuda_enter(const x264_cuda_t *ctx) { if (ctx) cudaSetDevice(ctx->device); }
 int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes);
 // caller memory <-> device.  Page-locked caller memory (x264_cuda_host_alloc / x264_cuda_host_register) is DMA'd directly;
 // pageable memory goes through the pinned stage at `hs`.  results_out also waits for the stream (the call's completion point).

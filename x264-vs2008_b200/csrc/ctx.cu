@@ -50,6 +50,7 @@ extern "C" int x264_cuda_open(x264_cuda_t **pctx, int device)
 
 extern "C" void x264_cuda_close(x264_cuda_t *ctx)
 {
+    x264_cuda_enter(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -68,12 +69,14 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
 
 extern "C" int x264_cuda_set_stream(x264_cuda_t *ctx, void *s)
 {
+    x264_cuda_enter(ctx);
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return 0;
 }
 extern "C" void *x264_cuda_get_stream(x264_cuda_t *ctx) { return (void *)ctx->stream; }
 extern "C" int x264_cuda_synchronize(x264_cuda_t *ctx)
 {
+    x264_cuda_enter(ctx);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -144,6 +147,7 @@ static inline int align_up(int x, int a) { return (x + a - 1) & ~(a - 1); }
 
 extern "C" x264_cuda_frame_t *x264_cuda_frame_new(x264_cuda_t *ctx, int width, int height, int flags)
 {
+    x264_cuda_enter(ctx);
     if (width <= 0 || height <= 0) {
         snprintf(ctx->err, 256, "x264_cuda: invalid frame size %dx%d", width, height);
         return nullptr;
@@ -198,7 +202,7 @@ extern "C" x264_cuda_frame_t *x264_cuda_frame_new(x264_cuda_t *ctx, int width, i
 extern "C" void x264_cuda_frame_delete(x264_cuda_frame_t *f)
 {
     if (!f) return;
-    cudaSetDevice(f->ctx->device);
+    x264_cuda_enter(f->ctx);
     cudaStreamSynchronize(f->ctx->stream);
     cudaFree(f->buf);
     cudaFree(f->buf_lowres);
@@ -224,12 +228,14 @@ extern "C" void *x264_cuda_frame_plane(const x264_cuda_frame_t *f, int plane)
 extern "C" int x264_cuda_frame_upload(x264_cuda_t *ctx, x264_cuda_frame_t *f, const uint8_t *src, int src_stride,
                                       int cols, int rows)
 {
+    x264_cuda_enter(ctx);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, src, src_stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
 extern "C" int x264_cuda_frame_upload_chroma(x264_cuda_t *ctx, x264_cuda_frame_t *f, int plane, const uint8_t *src, int src_stride,
                                              int cols, int rows)
 {
+    x264_cuda_enter(ctx);
     if (!f->buf_chroma || (plane != X264_CUDA_PLANE_CB && plane != X264_CUDA_PLANE_CR)) {
         snprintf(ctx->err, 256, "x264_cuda_frame_upload_chroma: frame has no chroma plane %d", plane);
         return -1;
@@ -241,12 +247,14 @@ extern "C" int x264_cuda_frame_upload_chroma(x264_cuda_t *ctx, x264_cuda_frame_t
 extern "C" int x264_cuda_frame_upload_dev(x264_cuda_t *ctx, x264_cuda_frame_t *f, const void *dsrc, int src_stride,
                                           int cols, int rows)
 {
+    x264_cuda_enter(ctx);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, dsrc, src_stride, cols, rows, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 
 extern "C" int x264_cuda_frame_download(x264_cuda_t *ctx, const x264_cuda_frame_t *f, int plane, void *dst, int dst_stride)
 {
+    x264_cuda_enter(ctx);
     const x264_cuda_geom_t &g = f->g;
     const void *p00 = x264_cuda_frame_plane(f, plane);
     if (!p00) {
@@ -273,6 +281,7 @@ extern "C" int x264_cuda_frame_download(x264_cuda_t *ctx, const x264_cuda_frame_
 // ------------------------------------------------------------------ MV cost tables
 extern "C" int x264_cuda_set_cost_mv(x264_cuda_t *ctx, int qp, const int16_t *table)
 {
+    x264_cuda_enter(ctx);
     if (qp < 0 || qp > 51) { snprintf(ctx->err, 256, "x264_cuda: qp %d out of range", qp); return -1; }
     const size_t n = (4 * 4 * 2048 + 1) * sizeof(int16_t);
     if (!ctx->d_cost_mv[qp]) CUDA_TRY(ctx, cudaMalloc(&ctx->d_cost_mv[qp], n + 16));

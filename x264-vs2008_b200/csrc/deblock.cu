@@ -380,6 +380,7 @@ extern "C" int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_t *
                                            const int8_t *d_qp, const int8_t *d_transform8x8, const uint8_t *d_nnz, const int8_t *d_ref0,
                                            const int16_t *d_mv0, const int8_t *d_ref1, const int16_t *d_mv1)
 {
+    x264_cuda_enter(ctx);
     if (!fdec->buf_chroma) {
         snprintf(ctx->err, 256, "x264_cuda_frame_deblock: frame needs X264_CUDA_FRAME_CHROMA");
         return -1;
@@ -424,6 +425,7 @@ extern "C" int x264_cuda_frame_deblock(x264_cuda_t *ctx, x264_cuda_frame_t *fdec
                                        const int8_t *qp, const int8_t *transform8x8, const uint8_t (*nnz)[24], const int8_t *ref0,
                                        const int16_t (*mv0)[2], const int8_t *ref1, const int16_t (*mv1)[2])
 {
+    x264_cuda_enter(ctx);
     const size_t n = (size_t)fdec->g.mb_width * fdec->g.mb_height;
     const bool b = pm->b_slice_b && ref1 && mv1;
     // staging layout (256-byte aligned pieces): type, qp, t8, nnz, ref0, mv0, ref1, mv1

@@ -198,6 +198,7 @@ int launch_border(x264_cuda_t *ctx, uint8_t *const planes[], int n_planes, int s
 
 extern "C" int x264_cuda_frame_expand_border(x264_cuda_t *ctx, x264_cuda_frame_t *f)
 {
+    x264_cuda_enter(ctx);
     const x264_cuda_geom_t &g = f->g;
     uint8_t *planes[1] = { f->plane[0] };
     // mod16 padding and the 32-px borders are both replications of the picture edge (frame.c:304-331, :218-267)
@@ -212,6 +213,7 @@ extern "C" int x264_cuda_frame_expand_border(x264_cuda_t *ctx, x264_cuda_frame_t
 
 extern "C" int x264_cuda_frame_filter(x264_cuda_t *ctx, x264_cuda_frame_t *f)
 {
+    x264_cuda_enter(ctx);
     const x264_cuda_geom_t &g = f->g;
     const int w16 = g.mb_width * 16;
     if (!(g.flags & X264_CUDA_FRAME_HPEL)) {
@@ -250,6 +252,7 @@ extern "C" int x264_cuda_frame_filter(x264_cuda_t *ctx, x264_cuda_frame_t *f)
 
 extern "C" int x264_cuda_frame_init_lowres(x264_cuda_t *ctx, x264_cuda_frame_t *f)
 {
+    x264_cuda_enter(ctx);
     const x264_cuda_geom_t &g = f->g;
     if (!(g.flags & X264_CUDA_FRAME_LOWRES)) {
         snprintf(ctx->err, 256, "x264_cuda_frame_init_lowres: frame was created without X264_CUDA_FRAME_LOWRES");

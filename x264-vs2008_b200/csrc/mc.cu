@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) mc_blocks_kernel(McPlanes pl, const x264_
 
 extern "C" int x264_cuda_mc_blocks_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec, const void *d_jobs, int n_jobs)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     if (!(fref->g.flags & X264_CUDA_FRAME_HPEL) || fref->g.stride != fdec->g.stride) {
         snprintf(ctx->err, 256, "x264_cuda_mc_blocks: fref needs the half-pel planes and the same geometry as fdec");
@@ -64,6 +65,7 @@ extern "C" int x264_cuda_mc_blocks_dev(x264_cuda_t *ctx, const x264_cuda_frame_t
 extern "C" int x264_cuda_mc_blocks(x264_cuda_t *ctx, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec, const x264_cuda_mc_job_t *jobs,
                                    int n_jobs)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_mc_job_t);
     if (x264_cuda_stage(ctx, jb, jb)) return -1;

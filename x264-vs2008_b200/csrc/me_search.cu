@@ -268,6 +268,7 @@ me_search_kernel(Geo geo, const x264_cuda_me_job_t *__restrict__ jobs, int n_job
 extern "C" int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
                                        int me_range, const void *d_jobs, int n_jobs, void *d_results)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     if (fenc->g.stride != fref->g.stride || fenc->g.lines != fref->g.lines) {
         snprintf(ctx->err, 256, "x264_cuda_me_search: fenc/fref geometry mismatch");
@@ -291,6 +292,7 @@ extern "C" int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_frame_t
 extern "C" int x264_cuda_me_search(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
                                    int me_range, const x264_cuda_me_job_t *jobs, int n_jobs, x264_cuda_me_result_t *results)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_me_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_me_result_t);
     const size_t jb_al = (jb + 255) & ~(size_t)255;

@@ -337,6 +337,7 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
 extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
                                           int me_range, const void *d_jobs, int n_jobs, void *d_results)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     if (fenc->g.stride != fref->g.stride || fenc->g.lines != fref->g.lines) {
         snprintf(ctx->err, 256, "x264_cuda_me_search_mb: fenc/fref geometry mismatch");
@@ -363,6 +364,7 @@ extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_fram
 extern "C" int x264_cuda_me_search_mb(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int me_range,
                                       const x264_cuda_me_mb_job_t *jobs, int n_jobs, x264_cuda_me_mb_result_t *results)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_me_mb_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_me_mb_result_t);
     const size_t jb_al = (jb + 255) & ~(size_t)255;

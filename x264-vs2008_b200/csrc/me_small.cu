@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(128) block_cmp_kernel(int metric, int bw, int 
 extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int method,
                                              int me_range, int subme, const void *d_jobs, int n_jobs, void *d_results)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     if (fenc->g.stride != fref->g.stride || fenc->g.lines != fref->g.lines) {
         snprintf(ctx->err, 256, "x264_cuda_me_search_small: fenc/fref geometry mismatch");
@@ -594,6 +595,7 @@ extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_f
 extern "C" int x264_cuda_me_search_small(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int method,
                                          int me_range, int subme, const x264_cuda_me_job_t *jobs, int n_jobs, x264_cuda_me_final_t *results)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_me_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_me_final_t);
     const size_t jb_al = (jb + 255) & ~(size_t)255;
@@ -607,6 +609,7 @@ extern "C" int x264_cuda_me_search_small(x264_cuda_t *ctx, const x264_cuda_frame
 
 extern "C" int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel, int n, const uint8_t *pix1, const uint8_t *pix2, int *out)
 {
+    x264_cuda_enter(ctx);
     if (n <= 0) return 0;
     static const int bws[7] = { 16, 16, 8, 8, 8, 4, 4 }, bhs[7] = { 16, 8, 16, 8, 4, 8, 4 };
     if (metric < 0 || metric > 3 || i_pixel < 0 || i_pixel > 6 || (metric == 3 && i_pixel != 0 && i_pixel != 3)) {
@@ -879,6 +882,7 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
 
 extern "C" int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame_t *f, int n_dist)
 {
+    x264_cuda_enter(ctx);
     if (!(f->g.flags & X264_CUDA_FRAME_LOWRES) || n_dist < 1 || n_dist > 17) {
         snprintf(ctx->err, 256, "x264_cuda_frame_lookahead_alloc: frame needs X264_CUDA_FRAME_LOWRES and 1 <= n_dist <= 17");
         return -1;
@@ -910,6 +914,7 @@ static int la_check(x264_cuda_t *ctx, const x264_cuda_frame_t *f, int list, int 
 extern "C" int x264_cuda_frame_lookahead_get(x264_cuda_t *ctx, const x264_cuda_frame_t *f, int list, int dist, int16_t *mvs, int *costs,
                                              uint16_t *intra_cost)
 {
+    x264_cuda_enter(ctx);
     if (la_check(ctx, f, list, dist)) return -1;
     const size_t n_mb = (size_t)f->g.mb_width * f->g.mb_height, o = ((size_t)list * f->la_dist + dist) * n_mb;
     if (mvs) CUDA_TRY(ctx, cudaMemcpyAsync(mvs, f->la_mvs + 2 * o, n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -928,6 +933,7 @@ extern "C" int x264_cuda_frame_lookahead_get(x264_cuda_t *ctx, const x264_cuda_f
 extern "C" int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_frame_t *f, int list, int dist, const int16_t *mvs, const int *costs,
                                              const uint16_t *intra_cost)
 {
+    x264_cuda_enter(ctx);
     if (la_check(ctx, f, list, dist)) return -1;
     const size_t n_mb = (size_t)f->g.mb_width * f->g.mb_height, o = ((size_t)list * f->la_dist + dist) * n_mb;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -946,6 +952,7 @@ extern "C" int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_frame_t
 extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
                                            const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *pm, x264_cuda_lowres_result_t *result)
 {
+    x264_cuda_enter(ctx);
     const x264_cuda_geom_t &g = fenc->g;
     const int W = g.mb_width, H = g.mb_height, b_bidir = pm->b < pm->p1, any = !(pm->p0 == pm->p1 && pm->p0 == pm->b);
     if (!fenc->lowres[0] || !fref0->lowres[0] || !fref1->lowres[0] || fref0->g.stride_lowres != g.stride_lowres || fref1->g.stride_lowres != g.stride_lowres) {

@@ -138,6 +138,7 @@ const uint8_t *plane00(const x264_cuda_frame_t *f, int plane, int *stride)
 extern "C" int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int x0, int y0, int width,
                                    int height, int64_t *ssd)
 {
+    x264_cuda_enter(ctx);
     int s1 = 0, s2 = 0;
     const uint8_t *p1 = plane00(a, plane, &s1), *p2 = plane00(b, plane, &s2);
     if (p1 && p2) { p1 += (ptrdiff_t)y0 * s1 + x0; p2 += (ptrdiff_t)y0 * s2 + x0; }
@@ -153,6 +154,7 @@ extern "C" int x264_cuda_frame_ssd(x264_cuda_t *ctx, const x264_cuda_frame_t *a,
 
 extern "C" int x264_cuda_frame_mb_energy(x264_cuda_t *ctx, const x264_cuda_frame_t *f, uint32_t *energy)
 {
+    x264_cuda_enter(ctx);
     if (!f->buf_chroma) { snprintf(ctx->err, 256, "x264_cuda_frame_mb_energy: frame needs X264_CUDA_FRAME_CHROMA"); return -1; }
     const int n = f->g.mb_width * f->g.mb_height;
     if (x264_cuda_stage(ctx, (size_t)n * 4, (size_t)n * 4)) return -1;
@@ -163,6 +165,7 @@ extern "C" int x264_cuda_frame_mb_energy(x264_cuda_t *ctx, const x264_cuda_frame
 
 extern "C" int x264_cuda_frame_mb_hadamard_ac(x264_cuda_t *ctx, const x264_cuda_frame_t *f, uint64_t *out)
 {
+    x264_cuda_enter(ctx);
     const int n = f->g.mb_width * f->g.mb_height;
     if (x264_cuda_stage(ctx, (size_t)n * 8, (size_t)n * 8)) return -1;
     mb_hadamard_ac_kernel<<<(4 * n + 127) / 128, 128, 0, ctx->stream>>>(f->plane[0], f->g.stride, f->g.mb_width, n, (unsigned long long *)ctx->d_stage);
@@ -173,6 +176,7 @@ extern "C" int x264_cuda_frame_mb_hadamard_ac(x264_cuda_t *ctx, const x264_cuda_
 extern "C" int x264_cuda_frame_ssim_sums(x264_cuda_t *ctx, const x264_cuda_frame_t *a, const x264_cuda_frame_t *b, int plane, int x0, int y0, int width,
                                          int height, int (*sums)[4])
 {
+    x264_cuda_enter(ctx);
     int s1 = 0, s2 = 0;
     const uint8_t *p1 = plane00(a, plane, &s1), *p2 = plane00(b, plane, &s2);
     if (p1 && p2) { p1 += (ptrdiff_t)y0 * s1 + x0; p2 += (ptrdiff_t)y0 * s2 + x0; }

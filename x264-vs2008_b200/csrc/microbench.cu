@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) sad4_rate_kernel(uint32_t *out, int iters
 /* thread-level VABSDIFF4.ACC operations per second, whole GPU, at the clocks the GPU runs under this load */
 extern "C" int x264_cuda_measure_int_pipe(x264_cuda_t *ctx, double *sad4_per_sec)
 {
+    x264_cuda_enter(ctx);
     uint32_t *d = nullptr;
     CUDA_TRY(ctx, cudaMalloc(&d, 256));
     cudaEvent_t e0, e1;

@@ -379,6 +379,7 @@ extern "C" int x264_cuda_set_quant_tables(x264_cuda_t *ctx, const uint16_t *cons
                                           const int *const dq4[4], const uint16_t *const q8mf[2], const uint16_t *const q8bias[2],
                                           const int *const dq8[2])
 {
+    x264_cuda_enter(ctx);
     QuantTables *h = (QuantTables *)calloc(1, sizeof(QuantTables));
     for (int l = 0; l < 4; l++) {
         memcpy(h->q4mf[l], q4mf[l], sizeof(h->q4mf[l]));
@@ -403,6 +404,7 @@ extern "C" int x264_cuda_set_quant_tables(x264_cuda_t *ctx, const uint16_t *cons
 
 extern "C" int x264_cuda_set_quant_preset(x264_cuda_t *ctx, int cqm_preset)
 {
+    x264_cuda_enter(ctx);
     QuantTables *h = (QuantTables *)calloc(1, sizeof(QuantTables));
     x264_cuda_host_cqm_tables(cqm_preset, h->q4mf, h->q4bias, h->dq4, h->q8mf, h->q8bias, h->dq8);
     const uint16_t *a[4], *b[4], *e[2], *f[2];
@@ -426,6 +428,7 @@ static int need_tables(x264_cuda_t *ctx, bool want8)
 extern "C" int x264_cuda_block_residual(x264_cuda_t *ctx, int kind, int n, const uint8_t *fenc, const uint8_t *pred, const uint8_t *qp,
                                         const uint8_t *cat, int16_t *dct_out, int16_t *level_out, uint8_t *nz_out, uint8_t *recon_out)
 {
+    x264_cuda_enter(ctx);
     if (n <= 0) return 0;
     if (need_tables(ctx, kind == 1)) return -1;
     const size_t bs = kind ? 64 : 16;
@@ -456,6 +459,7 @@ extern "C" int x264_cuda_block_residual(x264_cuda_t *ctx, int kind, int n, const
 extern "C" int x264_cuda_block_dc(x264_cuda_t *ctx, int n, const int16_t *dc_in, const uint8_t *qp, const uint8_t *cat, int16_t *fwd_out,
                                   int16_t *level_out, uint8_t *nz_out, int16_t *deq_out)
 {
+    x264_cuda_enter(ctx);
     if (n <= 0) return 0;
     if (need_tables(ctx, false)) return -1;
     size_t off[8], sz[7] = { (size_t)n * 32, (size_t)n, (size_t)n, (size_t)n * 32, (size_t)n * 32, (size_t)n, (size_t)n * 32 };
@@ -480,6 +484,7 @@ extern "C" int x264_cuda_block_dc(x264_cuda_t *ctx, int n, const int16_t *dc_in,
 extern "C" int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec, const void *d_jobs,
                                             int n_jobs, void *d_coeffs)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     if (need_tables(ctx, true)) return -1;
     if (!fenc->buf_chroma || !fdec->buf_chroma || fenc->g.stride != fdec->g.stride) {
@@ -497,6 +502,7 @@ extern "C" int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_fr
 extern "C" int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
                                         const x264_cuda_resid_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_t *coeffs)
 {
+    x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
     const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_resid_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_mb_coeffs_t);
     const size_t jb_al = (jb + 255) & ~(size_t)255;
