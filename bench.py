@@ -337,7 +337,7 @@ def run_ours(args):
     def step_e2e(ln, i):
         p = i % RING_PAIRS
         c = ln["ctx"]
-        ln["fe"].upload(host_pics[2 * p + 1].numpy()); ln["fe"].expand_border()
+        ln["fe"].upload(host_pics[2 * p + 1].numpy()); ln["fe"].expand_border_mod16()  # all the reference does to fenc (encoder.c:1413-1416)
         ln["fr"].upload(host_pics[2 * p].numpy()); ln["fr"].expand_border()
         c.check(L.x264_cuda_me_search_mb(c.h, ln["fe"].h, ln["fr"].h, ME_RANGE, h_mbjobs.data_ptr(), n_mb, ln["res"].data_ptr()))
 

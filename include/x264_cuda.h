@@ -100,6 +100,9 @@ X264_CUDA_API int x264_cuda_frame_download(x264_cuda_t *ctx, const x264_cuda_fra
 
 /* ≡ x264_frame_expand_border_mod16 + x264_frame_expand_border, luma (S/common/frame.c:304-331, :240-267) */
 X264_CUDA_API int x264_cuda_frame_expand_border(x264_cuda_t *ctx, x264_cuda_frame_t *frame);
+/* x264_frame_expand_border_mod16 only (S/common/frame.c:304-331): replicate the last column / row up to a multiple of 16 — all the
+ * reference does to fenc (S/encoder/encoder.c:1413-1416); reference frames need the full x264_cuda_frame_expand_border */
+X264_CUDA_API int x264_cuda_frame_expand_border_mod16(x264_cuda_t *ctx, x264_cuda_frame_t *frame);
 /* ≡ x264_frame_filter(h, frame, 0, 1) + x264_frame_expand_border_filtered(h, frame, 0, 1): the three half-pel
  * planes and the integral image(s) of a whole (border-expanded) frame (S/common/mc.c:404-463,
  * S/common/frame.c:269-295).  Hook: x264_fdec_filter_row, S/encoder/encoder.c:1016-1023. */

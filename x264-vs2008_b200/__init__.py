@@ -90,7 +90,7 @@ def lib():
         L.x264_cuda_residual_inter.argtypes = [vp, vp, vp, vp, ip, vp]
         L.x264_cuda_residual_inter_dev.argtypes = [vp, vp, vp, vp, ip, vp]
         L.x264_cuda_frame_download.argtypes = [vp, vp, ip, vp, ip]
-        for n in ("x264_cuda_frame_expand_border", "x264_cuda_frame_filter", "x264_cuda_frame_init_lowres"):
+        for n in ("x264_cuda_frame_expand_border", "x264_cuda_frame_expand_border_mod16", "x264_cuda_frame_filter", "x264_cuda_frame_init_lowres"):
             if hasattr(L, n):
                 getattr(L, n).argtypes = [vp, vp]
         L.x264_cuda_set_cost_mv.argtypes = [vp, ip, vp]
@@ -178,6 +178,9 @@ class Frame:
 
     def expand_border(self):
         self.ctx.check(lib().x264_cuda_frame_expand_border(self.ctx.h, self.h))
+
+    def expand_border_mod16(self):
+        self.ctx.check(lib().x264_cuda_frame_expand_border_mod16(self.ctx.h, self.h))
 
     def filter(self):
         self.ctx.check(lib().x264_cuda_frame_filter(self.ctx.h, self.h))

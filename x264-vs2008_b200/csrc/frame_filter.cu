@@ -19,22 +19,32 @@ namespace {
 // inside the core [cx0,cx1] x [cy0,cy1], write core[clamp(y)][clamp(x)].  x coordinates are relative to the
 // plane's pixel (0,0); X0 is a multiple of 4.  `zero_from`: columns >= zero_from (and <= cx1) of core rows are
 // treated as never-written zeros (lowres planes of odd-mb-width frames, see x264_cuda_frame_init_lowres).
-struct BorderArgs { uint8_t *p[4]; int stride, cx0, cx1, cy0, cy1, X0, X1, Y0, Y1; };
+struct BorderArgs { uint8_t *p[4]; int stride, cx0, cx1, cy0, cy1, X0, X1, Y0, Y1, words, nl, wr0, side, band_items, items; };
 
+// Clamp-copy of everything outside [cx0,cx1] x [cy0,cy1] inside [X0,X1) x [Y0,Y1): one thread per BORDER word only.  Rows above
+// and below the valid area are whole rows of `words` words; rows inside it only have `side` words (nl on the left, the rest from
+// word wr0 on the right), so a 1080p plane is 49k threads instead of 571k.
 __global__ void __launch_bounds__(256) replicate_border_kernel(BorderArgs a)
 {
-    uint8_t *plane = a.p[blockIdx.z];
-    const int words = (a.X1 - a.X0) >> 2;
-    const int y = a.Y0 + blockIdx.y;
-    for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < words; wi += gridDim.x * blockDim.x) {
-        const int x = a.X0 + wi * 4;
-        if (y >= a.cy0 && y <= a.cy1 && x >= a.cx0 && x + 3 <= a.cx1) continue; // interior word
-        const uint8_t *row = plane + (ptrdiff_t)clip3i(y, a.cy0, a.cy1) * a.stride;
-        uint32_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) v |= (uint32_t)row[clip3i(x + k, a.cx0, a.cx1)] << (8 * k);
-        *(uint32_t *)(plane + (ptrdiff_t)y * a.stride + x) = v;
+    uint8_t *plane = a.p[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.items) return;
+    int y, wi;
+    if (i < a.band_items) {
+        const int r = i / a.words, top = a.cy0 - a.Y0;
+        wi = i - r * a.words;
+        y = r < top ? a.Y0 + r : a.cy1 + 1 + (r - top);
+    } else {
+        const int j = i - a.band_items, r = j / a.side, k = j - r * a.side;
+        y = a.cy0 + r;
+        wi = k < a.nl ? k : a.wr0 + (k - a.nl);
     }
+    const int x = a.X0 + wi * 4;
+    const uint8_t *row = plane + (ptrdiff_t)clip3i(y, a.cy0, a.cy1) * a.stride;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v |= (uint32_t)row[clip3i(x + k, a.cx0, a.cx1)] << (8 * k);
+    *(uint32_t *)(plane + (ptrdiff_t)y * a.stride + x) = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -187,8 +197,14 @@ int launch_border(x264_cuda_t *ctx, uint8_t *const planes[], int n_planes, int s
     BorderArgs a;
     for (int i = 0; i < 4; i++) a.p[i] = planes[i < n_planes ? i : 0];
     a.stride = stride; a.cx0 = cx0; a.cx1 = cx1; a.cy0 = cy0; a.cy1 = cy1; a.X0 = X0; a.X1 = X1; a.Y0 = Y0; a.Y1 = Y1;
-    const int words = (X1 - X0) >> 2;
-    dim3 grid((words + 255) / 256, Y1 - Y0, n_planes);
+    a.words = (X1 - X0) >> 2;
+    a.nl = (cx0 - X0 + 3) >> 2;                  // words holding a pixel left of the valid area
+    a.wr0 = max(a.nl, (cx1 + 1 - X0) >> 2);      // first word holding a pixel right of it
+    a.side = a.nl + (a.words - a.wr0);
+    a.band_items = ((cy0 - Y0) + (Y1 - 1 - cy1)) * a.words;
+    a.items = a.band_items + (cy1 - cy0 + 1) * a.side;
+    if (a.items <= 0) return 0;
+    dim3 grid((a.items + 255) / 256, n_planes);
     replicate_border_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     LAUNCH_CHECK(ctx, "replicate_border_kernel");
     return 0;
@@ -207,6 +223,20 @@ extern "C" int x264_cuda_frame_expand_border(x264_cuda_t *ctx, x264_cuda_frame_t
         uint8_t *cp[2] = { f->chroma[0], f->chroma[1] };
         return launch_border(ctx, cp, 2, f->stride_c, 0, g.width / 2 - 1, 0, g.height / 2 - 1, -PADH / 2, g.mb_width * 8 + PADH / 2, -PADV / 2,
                              g.lines / 2 + PADV / 2);
+    }
+    return 0;
+}
+
+// x264_frame_expand_border_mod16 (frame.c:304-331): what the reference does to fenc — only the padding up to a multiple of 16
+extern "C" int x264_cuda_frame_expand_border_mod16(x264_cuda_t *ctx, x264_cuda_frame_t *f)
+{
+    x264_cuda_enter(ctx);
+    const x264_cuda_geom_t &g = f->g;
+    uint8_t *planes[1] = { f->plane[0] };
+    if (launch_border(ctx, planes, 1, g.stride, 0, g.width - 1, 0, g.height - 1, 0, g.mb_width * 16, 0, g.lines)) return -1;
+    if (f->buf_chroma) {
+        uint8_t *cp[2] = { f->chroma[0], f->chroma[1] };
+        return launch_border(ctx, cp, 2, f->stride_c, 0, g.width / 2 - 1, 0, g.height / 2 - 1, 0, g.mb_width * 8, 0, g.lines / 2);
     }
     return 0;
 }

@@ -56,6 +56,13 @@ __device__ __forceinline__ unsigned part_quads(int p)
     return (unsigned)(0x8421a5c3full >> (4 * p)) & 15; // p0:1111 p1:0011 p2:1100 p3:0101 p4:1010 p5:0001 p6:0010 p7:0100 p8:1000
 }
 
+// pair k of the 16 existing (partition, quadrant) pairs: p0 owns q0..3; p1: q0,q1; p2: q2,q3; p3: q0,q2; p4: q1,q3; p5..8: q(p-5)
+__device__ __forceinline__ void pair_pq(int k, int &p, int &q)
+{
+    p = (int)((0x8765443322110000ull >> (4 * k)) & 15);
+    q = (int)((0xe4d8e4e4u >> (2 * k)) & 3);
+}
+
 // SAD of the 8x8 fenc quadrant q against the reference bytes at `a` (any alignment); fully unrolled, uniform work
 __device__ __forceinline__ int sad_quad(const uint32_t (*F)[4], int q, const uint8_t *a, int stride)
 {
@@ -229,19 +236,27 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
                 S.pc_x[idx] = cx; S.pc_y[idx] = valid ? cy : (1 << 20); // pc_y == 1<<20 marks "skip"
             }
             __syncwarp();
-            // (item, quadrant) tasks, two per trip so that their 48 row loads are in flight together
-            for (int t0 = lane; t0 < NP * NCAND * 4; t0 += 64) {
-                int v[2];
+            // (candidate, partition, quadrant) tasks: only the 16 (partition, quadrant) pairs that exist — 6 x 16 = 96 tasks,
+            // three per lane, each one uniform 8x8 SAD; quadrants a partition does not own stay 0 (S.quad is cleared first)
+            for (int i = lane; i < NP * NCAND * 4; i += 32) (&S.quad[0][0])[i] = 0;
+            __syncwarp();
+            int v[3];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int t = t0 + 32 * u, idx = min(t >> 2, NP * NCAND - 1), q = t & 3, p = idx / NCAND;
-                    v[u] = 0;
-                    if (t < NP * NCAND * 4 && S.pc_y[idx] != (1 << 20) && (part_quads(p) >> q & 1))
-                        v[u] = sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + S.pc_y[idx]) * stride + (q & 1) * 8 + S.pc_x[idx], stride);
-                }
+            for (int u = 0; u < 3; u++) {
+                const int t = lane + 32 * u, c = t >> 4;
+                int p, q;
+                pair_pq(t & 15, p, q);
+                const int idx = p * NCAND + c;
+                v[u] = 0;
+                if (S.pc_y[idx] != (1 << 20))
+                    v[u] = sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + S.pc_y[idx]) * stride + (q & 1) * 8 + S.pc_x[idx], stride);
+            }
 #pragma unroll
-                for (int u = 0; u < 2; u++)
-                    if (t0 + 32 * u < NP * NCAND * 4) S.quad[(t0 + 32 * u) >> 2][(t0 + 32 * u) & 3] = v[u];
+            for (int u = 0; u < 3; u++) {
+                const int t = lane + 32 * u, c = t >> 4;
+                int p, q;
+                pair_pq(t & 15, p, q);
+                S.quad[p * NCAND + c][q] = v[u];
             }
             __syncwarp();
             if (lane < NP) {
