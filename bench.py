@@ -129,6 +129,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the headline kernel from the committed `ncu --set full` capture (profiles/), or None"""
+    try:
+        tot, seen = 0.0, 0
+        for line in open(os.path.join(ROOT, "profiles", "r1_ncu_me_search_mb.txt")):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+                seen += 1
+        return tot if seen == 2 else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -417,7 +431,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                         "traffic": None, "kernel": "me_search_mb_kernel", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "traffic": ncu_traffic(), "algorithmic_bytes": alg_bytes, "kernel": "me_search_mb_kernel", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                          "note": "this kernel is integer-ALU-pipe bound by design (64 4-byte SADs per 16x16 candidate, ~1 B of HBM traffic per 10k ops); see int_pipe"},
             "int_pipe": {"bound": "int_pipe", "op": "VABSDIFF4.U8.ACC (4-byte SAD-accumulate)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tsad4/s", "frac": int_ach / int_peak, "peak_source": "x264_cuda_measure_int_pipe, measured in this run"},
