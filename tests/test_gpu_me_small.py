@@ -157,3 +157,31 @@ def test_chroma_me(pkg, ctx, port, method, subme):
     assert not bad, (len(bad), bad[:4])
     assert n_differs > 100
     fenc.close(); fref.close()
+
+
+def test_tesa_many(pkg, ctx, port):
+    """4000 TESA searches on a 720p pair (frame-edge macroblocks, clipped windows, all partition sizes): guards the keeper-list /
+    threshold logic at scale (a 1-in-400 miscompile of this path was found and fixed in round 1)"""
+    from x264_vs2008_b200 import synth
+    w, h = 1280, 720
+    clip = synth.Clip(w, h, seed=88)
+    g = port.geometry(w, h)
+    fenc = ctx.frame(w, h, 0)
+    fref = ctx.frame(w, h, pkg.FRAME_HPEL | pkg.FRAME_INTEGRAL | pkg.FRAME_INTEGRAL4)
+    fenc.upload(clip.luma(1)); fenc.expand_border()
+    fref.upload(clip.luma(0)); fref.expand_border(); fref.filter()
+    pe, pr = port.plane_from_picture(g, clip.luma(1)), port.plane_from_picture(g, clip.luma(0))
+    fh, fv, fc, integ = port.frame_filter(g, pr, 1)
+    jobs, mis = make_me_jobs(pkg, g, seed=4242, n=4000, me_range=16, qp=(12, 26, 38), pixels=(0, 1, 2, 3, 4, 5, 6), tesa=True, fpel_satd=True)
+    _fill_spel(jobs, mis)
+    jobs["flags"] = pkg.ME_FPEL_SATD | pkg.ME_MBCMP_SATD
+    res = ctx.me_search_small(fenc, fref, pkg.ME_METHOD_TESA, 16, 7, jobs)
+    bad = []
+    for i, mi in enumerate(mis):
+        mi.b_sub8x8 = 1
+        o = port.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, 7, 1)
+        got = (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"]), int(res[i]["bmx"]), int(res[i]["bmy"]))
+        if got != (o.mv[0], o.mv[1], o.cost, o.cost_mv, o.bmx, o.bmy):
+            bad.append((i, mi.i_pixel, got, (o.mv[0], o.mv[1], o.cost, o.cost_mv, o.bmx, o.bmy)))
+    assert not bad, (len(bad), bad[:4])
+    fenc.close(); fref.close()
