@@ -5,8 +5,8 @@
 // edges were filtered, and its top edge reads rows the upper-right neighbour's left edge has already touched.  Exactness
 // therefore needs the reference's macroblock order, which leaves the classic 2:1 wavefront: (x,y) may run once (x-1,y)
 // and (x+1,y-1) are done.  ONE WARP PER MACROBLOCK ROW sweeps left to right; the left dependency never leaves the warp
-// (the previous macroblock's right columns stay in shared memory), the upper dependency is a per-row progress counter in
-// global memory.  Lanes 0-15 own the 16 luma lines across the current edge, lanes 16-31 the 8+8 chroma lines.
+// (the previous macroblock's right columns stay in shared memory), the upper dependency travels through distributed shared
+// memory inside a thread-block cluster of eight rows and through a global progress counter between clusters.  Lanes 0-15 own the 16 luma lines across the current edge, lanes 16-31 the 8+8 chroma lines.
 // Everything that does not depend on pixels — bS of all 8 edges of every macroblock, alpha/beta/tc0 lookups — is done
 // beforehand by a fully parallel kernel (one thread per macroblock edge) so that the dependent chain only filters.
 //
@@ -154,224 +154,302 @@ __global__ void __launch_bounds__(256) deblock_prep_kernel(DeblockArgs a, EdgeRe
     *(uint4 *)&recs[t] = *(const uint4 *)&r;
 }
 
-struct RowSmem {
-    __align__(16) uint8_t L[20][LT_STRIDE];
-    __align__(16) uint8_t C[2][10][CT_STRIDE];
-    __align__(16) EdgeRec rec[8];
-};
 
 __device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// One line across a luma edge held in two packed words: P = p3,p2,p1,p0 (byte 0..3), Q = q0,q1,q2,q3.
-// strong = the bS 4 filter of intra macroblock edges (frame.c:507-552), else the bS < 4 filter (frame.c:424-467).
-__device__ __forceinline__ void filter_luma_w(uint32_t &P, uint32_t &Q, int alpha, int beta, bool strong, int tc0)
+// One line across an edge held in two packed words: P = p3,p2,p1,p0 (byte 0..3), Q = q0,q1,q2,q3.  Branch-free, and the SAME
+// instruction stream serves luma and chroma lanes (a warp that branches on lane type runs both paths one after the other):
+//   bS < 4 (frame.c:424-467, :470-497): chroma is the luma filter without the p1/q1 taps and with tc given directly;
+//   bS 4   (frame.c:507-552, :562-580): chroma is the luma filter's "large step" branch.
+// `strong` is warp-uniform (a property of the edge).  `on` = this lane filters; `luma` = lane holds a luma line.
+__device__ __forceinline__ void filter_w(uint32_t &P, uint32_t &Q, int alpha, int beta, bool strong, int tc0, bool luma, bool on)
 {
     const int p3 = P & 255, p2 = (P >> 8) & 255, p1 = (P >> 16) & 255, p0 = P >> 24;
     const int q0 = Q & 255, q1 = (Q >> 8) & 255, q2 = (Q >> 16) & 255, q3 = Q >> 24;
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    int n2 = p2, n1 = p1, n0 = p0, m0 = q0, m1 = q1, m2 = q2;
+    const bool ok = on && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
+    const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
+    int n2 = p2, n1 = p1, n0, m0, m1 = q1, m2 = q2;
     if (!strong) {
-        int tc = tc0;
+        const int tc = tc0 + (luma ? (int)ap + (int)aq : 0);
         const int avg = (p0 + q0 + 1) >> 1;
-        if (abs(p2 - p0) < beta) { n1 = p1 + clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0); tc++; }
-        if (abs(q2 - q0) < beta) { m1 = q1 + clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0); tc++; }
-        const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-        n0 = clip_u8(p0 + delta);
-        m0 = clip_u8(q0 - delta);
-    } else if (abs(p0 - q0) < ((alpha >> 2) + 2)) {
-        if (abs(p2 - p0) < beta) {
-            n0 = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
-            n1 = (p2 + p1 + p0 + q0 + 2) >> 2;
-            n2 = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
-        } else
-            n0 = (2 * p1 + p0 + q1 + 2) >> 2;
-        if (abs(q2 - q0) < beta) {
-            m0 = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
-            m1 = (p0 + q0 + q1 + q2 + 2) >> 2;
-            m2 = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
-        } else
-            m0 = (2 * q1 + q0 + p1 + 2) >> 2;
-    } else {
-        n0 = (2 * p1 + p0 + q1 + 2) >> 2;
-        m0 = (2 * q1 + q0 + p1 + 2) >> 2;
-    }
-    P = (uint32_t)p3 | (uint32_t)n2 << 8 | (uint32_t)n1 << 16 | (uint32_t)n0 << 24;
-    Q = (uint32_t)m0 | (uint32_t)m1 << 8 | (uint32_t)m2 << 16 | (uint32_t)q3 << 24;
-}
-// chroma (frame.c:470-497, :562-580): P = x,x,p1,p0; Q = q0,q1,x,x
-__device__ __forceinline__ void filter_chroma_w(uint32_t &P, uint32_t &Q, int alpha, int beta, bool strong, int tc)
-{
-    const int p1 = (P >> 16) & 255, p0 = P >> 24, q0 = Q & 255, q1 = (Q >> 8) & 255;
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    int n0, m0;
-    if (!strong) {
+        const int d1 = clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0), e1 = clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0);
+        if (ap) n1 = p1 + d1;
+        if (aq) m1 = q1 + e1;
         const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
         n0 = clip_u8(p0 + delta);
         m0 = clip_u8(q0 - delta);
     } else {
-        n0 = (2 * p1 + p0 + q1 + 2) >> 2;
-        m0 = (2 * q1 + q0 + p1 + 2) >> 2;
+        const bool small = luma && abs(p0 - q0) < ((alpha >> 2) + 2);
+        const bool sp = small && ap, sq = small && aq;
+        n0 = sp ? (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3 : (2 * p1 + p0 + q1 + 2) >> 2;
+        m0 = sq ? (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3 : (2 * q1 + q0 + p1 + 2) >> 2;
+        if (sp) { n1 = (p2 + p1 + p0 + q0 + 2) >> 2; n2 = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3; }
+        if (sq) { m1 = (p0 + q0 + q1 + q2 + 2) >> 2; m2 = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3; }
     }
-    P = (P & 0x00ffffffu) | (uint32_t)n0 << 24;
-    Q = (Q & 0xffffff00u) | (uint32_t)m0;
+    if (ok) {
+        P = (uint32_t)p3 | (uint32_t)n2 << 8 | (uint32_t)n1 << 16 | (uint32_t)n0 << 24;
+        Q = (uint32_t)m0 | (uint32_t)m1 << 8 | (uint32_t)m2 << 16 | (uint32_t)q3 << 24;
+    }
 }
 
-// the four (luma) / two (chroma) edges of one direction on the line this lane holds in registers
+// the four (luma) / two (chroma) edges of one direction on the line this lane holds in registers.  Luma lines are w[0..4]
+// (edge e between w[e] and w[e+1]); chroma lines are w[0..2] (edge 0 between w[0], w[1]; edge 2 between w[1], w[2]).
 __device__ __forceinline__ void filter_line(uint32_t (&w)[5], const EdgeRec *rec, int dir, int lane)
 {
-    if (lane < 16) {
+    const bool luma = lane < 16;
+    const int grp = luma ? lane >> 2 : (lane & 7) >> 1;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const EdgeRec &r = rec[dir * 4 + e];
-            if (!r.mode) continue; // warp-uniform
-            const int tc0 = r.mode == 2 ? 0 : r.tc[lane >> 2];
-            if (tc0 != 0xff) filter_luma_w(w[e], w[e + 1], r.alpha, r.beta, r.mode == 2, tc0);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-            const EdgeRec &r = rec[dir * 4 + e];
-            if (!r.mode) continue;
-            const int tc = r.mode == 2 ? 1 : r.tc_c[(lane & 7) >> 1];
-            if (tc) filter_chroma_w(w[e >> 1], w[(e >> 1) + 1], r.alpha_c, r.beta_c, r.mode == 2, tc);
-        }
+    for (int e = 0; e < 4; e++) {
+        const EdgeRec &r = rec[dir * 4 + e];
+        if (!r.mode) continue; // warp-uniform
+        const bool strong = r.mode == 2;
+        const int alpha = luma ? r.alpha : r.alpha_c, beta = luma ? r.beta : r.beta_c;
+        const int tc0 = luma ? r.tc[grp] : r.tc_c[grp];
+        // luma: tc0 0xff marks bS 0; chroma: tc 0 marks bS 0 and only even edges exist
+        const bool on = strong ? (luma || !(e & 1)) : luma ? tc0 != 0xff : (tc0 != 0 && !(e & 1));
+        if (e == 2) { // chroma's second edge sits one word earlier than luma's third
+            uint32_t P = luma ? w[2] : w[1], Q = luma ? w[3] : w[2];
+            filter_w(P, Q, alpha, beta, strong, tc0, luma, on);
+            if (luma) { w[2] = P; w[3] = Q; } else { w[1] = P; w[2] = Q; }
+        } else
+            filter_w(w[e], w[e + 1], alpha, beta, strong, tc0, luma, on);
     }
 }
 
-__global__ void __launch_bounds__(32) deblock_rows_kernel(DeblockArgs a, const EdgeRec *__restrict__ recs)
+// ---- the wavefront: eight consecutive macroblock rows form a thread-block cluster.  Inside a cluster a row PUSHES the
+// final bottom rows of each finished macroblock into the next row's shared memory (DSMEM stores, ~200 cycles) and bumps a
+// counter there; only the first row of a cluster reads the previous cluster's rows and progress through global memory
+// (a global-memory flag handoff costs ~900 cycles relaxed / ~1500 with release-acquire one way on B200, measured), and only
+// the last row of a cluster publishes one.  This row's own pixels and edge records never depend on other rows: they are
+// always one macroblock ahead, in registers.
+#define DB_CLUSTER 8
+#define DB_RING 8          // macroblocks of top rows buffered per row
+struct __align__(16) TopSlot { uint8_t y[4][16]; uint8_t c[2][2][8]; }; // luma rows 12..15, chroma rows 6,7 of U and V: 96 bytes
+
+struct ClusterSmem {
+    __align__(16) uint8_t L[20][LT_STRIDE];
+    __align__(16) uint8_t C[2][10][CT_STRIDE];
+    __align__(16) EdgeRec rec[8];
+    __align__(16) TopSlot ring[DB_RING];   // written by the row above (remote), read here
+    __align__(16) TopSlot prev;            // bottom rows of this row's previous macroblock, pushed once its right columns are final
+    int top_avail;                         // macroblocks delivered into `ring` (written remotely, release)
+    int credit;                            // macroblocks the row below has taken out of ITS ring (written remotely, release)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, uint32_t rank)
 {
-    __shared__ RowSmem S;
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint2 v)
+{
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cluster_release(uint32_t addr, int v)
+{
+    asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_cluster_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(DB_CLUSTER, 1, 1) __launch_bounds__(32) deblock_rows_cluster_kernel(DeblockArgs a, const EdgeRec *__restrict__ recs)
+{
+    __shared__ ClusterSmem S;
     const int lane = threadIdx.x, mb_y = blockIdx.x;
-    uint8_t *rowy = a.y + (size_t)16 * mb_y * a.stride, *rowu = a.u + (size_t)8 * mb_y * a.stride_c, *rowv = a.v + (size_t)8 * mb_y * a.stride_c;
-    const uint4 *rrow = (const uint4 *)(recs + (size_t)mb_y * a.W * 8);
-    const int *above = a.progress + mb_y - 1;
-    // chroma lanes: plane and line inside the plane
-    const int cpl = (lane >> 3) & 1, cln = lane & 7;
-    // this row's own pixels and edge records never depend on the row above: always one macroblock ahead, in registers
-    uint4 ly = make_uint4(0, 0, 0, 0), rc = make_uint4(0, 0, 0, 0), tl = make_uint4(0, 0, 0, 0);
-    uint2 lc = make_uint2(0, 0), tc2 = make_uint2(0, 0);
-    if (lane < 16) {
-        ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride));
-        lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c));
-    }
-    if (lane < 8) rc = __ldg(rrow + lane);
-    // the rows above (4 luma, 2+2 chroma) depend on the upper row's progress.  `seen` caches the last value read; when it
-    // already covers the NEXT macroblock its top rows are fetched a whole step early (have_top), so a row that trails the
-    // one above by a few macroblocks never waits for memory.
-    int seen = 0;
-    bool have_top = false;
-    for (int mb_x = 0; mb_x < a.W; mb_x++) {
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (lane == 0) { S.top_avail = 0; S.credit = 0; }
+    // every CTA of the cluster has initialised its counters before anyone pushes into them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (mb_y < a.H) {
+        const bool top_local = mb_y > 0 && rank > 0;                       // top rows arrive through DSMEM
+        const bool top_global = mb_y > 0 && rank == 0;                     // ... or through global memory (previous cluster)
+        const bool push_down = mb_y + 1 < a.H && rank + 1 < DB_CLUSTER;    // the row below is in this cluster
+        const bool publish = mb_y + 1 < a.H && rank + 1 == DB_CLUSTER;     // the row below is the next cluster's first
+        const uint32_t down_ring = map_rank(smem_u32(&S.ring[0]), rank + (push_down ? 1 : 0));
+        const uint32_t down_avail = map_rank(smem_u32(&S.top_avail), rank + (push_down ? 1 : 0));
+        const uint32_t up_credit = map_rank(smem_u32(&S.credit), rank - (top_local ? 1 : 0));
+        uint8_t *rowy = a.y + (size_t)16 * mb_y * a.stride, *rowu = a.u + (size_t)8 * mb_y * a.stride_c, *rowv = a.v + (size_t)8 * mb_y * a.stride_c;
+        const uint4 *rrow = (const uint4 *)(recs + (size_t)mb_y * a.W * 8);
+        const int *above = a.progress + mb_y - 1;
+        const int cpl = (lane >> 3) & 1, cln = lane & 7;
+        uint4 ly = make_uint4(0, 0, 0, 0), rc = make_uint4(0, 0, 0, 0), tl = make_uint4(0, 0, 0, 0);
+        uint2 lc = make_uint2(0, 0), tc2 = make_uint2(0, 0);
         if (lane < 16) {
-            *(uint4 *)&S.L[4 + lane][16] = ly;
-            *(uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8] = lc;
+            ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride));
+            lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c));
         }
-        if (lane < 8) *(uint4 *)&S.rec[lane] = rc;
-        if (mb_x + 1 < a.W) {
+        if (lane < 8) rc = __ldg(rrow + lane);
+        int seen = 0, avail = 0, credit = 0;
+        bool have_top = false;
+        for (int mb_x = 0; mb_x < a.W; mb_x++) {
             if (lane < 16) {
-                ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride + 16 * (mb_x + 1)));
-                lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * (mb_x + 1)));
+                *(uint4 *)&S.L[4 + lane][16] = ly;
+                *(uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8] = lc;
             }
-            if (lane < 8) rc = __ldg(rrow + (size_t)(mb_x + 1) * 8 + lane);
-        }
-        int flag_probe = -1; // a non-blocking read of the upper row's progress, consumed at the end of the step
-        if (mb_y > 0) {
-            if (!have_top) {
-                const int need = min(mb_x + 2, a.W);
-                while (seen < need) seen = ld_acquire(above); // every lane reads the same word: one request
-                if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * mb_x));
-                else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * mb_x));
-            }
-            if (lane < 4) *(uint4 *)&S.L[lane][16] = tl;
-            else if (lane < 8) *(uint2 *)&S.C[(lane - 4) >> 1][(lane - 4) & 1][8] = tc2;
-            have_top = false;
+            if (lane < 8) *(uint4 *)&S.rec[lane] = rc;
             if (mb_x + 1 < a.W) {
+                if (lane < 16) {
+                    ly = __ldcg((const uint4 *)(rowy + (size_t)lane * a.stride + 16 * (mb_x + 1)));
+                    lc = __ldcg((const uint2 *)((lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * (mb_x + 1)));
+                }
+                if (lane < 8) rc = __ldg(rrow + (size_t)(mb_x + 1) * 8 + lane);
+            }
+            int flag_probe = -1;
+            if (top_local) { // the row above delivered (or will deliver) this macroblock's top rows into the ring
+                while (avail <= mb_x) avail = ld_cluster_acquire(&S.top_avail);
+                const TopSlot &t = S.ring[mb_x % DB_RING];
+                if (lane < 4) *(uint4 *)&S.L[lane][16] = *(const uint4 *)t.y[lane];
+                else if (lane < 8) *(uint2 *)&S.C[(lane - 4) >> 1][(lane - 4) & 1][8] = *(const uint2 *)t.c[(lane - 4) >> 1][(lane - 4) & 1];
+            } else if (top_global) {
+                if (!have_top) {
+                    const int need = min(mb_x + 2, a.W);
+                    while (seen < need) seen = ld_acquire(above);
+                    if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * mb_x));
+                    else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * mb_x));
+                }
+                if (lane < 4) *(uint4 *)&S.L[lane][16] = tl;
+                else if (lane < 8) *(uint2 *)&S.C[(lane - 4) >> 1][(lane - 4) & 1][8] = tc2;
+                have_top = false;
+                if (mb_x + 1 < a.W) {
+                    if (seen >= min(mb_x + 3, a.W)) {
+                        if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * (mb_x + 1)));
+                        else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * (mb_x + 1)));
+                        have_top = true;
+                    } else
+                        flag_probe = ld_acquire(above);
+                }
+            }
+            __syncwarp();
+
+            // ---- vertical edges: the lane's line (luma row / chroma row) lives in registers across all of them; then horizontal
+            // edges on the lane's column, gathered from the tile
+            uint32_t w[5];
+            if (lane < 16) {
+                w[0] = *(const uint32_t *)&S.L[4 + lane][12];
+                const uint4 v = *(const uint4 *)&S.L[4 + lane][16];
+                w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w;
+            } else {
+                w[0] = *(const uint32_t *)&S.C[cpl][2 + cln][4];
+                const uint2 v = *(const uint2 *)&S.C[cpl][2 + cln][8];
+                w[1] = v.x; w[2] = v.y; w[3] = w[4] = 0;
+            }
+            filter_line(w, S.rec, 0, lane);
+            if (lane < 16) {
+                *(uint32_t *)&S.L[4 + lane][12] = w[0];
+                *(uint4 *)&S.L[4 + lane][16] = make_uint4(w[1], w[2], w[3], w[4]);
+            } else {
+                *(uint32_t *)&S.C[cpl][2 + cln][4] = w[0];
+                *(uint2 *)&S.C[cpl][2 + cln][8] = make_uint2(w[1], w[2]);
+            }
+            __syncwarp();
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 5; k++)
+                    w[k] = (uint32_t)S.L[4 * k][16 + lane] | (uint32_t)S.L[4 * k + 1][16 + lane] << 8 | (uint32_t)S.L[4 * k + 2][16 + lane] << 16 |
+                           (uint32_t)S.L[4 * k + 3][16 + lane] << 24;
+            } else {
+                w[0] = (uint32_t)S.C[cpl][0][8 + cln] << 16 | (uint32_t)S.C[cpl][1][8 + cln] << 24;
+#pragma unroll
+                for (int k = 1; k < 3; k++)
+                    w[k] = (uint32_t)S.C[cpl][4 * k - 2][8 + cln] | (uint32_t)S.C[cpl][4 * k - 1][8 + cln] << 8 | (uint32_t)S.C[cpl][4 * k][8 + cln] << 16 |
+                           (uint32_t)S.C[cpl][4 * k + 1][8 + cln] << 24;
+            }
+            filter_line(w, S.rec, 1, lane);
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 5; k++)
+#pragma unroll
+                    for (int b = (k == 0 ? 1 : 0); b < (k == 4 ? 3 : 4); b++) S.L[4 * k + b][16 + lane] = (uint8_t)(w[k] >> (8 * b));
+            } else {
+                S.C[cpl][1][8 + cln] = (uint8_t)(w[0] >> 24);
+#pragma unroll
+                for (int k = 1; k < 3; k++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) S.C[cpl][4 * k - 2 + b][8 + cln] = (uint8_t)(w[k] >> (8 * b));
+            }
+            __syncwarp();
+
+            // Release stores wait for every earlier store of the thread to be acknowledged; this step's global write-back is
+            // therefore issued AFTER them (measured: a release right behind the write-back costs ~1 us per step), and the
+            // previous step's write-back has had the whole filter time to drain.
+            if (top_local && lane == 0) st_cluster_release(up_credit, mb_x + 1); // the ring slot may be reused
+            // ---- hand the now-final bottom rows of the PREVIOUS macroblock (its right columns were just filtered) to the row
+            // below, and at the end of the row this macroblock's too
+            if (push_down) {
+                const bool last = mb_x + 1 == a.W;
+                if (mb_x > 0 || last) {
+                    const int n_push = (mb_x > 0) + last, first = mb_x > 0 ? mb_x - 1 : mb_x;
+                    while (credit < first + n_push - DB_RING) credit = ld_cluster_acquire(&S.credit); // ring full: wait for the row below
+                    if (mb_x > 0) { // S.prev holds MB x-1's rows 12..15 / chroma rows 6,7 with stale right columns: patch them from the tile
+                        if (lane < 4) *(uint32_t *)&S.prev.y[lane][12] = *(const uint32_t *)&S.L[16 + lane][12];
+                        else if (lane < 8) *(uint16_t *)&S.prev.c[(lane - 4) >> 1][(lane - 4) & 1][6] = *(const uint16_t *)&S.C[(lane - 4) >> 1][8 + ((lane - 4) & 1)][6];
+                        __syncwarp();
+                        const uint32_t slot = down_ring + (uint32_t)((mb_x - 1) % DB_RING) * (uint32_t)sizeof(TopSlot);
+                        if (lane < 4) st_cluster_v4(slot + 16 * lane, *(const uint4 *)S.prev.y[lane]);
+                        else if (lane < 8) st_cluster_v2(slot + 64 + 8 * (lane - 4), *(const uint2 *)S.prev.c[(lane - 4) >> 1][(lane - 4) & 1]);
+                    }
+                    if (last) { // no right neighbour: this macroblock is final already
+                        const uint32_t slot = down_ring + (uint32_t)(mb_x % DB_RING) * (uint32_t)sizeof(TopSlot);
+                        if (lane < 4) st_cluster_v4(slot + 16 * lane, *(const uint4 *)&S.L[16 + lane][16]);
+                        else if (lane < 8) st_cluster_v2(slot + 64 + 8 * (lane - 4), *(const uint2 *)&S.C[(lane - 4) >> 1][8 + ((lane - 4) & 1)][8]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) st_cluster_release(down_avail, mb_x + last);
+                }
+                __syncwarp();
+                if (lane < 4) *(uint4 *)S.prev.y[lane] = *(const uint4 *)&S.L[16 + lane][16];
+                else if (lane < 8) *(uint2 *)S.prev.c[(lane - 4) >> 1][(lane - 4) & 1] = *(const uint2 *)&S.C[(lane - 4) >> 1][8 + ((lane - 4) & 1)][8];
+            }
+            __syncwarp();
+            // ---- write back to global memory (every row: the frame must end up there)
+            // (luma rows 13..15 and chroma row 7 are left to the in-cluster row below: it writes their final values after its
+            // top-edge filter, and an earlier value written from here after the hand-over could land on top of them)
+            if (lane < 16) {
+                if (!(push_down && lane >= 13)) {
+                    uint8_t *d = rowy + (size_t)lane * a.stride + 16 * mb_x;
+                    *(uint4 *)d = *(const uint4 *)&S.L[4 + lane][16];
+                    if (mb_x > 0) *(uint32_t *)(d - 4) = *(const uint32_t *)&S.L[4 + lane][12];
+                }
+                if (!(push_down && (lane & 7) == 7)) {
+                    uint8_t *dc = (lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * mb_x;
+                    *(uint2 *)dc = *(const uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8];
+                    if (mb_x > 0) *(uint16_t *)(dc - 2) = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6];
+                }
+            } else if (mb_y > 0) {
+                if (lane < 19) *(uint4 *)(rowy - (size_t)(19 - lane) * a.stride + 16 * mb_x) = *(const uint4 *)&S.L[lane - 15][16]; // rows -3..-1
+                else if (lane < 21) *(uint2 *)((lane == 19 ? rowu : rowv) - a.stride_c + 8 * mb_x) = *(const uint2 *)&S.C[lane - 19][1][8];
+            }
+            __syncwarp();
+            if (lane < 16) { // the right columns stay in shared memory as the next macroblock's left neighbour
+                *(uint32_t *)&S.L[4 + lane][12] = *(const uint32_t *)&S.L[4 + lane][28];
+                *(uint32_t *)&S.C[lane >> 3][2 + (lane & 7)][4] = *(const uint32_t *)&S.C[lane >> 3][2 + (lane & 7)][12];
+            }
+            __syncwarp();
+            if (publish && lane == 0) st_release(a.progress + mb_y, mb_x + 1);
+            if (flag_probe >= 0) {
+                seen = max(seen, flag_probe);
                 if (seen >= min(mb_x + 3, a.W)) {
                     if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * (mb_x + 1)));
                     else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * (mb_x + 1)));
                     have_top = true;
-                } else
-                    flag_probe = ld_acquire(above);
-            }
-        }
-        __syncwarp();
-
-        // ---- vertical edges: the lane's line (luma row / chroma row) lives in registers across all of them
-        uint32_t w[5];
-        if (lane < 16) {
-            w[0] = *(const uint32_t *)&S.L[4 + lane][12];
-            const uint4 v = *(const uint4 *)&S.L[4 + lane][16];
-            w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w;
-        } else {
-            w[0] = *(const uint32_t *)&S.C[cpl][2 + cln][4];
-            const uint2 v = *(const uint2 *)&S.C[cpl][2 + cln][8];
-            w[1] = v.x; w[2] = v.y; w[3] = w[4] = 0;
-        }
-        filter_line(w, S.rec, 0, lane);
-        if (lane < 16) {
-            *(uint32_t *)&S.L[4 + lane][12] = w[0];
-            *(uint4 *)&S.L[4 + lane][16] = make_uint4(w[1], w[2], w[3], w[4]);
-        } else {
-            *(uint32_t *)&S.C[cpl][2 + cln][4] = w[0];
-            *(uint2 *)&S.C[cpl][2 + cln][8] = make_uint2(w[1], w[2]);
-        }
-        __syncwarp();
-        // ---- horizontal edges: the lane's column, gathered from the tile
-        if (lane < 16) {
-#pragma unroll
-            for (int k = 0; k < 5; k++)
-                w[k] = (uint32_t)S.L[4 * k][16 + lane] | (uint32_t)S.L[4 * k + 1][16 + lane] << 8 | (uint32_t)S.L[4 * k + 2][16 + lane] << 16 |
-                       (uint32_t)S.L[4 * k + 3][16 + lane] << 24;
-        } else {
-            w[0] = (uint32_t)S.C[cpl][0][8 + cln] << 16 | (uint32_t)S.C[cpl][1][8 + cln] << 24;
-#pragma unroll
-            for (int k = 1; k < 3; k++)
-                w[k] = (uint32_t)S.C[cpl][4 * k - 2][8 + cln] | (uint32_t)S.C[cpl][4 * k - 1][8 + cln] << 8 | (uint32_t)S.C[cpl][4 * k][8 + cln] << 16 |
-                       (uint32_t)S.C[cpl][4 * k + 1][8 + cln] << 24;
-        }
-        filter_line(w, S.rec, 1, lane);
-        if (lane < 16) {
-#pragma unroll
-            for (int k = 0; k < 5; k++)
-#pragma unroll
-                for (int b = (k == 0 ? 1 : 0); b < (k == 4 ? 3 : 4); b++) S.L[4 * k + b][16 + lane] = (uint8_t)(w[k] >> (8 * b)); // p3 of the first and q3 of the last edge never change
-        } else {
-            S.C[cpl][1][8 + cln] = (uint8_t)(w[0] >> 24);
-#pragma unroll
-            for (int k = 1; k < 3; k++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) S.C[cpl][4 * k - 2 + b][8 + cln] = (uint8_t)(w[k] >> (8 * b));
-        }
-        __syncwarp();
-
-        // ---- write back: this macroblock, the 3 (chroma: 1) columns of the left neighbour and rows of the upper one it touched
-        if (lane < 16) {
-            uint8_t *d = rowy + (size_t)lane * a.stride + 16 * mb_x;
-            *(uint4 *)d = *(const uint4 *)&S.L[4 + lane][16];
-            if (mb_x > 0) *(uint32_t *)(d - 4) = *(const uint32_t *)&S.L[4 + lane][12];
-            uint8_t *dc = (lane < 8 ? rowu : rowv) + (size_t)(lane & 7) * a.stride_c + 8 * mb_x;
-            *(uint2 *)dc = *(const uint2 *)&S.C[lane >> 3][2 + (lane & 7)][8];
-            if (mb_x > 0) *(uint16_t *)(dc - 2) = *(const uint16_t *)&S.C[lane >> 3][2 + (lane & 7)][6];
-            // the right columns stay in shared memory as the next macroblock's left neighbour
-            *(uint32_t *)&S.L[4 + lane][12] = *(const uint32_t *)&S.L[4 + lane][28];
-            *(uint32_t *)&S.C[lane >> 3][2 + (lane & 7)][4] = *(const uint32_t *)&S.C[lane >> 3][2 + (lane & 7)][12];
-        } else if (mb_y > 0) {
-            if (lane < 19) *(uint4 *)(rowy - (size_t)(19 - lane) * a.stride + 16 * mb_x) = *(const uint4 *)&S.L[lane - 15][16]; // rows -3..-1
-            else if (lane < 21) *(uint2 *)((lane == 19 ? rowu : rowv) - a.stride_c + 8 * mb_x) = *(const uint2 *)&S.C[lane - 19][1][8];
-        }
-        // __syncwarp orders every lane's pixel stores before lane 0's release store; release is cumulative, so a row that
-        // acquires the new progress value sees all of them (no per-lane __threadfence on the critical path)
-        __syncwarp();
-        if (lane == 0) st_release(a.progress + mb_y, mb_x + 1);
-        if (flag_probe >= 0) {
-            seen = max(seen, flag_probe);
-            if (seen >= min(mb_x + 3, a.W)) { // became ready during this step: start the fetch now, it overlaps the next step's prologue
-                if (lane < 4) tl = __ldcg((const uint4 *)(rowy - (size_t)(4 - lane) * a.stride + 16 * (mb_x + 1)));
-                else if (lane < 8) tc2 = __ldcg((const uint2 *)(((lane - 4) >> 1 ? rowv : rowu) - (size_t)(2 - ((lane - 4) & 1)) * a.stride_c + 8 * (mb_x + 1)));
-                have_top = true;
+                }
             }
         }
     }
+    // nobody leaves while a neighbour may still write credits / rows into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 } // namespace
@@ -412,12 +490,12 @@ extern "C" int x264_cuda_frame_deblock_dev(x264_cuda_t *ctx, x264_cuda_frame_t *
     a.alpha_off = pm->alpha_c0_offset; a.beta_off = pm->beta_offset; a.chroma_off = pm->chroma_qp_offset;
     a.slice_b = !!pm->b_slice_b; a.psub8x8 = !!pm->b_psub8x8; a.cavlc8 = !!pm->b_cavlc_8x8dct;
     a.progress = ctx->d_deblock_progress;
-    // one single-warp CTA per macroblock row; all of them are resident at once (<= a few hundred), so a row can always
-    // wait for the row above
+    // one single-warp CTA per macroblock row in clusters of eight; all of them are resident at once (<= a few hundred), so
+    // a row can always wait for the row above
     deblock_prep_kernel<<<(int)((n_edges + 255) / 256), 256, 0, ctx->stream>>>(a, (EdgeRec *)ctx->d_deblock_recs);
     LAUNCH_CHECK(ctx, "deblock_prep_kernel");
-    deblock_rows_kernel<<<H, 32, 0, ctx->stream>>>(a, (const EdgeRec *)ctx->d_deblock_recs);
-    LAUNCH_CHECK(ctx, "deblock_rows_kernel");
+    deblock_rows_cluster_kernel<<<(H + DB_CLUSTER - 1) / DB_CLUSTER * DB_CLUSTER, 32, 0, ctx->stream>>>(a, (const EdgeRec *)ctx->d_deblock_recs);
+    LAUNCH_CHECK(ctx, "deblock_rows_cluster_kernel");
     return 0;
 }
 
