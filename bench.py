@@ -454,6 +454,124 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_rows(args):
+    """`--rows`: every SURVEY 8 row on one 1080p frame — device time of the frame-batched entry point (CUDA events, host arrays in,
+    results out where the entry point takes host arrays) beside the reference's own C for the same work on ONE host core
+    (oracle/_ref when built, else the oracle port).  A reported table, one JSON line; not the headline metric."""
+    import ctypes as C
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_pkg()
+    from x264_vs2008_b200 import synth
+    import xo_api as X
+    from helpers import make_deblock_info, lowres_planes, block_jobs_to_mis
+    o, kind = (X.ref(), "reference") if X.have_ref() else (X.port(), "port")
+    ctx = pkg.Context(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    clip = synth.Clip(W, H, seed=3)
+    flags = pkg.FRAME_HPEL | pkg.FRAME_INTEGRAL | pkg.FRAME_LOWRES | pkg.FRAME_CHROMA
+    fenc, fref, fdec = ctx.frame(W, H, flags), ctx.frame(W, H, flags), ctx.frame(W, H, flags)
+    (y1, u1, v1), (y0, u0, v0) = clip.yuv420(1), clip.yuv420(0)
+    g = fenc.g
+    og = o.geometry(W, H)
+    jobs = build_jobs(pkg, g.mb_width, g.mb_height)
+    mbjobs = to_mb_jobs(pkg, jobs, g.mb_width, g.mb_height)
+    ctx.set_cost_mv(QP); ctx.set_quant_preset(0)
+    n_mb = g.mb_width * g.mb_height
+    rj = np.zeros(n_mb, pkg.RESID_JOB)
+    rj["mb_x"], rj["mb_y"] = np.tile(np.arange(g.mb_width), g.mb_height), np.repeat(np.arange(g.mb_height), g.mb_width)
+    rj["qp"], rj["chroma_qp"], rj["flags"] = 26, 26, pkg.RESID_DECIMATE
+    dinfo = make_deblock_info(og, seed=7)
+    gpu = {}
+
+    def timed(name, fn, reps=5):
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); r = fn(); e1.record(stream); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        gpu[name] = best
+        return r
+
+    for f, (yy, uu, vv) in ((fenc, (y1, u1, v1)), (fref, (y0, u0, v0)), (fdec, (y0, u0, v0))):
+        f.upload(yy); f.upload_chroma(uu, vv)
+    timed("a7 border expansion (luma + chroma)", fref.expand_border)
+    fenc.expand_border()
+    timed("a7+a9 hpel filter + filtered borders + integral", fref.filter)
+    timed("a10 lowres init (4 planes + borders)", fenc.init_lowres)
+    fref.init_lowres()
+    for f in (fenc, fref):
+        f.lookahead_alloc(2)
+    res = timed("a1+a6 ESA merange 16, 9 partitions x 8160 MB", lambda: ctx.me_search_mb(fenc, fref, ME_RANGE, mbjobs))
+    r = res["part"].reshape(-1)
+    j2 = jobs.copy()
+    j2["seed_mv"][:, 0], j2["seed_mv"][:, 1], j2["seed_cost"] = r["bmx"], r["bmy"], r["bcost"]
+    j2["mv_min_spel"] = (j2["mv_min_fpel"].astype(np.int32) - 5) * 4
+    j2["mv_max_spel"] = (j2["mv_max_fpel"].astype(np.int32) + 5) * 4
+    j2["flags"] = pkg.ME_MBCMP_SATD
+    fin = timed("a2+a8 qpel refine subme 4 (SATD), 73440 searches", lambda: ctx.me_search_small(fenc, fref, pkg.ME_METHOD_SEEDED, ME_RANGE, 4, j2))
+    f16 = fin[0::9]
+    mc = np.zeros(len(f16), pkg.MC_JOB)
+    mc["bx"], mc["by"], mc["mvx"], mc["mvy"], mc["w"], mc["h"] = jobs["bx"][0::9], jobs["by"][0::9], f16["mv"][:, 0], f16["mv"][:, 1], 16, 16
+    timed("a8 motion compensation 16x16 (luma + chroma), 8160 MB", lambda: ctx.mc_blocks(fref, fdec, mc))
+    timed("a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB", lambda: ctx.residual_inter(fenc, fdec, rj), reps=3)
+    timed("f1 deblocking", lambda: ctx.frame_deblock(fdec, dinfo), reps=3)
+    timed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)), reps=3)
+    timed("f2 SSD + SSIM sums + AQ energies + hadamard_ac", lambda: (ctx.frame_ssd(fenc, fref, pkg.PLANE_FULL, W, H), ctx.frame_ssim(fenc, fref, pkg.PLANE_FULL, W, H),
+                                                                      ctx.frame_mb_energy(fenc), ctx.frame_mb_hadamard_ac(fenc)))
+
+    # ---- the reference's C on one core
+    cpu = {}
+
+    def ctimed(name, fn, scale=1.0, reps=2):
+        best = 1e9
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+        cpu[name] = best * 1e3 * scale
+
+    pe = o.new_plane(og); pe.reshape(-1, og.stride)[X.PADV:X.PADV + H, X.PADH:X.PADH + W] = y1
+    pr = o.new_plane(og); pr.reshape(-1, og.stride)[X.PADV:X.PADV + H, X.PADH:X.PADH + W] = y0
+    ctimed("a7 border expansion (luma + chroma)", lambda: o.lib.xo_frame_expand_border(C.byref(og), X._ptr(pr, X.u8p, og.origin)), scale=1.5)
+    o.lib.xo_frame_expand_border(C.byref(og), X._ptr(pe, X.u8p, og.origin))
+    filt = [None]
+    ctimed("a7+a9 hpel filter + filtered borders + integral", lambda: filt.__setitem__(0, o.frame_filter(og, pr, 0)))
+    ctimed("a10 lowres init (4 planes + borders)", lambda: o.init_lowres(og, pe.copy()))
+    fh, fv, fc, integ = filt[0]
+    rate, _, _, sample, _ = cpu_rate(1, 9 * 120 * 8, 1)
+    cands = count_cands(jobs, r, ME_RANGE)[0]
+    cpu["a1+a6 ESA merange 16, 9 partitions x 8160 MB"] = cands / rate * 1e3
+    n_s = 1800
+    mis = block_jobs_to_mis(j2[:n_s], ME_RANGE, method=X.ME_ESA)
+    for mi, j in zip(mis, j2[:n_s]):
+        mi.mv_min_spel[0], mi.mv_min_spel[1] = int(j["mv_min_spel"][0]), int(j["mv_min_spel"][1])
+        mi.mv_max_spel[0], mi.mv_max_spel[1] = int(j["mv_max_spel"][0]), int(j["mv_max_spel"][1])
+    t0 = time.perf_counter()
+    for mi in mis:
+        o.me_search_subpel(og, pe, [pr, fh, fv, fc], integ, mi, 4, 1)
+    t_full = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for mi in mis:
+        o.me_search_fpel(og, pe, pr, integ, mi)
+    t_fpel = time.perf_counter() - t0
+    cpu["a2+a8 qpel refine subme 4 (SATD), 73440 searches"] = max(t_full - t_fpel, 0.0) / n_s * len(jobs) * 1e3
+    yy, uu, vv = np.ascontiguousarray(pr.reshape(-1, og.stride)[X.PADV:X.PADV + 16 * og.mb_height, X.PADH:X.PADH + 16 * og.mb_width]), None, None
+    cu = np.zeros((8 * og.mb_height, 8 * og.mb_width), np.uint8); cu[:u0.shape[0], :u0.shape[1]] = u0
+    cv = np.zeros((8 * og.mb_height, 8 * og.mb_width), np.uint8); cv[:v0.shape[0], :v0.shape[1]] = v0
+    ctimed("f1 deblocking", lambda: o.frame_deblock(og, dinfo, pr.copy(), cu.copy(), cv.copy()))
+    planes = lowres_planes(o, og, clip, 2)
+    ctimed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: o.lowres_frame_cost(og, planes[1], planes[0], planes[1], 0, 1, 1, X.lowres_state(og), do_search=(1, 0)), reps=1)
+    a2, b2 = np.ascontiguousarray(y1), np.ascontiguousarray(y0)
+    ctimed("f2 SSD + SSIM sums + AQ energies + hadamard_ac", lambda: (o.frame_ssd(a2, b2, W, H), o.frame_ssim(a2, b2, W, H), o.frame_mb_energy(og, pe, cu, cv),
+                                                                      o.frame_mb_hadamard_ac(og, pe)))
+    rows = [{"row": k, "gpu_ms": round(v, 4), "cpu_ms_1core": (round(cpu[k], 3) if k in cpu else None),
+             "speedup_vs_1core": (round(cpu[k] / v, 1) if k in cpu else None)} for k, v in gpu.items()]
+    print(json.dumps({"rows_1080p": rows, "cpu_kind": kind, "note": "gpu_ms includes H2D/D2H of job/result arrays where the entry point takes host arrays; "
+                      "cpu: the reference's own C (-O4 -ffast-math, no asm) on one core of this box; qpel refine cpu time = (full search - full-pel search) on 1800 jobs, scaled"}))
+    for f in (fenc, fref, fdec):
+        f.close()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -461,10 +579,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rows", action="store_true", help="per-row device time vs the reference's C on one core (1080p); one JSON line")
     ap.add_argument("--e2e-threads", type=int, default=4, help="frames in flight (host threads, one context each) in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.rows:
+        run_rows(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

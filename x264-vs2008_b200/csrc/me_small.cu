@@ -724,13 +724,27 @@ __global__ void __launch_bounds__(64) lowres_intra_kernel(const uint8_t *__restr
 struct LaArgs {
     const uint8_t *fenc[4], *ref[2][4];
     int stride, W, H;
-    int16_t *mvs[2]; int *costs[2]; const int16_t *ref1_mvs; int *intra; int *done; const int *order; int n_order;
+    int16_t *mvs[2]; int *costs[2]; const int16_t *ref1_mvs; int *intra; unsigned long long *sync; int n_mb; const int *order; int n_order;
     int *ticket, *sums; // sums: score, intra_mbs, intra_cost_sum
     int epoch, b_bidir, b_any_inter, dsf, weight, method, me_range, do_search0, do_search1, mbcmp_satd, fpel_satd;
     const int16_t *tab; // p_cost_mv (qp 12) centre
 };
 
-__device__ __forceinline__ int ld_vol(const int *p) { return *(const volatile int *)p; }
+// Hand-over between blocks of one launch: a block publishes, per list, ONE 64-bit word (epoch << 32 | mvy << 16 | mvx) with a
+// relaxed store; a dependent block polls that word and takes the vector out of it.  The vector travels inside the flag, so
+// neither side needs a fence or a second dependent load (a fenced flag + data hand-over through global memory costs ~1500
+// cycles one way on B200, a relaxed one ~900: measured).
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void la_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // TRY_BIDIR (slicetype.c:96-112): lanes 0/1 own the two 8x4 units of the block
 __device__ int bidir_cost(const LaArgs &a, const uint8_t *fe, size_t off, int mv0x, int mv0y, int mv1x, int mv1y, int lane)
@@ -773,6 +787,7 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
 {
     __shared__ x264_cuda_me_job_t s_job[4];
     __shared__ x264_cuda_me_final_t s_fin[4];
+    __shared__ uint32_t s_mvc[4][4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (;;) {
         int t = 0;
@@ -784,19 +799,12 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
         const uint8_t *fe = a.fenc[0] + off;
         int bcost = COST_MAX;
         if (a.b_any_inter) {
-            // wait for the blocks whose vectors this one predicts from: right, below, below-left, below-right (slicetype.c:153-166)
-            if (a.do_search0 | a.do_search1) {
-                if (lane < 4) {
-                    const int dx = lane == 0 ? 1 : lane == 1 ? 0 : lane == 2 ? -1 : 1, dy = lane == 0 ? 0 : 1;
-                    const int nx = mx + dx, ny = my + dy;
-                    // only blocks evaluated in this call carry a flag: the interior ones (or all of them for tiny frames)
-                    const bool small = a.W <= 2 || a.H <= 2;
-                    const bool inside = small ? (nx >= 0 && nx < a.W && ny >= 0 && ny < a.H) : (nx >= 1 && nx <= a.W - 2 && ny >= 1 && ny <= a.H - 2);
-                    if (inside) while (ld_vol(a.done + nx + ny * a.W) != a.epoch) __nanosleep(40);
+            // while the neighbours finish: pull the full-pel search window of every list to be searched into this SM's L1
+            for (int l = 0; l < 1 + a.b_bidir; l++)
+                if (l ? a.do_search1 : a.do_search0) {
+                    const uint8_t *w0 = a.ref[l][0] + off - (ptrdiff_t)20 * a.stride - 20;
+                    for (int r = lane; r < 48; r += 32) { la_prefetch_l1(w0 + (size_t)r * a.stride); la_prefetch_l1(w0 + (size_t)r * a.stride + 47); }
                 }
-                __syncwarp();
-                __threadfence();
-            }
             const int fx_min = -8 * mx - 4, fx_max = 8 * (a.W - mx - 1) + 4, fy_min = -8 * my - 4, fy_max = 8 * (a.H - my - 1) + 4; // slicetype.c:75-85
             const int sx_min = 4 * (fx_min - 8), sx_max = 4 * (fx_max + 8), sy_min = 4 * (fy_min - 8), sy_max = 4 * (fy_max + 8);
             int mvx[2] = { 0, 0 }, mvy[2] = { 0, 0 };
@@ -812,20 +820,38 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
             for (int l = 0; l < 1 + a.b_bidir; l++) {
                 int cost;
                 if (l ? a.do_search1 : a.do_search0) {
+                    int n_mvc = 0;
+                    __syncwarp();
+                    // the vectors this block predicts from: right, below, below-left, below-right (slicetype.c:153-166), one lane
+                    // each.  Blocks evaluated in this launch (the interior ones, or all of them for tiny frames) hand theirs over
+                    // through the sync word; frame-edge blocks keep whatever the frame's array holds, like in the reference.
+                    if (lane < 4) s_mvc[wid][lane] = 0;
+                    __syncwarp();
+                    {
+                        const int dx = lane == 0 ? 1 : lane == 1 ? 0 : lane == 2 ? -1 : 1, dy = lane == 0 ? 0 : 1;
+                        const int nx = mx + dx, ny = my + dy;
+                        const bool ex = lane < 4 && nx >= 0 && nx < a.W && ny < a.H;
+                        uint32_t v = 0;
+                        if (ex) {
+                            const bool small = a.W <= 2 || a.H <= 2;
+                            const bool inside = small || (nx >= 1 && nx <= a.W - 2 && ny >= 1 && ny <= a.H - 2);
+                            if (inside) {
+                                unsigned long long wv;
+                                do wv = ld_relaxed_u64(a.sync + (size_t)l * a.n_mb + nx + ny * a.W); while ((uint32_t)(wv >> 32) != (uint32_t)a.epoch);
+                                v = (uint32_t)wv;
+                            } else
+                                v = *(const uint32_t *)(a.mvs[l] + 2 * (nx + ny * a.W));
+                        }
+                        const unsigned exm = __ballot_sync(0xffffffffu, ex);
+                        if (ex) s_mvc[wid][__popc(exm & ((1u << lane) - 1))] = v;
+                        n_mvc = __popc(exm);
+                    }
                     __syncwarp();
                     if (lane == 0) {
                         x264_cuda_me_job_t &j = s_job[wid];
-                        const volatile int16_t *fm = a.mvs[l] + 2 * xy; // written by other warps of this launch: no caching
-                        int n = 0;
-                        int16_t c[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-#define LA_MVC(o) { c[n][0] = fm[2 * (o)]; c[n][1] = fm[2 * (o) + 1]; n++; }
-                        if (mx < a.W - 1) LA_MVC(1);
-                        if (my < a.H - 1) {
-                            LA_MVC(a.W);
-                            if (mx > 0) LA_MVC(a.W - 1);
-                            if (mx < a.W - 1) LA_MVC(a.W + 1);
-                        }
-#undef LA_MVC
+                        const int n = n_mvc;
+                        int16_t c[4][2];
+                        for (int k = 0; k < 4; k++) { c[k][0] = (int16_t)(s_mvc[wid][k] & 0xffff); c[k][1] = (int16_t)(s_mvc[wid][k] >> 16); }
                         j.bx = 8 * mx; j.by = 8 * my; j.i_pixel = X264_CUDA_PIXEL_8x8; j.qp = 12; j.i_mvc = n;
                         j.flags = (a.fpel_satd ? X264_CUDA_ME_FPEL_SATD : 0) | (a.mbcmp_satd ? X264_CUDA_ME_MBCMP_SATD : 0);
                         for (int k = 0; k < 2; k++) { // x264_median_mv(mvc[0], mvc[1], mvc[2])
@@ -853,7 +879,9 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
                     if (fin.mv[0] | fin.mv[1]) cost += 5;
                     mvx[l] = fin.mv[0]; mvy[l] = fin.mv[1];
                     if (lane == 0) {
-                        *(volatile int *)(a.mvs[l] + 2 * xy) = (int)(((uint32_t)(uint16_t)fin.mv[0]) | ((uint32_t)(uint16_t)fin.mv[1] << 16));
+                        const uint32_t mvw = ((uint32_t)(uint16_t)fin.mv[0]) | ((uint32_t)(uint16_t)fin.mv[1] << 16);
+                        st_relaxed_u64(a.sync + (size_t)l * a.n_mb + xy, ((unsigned long long)(uint32_t)a.epoch << 32) | mvw); // hand-over
+                        *(uint32_t *)(a.mvs[l] + 2 * xy) = mvw; // the frame's persistent lowres_mvs
                         a.costs[l][xy] = cost;
                     }
                 } else {
@@ -870,8 +898,6 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
             if (b_intra) bcost = icost;
         }
         if (lane == 0) {
-            __threadfence();
-            *(volatile int *)(a.done + xy) = a.epoch;
             atomicAdd(a.sums + 0, bcost);
             if (!a.b_bidir && mx > 0 && mx < a.W - 1 && my > 0 && my < a.H - 1) { atomicAdd(a.sums + 1, b_intra); atomicAdd(a.sums + 2, icost); }
         }
@@ -893,11 +919,11 @@ extern "C" int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame
     CUDA_TRY(ctx, cudaMalloc(&f->la_mvs, 2 * n_dist * n_mb * 4));
     CUDA_TRY(ctx, cudaMalloc(&f->la_costs, 2 * n_dist * n_mb * 4));
     CUDA_TRY(ctx, cudaMalloc(&f->la_intra, n_mb * 4));
-    CUDA_TRY(ctx, cudaMalloc(&f->la_done, n_mb * 4));
+    CUDA_TRY(ctx, cudaMalloc(&f->la_done, 2 * n_mb * 8)); // hand-over words, per list (see lowres_cost_kernel)
     CUDA_TRY(ctx, cudaMemsetAsync(f->la_mvs, 0, 2 * n_dist * n_mb * 4, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(f->la_costs, 0, 2 * n_dist * n_mb * 4, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(f->la_intra, 0, n_mb * 4, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(f->la_done, 0, n_mb * 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->la_done, 0, 2 * n_mb * 8, ctx->stream));
     f->la_dist = n_dist;
     return 0;
 }
@@ -1004,7 +1030,7 @@ extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *
     a.mvs[0] = fenc->la_mvs + 2 * ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb; a.costs[0] = fenc->la_costs + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
     a.mvs[1] = fenc->la_mvs + 2 * ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb; a.costs[1] = fenc->la_costs + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
     a.ref1_mvs = b_bidir ? fref1->la_mvs + 2 * ((size_t)(pm->p1 - pm->p0 - 1)) * n_mb : nullptr;
-    a.intra = fenc->la_intra; a.done = fenc->la_done; a.order = ctx->d_la_order; a.n_order = ctx->la_n;
+    a.intra = fenc->la_intra; a.sync = (unsigned long long *)fenc->la_done; a.n_mb = (int)n_mb; a.order = ctx->d_la_order; a.n_order = ctx->la_n;
     a.ticket = ctx->d_la_sums + 4; a.sums = ctx->d_la_sums;
     a.epoch = ++ctx->la_epoch; a.b_bidir = b_bidir; a.b_any_inter = any;
     a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
