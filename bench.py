@@ -502,23 +502,48 @@ def run_rows(args):
     fref.init_lowres()
     for f in (fenc, fref):
         f.lookahead_alloc(2)
-    res = timed("a1+a6 ESA merange 16, 9 partitions x 8160 MB", lambda: ctx.me_search_mb(fenc, fref, ME_RANGE, mbjobs))
-    r = res["part"].reshape(-1)
+    # job lists and result arrays live in page-locked memory (x264_cuda_host_alloc in a C caller), so they are DMA'd directly
+    L = pkg.lib()
+    keep = []
+
+    def pinned(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).pin_memory()
+        keep.append(t)
+        return t
+
+    def pinned_out(nbytes):
+        t = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        keep.append(t)
+        return t
+
+    p_mbjobs, p_mbres = pinned(mbjobs), pinned_out(n_mb * pkg.ME_MB_RESULT.itemsize)
+    timed("a1+a6 ESA merange 16, 9 partitions x 8160 MB",
+          lambda: ctx.check(L.x264_cuda_me_search_mb(ctx.h, fenc.h, fref.h, ME_RANGE, p_mbjobs.data_ptr(), n_mb, p_mbres.data_ptr())))
+    r = p_mbres.numpy().view(pkg.ME_MB_RESULT)["part"].reshape(-1)
     j2 = jobs.copy()
     j2["seed_mv"][:, 0], j2["seed_mv"][:, 1], j2["seed_cost"] = r["bmx"], r["bmy"], r["bcost"]
     j2["mv_min_spel"] = (j2["mv_min_fpel"].astype(np.int32) - 5) * 4
     j2["mv_max_spel"] = (j2["mv_max_fpel"].astype(np.int32) + 5) * 4
     j2["flags"] = pkg.ME_MBCMP_SATD
-    fin = timed("a2+a8 qpel refine subme 4 (SATD), 73440 searches", lambda: ctx.me_search_small(fenc, fref, pkg.ME_METHOD_SEEDED, ME_RANGE, 4, j2))
+    p_j2, p_fin = pinned(j2), pinned_out(len(j2) * pkg.ME_FINAL.itemsize)
+    timed("a2+a8 qpel refine subme 4 (SATD), 73440 searches",
+          lambda: ctx.check(L.x264_cuda_me_search_small(ctx.h, fenc.h, fref.h, pkg.ME_METHOD_SEEDED, ME_RANGE, 4, p_j2.data_ptr(), len(j2), p_fin.data_ptr())))
+    fin = p_fin.numpy().view(pkg.ME_FINAL)
     f16 = fin[0::9]
     mc = np.zeros(len(f16), pkg.MC_JOB)
     mc["bx"], mc["by"], mc["mvx"], mc["mvy"], mc["w"], mc["h"] = jobs["bx"][0::9], jobs["by"][0::9], f16["mv"][:, 0], f16["mv"][:, 1], 16, 16
-    timed("a8 motion compensation 16x16 (luma + chroma), 8160 MB", lambda: ctx.mc_blocks(fref, fdec, mc))
-    timed("a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB", lambda: ctx.residual_inter(fenc, fdec, rj), reps=3)
+    p_mc = pinned(mc)
+    timed("a8 motion compensation 16x16 (luma + chroma), 8160 MB", lambda: ctx.check(L.x264_cuda_mc_blocks(ctx.h, fref.h, fdec.h, p_mc.data_ptr(), len(mc))))
+    p_rj, p_coef = pinned(rj), pinned_out(n_mb * pkg.MB_COEFFS.itemsize)
+    timed("a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB",
+          lambda: ctx.check(L.x264_cuda_residual_inter(ctx.h, fenc.h, fdec.h, p_rj.data_ptr(), n_mb, p_coef.data_ptr())), reps=3)
     timed("f1 deblocking", lambda: ctx.frame_deblock(fdec, dinfo), reps=3)
     timed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)), reps=3)
-    timed("f2 SSD + SSIM sums + AQ energies + hadamard_ac", lambda: (ctx.frame_ssd(fenc, fref, pkg.PLANE_FULL, W, H), ctx.frame_ssim(fenc, fref, pkg.PLANE_FULL, W, H),
-                                                                      ctx.frame_mb_energy(fenc), ctx.frame_mb_hadamard_ac(fenc)))
+    p_ssd, p_sums, p_en, p_had = pinned_out(8), pinned_out((H // 4) * (W // 4) * 16), pinned_out(n_mb * 4), pinned_out(n_mb * 8)
+    timed("f2 SSD + SSIM sums + AQ energies + hadamard_ac",
+          lambda: (ctx.check(L.x264_cuda_frame_ssd(ctx.h, fenc.h, fref.h, pkg.PLANE_FULL, 0, 0, W, H, p_ssd.data_ptr())),
+                   ctx.check(L.x264_cuda_frame_ssim_sums(ctx.h, fenc.h, fref.h, pkg.PLANE_FULL, 0, 0, W, H, p_sums.data_ptr())),
+                   ctx.check(L.x264_cuda_frame_mb_energy(ctx.h, fenc.h, p_en.data_ptr())), ctx.check(L.x264_cuda_frame_mb_hadamard_ac(ctx.h, fenc.h, p_had.data_ptr()))))
 
     # ---- the reference's C on one core
     cpu = {}
@@ -563,10 +588,48 @@ def run_rows(args):
     a2, b2 = np.ascontiguousarray(y1), np.ascontiguousarray(y0)
     ctimed("f2 SSD + SSIM sums + AQ energies + hadamard_ac", lambda: (o.frame_ssd(a2, b2, W, H), o.frame_ssim(a2, b2, W, H), o.frame_mb_energy(og, pe, cu, cv),
                                                                       o.frame_mb_hadamard_ac(og, pe)))
+    # residual and MC: the reference is per-macroblock code; time a sample of macroblocks through it and scale
+    class RIn(C.Structure):
+        _fields_ = [(n, C.c_int) for n in ("qp", "chroma_qp", "b_transform_8x8", "b_decimate", "cqm")]
+
+    class ROut(C.Structure):
+        _fields_ = [("luma4x4", (C.c_int16 * 16) * 24), ("luma8x8", (C.c_int16 * 64) * 4), ("chroma_dc", (C.c_int16 * 4) * 2),
+                    ("nnz", C.c_uint8 * 27), ("pad", C.c_uint8), ("cbp_luma", C.c_int), ("cbp_chroma", C.c_int)]
+    n_s = 1500
+    blk = []
+    for i in range(n_s):
+        mx, my = (i * 7) % g.mb_width, (i * 3) % (H // 16)
+        sl = lambda a, k: np.ascontiguousarray(a[my * k:my * k + k, mx * k:mx * k + k])
+        blk.append((sl(y1, 16), sl(u1, 8), sl(v1, 8), sl(y0, 16), sl(u0, 8), sl(v0, 8)))
+    rin, rout = RIn(26, 26, 0, 1, 0), ROut()
+    t0 = time.perf_counter()
+    for fy, fu, fv, py, pu, pv in blk:
+        o.lib.xo_residual_inter_mb(C.byref(rin), X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(py), X._ptr(pu), X._ptr(pv), C.byref(rout))
+    cpu["a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB"] = (time.perf_counter() - t0) / n_s * n_mb * 1e3
+    planes4 = (X.u8p * 4)(*[X._ptr(p_, X.u8p, og.origin + 64 * og.stride + 64) for p_ in (pr, fh, fv, fc)])
+    dst, dstc = np.zeros((16, 16), np.uint8), np.zeros((8, 8), np.uint8)
+    cup = np.ascontiguousarray(np.pad(u0, 16, mode="edge"))
+    t0 = time.perf_counter()
+    for i in range(n_s):
+        mvx, mvy = int(f16["mv"][i, 0]), int(f16["mv"][i, 1])
+        o.lib.xo_mc_luma(X._ptr(dst), 16, planes4, og.stride, mvx, mvy, 16, 16)
+        o.lib.xo_mc_chroma(X._ptr(dstc), 8, X._ptr(cup, X.u8p, 40 * cup.shape[1] + 40), cup.shape[1], mvx, mvy, 8, 8)
+        o.lib.xo_mc_chroma(X._ptr(dstc), 8, X._ptr(cup, X.u8p, 40 * cup.shape[1] + 40), cup.shape[1], mvx, mvy, 8, 8)
+    t_mc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(n_s):  # the same three calls with empty blocks: ctypes marshalling only
+        mvx, mvy = int(f16["mv"][i, 0]), int(f16["mv"][i, 1])
+        o.lib.xo_mc_luma(X._ptr(dst), 16, planes4, og.stride, mvx, mvy, 0, 0)
+        o.lib.xo_mc_chroma(X._ptr(dstc), 8, X._ptr(cup, X.u8p, 40 * cup.shape[1] + 40), cup.shape[1], mvx, mvy, 0, 0)
+        o.lib.xo_mc_chroma(X._ptr(dstc), 8, X._ptr(cup, X.u8p, 40 * cup.shape[1] + 40), cup.shape[1], mvx, mvy, 0, 0)
+    t_call = time.perf_counter() - t0
+    cpu["a8 motion compensation 16x16 (luma + chroma), 8160 MB"] = max(t_mc - t_call, 0.0) / n_s * n_mb * 1e3
+    key_r = "a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB"
+    cpu[key_r] = max(cpu[key_r] - t_call / 3 / n_s * n_mb * 1e3, 0.0)
     rows = [{"row": k, "gpu_ms": round(v, 4), "cpu_ms_1core": (round(cpu[k], 3) if k in cpu else None),
              "speedup_vs_1core": (round(cpu[k] / v, 1) if k in cpu else None)} for k, v in gpu.items()]
-    print(json.dumps({"rows_1080p": rows, "cpu_kind": kind, "note": "gpu_ms includes H2D/D2H of job/result arrays where the entry point takes host arrays; "
-                      "cpu: the reference's own C (-O4 -ffast-math, no asm) on one core of this box; qpel refine cpu time = (full search - full-pel search) on 1800 jobs, scaled"}))
+    print(json.dumps({"rows_1080p": rows, "cpu_kind": kind, "note": "gpu_ms includes H2D/D2H of job/result arrays (page-locked) where the entry point takes host arrays; "
+                      "cpu: the reference's own C (-O4 -ffast-math, no asm) on one core of this box; qpel refine cpu time = (full search - full-pel search) on 1800 jobs, scaled; residual / MC cpu time = 1500 macroblocks through the per-macroblock reference code, scaled, ctypes call overhead measured with empty blocks and subtracted"}))
     for f in (fenc, fref, fdec):
         f.close()
     ctx.close()
