@@ -234,6 +234,14 @@ X264_CUDA_API int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_fram
 X264_CUDA_API int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
                                               const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *params,
                                               x264_cuda_lowres_result_t *result);
+/* Several evaluations in ONE launch (up to 64): the slicetype decision asks for many (p0,p1,b) costs of a lookahead window
+ * (S/encoder/slicetype.c:357-470), and each wavefront alone occupies only a few dozen warps.  The evaluations of a batch must be
+ * independent: no two may search the same (frame, list, distance) state, and none may read (ref1's list-0 vectors) what another
+ * one of the batch searches.  E.g. all P costs cost(i-1, i, i) of a window, or all B costs between two fixed P frames whose own
+ * vectors are already cached.  results[i] as for the single call. */
+X264_CUDA_API int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs,
+                                                    const x264_cuda_frame_t *const *fref0s, const x264_cuda_frame_t *const *fref1s,
+                                                    const x264_cuda_lowres_params_t *params, x264_cuda_lowres_result_t *results);
 
 /* ------------------------------------------------------------------ in-loop deblocking ---------------- */
 /* x264_frame_deblock (S/common/frame.c:794-799 -> x264_frame_deblock_row :621-792) of one progressive frame, in place on the

@@ -67,3 +67,61 @@ def test_lowres_intra_all_blocks(pkg, ctx, port):
         want = np.array([port.lib.xo_lowres_intra_cost(X._ptr(planes[0][0], X.u8p, g.origin_lowres), g.stride_lowres, 8 * (i % g.mb_width), 8 * (i // g.mb_width), satd)
                          for i in range(g.mb_width * g.mb_height)])
         assert np.array_equal(intra, want), np.nonzero(intra != want)[0][:10]
+
+
+@pytest.mark.parametrize("size", [(176, 144), (1920, 1080)])
+def test_lowres_frame_cost_batch(pkg, ctx, port, size):
+    """the P costs cost(i-1, i, i) of a 5-frame window in ONE launch (independent evaluations, interleaved wavefronts) vs the
+    oracle run one evaluation at a time; then the B costs between frames 0 and 2 / 2 and 4 in one launch"""
+    from x264_vs2008_b200 import synth
+    w, h = size
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=52)
+    n_frames = 5
+    planes = lowres_planes(port, g, clip, n_frames)
+    frames = []
+    for i in range(n_frames):
+        f = ctx.frame(w, h, pkg.FRAME_LOWRES)
+        f.upload(clip.luma(i)); f.expand_border(); f.init_lowres(); f.lookahead_alloc(3)
+        frames.append(f)
+    n = g.mb_width * g.mb_height
+    st = [{"mvs": np.zeros((2, 3, n, 2), np.int16), "costs": np.zeros((2, 3, n), np.int32), "intra": np.zeros(n, np.uint16)} for _ in range(n_frames)]
+
+    def oracle_eval(fe, p0, p1, b, ds, bic):
+        d0, d1 = max(b - p0 - 1, 0), max(p1 - b - 1, 0)
+        s = st[fe]
+        state = {"mvs0": s["mvs"][0, d0], "costs0": s["costs"][0, d0], "mvs1": s["mvs"][1, d1], "costs1": s["costs"][1, d1],
+                 "intra": s["intra"], "ref1_mvs": st[p1]["mvs"][0, max(p1 - p0 - 1, 0)].copy()}
+        o = port.lowres_frame_cost(g, planes[b], planes[p0], planes[p1], p0, p1, b, state, do_search=ds, b_intra_calculated=bic)
+        return (o.score, o.intra_mbs if b == p1 else 0, o.intra_cost_sum if b == p1 else 0)
+
+    m = np.zeros((g.mb_height, g.mb_width), bool)
+    m[1:-1, 1:-1] = True
+    m = m.ravel()
+    # batch 1: P costs of frames 1..4 against their predecessors, plus P(0->2) and P(2->4) (distance 2) — all independent
+    # batch 0: intra costs of every frame (I evaluations), so that later batches may say b_intra_calculated
+    evals = [(i, i, i, i, (0, 0), 0) for i in range(n_frames)]
+    want = [oracle_eval(*e) for e in evals]
+    got = ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in evals])
+    assert [a[0] for a in want] == [b[0] for b in got], (want, got)
+    evals = [(i, i - 1, i, i, (1, 0), 1) for i in range(1, n_frames)]
+    want = [oracle_eval(*e) for e in evals]
+    got = ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in evals])
+    assert want == got, (want, got)
+    for fe, p0, p1, b, ds, bic in evals:
+        d0 = b - p0 - 1
+        mv, cost, _ = frames[fe].lookahead_get(0, d0)
+        assert np.array_equal(mv[m], st[fe]["mvs"][0, d0][m]) and np.array_equal(cost[m], st[fe]["costs"][0, d0][m]), (fe, p0)
+    # batch 2: distance-2 P costs (their own state slot, dist index 1)
+    evals = [(2, 0, 2, 2, (1, 0), 1), (4, 2, 4, 4, (1, 0), 1)]
+    want = [oracle_eval(*e) for e in evals]
+    got = ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in evals])
+    assert want == got, (want, got)
+    # batch 3: B costs (0,2,1) and (2,4,3): list-0 vectors of frames 1 and 3 are cached from batch 1, list 1 searched now,
+    # ref1's list-0 distance-2 vectors come from batch 2
+    evals = [(1, 0, 2, 1, (0, 1), 1), (3, 2, 4, 3, (0, 1), 1)]
+    want = [oracle_eval(*e) for e in evals]
+    got = ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in evals])
+    assert [a[0] for a in want] == [b[0] for b in got], (want, got)
+    for f in frames:
+        f.close()

@@ -107,6 +107,7 @@ def lib():
         L.x264_cuda_frame_lookahead_get.argtypes = [vp, vp, ip, ip, vp, vp, vp]
         L.x264_cuda_frame_lookahead_set.argtypes = [vp, vp, ip, ip, vp, vp, vp]
         L.x264_cuda_lowres_frame_cost.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_lowres_frame_cost_batch.argtypes = [vp, ip, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_ssd.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
@@ -366,6 +367,16 @@ class Context:
         out = np.zeros(f.g.mb_width * f.g.mb_height, np.uint64)
         self.check(lib().x264_cuda_frame_mb_hadamard_ac(self.h, f.h, out.ctypes.data))
         return out
+
+    def lowres_frame_cost_batch(self, evals, me_method=1, me_range=16, flags=ME_MBCMP_SATD):
+        """evals: list of (fenc, fref0, fref1, p0, p1, b, do_search, b_intra_calculated) — independent evaluations, one launch.
+        -> list of (score, intra_mbs, intra_cost_sum)"""
+        n = len(evals)
+        ptrs = [(C.c_void_p * n)(*[e[k].h for e in evals]) for k in range(3)]
+        pm = np.array([[e[3], e[4], e[5], me_method, me_range, flags, e[6][0], e[6][1], e[7]] for e in evals], np.int32)
+        res = np.zeros((n, 4), np.int32)
+        self.check(lib().x264_cuda_lowres_frame_cost_batch(self.h, n, ptrs[0], ptrs[1], ptrs[2], pm.ctypes.data, res.ctypes.data))
+        return [(int(r[0]), int(r[1]), int(r[2])) for r in res]
 
     def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
         self.check(lib().x264_cuda_me_search_mb_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

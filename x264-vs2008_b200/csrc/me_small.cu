@@ -783,7 +783,9 @@ __device__ int bidir_cost(const LaArgs &a, const uint8_t *fe, size_t off, int mv
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
-__global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
+// `evals` = n_evals independent evaluations sharing one launch: ticket t belongs to evaluation t % n_evals (interleaved, so all
+// wavefronts advance together) and is that evaluation's block number t / n_evals in wavefront order.
+__global__ void __launch_bounds__(128) lowres_cost_kernel(const LaArgs *__restrict__ evals, int n_evals, int *ticket_counter, int n_order)
 {
     __shared__ x264_cuda_me_job_t s_job[4];
     __shared__ x264_cuda_me_final_t s_fin[4];
@@ -791,9 +793,11 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(LaArgs a)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (;;) {
         int t = 0;
-        if (lane == 0) t = atomicAdd(a.ticket, 1);
+        if (lane == 0) t = atomicAdd(ticket_counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= a.n_order) return;
+        if (t >= n_order * n_evals) return;
+        const LaArgs &a = evals[t % n_evals];
+        t /= n_evals;
         const int xy = a.order[t], mx = xy % a.W, my = xy / a.W;
         const size_t off = (size_t)(8 * my) * a.stride + 8 * mx;
         const uint8_t *fe = a.fenc[0] + off;
@@ -975,21 +979,16 @@ extern "C" int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_frame_t
     return 0;
 }
 
-extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
-                                           const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *pm, x264_cuda_lowres_result_t *result)
+#define LA_MAX_BATCH 64
+
+extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs, const x264_cuda_frame_t *const *fref0s,
+                                                 const x264_cuda_frame_t *const *fref1s, const x264_cuda_lowres_params_t *pms,
+                                                 x264_cuda_lowres_result_t *results)
 {
     x264_cuda_enter(ctx);
-    const x264_cuda_geom_t &g = fenc->g;
-    const int W = g.mb_width, H = g.mb_height, b_bidir = pm->b < pm->p1, any = !(pm->p0 == pm->p1 && pm->p0 == pm->b);
-    if (!fenc->lowres[0] || !fref0->lowres[0] || !fref1->lowres[0] || fref0->g.stride_lowres != g.stride_lowres || fref1->g.stride_lowres != g.stride_lowres) {
-        snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: frames need X264_CUDA_FRAME_LOWRES and equal geometry");
-        return -1;
-    }
-    const int d0 = pm->b - pm->p0 - 1, d1 = pm->p1 - pm->b - 1;
-    if (!fenc->la_mvs || (any && (d0 < 0 || d0 >= fenc->la_dist)) || (b_bidir && (d1 < 0 || d1 >= fenc->la_dist || !fref1->la_mvs || pm->p1 - pm->p0 - 1 >= fref1->la_dist))) {
-        snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: lookahead state missing or distance out of range");
-        return -1;
-    }
+    if (n_evals < 1 || n_evals > LA_MAX_BATCH) { snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost_batch: 1..%d evaluations per call", LA_MAX_BATCH); return -1; }
+    const x264_cuda_geom_t &g = fencs[0]->g;
+    const int W = g.mb_width, H = g.mb_height;
     const int16_t *const *d_tabs;
     if (!ctx->d_cost_mv[12]) { // the lookahead always works at qp 12 (slicetype.c:35)
         int16_t *t = (int16_t *)malloc((4 * 4 * 2048 + 1) * sizeof(int16_t));
@@ -1011,42 +1010,80 @@ extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *
                 ord[n++] = x + y * W;
             }
         cudaFree(ctx->d_la_order); ctx->d_la_order = nullptr;
-        if (!ctx->d_la_sums) CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_sums, 8 * sizeof(int)));
+        // per evaluation 8 ints of sums; then the ticket counter; then the LaArgs array
+        if (!ctx->d_la_sums) CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_sums, (8 * LA_MAX_BATCH + 8) * sizeof(int) + LA_MAX_BATCH * sizeof(LaArgs)));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_order, (size_t)W * H * sizeof(int)));
         CUDA_TRY(ctx, cudaMemcpy(ctx->d_la_order, ord, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
         free(ord);
         ctx->la_w = W; ctx->la_h = H; ctx->la_n = n;
     }
     const size_t n_mb = (size_t)W * H;
-    if (!b_bidir && !pm->b_intra_calculated) {
-        lowres_intra_kernel<<<(int)((n_mb + 63) / 64), 64, 0, ctx->stream>>>(fenc->lowres[0], g.stride_lowres, W, H, !!(pm->flags & X264_CUDA_ME_MBCMP_SATD), fenc->la_intra);
-        LAUNCH_CHECK(ctx, "lowres_intra_kernel");
+    int *d_ticket = ctx->d_la_sums + 8 * LA_MAX_BATCH;
+    LaArgs *d_evals = (LaArgs *)(ctx->d_la_sums + 8 * LA_MAX_BATCH + 8);
+    static_assert(sizeof(LaArgs) % 8 == 0, "LaArgs array follows an 8-int header");
+    LaArgs *h_evals = (LaArgs *)malloc((size_t)n_evals * sizeof(LaArgs));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_la_sums, 0, (8 * LA_MAX_BATCH + 8) * sizeof(int), ctx->stream));
+    for (int e = 0; e < n_evals; e++) {
+        x264_cuda_frame_t *fenc = fencs[e];
+        const x264_cuda_frame_t *fref0 = fref0s[e], *fref1 = fref1s[e];
+        const x264_cuda_lowres_params_t *pm = pms + e;
+        const int b_bidir = pm->b < pm->p1, any = !(pm->p0 == pm->p1 && pm->p0 == pm->b);
+        if (!fenc->lowres[0] || !fref0->lowres[0] || !fref1->lowres[0] || fref0->g.stride_lowres != g.stride_lowres || fref1->g.stride_lowres != g.stride_lowres ||
+            fenc->g.stride_lowres != g.stride_lowres || fenc->g.mb_width != W || fenc->g.mb_height != H) {
+            snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: frames need X264_CUDA_FRAME_LOWRES and equal geometry");
+            free(h_evals);
+            return -1;
+        }
+        const int d0 = pm->b - pm->p0 - 1, d1 = pm->p1 - pm->b - 1;
+        if (!fenc->la_mvs || (any && (d0 < 0 || d0 >= fenc->la_dist)) ||
+            (b_bidir && (d1 < 0 || d1 >= fenc->la_dist || !fref1->la_mvs || pm->p1 - pm->p0 - 1 >= fref1->la_dist))) {
+            snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: lookahead state missing or distance out of range");
+            free(h_evals);
+            return -1;
+        }
+        if (!b_bidir && !pm->b_intra_calculated) {
+            lowres_intra_kernel<<<(int)((n_mb + 63) / 64), 64, 0, ctx->stream>>>(fenc->lowres[0], g.stride_lowres, W, H, !!(pm->flags & X264_CUDA_ME_MBCMP_SATD), fenc->la_intra);
+            ctx->launches++;
+        }
+        LaArgs &a = h_evals[e];
+        memset(&a, 0, sizeof(a));
+        for (int k = 0; k < 4; k++) { a.fenc[k] = fenc->lowres[k]; a.ref[0][k] = fref0->lowres[k]; a.ref[1][k] = fref1->lowres[k]; }
+        a.stride = g.stride_lowres; a.W = W; a.H = H;
+        a.mvs[0] = fenc->la_mvs + 2 * ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb; a.costs[0] = fenc->la_costs + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
+        a.mvs[1] = fenc->la_mvs + 2 * ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb; a.costs[1] = fenc->la_costs + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
+        a.ref1_mvs = b_bidir ? fref1->la_mvs + 2 * ((size_t)(pm->p1 - pm->p0 - 1)) * n_mb : nullptr;
+        a.intra = fenc->la_intra; a.sync = (unsigned long long *)fenc->la_done; a.n_mb = (int)n_mb; a.order = ctx->d_la_order; a.n_order = ctx->la_n;
+        a.ticket = d_ticket; a.sums = ctx->d_la_sums + 8 * e;
+        a.epoch = ++ctx->la_epoch; a.b_bidir = b_bidir; a.b_any_inter = any;
+        a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
+        a.weight = (pm->flags & X264_CUDA_LOWRES_WEIGHTED_BIPRED) ? 64 - (a.dsf >> 2) : 32;                          // slicetype.c:57
+        a.method = pm->me_method < 1 ? X264_CUDA_ME_METHOD_DIA : X264_CUDA_ME_METHOD_HEX;                            // min(HEX, me), slicetype.c:38
+        a.me_range = pm->me_range; a.do_search0 = pm->do_search[0]; a.do_search1 = pm->do_search[1];
+        a.mbcmp_satd = !!(pm->flags & X264_CUDA_ME_MBCMP_SATD); a.fpel_satd = !!(pm->flags & X264_CUDA_ME_FPEL_SATD);
+        a.tab = ctx->d_cost_mv[12] + 2 * 4 * 2048;
     }
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_la_sums, 0, 8 * sizeof(int), ctx->stream));
-    LaArgs a;
-    memset(&a, 0, sizeof(a));
-    for (int k = 0; k < 4; k++) { a.fenc[k] = fenc->lowres[k]; a.ref[0][k] = fref0->lowres[k]; a.ref[1][k] = fref1->lowres[k]; }
-    a.stride = g.stride_lowres; a.W = W; a.H = H;
-    a.mvs[0] = fenc->la_mvs + 2 * ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb; a.costs[0] = fenc->la_costs + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
-    a.mvs[1] = fenc->la_mvs + 2 * ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb; a.costs[1] = fenc->la_costs + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
-    a.ref1_mvs = b_bidir ? fref1->la_mvs + 2 * ((size_t)(pm->p1 - pm->p0 - 1)) * n_mb : nullptr;
-    a.intra = fenc->la_intra; a.sync = (unsigned long long *)fenc->la_done; a.n_mb = (int)n_mb; a.order = ctx->d_la_order; a.n_order = ctx->la_n;
-    a.ticket = ctx->d_la_sums + 4; a.sums = ctx->d_la_sums;
-    a.epoch = ++ctx->la_epoch; a.b_bidir = b_bidir; a.b_any_inter = any;
-    a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
-    a.weight = (pm->flags & X264_CUDA_LOWRES_WEIGHTED_BIPRED) ? 64 - (a.dsf >> 2) : 32;                          // slicetype.c:57
-    a.method = pm->me_method < 1 ? X264_CUDA_ME_METHOD_DIA : X264_CUDA_ME_METHOD_HEX;                            // min(HEX, me), slicetype.c:38
-    a.me_range = pm->me_range; a.do_search0 = pm->do_search[0]; a.do_search1 = pm->do_search[1];
-    a.mbcmp_satd = !!(pm->flags & X264_CUDA_ME_MBCMP_SATD); a.fpel_satd = !!(pm->flags & X264_CUDA_ME_FPEL_SATD);
-    a.tab = ctx->d_cost_mv[12] + 2 * 4 * 2048;
+    cudaError_t ce = cudaMemcpyAsync(d_evals, h_evals, (size_t)n_evals * sizeof(LaArgs), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream); // h_evals is pageable and freed below
+    free(h_evals);
+    if (ce != cudaSuccess) return x264_cuda_fail(ctx, "lowres_frame_cost: evaluation list upload", ce);
     // persistent warps pulling tickets in wavefront order: every ticket's dependencies hold smaller tickets, so a waiting
-    // warp only ever waits for warps that are already running (no co-residency assumption beyond one CTA per SM slot)
-    const int blocks = min((ctx->la_n + 3) / 4, ctx->sm_count * 2);
-    lowres_cost_kernel<<<blocks, 128, 0, ctx->stream>>>(a);
+    // warp only ever waits for warps that are already running.  A diagonal of one wavefront holds at most ~W/2 blocks; twice
+    // that many warps per evaluation keep the next diagonals prefetching while leaving the rest of the GPU to other kernels.
+    const int blocks = min((ctx->la_n * n_evals + 3) / 4, min(max(8, (W + 3) / 4) * n_evals, ctx->sm_count * 4));
+    lowres_cost_kernel<<<blocks, 128, 0, ctx->stream>>>(d_evals, n_evals, d_ticket, ctx->la_n);
     LAUNCH_CHECK(ctx, "lowres_cost_kernel");
-    int sums[8];
-    CUDA_TRY(ctx, cudaMemcpyAsync(sums, ctx->d_la_sums, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    result->score = sums[0]; result->intra_mbs = sums[1]; result->intra_cost_sum = sums[2]; result->reserved = 0;
+    int *sums = (int *)malloc((size_t)n_evals * 8 * sizeof(int));
+    ce = cudaMemcpyAsync(sums, ctx->d_la_sums, (size_t)n_evals * 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess)
+        for (int e = 0; e < n_evals; e++) { results[e].score = sums[8 * e]; results[e].intra_mbs = sums[8 * e + 1]; results[e].intra_cost_sum = sums[8 * e + 2]; results[e].reserved = 0; }
+    free(sums);
+    if (ce != cudaSuccess) return x264_cuda_fail(ctx, "lowres_frame_cost", ce);
     return 0;
+}
+
+extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
+                                           const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *pm, x264_cuda_lowres_result_t *result)
+{
+    return x264_cuda_lowres_frame_cost_batch(ctx, 1, &fenc, &fref0, &fref1, pm, result);
 }
