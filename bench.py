@@ -539,6 +539,17 @@ def run_rows(args):
           lambda: ctx.check(L.x264_cuda_residual_inter(ctx.h, fenc.h, fdec.h, p_rj.data_ptr(), n_mb, p_coef.data_ptr())), reps=3)
     timed("f1 deblocking", lambda: ctx.frame_deblock(fdec, dinfo), reps=3)
     timed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)), reps=3)
+    # candidate grids for the sequential-predictor use (host replay): all 9 partitions x 33 x 36 vectors per macroblock
+    gj = np.zeros(n_mb, pkg.GRID_JOB)
+    gj["mb_x"], gj["mb_y"], gj["part_mask"] = rj["mb_x"], rj["mb_y"], 511
+    gj["mv_min_fpel"], gj["mv_max_fpel"] = jobs["mv_min_fpel"][0::9], jobs["mv_max_fpel"][0::9]
+    gj["cx"] = np.clip(-5, gj["mv_min_fpel"][:, 0], gj["mv_max_fpel"][:, 0]); gj["cy"] = np.clip(-3, gj["mv_min_fpel"][:, 1], gj["mv_max_fpel"][:, 1])
+    d_gj = torch.from_numpy(gj.view(np.uint8).reshape(-1).copy()).cuda()
+    grid_bytes = n_mb * 9 * pkg.grid_w(ME_RANGE) * pkg.grid_h(ME_RANGE) * 2
+    d_grid = torch.empty(grid_bytes, dtype=torch.uint8, device="cuda")
+    timed("a1 SAD candidate grids, radius 16: 9 x 33 x 36 SADs per MB, %d MB written, device-resident" % (grid_bytes // 1000000),
+          lambda: ctx.check(L.x264_cuda_sad_grid_dev(ctx.h, fenc.h, fref.h, ME_RANGE, d_gj.data_ptr(), n_mb, d_grid.data_ptr())))
+    del d_grid
     p_ssd, p_sums, p_en, p_had = pinned_out(8), pinned_out((H // 4) * (W // 4) * 16), pinned_out(n_mb * 4), pinned_out(n_mb * 8)
     timed("f2 SSD + SSIM sums + AQ energies + hadamard_ac",
           lambda: (ctx.check(L.x264_cuda_frame_ssd(ctx.h, fenc.h, fref.h, pkg.PLANE_FULL, 0, 0, W, H, p_ssd.data_ptr())),

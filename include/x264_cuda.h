@@ -166,6 +166,36 @@ X264_CUDA_API int x264_cuda_me_search_dev(x264_cuda_t *ctx, const x264_cuda_fram
 X264_CUDA_API void x264_cuda_me_finish(const x264_cuda_me_job_t *job, const x264_cuda_me_result_t *res,
                                        const int16_t *cost_table, int mv_max_spel_y, int16_t mv[2], int *cost, int *cost_mv);
 
+/* ------------------------------------------------------------------ candidate grids + host replay ---- */
+/* For callers that only learn a block's predictors sequentially (mvp depends on the neighbours' final vectors, S/encoder/analyse.c):
+ * the device writes out the SAD of all nine inter partitions of a macroblock at every integer vector of a window around a centre
+ * the caller guesses (e.g. the lowres lookahead's vector), and x264_cuda_host_esa_replay then runs x264_me_search_ref's predictor
+ * stage and ESA loop (S/encoder/me.c:182-229, :449-492) on that grid with the exact mvp — same vectors, same costs.
+ *   grid[job][part 0..8][j][i] (uint16) = x264_pixel_sad_<part>( fenc block, fref block at mv (cx - radius + i, cy - radius + j) ),
+ *   i < X264_CUDA_GRID_W(radius), j < X264_CUDA_GRID_H(radius); 0xffff outside [mv_min_fpel, mv_max_fpel] (plus the 3 columns
+ *   beyond mv_max_fpel[0] that the ESA loop's width rounding tests, me.c:456-457) or for masked partitions.
+ * Partition order as in x264_cuda_me_mb_job_t: 16x16 | 16x8 top,bottom | 8x16 left,right | 8x8 TL,TR,BL,BR. */
+#define X264_CUDA_GRID_W(radius) ((2 * (radius) + 1 + 3) & ~3)
+#define X264_CUDA_GRID_H(radius) (2 * (radius) + 1)
+typedef struct x264_cuda_grid_job_t {
+    int16_t mb_x, mb_y;
+    int16_t cx, cy;                          /* grid centre, full-pel */
+    int16_t mv_min_fpel[2], mv_max_fpel[2];  /* h->mb.mv_{min,max}_fpel */
+    uint16_t part_mask;                      /* bit p: partition p wanted */
+    uint16_t reserved;
+} x264_cuda_grid_job_t;                      /* 20 bytes */
+X264_CUDA_API int x264_cuda_sad_grid(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                     const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid);
+X264_CUDA_API int x264_cuda_sad_grid_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                         const void *d_jobs, int n_jobs, void *d_grid);
+/* Host side, no device involved: the full-pel part of x264_me_search_ref for --me esa on one partition's grid plane
+ * (grid_part = grid + (job_index * 9 + part) * GW * GH).  job carries mvp, mvc[], i_mvc, qp limits exactly as for
+ * x264_cuda_me_search (bx/by are not used); cost_table = p_cost_mv of the qp (x264_cuda_host_cost_mv).  Returns 0 and fills res
+ * (bmx, bmy, bcost, seed_*), or 1 when a vector the search must test lies outside the grid (then enlarge the radius or fall back
+ * to x264_cuda_me_search for that block). */
+X264_CUDA_API int x264_cuda_host_esa_replay(const uint16_t *grid_part, int radius, int cx, int cy, const x264_cuda_me_job_t *job, int me_range,
+                                            const int16_t *cost_table, x264_cuda_me_result_t *res);
+
 /* ------------------------------------------------------------------ iterative + sub-pel search -------- */
 /* One job == one complete x264_me_search_ref() (S/encoder/me.c:156-631) for the small iterative methods, or the tail
  * of one for ESA/TESA:

@@ -33,6 +33,19 @@ ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1")
                    ("mvp", "<i2", (2,)), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
                    ("seed_mv", "<i2", (2,)), ("seed_cost", "<i4"), ("mvc", "<i2", (ME_MAX_MVC, 2)),
                    ("mv_min_spel", "<i2", (2,)), ("mv_max_spel", "<i2", (2,))], align=True)
+GRID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("cx", "<i2"), ("cy", "<i2"), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
+                     ("part_mask", "<u2"), ("reserved", "<u2")])
+assert GRID_JOB.itemsize == 20
+
+
+def grid_w(radius):
+    return (2 * radius + 1 + 3) & ~3
+
+
+def grid_h(radius):
+    return 2 * radius + 1
+
+
 ME_FINAL = np.dtype([("mv", "<i2", (2,)), ("cost", "<i4"), ("cost_mv", "<i4"), ("bmx", "<i2"), ("bmy", "<i2")], align=True)
 ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_TESA, ME_METHOD_SEEDED = 0, 1, 4, 8
 ME_MBCMP_SATD = 8
@@ -103,6 +116,11 @@ def lib():
         L.x264_cuda_me_search_small_dev.argtypes = [vp, vp, vp, ip, ip, ip, vp, ip, vp]
         L.x264_cuda_block_cmp.argtypes = [vp, ip, ip, ip, vp, vp, vp]
         L.x264_cuda_me_search_mb_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_me_finish.argtypes = [vp, vp, vp, ip, vp, vp, vp]
+        L.x264_cuda_me_finish.restype = None
+        L.x264_cuda_sad_grid.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_sad_grid_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
+        L.x264_cuda_host_esa_replay.argtypes = [vp, ip, ip, ip, vp, ip, vp, vp]
         L.x264_cuda_frame_lookahead_alloc.argtypes = [vp, vp, ip]
         L.x264_cuda_frame_lookahead_get.argtypes = [vp, vp, ip, ip, vp, vp, vp]
         L.x264_cuda_frame_lookahead_set.argtypes = [vp, vp, ip, ip, vp, vp, vp]
@@ -128,6 +146,15 @@ def lib():
 
 class CudaError(RuntimeError):
     pass
+
+
+def host_esa_replay(grid_part, radius, cx, cy, job, me_range, cost_table):
+    """x264_me_search_ref's predictor stage + ESA loop on one partition's grid plane -> ME_RESULT record or None (outside grid)"""
+    res = np.zeros(1, ME_RESULT)
+    j = np.ascontiguousarray(job)
+    gp = np.ascontiguousarray(grid_part)
+    rc = lib().x264_cuda_host_esa_replay(gp.ctypes.data, radius, cx, cy, j.ctypes.data, me_range, cost_table.ctypes.data, res.ctypes.data)
+    return res[0] if rc == 0 else None
 
 
 def host_aq(energy, aq_strength=1.0):
@@ -377,6 +404,13 @@ class Context:
         res = np.zeros((n, 4), np.int32)
         self.check(lib().x264_cuda_lowres_frame_cost_batch(self.h, n, ptrs[0], ptrs[1], ptrs[2], pm.ctypes.data, res.ctypes.data))
         return [(int(r[0]), int(r[1]), int(r[2])) for r in res]
+
+    def sad_grid(self, fenc, fref, radius, jobs):
+        """-> uint16 [n_jobs, 9, GH, GW]: SAD of every partition at every integer vector of the window (0xffff = not available)"""
+        assert jobs.dtype == GRID_JOB
+        out = np.zeros((len(jobs), 9, grid_h(radius), grid_w(radius)), np.uint16)
+        self.check(lib().x264_cuda_sad_grid(self.h, fenc.h, fref.h, radius, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
 
     def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):
         self.check(lib().x264_cuda_me_search_mb_dev(self.h, fenc.h, fref.h, me_range, d_jobs, n, d_results))

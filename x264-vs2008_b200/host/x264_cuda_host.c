@@ -144,3 +144,55 @@ void x264_cuda_host_aq(const uint32_t *energy, int n_mb, float aq_strength, floa
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * x264_me_search_ref, predictor stage + ESA loop (S/encoder/me.c:182-229, :449-492), replayed on a SAD grid produced by
+ * x264_cuda_sad_grid.  Pure host arithmetic in the reference's order: strict '<', candidates in mvc order, raster scan. */
+static inline int clip3_i(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+int x264_cuda_host_esa_replay(const uint16_t *gp, int radius, int cx, int cy, const x264_cuda_me_job_t *job, int me_range, const int16_t *cost_table,
+                              x264_cuda_me_result_t *res)
+{
+    const int GW = X264_CUDA_GRID_W(radius), GH = X264_CUDA_GRID_H(radius), gx0 = cx - radius, gy0 = cy - radius;
+    const int16_t *cmx = cost_table + 2 * 4 * 2048 - job->mvp[0], *cmy = cost_table + 2 * 4 * 2048 - job->mvp[1];
+    const int x_min = job->mv_min_fpel[0], y_min = job->mv_min_fpel[1], x_max = job->mv_max_fpel[0], y_max = job->mv_max_fpel[1];
+#define GRID_SAD(mx, my, v) do { const int i_ = (mx) - gx0, j_ = (my) - gy0; if (i_ < 0 || i_ >= GW || j_ < 0 || j_ >= GH) return 1; \
+                                 (v) = gp[j_ * GW + i_]; if ((v) == 0xffff) return 1; } while (0)
+    int bmx = clip3_i(job->mvp[0], x_min * 4, x_max * 4), bmy = clip3_i(job->mvp[1], y_min * 4, y_max * 4);
+    const int pmx = (bmx + 2) >> 2, pmy = (bmy + 2) >> 2;
+    int bcost, v;
+    bmx = pmx; bmy = pmy;
+    GRID_SAD(pmx, pmy, v);
+    bcost = v;                                   /* the prediction itself carries no mv cost (me.c:207) */
+    const int n_mvc = job->i_mvc < 12 ? job->i_mvc : 12;
+    for (int i = 0; i < n_mvc; i++) {            /* me.c:209-222 */
+        const int mx0 = (job->mvc[i][0] + 2) >> 2, my0 = (job->mvc[i][1] + 2) >> 2;
+        if ((mx0 | my0) && (mx0 != pmx || my0 != pmy)) {
+            const int mx = clip3_i(mx0, x_min, x_max), my = clip3_i(my0, y_min, y_max);
+            GRID_SAD(mx, my, v);
+            const int c = v + cmx[mx << 2] + cmy[my << 2];
+            if (c < bcost) { bcost = c; bmx = mx; bmy = my; }
+        }
+    }
+    GRID_SAD(0, 0, v);                           /* me.c:224-225: COST_MV( 0, 0 ) */
+    { const int c = v + cmx[0] + cmy[0]; if (c < bcost) { bcost = c; bmx = 0; bmy = 0; } }
+    res->seed_mx = (int16_t)bmx; res->seed_my = (int16_t)bmy; res->seed_cost = bcost;
+    /* me.c:451-457 and the plain-ESA loop :480-489 */
+    const int min_x = bmx - me_range > x_min ? bmx - me_range : x_min, min_y = bmy - me_range > y_min ? bmy - me_range : y_min;
+    const int max_x = bmx + me_range < x_max ? bmx + me_range : x_max, max_y = bmy + me_range < y_max ? bmy + me_range : y_max;
+    const int width = (max_x - min_x + 3) & ~3;
+    if (min_x < gx0 || min_x + width > gx0 + GW || min_y < gy0 || max_y >= gy0 + GH) return 1;
+    for (int my = min_y; my <= max_y; my++) {
+        const uint16_t *row = gp + (my - gy0) * GW - gx0;
+        const int cy_ = cmy[my << 2];
+        for (int mx = min_x; mx < min_x + width; mx++) {
+            /* the reference also evaluates the up-to-3 columns beyond max_x that the width rounding adds (they are inside the
+             * padded plane); the grid holds 0xffff for vectors beyond the MV limits: report "outside" rather than guess */
+            if (row[mx] == 0xffff) return 1;
+            const int c = row[mx] + cmx[mx << 2] + cy_;
+            if (c < bcost) { bcost = c; bmx = mx; bmy = my; }
+        }
+    }
+#undef GRID_SAD
+    res->bmx = (int16_t)bmx; res->bmy = (int16_t)bmy; res->bcost = bcost;
+    return 0;
+}
