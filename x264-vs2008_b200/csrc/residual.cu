@@ -164,6 +164,9 @@ __device__ __forceinline__ void store4x4(uint8_t *p, int stride, const int (&v)[
                                                 ((uint32_t)v[y * 4 + 3] << 24);
 }
 
+// ALLOW8 = false is the variant for batches without 8x8-transform macroblocks: without the 64-coefficient path it needs half the
+// registers, i.e. twice the resident warps for a kernel that is bound by instruction latency
+template <bool ALLOW8>
 __global__ void __launch_bounds__(128) residual_inter_kernel(const QuantTables *__restrict__ qt, FrameRefs fr,
                                                              const x264_cuda_resid_job_t *__restrict__ jobs, int n_jobs,
                                                              x264_cuda_mb_coeffs_t *__restrict__ outs)
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(128) residual_inter_kernel(const QuantTables *
     const x264_cuda_resid_job_t job = jobs[jb];
     x264_cuda_mb_coeffs_t *out = outs + jb;
     const int qp = min((int)job.qp, 51), cqp = min((int)job.chroma_qp, 51);
-    const bool dct8 = job.flags & X264_CUDA_RESID_8x8DCT, decim = job.flags & X264_CUDA_RESID_DECIMATE;
+    const bool dct8 = ALLOW8 && (job.flags & X264_CUDA_RESID_8x8DCT), decim = job.flags & X264_CUDA_RESID_DECIMATE;
     const unsigned FULL = 0xffffffffu;
 
     // zero the coefficient record first (uncoded blocks read as zero, like a cleared h->dct)
@@ -493,8 +496,13 @@ extern "C" int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_fr
     }
     FrameRefs fr = { fenc->plane[0], fenc->chroma[0], fenc->chroma[1], fdec->plane[0], fdec->chroma[0], fdec->chroma[1], fenc->g.stride,
                      fenc->stride_c };
-    residual_inter_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_qt, fr, (const x264_cuda_resid_job_t *)d_jobs, n_jobs,
-                                                                     (x264_cuda_mb_coeffs_t *)d_coeffs);
+    if (ctx->resid_no_dct8)
+        residual_inter_kernel<false><<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_qt, fr, (const x264_cuda_resid_job_t *)d_jobs, n_jobs,
+                                                                                (x264_cuda_mb_coeffs_t *)d_coeffs);
+    else
+        residual_inter_kernel<true><<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_qt, fr, (const x264_cuda_resid_job_t *)d_jobs, n_jobs,
+                                                                               (x264_cuda_mb_coeffs_t *)d_coeffs);
+    ctx->resid_no_dct8 = 0;
     LAUNCH_CHECK(ctx, "residual_inter_kernel");
     return 0;
 }
@@ -509,6 +517,9 @@ extern "C" int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_
     if (x264_cuda_stage(ctx, jb_al + rb, jb_al + rb)) return -1;
     uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
     if (x264_cuda_jobs_in(ctx, ds, jobs, hs, jb)) return -1;
+    int any8 = 0; // the job list is host memory here: pick the leaner kernel when no macroblock uses the 8x8 transform
+    for (int i = 0; i < n_jobs && !any8; i++) any8 = jobs[i].flags & X264_CUDA_RESID_8x8DCT;
+    ctx->resid_no_dct8 = !any8;
     if (x264_cuda_residual_inter_dev(ctx, fenc, fdec, ds, n_jobs, ds + jb_al)) return -1;
     if (x264_cuda_results_out(ctx, coeffs, ds + jb_al, hs + jb_al, rb)) return -1;
     return 0;
