@@ -330,6 +330,20 @@ X264_CUDA_API int x264_cuda_mc_blocks(x264_cuda_t *ctx, const x264_cuda_frame_t 
                                       const x264_cuda_mc_job_t *jobs, int n_jobs);
 X264_CUDA_API int x264_cuda_mc_blocks_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec,
                                           const void *d_jobs, int n_jobs);
+/* Bi-predicted blocks, x264_mb_mc_01xywh (S/common/macroblock.c:508-546): the two lists' predictions (luma qpel fetch and chroma
+ * mc_chroma from fref0 with mv0, from fref1 with mv1) blended by h->mc.avg (S/common/mc.c:52-125): weight 32 = rounded average,
+ * otherwise implicit weighted bi-prediction with weight = h->mb.bipred_weight[ref0][ref1]. */
+typedef struct x264_cuda_mc_bi_job_t {
+    int16_t bx, by;       /* luma position */
+    int16_t mv0[2], mv1[2];
+    uint8_t w, h;         /* luma size: 4, 8 or 16 */
+    uint8_t weight;       /* 32: plain average */
+    uint8_t reserved;
+} x264_cuda_mc_bi_job_t; /* 16 bytes */
+X264_CUDA_API int x264_cuda_mc_blocks_bi(x264_cuda_t *ctx, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1, x264_cuda_frame_t *fdec,
+                                         const x264_cuda_mc_bi_job_t *jobs, int n_jobs);
+X264_CUDA_API int x264_cuda_mc_blocks_bi_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1,
+                                             x264_cuda_frame_t *fdec, const void *d_jobs, int n_jobs);
 
 /* ------------------------------------------------------------------ transform / quantisation --------- */
 /* Quantiser tables exactly as x264_cqm_init leaves them in x264_t (S/common/set.c:68-174, S/common/common.h:294-304):

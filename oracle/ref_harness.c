@@ -206,6 +206,12 @@ void xo_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int src_stri
     g_mc.mc_chroma(dst, dst_stride, (uint8_t *)src, src_stride, mvx, mvy, w, hgt);
 }
 
+void xo_pixel_avg(int i_pixel, uint8_t *dst, int dst_stride, const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int weight)
+{
+    tables();
+    g_mc.avg[i_pixel](dst, dst_stride, (uint8_t *)a, a_stride, (uint8_t *)b, b_stride, weight);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 static void run_search_c(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref[4], const uint16_t *integral,
                          const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)

@@ -74,6 +74,9 @@ void xo_frame_init_lowres(const xo_geom *g, uint8_t *plane, uint8_t *l0, uint8_t
 void xo_mc_luma(uint8_t *dst, int dst_stride, const uint8_t *const src[4], int src_stride, int mvx, int mvy, int w, int h);
 /* S/common/mc.c:205-236 */
 void xo_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride, int mvx, int mvy, int w, int h);
+/* h->mc.avg[i_pixel] (S/common/mc.c:52-125): dst = (a + b + 1) >> 1 when weight == 32, else the implicit-weighted-bipred blend
+ * clip((a*weight + b*(64-weight) + 32) >> 6); i_pixel: XO_16x16 .. XO_4x4 and 7..9 for 4x2, 2x4, 2x2 (mc.avg has ten entries) */
+void xo_pixel_avg(int i_pixel, uint8_t *dst, int dst_stride, const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int weight);
 
 /* ---------------- full-pel motion search: S/encoder/me.c:156-631 with i_subpel_refine = 1 ----------------
  * One call == one x264_me_search_ref() on a block, stopping before sub-pel refinement.

@@ -184,3 +184,17 @@ void xo_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int src_stri
         for (int x = 0; x < w; x++)
             dst[x] = (cA * src[x] + cB * src[x + 1] + cC * src[x + src_stride] + cD * src[x + src_stride + 1] + 32) >> 6;
 }
+
+
+/* mc.c:52-125 (PIXEL_AVG_C over pixel_avg_wxh / pixel_avg_weight_wxh) */
+void xo_pixel_avg(int i_pixel, uint8_t *dst, int dst_stride, const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int weight)
+{
+    static const int ws[10] = { 16, 16, 8, 8, 8, 4, 4, 4, 2, 2 }, hs[10] = { 16, 8, 16, 8, 4, 8, 4, 2, 4, 2 };
+    const int w = ws[i_pixel], h = hs[i_pixel];
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int p = a[y * a_stride + x], q = b[y * b_stride + x];
+            int v = weight == 32 ? (p + q + 1) >> 1 : (p * weight + q * (64 - weight) + 32) >> 6;
+            dst[y * dst_stride + x] = v < 0 ? 0 : v > 255 ? 255 : v;
+        }
+}

@@ -250,3 +250,18 @@ def test_aq_tables_all_energies(pkg, port, ref):
         port.lib.xo_aq_from_energy(e.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint32)), len(e), __import__("ctypes").c_float(strength),
                                    q2.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)), X._ptr(i2, X.u16p))
         assert np.array_equal(q, q2) and np.array_equal(i, i2)
+
+
+def test_pixel_avg(port, ref):
+    """h->mc.avg[10] (mc.c:52-125): rounded average and implicit weighted bi-prediction, incl. weights that clip"""
+    rng = np.random.default_rng(12)
+    for ip in range(10):
+        for weight in (32, 21, 43, 0, 64, 11, 53, -20, 84):
+            a = rng.integers(0, 256, (16, 16), dtype=np.uint8)
+            b = rng.integers(0, 256, (16, 16), dtype=np.uint8)
+            if weight in (-20, 84):
+                a[:4], b[:4] = 255, 0
+            d1, d2 = np.zeros((16, 16), np.uint8), np.zeros((16, 16), np.uint8)
+            port.lib.xo_pixel_avg(ip, X._ptr(d1), 16, X._ptr(a), 16, X._ptr(b), 16, weight)
+            ref.lib.xo_pixel_avg(ip, X._ptr(d2), 16, X._ptr(a), 16, X._ptr(b), 16, weight)
+            assert np.array_equal(d1, d2), (ip, weight)

@@ -92,6 +92,7 @@ class Oracle:
         L.xo_frame_init_lowres.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, u8p, u8p]
         L.xo_mc_luma.argtypes = [u8p, C.c_int, C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.xo_mc_chroma.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.xo_pixel_avg.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int]
         L.xo_me_search_fpel.argtypes = [C.POINTER(Geom), u8p, u8p, u16p, C.POINTER(MeIn), C.POINTER(MeOut)]
         L.xo_me_search_fpel_batch.argtypes = [C.POINTER(Geom), u8p, u8p, u16p, C.POINTER(MeIn), C.c_int, C.POINTER(MeOut)]
         L.xo_me_search_subpel.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), u16p, C.POINTER(MeIn), C.c_int,

@@ -33,6 +33,9 @@ ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1")
                    ("mvp", "<i2", (2,)), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
                    ("seed_mv", "<i2", (2,)), ("seed_cost", "<i4"), ("mvc", "<i2", (ME_MAX_MVC, 2)),
                    ("mv_min_spel", "<i2", (2,)), ("mv_max_spel", "<i2", (2,))], align=True)
+MC_BI_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("mv0", "<i2", (2,)), ("mv1", "<i2", (2,)), ("w", "u1"), ("h", "u1"), ("weight", "u1"),
+                      ("reserved", "u1")])
+assert MC_BI_JOB.itemsize == 16
 GRID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("cx", "<i2"), ("cy", "<i2"), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
                      ("part_mask", "<u2"), ("reserved", "<u2")])
 assert GRID_JOB.itemsize == 20
@@ -98,6 +101,8 @@ def lib():
         L.x264_cuda_set_quant_preset.argtypes = [vp, ip]
         L.x264_cuda_mc_blocks.argtypes = [vp, vp, vp, vp, ip]
         L.x264_cuda_mc_blocks_dev.argtypes = [vp, vp, vp, vp, ip]
+        L.x264_cuda_mc_blocks_bi.argtypes = [vp, vp, vp, vp, vp, ip]
+        L.x264_cuda_mc_blocks_bi_dev.argtypes = [vp, vp, vp, vp, vp, ip]
         L.x264_cuda_block_residual.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_block_dc.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_residual_inter.argtypes = [vp, vp, vp, vp, ip, vp]
@@ -300,6 +305,10 @@ class Context:
     def mc_blocks(self, fref, fdec, jobs):
         jobs = np.ascontiguousarray(jobs, MC_JOB)
         self.check(lib().x264_cuda_mc_blocks(self.h, fref.h, fdec.h, jobs.ctypes.data, len(jobs)))
+
+    def mc_blocks_bi(self, fref0, fref1, fdec, jobs):
+        assert jobs.dtype == MC_BI_JOB
+        self.check(lib().x264_cuda_mc_blocks_bi(self.h, fref0.h, fref1.h, fdec.h, jobs.ctypes.data, len(jobs)))
 
     def set_quant_preset(self, cqm):
         self.check(lib().x264_cuda_set_quant_preset(self.h, cqm))

@@ -44,7 +44,104 @@ __global__ void __launch_bounds__(128) mc_blocks_kernel(McPlanes pl, const x264_
     }
 }
 
+// x264_mb_mc_01xywh (S/common/macroblock.c:508-546): both lists' predictions blended by h->mc.avg — the rounded average when
+// weight == 32, else implicit weighted bi-prediction clip((a*w + b*(64-w) + 32) >> 6) (mc.c:52-125)
+__device__ __forceinline__ uint32_t blend4(uint32_t a, uint32_t b, int weight)
+{
+    if (weight == 32) return __vavgu4(a, b);
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int p = (a >> (8 * k)) & 255, q = (b >> (8 * k)) & 255;
+        r |= (uint32_t)clip_u8((p * weight + q * (64 - weight) + 32) >> 6) << (8 * k);
+    }
+    return r;
+}
+
+struct McBiPlanes {
+    const uint8_t *ref[2][4]; const uint8_t *ref_cb[2], *ref_cr[2];
+    uint8_t *dst, *dst_cb, *dst_cr;
+    int stride, stride_c;
+};
+
+__global__ void __launch_bounds__(128) mc_blocks_bi_kernel(McBiPlanes pl, const x264_cuda_mc_bi_job_t *__restrict__ jobs, int n_jobs, int do_chroma)
+{
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_jobs) return;
+    const x264_cuda_mc_bi_job_t job = jobs[j];
+    const int w = job.w, h = job.h, weight = job.weight;
+    {
+        const size_t off = (size_t)job.by * pl.stride + job.bx;
+        const uint8_t *const p0[4] = { pl.ref[0][0] + off, pl.ref[0][1] + off, pl.ref[0][2] + off, pl.ref[0][3] + off };
+        const uint8_t *const p1[4] = { pl.ref[1][0] + off, pl.ref[1][1] + off, pl.ref[1][2] + off, pl.ref[1][3] + off };
+        const QpelSrc s0 = qpel_src(p0, pl.stride, job.mv0[0], job.mv0[1]), s1 = qpel_src(p1, pl.stride, job.mv1[0], job.mv1[1]);
+        const int wpr = w >> 2;
+        for (int i = lane; i < wpr * h; i += 32) {
+            const int y = i / wpr, x = (i - y * wpr) * 4;
+            const ptrdiff_t o = (ptrdiff_t)y * pl.stride + x;
+            *(uint32_t *)(pl.dst + off + o) = blend4(qpel_row4(s0, o), qpel_row4(s1, o), weight);
+        }
+    }
+    if (do_chroma) {
+        const int cw = w >> 1, ch = h >> 1;
+        const size_t off = (size_t)(job.by >> 1) * pl.stride_c + (job.bx >> 1);
+        int cA[2], cB[2], cC[2], cD[2];
+        ptrdiff_t so[2];
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+            const int mvx = l ? job.mv1[0] : job.mv0[0], mvy = l ? job.mv1[1] : job.mv0[1];
+            const int d8x = mvx & 7, d8y = mvy & 7;
+            cA[l] = (8 - d8x) * (8 - d8y); cB[l] = d8x * (8 - d8y); cC[l] = (8 - d8x) * d8y; cD[l] = d8x * d8y;
+            so[l] = (ptrdiff_t)(mvy >> 3) * pl.stride_c + (mvx >> 3);
+        }
+        for (int i = lane; i < 2 * cw * ch; i += 32) {
+            const int p = i / (cw * ch), k = i - p * cw * ch, y = k / cw, x = k - y * cw;
+            int v[2];
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                const uint8_t *s = (p ? pl.ref_cr[l] : pl.ref_cb[l]) + off + so[l] + (ptrdiff_t)y * pl.stride_c + x;
+                v[l] = (cA[l] * s[0] + cB[l] * s[1] + cC[l] * s[pl.stride_c] + cD[l] * s[pl.stride_c + 1] + 32) >> 6;
+            }
+            uint8_t *d = (p ? pl.dst_cr : pl.dst_cb) + off + (size_t)y * pl.stride_c + x;
+            *d = (uint8_t)(weight == 32 ? (v[0] + v[1] + 1) >> 1 : clip_u8((v[0] * weight + v[1] * (64 - weight) + 32) >> 6));
+        }
+    }
+}
+
 } // namespace
+
+extern "C" int x264_cuda_mc_blocks_bi_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1, x264_cuda_frame_t *fdec,
+                                          const void *d_jobs, int n_jobs)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    if (!(fref0->g.flags & fref1->g.flags & X264_CUDA_FRAME_HPEL) || fref0->g.stride != fdec->g.stride || fref1->g.stride != fdec->g.stride) {
+        snprintf(ctx->err, 256, "x264_cuda_mc_blocks_bi: both references need the half-pel planes and the same geometry as fdec");
+        return -1;
+    }
+    const int do_chroma = fref0->buf_chroma && fref1->buf_chroma && fdec->buf_chroma;
+    McBiPlanes pl;
+    for (int k = 0; k < 4; k++) { pl.ref[0][k] = fref0->plane[k]; pl.ref[1][k] = fref1->plane[k]; }
+    pl.ref_cb[0] = fref0->chroma[0]; pl.ref_cr[0] = fref0->chroma[1]; pl.ref_cb[1] = fref1->chroma[0]; pl.ref_cr[1] = fref1->chroma[1];
+    pl.dst = fdec->plane[0]; pl.dst_cb = fdec->chroma[0]; pl.dst_cr = fdec->chroma[1]; pl.stride = fdec->g.stride; pl.stride_c = fdec->stride_c;
+    mc_blocks_bi_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(pl, (const x264_cuda_mc_bi_job_t *)d_jobs, n_jobs, do_chroma);
+    LAUNCH_CHECK(ctx, "mc_blocks_bi_kernel");
+    return 0;
+}
+
+extern "C" int x264_cuda_mc_blocks_bi(x264_cuda_t *ctx, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1, x264_cuda_frame_t *fdec,
+                                      const x264_cuda_mc_bi_job_t *jobs, int n_jobs)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_mc_bi_job_t);
+    if (x264_cuda_stage(ctx, jb, jb)) return -1;
+    if (x264_cuda_jobs_in(ctx, ctx->d_stage, jobs, ctx->h_stage, jb)) return -1;
+    if (x264_cuda_mc_blocks_bi_dev(ctx, fref0, fref1, fdec, ctx->d_stage, n_jobs)) return -1;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 extern "C" int x264_cuda_mc_blocks_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec, const void *d_jobs, int n_jobs)
 {
