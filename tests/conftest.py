@@ -40,3 +40,18 @@ def ctx(pkg):
     c = pkg.Context(0)  # raises (loudly) when there is no GPU: no CPU fallback exists
     yield c
     c.close()
+
+
+# Soak runs: X264_TEST_SEED_OFFSET=k shifts every seeded generator used by the differential tests (job lists, macroblock state,
+# synthetic clips), so the same suite exercises fresh inputs:  for k in 1 2 3; do X264_TEST_SEED_OFFSET=$k pytest -m gpu; done
+# Use it with -m gpu only: the not-gpu suite compares against committed golden vectors and spawns unpatched worker processes.
+_SEED_OFFSET = int(os.environ.get("X264_TEST_SEED_OFFSET", "0"))
+if _SEED_OFFSET:
+    import numpy as _np
+    _orig_rng = _np.random.default_rng
+
+    def _shifted_rng(seed=None, *a, **k):
+        if isinstance(seed, (int, _np.integer)):
+            seed = int(seed) + 7919 * _SEED_OFFSET
+        return _orig_rng(seed, *a, **k)
+    _np.random.default_rng = _shifted_rng
