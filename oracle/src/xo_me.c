@@ -109,7 +109,8 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
                     const uint16_t *integral, const xo_me_in *in, const me_sub *sub, xo_me_out *out)
 {
     me_ctx cx, *c = &cx;
-    const int stride = g->stride > 0 ? g->stride : -g->stride, range = in->me_range; /* negative: explicit stride (lowres) */
+    const int stride = g->stride > 0 ? g->stride : -g->stride; /* negative: explicit stride (lowres) */
+    int range = in->me_range;                                     /* UMH adapts it (me.c:354-399) */
     const int x_min = in->mv_min_fpel[0], y_min = in->mv_min_fpel[1];
     const int x_max = in->mv_max_fpel[0], y_max = in->mv_max_fpel[1];
     const int16_t *tab = cost_table(in->qp);
@@ -189,7 +190,78 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
         } while (++i < range);
         break;
     }
-    case XO_ME_HEX: { /* me.c:246-305 (the de-duplicated form) */
+    case XO_ME_UMH: { /* me.c:306-447: uneven-cross multi-hexagon-grid search */
+        static const int shift[7] = { 0, 1, 1, 2, 3, 3, 4 }; /* x264_pixel_size_shift */
+#define SAD_THRESH(v) (bcost < ((v) >> shift[in->i_pixel]))
+#define DIA1(cx_, cy_) do { omx = (cx_); omy = (cy_); TRY_FPEL(omx, omy - 1); TRY_FPEL(omx, omy + 1); TRY_FPEL(omx - 1, omy); TRY_FPEL(omx + 1, omy); } while (0)
+#define X4(a0, b0, a1, b1, a2, b2, a3, b3) do { TRY_FPEL(omx + (a0), omy + (b0)); TRY_FPEL(omx + (a1), omy + (b1)); \
+                                                 TRY_FPEL(omx + (a2), omy + (b2)); TRY_FPEL(omx + (a3), omy + (b3)); } while (0)
+        /* CROSS (me.c:128-154): +-i along x for i = start, start+2, ... < x_max, then along y; the unchecked COST_MV_X4 form is
+         * only used when every candidate is inside the limits, so one range-checked loop is the same thing */
+#define CROSS(start_, xm_, ym_) do { \
+            for (int i_ = (start_); i_ < (xm_); i_ += 2) { if (omx + i_ <= x_max) TRY_FPEL(omx + i_, omy); if (omx - i_ >= x_min) TRY_FPEL(omx - i_, omy); } \
+            for (int i_ = (start_); i_ < (ym_); i_ += 2) { if (omy + i_ <= y_max) TRY_FPEL(omx, omy + i_); if (omy - i_ >= y_min) TRY_FPEL(omx, omy - i_); } } while (0)
+        int omx, omy, ucost1, ucost2, cross_start = 1;
+        ucost1 = bcost;
+        DIA1(pmx, pmy);
+        if (pmx | pmy) DIA1(0, 0);
+        if (in->i_pixel == XO_4x4) goto me_hex2;
+        ucost2 = bcost;
+        if ((bmx | bmy) && ((bmx - pmx) | (bmy - pmy))) DIA1(bmx, bmy);
+        if (bcost == ucost2) cross_start = 3;
+        omx = bmx; omy = bmy;
+        if (bcost == ucost2 && SAD_THRESH(2000)) { /* early termination */
+            X4(0, -2, -1, -1, 1, -1, -2, 0);
+            X4(2, 0, -1, 1, 1, 1, 0, 2);
+            if (bcost == ucost1 && SAD_THRESH(500)) break;
+            if (bcost == ucost2) {
+                const int r = (range >> 1) | 1;
+                CROSS(3, r, r);
+                X4(-1, -2, 1, -2, -2, -1, 2, -1);
+                X4(-2, 1, 2, 1, -1, 2, 1, 2);
+                if (bcost == ucost2) break;
+                cross_start = r + 2;
+            }
+        }
+        if (in->i_mvc) { /* adaptive search range */
+            static const int range_mul[4][4] = { { 3, 3, 4, 4 }, { 3, 4, 4, 4 }, { 4, 4, 4, 5 }, { 4, 4, 5, 6 } };
+            int mvd, denom = 1;
+            if (in->i_mvc == 1) {
+                if (in->i_pixel == XO_16x16) mvd = 25;
+                else mvd = abs(in->mvp[0] - in->mvc[0][0]) + abs(in->mvp[1] - in->mvc[0][1]);
+            } else {
+                denom = in->i_mvc - 1;
+                mvd = 0;
+                if (in->i_pixel != XO_16x16) { mvd = abs(in->mvp[0] - in->mvc[0][0]) + abs(in->mvp[1] - in->mvc[0][1]); denom++; }
+                for (int k = 0; k < in->i_mvc - 1; k++) /* x264_predictor_difference, common.h:135-145 */
+                    mvd += abs(in->mvc[k][0] - in->mvc[k + 1][0]) + abs(in->mvc[k][1] - in->mvc[k + 1][1]);
+            }
+            const int sad_ctx = SAD_THRESH(1000) ? 0 : SAD_THRESH(2000) ? 1 : SAD_THRESH(4000) ? 2 : 3;
+            const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+            range = range * range_mul[mvd_ctx][sad_ctx] / 4;
+        }
+        CROSS(cross_start, range, range / 2);
+        X4(-2, -2, -2, 2, 2, -2, 2, 2);
+        omx = bmx; omy = bmy;
+        {
+            static const int8_t hex4[16][2] = { { -4, 2 }, { -4, 1 }, { -4, 0 }, { -4, -1 }, { -4, -2 }, { 4, -2 }, { 4, -1 }, { 4, 0 }, { 4, 1 }, { 4, 2 },
+                                                { 2, 3 }, { 0, 4 }, { -2, 3 }, { -2, -3 }, { 0, -4 }, { 2, -3 } };
+            int i = 1;
+            do { /* hexagon grid: the unchecked form is only used when all 16 points are inside the limits */
+                for (int j = 0; j < 16; j++) {
+                    const int mx = omx + hex4[j][0] * i, my = omy + hex4[j][1] * i;
+                    if (IN_RANGE(mx, my)) TRY_FPEL(mx, my);
+                }
+            } while (++i <= range / 4);
+        }
+        if (bmy <= y_max) goto me_hex2;
+        break;
+#undef SAD_THRESH
+#undef DIA1
+#undef X4
+#undef CROSS
+    }
+    case XO_ME_HEX: me_hex2: { /* me.c:246-305 (the de-duplicated form) */
         int costs[6], dir = -2;
         static const int8_t first[6][2] = { { -2, 0 }, { -1, 2 }, { 1, 2 }, { 2, 0 }, { 1, -2 }, { -1, -2 } };
         for (int k = 0; k < 6; k++)

@@ -33,6 +33,25 @@ DEBLOCK_GOLDEN = (("qcif_p", (176, 144), dict()), ("qcif_b", (176, 144), dict(sl
                   ("chaos_b", (96, 80), dict(chaos=True, slice_b=1, cavlc_8x8dct=1, alpha=6, beta=-4, chroma_off=-5)), ("cif_p", (352, 288), dict(qp_centre=34)))
 
 
+def umh_results(o, g, pe, pr, fh, fv, fc, integ):
+    """--me umh on the 160x128 pair: scattered and agreeing predictors, three ranges, full-pel and sub-pel"""
+    res = []
+    for me_range in (16, 24, 8):
+        for spread, centre in ((48, None), (10, (-20, -12))):
+            _, mis = make_me_jobs(pkg, g, seed=900 + me_range + spread, n=80, me_range=me_range, qp=(12, 26, 40), pixels=(0, 1, 2, 3, 4, 5, 6),
+                                  mvp_spread=spread, centre=centre)
+            for i, mi in enumerate(mis):
+                mi.me_method = X.ME_UMH
+                mi.b_sub8x8 = 1
+                if centre is not None and i % 2:
+                    for k in range(mi.i_mvc):
+                        mi.mvc[k][0], mi.mvc[k][1] = mi.mvp[0] + (k % 3) - 1, mi.mvp[1] + (k % 2)
+                for subme in (1, 5):
+                    a = o.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
+                    res.append((me_range, subme, a.mv[0], a.mv[1], a.cost, a.cost_mv))
+    return res
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -100,6 +119,7 @@ def main():
                     o = r.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
                     res.append((method, 10 + subme, o.mv[0], o.mv[1], o.cost, o.cost_mv))
     out["me_results"] = np.array(res, np.int32)
+    out["me_results_umh"] = np.array(umh_results(r, g, pe, pr, fh, fv, fc, integ), np.int32)
     # ---- lowres lookahead schedule (I, P, P dist 2, B, cached) through the reference's x264_rc_analyse_slice
     for tag, (w, h), method, satd, weighted in LOOKAHEAD_GOLDEN:
         g = r.geometry(w, h)

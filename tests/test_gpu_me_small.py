@@ -185,3 +185,32 @@ def test_tesa_many(pkg, ctx, port):
             bad.append((i, mi.i_pixel, got, (o.mv[0], o.mv[1], o.cost, o.cost_mv, o.bmx, o.bmy)))
     assert not bad, (len(bad), bad[:4])
     fenc.close(); fref.close()
+
+
+@pytest.mark.parametrize("me_range", [16, 24, 8])
+@pytest.mark.parametrize("subme", [1, 2, 5])
+def test_umh(pkg, ctx, port, me_range, subme):
+    """--me umh on the device (me.c:306-447): every early-termination path, the adaptive range contexts, the hexagon grid, hex2"""
+    w, h = 320, 192
+    g, fenc, fref, pe, planes = _setup(pkg, ctx, port, w, h, seed=90 + subme)
+    for spread, centre in ((48, None), (10, (-20, -12)), (4, (-20, -12))):
+        jobs, mis = make_me_jobs(pkg, g, seed=700 + me_range + spread, n=400, me_range=me_range, qp=(12, 26, 38), pixels=(0, 1, 2, 3, 4, 5, 6),
+                                 mvp_spread=spread, centre=centre)
+        _fill_spel(jobs, mis)
+        for i, (j, mi) in enumerate(zip(jobs, mis)):
+            mi.me_method = X.ME_UMH
+            if centre is not None and i % 2:  # neighbours agreeing with the predictor: the small-range contexts
+                for k in range(mi.i_mvc):
+                    mi.mvc[k][0], mi.mvc[k][1] = mi.mvp[0] + (k % 3) - 1, mi.mvp[1] + (k % 2)
+                    j["mvc"][k] = [mi.mvc[k][0], mi.mvc[k][1]]
+        jobs["flags"] = pkg.ME_MBCMP_SATD
+        res = ctx.me_search_small(fenc, fref, pkg.ME_METHOD_UMH, me_range, subme, jobs)
+        bad = []
+        for i, mi in enumerate(mis):
+            o = port.me_search_subpel(g, pe, planes, None, mi, subme, 1)
+            got = (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"]), int(res[i]["bmx"]), int(res[i]["bmy"]))
+            want = (o.mv[0], o.mv[1], o.cost, o.cost_mv, o.bmx, o.bmy)
+            if got != want:
+                bad.append((i, mi.i_pixel, got, want))
+        assert not bad, (spread, len(bad), bad[:4])
+    fenc.close(); fref.close()

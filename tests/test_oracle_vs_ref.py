@@ -265,3 +265,28 @@ def test_pixel_avg(port, ref):
             port.lib.xo_pixel_avg(ip, X._ptr(d1), 16, X._ptr(a), 16, X._ptr(b), 16, weight)
             ref.lib.xo_pixel_avg(ip, X._ptr(d2), 16, X._ptr(a), 16, X._ptr(b), 16, weight)
             assert np.array_equal(d1, d2), (ip, weight)
+
+
+@pytest.mark.parametrize("me_range", [16, 24, 8])
+def test_umh(pkg, port, ref, me_range):
+    """--me umh (me.c:306-447): uneven cross, early terminations, adaptive range from predictor agreement, hexagon grid, hex2 refine"""
+    from x264_vs2008_b200 import synth
+    from helpers import make_me_jobs
+    w, h = 160, 128
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=21)
+    pe, pr = port.plane_from_picture(g, clip.luma(1)), port.plane_from_picture(g, clip.luma(0))
+    fh, fv, fc, integ = port.frame_filter(g, pr, 1)
+    for spread, centre in ((48, None), (10, (-20, -12)), (4, (-20, -12))):
+        _, mis = make_me_jobs(pkg, g, seed=500 + me_range + spread, n=150, me_range=me_range, qp=(12, 26, 40), pixels=(0, 1, 2, 3, 4, 5, 6), mvp_spread=spread,
+                              centre=centre)
+        for i, mi in enumerate(mis):
+            mi.me_method = X.ME_UMH
+            mi.b_sub8x8 = 1
+            if centre is not None and i % 2:  # neighbours that agree with the predictor: exercises the small-range contexts
+                for k in range(mi.i_mvc):
+                    mi.mvc[k][0], mi.mvc[k][1] = mi.mvp[0] + (k % 3) - 1, mi.mvp[1] + (k % 2)
+            for subme in (1, 2, 5):
+                a = port.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
+                b = ref.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
+                assert (a.mv[0], a.mv[1], a.cost, a.cost_mv) == (b.mv[0], b.mv[1], b.cost, b.cost_mv), (spread, i, subme, mi.i_pixel)

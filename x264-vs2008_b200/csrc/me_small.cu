@@ -135,6 +135,32 @@ __device__ __forceinline__ int scan_fpel(const SearchCtx &c, int lane, const Tab
     return best_k;
 }
 
+// the same for candidates produced by a generator: gen(k, mx, my) -> "candidate k exists", in list order
+template <typename Gen>
+__device__ __forceinline__ void scan_gen(const SearchCtx &c, int lane, int n, Gen gen, int &bcost, int &bmx, int &bmy)
+{
+    const int per = 32 / c.U;
+    for (int k0 = 0; k0 < n; k0 += per) {
+        const int k = k0 + lane / c.U;
+        int mx = 0, my = 0;
+        const bool valid = k < n && gen(k, mx, my);
+        const int cost = eval_round(c, c.fpel_satd, lane, valid, mx << 2, my << 2); // COST_MAX + 1 for absent candidates
+        for (int j = 0; j < per && k0 + j < n; j++) {
+            const int cj = cand_cost(c, cost, j);
+            const int jx = __shfl_sync(0xffffffffu, mx, j * c.U), jy = __shfl_sync(0xffffffffu, my, j * c.U);
+            if (cj < bcost) { bcost = cj; bmx = jx; bmy = jy; }
+        }
+    }
+}
+
+__constant__ int8_t c_umh_oct[8][2] = { { 0, -2 }, { -1, -1 }, { 1, -1 }, { -2, 0 }, { 2, 0 }, { -1, 1 }, { 1, 1 }, { 0, 2 } };     // me.c:334-335
+__constant__ int8_t c_umh_star[8][2] = { { -1, -2 }, { 1, -2 }, { -2, -1 }, { 2, -1 }, { -2, 1 }, { 2, 1 }, { -1, 2 }, { 1, 2 } };  // me.c:342-343
+__constant__ int8_t c_umh_diag2[4][2] = { { -2, -2 }, { -2, 2 }, { 2, -2 }, { 2, 2 } };                                              // me.c:405
+__constant__ int8_t c_umh_hex4[16][2] = { { -4, 2 }, { -4, 1 }, { -4, 0 }, { -4, -1 }, { -4, -2 }, { 4, -2 }, { 4, -1 }, { 4, 0 }, { 4, 1 }, { 4, 2 },
+                                          { 2, 3 }, { 0, 4 }, { -2, 3 }, { -2, -3 }, { 0, -4 }, { 2, -3 } };                       // me.c:412-417
+__constant__ int8_t c_umh_range_mul[4][4] = { { 3, 3, 4, 4 }, { 3, 4, 4, 4 }, { 4, 4, 4, 5 }, { 4, 4, 5, 6 } };                    // me.c:360-366
+__constant__ int8_t c_pixel_size_shift[7] = { 0, 1, 1, 2, 3, 3, 4 };                                                               // me.c:311
+
 // candidate-list accessors: the list is written and read by DIFFERENT lanes of the warp between __syncwarp()s; volatile
 // keeps every access a real memory operation (no register caching across the barriers)
 __device__ __forceinline__ int2 list_get(const int2 *l, int i) { const volatile int *p = (const volatile int *)(l + i); return make_int2(p[0], p[1]); }
@@ -351,22 +377,91 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
             if (bmx == ox && bmy == oy) break;
             if (!IN_RANGE(bmx, bmy)) break;
         } while (++i < me_range);
-    } else if (method == X264_CUDA_ME_METHOD_HEX) { // me.c:266-304
-        int ox = bmx, oy = bmy;
-        int dir = scan_fpel(c, lane, c_hex2, 1, 6, ox, oy, bcost, ox, oy); // hex2[1..6] == (-2,0),(-1,2),(1,2),(2,0),(1,-2),(-1,-2)
-        if (dir >= 0) {
-            bmx += c_hex2[dir + 1][0]; bmy += c_hex2[dir + 1][1];
-            for (int i = 1; i < me_range / 2 && IN_RANGE(bmx, bmy); i++) {
-                const int odir = c_mod6m1[dir + 1];
-                ox = bmx; oy = bmy;
-                const int k = scan_fpel(c, lane, c_hex2, odir, 3, bmx, bmy, bcost, ox, oy);
-                if (k < 0) break;
-                dir = odir - 1 + k;
-                bmx += c_hex2[dir + 1][0]; bmy += c_hex2[dir + 1][1];
+    } else if (method == X264_CUDA_ME_METHOD_HEX || method == X264_CUDA_ME_METHOD_UMH) {
+        int range = me_range;
+        bool hex2 = true;
+        if (method == X264_CUDA_ME_METHOD_UMH) { // me.c:306-447: uneven-cross multi-hexagon-grid search, then me_hex2
+            const int shift = c_pixel_size_shift[c.i_pixel];
+#define SAD_THRESH(v) (bcost < ((v) >> shift))
+            int omx = pmx, omy = pmy, cross_start = 1;
+            // CROSS (me.c:128-154): +-i along x for i = start, start+2, .. < xm, then along y.  The reference's unchecked
+            // COST_MV_X4 form only runs when every candidate is inside the limits, so one range-checked list is the same thing.
+            auto cross = [&](int start, int xm, int ym) {
+                const int ox = omx, oy = omy;
+                const int nx = xm > start ? (xm - start + 1) / 2 * 2 : 0, ny = ym > start ? (ym - start + 1) / 2 * 2 : 0;
+                scan_gen(c, lane, nx, [&](int k, int &mx, int &my) { const int i = start + (k >> 1) * 2; mx = ox + ((k & 1) ? -i : i); my = oy;
+                                                                     return (k & 1) ? mx >= x_min : mx <= x_max; }, bcost, bmx, bmy);
+                scan_gen(c, lane, ny, [&](int k, int &mx, int &my) { const int i = start + (k >> 1) * 2; mx = ox; my = oy + ((k & 1) ? -i : i);
+                                                                     return (k & 1) ? my >= y_min : my <= y_max; }, bcost, bmx, bmy);
+            };
+            const int ucost1 = bcost;
+            scan_fpel(c, lane, c_square1, 0, 4, pmx, pmy, bcost, bmx, bmy);                 // DIA1_ITER( pmx, pmy )
+            if (pmx | pmy) scan_fpel(c, lane, c_square1, 0, 4, 0, 0, bcost, bmx, bmy);      // DIA1_ITER( 0, 0 )
+            if (c.i_pixel != X264_CUDA_PIXEL_4x4) {
+                const int ucost2 = bcost;
+                if ((bmx | bmy) && ((bmx - pmx) | (bmy - pmy))) { const int cx = bmx, cy = bmy; scan_fpel(c, lane, c_square1, 0, 4, cx, cy, bcost, bmx, bmy); }
+                if (bcost == ucost2) cross_start = 3;
+                omx = bmx; omy = bmy;
+                bool done = false;
+                if (bcost == ucost2 && SAD_THRESH(2000)) { // early termination
+                    scan_fpel(c, lane, c_umh_oct, 0, 8, omx, omy, bcost, bmx, bmy);
+                    if (bcost == ucost1 && SAD_THRESH(500)) done = true;
+                    else if (bcost == ucost2) {
+                        const int r = (range >> 1) | 1;
+                        cross(3, r, r);
+                        scan_fpel(c, lane, c_umh_star, 0, 8, omx, omy, bcost, bmx, bmy);
+                        if (bcost == ucost2) done = true;
+                        else cross_start = r + 2;
+                    }
+                }
+                if (done) hex2 = false;
+                else {
+                    const int n_mvc = min((int)job.i_mvc, 12);
+                    if (n_mvc) { // adaptive search range from the agreement of the predictors (me.c:354-399)
+                        int mvd, denom = 1;
+                        if (n_mvc == 1)
+                            mvd = c.i_pixel == X264_CUDA_PIXEL_16x16 ? 25 : abs(job.mvp[0] - job.mvc[0][0]) + abs(job.mvp[1] - job.mvc[0][1]);
+                        else {
+                            denom = n_mvc - 1;
+                            mvd = 0;
+                            if (c.i_pixel != X264_CUDA_PIXEL_16x16) { mvd = abs(job.mvp[0] - job.mvc[0][0]) + abs(job.mvp[1] - job.mvc[0][1]); denom++; }
+                            for (int k = 0; k < n_mvc - 1; k++) mvd += abs(job.mvc[k][0] - job.mvc[k + 1][0]) + abs(job.mvc[k][1] - job.mvc[k + 1][1]);
+                        }
+                        const int sad_ctx = SAD_THRESH(1000) ? 0 : SAD_THRESH(2000) ? 1 : SAD_THRESH(4000) ? 2 : 3;
+                        const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+                        range = range * c_umh_range_mul[mvd_ctx][sad_ctx] / 4;
+                    }
+                    cross(cross_start, range, range / 2);
+                    scan_fpel(c, lane, c_umh_diag2, 0, 4, omx, omy, bcost, bmx, bmy);
+                    omx = bmx; omy = bmy;
+                    int i = 1;
+                    do { // hexagon grid, 16 points scaled by i (range-checked: the unchecked form needs all of them inside anyway)
+                        const int ox = omx, oy = omy, sc = i;
+                        scan_gen(c, lane, 16, [&](int k, int &mx, int &my) { mx = ox + c_umh_hex4[k][0] * sc; my = oy + c_umh_hex4[k][1] * sc;
+                                                                             return mx >= x_min && mx <= x_max && my >= y_min && my <= y_max; }, bcost, bmx, bmy);
+                    } while (++i <= range / 4);
+                    hex2 = bmy <= y_max;
+                }
             }
+#undef SAD_THRESH
         }
-        ox = bmx; oy = bmy; // square refine, me.c:301-304
-        scan_fpel(c, lane, c_square1, 0, 8, ox, oy, bcost, bmx, bmy);
+        if (hex2) { // me.c:246-304 (me_hex2)
+            int ox = bmx, oy = bmy;
+            int dir = scan_fpel(c, lane, c_hex2, 1, 6, ox, oy, bcost, ox, oy); // hex2[1..6] == (-2,0),(-1,2),(1,2),(2,0),(1,-2),(-1,-2)
+            if (dir >= 0) {
+                bmx += c_hex2[dir + 1][0]; bmy += c_hex2[dir + 1][1];
+                for (int i = 1; i < range / 2 && IN_RANGE(bmx, bmy); i++) {
+                    const int odir = c_mod6m1[dir + 1];
+                    ox = bmx; oy = bmy;
+                    const int k = scan_fpel(c, lane, c_hex2, odir, 3, bmx, bmy, bcost, ox, oy);
+                    if (k < 0) break;
+                    dir = odir - 1 + k;
+                    bmx += c_hex2[dir + 1][0]; bmy += c_hex2[dir + 1][1];
+                }
+            }
+            ox = bmx; oy = bmy; // square refine, me.c:301-304
+            scan_fpel(c, lane, c_square1, 0, 8, ox, oy, bcost, bmx, bmy);
+        }
     }
     else if (method == X264_CUDA_ME_METHOD_TESA)
         tesa_search(c, job, me_range, lane, bcost, bmx, bmy);
@@ -549,8 +644,8 @@ extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_f
         return -1;
     }
     if (subme < 0 || subme > 9 || me_range < 1 || me_range > 64 ||
-        (method != X264_CUDA_ME_METHOD_DIA && method != X264_CUDA_ME_METHOD_HEX && method != X264_CUDA_ME_METHOD_SEEDED &&
-         method != X264_CUDA_ME_METHOD_TESA)) {
+        (method != X264_CUDA_ME_METHOD_DIA && method != X264_CUDA_ME_METHOD_HEX && method != X264_CUDA_ME_METHOD_UMH &&
+         method != X264_CUDA_ME_METHOD_SEEDED && method != X264_CUDA_ME_METHOD_TESA)) {
         snprintf(ctx->err, 256, "x264_cuda_me_search_small: bad method %d / subme %d / me_range %d", method, subme, me_range);
         return -1;
     }
