@@ -697,7 +697,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rows", action="store_true", help="per-row device time vs the reference's C on one core (1080p); one JSON line")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="frames in flight (host threads, one context each) in the e2e leg")
+    ap.add_argument("--e2e-threads", type=int, default=8, help="frames in flight (host threads, one context each) in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.rows:
