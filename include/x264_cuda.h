@@ -207,10 +207,14 @@ X264_CUDA_API int x264_cuda_host_esa_replay(const uint16_t *grid_part, int radiu
  *   method X264_CUDA_ME_METHOD_TESA       : the complete --me tesa search: predictor stage, ADS threshold on the
  *       integral image (pixf.ads, S/common/pixel.c:515-559), SAD threshold list, keep merange/2, fpelcmp on the keepers
  *       (me.c:491-578), then the tail as above.  fref needs X264_CUDA_FRAME_INTEGRAL (+_INTEGRAL4 for sub-8x8 blocks);
+ *   method X264_CUDA_ME_METHOD_REFINE_QPEL: x264_me_refine_qpel (me.c:633-643) — refine_subpel with b_refine_qpel = 1 from job.seed_mv
+ *       (= m->mv, QUARTER-pel) and job.seed_cost (= m->cost after the caller's i_ref_cost adjustment); bmx/bmy in the result are
+ *       not meaningful;
  *   method X264_CUDA_ME_METHOD_SEEDED     : job.seed_mv/seed_cost carry the full-pel winner of x264_cuda_me_search
  *       (ESA/TESA, subme < 3 predictor stage) and only ":603-631" runs.
  * fref must have the half-pel planes (X264_CUDA_FRAME_HPEL, x264_cuda_frame_filter) when subme >= 2. */
-enum { X264_CUDA_ME_METHOD_DIA = 0, X264_CUDA_ME_METHOD_HEX = 1, X264_CUDA_ME_METHOD_UMH = 2, X264_CUDA_ME_METHOD_TESA = 4, X264_CUDA_ME_METHOD_SEEDED = 8 };
+enum { X264_CUDA_ME_METHOD_DIA = 0, X264_CUDA_ME_METHOD_HEX = 1, X264_CUDA_ME_METHOD_UMH = 2, X264_CUDA_ME_METHOD_TESA = 4, X264_CUDA_ME_METHOD_SEEDED = 8,
+       X264_CUDA_ME_METHOD_REFINE_QPEL = 16 };
 typedef struct x264_cuda_me_final_t {
     int16_t mv[2];               /* m->mv (qpel) */
     int32_t cost;                /* m->cost */

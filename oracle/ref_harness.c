@@ -213,6 +213,8 @@ void xo_pixel_avg(int i_pixel, uint8_t *dst, int dst_stride, const uint8_t *a, i
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+static const int16_t *g_refine_mv; /* non-NULL: run x264_me_refine_qpel from (g_refine_mv, g_refine_cost) instead of the search */
+static int g_refine_cost;
 static void run_search_c(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref[4], const uint16_t *integral,
                          const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
 {
@@ -258,7 +260,12 @@ static void run_search_c(const xo_geom *g, const uint8_t *fenc_plane, const uint
         }
         m.i_stride[1] = ch->stride_c;
     }
-    x264_me_search_ref(h, &m, mvc, in->i_mvc, NULL);
+    if (g_refine_mv) {
+        m.mv[0] = g_refine_mv[0]; m.mv[1] = g_refine_mv[1]; m.cost = g_refine_cost; m.i_ref_cost = 0;
+        x264_me_refine_qpel(h, &m);
+        m.cost_mv = m.p_cost_mv[m.mv[0] - m.mvp[0]] + m.p_cost_mv[m.mv[1] - m.mvp[1]]; /* refine_subpel sets it too */
+    } else
+        x264_me_search_ref(h, &m, mvc, in->i_mvc, NULL);
     memset(out, 0, sizeof(*out));
     out->mv[0] = m.mv[0]; out->mv[1] = m.mv[1];
     out->cost = m.cost; out->cost_mv = m.cost_mv;
@@ -275,6 +282,14 @@ void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, con
                                 const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out)
 {
     run_search_c(g, fenc_plane, fref_planes, integral, ch, in, subme, mbcmp_satd, out);
+}
+
+void xo_me_refine_qpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const xo_chroma *ch, const xo_me_in *in,
+                       int subme, int mbcmp_satd, const int16_t mv_in[2], int cost_in, xo_me_out *out)
+{
+    g_refine_mv = mv_in; g_refine_cost = cost_in;
+    run_search_c(g, fenc_plane, fref_planes, NULL, ch, in, subme, mbcmp_satd, out);
+    g_refine_mv = NULL;
 }
 
 void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,

@@ -165,6 +165,10 @@ typedef struct { const uint8_t *fenc_u, *fenc_v, *fref_u, *fref_v; int stride_c;
 void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const uint16_t *integral,
                                 const xo_chroma *ch, const xo_me_in *in, int subme, int mbcmp_satd, xo_me_out *out);
 
+/* x264_me_refine_qpel (me.c:633-643) from (mv_in, cost_in); ch may be NULL (no chroma ME) */
+void xo_me_refine_qpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const xo_chroma *ch, const xo_me_in *in,
+                       int subme, int mbcmp_satd, const int16_t mv_in[2], int cost_in, xo_me_out *out);
+
 /* ---------------- lowres lookahead: S/encoder/slicetype.c:43-355 (non-VBV, no AQ) ----------------
  * Planes are the four half-resolution planes (pixel 0,0 pointers, stride g->stride_lowres).  mvs/costs are the frame's
  * lowres_mvs[l][dist-1] / lowres_mv_costs[l][dist-1] arrays (mb_width*mb_height entries, updated in place when

@@ -105,18 +105,9 @@ typedef struct {
     const xo_chroma *ch; /* non-NULL: h->mb.b_chroma_me */
 } me_sub;
 
-static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
-                    const uint16_t *integral, const xo_me_in *in, const me_sub *sub, xo_me_out *out)
+static void ctx_setup(me_ctx *c, const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const xo_me_in *in,
+                      const me_sub *sub, int stride, const int16_t *tab)
 {
-    me_ctx cx, *c = &cx;
-    const int stride = g->stride > 0 ? g->stride : -g->stride; /* negative: explicit stride (lowres) */
-    int range = in->me_range;                                     /* UMH adapts it (me.c:354-399) */
-    const int x_min = in->mv_min_fpel[0], y_min = in->mv_min_fpel[1];
-    const int x_max = in->mv_max_fpel[0], y_max = in->mv_max_fpel[1];
-    const int16_t *tab = cost_table(in->qp);
-    int bmx, bmy, bcost, pmx, pmy;
-    int bpred_mx = 0, bpred_my = 0, bpred_cost = XO_COST_MAX;
-
     c->g = g; c->in = in; c->stride = stride;
     c->bw = blk_w[in->i_pixel]; c->bh = blk_h[in->i_pixel];
     c->fpel_metric = in->fpel_satd ? XO_SATD : XO_SAD;
@@ -138,6 +129,21 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
             c->fref_c[pl] = fr[pl] + (in->by / 2) * ch->stride_c + in->bx / 2;
         }
     }
+}
+
+static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4],
+                    const uint16_t *integral, const xo_me_in *in, const me_sub *sub, xo_me_out *out)
+{
+    me_ctx cx, *c = &cx;
+    const int stride = g->stride > 0 ? g->stride : -g->stride; /* negative: explicit stride (lowres) */
+    int range = in->me_range;                                     /* UMH adapts it (me.c:354-399) */
+    const int x_min = in->mv_min_fpel[0], y_min = in->mv_min_fpel[1];
+    const int x_max = in->mv_max_fpel[0], y_max = in->mv_max_fpel[1];
+    const int16_t *tab = cost_table(in->qp);
+    int bmx, bmy, bcost, pmx, pmy;
+    int bpred_mx = 0, bpred_my = 0, bpred_cost = XO_COST_MAX;
+
+    ctx_setup(c, g, fenc_plane, fref_planes, in, sub, stride, tab);
 
     /* me.c:182-186 */
     bmx = clip3(in->mvp[0], x_min * 4, x_max * 4);
@@ -440,6 +446,46 @@ static void me_core(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *
         mvy = in->mv_max_spel[1]; /* me.c:629-630 */
     }
     out->mv[0] = mvx; out->mv[1] = mvy; out->cost = cost; out->cost_mv = cost_mv;
+}
+
+/* x264_me_refine_qpel (me.c:633-643): refine_subpel( h, m, subpel_iterations[subme][0], [1], NULL, 1 ) from m->mv / m->cost.
+ * The caller has already applied the "m->cost -= m->i_ref_cost" of :638-639 if it wants it. */
+void xo_me_refine_qpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const xo_chroma *ch, const xo_me_in *in,
+                       int subme, int mbcmp_satd, const int16_t mv_in[2], int cost_in, xo_me_out *out)
+{
+    static const int8_t iters[10][2] = { { 0, 0 }, { 1, 1 }, { 0, 1 }, { 0, 2 }, { 0, 2 }, { 0, 2 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    me_ctx cx, *c = &cx;
+    me_sub sub = { subme, mbcmp_satd, ch };
+    const int stride = g->stride > 0 ? g->stride : -g->stride;
+    ctx_setup(c, g, fenc_plane, fref_planes, in, &sub, stride, cost_table(in->qp));
+    int bmx = mv_in[0], bmy = mv_in[1], bcost = cost_in, bdir = -1;
+    const int hpel_iters = iters[subme][0], qpel_iters = iters[subme][1], spel_y_max = in->mv_max_spel[1];
+    if (hpel_iters && subme < 3) { /* me.c:699-705 */
+        const int mx = clip3(in->mvp[0], in->mv_min_spel[0], in->mv_max_spel[0]), my = clip3(in->mvp[1], in->mv_min_spel[1], in->mv_max_spel[1]);
+        if ((mx - bmx) | (my - bmy)) { const int cst = qpel_cost(c, c->fpel_metric, mx, my); if (cst < bcost) { bcost = cst; bmx = mx; bmy = my; } }
+    }
+    for (int i = hpel_iters; i > 0; i--) { /* me.c:708-727 */
+        const int ox = bmx, oy = bmy;
+        int cst;
+        cst = qpel_cost(c, c->fpel_metric, ox, oy - 2); if (cst < bcost) { bcost = cst; bmy = oy - 2; }
+        cst = qpel_cost(c, c->fpel_metric, ox, oy + 2); if (cst < bcost) { bcost = cst; bmy = oy + 2; }
+        cst = qpel_cost(c, c->fpel_metric, ox - 2, oy); if (cst < bcost) { bcost = cst; bmx = ox - 2; bmy = oy; }
+        cst = qpel_cost(c, c->fpel_metric, ox + 2, oy); if (cst < bcost) { bcost = cst; bmx = ox + 2; bmy = oy; }
+        if (bmx == ox && bmy == oy) break;
+    }
+    for (int i = qpel_iters; i > 0; i--) { /* me.c:755-767 with b_refine_qpel: all four neighbours every time */
+        static const int8_t d[4][2] = { { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 } };
+        const int ox = bmx, oy = bmy;
+        for (int k = 0; k < 4; k++) {
+            const int cst = satd_cost(c, ox + d[k][0], oy + d[k][1], bcost);
+            if (cst < bcost) { bcost = cst; bmx = ox + d[k][0]; bmy = oy + d[k][1]; bdir = k; }
+        }
+        if (bmx == ox && bmy == oy) break;
+    }
+    (void)bdir;
+    if (bmy > spel_y_max) { bmy = spel_y_max; bcost = satd_cost(c, bmx, bmy, XO_COST_MAX); } /* me.c:770-775 */
+    memset(out, 0, sizeof(*out));
+    out->mv[0] = bmx; out->mv[1] = bmy; out->cost = bcost; out->cost_mv = c->cmx[bmx] + c->cmy[bmy];
 }
 
 void xo_me_search_fpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *fref_plane,

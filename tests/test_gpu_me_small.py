@@ -214,3 +214,39 @@ def test_umh(pkg, ctx, port, me_range, subme):
                 bad.append((i, mi.i_pixel, got, want))
         assert not bad, (spread, len(bad), bad[:4])
     fenc.close(); fref.close()
+
+
+@pytest.mark.parametrize("with_chroma", [0, 1])
+def test_refine_qpel(pkg, ctx, port, with_chroma):
+    """x264_me_refine_qpel on the device: refine_subpel with b_refine_qpel = 1 from a given quarter-pel vector and cost"""
+    from x264_vs2008_b200 import synth
+    from helpers import padded_chroma
+    w, h = 320, 192
+    clip = synth.Clip(w, h, seed=71)
+    g = port.geometry(w, h)
+    (y1, u1, v1), (y0, u0, v0) = clip.yuv420(1), clip.yuv420(0)
+    fenc, fref = ctx.frame(w, h, pkg.FRAME_CHROMA), ctx.frame(w, h, pkg.FRAME_HPEL | pkg.FRAME_CHROMA)
+    fenc.upload(y1); fenc.upload_chroma(u1, v1); fenc.expand_border()
+    fref.upload(y0); fref.upload_chroma(u0, v0); fref.expand_border(); fref.filter()
+    chroma = [padded_chroma(g, c) for c in (u1, v1, u0, v0)] if with_chroma else None
+    pe, pr = port.plane_from_picture(g, y1), port.plane_from_picture(g, y0)
+    fh, fv, fc, _ = port.frame_filter(g, pr, 0, want_integral=False)
+    rng = np.random.default_rng(9)
+    for subme in (1, 2, 3, 5, 7):
+        jobs, mis = make_me_jobs(pkg, g, seed=40 + subme, n=300, me_range=16, qp=(12, 26, 38), pixels=(0, 1, 2, 3, 4, 5, 6), mvp_spread=30, centre=(-20, -12))
+        _fill_spel(jobs, mis)
+        for j, mi in zip(jobs, mis):
+            j["bx"], j["by"] = (int(j["bx"]) // 8) * 8 if mi.i_pixel <= 3 else j["bx"], (int(j["by"]) // 8) * 8 if mi.i_pixel <= 3 else j["by"]
+            mi.bx, mi.by = int(j["bx"]), int(j["by"])
+            j["seed_mv"] = [int(rng.integers(-12, 13)) - 20, int(rng.integers(-12, 13)) - 12]
+            j["seed_cost"] = int(rng.integers(200, 6000))
+        jobs["flags"] = pkg.ME_MBCMP_SATD | (pkg.ME_CHROMA if with_chroma else 0)
+        res = ctx.me_search_small(fenc, fref, pkg.ME_METHOD_REFINE_QPEL, 16, subme, jobs)
+        bad = []
+        for i, (j, mi) in enumerate(zip(jobs, mis)):
+            o = port.me_refine_qpel(g, pe, [pr, fh, fv, fc], chroma, mi, subme, 1, [int(j["seed_mv"][0]), int(j["seed_mv"][1])], int(j["seed_cost"]))
+            got = (int(res[i]["mv"][0]), int(res[i]["mv"][1]), int(res[i]["cost"]), int(res[i]["cost_mv"]))
+            if got != (o.mv[0], o.mv[1], o.cost, o.cost_mv):
+                bad.append((i, mi.i_pixel, got, (o.mv[0], o.mv[1], o.cost, o.cost_mv)))
+        assert not bad, (subme, len(bad), bad[:4])
+    fenc.close(); fref.close()

@@ -290,3 +290,28 @@ def test_umh(pkg, port, ref, me_range):
                 a = port.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
                 b = ref.me_search_subpel(g, pe, [pr, fh, fv, fc], integ, mi, subme, 1)
                 assert (a.mv[0], a.mv[1], a.cost, a.cost_mv) == (b.mv[0], b.mv[1], b.cost, b.cost_mv), (spread, i, subme, mi.i_pixel)
+
+
+def test_refine_qpel(pkg, port, ref):
+    """x264_me_refine_qpel (me.c:633-643): refine_subpel with b_refine_qpel = 1 from a given vector, with and without chroma ME"""
+    from x264_vs2008_b200 import synth
+    from helpers import make_me_jobs, padded_chroma
+    w, h = 160, 128
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=21)
+    (y1, u1, v1), (y0, u0, v0) = clip.yuv420(1), clip.yuv420(0)
+    pe, pr = port.plane_from_picture(g, y1), port.plane_from_picture(g, y0)
+    fh, fv, fc, _ = port.frame_filter(g, pr, 0, want_integral=False)
+    chroma = [padded_chroma(g, c) for c in (u1, v1, u0, v0)]
+    rng = np.random.default_rng(77)
+    _, mis = make_me_jobs(pkg, g, seed=321, n=120, me_range=16, qp=(12, 26, 40), pixels=(0, 1, 2, 3, 4, 5, 6), mvp_spread=30, centre=(-20, -12))
+    for i, mi in enumerate(mis):
+        if mi.i_pixel <= 3:
+            mi.bx, mi.by = (mi.bx // 8) * 8, (mi.by // 8) * 8
+        mv = [int(rng.integers(-12, 13)) - 20, int(rng.integers(-12, 13)) - 12]
+        cost = int(rng.integers(200, 6000))
+        for subme in (1, 2, 3, 5, 7):
+            for ch in (None, chroma):
+                a = port.me_refine_qpel(g, pe, [pr, fh, fv, fc], ch, mi, subme, 1, mv, cost)
+                b = ref.me_refine_qpel(g, pe, [pr, fh, fv, fc], ch, mi, subme, 1, mv, cost)
+                assert (a.mv[0], a.mv[1], a.cost, a.cost_mv) == (b.mv[0], b.mv[1], b.cost, b.cost_mv), (i, subme, ch is not None, mi.i_pixel)

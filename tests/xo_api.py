@@ -128,6 +128,8 @@ class Oracle:
         L.xo_frame_mb_energy.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, C.c_int, C.POINTER(C.c_uint32)]
         L.xo_frame_mb_hadamard_ac.argtypes = [C.POINTER(Geom), u8p, C.POINTER(C.c_uint64)]
         L.xo_frame_aq.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, C.c_int, C.c_float, C.POINTER(C.c_float), u16p]
+        L.xo_me_refine_qpel.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), C.POINTER(Chroma), C.POINTER(MeIn), C.c_int, C.c_int, i16p, C.c_int,
+                                        C.POINTER(MeOut)]
         L.xo_frame_deblock.argtypes = [C.POINTER(Geom), C.POINTER(DeblockIn), u8p, u8p, u8p, C.c_int]
         self.backend = L.xo_backend().decode()
 
@@ -236,6 +238,17 @@ class Oracle:
         qp, inv = np.zeros(n, np.float32), np.zeros(n, np.uint16)
         self.lib.xo_frame_aq(C.byref(g), _ptr(y, u8p, g.origin), _ptr(u), _ptr(v), u.shape[1], strength, qp.ctypes.data_as(C.POINTER(C.c_float)), _ptr(inv, u16p))
         return qp, inv
+
+    def me_refine_qpel(self, g, fenc, planes4, chroma, mi, subme, mbcmp_satd, mv, cost):
+        out = MeOut()
+        arr = (u8p * 4)(*[_ptr(p, u8p, g.origin) for p in planes4])
+        chp = None
+        if chroma is not None:
+            sc = chroma[0].shape[1]
+            chp = C.byref(Chroma(*[a.ctypes.data + 16 * sc + 16 for a in chroma], sc))
+        mvv = np.array(mv, np.int16)
+        self.lib.xo_me_refine_qpel(C.byref(g), _ptr(fenc, u8p, g.origin), arr, chp, C.byref(mi), subme, mbcmp_satd, _ptr(mvv, i16p), int(cost), C.byref(out))
+        return out
 
     def frame_deblock(self, g, info, y, u, v):
         """y: padded luma plane (flat, pixel 0,0 at g.origin); u, v: 2-D chroma arrays (contiguous).  Filtered in place."""

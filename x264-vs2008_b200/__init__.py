@@ -50,7 +50,7 @@ def grid_h(radius):
 
 
 ME_FINAL = np.dtype([("mv", "<i2", (2,)), ("cost", "<i4"), ("cost_mv", "<i4"), ("bmx", "<i2"), ("bmy", "<i2")], align=True)
-ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_UMH, ME_METHOD_TESA, ME_METHOD_SEEDED = 0, 1, 2, 4, 8
+ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_UMH, ME_METHOD_TESA, ME_METHOD_SEEDED, ME_METHOD_REFINE_QPEL = 0, 1, 2, 4, 8, 16
 ME_MBCMP_SATD = 8
 ME_CHROMA = 32
 LOWRES_WEIGHTED_BIPRED = 16

@@ -317,7 +317,8 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
     bcost = COST_MAX;
     const int n_mvc = min((int)job.i_mvc, X264_CUDA_ME_MAX_MVC);
 
-    if (method == X264_CUDA_ME_METHOD_SEEDED) {
+    const bool refine_only = method == X264_CUDA_ME_METHOD_REFINE_QPEL; // x264_me_refine_qpel: seed_mv is m->mv (quarter-pel), seed_cost m->cost
+    if (method == X264_CUDA_ME_METHOD_SEEDED || refine_only) {
         bmx = job.seed_mv[0]; bmy = job.seed_mv[1]; bcost = job.seed_cost;
     } else {
         if (subme >= 3) { // me.c:189-205: predictors at quarter-pel precision
@@ -469,14 +470,16 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
 
     // ---- "-> qpel mv", me.c:603-620
     int mvx, mvy, cost;
-    if (bpred_cost < bcost) { mvx = bpred_mx; mvy = bpred_my; cost = bpred_cost; }
+    if (refine_only) { mvx = bmx; mvy = bmy; cost = bcost; }
+    else if (bpred_cost < bcost) { mvx = bpred_mx; mvy = bpred_my; cost = bpred_cost; }
     else { mvx = bmx << 2; mvy = bmy << 2; cost = bcost; }
     int cost_mv = c.cmx[mvx] + c.cmy[mvy];
-    if (bmx == pmx && bmy == pmy && subme < 3) cost += cost_mv;
+    if (!refine_only && bmx == pmx && bmy == pmy && subme < 3) cost += cost_mv;
 
-    // ---- refine_subpel(h, m, hpel, qpel, NULL, 0), me.c:680-778
-    if (subme >= 2) {
-        const int hpel_iters = c_subpel_iters[subme][2], qpel_iters = c_subpel_iters[subme][3];
+    // ---- refine_subpel(h, m, hpel, qpel, NULL, b_refine_qpel), me.c:680-778: from x264_me_search_ref (columns 2,3 of the iteration
+    // table, b_refine_qpel 0, only for subme >= 2) or as x264_me_refine_qpel (me.c:633-643: columns 0,1, b_refine_qpel 1)
+    if (subme >= 2 || refine_only) {
+        const int hpel_iters = c_subpel_iters[subme][refine_only ? 0 : 2], qpel_iters = c_subpel_iters[subme][refine_only ? 1 : 3];
         int sx = mvx, sy = mvy, sc = cost;
         const int spel_ymax = job.mv_max_spel[1];
         if (hpel_iters && subme < 3) {
@@ -499,19 +502,21 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
             if (v3 < sc) { sc = v3; sx = ox + 2; sy = oy; }
             if (sx == ox && sy == oy) break;
         }
-        if (sy > spel_ymax) sy = spel_ymax; // !b_refine_qpel, me.c:729-736
-        sc = eval_round_satd(c, lane, true, sx, sy);
+        if (!refine_only) { // !b_refine_qpel, me.c:729-736
+            if (sy > spel_ymax) sy = spel_ymax;
+            sc = eval_round_satd(c, lane, true, sx, sy);
+        }
         int bdir = -1;
         for (int i = qpel_iters; i > 0; i--) { // quarter-pel diamond with mbcmp, me.c:755-767
             const int odir = bdir, ox = sx, oy = sy;
             const int k = lane / c.U;
             const int dx = k == 2 ? -1 : k == 3 ? 1 : 0, dy = k == 0 ? -1 : k == 1 ? 1 : 0;
-            const bool valid = k < 4 && (k ^ 1) != odir;
+            const bool valid = k < 4 && (refine_only || (k ^ 1) != odir); // COST_MV_SATD: if( b_refine_qpel || (dir^1) != odir )
             const int v = eval_round_satd(c, lane, valid, ox + dx, oy + dy);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int vj = cand_cost(c, v, j);
-                if ((j ^ 1) != odir && vj < sc) {
+                if ((refine_only || (j ^ 1) != odir) && vj < sc) {
                     sc = vj; bdir = j;
                     sx = ox + (j == 2 ? -1 : j == 3 ? 1 : 0); sy = oy + (j == 0 ? -1 : j == 1 ? 1 : 0);
                 }
@@ -645,7 +650,7 @@ extern "C" int x264_cuda_me_search_small_dev(x264_cuda_t *ctx, const x264_cuda_f
     }
     if (subme < 0 || subme > 9 || me_range < 1 || me_range > 64 ||
         (method != X264_CUDA_ME_METHOD_DIA && method != X264_CUDA_ME_METHOD_HEX && method != X264_CUDA_ME_METHOD_UMH &&
-         method != X264_CUDA_ME_METHOD_SEEDED && method != X264_CUDA_ME_METHOD_TESA)) {
+         method != X264_CUDA_ME_METHOD_SEEDED && method != X264_CUDA_ME_METHOD_TESA && method != X264_CUDA_ME_METHOD_REFINE_QPEL)) {
         snprintf(ctx->err, 256, "x264_cuda_me_search_small: bad method %d / subme %d / me_range %d", method, subme, me_range);
         return -1;
     }
