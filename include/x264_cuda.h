@@ -113,7 +113,8 @@ X264_CUDA_API int x264_cuda_frame_init_lowres(x264_cuda_t *ctx, x264_cuda_frame_
 /* ------------------------------------------------------------------ MV cost tables ------------------ */
 /* Upload the HOST-computed lambda*bits table of one qp: p_cost_mv as built by x264_mb_analyse_load_costs
  * (S/encoder/analyse.c:182-203), `table` = the malloc base, 4*4*2048+1 int16 entries (centre at +2*4*2048).
- * Float-derived on the host — never recomputed on the device. */
+ * Float-derived on the host — never recomputed on the device.  A qp the caller never uploads falls back to the
+ * library's own host-side builder below at first use (identical to the reference's table for all 52 qps in our tests). */
 X264_CUDA_API int x264_cuda_set_cost_mv(x264_cuda_t *ctx, int qp, const int16_t *table);
 /* host-side mirror of that table builder for standalone use (tests, bench): fills table[4*4*2048+1] */
 X264_CUDA_API void x264_cuda_host_cost_mv(int qp, int16_t *table);
@@ -401,6 +402,28 @@ X264_CUDA_API int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_fra
                                            const x264_cuda_resid_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_t *coeffs);
 X264_CUDA_API int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
                                                const void *d_jobs, int n_jobs, void *d_coeffs);
+
+/* ------------------------------------------------------------------ bidirectional refinement --------- */
+/* x264_me_refine_bidir_satd (S/encoder/me.c:843-927): joint quarter-pel refinement of the list-0 / list-1 vectors of one B partition
+ * (16x16, 16x8, 8x16, 8x8) against the blended prediction, called by x264_mb_analyse_inter_b* refinement (analyse.c:2085-2105).
+ * Both references need X264_CUDA_FRAME_HPEL.  cost: best blended cost + mv bits seen (the reference does not return it); -1 = input
+ * vectors outside the cost table; the job's vectors are returned unchanged when the reference's early exit applies (:874-876). */
+typedef struct x264_cuda_bidir_job_t {
+    int16_t bx, by;                  /* luma position of the partition */
+    uint8_t i_pixel;                 /* X264_CUDA_PIXEL_16x16 .. _8x8 */
+    uint8_t qp;                      /* selects p_cost_mv */
+    uint8_t weight;                  /* h->mb.bipred_weight[ref0][ref1]; 32 = plain average */
+    uint8_t flags;                   /* X264_CUDA_ME_MBCMP_SATD */
+    int16_t mv0[2], mv1[2];          /* m0->mv, m1->mv (quarter-pel) */
+    int16_t mvp0[2], mvp1[2];        /* m0->mvp, m1->mvp */
+    int16_t mv_min_spel[2], mv_max_spel[2];
+} x264_cuda_bidir_job_t;             /* 32 bytes */
+typedef struct x264_cuda_bidir_result_t { int16_t mv0[2], mv1[2]; int32_t cost; } x264_cuda_bidir_result_t; /* 12 bytes */
+X264_CUDA_API int x264_cuda_me_refine_bidir(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
+                                            const x264_cuda_frame_t *fref1, const x264_cuda_bidir_job_t *jobs, int n_jobs,
+                                            x264_cuda_bidir_result_t *results);
+X264_CUDA_API int x264_cuda_me_refine_bidir_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
+                                                const x264_cuda_frame_t *fref1, const void *d_jobs, int n_jobs, void *d_results);
 
 /* ------------------------------------------------------------------ macroblock-batched motion search - */
 /* One job == ALL inter partition searches of one macroblock against one reference: 16x16, 2x16x8, 2x8x16,

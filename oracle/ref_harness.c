@@ -667,3 +667,31 @@ void xo_frame_aq(const xo_geom *g, const uint8_t *py, const uint8_t *pu, const u
     memcpy(qp_offset, f->f_qp_offset, n * sizeof(float));
     if (h->frames.b_have_lowres) memcpy(inv_qscale, f->i_inv_qscale_factor, n * sizeof(uint16_t));
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+int xo_me_refine_bidir_satd(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref0[4], const uint8_t *const fref1[4],
+                            const xo_me_in *in, const int16_t mvp0[2], const int16_t mvp1[2], int weight, int mbcmp_satd, int16_t mv0[2], int16_t mv1[2])
+{
+    x264_frame_t *f;
+    x264_t *h = get_h(g->width, g->height, X264_ME_HEX, mbcmp_satd ? 7 : 1, 0, 0, &f);
+    DECLARE_ALIGNED_16(uint8_t fenc[16 * 16]);
+    x264_me_t m0, m1;
+    ensure_costs(in->qp);
+    memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1));
+    for (int y = 0; y < x264_pixel_size[in->i_pixel].h; y++)
+        memcpy(fenc + 16 * y, fenc_plane + (in->by + y) * g->stride + in->bx, x264_pixel_size[in->i_pixel].w);
+    for (int k = 0; k < 2; k++) { h->mb.mv_min_spel[k] = in->mv_min_spel[k]; h->mb.mv_max_spel[k] = in->mv_max_spel[k]; }
+    m0.i_pixel = m1.i_pixel = in->i_pixel;
+    m0.p_cost_mv = m1.p_cost_mv = g_cost_mv[in->qp] + 2 * 4 * 2048;
+    m0.i_stride[0] = m1.i_stride[0] = g->stride;
+    m0.p_fenc[0] = m1.p_fenc[0] = fenc;
+    for (int k = 0; k < 4; k++) {
+        m0.p_fref[k] = (uint8_t *)fref0[k] + in->by * g->stride + in->bx;
+        m1.p_fref[k] = (uint8_t *)fref1[k] + in->by * g->stride + in->bx;
+    }
+    m0.mvp[0] = mvp0[0]; m0.mvp[1] = mvp0[1]; m1.mvp[0] = mvp1[0]; m1.mvp[1] = mvp1[1];
+    m0.mv[0] = mv0[0]; m0.mv[1] = mv0[1]; m1.mv[0] = mv1[0]; m1.mv[1] = mv1[1];
+    x264_me_refine_bidir_satd(h, &m0, &m1, weight);
+    mv0[0] = m0.mv[0]; mv0[1] = m0.mv[1]; mv1[0] = m1.mv[0]; mv1[1] = m1.mv[1];
+    return -1; /* the reference keeps the cost to itself */
+}

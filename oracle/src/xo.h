@@ -169,6 +169,12 @@ void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, con
 void xo_me_refine_qpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const xo_chroma *ch, const xo_me_in *in,
                        int subme, int mbcmp_satd, const int16_t mv_in[2], int cost_in, xo_me_out *out);
 
+/* x264_me_refine_bidir_satd (me.c:843-927): joint quarter-pel refinement of a list-0 / list-1 vector pair of one partition
+ * (16x16, 16x8, 8x16 or 8x8 at (bx,by)) against the blended prediction.  mv0/mv1 are updated in place; returns the best cost seen
+ * (the reference does not store it).  Uses in->i_pixel, bx, by, qp, mv_min_spel/mv_max_spel; mvp0/mvp1 are the two lists' predictors. */
+int xo_me_refine_bidir_satd(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref0[4], const uint8_t *const fref1[4],
+                            const xo_me_in *in, const int16_t mvp0[2], const int16_t mvp1[2], int weight, int mbcmp_satd, int16_t mv0[2], int16_t mv1[2]);
+
 /* ---------------- lowres lookahead: S/encoder/slicetype.c:43-355 (non-VBV, no AQ) ----------------
  * Planes are the four half-resolution planes (pixel 0,0 pointers, stride g->stride_lowres).  mvs/costs are the frame's
  * lowres_mvs[l][dist-1] / lowres_mv_costs[l][dist-1] arrays (mb_width*mb_height entries, updated in place when

@@ -530,3 +530,50 @@ void xo_me_search_subpel_strided(int stride, int lines_unused, const uint8_t *fe
     me_sub sub = { subme, mbcmp_satd, NULL };
     me_core(&g, fenc_plane, fref_planes, NULL, in, &sub, out);
 }
+
+
+/* x264_me_refine_bidir( h, m0, m1, i_weight, 0, 0, 0 ), me.c:843-927.  The 32 candidate pairs of a pass in the reference's order
+ * (CHECK_BIDIR8 / CHECK_BIDIR2 expanded); `visited` is the reference's aliasing 8x8x8x8-bit map (indices & 7), reproduced as is.
+ * The y cost tables are offset by mvp[1] clipped to the X limits — the reference does that (me.c:855,857) and so does this. */
+int xo_me_refine_bidir_satd(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref0[4], const uint8_t *const fref1[4],
+                            const xo_me_in *in, const int16_t mvp0[2], const int16_t mvp1[2], int weight, int mbcmp_satd, int16_t mv0[2], int16_t mv1[2])
+{
+    static const int8_t cand[32][4] = {
+        { 0, 0, 0, 1 }, { 0, 0, 0, -1 }, { 0, 0, 1, 0 }, { 0, 0, -1, 0 }, { 0, 1, 0, 0 }, { 0, -1, 0, 0 }, { 1, 0, 0, 0 }, { -1, 0, 0, 0 },
+        { 0, 0, 1, 1 }, { 0, 0, -1, -1 }, { 0, 1, 1, 0 }, { 0, -1, -1, 0 }, { 1, 1, 0, 0 }, { -1, -1, 0, 0 }, { 1, 0, 0, 1 }, { -1, 0, 0, -1 },
+        { 0, 1, 0, 1 }, { 0, -1, 0, -1 }, { 1, 0, 1, 0 }, { -1, 0, -1, 0 },
+        { 0, 0, -1, 1 }, { 0, 0, 1, -1 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { 1, 0, 0, -1 }, { -1, 0, 0, 1 },
+        { 0, -1, 0, 1 }, { 0, 1, 0, -1 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 } };
+    const int stride = g->stride, bw = blk_w[in->i_pixel], bh = blk_h[in->i_pixel], metric = mbcmp_satd ? XO_SATD : XO_SAD;
+    const int16_t *tab = cost_table(in->qp);
+    const int lo = in->mv_min_spel[0], hi = in->mv_max_spel[0];
+    const int16_t *c0x = tab - clip3(mvp0[0], lo, hi), *c0y = tab - clip3(mvp0[1], lo, hi);
+    const int16_t *c1x = tab - clip3(mvp1[0], lo, hi), *c1y = tab - clip3(mvp1[1], lo, hi);
+    uint8_t fenc[16 * 16], visited[8][8][8];
+    const uint8_t *p0[4], *p1[4];
+    int bm0x = mv0[0], bm0y = mv0[1], bm1x = mv1[0], bm1y = mv1[1], om0x = bm0x, om0y = bm0y, om1x = bm1x, om1y = bm1y, bcost = XO_COST_MAX;
+    if (bm0y > in->mv_max_spel[1] - 8 || bm1y > in->mv_max_spel[1] - 8) return bcost;
+    for (int y = 0; y < bh; y++) memcpy(fenc + 16 * y, fenc_plane + (in->by + y) * stride + in->bx, bw);
+    for (int k = 0; k < 4; k++) { p0[k] = fref0[k] + in->by * stride + in->bx; p1[k] = fref1[k] + in->by * stride + in->bx; }
+    memset(visited, 0, sizeof(visited));
+#define TRY_PAIR(m0x, m0y, m1x, m1y) do { \
+        if (pass == 0 || !(visited[(m0x) & 7][(m0y) & 7][(m1x) & 7] & (1 << ((m1y) & 7)))) { \
+            uint8_t a[16 * 16], b[16 * 16], pix[16 * 16]; \
+            visited[(m0x) & 7][(m0y) & 7][(m1x) & 7] |= (1 << ((m1y) & 7)); \
+            xo_mc_luma(a, 16, p0, stride, (m0x), (m0y), bw, bh); \
+            xo_mc_luma(b, 16, p1, stride, (m1x), (m1y), bw, bh); \
+            xo_pixel_avg(in->i_pixel, pix, 16, a, 16, b, 16, weight); \
+            const int cost = xo_pixel_cmp(metric, in->i_pixel, fenc, 16, pix, 16) + c0x[(m0x)] + c0y[(m0y)] + c1x[(m1x)] + c1y[(m1y)]; \
+            if (cost < bcost) { bcost = cost; bm0x = (m0x); bm0y = (m0y); bm1x = (m1x); bm1y = (m1y); } \
+        } } while (0)
+    int pass = 0;
+    TRY_PAIR(om0x, om0y, om1x, om1y);
+    for (pass = 0; pass < 8; pass++) {
+        for (int k = 0; k < 32; k++) TRY_PAIR(om0x + cand[k][0], om0y + cand[k][1], om1x + cand[k][2], om1y + cand[k][3]);
+        if (om0x == bm0x && om0y == bm0y && om1x == bm1x && om1y == bm1y) break;
+        om0x = bm0x; om0y = bm0y; om1x = bm1x; om1y = bm1y;
+    }
+#undef TRY_PAIR
+    mv0[0] = bm0x; mv0[1] = bm0y; mv1[0] = bm1x; mv1[1] = bm1y;
+    return bcost;
+}

@@ -250,3 +250,45 @@ def test_refine_qpel(pkg, ctx, port, with_chroma):
                 bad.append((i, mi.i_pixel, got, (o.mv[0], o.mv[1], o.cost, o.cost_mv)))
         assert not bad, (subme, len(bad), bad[:4])
     fenc.close(); fref.close()
+
+
+def test_refine_bidir(pkg, ctx, port):
+    """x264_me_refine_bidir_satd on the device vs the oracle (which is pinned to the reference by tests/test_oracle_vs_ref.py)"""
+    from x264_vs2008_b200 import synth
+    from test_oracle_vs_ref import bidir_cases
+    w, h = 320, 192
+    clip = synth.Clip(w, h, seed=81)
+    g = port.geometry(w, h)
+    fenc = ctx.frame(w, h, 0)
+    fenc.upload(clip.luma(1)); fenc.expand_border()
+    pe = port.plane_from_picture(g, clip.luma(1))
+    frefs, refs = [], []
+    for fr in (0, 2):
+        f = ctx.frame(w, h, pkg.FRAME_HPEL)
+        f.upload(clip.luma(fr)); f.expand_border(); f.filter()
+        frefs.append(f)
+        pr = port.plane_from_picture(g, clip.luma(fr))
+        fh, fv, fc, _ = port.frame_filter(g, pr, 0, want_integral=False)
+        refs.append([pr, fh, fv, fc])
+    for satd in (1, 0):
+        cases = bidir_cases(pkg, g, 66 + satd, 600)
+        jobs = np.zeros(len(cases), pkg.BIDIR_JOB)
+        for k, (j, mi, mvp0, mvp1, mv0, mv1, weight) in enumerate(cases):
+            jobs[k]["bx"], jobs[k]["by"], jobs[k]["i_pixel"], jobs[k]["qp"], jobs[k]["weight"] = mi.bx, mi.by, mi.i_pixel, mi.qp, weight
+            jobs[k]["flags"] = pkg.ME_MBCMP_SATD if satd else 0
+            jobs[k]["mv0"], jobs[k]["mv1"], jobs[k]["mvp0"], jobs[k]["mvp1"] = mv0, mv1, mvp0, mvp1
+            jobs[k]["mv_min_spel"] = [mi.mv_min_spel[0], mi.mv_min_spel[1]]
+            jobs[k]["mv_max_spel"] = [mi.mv_max_spel[0], mi.mv_max_spel[1]]
+        res = ctx.me_refine_bidir(fenc, frefs[0], frefs[1], jobs)
+        bad, moved = [], 0
+        for k, (j, mi, mvp0, mvp1, mv0, mv1, weight) in enumerate(cases):
+            a0, a1, cost = port.me_refine_bidir_satd(g, pe, refs[0], refs[1], mi, mvp0, mvp1, weight, satd, mv0, mv1)
+            got = (tuple(int(x) for x in res[k]["mv0"]), tuple(int(x) for x in res[k]["mv1"]), int(res[k]["cost"]))
+            if got != (a0, a1, cost):
+                bad.append((k, mi.i_pixel, got, (a0, a1, cost)))
+            moved += (a0, a1) != (tuple(mv0), tuple(mv1))
+        assert not bad, (satd, len(bad), bad[:4])
+        assert moved > 300
+    fenc.close()
+    for f in frefs:
+        f.close()

@@ -315,3 +315,45 @@ def test_refine_qpel(pkg, port, ref):
                 a = port.me_refine_qpel(g, pe, [pr, fh, fv, fc], ch, mi, subme, 1, mv, cost)
                 b = ref.me_refine_qpel(g, pe, [pr, fh, fv, fc], ch, mi, subme, 1, mv, cost)
                 assert (a.mv[0], a.mv[1], a.cost, a.cost_mv) == (b.mv[0], b.mv[1], b.cost, b.cost_mv), (i, subme, ch is not None, mi.i_pixel)
+
+
+def bidir_cases(pkg, g, seed, n):
+    """seeded (MeIn, mvp0, mvp1, mv0, mv1, weight) for the bidirectional refinement"""
+    from helpers import make_me_jobs
+    rng = np.random.default_rng(seed)
+    jobs, mis = make_me_jobs(pkg, g, seed=seed, n=n, me_range=16, qp=(12, 26, 40), pixels=(0, 1, 2, 3), mvp_spread=8, centre=(-20, -12))
+    out = []
+    for j, mi in zip(jobs, mis):
+        mi.bx, mi.by = (mi.bx // 8) * 8, (mi.by // 8) * 8
+        j["bx"], j["by"] = mi.bx, mi.by
+        mvp0 = [int(rng.integers(-10, 11)) - 20, int(rng.integers(-10, 11)) - 12]
+        mvp1 = [int(rng.integers(-10, 11)) + 20, int(rng.integers(-10, 11)) + 12]
+        mv0 = [mvp0[0] + int(rng.integers(-6, 7)), mvp0[1] + int(rng.integers(-6, 7))]
+        mv1 = [mvp1[0] + int(rng.integers(-6, 7)), mvp1[1] + int(rng.integers(-6, 7))]
+        if rng.integers(0, 25) == 0:
+            mv0[1] = mi.mv_max_spel[1] - int(rng.integers(0, 8))  # the early return of me.c:874-876
+        out.append((j, mi, mvp0, mvp1, mv0, mv1, int(rng.choice([32, 32, 21, 43, 27]))))
+    return out
+
+
+def test_refine_bidir_satd(pkg, port, ref):
+    """x264_me_refine_bidir_satd (me.c:843-927): 32 candidate pairs per pass in the reference's order, the aliasing visited map,
+    the quirk of clipping mvp[1] with the x limits"""
+    from x264_vs2008_b200 import synth
+    w, h = 160, 128
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=21)
+    pe = port.plane_from_picture(g, clip.luma(1))
+    refs = []
+    for fr in (0, 2):
+        pr = port.plane_from_picture(g, clip.luma(fr))
+        fh, fv, fc, _ = port.frame_filter(g, pr, 0, want_integral=False)
+        refs.append([pr, fh, fv, fc])
+    moved = 0
+    for j, mi, mvp0, mvp1, mv0, mv1, weight in bidir_cases(pkg, g, 55, 150):
+        for satd in (1, 0):
+            a0, a1, _ = port.me_refine_bidir_satd(g, pe, refs[0], refs[1], mi, mvp0, mvp1, weight, satd, mv0, mv1)
+            b0, b1, _ = ref.me_refine_bidir_satd(g, pe, refs[0], refs[1], mi, mvp0, mvp1, weight, satd, mv0, mv1)
+            assert (a0, a1) == (b0, b1), (mi.i_pixel, mvp0, mvp1, mv0, mv1, weight, satd)
+            moved += (a0, a1) != (tuple(mv0), tuple(mv1))
+    assert moved > 100

@@ -130,6 +130,7 @@ class Oracle:
         L.xo_frame_aq.argtypes = [C.POINTER(Geom), u8p, u8p, u8p, C.c_int, C.c_float, C.POINTER(C.c_float), u16p]
         L.xo_me_refine_qpel.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), C.POINTER(Chroma), C.POINTER(MeIn), C.c_int, C.c_int, i16p, C.c_int,
                                         C.POINTER(MeOut)]
+        L.xo_me_refine_bidir_satd.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), C.POINTER(u8p), C.POINTER(MeIn), i16p, i16p, C.c_int, C.c_int, i16p, i16p]
         L.xo_frame_deblock.argtypes = [C.POINTER(Geom), C.POINTER(DeblockIn), u8p, u8p, u8p, C.c_int]
         self.backend = L.xo_backend().decode()
 
@@ -249,6 +250,15 @@ class Oracle:
         mvv = np.array(mv, np.int16)
         self.lib.xo_me_refine_qpel(C.byref(g), _ptr(fenc, u8p, g.origin), arr, chp, C.byref(mi), subme, mbcmp_satd, _ptr(mvv, i16p), int(cost), C.byref(out))
         return out
+
+    def me_refine_bidir_satd(self, g, fenc, planes0, planes1, mi, mvp0, mvp1, weight, mbcmp_satd, mv0, mv1):
+        """-> (mv0, mv1, best cost or -1)"""
+        a0 = (u8p * 4)(*[_ptr(p, u8p, g.origin) for p in planes0])
+        a1 = (u8p * 4)(*[_ptr(p, u8p, g.origin) for p in planes1])
+        p0, p1, v0, v1 = (np.array(x, np.int16) for x in (mvp0, mvp1, mv0, mv1))
+        c = self.lib.xo_me_refine_bidir_satd(C.byref(g), _ptr(fenc, u8p, g.origin), a0, a1, C.byref(mi), _ptr(p0, i16p), _ptr(p1, i16p), weight, mbcmp_satd,
+                                             _ptr(v0, i16p), _ptr(v1, i16p))
+        return (int(v0[0]), int(v0[1])), (int(v1[0]), int(v1[1])), c
 
     def frame_deblock(self, g, info, y, u, v):
         """y: padded luma plane (flat, pixel 0,0 at g.origin); u, v: 2-D chroma arrays (contiguous).  Filtered in place."""

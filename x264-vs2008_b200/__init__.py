@@ -36,6 +36,10 @@ ME_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1")
 MC_BI_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("mv0", "<i2", (2,)), ("mv1", "<i2", (2,)), ("w", "u1"), ("h", "u1"), ("weight", "u1"),
                       ("reserved", "u1")])
 assert MC_BI_JOB.itemsize == 16
+BIDIR_JOB = np.dtype([("bx", "<i2"), ("by", "<i2"), ("i_pixel", "u1"), ("qp", "u1"), ("weight", "u1"), ("flags", "u1"), ("mv0", "<i2", (2,)),
+                      ("mv1", "<i2", (2,)), ("mvp0", "<i2", (2,)), ("mvp1", "<i2", (2,)), ("mv_min_spel", "<i2", (2,)), ("mv_max_spel", "<i2", (2,))])
+BIDIR_RESULT = np.dtype([("mv0", "<i2", (2,)), ("mv1", "<i2", (2,)), ("cost", "<i4")])
+assert BIDIR_JOB.itemsize == 32 and BIDIR_RESULT.itemsize == 12
 GRID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("cx", "<i2"), ("cy", "<i2"), ("mv_min_fpel", "<i2", (2,)), ("mv_max_fpel", "<i2", (2,)),
                      ("part_mask", "<u2"), ("reserved", "<u2")])
 assert GRID_JOB.itemsize == 20
@@ -123,6 +127,8 @@ def lib():
         L.x264_cuda_me_search_mb_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_finish.argtypes = [vp, vp, vp, ip, vp, vp, vp]
         L.x264_cuda_me_finish.restype = None
+        L.x264_cuda_me_refine_bidir.argtypes = [vp, vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_me_refine_bidir_dev.argtypes = [vp, vp, vp, vp, vp, ip, vp]
         L.x264_cuda_sad_grid.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_sad_grid_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_host_esa_replay.argtypes = [vp, ip, ip, ip, vp, ip, vp, vp]
@@ -309,6 +315,12 @@ class Context:
     def mc_blocks_bi(self, fref0, fref1, fdec, jobs):
         assert jobs.dtype == MC_BI_JOB
         self.check(lib().x264_cuda_mc_blocks_bi(self.h, fref0.h, fref1.h, fdec.h, jobs.ctypes.data, len(jobs)))
+
+    def me_refine_bidir(self, fenc, fref0, fref1, jobs):
+        assert jobs.dtype == BIDIR_JOB
+        out = np.zeros(len(jobs), BIDIR_RESULT)
+        self.check(lib().x264_cuda_me_refine_bidir(self.h, fenc.h, fref0.h, fref1.h, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
 
     def set_quant_preset(self, cqm):
         self.check(lib().x264_cuda_set_quant_preset(self.h, cqm))

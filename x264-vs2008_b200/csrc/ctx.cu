@@ -297,6 +297,17 @@ int x264_cuda_cost_tables(x264_cuda_t *ctx, const int16_t *const **d_ptrs)
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_cost_ptrs, 52 * sizeof(void *)));
         ctx->cost_ptrs_dirty = 1;
     }
+    // A job may name any qp: tables the caller has not uploaded (x264_cuda_set_cost_mv) are filled with the library's own
+    // x264_cuda_host_cost_mv — the same expression as x264_mb_analyse_load_costs, verified equal to the reference's for all 52 qps —
+    // so that no kernel ever dereferences a missing table.
+    for (int q = 0; q < 52; q++)
+        if (!ctx->d_cost_mv[q]) {
+            int16_t *t = (int16_t *)malloc((4 * 4 * 2048 + 1) * sizeof(int16_t));
+            x264_cuda_host_cost_mv(q, t);
+            const int rc = x264_cuda_set_cost_mv(ctx, q, t);
+            free(t);
+            if (rc) return -1;
+        }
     if (ctx->cost_ptrs_dirty) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cost_ptrs, ctx->d_cost_mv, 52 * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

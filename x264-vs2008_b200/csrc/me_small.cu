@@ -1187,3 +1187,166 @@ extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *
 {
     return x264_cuda_lowres_frame_cost_batch(ctx, 1, &fenc, &fref0, &fref1, pm, result);
 }
+
+// =====================================================================================================================
+// x264_me_refine_bidir_satd (S/encoder/me.c:843-927): joint quarter-pel refinement of a (list 0, list 1) vector pair against the
+// blended prediction.  One warp per partition: the 32 candidate pairs of a pass are spread over the lanes (U lanes per candidate, one
+// 8x4 unit each), their costs land in shared memory, and the reference's sequential part — the aliasing `visited` map (indices & 7)
+// and the strict-'<' scan in CHECK_BIDIR order — is then replayed over those 32 costs.
+// =====================================================================================================================
+namespace {
+
+__constant__ int8_t c_bidir_cand[32][4] = {
+    { 0, 0, 0, 1 }, { 0, 0, 0, -1 }, { 0, 0, 1, 0 }, { 0, 0, -1, 0 }, { 0, 1, 0, 0 }, { 0, -1, 0, 0 }, { 1, 0, 0, 0 }, { -1, 0, 0, 0 },   // CHECK_BIDIR8( 0, 0, 0, 1 )
+    { 0, 0, 1, 1 }, { 0, 0, -1, -1 }, { 0, 1, 1, 0 }, { 0, -1, -1, 0 }, { 1, 1, 0, 0 }, { -1, -1, 0, 0 }, { 1, 0, 0, 1 }, { -1, 0, 0, -1 }, // CHECK_BIDIR8( 0, 0, 1, 1 )
+    { 0, 1, 0, 1 }, { 0, -1, 0, -1 }, { 1, 0, 1, 0 }, { -1, 0, -1, 0 },                                                                 // CHECK_BIDIR2 x 2
+    { 0, 0, -1, 1 }, { 0, 0, 1, -1 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { 1, 0, 0, -1 }, { -1, 0, 0, 1 }, // CHECK_BIDIR8( 0, 0,-1, 1 )
+    { 0, -1, 0, 1 }, { 0, 1, 0, -1 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 } };                                                               // CHECK_BIDIR2 x 2
+
+struct BidirPlanes { const uint8_t *fenc; const uint8_t *ref0[4], *ref1[4]; int stride; };
+
+// mbcmp of one 8x4 unit of the blended prediction (h->mc.avg then pixf.mbcmp, me.c:802-803)
+__device__ __forceinline__ int bidir_unit(const uint8_t *fe, const QpelSrc &s0, const QpelSrc &s1, int stride, int ux, int uy, int weight, bool satd)
+{
+    uint2 f[4], r[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const ptrdiff_t o = (ptrdiff_t)(uy + y) * stride + ux;
+        f[y] = ldg8(fe + o);
+        const uint2 a = qpel_row8(s0, o), b = qpel_row8(s1, o);
+        if (weight == 32) r[y] = make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y));
+        else {
+            uint32_t w[2] = { 0, 0 };
+            const uint32_t xa[2] = { a.x, a.y }, xb[2] = { b.x, b.y };
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int pa = (xa[k >> 2] >> (8 * (k & 3))) & 255, pb = (xb[k >> 2] >> (8 * (k & 3))) & 255;
+                w[k >> 2] |= (uint32_t)clip_u8((pa * weight + pb * (64 - weight) + 32) >> 6) << (8 * (k & 3));
+            }
+            r[y] = make_uint2(w[0], w[1]);
+        }
+    }
+    if (satd) return satd_8x4_rows(f, r);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++) { acc = sad4_acc(f[y].x, r[y].x, acc); acc = sad4_acc(f[y].y, r[y].y, acc); }
+    return (int)acc;
+}
+
+__global__ void __launch_bounds__(128) me_bidir_kernel(BidirPlanes pl, const x264_cuda_bidir_job_t *__restrict__ jobs, int n_jobs,
+                                                       const int16_t *const *__restrict__ cost_tabs, x264_cuda_bidir_result_t *__restrict__ results)
+{
+    __shared__ uint8_t s_visited[4][512];
+    __shared__ int s_cost[4][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_jobs) return;
+    const x264_cuda_bidir_job_t job = jobs[j];
+    const int ip = min((int)job.i_pixel, 3);
+    const int bw = ip <= 1 ? 16 : 8, bh = (ip == 0 || ip == 2) ? 16 : 8;
+    const int U = unit_count(bw, bh), per = 32 / U, weight = job.weight;
+    const bool satd = job.flags & X264_CUDA_ME_MBCMP_SATD;
+    const int16_t *tab = cost_tabs[job.qp > 51 ? 51 : job.qp] + 2 * 4 * 2048;
+    const int lo = job.mv_min_spel[0], hi = job.mv_max_spel[0]; // the reference clips BOTH components of mvp with the x limits (me.c:854-857)
+    const int16_t *c0x = tab - clip3i(job.mvp0[0], lo, hi), *c0y = tab - clip3i(job.mvp0[1], lo, hi);
+    const int16_t *c1x = tab - clip3i(job.mvp1[0], lo, hi), *c1y = tab - clip3i(job.mvp1[1], lo, hi);
+    int bm0x = job.mv0[0], bm0y = job.mv0[1], bm1x = job.mv1[0], bm1y = job.mv1[1], bcost = COST_MAX;
+    x264_cuda_bidir_result_t res = { { (int16_t)bm0x, (int16_t)bm0y }, { (int16_t)bm1x, (int16_t)bm1y }, COST_MAX };
+    // table indices must stay inside p_cost_mv (+-2*4*2048): vectors move by at most 8 quarter-pels from here
+    const int lim = 2 * 4 * 2048 - 16;
+    const bool bad = abs(bm0x - clip3i(job.mvp0[0], lo, hi)) > lim || abs(bm0y - clip3i(job.mvp0[1], lo, hi)) > lim ||
+                     abs(bm1x - clip3i(job.mvp1[0], lo, hi)) > lim || abs(bm1y - clip3i(job.mvp1[1], lo, hi)) > lim;
+    if (bad || bm0y > job.mv_max_spel[1] - 8 || bm1y > job.mv_max_spel[1] - 8) { // me.c:874-876 (or unusable input: cost -1)
+        if (bad) res.cost = -1;
+        if (lane == 0) results[j] = res;
+        return;
+    }
+    const size_t off = (size_t)job.by * pl.stride + job.bx;
+    const uint8_t *fe = pl.fenc + off;
+    const uint8_t *const p0[4] = { pl.ref0[0] + off, pl.ref0[1] + off, pl.ref0[2] + off, pl.ref0[3] + off };
+    const uint8_t *const p1[4] = { pl.ref1[0] + off, pl.ref1[1] + off, pl.ref1[2] + off, pl.ref1[3] + off };
+    for (int i = lane; i < 128; i += 32) ((uint32_t *)s_visited[wid])[i] = 0;
+    __syncwarp();
+    auto pair_cost = [&](bool valid, int m0x, int m0y, int m1x, int m1y) { // all lanes of a candidate's group return its cost
+        int v = 0;
+        const int u = lane & (U - 1);
+        if (valid) {
+            int ux, uy;
+            unit_pos(bw, u, ux, uy);
+            const QpelSrc s0 = qpel_src(p0, pl.stride, m0x, m0y), s1 = qpel_src(p1, pl.stride, m1x, m1y);
+            v = bidir_unit(fe, s0, s1, pl.stride, ux, uy, weight, satd);
+        }
+        for (int o = U >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v + c0x[m0x] + c0y[m0y] + c1x[m1x] + c1y[m1y];
+    };
+    auto visit = [&](int m0x, int m0y, int m1x, int m1y, int pass) { // COST_BIMV_SATD's gate; returns "evaluate" (uniform)
+        uint8_t &cell = s_visited[wid][((m0x & 7) * 8 + (m0y & 7)) * 8 + (m1x & 7)];
+        const bool go = pass == 0 || !(cell & (1 << (m1y & 7)));
+        __syncwarp();
+        if (go && lane == 0) cell |= (uint8_t)(1 << (m1y & 7));
+        __syncwarp();
+        return go;
+    };
+    int om0x = bm0x, om0y = bm0y, om1x = bm1x, om1y = bm1y;
+    { // CHECK_BIDIR( 0, 0, 0, 0 ) with pass == 0
+        visit(om0x, om0y, om1x, om1y, 0);
+        bcost = __shfl_sync(0xffffffffu, pair_cost(lane < U, om0x, om0y, om1x, om1y), 0);
+    }
+    for (int pass = 0; pass < 8; pass++) {
+        for (int k0 = 0; k0 < 32; k0 += per) {
+            const int k = k0 + lane / U;
+            const int c = pair_cost(true, om0x + c_bidir_cand[k][0], om0y + c_bidir_cand[k][1], om1x + c_bidir_cand[k][2], om1y + c_bidir_cand[k][3]);
+            if ((lane & (U - 1)) == 0) s_cost[wid][k] = c;
+        }
+        __syncwarp();
+        for (int k = 0; k < 32; k++) { // the sequential part, in CHECK_BIDIR order
+            const int m0x = om0x + c_bidir_cand[k][0], m0y = om0y + c_bidir_cand[k][1], m1x = om1x + c_bidir_cand[k][2], m1y = om1y + c_bidir_cand[k][3];
+            if (visit(m0x, m0y, m1x, m1y, pass)) {
+                const int c = s_cost[wid][k];
+                if (c < bcost) { bcost = c; bm0x = m0x; bm0y = m0y; bm1x = m1x; bm1y = m1y; }
+            }
+        }
+        __syncwarp();
+        if (om0x == bm0x && om0y == bm0y && om1x == bm1x && om1y == bm1y) break;
+        om0x = bm0x; om0y = bm0y; om1x = bm1x; om1y = bm1y;
+    }
+    if (lane == 0) {
+        res.mv0[0] = (int16_t)bm0x; res.mv0[1] = (int16_t)bm0y; res.mv1[0] = (int16_t)bm1x; res.mv1[1] = (int16_t)bm1y; res.cost = bcost;
+        results[j] = res;
+    }
+}
+
+} // namespace
+
+extern "C" int x264_cuda_me_refine_bidir_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1,
+                                             const void *d_jobs, int n_jobs, void *d_results)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    if (!(fref0->g.flags & fref1->g.flags & X264_CUDA_FRAME_HPEL) || fref0->g.stride != fenc->g.stride || fref1->g.stride != fenc->g.stride) {
+        snprintf(ctx->err, 256, "x264_cuda_me_refine_bidir: both references need the half-pel planes and fenc's geometry");
+        return -1;
+    }
+    const int16_t *const *d_tabs;
+    if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
+    BidirPlanes pl;
+    pl.fenc = fenc->plane[0]; pl.stride = fenc->g.stride;
+    for (int k = 0; k < 4; k++) { pl.ref0[k] = fref0->plane[k]; pl.ref1[k] = fref1->plane[k]; }
+    me_bidir_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(pl, (const x264_cuda_bidir_job_t *)d_jobs, n_jobs, d_tabs, (x264_cuda_bidir_result_t *)d_results);
+    LAUNCH_CHECK(ctx, "me_bidir_kernel");
+    return 0;
+}
+
+extern "C" int x264_cuda_me_refine_bidir(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1,
+                                         const x264_cuda_bidir_job_t *jobs, int n_jobs, x264_cuda_bidir_result_t *results)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_bidir_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_bidir_result_t);
+    const size_t jb_al = (jb + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, jb_al + rb, jb_al + rb)) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    if (x264_cuda_jobs_in(ctx, ds, jobs, hs, jb)) return -1;
+    if (x264_cuda_me_refine_bidir_dev(ctx, fenc, fref0, fref1, ds, n_jobs, ds + jb_al)) return -1;
+    return x264_cuda_results_out(ctx, results, ds + jb_al, hs + jb_al, rb);
+}
