@@ -537,6 +537,11 @@ def run_rows(args):
     p_rj, p_coef = pinned(rj), pinned_out(n_mb * pkg.MB_COEFFS.itemsize)
     timed("a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB",
           lambda: ctx.check(L.x264_cuda_residual_inter(ctx.h, fenc.h, fdec.h, p_rj.data_ptr(), n_mb, p_coef.data_ptr())), reps=3)
+    sj = np.zeros(n_mb, pkg.SKIP_JOB)
+    sj["mb_x"], sj["mb_y"], sj["qp"], sj["chroma_qp"] = rj["mb_x"], rj["mb_y"], 26, 26
+    p_sj, p_skip = pinned(sj), pinned_out(n_mb)
+    key_s = "a14 skip probe (mc of the skip vector + dct, quant, decimate; luma + chroma), 8160 MB"
+    timed(key_s, lambda: ctx.check(L.x264_cuda_probe_skip(ctx.h, fenc.h, fref.h, None, p_sj.data_ptr(), n_mb, p_skip.data_ptr())))
     timed("f1 deblocking", lambda: ctx.frame_deblock(fdec, dinfo), reps=3)
     timed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)), reps=3)
     # candidate grids for the sequential-predictor use (host replay): all 9 partitions x 33 x 36 vectors per macroblock
@@ -656,6 +661,10 @@ def run_rows(args):
     for fy, fu, fv, py, pu, pv in blk:
         o.lib.xo_residual_inter_mb(C.byref(rin), X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(py), X._ptr(pu), X._ptr(pv), C.byref(rout))
     cpu["a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB"] = (time.perf_counter() - t0) / n_s * n_mb * 1e3
+    t0 = time.perf_counter()
+    for fy, fu, fv, py, pu, pv in blk:
+        o.lib.xo_probe_skip_mb(C.byref(rin), X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(py), X._ptr(pu), X._ptr(pv))
+    cpu[key_s] = (time.perf_counter() - t0) / n_s * n_mb * 1e3
     planes4 = (X.u8p * 4)(*[X._ptr(p_, X.u8p, og.origin + 64 * og.stride + 64) for p_ in (pr, fh, fv, fc)])
     dst, dstc = np.zeros((16, 16), np.uint8), np.zeros((8, 8), np.uint8)
     cup = np.ascontiguousarray(np.pad(u0, 16, mode="edge"))
@@ -677,6 +686,7 @@ def run_rows(args):
     del t_mc
     key_r = "a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB"
     cpu[key_r] = max(cpu[key_r] - t_call / 3 / n_s * n_mb * 1e3, 0.0)
+    cpu[key_s] = max(cpu[key_s] - t_call / 3 / n_s * n_mb * 1e3, 0.0)  # (the reference's mc of the skip vector is not in this figure)
     cpu["f1 deblocking, 4 frames in flight (per frame)"] = cpu["f1 deblocking"]
     cpu["a11 lowres P frame cost, 4 evaluations in flight (per evaluation)"] = cpu["a11 lowres P frame cost (intra + HEX/subme 4 search)"]
     cpu[key_b] = cpu["a11 lowres P frame cost (intra + HEX/subme 4 search)"]

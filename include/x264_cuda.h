@@ -119,6 +119,7 @@ X264_CUDA_API int x264_cuda_set_cost_mv(x264_cuda_t *ctx, int qp, const int16_t 
 /* host-side mirror of that table builder for standalone use (tests, bench): fills table[4*4*2048+1] */
 X264_CUDA_API void x264_cuda_host_cost_mv(int qp, int16_t *table);
 X264_CUDA_API int x264_cuda_host_lambda(int qp);
+X264_CUDA_API int x264_cuda_host_lambda2(int qp); /* x264_lambda2_tab[qp], S/encoder/analyse.c:150-160 */
 
 /* ------------------------------------------------------------------ motion search ------------------- */
 /* One job == one x264_me_search_ref() call (S/encoder/me.c:156-631) up to and including the ESA/TESA loop,
@@ -402,6 +403,30 @@ X264_CUDA_API int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_fra
                                            const x264_cuda_resid_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_t *coeffs);
 X264_CUDA_API int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
                                                const void *d_jobs, int n_jobs, void *d_coeffs);
+
+/* x264_macroblock_probe_skip (S/encoder/macroblock.c:797-883), frame-batched: skip[i] = 1 when macroblock i quantises to nothing
+ * against its skip prediction — luma decimation total < 6 (:822-840) and, for each chroma plane whose SSD reaches
+ * (x264_lambda2_tab[chroma_qp] + 32) >> 6, a zero 2x2 DC and an AC decimation total < 7 (:843-879).  Called per macroblock by
+ * x264_macroblock_analyse for P (analyse.c:2207 and :1111, with the pskip mv) and B (analyse.c:2489, b_bidir = 1) slices.
+ *   default               : the prediction is mc_luma(16x16) / mc_chroma(8x8) of (mvx, mvy) from fref (:809-819, :851-856); mvx/mvy are
+ *                           h->mb.cache.pskip_mv ALREADY clipped to h->mb.mv_min/mv_max (:812-813).  fref needs HPEL | CHROMA.
+ *   SKIP_PRED_IN_FDEC     : b_bidir = 1 — the prediction of that macroblock is already in fdec (e.g. from x264_cuda_mc_blocks_bi).
+ *   SKIP_STORE_PRED       : also write the motion-compensated prediction into fdec, the side effect h->mb.b_skip_mc = 1 relies on
+ *                           (the reference stops writing at its first early exit; here luma and chroma are always both written).
+ * fref may be NULL when every job has PRED_IN_FDEC, fdec may be NULL when no job has either flag. */
+#define X264_CUDA_SKIP_PRED_IN_FDEC 1
+#define X264_CUDA_SKIP_STORE_PRED   2
+typedef struct x264_cuda_skip_job_t {
+    int16_t mb_x, mb_y;
+    int16_t mvx, mvy;      /* quarter-pel */
+    uint8_t qp, chroma_qp; /* h->mb.i_qp, h->mb.i_chroma_qp */
+    uint8_t flags, reserved;
+} x264_cuda_skip_job_t;    /* 12 bytes */
+X264_CUDA_API int x264_cuda_probe_skip(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec,
+                                       const x264_cuda_skip_job_t *jobs, int n_jobs, uint8_t *skip);
+/* device-resident job list / result bytes; any_mc / any_fdec say whether some job needs fref / fdec (validated up front) */
+X264_CUDA_API int x264_cuda_probe_skip_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
+                                           x264_cuda_frame_t *fdec, const void *d_jobs, int n_jobs, int any_mc, int any_fdec, void *d_skip);
 
 /* ------------------------------------------------------------------ bidirectional refinement --------- */
 /* x264_me_refine_bidir_satd (S/encoder/me.c:843-927): joint quarter-pel refinement of the list-0 / list-1 vectors of one B partition

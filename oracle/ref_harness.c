@@ -436,6 +436,28 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
     }
 }
 
+/* the reference's own x264_macroblock_probe_skip on a hand-loaded macroblock, prediction already in p_fdec (b_bidir = 1) */
+extern const int x264_lambda2_tab[52];
+int xo_lambda2(int qp) { return x264_lambda2_tab[qp]; }
+int xo_probe_skip_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                     const uint8_t pred_y[256], const uint8_t pred_u[64], const uint8_t pred_v[64])
+{
+    xo_resid_in tmp = *in;
+    uint8_t ry[256], ru[64], rv[64];
+    xo_resid_out dummy;
+    tmp.b_transform_8x8 = 0;
+    memcpy(ry, pred_y, 256); memcpy(ru, pred_u, 64); memcpy(rv, pred_v, 64);
+    xo_residual_inter_mb(&tmp, fenc_y, fenc_u, fenc_v, ry, ru, rv, &dummy); /* opens / configures the handle */
+    x264_t *h = g_res_h[!!in->cqm][0];
+    for (int y = 0; y < 16; y++) memcpy(h->mb.pic.p_fdec[0] + FDEC_STRIDE * y, pred_y + 16 * y, 16);
+    for (int y = 0; y < 8; y++) {
+        memcpy(h->mb.pic.p_fdec[1] + FDEC_STRIDE * y, pred_u + 8 * y, 8);
+        memcpy(h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, pred_v + 8 * y, 8);
+    }
+    h->mb.i_qp = in->qp; h->mb.i_chroma_qp = in->chroma_qp;
+    return x264_macroblock_probe_skip(h, 1);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* lowres lookahead through the reference's own x264_rc_analyse_slice -> x264_slicetype_frame_cost   */
 #include "common/predict.h"

@@ -160,6 +160,12 @@ typedef struct {
 void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
                           uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out);
 
+/* x264_macroblock_probe_skip (S/encoder/macroblock.c:797-883) with the prediction supplied (b_bidir = 1); 1 = skippable.
+ * in->b_transform_8x8 / b_decimate are ignored (the probe always uses the 4x4 transform and the decimation scores). */
+int xo_probe_skip_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                     const uint8_t pred_y[256], const uint8_t pred_u[64], const uint8_t pred_v[64]);
+int xo_lambda2(int qp); /* x264_lambda2_tab[qp], S/encoder/analyse.c:151-160 */
+
 /* chroma planes for b_chroma_me (pixel (0,0) pointers; borders expanded by 16 like x264_frame_expand_border does for planes 1,2) */
 typedef struct { const uint8_t *fenc_u, *fenc_v, *fref_u, *fref_v; int stride_c; } xo_chroma;
 void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const uint16_t *integral,

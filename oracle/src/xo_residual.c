@@ -205,3 +205,69 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
     else if (out->nnz[25] | out->nnz[26]) cbp_chroma = 1;
     out->cbp_chroma = cbp_chroma;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * x264_macroblock_probe_skip (S/encoder/macroblock.c:797-883) on a prediction the caller has already formed
+ * (b_bidir = 1; the P-skip form only adds mc_luma / mc_chroma of the clipped pskip mv in front, :809-819, :851-856).
+ * Returns 1 when the macroblock would quantise to nothing (skippable). */
+int xo_lambda2(int qp)
+{
+    /* x264_lambda2_tab (S/encoder/analyse.c:151-160) restated as the closed form that generates it:
+     * floor(0.9 * 2^((qp-12)/3) * 256); checked against every entry of the reference table in tests/test_oracle_vs_ref.py */
+    static const double cbrt2[3] = { 1.0, 1.2599210498948732, 1.5874010519681994 };
+    double v = 0.9 * 256.0 * cbrt2[qp % 3];
+    int e = qp / 3 - 4;
+    for (; e > 0; e--) v *= 2.0;
+    for (; e < 0; e++) v *= 0.5;
+    return (int)v;
+}
+
+int xo_probe_skip_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                     const uint8_t pred_y[256], const uint8_t pred_u[64], const uint8_t pred_v[64])
+{
+    uint8_t fe[16 * 16], fd[32 * 16];
+    uint16_t mf[16], bias[16];
+    int16_t dct[16], scan[16];
+    int decimate_mb = 0;
+
+    /* luma: 16 4x4 blocks in block order, early out once the running score reaches 6 (:822-840) */
+    to_tiles(fe, fd, fenc_y, pred_y, 16);
+    xo_quant4_tables(in->cqm, 1, in->qp, mf, bias); /* CQM_4PY */
+    for (int i = 0; i < 16; i++) {
+        xo_sub4x4_dct(dct, fe + 4 * bx4[i] + 4 * by4[i] * 16, fd + 4 * bx4[i] + 4 * by4[i] * 32);
+        if (!xo_quant_4x4(dct, mf, bias)) continue;
+        xo_zigzag_scan_4x4(scan, dct);
+        decimate_mb += xo_decimate_score(scan, 16);
+        if (decimate_mb >= 6) return 0;
+    }
+
+    /* chroma (:843-879): planes whose SSD is under the lambda2 threshold are not examined at all */
+    const int cqp = in->chroma_qp;
+    const int thresh = (xo_lambda2(cqp) + 32) >> 6;
+    xo_quant4_tables(in->cqm, 3, cqp, mf, bias); /* CQM_4PC */
+    for (int ch = 0; ch < 2; ch++) {
+        const uint8_t *src = ch ? fenc_v : fenc_u, *prd = ch ? pred_v : pred_u;
+        int ssd = 0;
+        for (int k = 0; k < 64; k++) { int d = src[k] - prd[k]; ssd += d * d; }
+        if (ssd < thresh) continue;
+        int16_t dct4[4][16], dc[4];
+        to_tiles(fe, fd, src, prd, 8);
+        for (int i = 0; i < 4; i++)
+            xo_sub4x4_dct(dct4[i], fe + 4 * (i & 1) + 4 * (i >> 1) * 16, fd + 4 * (i & 1) + 4 * (i >> 1) * 32);
+        {
+            int d0 = dct4[0][0] + dct4[1][0], d1 = dct4[2][0] + dct4[3][0];
+            int d2 = dct4[0][0] - dct4[1][0], d3 = dct4[2][0] - dct4[3][0];
+            dc[0] = d0 + d1; dc[2] = d2 + d3; dc[1] = d0 - d1; dc[3] = d2 - d3;
+            for (int i = 0; i < 4; i++) dct4[i][0] = 0;
+        }
+        if (xo_quant_2x2_dc(dc, mf[0] >> 1, bias[0] << 1)) return 0;
+        decimate_mb = 0;
+        for (int i = 0; i < 4; i++) {
+            if (!xo_quant_4x4(dct4[i], mf, bias)) continue;
+            xo_zigzag_scan_4x4(scan, dct4[i]);
+            decimate_mb += xo_decimate_score(scan, 15);
+            if (decimate_mb >= 7) return 0;
+        }
+    }
+    return 1;
+}

@@ -276,3 +276,52 @@ def padded_chroma(g, c):
     xs = np.clip(np.arange(-16, W + 16), 0, c.shape[1] - 1)
     out[:] = c[np.ix_(ys, xs)]
     return out
+
+
+def skip_probe_cases(seed, n):
+    """macroblock (fenc, pred) tile pairs around the skip decision: pred = fenc + noise of a few amplitudes, flat offsets (DC-only
+    differences), single-pixel spikes, identical tiles.  -> list of (qp, chroma_qp, fy, fu, fv, py, pu, pv)"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        fy = rng.integers(0, 256, (16, 16), dtype=np.uint8)
+        fu = rng.integers(0, 256, (8, 8), dtype=np.uint8)
+        fv = rng.integers(0, 256, (8, 8), dtype=np.uint8)
+        kind = i % 6
+        amp = (0, 1, 2, 3, 6, 12)[int(rng.integers(0, 6))]
+
+        def near(a, amp):
+            if kind == 0:
+                return a.copy()
+            if kind == 1:   # flat offset: only the DC differs
+                return np.clip(a.astype(np.int32) + int(rng.integers(-amp, amp + 1)), 0, 255).astype(np.uint8)
+            if kind == 2:   # one spike
+                b = a.copy()
+                b[int(rng.integers(0, a.shape[0])), int(rng.integers(0, a.shape[1]))] ^= int(rng.integers(0, 64))
+                return b
+            if kind == 3:   # luma clean, chroma noisy (the SSD gate and chroma DC/AC exits decide)
+                amp2 = 0 if a.shape[0] == 16 else amp
+                return np.clip(a.astype(np.int32) + rng.integers(-amp2, amp2 + 1, a.shape), 0, 255).astype(np.uint8)
+            return np.clip(a.astype(np.int32) + rng.integers(-amp, amp + 1, a.shape), 0, 255).astype(np.uint8)
+        py, pu, pv = near(fy, amp), near(fu, amp), near(fv, amp)
+        qp = int(rng.integers(0, 52))
+        cqp = int(rng.integers(0, 52)) if i % 3 else min(qp, 39)
+        out.append((qp, cqp, fy, fu, fv, py, pu, pv))
+    return out
+
+
+def residual_digest(o, cases, cqm):
+    """run the inter residual driver and the skip probe over skip_probe_cases -> (int32 summary rows, uint8 skip flags); the summary row
+    of a case/flag pair is (cbp_luma, cbp_chroma, sum nnz, sum |coeff|, crc-ish weighted coefficient sum, sum of reconstructed pixels)"""
+    import xo_api as X
+    rows, skips = [], []
+    for (qp, cqp, fy, fu, fv, py, pu, pv) in cases:
+        for flags in range(4):
+            r, ry, ru, rv = o.residual_inter_mb(X.ResidIn(qp, cqp, flags & 1, flags >> 1, cqm), fy, fu, fv, py, pu, pv)
+            co = np.concatenate([np.array(r.luma8x8).reshape(-1) if flags & 1 else np.array(r.luma4x4)[:16].reshape(-1),
+                                 np.array(r.luma4x4)[16:].reshape(-1), np.array(r.chroma_dc).reshape(-1)]).astype(np.int64)
+            wsum = int((co * (np.arange(len(co)) % 251 + 1)).sum() & 0x7fffffff)
+            rows.append((r.cbp_luma, r.cbp_chroma, int(np.array(r.nnz).sum()), int(np.abs(co).sum()), wsum,
+                         int(ry.astype(np.int64).sum() + 3 * ru.astype(np.int64).sum() + 5 * rv.astype(np.int64).sum())))
+        skips.append(o.probe_skip_mb(X.ResidIn(qp, cqp, 0, 1, cqm), fy, fu, fv, py, pu, pv))
+    return np.array(rows, np.int32), np.array(skips, np.uint8)

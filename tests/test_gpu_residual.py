@@ -8,13 +8,7 @@ import xo_api as X
 pytestmark = pytest.mark.gpu
 
 
-class RIn(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("qp", "chroma_qp", "b_transform_8x8", "b_decimate", "cqm")]
-
-
-class ROut(C.Structure):
-    _fields_ = [("luma4x4", (C.c_int16 * 16) * 24), ("luma8x8", (C.c_int16 * 64) * 4), ("chroma_dc", (C.c_int16 * 4) * 2),
-                ("nnz", C.c_uint8 * 27), ("pad", C.c_uint8), ("cbp_luma", C.c_int), ("cbp_chroma", C.c_int)]
+RIn, ROut = X.ResidIn, X.ResidOut
 
 
 def _blocks(rng, n, bs):
@@ -131,3 +125,95 @@ def test_residual_inter_frame(pkg, ctx, port, cqm):
             assert np.array_equal(ry[my * 16:my * 16 + 16, mx * 16:mx * 16 + 16], py), tag
             assert np.array_equal(ru[my * 8:my * 8 + 8, mx * 8:mx * 8 + 8], pu) and np.array_equal(rv[my * 8:my * 8 + 8, mx * 8:mx * 8 + 8], pv), tag
     fenc.close(); fdec.close()
+
+
+@pytest.mark.parametrize("cqm", [0, 1])
+def test_probe_skip_pred_in_fdec(pkg, ctx, port, cqm):
+    """x264_macroblock_probe_skip, b_bidir form: tiles around the skip decision laid out as the macroblocks of a CIF frame pair"""
+    import helpers
+    w, h = 352, 288
+    mbw, mbh = w // 16, h // 16
+    cases = helpers.skip_probe_cases(70 + cqm, mbw * mbh)
+    fy, py = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint8)
+    fu, fv, pu, pv = (np.zeros((h // 2, w // 2), np.uint8) for _ in range(4))
+    jobs = np.zeros(len(cases), pkg.SKIP_JOB)
+    for i, (qp, cqp, a, b, c, d, e, f) in enumerate(cases):
+        mx, my = i % mbw, i // mbw
+        fy[my * 16:my * 16 + 16, mx * 16:mx * 16 + 16], py[my * 16:my * 16 + 16, mx * 16:mx * 16 + 16] = a, d
+        fu[my * 8:my * 8 + 8, mx * 8:mx * 8 + 8], pu[my * 8:my * 8 + 8, mx * 8:mx * 8 + 8] = b, e
+        fv[my * 8:my * 8 + 8, mx * 8:mx * 8 + 8], pv[my * 8:my * 8 + 8, mx * 8:mx * 8 + 8] = c, f
+        jobs[i] = (mx, my, 0, 0, qp, cqp, pkg.SKIP_PRED_IN_FDEC, 0)
+    fenc, fdec = ctx.frame(w, h, pkg.FRAME_CHROMA), ctx.frame(w, h, pkg.FRAME_CHROMA)
+    fenc.upload(fy); fenc.upload_chroma(fu, fv)
+    fdec.upload(py); fdec.upload_chroma(pu, pv)
+    ctx.set_quant_preset(cqm)
+    got = ctx.probe_skip(fenc, None, fdec, jobs)
+    want = np.array([port.probe_skip_mb(X.ResidIn(qp, cqp, 0, 1, cqm), a, b, c, d, e, f) for (qp, cqp, a, b, c, d, e, f) in cases], np.uint8)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (bad[:8], [cases[k][:2] for k in bad[:8]])
+    assert len(cases) // 5 < int(want.sum()) < 4 * len(cases) // 5
+    ctx.set_quant_preset(0)
+    fenc.close(); fdec.close()
+
+
+def test_probe_skip_mc(pkg, ctx, port):
+    """P-skip form: prediction = mc_luma / mc_chroma of the job's vector from the reference's half-pel and chroma planes, formed inside
+    the kernel (and stored to fdec on request)"""
+    from x264_vs2008_b200 import synth
+    from helpers import padded_chroma
+    w, h = 352, 288
+    mbw, mbh = w // 16, h // 16
+    clip = synth.Clip(w, h, seed=41, noise=1)
+    (y0, u0, v0), (y1, u1, v1) = clip.yuv420(0), clip.yuv420(1)
+    g = port.geometry(w, h)
+    fref = ctx.frame(w, h, pkg.FRAME_HPEL | pkg.FRAME_CHROMA)
+    fenc, fdec = ctx.frame(w, h, pkg.FRAME_CHROMA), ctx.frame(w, h, pkg.FRAME_CHROMA)
+    fref.upload(y0); fref.upload_chroma(u0, v0); fref.expand_border(); fref.filter()
+    fenc.upload(y1); fenc.upload_chroma(u1, v1)
+    plane = port.plane_from_picture(g, y0)
+    fh, fv, fc, _ = port.frame_filter(g, plane, 0, want_integral=False)
+    planes, cu, cv = [plane, fh, fv, fc], padded_chroma(g, u0), padded_chroma(g, v0)
+    rng = np.random.default_rng(8)
+    sent = np.full((h, w), 77, np.uint8)
+    for rep in range(3):
+        fdec.upload(sent); fdec.upload_chroma(sent[:h // 2, :w // 2], sent[:h // 2, :w // 2])
+        jobs = np.zeros(mbw * mbh, pkg.SKIP_JOB)
+        ey, eu, ev = y1.copy(), u1.copy(), v1.copy()
+        preds = []
+        for i in range(len(jobs)):
+            mx, my = i % mbw, i // mbw
+            mv = (0, 0) if rng.integers(0, 3) == 0 else (int(rng.integers(-6, 7)), int(rng.integers(-6, 7))) if rng.integers(0, 2) else \
+                (int(rng.integers(-60, 61)), int(rng.integers(-60, 61)))
+            jobs[i] = (mx, my, mv[0], mv[1], int(rng.integers(18, 52)), int(rng.integers(18, 52)), pkg.SKIP_STORE_PRED * int(rng.integers(0, 2)), 0)
+            py = np.zeros((16, 16), np.uint8)
+            arr = (X.u8p * 4)(*[X._ptr(p, X.u8p, g.origin + my * 16 * g.stride + mx * 16) for p in planes])
+            port.lib.xo_mc_luma(X._ptr(py), 16, arr, g.stride, mv[0], mv[1], 16, 16)
+            pc = []
+            for cp in (cu, cv):
+                t = np.zeros((8, 8), np.uint8)
+                port.lib.xo_mc_chroma(X._ptr(t), 8, X._ptr(cp, X.u8p, (16 + my * 8) * cp.shape[1] + 16 + mx * 8), cp.shape[1], mv[0], mv[1], 8, 8)
+                pc.append(t)
+            preds.append((py, pc[0], pc[1]))
+            if i % 4:  # most macroblocks: source = that prediction + a little noise, so the decision is close; the rest keep frame 1
+                amp = int(rng.integers(0, 4))
+                for dst, src, n in ((ey, py, 16), (eu, pc[0], 8), (ev, pc[1], 8)):
+                    dst[my * n:my * n + n, mx * n:mx * n + n] = np.clip(src.astype(np.int32) + rng.integers(-amp, amp + 1, src.shape), 0, 255)
+        fenc.upload(ey); fenc.upload_chroma(eu, ev)
+        got = ctx.probe_skip(fenc, fref, fdec, jobs)
+        ry, ru, rv = fdec.download(pkg.PLANE_FULL)[32:32 + h, 32:32 + w], fdec.download(pkg.PLANE_CB)[16:16 + h // 2, 16:16 + w // 2], \
+            fdec.download(pkg.PLANE_CR)[16:16 + h // 2, 16:16 + w // 2]
+        n1 = 0
+        for i, j in enumerate(jobs):
+            mx, my = int(j["mb_x"]), int(j["mb_y"])
+            py, pu, pv = preds[i]
+            tile = lambda a, n: np.ascontiguousarray(a[my * n:my * n + n, mx * n:mx * n + n])
+            want = port.probe_skip_mb(X.ResidIn(int(j["qp"]), int(j["chroma_qp"]), 0, 1, 0), tile(ey, 16), tile(eu, 8), tile(ev, 8), py, pu, pv)
+            assert int(got[i]) == want, (rep, i, int(j["mvx"]), int(j["mvy"]), int(j["qp"]), int(j["chroma_qp"]))
+            n1 += want
+            if int(j["flags"]) & pkg.SKIP_STORE_PRED:
+                assert np.array_equal(tile(ry, 16), py) and np.array_equal(tile(ru, 8), pu) and np.array_equal(tile(rv, 8), pv), (rep, i)
+            else:
+                assert (tile(ry, 16) == 77).all() and (tile(ru, 8) == 77).all() and (tile(rv, 8) == 77).all(), (rep, i)
+        assert len(jobs) // 8 < n1 < 7 * len(jobs) // 8, n1
+    for f in (fref, fenc, fdec):
+        f.close()

@@ -357,3 +357,40 @@ def test_refine_bidir_satd(pkg, port, ref):
             assert (a0, a1) == (b0, b1), (mi.i_pixel, mvp0, mvp1, mv0, mv1, weight, satd)
             moved += (a0, a1) != (tuple(mv0), tuple(mv1))
     assert moved > 100
+
+
+@pytest.mark.parametrize("cqm", [0, 1])
+def test_residual_inter_mb(port, ref, cqm):
+    """the inter branch of x264_macroblock_encode (+ chroma) on hand-loaded macroblocks: port vs the reference's own function"""
+    import helpers
+    for i, (qp, cqp, fy, fu, fv, py, pu, pv) in enumerate(helpers.skip_probe_cases(50 + cqm, 240)):
+        for flags in range(4):
+            rin = X.ResidIn(qp, min(cqp, 51), flags & 1, flags >> 1, cqm)
+            a, b = port.residual_inter_mb(rin, fy, fu, fv, py, pu, pv), ref.residual_inter_mb(rin, fy, fu, fv, py, pu, pv)
+            tag = (i, qp, cqp, flags)
+            assert (a[0].cbp_luma, a[0].cbp_chroma) == (b[0].cbp_luma, b[0].cbp_chroma), tag
+            assert bytes(a[0].nnz) == bytes(b[0].nnz), tag
+            if flags & 1:
+                assert np.array_equal(np.array(a[0].luma8x8), np.array(b[0].luma8x8)), tag
+                assert np.array_equal(np.array(a[0].luma4x4)[16:], np.array(b[0].luma4x4)[16:]), tag
+            else:
+                assert np.array_equal(np.array(a[0].luma4x4), np.array(b[0].luma4x4)), tag
+            assert np.array_equal(np.array(a[0].chroma_dc), np.array(b[0].chroma_dc)), tag
+            for k in (1, 2, 3):
+                assert np.array_equal(a[k], b[k]), tag
+
+
+@pytest.mark.parametrize("cqm", [0, 1])
+def test_probe_skip(port, ref, cqm):
+    """x264_macroblock_probe_skip (b_bidir form) + the lambda2 table its chroma gate reads"""
+    import helpers
+    for q in range(52):
+        assert port.lib.xo_lambda2(q) == ref.lib.xo_lambda2(q), q
+    n1 = 0
+    cases = helpers.skip_probe_cases(60 + cqm, 1500)
+    for i, (qp, cqp, fy, fu, fv, py, pu, pv) in enumerate(cases):
+        rin = X.ResidIn(qp, cqp, 0, 1, cqm)
+        a, b = port.probe_skip_mb(rin, fy, fu, fv, py, pu, pv), ref.probe_skip_mb(rin, fy, fu, fv, py, pu, pv)
+        assert a == b, (i, qp, cqp)
+        n1 += a
+    assert len(cases) // 5 < n1 < 4 * len(cases) // 5, n1  # both outcomes well represented

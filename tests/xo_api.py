@@ -64,6 +64,15 @@ class DeblockIn(C.Structure):
                 ("ref", C.c_void_p * 2), ("mv", C.c_void_p * 2)]
 
 
+class ResidIn(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("qp", "chroma_qp", "b_transform_8x8", "b_decimate", "cqm")]
+
+
+class ResidOut(C.Structure):
+    _fields_ = [("luma4x4", (C.c_int16 * 16) * 24), ("luma8x8", (C.c_int16 * 64) * 4), ("chroma_dc", (C.c_int16 * 4) * 2),
+                ("nnz", C.c_uint8 * 27), ("pad", C.c_uint8), ("cbp_luma", C.c_int), ("cbp_chroma", C.c_int)]
+
+
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
 i16p = C.POINTER(C.c_int16)
@@ -259,6 +268,17 @@ class Oracle:
         c = self.lib.xo_me_refine_bidir_satd(C.byref(g), _ptr(fenc, u8p, g.origin), a0, a1, C.byref(mi), _ptr(p0, i16p), _ptr(p1, i16p), weight, mbcmp_satd,
                                              _ptr(v0, i16p), _ptr(v1, i16p))
         return (int(v0[0]), int(v0[1])), (int(v1[0]), int(v1[1])), c
+
+    def residual_inter_mb(self, rin, fy, fu, fv, py, pu, pv):
+        """x264_macroblock_encode's inter branch on one macroblock -> (ResidOut, rec_y, rec_u, rec_v); inputs are contiguous uint8 tiles"""
+        o = ResidOut()
+        ry, ru, rv = py.copy(), pu.copy(), pv.copy()
+        self.lib.xo_residual_inter_mb(C.byref(rin), _ptr(fy), _ptr(fu), _ptr(fv), _ptr(ry), _ptr(ru), _ptr(rv), C.byref(o))
+        return o, ry, ru, rv
+
+    def probe_skip_mb(self, rin, fy, fu, fv, py, pu, pv):
+        """x264_macroblock_probe_skip with the prediction supplied -> 0/1"""
+        return int(self.lib.xo_probe_skip_mb(C.byref(rin), _ptr(fy), _ptr(fu), _ptr(fv), _ptr(py), _ptr(pu), _ptr(pv)))
 
     def frame_deblock(self, g, info, y, u, v):
         """y: padded luma plane (flat, pixel 0,0 at g.origin); u, v: 2-D chroma arrays (contiguous).  Filtered in place."""

@@ -19,6 +19,10 @@ RESID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("qp", "u1"), ("chroma_q
 MB_COEFFS = np.dtype([("luma", "<i2", (256,)), ("chroma_ac", "<i2", (8, 16)), ("chroma_dc", "<i2", (2, 4)), ("nnz", "u1", (27,)),
                       ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("reserved", "u1", (3,))], align=True)
 assert RESID_JOB.itemsize == 8 and MB_COEFFS.itemsize == 816
+SKIP_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("mvx", "<i2"), ("mvy", "<i2"), ("qp", "u1"), ("chroma_qp", "u1"), ("flags", "u1"),
+                     ("reserved", "u1")], align=True)
+assert SKIP_JOB.itemsize == 12
+SKIP_PRED_IN_FDEC, SKIP_STORE_PRED = 1, 2
 ME_SEEDED, ME_TESA, ME_FPEL_SATD = 1, 2, 4
 ME_MAX_MVC = 12
 
@@ -118,6 +122,9 @@ def lib():
         L.x264_cuda_set_cost_mv.argtypes = [vp, ip, vp]
         L.x264_cuda_host_cost_mv.argtypes = [ip, vp]
         L.x264_cuda_host_lambda.argtypes = [ip]
+        L.x264_cuda_host_lambda2.argtypes = [ip]
+        L.x264_cuda_probe_skip.argtypes = [vp, vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_probe_skip_dev.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, vp]
         L.x264_cuda_me_search.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_search_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_search_mb.argtypes = [vp, vp, vp, ip, vp, ip, vp]
@@ -343,6 +350,14 @@ class Context:
         self.check(lib().x264_cuda_block_dc(self.h, n, dc.ctypes.data, qp.ctypes.data, cat.ctypes.data, fwd.ctypes.data, level.ctypes.data,
                                             nz.ctypes.data, deq.ctypes.data))
         return dict(fwd=fwd, level=level, nz=nz, deq=deq)
+
+    def probe_skip(self, fenc, fref, fdec, jobs):
+        """x264_macroblock_probe_skip for a list of macroblocks -> uint8[n] (1 = skippable); fref / fdec may be None (see the header)"""
+        jobs = np.ascontiguousarray(jobs, SKIP_JOB)
+        out = np.zeros(len(jobs), np.uint8)
+        self.check(lib().x264_cuda_probe_skip(self.h, fenc.h, fref.h if fref else None, fdec.h if fdec else None, jobs.ctypes.data,
+                                              len(jobs), out.ctypes.data))
+        return out
 
     def residual_inter(self, fenc, fdec, jobs):
         jobs = np.ascontiguousarray(jobs, RESID_JOB)

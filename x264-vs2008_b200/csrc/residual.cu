@@ -5,6 +5,7 @@
 // Layout conventions follow the reference: coefficient blocks are stored TRANSPOSED (dct[i][k], dct.c:131-154),
 // every intermediate that the reference keeps in an int16_t array is narrowed to int16 at the same point.
 #include "dct_dev.cuh"
+#include "pixel_dev.cuh"
 
 namespace {
 
@@ -522,5 +523,182 @@ extern "C" int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_
     ctx->resid_no_dct8 = !any8;
     if (x264_cuda_residual_inter_dev(ctx, fenc, fdec, ds, n_jobs, ds + jb_al)) return -1;
     if (x264_cuda_results_out(ctx, coeffs, ds + jb_al, hs + jb_al, rb)) return -1;
+    return 0;
+}
+
+// =========================================================================================================
+// x264_macroblock_probe_skip (S/encoder/macroblock.c:797-883): would this macroblock quantise to nothing against the
+// P-skip (or B-direct) prediction?  ONE WARP PER MACROBLOCK with the lane roles of residual_inter_kernel: lanes 0..15
+// the luma 4x4 blocks, lanes 16..23 the chroma blocks.  The prediction is formed on the fly from the half-pel planes and
+// the 1/8-pel chroma taps (mc_luma / mc_chroma, macroblock.c:816-818, :851-856) or read from fdec (b_bidir = 1).  The
+// reference's early exits are sums of non-negative scores, so the warp evaluates every block and compares the totals.
+namespace {
+
+struct SkipPlanes {
+    const uint8_t *fe_y, *fe_u, *fe_v;
+    const uint8_t *ref[4], *ref_u, *ref_v;
+    uint8_t *fd_y, *fd_u, *fd_v;
+    int stride, stride_c;
+    uint16_t ssd_thresh[52]; // (x264_lambda2_tab[chroma qp] + 32) >> 6, macroblock.c:843
+};
+
+__global__ void __launch_bounds__(128) probe_skip_kernel(const QuantTables *__restrict__ qt, SkipPlanes pl,
+                                                         const x264_cuda_skip_job_t *__restrict__ jobs, int n_jobs, uint8_t *__restrict__ skip)
+{
+    const int lane = threadIdx.x & 31;
+    const int jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (jb >= n_jobs) return;
+    const x264_cuda_skip_job_t job = jobs[jb];
+    const int qp = min((int)job.qp, 51), cqp = min((int)job.chroma_qp, 51);
+    const bool in_fdec = job.flags & X264_CUDA_SKIP_PRED_IN_FDEC;
+    const bool store = !in_fdec && (job.flags & X264_CUDA_SKIP_STORE_PRED) && pl.fd_y;
+    const unsigned FULL = 0xffffffffu;
+
+    int score = 0, ssd = 0, dc0 = 0;
+    if (lane < 16) { // luma, macroblock.c:822-840
+        const int bx = (lane & 1) + ((lane >> 2) & 1) * 2, by = ((lane >> 1) & 1) + ((lane >> 3) & 1) * 2;
+        const size_t off = ((size_t)job.mb_y * 16 + by * 4) * pl.stride + job.mb_x * 16 + bx * 4;
+        int f[16], p[16], d[16], c[16];
+        load4x4(pl.fe_y + off, pl.stride, f);
+        if (in_fdec)
+            load4x4(pl.fd_y + off, pl.stride, p);
+        else {
+            const uint8_t *const planes[4] = { pl.ref[0] + off, pl.ref[1] + off, pl.ref[2] + off, pl.ref[3] + off };
+            const QpelSrc src = qpel_src(planes, pl.stride, job.mvx, job.mvy);
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                const uint32_t w = qpel_row4(src, (ptrdiff_t)y * pl.stride);
+#pragma unroll
+                for (int x = 0; x < 4; x++) p[y * 4 + x] = (w >> (8 * x)) & 255;
+                if (store) *(uint32_t *)(pl.fd_y + off + (size_t)y * pl.stride) = w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
+        fwd4x4(d, c);
+        const uint16_t *mf = qt->q4mf[1][qp], *bias = qt->q4bias[1][qp]; // CQM_4PY
+        int nz = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+        if (nz) {
+            int16_t lv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
+            score = decimate_score(lv, 0, 16);
+        }
+    } else if (lane < 24) { // chroma, macroblock.c:845-879
+        const int cl = lane - 16, ch = cl >> 2, bi = cl & 3;
+        const size_t off = ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * pl.stride_c + job.mb_x * 8 + (bi & 1) * 4;
+        int f[16], p[16], d[16], c[16];
+        load4x4((ch ? pl.fe_v : pl.fe_u) + off, pl.stride_c, f);
+        uint8_t *fd = (ch ? pl.fd_v : pl.fd_u);
+        if (in_fdec)
+            load4x4(fd + off, pl.stride_c, p);
+        else { // mc_chroma, mc.c:205-236
+            const int d8x = job.mvx & 7, d8y = job.mvy & 7;
+            const int cA = (8 - d8x) * (8 - d8y), cB = d8x * (8 - d8y), cC = (8 - d8x) * d8y, cD = d8x * d8y;
+            const uint8_t *s = (ch ? pl.ref_v : pl.ref_u) + off + (ptrdiff_t)(job.mvy >> 3) * pl.stride_c + (job.mvx >> 3);
+            int top[5];
+#pragma unroll
+            for (int x = 0; x < 5; x++) top[x] = s[x];
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                int bot[5];
+#pragma unroll
+                for (int x = 0; x < 5; x++) bot[x] = s[(size_t)(y + 1) * pl.stride_c + x];
+#pragma unroll
+                for (int x = 0; x < 4; x++) p[y * 4 + x] = (cA * top[x] + cB * top[x + 1] + cC * bot[x] + cD * bot[x + 1] + 32) >> 6;
+#pragma unroll
+                for (int x = 0; x < 5; x++) top[x] = bot[x];
+            }
+            if (store) store4x4(fd + off, pl.stride_c, p);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) { d[k] = f[k] - p[k]; ssd += d[k] * d[k]; }
+        fwd4x4(d, c);
+        dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
+        const uint16_t *mf = qt->q4mf[3][cqp], *bias = qt->q4bias[3][cqp]; // CQM_4PC
+        int nz = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+        if (nz) {
+            int16_t lv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
+            score = decimate_score(lv, 1, 16);
+        }
+    }
+
+    // luma total over lanes 0..15, per-plane chroma totals over lanes 16..19 / 20..23
+    int luma = lane < 16 ? score : 0;
+#pragma unroll
+    for (int o = 8; o; o >>= 1) luma += __shfl_xor_sync(FULL, luma, o);
+    luma = __shfl_sync(FULL, luma, 0);
+    int ac = score, sq = ssd;
+#pragma unroll
+    for (int o = 2; o; o >>= 1) { ac += __shfl_xor_sync(FULL, ac, o); sq += __shfl_xor_sync(FULL, sq, o); }
+    const int cb = lane & ~3;
+    const int b0 = __shfl_sync(FULL, dc0, cb), b1 = __shfl_sync(FULL, dc0, cb + 1), b2 = __shfl_sync(FULL, dc0, cb + 2),
+              b3 = __shfl_sync(FULL, dc0, cb + 3);
+    // dct2x2dc (macroblock.c:72-80) then quant_2x2_dc with the halved mf / doubled bias (:866)
+    const int d0 = b0 + b1, d1 = b2 + b3, d2 = b0 - b1, d3 = b2 - b3;
+    const int mfdc = qt->q4mf[3][cqp][0] >> 1, biasdc = qt->q4bias[3][cqp][0] << 1;
+    const int nz_dc = quant1(s16(d0 + d1), mfdc, biasdc) | quant1(s16(d0 - d1), mfdc, biasdc) | quant1(s16(d2 + d3), mfdc, biasdc) |
+                      quant1(s16(d2 - d3), mfdc, biasdc);
+    const bool plane_fails = lane >= 16 && lane < 24 && sq >= (int)pl.ssd_thresh[cqp] && (nz_dc != 0 || ac >= 7);
+    const unsigned fails = __ballot_sync(FULL, plane_fails);
+    if (lane == 0) skip[jb] = (uint8_t)(luma < 6 && fails == 0);
+}
+} // namespace
+
+extern "C" int x264_cuda_probe_skip_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec,
+                                        const void *d_jobs, int n_jobs, int any_mc, int any_fdec, void *d_skip)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    if (need_tables(ctx, false)) return -1;
+    if (!fenc->buf_chroma) {
+        snprintf(ctx->err, 256, "x264_cuda_probe_skip: fenc needs X264_CUDA_FRAME_CHROMA");
+        return -1;
+    }
+    if (any_mc && (!fref || !(fref->g.flags & X264_CUDA_FRAME_HPEL) || !fref->buf_chroma || fref->g.stride != fenc->g.stride)) {
+        snprintf(ctx->err, 256, "x264_cuda_probe_skip: the reference needs X264_CUDA_FRAME_HPEL | X264_CUDA_FRAME_CHROMA and fenc's geometry");
+        return -1;
+    }
+    if (any_fdec && (!fdec || !fdec->buf_chroma || fdec->g.stride != fenc->g.stride)) {
+        snprintf(ctx->err, 256, "x264_cuda_probe_skip: fdec needs X264_CUDA_FRAME_CHROMA and fenc's geometry");
+        return -1;
+    }
+    SkipPlanes pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.fe_y = fenc->plane[0]; pl.fe_u = fenc->chroma[0]; pl.fe_v = fenc->chroma[1];
+    if (fref) {
+        for (int k = 0; k < 4; k++) pl.ref[k] = fref->plane[k];
+        pl.ref_u = fref->chroma[0]; pl.ref_v = fref->chroma[1];
+    }
+    if (fdec && fdec->buf_chroma && fdec->g.stride == fenc->g.stride) { pl.fd_y = fdec->plane[0]; pl.fd_u = fdec->chroma[0]; pl.fd_v = fdec->chroma[1]; }
+    pl.stride = fenc->g.stride; pl.stride_c = fenc->stride_c;
+    for (int q = 0; q < 52; q++) pl.ssd_thresh[q] = (uint16_t)((x264_cuda_host_lambda2(q) + 32) >> 6);
+    probe_skip_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_qt, pl, (const x264_cuda_skip_job_t *)d_jobs, n_jobs, (uint8_t *)d_skip);
+    LAUNCH_CHECK(ctx, "probe_skip_kernel");
+    return 0;
+}
+
+extern "C" int x264_cuda_probe_skip(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, x264_cuda_frame_t *fdec,
+                                    const x264_cuda_skip_job_t *jobs, int n_jobs, uint8_t *skip)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_skip_job_t), jb_al = (jb + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, jb_al + n_jobs, jb_al + n_jobs)) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    int any_mc = 0, any_fdec = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        if (jobs[i].flags & X264_CUDA_SKIP_PRED_IN_FDEC) any_fdec = 1;
+        else { any_mc = 1; any_fdec |= jobs[i].flags & X264_CUDA_SKIP_STORE_PRED; }
+    }
+    if (x264_cuda_jobs_in(ctx, ds, jobs, hs, jb)) return -1;
+    if (x264_cuda_probe_skip_dev(ctx, fenc, fref, fdec, ds, n_jobs, any_mc, any_fdec, ds + jb_al)) return -1;
+    if (x264_cuda_results_out(ctx, skip, ds + jb_al, hs + jb_al, (size_t)n_jobs)) return -1;
     return 0;
 }

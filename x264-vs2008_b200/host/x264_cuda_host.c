@@ -13,6 +13,15 @@ int x264_cuda_host_lambda(int qp)
     return qp < 0 ? 1 : qp > 51 ? 91 : lambda_of_qp[qp];
 }
 
+/* lambda2 = lambda^2 * .9 * 256 with lambda = 2^(qp/6-2) unrounded: x264_lambda2_tab (S/encoder/analyse.c:150-160) is
+ * floor(0.9 * 256 * 2^((qp-12)/3)) for every qp, which is how it is produced here */
+int x264_cuda_host_lambda2(int qp)
+{
+    static const double cube_root_of_2_pow[3] = { 1.0, 1.2599210498948732, 1.5874010519681994 };
+    qp = qp < 0 ? 0 : qp > 51 ? 51 : qp;
+    return (int)ldexp(0.9 * 256.0 * cube_root_of_2_pow[qp % 3], qp / 3 - 4);
+}
+
 /* p_cost_mv[qp] exactly as x264_mb_analyse_load_costs builds it (S/encoder/analyse.c:40,192-203): the
  * reference's log2f is a macro around double log(), narrowed to float before the division by log(2).
  * In a drop-in integration the reference's own table is uploaded instead (x264_cuda_set_cost_mv). */
