@@ -428,6 +428,41 @@ X264_CUDA_API int x264_cuda_probe_skip(x264_cuda_t *ctx, const x264_cuda_frame_t
 X264_CUDA_API int x264_cuda_probe_skip_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
                                            x264_cuda_frame_t *fdec, const void *d_jobs, int n_jobs, int any_mc, int any_fdec, void *d_skip);
 
+/* ------------------------------------------------------------------ intra analysis from neighbouring macroblocks ------ */
+/* The two stages of intra analysis whose inputs are the source macroblock and reconstructed pixels of NEIGHBOURING macroblocks only:
+ *   - Intra16x16: every candidate of predict_16x16_mode_available (S/encoder/analyse.c:372-404) predicted (S/common/predict.c:40-170)
+ *     and costed  mbcmp[PIXEL_16x16] + lambda * bs_size_ue(mode)  — x264_mb_analyse_intra, analyse.c:612-664;
+ *   - chroma 8x8: every candidate of predict_8x8chroma_mode_available (:407-440), predictors predict.c:172-336, cost
+ *     mbcmp[PIXEL_8x8](U) + mbcmp[PIXEL_8x8](V) + lambda * bs_size_ue(mode) — x264_mb_analyse_intra_chroma, analyse.c:541-609.
+ * These are also the numbers the reference's optional table entries intra_mbcmp_x3_16x16 / intra_satd_x3_8x8c return
+ * (S/common/pixel.h:97-100; asm-only there, checked against predict + mbcmp by tools/checkasm.c:380-407).
+ * fdec holds the UNFILTERED reconstruction of the neighbours (row above, column left, corner of each listed macroblock: what
+ * x264_macroblock_cache_load puts around p_fdec: the intra_border_backup row and the previous macroblock's last column, S/common/macroblock.c:839-848, :1015-1021); the caller lists macroblocks whose neighbours are
+ * final — a wavefront diagonal, or every macroblock when the neighbourhood comes from another source.  The I4x4 / I8x8 stages need
+ * reconstructed blocks of the same macroblock and stay on the host. */
+#define X264_CUDA_INTRA_SATD    1 /* h->pixf.mbcmp == satd (subme > 1); else SAD */
+#define X264_CUDA_INTRA_SLICE_B 2 /* adds the B-slice mb-type prefix lambda * i_mb_b_cost_table[I_16x16] to best16 (analyse.c:659-661) */
+typedef struct x264_cuda_intra_job_t {
+    int16_t mb_x, mb_y;
+    uint8_t neighbour;     /* h->mb.i_neighbour: MB_LEFT 1 | MB_TOP 2 | MB_TOPRIGHT 4 | MB_TOPLEFT 8 (S/common/macroblock.h:28-34) */
+    uint8_t flags;
+    uint16_t lambda;       /* a->i_lambda = x264_lambda_tab[qp] (x264_cuda_host_lambda) */
+} x264_cuda_intra_job_t;   /* 8 bytes */
+typedef struct x264_cuda_intra_result_t {
+    int32_t cost16[7];     /* a->i_satd_i16x16_dir[mode], mode = enum intra16x16_pred_e (V H DC P DC_LEFT DC_TOP DC_128); -1: not a candidate */
+    int32_t cost_chroma[7];/* per enum intra_chroma_pred_e (DC H V P DC_LEFT DC_TOP DC_128); the reference stores these by list position in
+                            * a->i_satd_i8x8chroma_dir[i]; -1: not a candidate */
+    int32_t best16;        /* a->i_satd_i16x16 */
+    int32_t best_chroma;   /* a->i_satd_i8x8chroma */
+    uint8_t mode16;        /* a->i_predict16x16 */
+    uint8_t mode_chroma;   /* a->i_predict8x8chroma */
+    uint8_t reserved[2];
+} x264_cuda_intra_result_t;/* 68 bytes */
+X264_CUDA_API int x264_cuda_intra_mb_costs(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fdec,
+                                           const x264_cuda_intra_job_t *jobs, int n_jobs, x264_cuda_intra_result_t *results);
+X264_CUDA_API int x264_cuda_intra_mb_costs_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fdec,
+                                               const void *d_jobs, int n_jobs, void *d_results);
+
 /* ------------------------------------------------------------------ bidirectional refinement --------- */
 /* x264_me_refine_bidir_satd (S/encoder/me.c:843-927): joint quarter-pel refinement of the list-0 / list-1 vectors of one B partition
  * (16x16, 16x8, 8x16, 8x8) against the blended prediction, called by x264_mb_analyse_inter_b* refinement (analyse.c:2085-2105).

@@ -382,8 +382,9 @@ int xo_decimate_score(const int16_t *dct, int i_max)
  * p_fdec, b_skip_mc = 1) */
 #include "encoder/macroblock.h"
 static x264_t *g_res_h[2][2];
-void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
-                          uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out)
+/* opens (once per cqm / 8x8dct pair) and hand-loads a handle: P slice, P_L0 16x16, fenc tiles and the prediction in p_fdec */
+static x264_t *res_handle(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                          const uint8_t rec_y[256], const uint8_t rec_u[64], const uint8_t rec_v[64])
 {
     x264_t **ph = &g_res_h[!!in->cqm][!!in->b_transform_8x8], *h;
     if (!*ph) {
@@ -422,6 +423,13 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
         memcpy(h->mb.pic.p_fdec[1] + FDEC_STRIDE * y, rec_u + 8 * y, 8);
         memcpy(h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, rec_v + 8 * y, 8);
     }
+    return h;
+}
+
+void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                          uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out)
+{
+    x264_t *h = res_handle(in, fenc_y, fenc_u, fenc_v, rec_y, rec_u, rec_v);
     x264_macroblock_encode(h);
     memset(out, 0, sizeof(*out));
     memcpy(out->luma4x4, h->dct.luma4x4, sizeof(out->luma4x4));
@@ -436,6 +444,77 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
     }
 }
 
+/* intra mode costs with the reference's own predictors (x264_predict_16x16_init / x264_predict_8x8c_init tables) and mbcmp functions,
+ * on an FDEC_STRIDE tile loaded with the neighbour pixels; the candidate lists and the lambda terms are the few lines of glue around
+ * them in x264_mb_analyse_intra / _intra_chroma (static there), followed literally */
+static void load_tile(uint8_t *tile, const uint8_t *nb, int n)
+{
+    uint8_t *p = tile + FDEC_STRIDE + 16; /* block origin; row above and column left inside the tile */
+    p[-FDEC_STRIDE - 1] = nb[0];
+    memcpy(p - FDEC_STRIDE, nb + 1, n);
+    for (int y = 0; y < n; y++) p[y * FDEC_STRIDE - 1] = nb[1 + n + y];
+}
+static void ref_predict(int chroma, int mode, const uint8_t *nb, uint8_t *pred)
+{
+    static x264_predict_t p16[7], p8c[7];
+    static int init;
+    DECLARE_ALIGNED_16(uint8_t tile[FDEC_STRIDE * 17 + 32]);
+    if (!init) { x264_predict_16x16_init(0, p16); x264_predict_8x8c_init(0, p8c); init = 1; }
+    const int n = chroma ? 8 : 16;
+    memset(tile, 0xAA, sizeof(tile));
+    load_tile(tile, nb, n);
+    (chroma ? p8c : p16)[mode](tile + FDEC_STRIDE + 16);
+    for (int y = 0; y < n; y++) memcpy(pred + n * y, tile + FDEC_STRIDE + 16 + y * FDEC_STRIDE, n);
+}
+void xo_predict_16x16(int mode, const uint8_t nb[33], uint8_t pred[256]) { ref_predict(0, mode, nb, pred); }
+void xo_predict_8x8c(int mode, const uint8_t nb[17], uint8_t pred[64]) { ref_predict(1, mode, nb, pred); }
+
+void xo_intra_mb_costs(const xo_intra_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                       const uint8_t nb_y[33], const uint8_t nb_u[17], const uint8_t nb_v[17], xo_intra_out *out)
+{
+    static x264_pixel_function_t pixf;
+    static int init;
+    if (!init) { x264_pixel_init(0, &pixf); init = 1; }
+    x264_pixel_cmp_t *mbcmp = in->mbcmp_satd ? pixf.satd : pixf.sad;
+    DECLARE_ALIGNED_16(uint8_t fe[16 * FENC_STRIDE]);
+    DECLARE_ALIGNED_16(uint8_t fd[3][16 * 16]);
+    int predict_mode[4], i_max;
+    for (int i = 0; i < 7; i++) out->cost16[i] = out->cost_chroma[i] = -1;
+    out->best16 = out->best_chroma = COST_MAX;
+    out->mode16 = out->mode_chroma = 0;
+    const unsigned nbr = in->neighbour;
+    /* predict_16x16_mode_available, analyse.c:372-404 */
+    if (nbr & MB_TOPLEFT) { predict_mode[0] = I_PRED_16x16_V; predict_mode[1] = I_PRED_16x16_H; predict_mode[2] = I_PRED_16x16_DC; predict_mode[3] = I_PRED_16x16_P; i_max = 4; }
+    else if (nbr & MB_LEFT) { predict_mode[0] = I_PRED_16x16_DC_LEFT; predict_mode[1] = I_PRED_16x16_H; i_max = 2; }
+    else if (nbr & MB_TOP) { predict_mode[0] = I_PRED_16x16_DC_TOP; predict_mode[1] = I_PRED_16x16_V; i_max = 2; }
+    else { predict_mode[0] = I_PRED_16x16_DC_128; i_max = 1; }
+    for (int y = 0; y < 16; y++) memcpy(fe + FENC_STRIDE * y, fenc_y + 16 * y, 16);
+    for (int i = 0; i < i_max; i++) {
+        int m = predict_mode[i];
+        xo_predict_16x16(m, nb_y, fd[0]);
+        int c = mbcmp[PIXEL_16x16](fd[0], 16, fe, FENC_STRIDE) + in->lambda * bs_size_ue(x264_mb_pred_mode16x16_fix[m]);
+        out->cost16[m] = c;
+        if (c < out->best16) { out->best16 = c; out->mode16 = m; }
+    }
+    if (in->b_slice_b) out->best16 += in->lambda * 9;
+    /* predict_8x8chroma_mode_available, analyse.c:407-440 */
+    if (nbr & MB_TOPLEFT) { predict_mode[0] = I_PRED_CHROMA_V; predict_mode[1] = I_PRED_CHROMA_H; predict_mode[2] = I_PRED_CHROMA_DC; predict_mode[3] = I_PRED_CHROMA_P; i_max = 4; }
+    else if (nbr & MB_LEFT) { predict_mode[0] = I_PRED_CHROMA_DC_LEFT; predict_mode[1] = I_PRED_CHROMA_H; i_max = 2; }
+    else if (nbr & MB_TOP) { predict_mode[0] = I_PRED_CHROMA_DC_TOP; predict_mode[1] = I_PRED_CHROMA_V; i_max = 2; }
+    else { predict_mode[0] = I_PRED_CHROMA_DC_128; i_max = 1; }
+    for (int i = 0; i < i_max; i++) {
+        int m = predict_mode[i], c = in->lambda * bs_size_ue(x264_mb_pred_mode8x8c_fix[m]);
+        for (int ch = 0; ch < 2; ch++) {
+            const uint8_t *src = ch ? fenc_v : fenc_u;
+            for (int y = 0; y < 8; y++) memcpy(fe + FENC_STRIDE * y, src + 8 * y, 8);
+            xo_predict_8x8c(m, ch ? nb_v : nb_u, fd[1 + ch]);
+            c += mbcmp[PIXEL_8x8](fd[1 + ch], 8, fe, FENC_STRIDE);
+        }
+        out->cost_chroma[m] = c;
+        if (c < out->best_chroma) { out->best_chroma = c; out->mode_chroma = m; }
+    }
+}
+
 /* the reference's own x264_macroblock_probe_skip on a hand-loaded macroblock, prediction already in p_fdec (b_bidir = 1) */
 extern const int x264_lambda2_tab[52];
 int xo_lambda2(int qp) { return x264_lambda2_tab[qp]; }
@@ -443,18 +522,8 @@ int xo_probe_skip_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uin
                      const uint8_t pred_y[256], const uint8_t pred_u[64], const uint8_t pred_v[64])
 {
     xo_resid_in tmp = *in;
-    uint8_t ry[256], ru[64], rv[64];
-    xo_resid_out dummy;
     tmp.b_transform_8x8 = 0;
-    memcpy(ry, pred_y, 256); memcpy(ru, pred_u, 64); memcpy(rv, pred_v, 64);
-    xo_residual_inter_mb(&tmp, fenc_y, fenc_u, fenc_v, ry, ru, rv, &dummy); /* opens / configures the handle */
-    x264_t *h = g_res_h[!!in->cqm][0];
-    for (int y = 0; y < 16; y++) memcpy(h->mb.pic.p_fdec[0] + FDEC_STRIDE * y, pred_y + 16 * y, 16);
-    for (int y = 0; y < 8; y++) {
-        memcpy(h->mb.pic.p_fdec[1] + FDEC_STRIDE * y, pred_u + 8 * y, 8);
-        memcpy(h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, pred_v + 8 * y, 8);
-    }
-    h->mb.i_qp = in->qp; h->mb.i_chroma_qp = in->chroma_qp;
+    x264_t *h = res_handle(&tmp, fenc_y, fenc_u, fenc_v, pred_y, pred_u, pred_v);
     return x264_macroblock_probe_skip(h, 1);
 }
 

@@ -166,6 +166,26 @@ int xo_probe_skip_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uin
                      const uint8_t pred_y[256], const uint8_t pred_u[64], const uint8_t pred_v[64]);
 int xo_lambda2(int qp); /* x264_lambda2_tab[qp], S/encoder/analyse.c:151-160 */
 
+/* ---------------- intra analysis from neighbouring macroblocks: Intra16x16 and chroma 8x8 mode costs -----------------------------
+ * x264_mb_analyse_intra's 16x16 stage (S/encoder/analyse.c:612-664) and x264_mb_analyse_intra_chroma (:541-609).
+ * nb_*: [0] top-left, [1..n] row above, [n+1..2n] left column (n = 16 luma, 8 chroma) of the UNFILTERED reconstruction. */
+typedef struct {
+    int neighbour;  /* h->mb.i_neighbour: MB_LEFT 1, MB_TOP 2, MB_TOPRIGHT 4, MB_TOPLEFT 8 */
+    int lambda;     /* a->i_lambda */
+    int mbcmp_satd; /* h->pixf.mbcmp == satd (subme > 1) */
+    int b_slice_b;
+} xo_intra_in;
+typedef struct {
+    int cost16[7];      /* a->i_satd_i16x16_dir[mode] (mode = enum intra16x16_pred_e), -1 where the mode is not a candidate */
+    int cost_chroma[7]; /* cost of chroma mode (enum intra_chroma_pred_e), -1 where not a candidate */
+    int best16, best_chroma; /* a->i_satd_i16x16 (with the B-slice mb-type prefix), a->i_satd_i8x8chroma */
+    int mode16, mode_chroma; /* a->i_predict16x16, a->i_predict8x8chroma */
+} xo_intra_out;
+void xo_predict_16x16(int mode, const uint8_t nb[33], uint8_t pred[256]);
+void xo_predict_8x8c(int mode, const uint8_t nb[17], uint8_t pred[64]);
+void xo_intra_mb_costs(const xo_intra_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                       const uint8_t nb_y[33], const uint8_t nb_u[17], const uint8_t nb_v[17], xo_intra_out *out);
+
 /* chroma planes for b_chroma_me (pixel (0,0) pointers; borders expanded by 16 like x264_frame_expand_border does for planes 1,2) */
 typedef struct { const uint8_t *fenc_u, *fenc_v, *fref_u, *fref_v; int stride_c; } xo_chroma;
 void xo_me_search_subpel_chroma(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref_planes[4], const uint16_t *integral,

@@ -21,7 +21,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 pkg = ge.load_pkg()
 from x264_vs2008_b200 import synth  # noqa: E402
-from helpers import make_me_jobs, lowres_planes, oracle_lookahead, lookahead_digest, make_deblock_info, blocky_recon, skip_probe_cases, residual_digest  # noqa: E402
+from helpers import make_me_jobs, lowres_planes, oracle_lookahead, lookahead_digest, make_deblock_info, blocky_recon, skip_probe_cases, residual_digest, intra_cases, intra_digest  # noqa: E402
 
 
 LOOKAHEAD_GOLDEN = (("qcif_hex_satd", (176, 144), X.ME_HEX, 1, 0), ("qcif_dia_sad", (176, 144), X.ME_DIA, 0, 0),
@@ -138,6 +138,8 @@ def main():
     # ---- inter residual driver (x264_macroblock_encode) and x264_macroblock_probe_skip on tiles around the skip decision
     for cqm in (0, 1):
         out["resid_cqm%d_rows" % cqm], out["skip_cqm%d" % cqm] = residual_digest(r, skip_probe_cases(80 + cqm, 300), cqm)
+    # ---- Intra16x16 + chroma candidate costs through the reference's predict_16x16 / predict_8x8c tables and mbcmp functions
+    out["intra_costs"] = intra_digest(r, intra_cases(91, 400))
     out["lambda2_tab"] = np.array([r.lib.xo_lambda2(q) for q in range(52)], np.int32)
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")), "bytes")

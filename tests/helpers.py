@@ -325,3 +325,48 @@ def residual_digest(o, cases, cqm):
                          int(ry.astype(np.int64).sum() + 3 * ru.astype(np.int64).sum() + 5 * rv.astype(np.int64).sum())))
         skips.append(o.probe_skip_mb(X.ResidIn(qp, cqp, 0, 1, cqm), fy, fu, fv, py, pu, pv))
     return np.array(rows, np.int32), np.array(skips, np.uint8)
+
+
+def intra_cases(seed, n):
+    """(neighbour mask, lambda, satd?, slice_b?, fenc tiles, neighbour vectors) for the Intra16x16 / chroma cost stage: smooth ramps (the
+    plane predictor's home ground, incl. slopes that clip), flat, noise and 0/255 extremes; every neighbour-mask branch"""
+    rng = np.random.default_rng(seed)
+    out = []
+    masks = [0xF, 0xB, 0x1, 0x2, 0x0, 0x3, 0x5, 0x6, 0xA, 0x9]
+    for i in range(n):
+        kind = i % 5
+        yy, xx = np.mgrid[-1:16, -1:16]
+        if kind == 0:
+            big = rng.integers(0, 256, (17, 17))
+        elif kind == 1:   # ramp + noise
+            big = rng.integers(0, 256) + rng.integers(-20, 21) * xx + rng.integers(-20, 21) * yy + rng.integers(-3, 4, (17, 17))
+        elif kind == 2:
+            big = np.full((17, 17), int(rng.integers(0, 256))) + rng.integers(-2, 3, (17, 17))
+        elif kind == 3:   # extremes
+            big = rng.integers(0, 2, (17, 17)) * 255
+        else:             # gentle ramp
+            big = 128 + rng.integers(-4, 5) * xx + rng.integers(-4, 5) * yy + rng.integers(-1, 2, (17, 17))
+        big = np.clip(big, 0, 255).astype(np.uint8)
+        nby = np.concatenate([big[0, :1], big[0, 1:], big[1:, 0]]).astype(np.uint8)
+        fy = np.ascontiguousarray(big[1:, 1:])
+        if kind == 3 and i % 2:
+            fy = (255 - fy).astype(np.uint8)
+        chroma = []
+        for c in range(2):
+            b2 = np.clip(big[:9, :9].astype(np.int32) + rng.integers(-6, 7, (9, 9)), 0, 255).astype(np.uint8) if kind else \
+                rng.integers(0, 256, (9, 9), dtype=np.uint8)
+            chroma.append((np.ascontiguousarray(b2[1:, 1:]), np.concatenate([b2[0, :1], b2[0, 1:], b2[1:, 0]]).astype(np.uint8)))
+        lam = int(rng.choice([1, 1, 2, 4, 6, 10, 18, 32, 57, 91]))
+        out.append((masks[i % len(masks)] if i % 3 else 0xF, lam, int(rng.integers(0, 4) != 0), int(rng.integers(0, 2)), fy, chroma[0][0], chroma[1][0],
+                    nby, chroma[0][1], chroma[1][1]))
+    return out
+
+
+def intra_digest(o, cases):
+    """-> int32[n, 18]: cost16[7], cost_chroma[7], best16, best_chroma, mode16, mode_chroma of every case"""
+    import xo_api as X
+    rows = []
+    for (nbr, lam, satd, sb, fy, fu, fv, nby, nbu, nbv) in cases:
+        r = o.intra_mb_costs(X.IntraIn(nbr, lam, satd, sb), fy, fu, fv, nby, nbu, nbv).astuple()
+        rows.append(list(r[0]) + list(r[1]) + list(r[2:]))
+    return np.array(rows, np.int32)

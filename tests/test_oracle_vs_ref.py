@@ -394,3 +394,18 @@ def test_probe_skip(port, ref, cqm):
         assert a == b, (i, qp, cqp)
         n1 += a
     assert len(cases) // 5 < n1 < 4 * len(cases) // 5, n1  # both outcomes well represented
+
+
+def test_intra_predictors_and_mb_costs(port, ref):
+    """predict_16x16 / predict_8x8c (all seven modes each) and the Intra16x16 + chroma cost stage of x264_mb_analyse_intra(_chroma)"""
+    import helpers
+    modes16, modesc = set(), set()
+    for i, (nbr, lam, satd, sb, fy, fu, fv, nby, nbu, nbv) in enumerate(helpers.intra_cases(90, 600)):
+        for m in range(7):
+            assert np.array_equal(port.predict(0, m, nby), ref.predict(0, m, nby)), (i, "16x16", m)
+            assert np.array_equal(port.predict(1, m, nbu), ref.predict(1, m, nbu)), (i, "8x8c", m)
+        iin = X.IntraIn(nbr, lam, satd, sb)
+        a, b = port.intra_mb_costs(iin, fy, fu, fv, nby, nbu, nbv), ref.intra_mb_costs(iin, fy, fu, fv, nby, nbu, nbv)
+        assert a.astuple() == b.astuple(), (i, nbr, lam, satd, sb)
+        modes16.add(a.mode16); modesc.add(a.mode_chroma)
+    assert modes16 == set(range(7)) and modesc == set(range(7)), (modes16, modesc)  # every mode wins somewhere

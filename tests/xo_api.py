@@ -73,6 +73,18 @@ class ResidOut(C.Structure):
                 ("nnz", C.c_uint8 * 27), ("pad", C.c_uint8), ("cbp_luma", C.c_int), ("cbp_chroma", C.c_int)]
 
 
+class IntraIn(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("neighbour", "lambda_", "mbcmp_satd", "b_slice_b")]
+
+
+class IntraOut(C.Structure):
+    _fields_ = [("cost16", C.c_int * 7), ("cost_chroma", C.c_int * 7), ("best16", C.c_int), ("best_chroma", C.c_int),
+                ("mode16", C.c_int), ("mode_chroma", C.c_int)]
+
+    def astuple(self):
+        return (tuple(self.cost16), tuple(self.cost_chroma), self.best16, self.best_chroma, self.mode16, self.mode_chroma)
+
+
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
 i16p = C.POINTER(C.c_int16)
@@ -275,6 +287,18 @@ class Oracle:
         ry, ru, rv = py.copy(), pu.copy(), pv.copy()
         self.lib.xo_residual_inter_mb(C.byref(rin), _ptr(fy), _ptr(fu), _ptr(fv), _ptr(ry), _ptr(ru), _ptr(rv), C.byref(o))
         return o, ry, ru, rv
+
+    def intra_mb_costs(self, iin, fy, fu, fv, nby, nbu, nbv):
+        """Intra16x16 + chroma mode costs from neighbour pixels (nb*: corner, row above, left column) -> IntraOut"""
+        o = IntraOut()
+        self.lib.xo_intra_mb_costs(C.byref(iin), _ptr(fy), _ptr(fu), _ptr(fv), _ptr(nby), _ptr(nbu), _ptr(nbv), C.byref(o))
+        return o
+
+    def predict(self, chroma, mode, nb):
+        n = 8 if chroma else 16
+        out = np.zeros((n, n), np.uint8)
+        (self.lib.xo_predict_8x8c if chroma else self.lib.xo_predict_16x16)(mode, _ptr(nb), _ptr(out))
+        return out
 
     def probe_skip_mb(self, rin, fy, fu, fv, py, pu, pv):
         """x264_macroblock_probe_skip with the prediction supplied -> 0/1"""

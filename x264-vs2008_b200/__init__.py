@@ -23,6 +23,12 @@ SKIP_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("mvx", "<i2"), ("mvy", "
                      ("reserved", "u1")], align=True)
 assert SKIP_JOB.itemsize == 12
 SKIP_PRED_IN_FDEC, SKIP_STORE_PRED = 1, 2
+INTRA_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("neighbour", "u1"), ("flags", "u1"), ("lambda", "<u2")], align=True)
+INTRA_RESULT = np.dtype([("cost16", "<i4", (7,)), ("cost_chroma", "<i4", (7,)), ("best16", "<i4"), ("best_chroma", "<i4"), ("mode16", "u1"),
+                         ("mode_chroma", "u1"), ("reserved", "u1", (2,))], align=True)
+assert INTRA_JOB.itemsize == 8 and INTRA_RESULT.itemsize == 68
+INTRA_SATD, INTRA_SLICE_B = 1, 2
+MB_LEFT, MB_TOP, MB_TOPRIGHT, MB_TOPLEFT = 1, 2, 4, 8
 ME_SEEDED, ME_TESA, ME_FPEL_SATD = 1, 2, 4
 ME_MAX_MVC = 12
 
@@ -124,6 +130,8 @@ def lib():
         L.x264_cuda_host_lambda.argtypes = [ip]
         L.x264_cuda_host_lambda2.argtypes = [ip]
         L.x264_cuda_probe_skip.argtypes = [vp, vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_intra_mb_costs.argtypes = [vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_intra_mb_costs_dev.argtypes = [vp, vp, vp, vp, ip, vp]
         L.x264_cuda_probe_skip_dev.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, vp]
         L.x264_cuda_me_search.argtypes = [vp, vp, vp, ip, vp, ip, vp]
         L.x264_cuda_me_search_dev.argtypes = [vp, vp, vp, ip, vp, ip, vp]
@@ -350,6 +358,13 @@ class Context:
         self.check(lib().x264_cuda_block_dc(self.h, n, dc.ctypes.data, qp.ctypes.data, cat.ctypes.data, fwd.ctypes.data, level.ctypes.data,
                                             nz.ctypes.data, deq.ctypes.data))
         return dict(fwd=fwd, level=level, nz=nz, deq=deq)
+
+    def intra_mb_costs(self, fenc, fdec, jobs):
+        """Intra16x16 + chroma 8x8 candidate costs of the listed macroblocks from the neighbours in fdec -> INTRA_RESULT[n]"""
+        jobs = np.ascontiguousarray(jobs, INTRA_JOB)
+        out = np.zeros(len(jobs), INTRA_RESULT)
+        self.check(lib().x264_cuda_intra_mb_costs(self.h, fenc.h, fdec.h, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
 
     def probe_skip(self, fenc, fref, fdec, jobs):
         """x264_macroblock_probe_skip for a list of macroblocks -> uint8[n] (1 = skippable); fref / fdec may be None (see the header)"""
