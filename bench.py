@@ -542,6 +542,12 @@ def run_rows(args):
     p_sj, p_skip = pinned(sj), pinned_out(n_mb)
     key_s = "a14 skip probe (mc of the skip vector + dct, quant, decimate; luma + chroma), 8160 MB"
     timed(key_s, lambda: ctx.check(L.x264_cuda_probe_skip(ctx.h, fenc.h, fref.h, None, p_sj.data_ptr(), n_mb, p_skip.data_ptr())))
+    ij = np.zeros(n_mb, pkg.INTRA_JOB)
+    ij["mb_x"], ij["mb_y"], ij["flags"], ij["lambda"] = rj["mb_x"], rj["mb_y"], pkg.INTRA_SATD, 4
+    ij["neighbour"] = (ij["mb_x"] > 0) * 1 + (ij["mb_y"] > 0) * 2 + ((ij["mb_y"] > 0) & (ij["mb_x"] < g.mb_width - 1)) * 4 + ((ij["mb_x"] > 0) & (ij["mb_y"] > 0)) * 8
+    p_ij, p_ires = pinned(ij), pinned_out(n_mb * pkg.INTRA_RESULT.itemsize)
+    key_i = "f4 Intra16x16 + chroma 8x8 candidate costs (predict + SATD, up to 4 + 4 modes), 8160 MB"
+    timed(key_i, lambda: ctx.check(L.x264_cuda_intra_mb_costs(ctx.h, fenc.h, fdec.h, p_ij.data_ptr(), n_mb, p_ires.data_ptr())))
     timed("f1 deblocking", lambda: ctx.frame_deblock(fdec, dinfo), reps=3)
     timed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)), reps=3)
     # candidate grids for the sequential-predictor use (host replay): all 9 partitions x 33 x 36 vectors per macroblock
@@ -665,6 +671,13 @@ def run_rows(args):
     for fy, fu, fv, py, pu, pv in blk:
         o.lib.xo_probe_skip_mb(C.byref(rin), X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(py), X._ptr(pu), X._ptr(pv))
     cpu[key_s] = (time.perf_counter() - t0) / n_s * n_mb * 1e3
+    iin, iout = X.IntraIn(15, 4, 1, 0), X.IntraOut()
+    nbs = [(np.concatenate([py[0, :1], py[0], py[:, 0]]), np.concatenate([pu[0, :1], pu[0], pu[:, 0]]), np.concatenate([pv[0, :1], pv[0], pv[:, 0]]))
+           for _, _, _, py, pu, pv in blk]
+    t0 = time.perf_counter()
+    for (fy, fu, fv, _, _, _), (ny, nu, nv) in zip(blk, nbs):
+        o.lib.xo_intra_mb_costs(C.byref(iin), X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(ny), X._ptr(nu), X._ptr(nv), C.byref(iout))
+    cpu[key_i] = (time.perf_counter() - t0) / n_s * n_mb * 1e3
     planes4 = (X.u8p * 4)(*[X._ptr(p_, X.u8p, og.origin + 64 * og.stride + 64) for p_ in (pr, fh, fv, fc)])
     dst, dstc = np.zeros((16, 16), np.uint8), np.zeros((8, 8), np.uint8)
     cup = np.ascontiguousarray(np.pad(u0, 16, mode="edge"))
@@ -686,6 +699,7 @@ def run_rows(args):
     del t_mc
     key_r = "a12-a14 inter residual (dct, quant, decimate, dequant, idct), 8160 MB"
     cpu[key_r] = max(cpu[key_r] - t_call / 3 / n_s * n_mb * 1e3, 0.0)
+    cpu[key_i] = max(cpu[key_i] - t_call / 3 / n_s * n_mb * 1e3, 0.0)
     cpu[key_s] = max(cpu[key_s] - t_call / 3 / n_s * n_mb * 1e3, 0.0)  # (the reference's mc of the skip vector is not in this figure)
     cpu["f1 deblocking, 4 frames in flight (per frame)"] = cpu["f1 deblocking"]
     cpu["a11 lowres P frame cost, 4 evaluations in flight (per evaluation)"] = cpu["a11 lowres P frame cost (intra + HEX/subme 4 search)"]

@@ -13,6 +13,7 @@ CMP = C.CFUNCTYPE(C.c_int, u8p, C.c_int, u8p, C.c_int)
 CMP3 = C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, C.c_int, i32p)
 CMP4 = C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, u8p, C.c_int, i32p)
 VP = C.c_void_p
+INTRA3 = C.CFUNCTYPE(None, u8p, u8p, i32p)
 
 
 class PixelTable(C.Structure):
@@ -20,7 +21,9 @@ class PixelTable(C.Structure):
                 ("mbcmp_unaligned", CMP * 7), ("fpelcmp", CMP * 7), ("fpelcmp_x3", CMP3 * 7), ("fpelcmp_x4", CMP4 * 7),
                 ("sad_aligned", CMP * 7), ("var", VP * 4), ("hadamard_ac", VP * 4), ("ssim_4x4x2_core", VP), ("ssim_end4", VP),
                 ("sad_x3", CMP3 * 7), ("sad_x4", CMP4 * 7), ("satd_x3", CMP3 * 7), ("satd_x4", CMP4 * 7),
-                ("ads", C.CFUNCTYPE(C.c_int, i32p, u16p, C.c_int, u16p, i16p, C.c_int, C.c_int) * 7), ("intra", VP * 6)]
+                ("ads", C.CFUNCTYPE(C.c_int, i32p, u16p, C.c_int, u16p, i16p, C.c_int, C.c_int) * 7),
+                ("intra_mbcmp_x3_16x16", INTRA3), ("intra_satd_x3_16x16", INTRA3), ("intra_sad_x3_16x16", INTRA3), ("intra_satd_x3_8x8c", INTRA3),
+                ("intra_satd_x3_4x4", VP), ("intra_sa8d_x3_8x8", VP)]
 
 
 class DctTable(C.Structure):
@@ -63,7 +66,7 @@ def L(pkg, ctx):
 def test_pixel_table(pkg, L, port):
     t = PixelTable()
     assert L.x264_pixel_init_cuda(C.byref(t)) == 0
-    assert not t.var[0] and not t.ssim_end4 and not t.intra[0]  # entries outside the hot path are left to the C table
+    assert not t.var[0] and not t.ssim_end4 and not t.intra_satd_x3_4x4 and not t.intra_sa8d_x3_8x8  # left to the C table
     rng = np.random.default_rng(1)
     a = rng.integers(0, 256, (48, 64), dtype=np.uint8)
     b = rng.integers(0, 256, (48, 64), dtype=np.uint8)
@@ -94,6 +97,28 @@ def test_pixel_table(pkg, L, port):
             n1 = t.ads[ip](dc, P(sums, 0, u16p), 32, P(cost, 0, u16p), P(m1, 0, i16p), 28, thresh)
             n2 = port.lib.xo_pixel_ads(ip, dc, X._ptr(sums, X.u16p), 32, X._ptr(cost, X.u16p), X._ptr(m2, X.i16p), 28, thresh)
             assert n1 == n2 and np.array_equal(m1[:n1], m2[:n2]), ip
+
+
+def test_intra_x3_entries(pkg, L, port):
+    """intra_{satd,sad,mbcmp}_x3_16x16 / intra_satd_x3_8x8c the way checkasm tests them (S/tools/checkasm.c:380-407): against
+    predict + mbcmp of the first three modes, on an FDEC_STRIDE tile with the neighbours in place"""
+    import helpers
+    t = PixelTable()
+    assert L.x264_pixel_init_cuda(C.byref(t)) == 0
+    for i, (nbr, lam, satd, sb, fy, fu, fv, nby, nbu, nbv) in enumerate(helpers.intra_cases(95, 60)):
+        for n, fenc, nb, entries in ((16, fy, nby, (("intra_satd_x3_16x16", X.SATD), ("intra_sad_x3_16x16", X.SAD), ("intra_mbcmp_x3_16x16", X.SATD))),
+                                     (8, fu, nbu, (("intra_satd_x3_8x8c", X.SATD),))):
+            fe = np.zeros((16, 16), np.uint8); fe[:n, :n] = fenc
+            tile = np.full((17, 32), 0x55, np.uint8)   # block origin at (1, 16): row 0 is the row above, column 15 the left column
+            tile[0, 15], tile[0, 16:16 + n], tile[1:1 + n, 15] = nb[0], nb[1:1 + n], nb[1 + n:1 + 2 * n]
+            for name, metric in entries:
+                res = (C.c_int * 3)()
+                getattr(t, name)(P(fe), P(tile, 32 + 16), res)
+                want = []
+                for m in range(3):
+                    pred = np.zeros((16, 16), np.uint8); pred[:n, :n] = port.predict(n == 8, m, nb)
+                    want.append(port.pixel_cmp(metric, 0 if n == 16 else 3, pred, 16, fe, 16, 0, 0))
+                assert list(res) == want, (i, name)
 
 
 def test_dct_and_quant_tables(pkg, L, port):

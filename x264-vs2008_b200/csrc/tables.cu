@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include "dct_dev.cuh"
 #include "pixel_dev.cuh"
+#include "intra_dev.cuh"
 #include "../../include/x264_cuda_tables.h"
 
 namespace {
@@ -482,6 +483,53 @@ template <int METRIC> void fill_x4(x264_cuda_pixel_cmp_x4_t (&t)[7])
     t[4] = cmp_x4<METRIC, 4>; t[5] = cmp_x4<METRIC, 5>; t[6] = cmp_x4<METRIC, 6>;
 }
 
+// intra_{satd,sad}_x3_16x16 / intra_satd_x3_8x8c (S/common/pixel.h:97-100): the costs of the first three modes of the respective enum
+// (16x16: V H DC; chroma: DC H V) of one block against its neighbours.  One warp: lane = mode (0..2) x 8x4 unit.
+template <int N>
+__global__ void intra_x3_kernel(bool satd, const uint8_t *edges, const uint8_t *fenc, int *out)
+{
+    constexpr int UNITS = N == 16 ? 8 : 2;
+    const int lane = threadIdx.x, mi = lane / UNITS, u = lane % UNITS;
+    const int x0 = N == 16 ? (u & 1) * 8 : 0, y0 = N == 16 ? (u >> 1) * 4 : u * 4;
+    int cost = 0;
+    if (mi < 3) {
+        const int kind = N == 16 ? mi : (mi == 0 ? 2 : mi == 1 ? 1 : 0);
+        int dcq[4] = { 0, 0, 0, 0 };
+        if (kind == 2) {
+            if (N == 16) {
+                int s = 16;
+                for (int i = 0; i < 32; i++) s += edges[4 + i];
+                dcq[0] = s >> 5;
+            } else {
+                int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                for (int i = 0; i < 4; i++) { s0 += edges[4 + i]; s1 += edges[8 + i]; s2 += edges[12 + i]; s3 += edges[16 + i]; }
+                dcq[0] = (s0 + s2 + 4) >> 3; dcq[1] = (s1 + 2) >> 2; dcq[2] = (s3 + 2) >> 2; dcq[3] = (s1 + s3 + 4) >> 3;
+            }
+        }
+        uint2 f[4], r[4];
+        for (int k = 0; k < 4; k++) f[k] = *(const uint2 *)(fenc + (y0 + k) * 16 + x0);
+        predict_unit<N>(edges, kind, dcq, x0, y0, r);
+        cost = unit_metric(satd, f, r);
+    }
+    for (int o = 1; o < UNITS; o <<= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    if (mi < 3 && u == 0) out[mi] = cost;
+}
+
+// fenc at FENC_STRIDE, fdec at FDEC_STRIDE with its neighbours in place (row -1, column -1, corner)
+template <int N, bool SATD> void intra_x3(uint8_t *fenc, uint8_t *fdec, int res[3])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Stage st(256 + 64, 3 * sizeof(int));
+    pack_tile(st.h, fenc, 16, N, N);
+    uint8_t *e = st.h + 256; // IntraEdges layout: [3] corner, [4..4+N) top, [4+N..4+2N) left
+    e[3] = fdec[-32 - 1];
+    for (int i = 0; i < N; i++) { e[4 + i] = fdec[-32 + i]; e[4 + N + i] = fdec[i * 32 - 1]; }
+    st.up();
+    intra_x3_kernel<N><<<1, 32, 0, g_ctx->stream>>>(SATD, st.d + 256, st.d, (int *)st.dout());
+    st.down();
+    memcpy(res, st.hout(), 3 * sizeof(int));
+}
+
 } // namespace
 
 extern "C" int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf)
@@ -494,6 +542,11 @@ extern "C" int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf)
     pixf->ads[X264_CUDA_PIXEL_16x16] = ads_entry<4>;
     pixf->ads[X264_CUDA_PIXEL_16x8] = pixf->ads[X264_CUDA_PIXEL_8x16] = pixf->ads[X264_CUDA_PIXEL_8x4] = pixf->ads[X264_CUDA_PIXEL_4x8] = ads_entry<2>;
     pixf->ads[X264_CUDA_PIXEL_8x8] = pixf->ads[X264_CUDA_PIXEL_4x4] = ads_entry<1>;
+    // the merged intra cost entries the C table leaves NULL (pixel.c:664-667 sets them for mmxext): x264_mb_analyse_intra(_chroma) uses
+    // them when present (analyse.c:560, :627); mbcmp_init (encoder.c:608-618) re-aliases intra_mbcmp_x3_16x16 to the sad or satd one
+    pixf->intra_satd_x3_16x16 = pixf->intra_mbcmp_x3_16x16 = intra_x3<16, true>;
+    pixf->intra_sad_x3_16x16 = intra_x3<16, false>;
+    pixf->intra_satd_x3_8x8c = intra_x3<8, true>;
     return 0;
 }
 
