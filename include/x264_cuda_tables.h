@@ -6,9 +6,9 @@
  *     x264_mc_functions_t    S/common/mc.h:31-77            x264_quant_function_t S/common/quant.h:26-44
  * so a maintainer can pass &h->pixf etc. straight in (INTEGRATION.md shows the four call sites).  Like
  * x264_pixel_altivec_init (S/common/pixel.c:781-786) the *_init_cuda functions OVERRIDE entries of a table that
- * x264_*_init(cpu=0) has already filled with the C bodies; members this back-end does not implement (var, ssim,
- * hadamard_ac, intra_satd_x3_4x4, intra_sa8d_x3_8x8, mc_chroma, avg, copy, plane_copy, prefetch, memcpy, denoise, decimate, coeff_last/level_run,
- * zigzag) keep their C bodies, exactly as SURVEY.md §8(a) prescribes.
+ * x264_*_init(cpu=0) has already filled with the C bodies; members this back-end does not implement (ssim (unused), ssim_end4 (float),
+ * intra_satd_x3_4x4, intra_sa8d_x3_8x8, copy, plane_copy, prefetch, memcpy, integral_init*, denoise, decimate, coeff_last/level_run,
+ * zigzag) keep their C bodies.
  *
  * Every overridden entry runs on the GPU: operands are staged to the device, one kernel computes the result with the
  * same device functions the frame-batched entry points use, and the result is copied back.  They are correct drop-ins
@@ -119,10 +119,11 @@ typedef struct x264_cuda_mc_functions_t { /* == x264_mc_functions_t */
 /* Each returns 0, or -1 when no CUDA device is usable (table left as it was).  The per-call entries share one
  * process-wide device context (device = $X264_CUDA_DEVICE or 0), serialised by a mutex: re-entrant as the reference
  * requires (S/common/common.h:50), though not concurrent. */
-X264_CUDA_API int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf); /* sad, sad_aligned, ssd, satd, sa8d, sad_x3/x4, satd_x3/x4, ads, intra_{mbcmp,satd,sad}_x3_16x16, intra_satd_x3_8x8c */
+X264_CUDA_API int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf); /* sad, sad_aligned, ssd, satd, sa8d, sad_x3/x4, satd_x3/x4, ads, var, hadamard_ac,
+                                                                           * ssim_4x4x2_core, intra_{mbcmp,satd,sad}_x3_16x16, intra_satd_x3_8x8c */
 X264_CUDA_API int x264_dct_init_cuda(x264_cuda_dct_function_t *dctf);     /* all 14 entries */
 X264_CUDA_API int x264_quant_init_cuda(x264_cuda_quant_function_t *pf);   /* quant_*, dequant_* */
-X264_CUDA_API int x264_mc_init_cuda(x264_cuda_mc_functions_t *pf);        /* mc_luma, get_ref, hpel_filter, frame_init_lowres_core */
+X264_CUDA_API int x264_mc_init_cuda(x264_cuda_mc_functions_t *pf);        /* mc_luma, get_ref, mc_chroma, avg[10], hpel_filter, frame_init_lowres_core */
 X264_CUDA_API void x264_cuda_tables_shutdown(void);                       /* releases the shared context */
 
 #ifdef __cplusplus

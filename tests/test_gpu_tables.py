@@ -19,7 +19,8 @@ INTRA3 = C.CFUNCTYPE(None, u8p, u8p, i32p)
 class PixelTable(C.Structure):
     _fields_ = [("sad", CMP * 7), ("ssd", CMP * 7), ("satd", CMP * 7), ("ssim", CMP * 7), ("sa8d", CMP * 4), ("mbcmp", CMP * 7),
                 ("mbcmp_unaligned", CMP * 7), ("fpelcmp", CMP * 7), ("fpelcmp_x3", CMP3 * 7), ("fpelcmp_x4", CMP4 * 7),
-                ("sad_aligned", CMP * 7), ("var", VP * 4), ("hadamard_ac", VP * 4), ("ssim_4x4x2_core", VP), ("ssim_end4", VP),
+                ("sad_aligned", CMP * 7), ("var", C.CFUNCTYPE(C.c_int, u8p, C.c_int) * 4), ("hadamard_ac", C.CFUNCTYPE(C.c_uint64, u8p, C.c_int) * 4),
+                ("ssim_4x4x2_core", C.CFUNCTYPE(None, u8p, C.c_int, u8p, C.c_int, i32p)), ("ssim_end4", VP),
                 ("sad_x3", CMP3 * 7), ("sad_x4", CMP4 * 7), ("satd_x3", CMP3 * 7), ("satd_x4", CMP4 * 7),
                 ("ads", C.CFUNCTYPE(C.c_int, i32p, u16p, C.c_int, u16p, i16p, C.c_int, C.c_int) * 7),
                 ("intra_mbcmp_x3_16x16", INTRA3), ("intra_satd_x3_16x16", INTRA3), ("intra_sad_x3_16x16", INTRA3), ("intra_satd_x3_8x8c", INTRA3),
@@ -47,7 +48,8 @@ class QuantTable(C.Structure):
 class McTable(C.Structure):
     _fields_ = [("mc_luma", C.CFUNCTYPE(None, u8p, C.c_int, C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)),
                 ("get_ref", C.CFUNCTYPE(u8p, u8p, C.POINTER(C.c_int), C.POINTER(u8p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)),
-                ("mc_chroma", VP), ("avg", VP * 10), ("copy", VP * 7), ("copy_16x16_unaligned", VP), ("plane_copy", VP),
+                ("mc_chroma", C.CFUNCTYPE(None, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)),
+                ("avg", C.CFUNCTYPE(None, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int) * 10), ("copy", VP * 7), ("copy_16x16_unaligned", VP), ("plane_copy", VP),
                 ("hpel_filter", C.CFUNCTYPE(None, u8p, u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, i16p)),
                 ("prefetch_fenc", VP), ("prefetch_ref", VP), ("memcpy_aligned", VP), ("memzero_aligned", VP),
                 ("integral", VP * 4),
@@ -66,7 +68,7 @@ def L(pkg, ctx):
 def test_pixel_table(pkg, L, port):
     t = PixelTable()
     assert L.x264_pixel_init_cuda(C.byref(t)) == 0
-    assert not t.var[0] and not t.ssim_end4 and not t.intra_satd_x3_4x4 and not t.intra_sa8d_x3_8x8  # left to the C table
+    assert not t.ssim_end4 and not t.intra_satd_x3_4x4 and not t.intra_sa8d_x3_8x8 and not t.var[1] and not t.var[2]  # left to the C table (or NULL there too)
     rng = np.random.default_rng(1)
     a = rng.integers(0, 256, (48, 64), dtype=np.uint8)
     b = rng.integers(0, 256, (48, 64), dtype=np.uint8)
@@ -97,6 +99,28 @@ def test_pixel_table(pkg, L, port):
             n1 = t.ads[ip](dc, P(sums, 0, u16p), 32, P(cost, 0, u16p), P(m1, 0, i16p), 28, thresh)
             n2 = port.lib.xo_pixel_ads(ip, dc, X._ptr(sums, X.u16p), 32, X._ptr(cost, X.u16p), X._ptr(m2, X.i16p), 28, thresh)
             assert n1 == n2 and np.array_equal(m1[:n1], m2[:n2]), ip
+
+
+def test_stat_entries(pkg, L, port):
+    """var, hadamard_ac, ssim_4x4x2_core (checkasm.c:330-378, :409-431) incl. flat and extreme blocks"""
+    t = PixelTable()
+    assert L.x264_pixel_init_cuda(C.byref(t)) == 0
+    rng = np.random.default_rng(12)
+    for trial in range(40):
+        a = rng.integers(0, 256, (32, 64), dtype=np.uint8) if trial % 4 else np.full((32, 64), 255 * (trial % 8 == 0), np.uint8)
+        b = rng.integers(0, 256, (32, 64), dtype=np.uint8)
+        if trial % 5 == 1:
+            a[:] = ((np.add.outer(np.arange(32), np.arange(64)) & 1) * 255).astype(np.uint8)
+        off = int(rng.integers(0, 16)) * 64 + int(rng.integers(0, 40))
+        for ip in (0, 3):
+            assert t.var[ip](P(a, off), 64) == port.lib.xo_pixel_var(ip, X._ptr(a, X.u8p, off), 64), ("var", ip, trial)
+        for ip in range(4):
+            assert t.hadamard_ac[ip](P(a, off), 64) == port.lib.xo_pixel_hadamard_ac(ip, X._ptr(a, X.u8p, off), 64), ("hadamard_ac", ip, trial)
+        sums = (C.c_int * 8)()
+        t.ssim_4x4x2_core(P(a, off), 64, P(b, off), 64, sums)
+        want = np.zeros((1, 2, 4), np.int32)
+        port.lib.xo_frame_ssim_sums(X._ptr(a, X.u8p, off), 64, X._ptr(b, X.u8p, off), 64, 8, 4, X._ptr(want, X.i32p))
+        assert list(sums) == list(want.reshape(-1)), ("ssim", trial)
 
 
 def test_intra_x3_entries(pkg, L, port):
@@ -220,6 +244,24 @@ def test_mc_table(pkg, L, port):
     for k in range(4):
         for y in range(20):
             assert np.array_equal(outs[k][y * 64:y * 64 + 40], want[k][g.origin_lowres + y * g.stride_lowres:][:40])
+    # mc_chroma (checkasm.c:748-768) and avg with plain / implicit weights (:770-800)
+    rngc = np.random.default_rng(14)
+    src = rngc.integers(0, 256, (64, 64), dtype=np.uint8)
+    for (bw, bh) in ((8, 8), (8, 4), (4, 8), (4, 4), (4, 2), (2, 4), (2, 2)):
+        for _ in range(6):
+            mvx, mvy = int(rngc.integers(-60, 61)), int(rngc.integers(-60, 61))
+            d1, d2 = np.full((8, 16), 9, np.uint8), np.full((8, 16), 9, np.uint8)
+            m.mc_chroma(P(d1), 16, P(src, 24 * 64 + 24), 64, mvx, mvy, bw, bh)
+            port.lib.xo_mc_chroma(X._ptr(d2), 16, X._ptr(src, X.u8p, 24 * 64 + 24), 64, mvx, mvy, bw, bh)
+            assert np.array_equal(d1[:bh, :bw], d2[:bh, :bw]) and (d1[:, bw + 2:] == 9).all(), ("mc_chroma", bw, bh, mvx, mvy)
+    s1, s2 = rngc.integers(0, 256, (16, 32), dtype=np.uint8), rngc.integers(0, 256, (16, 48), dtype=np.uint8)
+    s1[0, :4], s2[0, :4] = (0, 255, 0, 255), (255, 0, 255, 0)
+    for ip, (bw, bh) in enumerate(((16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4), (4, 2), (2, 4), (2, 2))):
+        for weight in (32, 21, 43, 5, 59, -10, 74):
+            d1, d2 = np.full((16, 16), 7, np.uint8), np.full((16, 16), 7, np.uint8)
+            m.avg[ip](P(d1), 16, P(s1), 32, P(s2), 48, weight)
+            port.lib.xo_pixel_avg(ip, X._ptr(d2), 16, X._ptr(s1), 32, X._ptr(s2), 48, weight)
+            assert np.array_equal(d1, d2), ("avg", ip, weight)
     # mc_luma / get_ref at random qpel vectors (checkasm.c:702-746)
     rng = np.random.default_rng(4)
     planes = [plane, fh, fv, fc]

@@ -61,40 +61,6 @@ __global__ void __launch_bounds__(128) mb_energy_kernel(const uint8_t *__restric
     if (lane == 0) out[mb] = max(vy + vu + vv, 1u);
 }
 
-// pixel_hadamard_ac (pixel.c:306-341) of one 8x8 block, the reference's packed 2x16-bit arithmetic executed verbatim
-__device__ uint64_t hadamard_ac_8x8(const uint8_t *pix, int stride)
-{
-    uint32_t tmp[32];
-    uint32_t sum4 = 0, sum8 = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint2 r = __ldg((const uint2 *)(pix + (size_t)i * stride));
-        const uint32_t p0 = r.x & 255, p1 = (r.x >> 8) & 255, p2 = (r.x >> 16) & 255, p3 = r.x >> 24, p4 = r.y & 255, p5 = (r.y >> 8) & 255,
-                       p6 = (r.y >> 16) & 255, p7 = r.y >> 24;
-        const int t = (i & 3) + (i & 4) * 4;
-        const uint32_t a0 = (p0 + p1) + ((p0 - p1) << 16), a1 = (p2 + p3) + ((p2 - p3) << 16);
-        tmp[t] = a0 + a1; tmp[t + 4] = a0 - a1;
-        const uint32_t a2 = (p4 + p5) + ((p4 - p5) << 16), a3 = (p6 + p7) + ((p6 - p7) << 16);
-        tmp[t + 8] = a2 + a3; tmp[t + 12] = a2 - a3;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t a0, a1, a2, a3;
-        HADAMARD4_PK(a0, a1, a2, a3, tmp[i * 4 + 0], tmp[i * 4 + 1], tmp[i * 4 + 2], tmp[i * 4 + 3]);
-        tmp[i * 4 + 0] = a0; tmp[i * 4 + 1] = a1; tmp[i * 4 + 2] = a2; tmp[i * 4 + 3] = a3;
-        sum4 += abs2(a0) + abs2(a1) + abs2(a2) + abs2(a3);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t a0, a1, a2, a3;
-        HADAMARD4_PK(a0, a1, a2, a3, tmp[i], tmp[8 + i], tmp[16 + i], tmp[24 + i]);
-        sum8 += abs2(a0) + abs2(a1) + abs2(a2) + abs2(a3);
-    }
-    const uint32_t dc = (uint16_t)(tmp[0] + tmp[8] + tmp[16] + tmp[24]);
-    const int s4 = (int)((uint16_t)sum4 + (sum4 >> 16) - dc), s8 = (int)((uint16_t)sum8 + (sum8 >> 16) - dc);
-    return ((uint64_t)s8 << 32) + s4; // int -> uint64 conversions as in the reference (sum4 is added sign-extended)
-}
-
 // four threads per macroblock (its 8x8 quadrants), HADAMARD_AC(16,16) pixel.c:343-355
 __global__ void __launch_bounds__(128) mb_hadamard_ac_kernel(const uint8_t *__restrict__ py, int stride, int W, int n_mb, unsigned long long *__restrict__ out)
 {

@@ -515,6 +515,91 @@ __global__ void intra_x3_kernel(bool satd, const uint8_t *edges, const uint8_t *
     if (mi < 3 && u == 0) out[mi] = cost;
 }
 
+// ---- whole-block statistics on a staged 16x16 tile: var (pixel.c:141-160), hadamard_ac (:306-355), ssim_4x4x2_core (:431-458)
+__global__ void block_stat_kernel(int op, int w, int h, const uint8_t *a, const uint8_t *b, unsigned long long *out)
+{
+    if (op == 0) { // PIXEL_VAR_C: w x w, shift = log2(w*w)
+        uint32_t sum = 0, sqr = 0;
+        for (int y = 0; y < w; y++)
+            for (int x = 0; x < w; x += 4) { const uint32_t v = *(const uint32_t *)(a + y * 16 + x); sum = __dp4a(v, 0x01010101u, sum); sqr = __dp4a(v, v, sqr); }
+        out[0] = sqr - (sum * sum >> (w == 16 ? 8 : 6));
+    } else if (op == 1) { // HADAMARD_AC(w, h)
+        unsigned long long sum = 0;
+        for (int y = 0; y < h; y += 8)
+            for (int x = 0; x < w; x += 8) sum += hadamard_ac_8x8(a + y * 16 + x, 16);
+        out[0] = ((sum >> 34) << 32) + ((uint32_t)sum >> 1);
+    } else { // two horizontally adjacent 4x4 blocks: s1, s2, ss, s12 each
+        int *o = (int *)out;
+        for (int z = 0; z < 2; z++) {
+            uint32_t s1 = 0, s2 = 0, ss = 0, s12 = 0;
+            for (int y = 0; y < 4; y++) {
+                const uint32_t va = *(const uint32_t *)(a + y * 16 + 4 * z), vb = *(const uint32_t *)(b + y * 16 + 4 * z);
+                s1 = __dp4a(va, 0x01010101u, s1); s2 = __dp4a(vb, 0x01010101u, s2);
+                ss = __dp4a(va, va, ss); ss = __dp4a(vb, vb, ss); s12 = __dp4a(va, vb, s12);
+            }
+            o[4 * z] = (int)s1; o[4 * z + 1] = (int)s2; o[4 * z + 2] = (int)ss; o[4 * z + 3] = (int)s12;
+        }
+    }
+}
+unsigned long long block_stat(int op, int w, int h, const uint8_t *p1, int s1, const uint8_t *p2, int s2, int *sums)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Stage st(512, 32);
+    pack_tile(st.h, p1, s1, w, h);
+    if (p2) pack_tile(st.h + 256, p2, s2, w, h);
+    st.up();
+    block_stat_kernel<<<1, 1, 0, g_ctx->stream>>>(op, w, h, st.d, st.d + 256, (unsigned long long *)st.dout());
+    st.down();
+    if (sums) memcpy(sums, st.hout(), 32);
+    unsigned long long v;
+    memcpy(&v, st.hout(), 8);
+    return v;
+}
+template <int W> int t_var(uint8_t *pix, int stride) { return (int)(uint32_t)block_stat(0, W, W, pix, stride, nullptr, 0, nullptr); }
+template <int W, int H> uint64_t t_hadamard_ac(uint8_t *pix, int stride) { return block_stat(1, W, H, pix, stride, nullptr, 0, nullptr); }
+void t_ssim_4x4x2_core(const uint8_t *pix1, int stride1, const uint8_t *pix2, int stride2, int sums[2][4])
+{
+    block_stat(2, 8, 4, pix1, stride1, pix2, stride2, &sums[0][0]);
+}
+
+// ---- mc_chroma (mc.c:205-236) and the ten avg entries (mc.c:52-125) on staged tiles (stride 32 in, 16 out)
+__global__ void chroma_avg_kernel(int op, int w, int h, int p0, int p1, const uint8_t *a, const uint8_t *b, uint8_t *out)
+{
+    const int i = threadIdx.x;
+    if (i >= w * h) return;
+    const int y = i / w, x = i - y * w;
+    if (op == 0) { // p0, p1 = the 1/8-pel fractions
+        const int cA = (8 - p0) * (8 - p1), cB = p0 * (8 - p1), cC = (8 - p0) * p1, cD = p0 * p1;
+        const uint8_t *s = a + y * 32 + x;
+        out[y * 16 + x] = (uint8_t)((cA * s[0] + cB * s[1] + cC * s[32] + cD * s[33] + 32) >> 6);
+    } else { // p0 = weight of a
+        const int va = a[y * 16 + x], vb = b[y * 16 + x];
+        out[y * 16 + x] = p0 == 32 ? (uint8_t)((va + vb + 1) >> 1) : (uint8_t)clip_u8((va * p0 + vb * (64 - p0) + 32) >> 6);
+    }
+}
+void t_mc_chroma(uint8_t *dst, int i_dst, uint8_t *src, int i_src, int mvx, int mvy, int w, int h)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Stage st(32 * 17, 256);
+    const uint8_t *s = src + (ptrdiff_t)(mvy >> 3) * i_src + (mvx >> 3);
+    for (int y = 0; y <= h; y++) memcpy(st.h + 32 * y, s + (ptrdiff_t)y * i_src, w + 1);
+    st.up();
+    chroma_avg_kernel<<<1, 256, 0, g_ctx->stream>>>(0, w, h, mvx & 7, mvy & 7, st.d, nullptr, st.dout());
+    st.down();
+    for (int y = 0; y < h; y++) memcpy(dst + (ptrdiff_t)y * i_dst, st.hout() + 16 * y, w);
+}
+template <int W, int H> void t_avg(uint8_t *dst, int i_dst, uint8_t *src1, int i_src1, uint8_t *src2, int i_src2, int weight)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Stage st(512, 256);
+    pack_tile(st.h, src1, i_src1, W, H);
+    pack_tile(st.h + 256, src2, i_src2, W, H);
+    st.up();
+    chroma_avg_kernel<<<1, 256, 0, g_ctx->stream>>>(1, W, H, weight, 0, st.d, st.d + 256, st.dout());
+    st.down();
+    for (int y = 0; y < H; y++) memcpy(dst + (ptrdiff_t)y * i_dst, st.hout() + 16 * y, W);
+}
+
 // fenc at FENC_STRIDE, fdec at FDEC_STRIDE with its neighbours in place (row -1, column -1, corner)
 template <int N, bool SATD> void intra_x3(uint8_t *fenc, uint8_t *fdec, int res[3])
 {
@@ -547,6 +632,11 @@ extern "C" int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf)
     pixf->intra_satd_x3_16x16 = pixf->intra_mbcmp_x3_16x16 = intra_x3<16, true>;
     pixf->intra_sad_x3_16x16 = intra_x3<16, false>;
     pixf->intra_satd_x3_8x8c = intra_x3<8, true>;
+    // AQ / psy / SSIM primitives (pixel.c:597-613 wiring)
+    pixf->var[X264_CUDA_PIXEL_16x16] = t_var<16>; pixf->var[X264_CUDA_PIXEL_8x8] = t_var<8>;
+    pixf->hadamard_ac[X264_CUDA_PIXEL_16x16] = t_hadamard_ac<16, 16>; pixf->hadamard_ac[X264_CUDA_PIXEL_16x8] = t_hadamard_ac<16, 8>;
+    pixf->hadamard_ac[X264_CUDA_PIXEL_8x16] = t_hadamard_ac<8, 16>; pixf->hadamard_ac[X264_CUDA_PIXEL_8x8] = t_hadamard_ac<8, 8>;
+    pixf->ssim_4x4x2_core = t_ssim_4x4x2_core;
     return 0;
 }
 
@@ -572,6 +662,10 @@ extern "C" int x264_mc_init_cuda(x264_cuda_mc_functions_t *m)
 {
     { std::lock_guard<std::mutex> lk(g_mu); if (ensure_ctx()) return -1; }
     m->mc_luma = t_mc_luma; m->get_ref = t_get_ref; m->hpel_filter = t_hpel_filter; m->frame_init_lowres_core = t_frame_init_lowres_core;
+    // chroma MC and the bi-prediction averages, in the table's PIXEL_* order (mc.c:379-389)
+    m->mc_chroma = t_mc_chroma;
+    m->avg[0] = t_avg<16, 16>; m->avg[1] = t_avg<16, 8>; m->avg[2] = t_avg<8, 16>; m->avg[3] = t_avg<8, 8>; m->avg[4] = t_avg<8, 4>;
+    m->avg[5] = t_avg<4, 8>; m->avg[6] = t_avg<4, 4>; m->avg[7] = t_avg<4, 2>; m->avg[8] = t_avg<2, 4>; m->avg[9] = t_avg<2, 2>;
     return 0;
 }
 
