@@ -124,6 +124,7 @@ X264_CUDA_API int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf); /* sad
 X264_CUDA_API int x264_dct_init_cuda(x264_cuda_dct_function_t *dctf);     /* all 14 entries */
 X264_CUDA_API int x264_quant_init_cuda(x264_cuda_quant_function_t *pf);   /* quant_*, dequant_* */
 X264_CUDA_API int x264_mc_init_cuda(x264_cuda_mc_functions_t *pf);        /* mc_luma, get_ref, mc_chroma, avg[10], hpel_filter, frame_init_lowres_core */
+X264_CUDA_API long long x264_cuda_tables_launches(void);                  /* kernels launched by table entries so far (diagnostic) */
 X264_CUDA_API void x264_cuda_tables_shutdown(void);                       /* releases the shared context */
 
 #ifdef __cplusplus

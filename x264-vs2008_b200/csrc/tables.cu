@@ -669,6 +669,12 @@ extern "C" int x264_mc_init_cuda(x264_cuda_mc_functions_t *m)
     return 0;
 }
 
+extern "C" long long x264_cuda_tables_launches(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_ctx ? g_ctx->launches : 0;
+}
+
 extern "C" void x264_cuda_tables_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
