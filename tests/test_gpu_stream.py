@@ -14,13 +14,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "x264")
 CUD = os.path.join(ROOT, "oracle", "_ref", "x264_cuda")
 
+# frame sizes have an even macroblock width: for odd widths the reference's lowres planes contain never-written columns (frame.c:301)
 CONFIGS = [
-    ("config1_dia", 80, 64, 3, "--me dia --subme 1"),
-    ("hex_8x8dct_b", 80, 64, 4, "--me hex --subme 5 --8x8dct --bframes 1"),
-    ("esa", 80, 64, 2, "--me esa --merange 8 --subme 2"),                                                 # config 2's search
+    ("config1_dia", 96, 64, 3, "--me dia --subme 1"),
+    ("hex_8x8dct_b", 96, 64, 4, "--me hex --subme 5 --8x8dct --bframes 1"),
+    ("esa", 96, 64, 2, "--me esa --merange 8 --subme 2"),                                                 # config 2's search
+    ("esa_p4x4", 64, 48, 2, "--me esa --merange 8 --subme 2 --partitions all"),                           # 4x4 integral plane
     ("umh_rd_weightb", 64, 48, 5, "--me umh --subme 7 --8x8dct --bframes 2 --b-adapt 2 --weightb --mixed-refs --ref 2"),  # config 3
     ("tesa_b3", 64, 48, 5, "--me tesa --merange 8 --subme 6 --bframes 3 --b-adapt 2"),                    # config 4's options
-    ("cqm_jvt_qcif", 176, 144, 2, "--me hex --subme 4 --cqm jvt"),
+    ("cavlc_8x8dct_deblock", 96, 64, 3, "--me hex --subme 4 --no-cabac --8x8dct --deblock 2:-1 --chroma-qp-offset 3"),
+    ("cqm_jvt", 160, 128, 2, "--me hex --subme 4 --cqm jvt"),
+    ("crf_aq_lookahead", 96, 64, 5, "--crf 24 --me hex --subme 6 --bframes 2 --b-adapt 2"),               # lowres costs steer rate control
 ]
 
 
@@ -39,10 +43,10 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
         pytest.skip("oracle/_ref CLI builds not present (they are produced where the reference sources exist)")
     src = str(tmp_path / "in.yuv")
     _clip(pkg, w, h, n, src)
-    outs, launches = [], 0
+    outs, launches, frames = [], 0, None
     for exe in (REF, CUD):
         out = str(tmp_path / (os.path.basename(exe) + ".264"))
-        r = subprocess.run([exe, "--qp", "26", "--no-asm", "--threads", "1"] + opts.split() + ["-o", out, src, "%dx%d" % (w, h)],
+        r = subprocess.run([exe, "--no-asm", "--threads", "1"] + ([] if "--crf" in opts else ["--qp", "26"]) + opts.split() + ["-o", out, src, "%dx%d" % (w, h)],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         assert "encoded %d frames" % n in r.stderr + r.stdout
@@ -50,5 +54,13 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
         m = re.search(r"ref_cuda_shim: (\d+) device launches", r.stderr)
         if m:
             launches = int(m.group(1))
+        m = re.search(r"frame hooks: (\d+) lowres, (\d+) filter, (\d+) deblock frames recomputed on the device, (\d+) bytes compared equal", r.stderr)
+        if m:
+            frames = tuple(int(x) for x in m.groups())
     assert launches > 1000 * n, launches   # the table entries really ran on the device
+    # frame-level hooks: every input frame's lowres planes, every kept reference's deblocking + half-pel/integral planes were recomputed
+    # on the device from the encoder's own data, compared byte for byte inside the shim (it exits 4 on a mismatch) and used from then on
+    # (lowres planes exist only when the lookahead needs them: B-frame decision or CRF, encoder.c:711-716)
+    want_lowres = n if ("--bframes" in opts or "--crf" in opts) else 0
+    assert frames is not None and frames[0] == want_lowres and frames[1] >= 1 and frames[2] >= 1 and frames[3] > 0, frames
     assert len(outs[0]) > 500 and outs[0] == outs[1], (tag, len(outs[0]), len(outs[1]))
