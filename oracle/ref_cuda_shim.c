@@ -197,3 +197,196 @@ void x264_frame_deblock_row(x264_t *h, int mb_y)
     }
     n_deblock++;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Motion-search hooks: every full-resolution x264_me_search_ref, x264_me_refine_qpel and x264_me_refine_bidir_satd call of the live
+ * encoder is repeated on the device as a one-job batch through the C ABI (x264_cuda_me_search / _me_search_small /
+ * _me_refine_bidir) with the encoder's own predictors, limits and cost table, and must return the same vector and costs.
+ * Device frames are kept per (x264_frame_t, frame number): source pictures as they are, references border-expanded and filtered
+ * on the device.  Lowres (lookahead) searches and searches with a half-pel early-exit threshold (multi-reference P16x16, analyse.c:
+ * 1095-1100: the threshold is carried across calls) are left to the C path.  Off with X264_CUDA_ME_HOOKS=0. */
+#include "encoder/me.h"
+void x264_me_search_ref_c(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh);
+void x264_me_refine_qpel_c(x264_t *h, x264_me_t *m);
+void x264_me_refine_bidir_satd_c(x264_t *h, x264_me_t *m0, x264_me_t *m1, int i_weight);
+extern int16_t *g_cost_mv[52];
+
+typedef struct { x264_frame_t *f; int frame, poc, is_ref; x264_cuda_frame_t *d; long long used; } dev_slot;
+static dev_slot slots[8];
+static long long slot_clock, n_search, n_qpel, n_bidir, n_skipped;
+static int cost_uploaded[52];
+
+static int me_hooks_on(void)
+{
+    const char *e = getenv("X264_CUDA_ME_HOOKS");
+    return (!e || atoi(e)) && hooks_on();
+}
+static void report_me(void)
+{
+    fprintf(stderr, "ref_cuda_shim: me hooks: %lld searches, %lld qpel refinements, %lld bidir refinements repeated on the device and equal; %lld left to C\n",
+            n_search, n_qpel, n_bidir, n_skipped);
+}
+static x264_cuda_frame_t *dev_frame(x264_t *h, x264_frame_t *f, int is_ref)
+{
+    static int once;
+    if (!once++) atexit(report_me);
+    frame_ctx(h, f);
+    dev_slot *victim = &slots[0];
+    for (int i = 0; i < 8; i++) {
+        dev_slot *s = &slots[i];
+        if (s->d && s->f == f && s->frame == f->i_frame && s->poc == f->i_poc && s->is_ref == is_ref) { s->used = ++slot_clock; return s->d; }
+        if (s->used < victim->used) victim = s;
+    }
+    if (!victim->d) {
+        x264_cuda_geom_t g;
+        x264_cuda_frame_geometry(ffr, &g);
+        victim->d = x264_cuda_frame_new(fctx, f->i_width[0], f->i_lines[0], g.flags);
+        if (!victim->d) ck(-1, "x264_cuda_frame_new");
+    }
+    victim->f = f; victim->frame = f->i_frame; victim->poc = f->i_poc; victim->is_ref = is_ref; victim->used = ++slot_clock;
+    ck(x264_cuda_frame_upload(fctx, victim->d, f->plane[0], f->i_stride[0], f->i_width[0], f->i_lines[0]), "upload");
+    ck(x264_cuda_frame_upload_chroma(fctx, victim->d, X264_CUDA_PLANE_CB, f->plane[1], f->i_stride[1], f->i_width[1], f->i_lines[1]), "upload cb");
+    ck(x264_cuda_frame_upload_chroma(fctx, victim->d, X264_CUDA_PLANE_CR, f->plane[2], f->i_stride[2], f->i_width[2], f->i_lines[2]), "upload cr");
+    if (is_ref) {
+        ck(x264_cuda_frame_expand_border(fctx, victim->d), "expand_border");
+        if (h->param.analyse.i_subpel_refine) ck(x264_cuda_frame_filter(fctx, victim->d), "frame_filter");
+    }
+    return victim->d;
+}
+/* which reference frame (and block position) does m->p_fref[0] point into?  NULL for lowres / unknown */
+static x264_frame_t *find_ref(x264_t *h, const x264_me_t *m, int *bx, int *by)
+{
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < (l ? h->i_ref1 : h->i_ref0); i++) {
+            x264_frame_t *f = l ? h->fref1[i] : h->fref0[i];
+            const ptrdiff_t off = m->p_fref[0] - f->plane[0];
+            const ptrdiff_t lim = (ptrdiff_t)f->i_stride[0] * f->i_lines[0];
+            if (off >= 0 && off < lim && m->i_stride[0] == f->i_stride[0]) { *bx = (int)(off % f->i_stride[0]); *by = (int)(off / f->i_stride[0]); return f; }
+        }
+    return NULL;
+}
+static int qp_of(const x264_me_t *m)
+{
+    for (int q = 0; q < 52; q++)
+        if (g_cost_mv[q] && g_cost_mv[q] + 2 * 4 * 2048 == m->p_cost_mv) {
+            if (!cost_uploaded[q]) { ck(x264_cuda_set_cost_mv(fctx, q, g_cost_mv[q]), "set_cost_mv"); cost_uploaded[q] = 1; } /* the reference's own table */
+            return q;
+        }
+    return -1;
+}
+static int fenc_pos_ok(x264_t *h, const x264_me_t *m, int bx, int by)
+{
+    const ptrdiff_t off = m->p_fenc[0] - h->mb.pic.p_fenc[0];
+    return off >= 0 && off < 16 * FENC_STRIDE && bx == 16 * h->mb.i_mb_x + (int)(off % FENC_STRIDE) && by == 16 * h->mb.i_mb_y + (int)(off / FENC_STRIDE);
+}
+static int me_flags(x264_t *h)
+{
+    return (h->pixf.mbcmp[0] == h->pixf.satd[0] ? X264_CUDA_ME_MBCMP_SATD : 0) | (h->pixf.fpelcmp[0] == h->pixf.satd[0] ? X264_CUDA_ME_FPEL_SATD : 0) |
+           (h->mb.b_chroma_me ? X264_CUDA_ME_CHROMA : 0);
+}
+static void fill_limits(x264_t *h, x264_cuda_me_job_t *j)
+{
+    for (int k = 0; k < 2; k++) {
+        j->mv_min_fpel[k] = h->mb.mv_min_fpel[k]; j->mv_max_fpel[k] = h->mb.mv_max_fpel[k];
+        j->mv_min_spel[k] = h->mb.mv_min_spel[k]; j->mv_max_spel[k] = h->mb.mv_max_spel[k];
+    }
+}
+static void me_differs(const char *what, x264_t *h, const x264_me_t *m, const x264_cuda_me_final_t *d, int bx, int by)
+{
+    fprintf(stderr, "ref_cuda_shim: %s differs at frame %d block (%d,%d) pixel %d method %d subme %d: reference mv (%d,%d) cost %d cost_mv %d, device mv (%d,%d) "
+            "cost %d cost_mv %d\n", what, h->fenc->i_frame, bx, by, m->i_pixel, h->mb.i_me_method, h->mb.i_subpel_refine, m->mv[0], m->mv[1], m->cost, m->cost_mv,
+            d->mv[0], d->mv[1], d->cost, d->cost_mv);
+    exit(5);
+}
+
+void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh)
+{
+    x264_cuda_me_job_t j;
+    x264_cuda_frame_t *dref = NULL, *denc = NULL;
+    int bx = 0, by = 0, qp = -1, ok = me_hooks_on() && !h->sh.b_mbaff && !p_halfpel_thresh && i_mvc <= X264_CUDA_ME_MAX_MVC;
+    const int method = h->mb.i_me_method, subme = h->mb.i_subpel_refine;
+    if (ok) {
+        x264_frame_t *fr = find_ref(h, m, &bx, &by);
+        ok = fr && fenc_pos_ok(h, m, bx, by) && !(method == X264_ME_ESA && subme >= 3);
+        if (ok) { frame_ctx(h, fr); qp = qp_of(m); ok = qp >= 0; }
+        if (ok) {
+            dref = dev_frame(h, fr, 1); denc = dev_frame(h, h->fenc, 0);
+            memset(&j, 0, sizeof(j));
+            j.bx = bx; j.by = by; j.i_pixel = m->i_pixel; j.qp = qp; j.i_mvc = i_mvc; j.flags = me_flags(h);
+            j.mvp[0] = m->mvp[0]; j.mvp[1] = m->mvp[1];
+            for (int k = 0; k < i_mvc; k++) { j.mvc[k][0] = mvc[k][0]; j.mvc[k][1] = mvc[k][1]; }
+            fill_limits(h, &j);
+        }
+    }
+    x264_me_search_ref_c(h, m, mvc, i_mvc, p_halfpel_thresh);
+    if (!ok) { n_skipped++; return; }
+    x264_cuda_me_final_t fin;
+    const int range = h->param.analyse.i_me_range;
+    if (method == X264_ME_ESA) { /* full-pel stage as its own job, then the "-> qpel" + refine_subpel tail seeded with its winner */
+        x264_cuda_me_result_t r;
+        ck(x264_cuda_me_search(fctx, denc, dref, range, &j, 1, &r), "me_search");
+        j.seed_mv[0] = r.bmx; j.seed_mv[1] = r.bmy; j.seed_cost = r.bcost;
+        ck(x264_cuda_me_search_small(fctx, denc, dref, X264_CUDA_ME_METHOD_SEEDED, range, subme, &j, 1, &fin), "me_search_small (seeded)");
+    } else
+        ck(x264_cuda_me_search_small(fctx, denc, dref, method == X264_ME_TESA ? X264_CUDA_ME_METHOD_TESA : method, range, subme, &j, 1, &fin), "me_search_small");
+    if (fin.mv[0] != m->mv[0] || fin.mv[1] != m->mv[1] || fin.cost != m->cost || fin.cost_mv != m->cost_mv) me_differs("x264_me_search_ref", h, m, &fin, bx, by);
+    n_search++;
+}
+
+void x264_me_refine_qpel(x264_t *h, x264_me_t *m)
+{
+    x264_cuda_me_job_t j;
+    x264_cuda_frame_t *dref = NULL, *denc = NULL;
+    int bx = 0, by = 0, qp = -1, ok = me_hooks_on() && !h->sh.b_mbaff;
+    if (ok) {
+        x264_frame_t *fr = find_ref(h, m, &bx, &by);
+        ok = fr && fenc_pos_ok(h, m, bx, by);
+        if (ok) { frame_ctx(h, fr); qp = qp_of(m); ok = qp >= 0; }
+        if (ok) {
+            dref = dev_frame(h, fr, 1); denc = dev_frame(h, h->fenc, 0);
+            memset(&j, 0, sizeof(j));
+            j.bx = bx; j.by = by; j.i_pixel = m->i_pixel; j.qp = qp; j.flags = me_flags(h);
+            j.mvp[0] = m->mvp[0]; j.mvp[1] = m->mvp[1];
+            j.seed_mv[0] = m->mv[0]; j.seed_mv[1] = m->mv[1];
+            j.seed_cost = m->cost - ((m->i_pixel <= PIXEL_8x8 && h->sh.i_type == SLICE_TYPE_P) ? m->i_ref_cost : 0); /* me.c:639-640 */
+            fill_limits(h, &j);
+        }
+    }
+    x264_me_refine_qpel_c(h, m);
+    if (!ok) { n_skipped++; return; }
+    x264_cuda_me_final_t fin;
+    ck(x264_cuda_me_search_small(fctx, denc, dref, X264_CUDA_ME_METHOD_REFINE_QPEL, h->param.analyse.i_me_range, h->mb.i_subpel_refine, &j, 1, &fin), "refine_qpel");
+    if (fin.mv[0] != m->mv[0] || fin.mv[1] != m->mv[1] || fin.cost != m->cost || fin.cost_mv != m->cost_mv) me_differs("x264_me_refine_qpel", h, m, &fin, bx, by);
+    n_qpel++;
+}
+
+void x264_me_refine_bidir_satd(x264_t *h, x264_me_t *m0, x264_me_t *m1, int i_weight)
+{
+    x264_cuda_bidir_job_t j;
+    x264_cuda_frame_t *d0 = NULL, *d1 = NULL, *denc = NULL;
+    int bx = 0, by = 0, bx1 = 0, by1 = 0, qp = -1, ok = me_hooks_on() && !h->sh.b_mbaff && i_weight >= 0 && i_weight < 256;
+    if (ok) {
+        x264_frame_t *f0 = find_ref(h, m0, &bx, &by), *f1 = find_ref(h, m1, &bx1, &by1);
+        ok = f0 && f1 && bx == bx1 && by == by1 && fenc_pos_ok(h, m0, bx, by);
+        if (ok) { frame_ctx(h, f0); qp = qp_of(m0); ok = qp >= 0; }
+        if (ok) {
+            d0 = dev_frame(h, f0, 1); d1 = dev_frame(h, f1, 1); denc = dev_frame(h, h->fenc, 0);
+            memset(&j, 0, sizeof(j));
+            j.bx = bx; j.by = by; j.i_pixel = m0->i_pixel; j.qp = qp; j.weight = i_weight; j.flags = me_flags(h) & X264_CUDA_ME_MBCMP_SATD;
+            for (int k = 0; k < 2; k++) {
+                j.mv0[k] = m0->mv[k]; j.mv1[k] = m1->mv[k]; j.mvp0[k] = m0->mvp[k]; j.mvp1[k] = m1->mvp[k];
+                j.mv_min_spel[k] = h->mb.mv_min_spel[k]; j.mv_max_spel[k] = h->mb.mv_max_spel[k];
+            }
+        }
+    }
+    x264_me_refine_bidir_satd_c(h, m0, m1, i_weight);
+    if (!ok) { n_skipped++; return; }
+    x264_cuda_bidir_result_t r;
+    ck(x264_cuda_me_refine_bidir(fctx, denc, d0, d1, &j, 1, &r), "me_refine_bidir");
+    if (r.mv0[0] != m0->mv[0] || r.mv0[1] != m0->mv[1] || r.mv1[0] != m1->mv[0] || r.mv1[1] != m1->mv[1]) {
+        fprintf(stderr, "ref_cuda_shim: x264_me_refine_bidir_satd differs at frame %d block (%d,%d) pixel %d weight %d: reference (%d,%d)/(%d,%d), device (%d,%d)/(%d,%d)\n",
+                h->fenc->i_frame, bx, by, m0->i_pixel, i_weight, m0->mv[0], m0->mv[1], m1->mv[0], m1->mv[1], r.mv0[0], r.mv0[1], r.mv1[0], r.mv1[1]);
+        exit(5);
+    }
+    n_bidir++;
+}

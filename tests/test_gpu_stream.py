@@ -57,6 +57,11 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
         m = re.search(r"frame hooks: (\d+) lowres, (\d+) filter, (\d+) deblock frames recomputed on the device, (\d+) bytes compared equal", r.stderr)
         if m:
             frames = tuple(int(x) for x in m.groups())
+    m = re.search(r"me hooks: (\d+) searches, (\d+) qpel refinements, (\d+) bidir refinements repeated on the device and equal; (\d+) left to C", r.stderr)
+    me = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "launches", launches, "frame hooks", frames, "me hooks", me)
+    # every full-resolution motion search of the encode was repeated on the device with the encoder's own predictors and agreed (exit 5 otherwise)
+    assert me is not None and me[0] > 20 * (n - 1), me
     assert launches > 1000 * n, launches   # the table entries really ran on the device
     # frame-level hooks: every input frame's lowres planes, every kept reference's deblocking + half-pel/integral planes were recomputed
     # on the device from the encoder's own data, compared byte for byte inside the shim (it exits 4 on a mismatch) and used from then on
