@@ -3,7 +3,8 @@
  * S/common/{pixel,mc,dct,quant}.c a second time with -Dx264_<t>_init=x264_<t>_init_c (a rename of the one symbol each file exports for
  * its table), and this file supplies x264_<t>_init: C table first, then the x264_<t>_init_cuda overrides on top
  * (include/x264_cuda_tables.h).  The resulting CLI (oracle/_ref/x264_cuda) must write a byte-identical stream
- * (tests/test_gpu_stream.py): SURVEY 8c "stream level" parity. */
+ * (tests/test_gpu_stream.py): SURVEY 8c "stream level" parity.  Further down the same trick wraps frame-level functions, the motion
+ * searches and the macroblock residual coder so that the frame-batched C ABI is driven by the live encoder's data as well. */
 #include <stdio.h>
 #include <stdlib.h>
 #include "common/common.h"
@@ -389,4 +390,129 @@ void x264_me_refine_bidir_satd(x264_t *h, x264_me_t *m0, x264_me_t *m1, int i_we
         exit(5);
     }
     n_bidir++;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Residual hooks: x264_macroblock_probe_skip and the inter branch of x264_macroblock_encode (no trellis / noise reduction / lossless)
+ * repeated on the device for the live macroblock, with the encoder's own quantiser tables (x264_cuda_set_quant_tables from
+ * h->quant4_mf ...).  The prediction the C code works from (formed by x264_mb_mc, or by the probe's own mc) is placed at the
+ * macroblock's position of a device frame; coefficients, non-zero counts, cbp and the reconstructed pixels must agree (exit 6). */
+#include "encoder/macroblock.h"
+void x264_macroblock_encode_c(x264_t *h);
+int x264_macroblock_probe_skip_c(x264_t *h, int b_bidir);
+static x264_cuda_frame_t *fpred;
+static uint8_t *shadow[3];
+static long long n_resid, n_probe, n_resid_c;
+
+static void report_resid(void)
+{
+    fprintf(stderr, "ref_cuda_shim: residual hooks: %lld inter macroblock encodes, %lld skip probes repeated on the device and equal; %lld encodes left to C\n",
+            n_resid, n_probe, n_resid_c);
+}
+static int resid_hooks_on(void)
+{
+    const char *e = getenv("X264_CUDA_RESID_HOOKS");
+    return (!e || atoi(e)) && hooks_on();
+}
+static void resid_ctx(x264_t *h)
+{
+    if (fpred) return;
+    x264_frame_t *f = h->fdec;
+    frame_ctx(h, f);
+    fpred = x264_cuda_frame_new(fctx, f->i_width[0], f->i_lines[0], X264_CUDA_FRAME_CHROMA);
+    if (!fpred) ck(-1, "x264_cuda_frame_new");
+    for (int i = 0; i < 3; i++) shadow[i] = calloc((size_t)f->i_stride[i] * (f->i_lines[i] + 2 * PADV), 1);
+    ck(x264_cuda_set_quant_tables(fctx, (const uint16_t *const *)h->quant4_mf, (const uint16_t *const *)h->quant4_bias, (const int *const *)h->dequant4_mf,
+                                  (const uint16_t *const *)h->quant8_mf, (const uint16_t *const *)h->quant8_bias, (const int *const *)h->dequant8_mf),
+       "set_quant_tables");
+    atexit(report_resid);
+}
+/* the macroblock's prediction (p_fdec tiles) -> device frame at the macroblock's position */
+static void upload_pred(x264_t *h)
+{
+    x264_frame_t *f = h->fdec;
+    for (int i = 0; i < 3; i++) {
+        const int n = 16 >> !!i;
+        for (int y = 0; y < n; y++)
+            memcpy(shadow[i] + ((size_t)h->mb.i_mb_y * n + y) * f->i_stride[i] + h->mb.i_mb_x * n, h->mb.pic.p_fdec[i] + y * FDEC_STRIDE, n);
+    }
+    ck(x264_cuda_frame_upload(fctx, fpred, shadow[0], f->i_stride[0], f->i_width[0], f->i_lines[0]), "upload pred");
+    ck(x264_cuda_frame_upload_chroma(fctx, fpred, X264_CUDA_PLANE_CB, shadow[1], f->i_stride[1], f->i_width[1], f->i_lines[1]), "upload pred cb");
+    ck(x264_cuda_frame_upload_chroma(fctx, fpred, X264_CUDA_PLANE_CR, shadow[2], f->i_stride[2], f->i_width[2], f->i_lines[2]), "upload pred cr");
+}
+
+int x264_macroblock_probe_skip(x264_t *h, int b_bidir)
+{
+    uint8_t dev_skip = 0xff;
+    if (resid_hooks_on() && !h->sh.b_mbaff) {
+        resid_ctx(h);
+        x264_cuda_skip_job_t j;
+        memset(&j, 0, sizeof(j));
+        j.mb_x = h->mb.i_mb_x; j.mb_y = h->mb.i_mb_y; j.qp = h->mb.i_qp; j.chroma_qp = h->mb.i_chroma_qp;
+        x264_cuda_frame_t *denc = dev_frame(h, h->fenc, 0);
+        if (b_bidir) { /* the caller has put the direct prediction into p_fdec (analyse.c:2486-2489) */
+            upload_pred(h);
+            j.flags = X264_CUDA_SKIP_PRED_IN_FDEC;
+            ck(x264_cuda_probe_skip(fctx, denc, NULL, fpred, &j, 1, &dev_skip), "probe_skip (bidir)");
+        } else {
+            j.mvx = x264_clip3(h->mb.cache.pskip_mv[0], h->mb.mv_min[0], h->mb.mv_max[0]); /* macroblock.c:812-813 */
+            j.mvy = x264_clip3(h->mb.cache.pskip_mv[1], h->mb.mv_min[1], h->mb.mv_max[1]);
+            ck(x264_cuda_probe_skip(fctx, denc, dev_frame(h, h->fref0[0], 1), NULL, &j, 1, &dev_skip), "probe_skip");
+        }
+    }
+    const int r = x264_macroblock_probe_skip_c(h, b_bidir);
+    if (dev_skip != 0xff) {
+        if (dev_skip != r) {
+            fprintf(stderr, "ref_cuda_shim: x264_macroblock_probe_skip differs at frame %d mb (%d,%d) bidir %d: reference %d, device %d\n", h->fenc->i_frame,
+                    h->mb.i_mb_x, h->mb.i_mb_y, b_bidir, r, dev_skip);
+            exit(6);
+        }
+        n_probe++;
+    }
+    return r;
+}
+
+void x264_macroblock_encode(x264_t *h)
+{
+    const int t = h->mb.i_type;
+    const int inter = !IS_INTRA(t) && t != P_SKIP && t != B_SKIP;
+    if (!(resid_hooks_on() && inter && !h->sh.b_mbaff && !h->mb.b_lossless && !h->mb.b_trellis && !h->mb.b_noise_reduction)) {
+        n_resid_c++;
+        x264_macroblock_encode_c(h);
+        return;
+    }
+    resid_ctx(h);
+    if (!h->mb.b_skip_mc) x264_mb_mc(h); /* the prediction x264_macroblock_encode is about to form itself (macroblock.c:596-598) */
+    upload_pred(h);
+    x264_cuda_resid_job_t j;
+    memset(&j, 0, sizeof(j));
+    j.mb_x = h->mb.i_mb_x; j.mb_y = h->mb.i_mb_y; j.qp = h->mb.i_qp; j.chroma_qp = h->mb.i_chroma_qp;
+    j.flags = (h->mb.b_transform_8x8 ? X264_CUDA_RESID_8x8DCT : 0) |
+              ((h->sh.i_type == SLICE_TYPE_B || h->param.analyse.b_dct_decimate) ? X264_CUDA_RESID_DECIMATE : 0);
+    static x264_cuda_mb_coeffs_t co;
+    ck(x264_cuda_residual_inter(fctx, dev_frame(h, h->fenc, 0), fpred, &j, 1, &co), "residual_inter");
+    const int was8 = h->mb.b_transform_8x8;
+    memset(&h->dct, 0, sizeof(h->dct)); /* blocks the C code does not code keep stale coefficients otherwise; nothing reads them */
+    x264_macroblock_encode_c(h);
+    int bad = 0;
+    if (was8) bad |= memcmp(co.luma, h->dct.luma8x8, sizeof(h->dct.luma8x8)) ? 1 : 0;
+    else bad |= memcmp(co.luma, h->dct.luma4x4, 16 * 16 * sizeof(int16_t)) ? 1 : 0;
+    bad |= memcmp(co.chroma_ac, h->dct.luma4x4[16], 8 * 16 * sizeof(int16_t)) ? 2 : 0;
+    bad |= memcmp(co.chroma_dc, h->dct.chroma_dc, sizeof(h->dct.chroma_dc)) ? 4 : 0;
+    for (int i = 0; i < 27; i++) bad |= co.nnz[i] != h->mb.cache.non_zero_count[x264_scan8[i]] ? 8 : 0;
+    bad |= (co.cbp_luma != h->mb.i_cbp_luma || co.cbp_chroma != h->mb.i_cbp_chroma) ? 16 : 0;
+    static const int ids[3] = { X264_CUDA_PLANE_FULL, X264_CUDA_PLANE_CB, X264_CUDA_PLANE_CR };
+    x264_frame_t *f = h->fdec;
+    for (int i = 0; i < 3 && !bad; i++) {
+        const int s = f->i_stride[i], padv = PADV >> !!i, padh = PADH >> !!i, n = 16 >> !!i;
+        ck(x264_cuda_frame_download(fctx, fpred, ids[i], tmp_plane, s), "download recon");
+        for (int y = 0; y < n; y++)
+            if (memcmp(tmp_plane + (size_t)(padv + h->mb.i_mb_y * n + y) * s + padh + h->mb.i_mb_x * n, h->mb.pic.p_fdec[i] + y * FDEC_STRIDE, n)) bad |= 32 << i;
+    }
+    if (bad) {
+        fprintf(stderr, "ref_cuda_shim: x264_macroblock_encode (inter) differs at frame %d mb (%d,%d) type %d qp %d/%d 8x8dct %d: mask %d\n", h->fenc->i_frame,
+                h->mb.i_mb_x, h->mb.i_mb_y, t, h->mb.i_qp, h->mb.i_chroma_qp, was8, bad);
+        exit(6);
+    }
+    n_resid++;
 }

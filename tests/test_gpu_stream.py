@@ -25,16 +25,23 @@ CONFIGS = [
     ("cavlc_8x8dct_deblock", 96, 64, 3, "--me hex --subme 4 --no-cabac --8x8dct --deblock 2:-1 --chroma-qp-offset 3"),
     ("cqm_jvt", 160, 128, 2, "--me hex --subme 4 --cqm jvt"),
     ("crf_aq_lookahead", 96, 64, 5, "--crf 24 --me hex --subme 6 --bframes 2 --b-adapt 2"),               # lowres costs steer rate control
+    ("static_skips", 96, 64, 5, "--me hex --subme 4 --bframes 1 --static"),                               # P- and B-skip probes everywhere
 ]
 
 
-def _clip(pkg, w, h, n, path):
+def _clip(pkg, w, h, n, path, static=False):
     from x264_vs2008_b200 import synth
     clip = synth.Clip(w, h, seed=3)
+    rng = np.random.default_rng(2)
     with open(path, "wb") as f:
         for i in range(n):
-            for p in clip.yuv420(i):
-                f.write(np.ascontiguousarray(p).tobytes())
+            for p in clip.yuv420(0 if static else i):
+                p = np.ascontiguousarray(p).copy()
+                if static and i:   # the same picture with a few touched pixels: most macroblocks pass the skip probe, some just fail it
+                    for _ in range(p.size // 200):
+                        y, x = int(rng.integers(0, p.shape[0])), int(rng.integers(0, p.shape[1]))
+                        p[y, x] = np.clip(int(p[y, x]) + int(rng.integers(-12, 13)), 0, 255)
+                f.write(p.tobytes())
 
 
 @pytest.mark.parametrize("tag,w,h,n,opts", CONFIGS, ids=[c[0] for c in CONFIGS])
@@ -42,7 +49,9 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     if not (os.path.exists(REF) and os.path.exists(CUD)):
         pytest.skip("oracle/_ref CLI builds not present (they are produced where the reference sources exist)")
     src = str(tmp_path / "in.yuv")
-    _clip(pkg, w, h, n, src)
+    static = "--static" in opts
+    opts = opts.replace(" --static", "")
+    _clip(pkg, w, h, n, src, static)
     outs, launches, frames = [], 0, None
     for exe in (REF, CUD):
         out = str(tmp_path / (os.path.basename(exe) + ".264"))
@@ -59,9 +68,13 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
             frames = tuple(int(x) for x in m.groups())
     m = re.search(r"me hooks: (\d+) searches, (\d+) qpel refinements, (\d+) bidir refinements repeated on the device and equal; (\d+) left to C", r.stderr)
     me = tuple(int(x) for x in m.groups()) if m else None
-    print(tag, "launches", launches, "frame hooks", frames, "me hooks", me)
+    m = re.search(r"residual hooks: (\d+) inter macroblock encodes, (\d+) skip probes repeated on the device and equal; (\d+) encodes left to C", r.stderr)
+    resid = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "launches", launches, "frame hooks", frames, "me hooks", me, "residual hooks", resid)
+    # every inter macroblock encode (coefficients, nnz, cbp, reconstruction) and every skip probe was repeated on the device (exit 6 on a difference)
+    assert resid is not None and (resid[1] > 40 if static else resid[0] > 10 * (n - 1)), resid
     # every full-resolution motion search of the encode was repeated on the device with the encoder's own predictors and agreed (exit 5 otherwise)
-    assert me is not None and me[0] > 20 * (n - 1), me
+    assert me is not None and (static or me[0] > 20 * (n - 1)), me
     assert launches > 1000 * n, launches   # the table entries really ran on the device
     # frame-level hooks: every input frame's lowres planes, every kept reference's deblocking + half-pel/integral planes were recomputed
     # on the device from the encoder's own data, compared byte for byte inside the shim (it exits 4 on a mismatch) and used from then on
