@@ -66,6 +66,7 @@ void x264_frame_expand_border_filtered_c(x264_t *h, x264_frame_t *frame, int mb_
 void x264_frame_deblock_row_c(x264_t *h, int mb_y);
 
 static x264_cuda_t *fctx;
+static x264_t *g_h; /* for the hooks whose reference signature does not carry the encoder handle */
 static x264_cuda_frame_t *ffr;
 static uint8_t *tmp_plane, *pre[3];
 static long long n_lowres, n_filter, n_deblock, n_bytes_checked;
@@ -86,6 +87,7 @@ static void ck(int rc, const char *what)
 }
 static void frame_ctx(x264_t *h, x264_frame_t *fr)
 {
+    g_h = h;
     if (fctx) return;
     need(x264_cuda_open(&fctx, 0), "x264_cuda_open");
     int flags = X264_CUDA_FRAME_CHROMA;
@@ -515,4 +517,106 @@ void x264_macroblock_encode(x264_t *h)
         exit(6);
     }
     n_resid++;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Frame-metric hooks on live data: x264_adaptive_quant_frame (device macroblock energies + the host float tail
+ * must give the same f_qp_offset / i_inv_qscale_factor bit for bit — these steer every macroblock's qp), x264_pixel_ssd_wxh and
+ * x264_pixel_ssim_wxh (the PSNR / SSIM row slabs of x264_fdec_filter_row, encoder.c:1034-1056).  Exit 7 on a difference. */
+void x264_adaptive_quant_frame_c(x264_t *h, x264_frame_t *frame);
+int64_t x264_pixel_ssd_wxh_c(x264_pixel_function_t *pf, uint8_t *pix1, int i_pix1, uint8_t *pix2, int i_pix2, int i_width, int i_height);
+float x264_pixel_ssim_wxh_c(x264_pixel_function_t *pf, uint8_t *pix1, int i_pix1, uint8_t *pix2, int i_pix2, int i_width, int i_height, void *buf);
+static x264_cuda_frame_t *fm[2];
+static long long n_aq, n_ssd, n_ssim;
+
+static void report_metrics(void)
+{
+    fprintf(stderr, "ref_cuda_shim: metric hooks: %lld AQ frames, %lld SSD slabs, %lld SSIM slabs repeated on the device and equal\n", n_aq, n_ssd, n_ssim);
+}
+static void metric_ctx(x264_t *h, x264_frame_t *f)
+{
+    g_h = h;
+    if (fm[0]) return;
+    frame_ctx(h, f);
+    for (int k = 0; k < 2; k++) {
+        fm[k] = x264_cuda_frame_new(fctx, f->i_width[0], f->i_lines[0], X264_CUDA_FRAME_CHROMA);
+        if (!fm[k]) ck(-1, "x264_cuda_frame_new");
+    }
+    atexit(report_metrics);
+}
+static void upload_all(x264_cuda_frame_t *d, x264_frame_t *f)
+{
+    ck(x264_cuda_frame_upload(fctx, d, f->plane[0], f->i_stride[0], f->i_width[0], f->i_lines[0]), "upload");
+    ck(x264_cuda_frame_upload_chroma(fctx, d, X264_CUDA_PLANE_CB, f->plane[1], f->i_stride[1], f->i_width[1], f->i_lines[1]), "upload cb");
+    ck(x264_cuda_frame_upload_chroma(fctx, d, X264_CUDA_PLANE_CR, f->plane[2], f->i_stride[2], f->i_width[2], f->i_lines[2]), "upload cr");
+}
+
+void x264_adaptive_quant_frame(x264_t *h, x264_frame_t *frame)
+{
+    x264_adaptive_quant_frame_c(h, frame);
+    if (!hooks_on() || h->mb.b_interlaced) return;
+    metric_ctx(h, frame);
+    upload_all(fm[0], frame);
+    const int n = h->mb.i_mb_count;
+    uint32_t *energy = malloc(n * sizeof(uint32_t));
+    float *qp = malloc(n * sizeof(float));
+    uint16_t *inv = malloc(n * sizeof(uint16_t));
+    ck(x264_cuda_frame_mb_energy(fctx, fm[0], energy), "frame_mb_energy");
+    x264_cuda_host_aq(energy, n, h->param.rc.f_aq_strength, qp, inv);
+    if (memcmp(qp, frame->f_qp_offset, n * sizeof(float)) || (h->frames.b_have_lowres && memcmp(inv, frame->i_inv_qscale_factor, n * sizeof(uint16_t)))) {
+        fprintf(stderr, "ref_cuda_shim: x264_adaptive_quant_frame differs\n");
+        exit(7);
+    }
+    memcpy(frame->f_qp_offset, qp, n * sizeof(float));
+    free(energy); free(qp); free(inv);
+    n_aq++;
+}
+
+/* pix1 inside a plane of the frame being reconstructed, pix2 at the same offset of the source frame (encoder.c:1038-1055)? */
+static int locate(uint8_t *pix1, uint8_t *pix2, int s1, int s2, int *plane, int *x0, int *y0)
+{
+    x264_t *h = g_h;
+    if (!h || !h->fdec || !h->fenc) return 0;
+    for (int i = 0; i < 3; i++) {
+        const ptrdiff_t off = pix1 - h->fdec->plane[i], lim = (ptrdiff_t)h->fdec->i_stride[i] * h->fdec->i_lines[i];
+        if (off >= 0 && off < lim && s1 == h->fdec->i_stride[i] && s2 == h->fenc->i_stride[i] && pix2 - h->fenc->plane[i] == off) {
+            *plane = i ? (i == 1 ? X264_CUDA_PLANE_CB : X264_CUDA_PLANE_CR) : X264_CUDA_PLANE_FULL;
+            *x0 = (int)(off % s1); *y0 = (int)(off / s1);
+            return 1;
+        }
+    }
+    return 0;
+}
+
+int64_t x264_pixel_ssd_wxh(x264_pixel_function_t *pf, uint8_t *pix1, int i_pix1, uint8_t *pix2, int i_pix2, int i_width, int i_height)
+{
+    const int64_t r = x264_pixel_ssd_wxh_c(pf, pix1, i_pix1, pix2, i_pix2, i_width, i_height);
+    int plane, x0, y0;
+    if (hooks_on() && i_width > 0 && i_height > 0 && locate(pix1, pix2, i_pix1, i_pix2, &plane, &x0, &y0)) {
+        metric_ctx(g_h, g_h->fdec);
+        upload_all(fm[0], g_h->fdec); upload_all(fm[1], g_h->fenc);
+        int64_t d = -1;
+        ck(x264_cuda_frame_ssd(fctx, fm[0], fm[1], plane, x0, y0, i_width, i_height, &d), "frame_ssd");
+        if (d != r) { fprintf(stderr, "ref_cuda_shim: x264_pixel_ssd_wxh differs: reference %lld, device %lld\n", (long long)r, (long long)d); exit(7); }
+        n_ssd++;
+    }
+    return r;
+}
+
+float x264_pixel_ssim_wxh(x264_pixel_function_t *pf, uint8_t *pix1, int i_pix1, uint8_t *pix2, int i_pix2, int i_width, int i_height, void *buf)
+{
+    const float r = x264_pixel_ssim_wxh_c(pf, pix1, i_pix1, pix2, i_pix2, i_width, i_height, buf);
+    int plane, x0, y0;
+    if (hooks_on() && i_width >= 8 && i_height >= 8 && locate(pix1, pix2, i_pix1, i_pix2, &plane, &x0, &y0)) {
+        metric_ctx(g_h, g_h->fdec);
+        upload_all(fm[0], g_h->fdec); upload_all(fm[1], g_h->fenc);
+        const int w4 = i_width >> 2, h4 = i_height >> 2;
+        int (*sums)[4] = malloc((size_t)w4 * h4 * sizeof(*sums));
+        ck(x264_cuda_frame_ssim_sums(fctx, fm[0], fm[1], plane, x0, y0, i_width, i_height, sums), "frame_ssim_sums");
+        const float d = x264_cuda_host_ssim_end((const int(*)[4])sums, w4, h4);
+        free(sums);
+        if (memcmp(&d, &r, sizeof(float))) { fprintf(stderr, "ref_cuda_shim: x264_pixel_ssim_wxh differs: reference %.9g, device %.9g\n", r, d); exit(7); }
+        n_ssim++;
+    }
+    return r;
 }

@@ -70,7 +70,11 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     me = tuple(int(x) for x in m.groups()) if m else None
     m = re.search(r"residual hooks: (\d+) inter macroblock encodes, (\d+) skip probes repeated on the device and equal; (\d+) encodes left to C", r.stderr)
     resid = tuple(int(x) for x in m.groups()) if m else None
-    print(tag, "launches", launches, "frame hooks", frames, "me hooks", me, "residual hooks", resid)
+    m = re.search(r"metric hooks: (\d+) AQ frames, (\d+) SSD slabs, (\d+) SSIM slabs repeated on the device and equal", r.stderr)
+    metric = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "launches", launches, "frame hooks", frames, "me hooks", me, "residual hooks", resid, "metric hooks", metric)
+    # PSNR / SSIM slabs of every kept frame, and with rate control the AQ offsets of every input frame (exit 7 on a difference)
+    assert metric is not None and metric[1] >= 3 and metric[2] >= 1 and (metric[0] == n or "--crf" not in opts), metric
     # every inter macroblock encode (coefficients, nnz, cbp, reconstruction) and every skip probe was repeated on the device (exit 6 on a difference)
     assert resid is not None and (resid[1] > 40 if static else resid[0] > 10 * (n - 1)), resid
     # every full-resolution motion search of the encode was repeated on the device with the encoder's own predictors and agreed (exit 5 otherwise)
