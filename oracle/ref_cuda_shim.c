@@ -302,14 +302,18 @@ static void me_differs(const char *what, x264_t *h, const x264_me_t *m, const x2
     exit(5);
 }
 
+static void record_search(x264_t *h, x264_frame_t *ref, const x264_cuda_me_job_t *j, const x264_me_t *m);
+static void flush_batched(x264_t *h);
+
 void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh)
 {
     x264_cuda_me_job_t j;
     x264_cuda_frame_t *dref = NULL, *denc = NULL;
     int bx = 0, by = 0, qp = -1, ok = me_hooks_on() && !h->sh.b_mbaff && !p_halfpel_thresh && i_mvc <= X264_CUDA_ME_MAX_MVC;
     const int method = h->mb.i_me_method, subme = h->mb.i_subpel_refine;
+    x264_frame_t *fr = NULL;
     if (ok) {
-        x264_frame_t *fr = find_ref(h, m, &bx, &by);
+        fr = find_ref(h, m, &bx, &by);
         ok = fr && fenc_pos_ok(h, m, bx, by) && !(method == X264_ME_ESA && subme >= 3);
         if (ok) { frame_ctx(h, fr); qp = qp_of(m); ok = qp >= 0; }
         if (ok) {
@@ -334,6 +338,7 @@ void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, i
         ck(x264_cuda_me_search_small(fctx, denc, dref, method == X264_ME_TESA ? X264_CUDA_ME_METHOD_TESA : method, range, subme, &j, 1, &fin), "me_search_small");
     if (fin.mv[0] != m->mv[0] || fin.mv[1] != m->mv[1] || fin.cost != m->cost || fin.cost_mv != m->cost_mv) me_differs("x264_me_search_ref", h, m, &fin, bx, by);
     n_search++;
+    record_search(h, fr, &j, m);
 }
 
 void x264_me_refine_qpel(x264_t *h, x264_me_t *m)
@@ -481,6 +486,7 @@ void x264_macroblock_encode(x264_t *h)
     if (!(resid_hooks_on() && inter && !h->sh.b_mbaff && !h->mb.b_lossless && !h->mb.b_trellis && !h->mb.b_noise_reduction)) {
         n_resid_c++;
         x264_macroblock_encode_c(h);
+        if (h->mb.i_mb_xy == h->mb.i_mb_count - 1) flush_batched(h);
         return;
     }
     resid_ctx(h);
@@ -517,6 +523,7 @@ void x264_macroblock_encode(x264_t *h)
         exit(6);
     }
     n_resid++;
+    if (h->mb.i_mb_xy == h->mb.i_mb_count - 1) flush_batched(h);
 }
 
 /* ------------------------------------------------------------------------------------------------------------------------------
@@ -619,4 +626,96 @@ float x264_pixel_ssim_wxh(x264_pixel_function_t *pf, uint8_t *pix1, int i_pix1, 
         n_ssim++;
     }
     return r;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * The macroblock-batched ESA kernel (x264_cuda_me_search_mb, the headline kernel) on live data: for --me esa with subme < 3 and no RD,
+ * every 16x16 / 16x8 / 8x16 / 8x8 search of a frame is RECORDED by the x264_me_search_ref hook (predictors, limits, the C result);
+ * when the frame's last macroblock has been encoded, one x264_cuda_me_search_mb launch per reference frame searches all recorded
+ * partitions of all macroblocks at once, one x264_cuda_me_search_small (SEEDED) launch adds the sub-pel tail, and every result must
+ * equal what the C code returned at the time — the data flow of INTEGRATION.md section 3 / bench.py, inside the real encoder.
+ * Partitions with more than X264_CUDA_ME_MB_MVC extra predictors are not representable in the batched job and are left out. */
+typedef struct { x264_frame_t *ref; int mb, part; x264_cuda_me_job_t job; int16_t mv[2]; int cost, cost_mv; } rec_t;
+static rec_t *recs;
+static int n_recs, cap_recs, rec_frame = -1;
+static long long n_mb_batched, n_mb_launches, n_mb_unrep;
+
+static void report_batched(void)
+{
+    fprintf(stderr, "ref_cuda_shim: batched ESA: %lld partition searches in %lld x264_cuda_me_search_mb launches equal to the C results; %lld not representable\n",
+            n_mb_batched, n_mb_launches, n_mb_unrep);
+}
+static void record_search(x264_t *h, x264_frame_t *ref, const x264_cuda_me_job_t *j, const x264_me_t *m)
+{
+    static int once;
+    if (!once++) atexit(report_batched);
+    if (h->mb.i_me_method != X264_ME_ESA || h->mb.i_subpel_refine >= 3 || m->i_pixel > PIXEL_8x8) return;
+    if (j->i_mvc > X264_CUDA_ME_MB_MVC) { n_mb_unrep++; return; }
+    if (rec_frame != h->fenc->i_frame) { n_recs = 0; rec_frame = h->fenc->i_frame; }
+    const int ox = j->bx & 15, oy = j->by & 15;
+    const int part = m->i_pixel == PIXEL_16x16 ? 0 : m->i_pixel == PIXEL_16x8 ? 1 + (oy >> 3) : m->i_pixel == PIXEL_8x16 ? 3 + (ox >> 3) : 5 + (oy >> 3) * 2 + (ox >> 3);
+    const int mb = h->mb.i_mb_xy;
+    for (int i = 0; i < n_recs; i++)
+        if (recs[i].ref == ref && recs[i].mb == mb && recs[i].part == part) { n_mb_unrep++; return; } /* searched twice: keep the first */
+    if (n_recs == cap_recs) { cap_recs = cap_recs ? 2 * cap_recs : 1024; recs = realloc(recs, cap_recs * sizeof(rec_t)); }
+    rec_t *r = &recs[n_recs++];
+    r->ref = ref; r->mb = mb; r->part = part; r->job = *j; r->mv[0] = m->mv[0]; r->mv[1] = m->mv[1]; r->cost = m->cost; r->cost_mv = m->cost_mv;
+}
+static void flush_batched(x264_t *h)
+{
+    if (!n_recs || rec_frame != h->fenc->i_frame) return;
+    const int n_mb = h->mb.i_mb_count, range = h->param.analyse.i_me_range, subme = h->mb.i_subpel_refine;
+    x264_cuda_me_mb_job_t *jobs = calloc(n_mb, sizeof(*jobs));
+    x264_cuda_me_mb_result_t *res = malloc(n_mb * sizeof(*res));
+    x264_cuda_me_job_t *tail = malloc(n_recs * sizeof(*tail));
+    x264_cuda_me_final_t *fin = malloc(n_recs * sizeof(*fin));
+    int *idx = malloc(n_recs * sizeof(int));
+    x264_cuda_frame_t *denc = dev_frame(h, h->fenc, 0);
+    for (int done = 0; done < n_recs;) {
+        x264_frame_t *ref = NULL;
+        int n = 0, n_jobs = 0;
+        for (int i = 0; i < n_recs; i++) /* next reference frame with unprocessed records */
+            if (recs[i].mb >= 0 && (!ref || recs[i].ref == ref)) { ref = recs[i].ref; idx[n++] = i; }
+        int *slot = malloc(n_mb * sizeof(int));
+        for (int i = 0; i < n_mb; i++) slot[i] = -1;
+        for (int k = 0; k < n; k++) {
+            const rec_t *r = &recs[idx[k]];
+            if (slot[r->mb] < 0) {
+                slot[r->mb] = n_jobs;
+                x264_cuda_me_mb_job_t *J = &jobs[n_jobs++];
+                memset(J, 0, sizeof(*J));
+                J->mb_x = r->job.bx >> 4; J->mb_y = r->job.by >> 4; J->qp = r->job.qp;
+                for (int c = 0; c < 2; c++) { J->mv_min_fpel[c] = r->job.mv_min_fpel[c]; J->mv_max_fpel[c] = r->job.mv_max_fpel[c]; }
+            }
+            x264_cuda_me_mb_job_t *J = &jobs[slot[r->mb]];
+            J->part_mask |= 1 << r->part;
+            J->i_mvc[r->part] = r->job.i_mvc;
+            J->mvp[r->part][0] = r->job.mvp[0]; J->mvp[r->part][1] = r->job.mvp[1];
+            for (int c = 0; c < r->job.i_mvc; c++) { J->mvc[r->part][c][0] = r->job.mvc[c][0]; J->mvc[r->part][c][1] = r->job.mvc[c][1]; }
+        }
+        x264_cuda_frame_t *dref = dev_frame(h, ref, 1);
+        ck(x264_cuda_me_search_mb(fctx, denc, dref, range, jobs, n_jobs, res), "me_search_mb");
+        n_mb_launches++;
+        for (int k = 0; k < n; k++) { /* sub-pel tail of every search, seeded with the batched kernel's full-pel winner (me.c:603-631) */
+            const rec_t *r = &recs[idx[k]];
+            const x264_cuda_me_result_t *w = &res[slot[r->mb]].part[r->part];
+            tail[k] = r->job;
+            tail[k].seed_mv[0] = w->bmx; tail[k].seed_mv[1] = w->bmy; tail[k].seed_cost = w->bcost;
+        }
+        ck(x264_cuda_me_search_small(fctx, denc, dref, X264_CUDA_ME_METHOD_SEEDED, range, subme, tail, n, fin), "me_search_small (seeded batch)");
+        for (int k = 0; k < n; k++) {
+            rec_t *r = &recs[idx[k]];
+            if (fin[k].mv[0] != r->mv[0] || fin[k].mv[1] != r->mv[1] || fin[k].cost != r->cost || fin[k].cost_mv != r->cost_mv) {
+                fprintf(stderr, "ref_cuda_shim: batched ESA differs at frame %d mb %d part %d: reference mv (%d,%d) cost %d, device mv (%d,%d) cost %d\n", rec_frame,
+                        r->mb, r->part, r->mv[0], r->mv[1], r->cost, fin[k].mv[0], fin[k].mv[1], fin[k].cost);
+                exit(5);
+            }
+            r->mb = -1;
+            n_mb_batched++;
+        }
+        done += n;
+        free(slot);
+    }
+    n_recs = 0;
+    free(jobs); free(res); free(tail); free(fin); free(idx);
 }

@@ -19,6 +19,7 @@ CONFIGS = [
     ("config1_dia", 96, 64, 3, "--me dia --subme 1"),
     ("hex_8x8dct_b", 96, 64, 4, "--me hex --subme 5 --8x8dct --bframes 1"),
     ("esa", 96, 64, 2, "--me esa --merange 8 --subme 2"),                                                 # config 2's search
+    ("esa_refs_b", 96, 64, 5, "--me esa --merange 16 --subme 2 --ref 2 --bframes 1"),                     # config 2 with two refs and B-frames
     ("esa_p4x4", 64, 48, 2, "--me esa --merange 8 --subme 2 --partitions all"),                           # 4x4 integral plane
     ("umh_rd_weightb", 64, 48, 5, "--me umh --subme 7 --8x8dct --bframes 2 --b-adapt 2 --weightb --mixed-refs --ref 2"),  # config 3
     ("tesa_b3", 64, 48, 5, "--me tesa --merange 8 --subme 6 --bframes 3 --b-adapt 2"),                    # config 4's options
@@ -73,6 +74,11 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     m = re.search(r"metric hooks: (\d+) AQ frames, (\d+) SSD slabs, (\d+) SSIM slabs repeated on the device and equal", r.stderr)
     metric = tuple(int(x) for x in m.groups()) if m else None
     print(tag, "launches", launches, "frame hooks", frames, "me hooks", me, "residual hooks", resid, "metric hooks", metric)
+    m = re.search(r"batched ESA: (\d+) partition searches in (\d+) x264_cuda_me_search_mb launches equal to the C results; (\d+) not representable", r.stderr)
+    batched = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "batched ESA", batched)
+    if "--me esa" in opts:   # the macroblock-batched kernel searched whole frames of recorded partitions and agreed with every C result
+        assert batched is not None and batched[0] > 40 * (n - 1) and batched[1] >= n - 1, batched
     # PSNR / SSIM slabs of every kept frame, and with rate control the AQ offsets of every input frame (exit 7 on a difference)
     assert metric is not None and metric[1] >= 3 and metric[2] >= 1 and (metric[0] == n or "--crf" not in opts), metric
     # every inter macroblock encode (coefficients, nnz, cbp, reconstruction) and every skip probe was repeated on the device (exit 6 on a difference)
