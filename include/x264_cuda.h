@@ -494,12 +494,18 @@ X264_CUDA_API int x264_cuda_me_refine_bidir_dev(x264_cuda_t *ctx, const x264_cud
  * cost about one.  Results are identical to nine x264_cuda_me_search jobs. */
 #define X264_CUDA_ME_MB_PARTS 9 /* 0: 16x16 | 1,2: 16x8 top,bottom | 3,4: 8x16 left,right | 5..8: 8x8 TL,TR,BL,BR */
 #define X264_CUDA_ME_MB_MVC 4
+/* The 16x16 search gets up to nine extra predictors from x264_mb_predict_mv_ref16x16 (S/common/macroblock.c:376-449); the 16x8 / 8x16
+ * searches get at most three and the 8x8 searches one to four, growing in block order (S/encoder/analyse.c:1229-1256, :1278, :1328).
+ * Partition 0 may therefore carry up to 4 + 7: predictor 4 + k is stored in the fourth slot of partition 1 + k (k = 0..6; use the
+ * accessor below), and a job that does so must keep i_mvc[1 + k] <= 3 for every slot it borrows.  The last 8x8 block keeps its four. */
+#define X264_CUDA_ME_MB_MVC16_EXTRA 7
+#define X264_CUDA_ME_MB_MVC16(job, k) ((k) < X264_CUDA_ME_MB_MVC ? (job)->mvc[0][k] : (job)->mvc[(k) - X264_CUDA_ME_MB_MVC + 1][X264_CUDA_ME_MB_MVC - 1])
 typedef struct x264_cuda_me_mb_job_t {
     int16_t mb_x, mb_y;              /* macroblock coordinates */
     uint16_t part_mask;              /* bit p: search partition p */
     uint8_t qp, flags;               /* flags: X264_CUDA_ME_SEEDED */
     int16_t mv_min_fpel[2], mv_max_fpel[2];
-    uint8_t i_mvc[X264_CUDA_ME_MB_PARTS];
+    uint8_t i_mvc[X264_CUDA_ME_MB_PARTS]; /* <= 4; i_mvc[0] <= 11 (see X264_CUDA_ME_MB_MVC16) */
     uint8_t reserved[3];
     int16_t mvp[X264_CUDA_ME_MB_PARTS][2];
     int16_t mvc[X264_CUDA_ME_MB_PARTS][X264_CUDA_ME_MB_MVC][2];

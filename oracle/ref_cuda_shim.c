@@ -634,7 +634,7 @@ float x264_pixel_ssim_wxh(x264_pixel_function_t *pf, uint8_t *pix1, int i_pix1, 
  * when the frame's last macroblock has been encoded, one x264_cuda_me_search_mb launch per reference frame searches all recorded
  * partitions of all macroblocks at once, one x264_cuda_me_search_small (SEEDED) launch adds the sub-pel tail, and every result must
  * equal what the C code returned at the time — the data flow of INTEGRATION.md section 3 / bench.py, inside the real encoder.
- * Partitions with more than X264_CUDA_ME_MB_MVC extra predictors are not representable in the batched job and are left out. */
+ * (A 16x16 search may carry up to twelve extra predictors, a sub-partition three: what the batched job can hold.) */
 typedef struct { x264_frame_t *ref; int mb, part; x264_cuda_me_job_t job; int16_t mv[2]; int cost, cost_mv; } rec_t;
 static rec_t *recs;
 static int n_recs, cap_recs, rec_frame = -1;
@@ -650,10 +650,14 @@ static void record_search(x264_t *h, x264_frame_t *ref, const x264_cuda_me_job_t
     static int once;
     if (!once++) atexit(report_batched);
     if (h->mb.i_me_method != X264_ME_ESA || h->mb.i_subpel_refine >= 3 || m->i_pixel > PIXEL_8x8) return;
-    if (j->i_mvc > X264_CUDA_ME_MB_MVC) { n_mb_unrep++; return; }
     if (rec_frame != h->fenc->i_frame) { n_recs = 0; rec_frame = h->fenc->i_frame; }
     const int ox = j->bx & 15, oy = j->by & 15;
     const int part = m->i_pixel == PIXEL_16x16 ? 0 : m->i_pixel == PIXEL_16x8 ? 1 + (oy >> 3) : m->i_pixel == PIXEL_8x16 ? 3 + (ox >> 3) : 5 + (oy >> 3) * 2 + (ox >> 3);
+    /* the 16x16 search may carry up to 4 + 7 predictors (X264_CUDA_ME_MB_MVC16); a sub-partition whose fourth slot it borrows only three */
+    if (j->i_mvc > (part ? X264_CUDA_ME_MB_MVC : X264_CUDA_ME_MB_MVC + X264_CUDA_ME_MB_MVC16_EXTRA)) { n_mb_unrep++; return; }
+    if (part && j->i_mvc == X264_CUDA_ME_MB_MVC)
+        for (int i = 0; i < n_recs; i++)
+            if (recs[i].ref == ref && recs[i].mb == h->mb.i_mb_xy && recs[i].part == 0 && recs[i].job.i_mvc - X264_CUDA_ME_MB_MVC > part - 1) { n_mb_unrep++; return; }
     const int mb = h->mb.i_mb_xy;
     for (int i = 0; i < n_recs; i++)
         if (recs[i].ref == ref && recs[i].mb == mb && recs[i].part == part) { n_mb_unrep++; return; } /* searched twice: keep the first */
@@ -691,7 +695,10 @@ static void flush_batched(x264_t *h)
             J->part_mask |= 1 << r->part;
             J->i_mvc[r->part] = r->job.i_mvc;
             J->mvp[r->part][0] = r->job.mvp[0]; J->mvp[r->part][1] = r->job.mvp[1];
-            for (int c = 0; c < r->job.i_mvc; c++) { J->mvc[r->part][c][0] = r->job.mvc[c][0]; J->mvc[r->part][c][1] = r->job.mvc[c][1]; }
+            for (int c = 0; c < r->job.i_mvc; c++) {
+                int16_t *dst = r->part ? J->mvc[r->part][c] : X264_CUDA_ME_MB_MVC16(J, c);
+                dst[0] = r->job.mvc[c][0]; dst[1] = r->job.mvc[c][1];
+            }
         }
         x264_cuda_frame_t *dref = dev_frame(h, ref, 1);
         ck(x264_cuda_me_search_mb(fctx, denc, dref, range, jobs, n_jobs, res), "me_search_mb");

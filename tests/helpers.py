@@ -81,13 +81,19 @@ def make_mb_jobs(pkg, g, seed, n, qp, mvp_spread=40, mvc_spread=60, centre=(0, 0
             # partitions of one MB have correlated predictors (as in the encoder) with occasional outliers
             jit = 6 if rng.integers(0, 6) else 70
             j["mvp"][p] = [base[0] + int(rng.integers(-jit, jit + 1)), base[1] + int(rng.integers(-jit, jit + 1))]
-            nm = int(rng.integers(0, pkg.ME_MB_MVC + 1))
+            # every third job: the 16x16 search carries 5..11 predictors like x264_mb_predict_mv_ref16x16's list; the ones beyond four live
+            # in the fourth slot of partitions 1..7 (X264_CUDA_ME_MB_MVC16), which then use at most three themselves (the last 8x8 may use four)
+            wide = i % 3 == 1
+            nm = int(rng.integers(5, 12)) if (wide and p == 0) else int(rng.integers(0, pkg.ME_MB_MVC + (0 if (wide and p < 8) else 1)))
             j["i_mvc"][p] = nm
             for k in range(nm):
                 v = [base[0] + int(rng.integers(-mvc_spread, mvc_spread + 1)), base[1] + int(rng.integers(-mvc_spread, mvc_spread + 1))]
                 if rng.integers(0, 8) == 0:
                     v = [0, 0]
-                j["mvc"][p][k] = v
+                if k < pkg.ME_MB_MVC:
+                    j["mvc"][p][k] = v
+                else:
+                    j["mvc"][k - pkg.ME_MB_MVC + 1][pkg.ME_MB_MVC - 1] = v
     return jobs
 
 
@@ -105,6 +111,9 @@ def mb_jobs_to_block_jobs(pkg, mbjobs):
             j["mvp"] = mj["mvp"][p]
             j["mv_min_fpel"], j["mv_max_fpel"] = mj["mv_min_fpel"], mj["mv_max_fpel"]
             j["mvc"][:pkg.ME_MB_MVC] = mj["mvc"][p]
+            if p == 0:
+                for k in range(pkg.ME_MB_MVC, int(mj["i_mvc"][0])):
+                    j["mvc"][k] = mj["mvc"][k - pkg.ME_MB_MVC + 1][pkg.ME_MB_MVC - 1]
             out.append(j)
             idx.append((i, p))
     return np.array(out, pkg.ME_JOB), idx

@@ -35,6 +35,7 @@ struct __align__(16) WarpSmem {
     x264_cuda_me_mb_job_t job;               // 280 B
     int quad[NP * NCAND][4];                 // predictor stage: 8x8 quadrant SADs of every (partition, candidate)
     int pc_x[NP * NCAND], pc_y[NP * NCAND];
+    int ext[8][3];                           // partition 0's predictors 4..10: cost (or -1), x, y
     int seed[NP][3];                         // bmx, bmy, bcost per partition
     int win[NP][4];                          // min_x, min_y, width, rows per partition
 };
@@ -209,6 +210,9 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
             bad |= max(abs(4 * x_min - job.mvp[lane][0]), abs(4 * x_max - job.mvp[lane][0])) > lim;
             bad |= max(abs(4 * y_min - job.mvp[lane][1]), abs(4 * y_max - job.mvp[lane][1])) > lim;
         }
+        // partition 0 may carry up to 4 + 7 predictors; extra k occupies slot 3 of partition 1 + k, which then must not use it itself
+        const int n_ext = min(max((int)job.i_mvc[0] - X264_CUDA_ME_MB_MVC, 0), X264_CUDA_ME_MB_MVC16_EXTRA);
+        if (lane >= 1 && lane < NP && lane - 1 < n_ext) bad |= job.i_mvc[lane] > X264_CUDA_ME_MB_MVC - 1;
         if (__any_sync(0xffffffffu, bad) || !mask) {
             if (lane < NP) { x264_cuda_me_result_t r = { 0, 0, -1, 0, 0, -1 }; out[lane] = r; }
             continue;
@@ -258,11 +262,27 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
                 pair_pq(t & 15, p, q);
                 S.quad[p * NCAND + c][q] = v[u];
             }
+            if (n_ext > 0 && (mask & 1)) { // warp-uniform: lane = extra predictor (lane >> 2) x quadrant (lane & 3), one 8x8 SAD each
+                const int k = lane >> 2, q = lane & 3;
+                const int mx = (job.mvc[1 + k][X264_CUDA_ME_MB_MVC - 1][0] + 2) >> 2, my = (job.mvc[1 + k][X264_CUDA_ME_MB_MVC - 1][1] + 2) >> 2;
+                const bool valid = k < n_ext && (mx | my) != 0;
+                const int cx = clip3i(mx, x_min, x_max), cy = clip3i(my, y_min, y_max);
+                int v = valid ? sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + cy) * stride + (q & 1) * 8 + cx, stride) : 0;
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (q == 0) {
+                    S.ext[k][0] = valid ? v + tab[(cx << 2) - job.mvp[0][0]] + tab[(cy << 2) - job.mvp[0][1]] : -1;
+                    S.ext[k][1] = cx; S.ext[k][2] = cy;
+                }
+            }
             __syncwarp();
             if (lane < NP) {
                 int bc = COST_MAX + 1, bx = 0, by = 0; // sequential strict '<' in candidate order
                 for (int c = 0; c < NCAND; c++) {
                     const int idx = lane * NCAND + c;
+                    if (c == NCAND - 1 && lane == 0 && n_ext > 0) // partition 0's extra predictors come before the (0,0) test (me.c:219-229)
+                        for (int k = 0; k < n_ext; k++)
+                            if (S.ext[k][0] >= 0 && S.ext[k][0] < bc) { bc = S.ext[k][0]; bx = S.ext[k][1]; by = S.ext[k][2]; }
                     if (S.pc_y[idx] == (1 << 20)) continue;
                     int v = S.quad[idx][0] + S.quad[idx][1] + S.quad[idx][2] + S.quad[idx][3];
                     if (c != 0) v += tab[(S.pc_x[idx] << 2) - job.mvp[lane][0]] + tab[(S.pc_y[idx] << 2) - job.mvp[lane][1]];
