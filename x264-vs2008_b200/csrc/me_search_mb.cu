@@ -81,6 +81,43 @@ __device__ __forceinline__ int sad_quad(const uint32_t (*F)[4], int q, const uin
     return (int)(acc0 + acc1);
 }
 
+// Partition 0 with more than four extra predictors (X264_CUDA_ME_MB_MVC16): predictors 4.. live in slot 3 of partitions 1..7.  Their
+// 16x16 SADs are computed here (lane = predictor x quadrant) and lane 0 redoes the reference's sequential strict-'<' selection in its
+// order — mvp, mvc[0..], then (0,0) (me.c:207-229) — from the quadrant sums the main stage left in S.quad.  Kept out of line so that the
+// common path's code is unaffected.
+__device__ __noinline__ void seed_p0_wide(WarpSmem &S, const int16_t *tab, const uint8_t *ref0, int stride, int n_ext, int x_min, int x_max,
+                                          int y_min, int y_max, int lane)
+{
+    const x264_cuda_me_mb_job_t &job = S.job;
+    const int k = lane >> 2, q = lane & 3;
+    const int mx = (job.mvc[1 + min(k, 6)][X264_CUDA_ME_MB_MVC - 1][0] + 2) >> 2, my = (job.mvc[1 + min(k, 6)][X264_CUDA_ME_MB_MVC - 1][1] + 2) >> 2;
+    const bool valid = k < n_ext && (mx | my) != 0;
+    const int cx = clip3i(mx, x_min, x_max), cy = clip3i(my, y_min, y_max);
+    int v = valid ? sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + cy) * stride + (q & 1) * 8 + cx, stride) : 0;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    __syncwarp();
+    if (q == 0) {
+        S.ext[k][0] = valid ? v + tab[(cx << 2) - job.mvp[0][0]] + tab[(cy << 2) - job.mvp[0][1]] : -1;
+        S.ext[k][1] = cx; S.ext[k][2] = cy;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int bc = COST_MAX + 1, bx = 0, by = 0;
+        for (int c = 0; c < NCAND; c++) {
+            if (c == NCAND - 1)
+                for (int e = 0; e < n_ext; e++)
+                    if (S.ext[e][0] >= 0 && S.ext[e][0] < bc) { bc = S.ext[e][0]; bx = S.ext[e][1]; by = S.ext[e][2]; }
+            if (S.pc_y[c] == (1 << 20)) continue;
+            int w = S.quad[c][0] + S.quad[c][1] + S.quad[c][2] + S.quad[c][3];
+            if (c != 0) w += tab[(S.pc_x[c] << 2) - job.mvp[0][0]] + tab[(S.pc_y[c] << 2) - job.mvp[0][1]];
+            if (w < bc) { bc = w; bx = S.pc_x[c]; by = S.pc_y[c]; }
+        }
+        S.seed[0][0] = bx; S.seed[0][1] = by; S.seed[0][2] = bc;
+    }
+    __syncwarp();
+}
+
 // The exhaustive pass over the union window of the partitions in `mask`.  Returns per-lane best keys in best[].
 // cyt: per union row the 9 partition y-costs, pre-shifted, | row<<2 (+3 pad) — dynamic smem of 2*me_range+1+MB_UNION_SLACK+4
 // rows (a small table leaves the L1 to the window tiles)
@@ -262,27 +299,11 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
                 pair_pq(t & 15, p, q);
                 S.quad[p * NCAND + c][q] = v[u];
             }
-            if (n_ext > 0 && (mask & 1)) { // warp-uniform: lane = extra predictor (lane >> 2) x quadrant (lane & 3), one 8x8 SAD each
-                const int k = lane >> 2, q = lane & 3;
-                const int mx = (job.mvc[1 + k][X264_CUDA_ME_MB_MVC - 1][0] + 2) >> 2, my = (job.mvc[1 + k][X264_CUDA_ME_MB_MVC - 1][1] + 2) >> 2;
-                const bool valid = k < n_ext && (mx | my) != 0;
-                const int cx = clip3i(mx, x_min, x_max), cy = clip3i(my, y_min, y_max);
-                int v = valid ? sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + cy) * stride + (q & 1) * 8 + cx, stride) : 0;
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (q == 0) {
-                    S.ext[k][0] = valid ? v + tab[(cx << 2) - job.mvp[0][0]] + tab[(cy << 2) - job.mvp[0][1]] : -1;
-                    S.ext[k][1] = cx; S.ext[k][2] = cy;
-                }
-            }
             __syncwarp();
             if (lane < NP) {
                 int bc = COST_MAX + 1, bx = 0, by = 0; // sequential strict '<' in candidate order
                 for (int c = 0; c < NCAND; c++) {
                     const int idx = lane * NCAND + c;
-                    if (c == NCAND - 1 && lane == 0 && n_ext > 0) // partition 0's extra predictors come before the (0,0) test (me.c:219-229)
-                        for (int k = 0; k < n_ext; k++)
-                            if (S.ext[k][0] >= 0 && S.ext[k][0] < bc) { bc = S.ext[k][0]; bx = S.ext[k][1]; by = S.ext[k][2]; }
                     if (S.pc_y[idx] == (1 << 20)) continue;
                     int v = S.quad[idx][0] + S.quad[idx][1] + S.quad[idx][2] + S.quad[idx][3];
                     if (c != 0) v += tab[(S.pc_x[idx] << 2) - job.mvp[lane][0]] + tab[(S.pc_y[idx] << 2) - job.mvp[lane][1]];
@@ -290,6 +311,7 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
                 }
                 S.seed[lane][0] = bx; S.seed[lane][1] = by; S.seed[lane][2] = bc;
             }
+            if (n_ext > 0 && (mask & 1)) seed_p0_wide(S, tab, ref0, stride, n_ext, x_min, x_max, y_min, y_max, lane); // warp-uniform, rare
         } else if (lane < NP) {
             S.seed[lane][0] = clip3i(job.seed_mv[lane][0], x_min, x_max);
             S.seed[lane][1] = clip3i(job.seed_mv[lane][1], y_min, y_max);
