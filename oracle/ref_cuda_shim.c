@@ -726,3 +726,77 @@ static void flush_batched(x264_t *h)
     n_recs = 0;
     free(jobs); free(res); free(tail); free(fin); free(idx);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Intra hook on live data: after x264_macroblock_analyse has decided an intra macroblock without RD, the device
+ * evaluates the Intra16x16 and chroma candidates of that macroblock (x264_cuda_intra_mb_costs) from the same source pixels and the
+ * same neighbouring reconstruction (still around p_fdec), with the macroblock's neighbour mask and lambda; its best chroma mode must be
+ * the encoder's h->mb.i_chroma_pred_mode and, when Intra16x16 won, its best 16x16 mode h->mb.i_intra16x16_pred_mode.  Exit 8. */
+void x264_macroblock_analyse_c(x264_t *h);
+extern const int x264_lambda_tab[52];
+static long long n_intra16, n_intra_chroma;
+
+static void report_intra(void)
+{
+    fprintf(stderr, "ref_cuda_shim: intra hooks: %lld Intra16x16 decisions, %lld chroma mode decisions repeated on the device and equal\n", n_intra16, n_intra_chroma);
+}
+
+void x264_macroblock_analyse(x264_t *h)
+{
+    x264_macroblock_analyse_c(h);
+    const int subme = h->param.analyse.i_subpel_refine - (h->sh.i_type == SLICE_TYPE_B);
+    if (!resid_hooks_on() || h->sh.b_mbaff || h->mb.b_lossless || subme >= 6 || !IS_INTRA(h->mb.i_type) || h->mb.i_type == I_PCM) return;
+    static int once;
+    if (!once++) atexit(report_intra);
+    resid_ctx(h);
+    x264_frame_t *f = h->fdec;
+    /* neighbours of this macroblock as the encoder sees them: row above, column left, corner of each p_fdec tile */
+    for (int i = 0; i < 3; i++) {
+        const int n = 16 >> !!i, s = f->i_stride[i];
+        uint8_t *dst = shadow[i] + (size_t)(PADV >> !!i) * s + (PADH >> !!i) + (size_t)h->mb.i_mb_y * n * s + h->mb.i_mb_x * n; /* picture origin inside the bordered plane */
+        const uint8_t *src = h->mb.pic.p_fdec[i];
+        memcpy(dst - s - 1, src - FDEC_STRIDE - 1, n + 1);
+        for (int y = 0; y < n; y++) dst[(ptrdiff_t)y * s - 1] = src[y * FDEC_STRIDE - 1];
+    }
+    static x264_cuda_frame_t *fnb;
+    if (!fnb) {
+        fnb = x264_cuda_frame_new(fctx, f->i_width[0] + 2 * PADH, f->i_lines[0] + 2 * PADV, X264_CUDA_FRAME_CHROMA);
+        if (!fnb) ck(-1, "x264_cuda_frame_new");
+    }
+    /* the bordered shadow planes are uploaded as one bigger picture, so that row -1 / column -1 of the first macroblocks exist too;
+     * the source frame goes into a frame of the same geometry at the same offset */
+    static x264_cuda_frame_t *fsrc;
+    static uint8_t *src_shadow[3];
+    if (!fsrc) {
+        fsrc = x264_cuda_frame_new(fctx, f->i_width[0] + 2 * PADH, f->i_lines[0] + 2 * PADV, X264_CUDA_FRAME_CHROMA);
+        if (!fsrc) ck(-1, "x264_cuda_frame_new");
+        for (int i = 0; i < 3; i++) src_shadow[i] = calloc((size_t)f->i_stride[i] * (f->i_lines[i] + 2 * PADV), 1);
+    }
+    for (int i = 0; i < 3; i++) {
+        const int n = 16 >> !!i, s = f->i_stride[i];
+        uint8_t *dst = src_shadow[i] + (size_t)(PADV >> !!i) * s + (PADH >> !!i) + (size_t)h->mb.i_mb_y * n * s + h->mb.i_mb_x * n;
+        for (int y = 0; y < n; y++) memcpy(dst + (size_t)y * s, h->mb.pic.p_fenc[i] + y * FENC_STRIDE, n);
+    }
+    const int W = f->i_width[0] + 2 * PADH, H = f->i_lines[0] + 2 * PADV;
+    ck(x264_cuda_frame_upload(fctx, fnb, shadow[0], f->i_stride[0], W, H), "upload nb");
+    ck(x264_cuda_frame_upload_chroma(fctx, fnb, X264_CUDA_PLANE_CB, shadow[1], f->i_stride[1], W / 2, H / 2), "upload nb cb");
+    ck(x264_cuda_frame_upload_chroma(fctx, fnb, X264_CUDA_PLANE_CR, shadow[2], f->i_stride[2], W / 2, H / 2), "upload nb cr");
+    ck(x264_cuda_frame_upload(fctx, fsrc, src_shadow[0], f->i_stride[0], W, H), "upload src");
+    ck(x264_cuda_frame_upload_chroma(fctx, fsrc, X264_CUDA_PLANE_CB, src_shadow[1], f->i_stride[1], W / 2, H / 2), "upload src cb");
+    ck(x264_cuda_frame_upload_chroma(fctx, fsrc, X264_CUDA_PLANE_CR, src_shadow[2], f->i_stride[2], W / 2, H / 2), "upload src cr");
+    x264_cuda_intra_job_t j;
+    memset(&j, 0, sizeof(j));
+    j.mb_x = h->mb.i_mb_x + PADH / 16; j.mb_y = h->mb.i_mb_y + PADV / 16; /* position inside the bordered picture */
+    j.neighbour = h->mb.i_neighbour;
+    j.flags = (h->pixf.mbcmp[0] == h->pixf.satd[0] ? X264_CUDA_INTRA_SATD : 0) | (h->sh.i_type == SLICE_TYPE_B ? X264_CUDA_INTRA_SLICE_B : 0);
+    j.lambda = x264_lambda_tab[h->mb.i_qp];
+    x264_cuda_intra_result_t r;
+    ck(x264_cuda_intra_mb_costs(fctx, fsrc, fnb, &j, 1, &r), "intra_mb_costs");
+    if (r.mode_chroma != h->mb.i_chroma_pred_mode || (h->mb.i_type == I_16x16 && r.mode16 != h->mb.i_intra16x16_pred_mode)) {
+        fprintf(stderr, "ref_cuda_shim: intra decision differs at frame %d mb (%d,%d) type %d: reference 16x16 mode %d chroma mode %d, device %d / %d\n",
+                h->fenc->i_frame, h->mb.i_mb_x, h->mb.i_mb_y, h->mb.i_type, h->mb.i_intra16x16_pred_mode, h->mb.i_chroma_pred_mode, r.mode16, r.mode_chroma);
+        exit(8);
+    }
+    n_intra_chroma++;
+    n_intra16 += h->mb.i_type == I_16x16;
+}
