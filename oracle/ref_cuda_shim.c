@@ -407,6 +407,7 @@ void x264_me_refine_bidir_satd(x264_t *h, x264_me_t *m0, x264_me_t *m1, int i_we
 #include "encoder/macroblock.h"
 void x264_macroblock_encode_c(x264_t *h);
 int x264_macroblock_probe_skip_c(x264_t *h, int b_bidir);
+static void mc_check(x264_t *h);
 static x264_cuda_frame_t *fpred;
 static uint8_t *shadow[3];
 static long long n_resid, n_probe, n_resid_c;
@@ -491,6 +492,7 @@ void x264_macroblock_encode(x264_t *h)
     }
     resid_ctx(h);
     if (!h->mb.b_skip_mc) x264_mb_mc(h); /* the prediction x264_macroblock_encode is about to form itself (macroblock.c:596-598) */
+    mc_check(h);
     upload_pred(h);
     x264_cuda_resid_job_t j;
     memset(&j, 0, sizeof(j));
@@ -799,4 +801,88 @@ void x264_macroblock_analyse(x264_t *h)
     }
     n_intra_chroma++;
     n_intra16 += h->mb.i_type == I_16x16;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Motion-compensation hook: the prediction x264_mb_mc has just formed in p_fdec for an inter macroblock is formed again on the device
+ * with the frame-batched x264_cuda_mc_blocks / x264_cuda_mc_blocks_bi — same partition walk as S/common/macroblock.c:560-655, vectors
+ * and reference indices from the macroblock cache, clipped like x264_mb_mc_0xywh (:462-467) — into a device frame, and the macroblock's
+ * luma and chroma pixels must be equal (exit 9).  Called from the x264_macroblock_encode wrapper. */
+static x264_cuda_frame_t *fmc;
+static long long n_mc_mb, n_mc_rect;
+static void report_mc(void)
+{
+    fprintf(stderr, "ref_cuda_shim: mc hooks: %lld inter macroblocks (%lld partition rectangles) predicted on the device and equal\n", n_mc_mb, n_mc_rect);
+}
+static void mc_rect(x264_t *h, int x, int y, int w, int hh, int lists)
+{
+    const int i8 = x264_scan8[0] + x + 8 * y;
+    int mv[2][2], ref[2];
+    for (int l = 0; l < 2; l++) {
+        ref[l] = h->mb.cache.ref[l][i8];
+        mv[l][0] = x264_clip3(h->mb.cache.mv[l][i8][0], h->mb.mv_min[0], h->mb.mv_max[0]);
+        mv[l][1] = x264_clip3(h->mb.cache.mv[l][i8][1], h->mb.mv_min[1], h->mb.mv_max[1]);
+    }
+    if (lists == 4) lists = ref[0] >= 0 ? (ref[1] >= 0 ? 3 : 1) : 2; /* x264_mb_mc_direct8x8 */
+    const int bx = 16 * h->mb.i_mb_x + 4 * x, by = 16 * h->mb.i_mb_y + 4 * y;
+    if (lists == 3) {
+        x264_cuda_mc_bi_job_t j;
+        memset(&j, 0, sizeof(j));
+        j.bx = bx; j.by = by; j.w = 4 * w; j.h = 4 * hh; j.weight = h->mb.bipred_weight[ref[0]][ref[1]];
+        j.mv0[0] = mv[0][0]; j.mv0[1] = mv[0][1]; j.mv1[0] = mv[1][0]; j.mv1[1] = mv[1][1];
+        ck(x264_cuda_mc_blocks_bi(fctx, dev_frame(h, h->fref0[ref[0]], 1), dev_frame(h, h->fref1[ref[1]], 1), fmc, &j, 1), "mc_blocks_bi");
+    } else {
+        const int l = lists == 2;
+        x264_cuda_mc_job_t j;
+        memset(&j, 0, sizeof(j));
+        j.bx = bx; j.by = by; j.w = 4 * w; j.h = 4 * hh; j.mvx = mv[l][0]; j.mvy = mv[l][1];
+        ck(x264_cuda_mc_blocks(fctx, dev_frame(h, l ? h->fref1[ref[l]] : h->fref0[ref[l]], 1), fmc, &j, 1), "mc_blocks");
+    }
+    n_mc_rect++;
+}
+static void mc_check(x264_t *h)
+{
+    x264_frame_t *f = h->fdec;
+    if (!fmc) {
+        fmc = x264_cuda_frame_new(fctx, f->i_width[0], f->i_lines[0], X264_CUDA_FRAME_CHROMA);
+        if (!fmc) ck(-1, "x264_cuda_frame_new");
+        atexit(report_mc);
+    }
+    const int t = h->mb.i_type;
+    if (t == P_L0 || (t != P_8x8 && t != B_8x8 && t != B_SKIP && t != B_DIRECT)) {
+        const uint8_t *l0 = x264_mb_type_list_table[t][0], *l1 = x264_mb_type_list_table[t][1];
+        const int n = h->mb.i_partition == D_16x16 ? 1 : 2;
+        for (int k = 0; k < n; k++) {
+            const int lists = t == P_L0 ? 1 : (l0[k] ? 1 : 0) | (l1[k] ? 2 : 0);
+            if (h->mb.i_partition == D_16x16) mc_rect(h, 0, 0, 4, 4, lists);
+            else if (h->mb.i_partition == D_16x8) mc_rect(h, 0, 2 * k, 4, 2, lists);
+            else mc_rect(h, 2 * k, 0, 2, 4, lists);
+        }
+    } else
+        for (int i8 = 0; i8 < 4; i8++) {
+            const int x = 2 * (i8 & 1), y = 2 * (i8 >> 1);
+            if (t == B_SKIP || t == B_DIRECT) { mc_rect(h, x, y, 2, 2, 4); continue; }
+            switch (h->mb.i_sub_partition[i8]) {
+            case D_L0_8x8: mc_rect(h, x, y, 2, 2, 1); break;
+            case D_L0_8x4: mc_rect(h, x, y, 2, 1, 1); mc_rect(h, x, y + 1, 2, 1, 1); break;
+            case D_L0_4x8: mc_rect(h, x, y, 1, 2, 1); mc_rect(h, x + 1, y, 1, 2, 1); break;
+            case D_L0_4x4: mc_rect(h, x, y, 1, 1, 1); mc_rect(h, x + 1, y, 1, 1, 1); mc_rect(h, x, y + 1, 1, 1, 1); mc_rect(h, x + 1, y + 1, 1, 1, 1); break;
+            case D_L1_8x8: mc_rect(h, x, y, 2, 2, 2); break;
+            case D_BI_8x8: mc_rect(h, x, y, 2, 2, 3); break;
+            case D_DIRECT_8x8: mc_rect(h, x, y, 2, 2, 4); break;
+            default: return; /* (B sub-8x8 partitions do not exist in this encoder) */
+            }
+        }
+    static const int ids[3] = { X264_CUDA_PLANE_FULL, X264_CUDA_PLANE_CB, X264_CUDA_PLANE_CR };
+    for (int i = 0; i < 3; i++) {
+        const int s = f->i_stride[i], padv = PADV >> !!i, padh = PADH >> !!i, n = 16 >> !!i;
+        ck(x264_cuda_frame_download(fctx, fmc, ids[i], tmp_plane, s), "download prediction");
+        for (int y = 0; y < n; y++)
+            if (memcmp(tmp_plane + (size_t)(padv + h->mb.i_mb_y * n + y) * s + padh + h->mb.i_mb_x * n, h->mb.pic.p_fdec[i] + y * FDEC_STRIDE, n)) {
+                fprintf(stderr, "ref_cuda_shim: x264_mb_mc differs at frame %d mb (%d,%d) type %d partition %d plane %d row %d\n", h->fenc->i_frame, h->mb.i_mb_x,
+                        h->mb.i_mb_y, t, h->mb.i_partition, i, y);
+                exit(9);
+            }
+    }
+    n_mc_mb++;
 }

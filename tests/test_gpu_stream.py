@@ -92,6 +92,11 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     print(tag, "intra hooks", intra)
     if not re.search(r"--subme [6-9]", opts):   # (RD decides modes differently: left to C there) every intra macroblock's 16x16 / chroma mode choice agreed (exit 8)
         assert intra is not None and intra[1] >= (w // 16) * (h // 16) // 2 and (not smooth or intra[0] > n * 2), intra
+    m = re.search(r"mc hooks: (\d+) inter macroblocks \((\d+) partition rectangles\) predicted on the device and equal", r.stderr)
+    mc = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "mc hooks", mc)
+    # the prediction of every inter macroblock encode formed again with x264_cuda_mc_blocks / _bi from the cache's vectors (exit 9)
+    assert smooth or static or (mc is not None and mc[0] == resid[0] and mc[1] >= mc[0]), (mc, resid)
     # PSNR / SSIM slabs of every kept frame, and with rate control the AQ offsets of every input frame (exit 7 on a difference)
     assert metric is not None and metric[1] >= 3 and metric[2] >= 1 and (metric[0] == n or "--crf" not in opts), metric
     # every inter macroblock encode (coefficients, nnz, cbp, reconstruction) and every skip probe was repeated on the device (exit 6 on a difference)
