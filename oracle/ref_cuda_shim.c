@@ -66,6 +66,8 @@ void x264_frame_expand_border_filtered_c(x264_t *h, x264_frame_t *frame, int mb_
 void x264_frame_deblock_row_c(x264_t *h, int mb_y);
 
 static x264_cuda_t *fctx;
+static long long slot_clock;
+static x264_cuda_frame_t *lowres_slot(x264_t *h, x264_frame_t *f, int frame_no, int create);
 static x264_t *g_h; /* for the hooks whose reference signature does not carry the encoder handle */
 static x264_cuda_frame_t *ffr;
 static uint8_t *tmp_plane, *pre[3];
@@ -124,12 +126,13 @@ void x264_frame_init_lowres(x264_t *h, x264_frame_t *frame)
     x264_frame_init_lowres_c(h, frame); /* pixel work + the per-frame lookahead bookkeeping (mc.c:306-331) */
     if (!hooks_on()) return;
     frame_ctx(h, frame);
-    ck(x264_cuda_frame_upload(fctx, ffr, frame->plane[0], frame->i_stride[0], frame->i_width[0], frame->i_lines[0]), "upload");
-    ck(x264_cuda_frame_expand_border(fctx, ffr), "expand_border");
-    ck(x264_cuda_frame_init_lowres(fctx, ffr), "init_lowres");
+    x264_cuda_frame_t *dl = lowres_slot(h, frame, frame->i_frame, 1); /* kept per input frame: the lookahead hook evaluates costs on these planes */
+    ck(x264_cuda_frame_upload(fctx, dl, frame->plane[0], frame->i_stride[0], frame->i_width[0], frame->i_lines[0]), "upload");
+    ck(x264_cuda_frame_expand_border(fctx, dl), "expand_border");
+    ck(x264_cuda_frame_init_lowres(fctx, dl), "init_lowres");
     const int s = frame->i_stride_lowres, rows = frame->i_lines_lowres + 2 * PADV, cols = frame->i_width_lowres + 2 * PADH;
     for (int k = 0; k < 4; k++) {
-        ck(x264_cuda_frame_download(fctx, ffr, X264_CUDA_PLANE_LOWRES + k, tmp_plane, s), "download lowres");
+        ck(x264_cuda_frame_download(fctx, dl, X264_CUDA_PLANE_LOWRES + k, tmp_plane, s), "download lowres");
         uint8_t *host = frame->lowres[k] - (s * PADV + PADH);
         if (k < 3)
             same_then_take("lowres plane", host, tmp_plane, s, 1, 0, rows, 0, cols);
@@ -216,7 +219,7 @@ extern int16_t *g_cost_mv[52];
 
 typedef struct { x264_frame_t *f; int frame, poc, is_ref; x264_cuda_frame_t *d; long long used; } dev_slot;
 static dev_slot slots[8];
-static long long slot_clock, n_search, n_qpel, n_bidir, n_skipped;
+static long long n_search, n_qpel, n_bidir, n_skipped;
 static int cost_uploaded[52];
 
 static int me_hooks_on(void)
@@ -885,4 +888,98 @@ static void mc_check(x264_t *h)
             }
     }
     n_mc_mb++;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Lookahead hook: x264_slicetype_frame_cost is static, but rate control reaches it through the extern x264_rc_analyse_slice
+ * (S/encoder/slicetype.c:638-679; CRF / ABR only).  After the C call, the cost of the same (p0, p1, b) is evaluated from scratch on the
+ * device (x264_cuda_lowres_frame_cost on the lowres planes the device itself produced when each frame came in) and must reproduce what
+ * the reference holds for that frame: i_cost_est, i_intra_mbs, and the motion vectors / costs of every interior block.  Exit 10.
+ * B frames are checked when the index arithmetic of :661-662 agrees with the frame's true position (it does not always). */
+int x264_rc_analyse_slice_c(x264_t *h);
+typedef struct { int frame; x264_cuda_frame_t *d; long long used; } lslot_t;
+static lslot_t lslots[12];
+static long long n_la_p, n_la_b, n_la_skipped;
+
+static void report_la(void)
+{
+    fprintf(stderr, "ref_cuda_shim: lookahead hooks: %lld P and %lld B frame costs re-evaluated on the device and equal; %lld left to C\n", n_la_p, n_la_b, n_la_skipped);
+}
+static x264_cuda_frame_t *lowres_slot(x264_t *h, x264_frame_t *f, int frame_no, int create)
+{
+    lslot_t *victim = &lslots[0];
+    for (int i = 0; i < 12; i++) {
+        if (lslots[i].d && lslots[i].frame == frame_no) { lslots[i].used = ++slot_clock; return lslots[i].d; }
+        if (lslots[i].used < victim->used) victim = &lslots[i];
+    }
+    if (!create) return NULL;
+    if (!victim->d) {
+        victim->d = x264_cuda_frame_new(fctx, f->i_width[0], f->i_lines[0], X264_CUDA_FRAME_LOWRES);
+        if (!victim->d) ck(-1, "x264_cuda_frame_new");
+    }
+    victim->frame = frame_no; victim->used = ++slot_clock;
+    return victim->d;
+}
+
+int x264_rc_analyse_slice(x264_t *h)
+{
+    const int cost = x264_rc_analyse_slice_c(h);
+    static int once;
+    if (!hooks_on() || h->sh.b_mbaff || h->param.rc.i_vbv_buffer_size || !h->frames.b_have_lowres) return cost;
+    if (!once++) atexit(report_la);
+    if (IS_X264_TYPE_I(h->fenc->i_type)) return cost;
+    x264_frame_t *f0 = h->fref0[0], *f1 = NULL, *fb = h->fenc;
+    int p1, b;
+    if (h->fenc->i_type == X264_TYPE_P) {
+        p1 = 0;
+        while (h->frames.current[p1] && IS_X264_TYPE_B(h->frames.current[p1]->i_type)) p1++;
+        b = ++p1;
+    } else {
+        f1 = h->fref1[0];
+        p1 = (f1->i_poc - f0->i_poc) / 2;
+        b = (f1->i_poc - fb->i_poc) / 2;
+        if (b != (fb->i_poc - f0->i_poc) / 2) { n_la_skipped++; return cost; }
+    }
+    /* the source frames' numbers: reconstructed frames carry poc = 2 * (frame - last idr) (encoder.c:1514-1515) */
+    const int nb = fb->i_frame, n0 = f0->i_poc / 2 + h->frames.i_last_idr, n1 = f1 ? f1->i_poc / 2 + h->frames.i_last_idr : nb;
+    x264_cuda_frame_t *db = lowres_slot(h, fb, nb, 0), *d0 = lowres_slot(h, fb, n0, 0), *d1 = lowres_slot(h, fb, n1, 0);
+    if (!db || !d0 || !d1 || nb - n0 != b || (f1 && n1 - n0 != p1)) { n_la_skipped++; return cost; }
+    const int n_dist = h->param.i_bframe + 1, n_mb = h->mb.i_mb_count;
+    ck(x264_cuda_frame_lookahead_alloc(fctx, db, n_dist), "lookahead_alloc"); /* fresh state: everything is searched again */
+    if (f1) { /* the direct-like candidate of a B block reads the later reference's own list-0 vectors (slicetype.c:96-112) */
+        ck(x264_cuda_frame_lookahead_alloc(fctx, d1, n_dist), "lookahead_alloc");
+        ck(x264_cuda_frame_lookahead_set(fctx, d1, 0, p1 - 1, &f1->lowres_mvs[0][p1 - 1][0][0], f1->lowres_mv_costs[0][p1 - 1], NULL), "lookahead_set");
+    }
+    x264_cuda_lowres_params_t pm;
+    memset(&pm, 0, sizeof(pm));
+    pm.p0 = 0; pm.p1 = p1; pm.b = b; pm.me_method = h->param.analyse.i_me_method; pm.me_range = h->param.analyse.i_me_range;
+    pm.flags = (h->pixf.mbcmp[0] == h->pixf.satd[0] ? X264_CUDA_ME_MBCMP_SATD : 0) | (h->pixf.fpelcmp[0] == h->pixf.satd[0] ? X264_CUDA_ME_FPEL_SATD : 0) |
+               (h->param.analyse.b_weighted_bipred ? X264_CUDA_LOWRES_WEIGHTED_BIPRED : 0);
+    pm.do_search[0] = 1; pm.do_search[1] = b != p1;
+    x264_cuda_lowres_result_t r;
+    ck(x264_cuda_lowres_frame_cost(fctx, db, d0, d1, &pm, &r), "lowres_frame_cost");
+    int score = r.score;
+    if (b != p1) score = score * 100 / (120 + h->param.i_bframe_bias);
+    int bad = score != fb->i_cost_est[b][p1 - b];
+    if (b == p1) bad |= (r.intra_mbs != fb->i_intra_mbs[b]) << 1;
+    int16_t *mv = malloc(n_mb * 4);
+    int *cs = malloc(n_mb * sizeof(int));
+    const int W = h->sps->i_mb_width, H = h->sps->i_mb_height;
+    for (int l = 0; l < 1 + (b != p1) && !bad; l++) {
+        const int d = l ? p1 - b - 1 : b - 1;
+        ck(x264_cuda_frame_lookahead_get(fctx, db, l, d, mv, cs, NULL), "lookahead_get");
+        for (int y = 1; y < H - 1; y++)
+            for (int x = 1; x < W - 1; x++) {
+                const int i = y * W + x;
+                if (mv[2 * i] != fb->lowres_mvs[l][d][i][0] || mv[2 * i + 1] != fb->lowres_mvs[l][d][i][1] || cs[i] != fb->lowres_mv_costs[l][d][i]) bad |= 4 << l;
+            }
+    }
+    free(mv); free(cs);
+    if (bad) {
+        fprintf(stderr, "ref_cuda_shim: lookahead cost differs for frame %d (p0 %d, p1 %d, b %d): reference score %d intra mbs %d, device %d / %d, mask %d\n", nb, 0,
+                p1, b, fb->i_cost_est[b][p1 - b], fb->i_intra_mbs[b], score, r.intra_mbs, bad);
+        exit(10);
+    }
+    if (b == p1) n_la_p++; else n_la_b++;
+    return cost;
 }

@@ -26,6 +26,7 @@ CONFIGS = [
     ("cavlc_8x8dct_deblock", 96, 64, 3, "--me hex --subme 4 --no-cabac --8x8dct --deblock 2:-1 --chroma-qp-offset 3"),
     ("cqm_jvt", 160, 128, 2, "--me hex --subme 4 --cqm jvt"),
     ("crf_aq_lookahead", 96, 64, 5, "--crf 24 --me hex --subme 6 --bframes 2 --b-adapt 2"),               # lowres costs steer rate control
+    ("crf_fixed_b", 96, 64, 7, "--crf 24 --me hex --subme 5 --bframes 1 --b-adapt 0 --weightb"),           # B-frame lowres costs, bidir
     ("static_skips", 96, 64, 5, "--me hex --subme 4 --bframes 1 --static"),                               # P- and B-skip probes everywhere
     ("smooth_i16x16", 96, 64, 3, "--me dia --subme 2 --keyint 1 --smooth"),                               # all-intra, Intra16x16 wins often
 ]
@@ -97,6 +98,11 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     print(tag, "mc hooks", mc)
     # the prediction of every inter macroblock encode formed again with x264_cuda_mc_blocks / _bi from the cache's vectors (exit 9)
     assert smooth or static or (mc is not None and mc[0] == resid[0] and mc[1] >= mc[0]), (mc, resid)
+    m = re.search(r"lookahead hooks: (\d+) P and (\d+) B frame costs re-evaluated on the device and equal; (\d+) left to C", r.stderr)
+    la = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "lookahead hooks", la)
+    if "--crf" in opts:   # rate control asks for each frame's lowres cost (x264_rc_analyse_slice): re-evaluated from scratch on the device (exit 10)
+        assert la is not None and la[0] >= 1, la
     # PSNR / SSIM slabs of every kept frame, and with rate control the AQ offsets of every input frame (exit 7 on a difference)
     assert metric is not None and metric[1] >= 3 and metric[2] >= 1 and (metric[0] == n or "--crf" not in opts), metric
     # every inter macroblock encode (coefficients, nnz, cbp, reconstruction) and every skip probe was repeated on the device (exit 6 on a difference)
