@@ -306,6 +306,42 @@ static void me_differs(const char *what, x264_t *h, const x264_me_t *m, const x2
 }
 
 static void record_search(x264_t *h, x264_frame_t *ref, const x264_cuda_me_job_t *j, const x264_me_t *m);
+static long long n_grid, n_grid_outside;
+static void report_grid(void)
+{
+    fprintf(stderr, "ref_cuda_shim: grid replay: %lld ESA searches replayed on device SAD grids and equal; %lld needed a vector outside the grid\n", n_grid, n_grid_outside);
+}
+/* the sequential-predictor path of INTEGRATION.md: SAD grids of the macroblock around a guessed centre (here: the rounded mvp of the 16x16
+ * search would do; we use this search's own mvp), then x264_cuda_host_esa_replay with the exact predictors must give the per-block
+ * kernel's full-pel result (which the caller has just shown to lead to the C result) */
+static void grid_replay_check(x264_t *h, const x264_me_t *m, const x264_cuda_me_job_t *j, const x264_cuda_me_result_t *want, x264_cuda_frame_t *denc,
+                              x264_cuda_frame_t *dref, int range)
+{
+    static uint16_t *grid;
+    static int once;
+    const int R = range + 8, gw = X264_CUDA_GRID_W(R), gh = X264_CUDA_GRID_H(R);
+    if (!once++) { atexit(report_grid); }
+    if (!grid) grid = malloc((size_t)9 * X264_CUDA_GRID_W(64 + 8) * X264_CUDA_GRID_H(64 + 8) * sizeof(uint16_t));
+    if (range > 64) return;
+    const int ox = j->bx & 15, oy = j->by & 15;
+    const int part = m->i_pixel == PIXEL_16x16 ? 0 : m->i_pixel == PIXEL_16x8 ? 1 + (oy >> 3) : m->i_pixel == PIXEL_8x16 ? 3 + (ox >> 3) : 5 + (oy >> 3) * 2 + (ox >> 3);
+    x264_cuda_grid_job_t g;
+    memset(&g, 0, sizeof(g));
+    g.mb_x = j->bx >> 4; g.mb_y = j->by >> 4; g.part_mask = 1 << part;
+    g.cx = x264_clip3((j->mvp[0] + 2) >> 2, j->mv_min_fpel[0], j->mv_max_fpel[0]);
+    g.cy = x264_clip3((j->mvp[1] + 2) >> 2, j->mv_min_fpel[1], j->mv_max_fpel[1]);
+    for (int k = 0; k < 2; k++) { g.mv_min_fpel[k] = j->mv_min_fpel[k]; g.mv_max_fpel[k] = j->mv_max_fpel[k]; }
+    ck(x264_cuda_sad_grid(fctx, denc, dref, R, &g, 1, grid), "sad_grid");
+    x264_cuda_me_result_t r;
+    const int rc = x264_cuda_host_esa_replay(grid + (size_t)part * gw * gh, R, g.cx, g.cy, j, range, m->p_cost_mv - 2 * 4 * 2048, &r);
+    if (rc) { n_grid_outside++; return; }
+    if (r.bmx != want->bmx || r.bmy != want->bmy || r.bcost != want->bcost) {
+        fprintf(stderr, "ref_cuda_shim: grid replay differs at block (%d,%d) part %d: search (%d,%d) %d, replay (%d,%d) %d\n", j->bx, j->by, part, want->bmx, want->bmy,
+                want->bcost, r.bmx, r.bmy, r.bcost);
+        exit(5);
+    }
+    n_grid++;
+}
 static void flush_batched(x264_t *h);
 
 void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh)
@@ -337,6 +373,7 @@ void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, i
         ck(x264_cuda_me_search(fctx, denc, dref, range, &j, 1, &r), "me_search");
         j.seed_mv[0] = r.bmx; j.seed_mv[1] = r.bmy; j.seed_cost = r.bcost;
         ck(x264_cuda_me_search_small(fctx, denc, dref, X264_CUDA_ME_METHOD_SEEDED, range, subme, &j, 1, &fin), "me_search_small (seeded)");
+        if (m->i_pixel <= PIXEL_8x8) grid_replay_check(h, m, &j, &r, denc, dref, range);
     } else
         ck(x264_cuda_me_search_small(fctx, denc, dref, method == X264_ME_TESA ? X264_CUDA_ME_METHOD_TESA : method, range, subme, &j, 1, &fin), "me_search_small");
     if (fin.mv[0] != m->mv[0] || fin.mv[1] != m->mv[1] || fin.cost != m->cost || fin.cost_mv != m->cost_mv) me_differs("x264_me_search_ref", h, m, &fin, bx, by);

@@ -86,6 +86,11 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     m = re.search(r"batched ESA: (\d+) partition searches in (\d+) x264_cuda_me_search_mb launches equal to the C results; (\d+) not representable", r.stderr)
     batched = tuple(int(x) for x in m.groups()) if m else None
     print(tag, "batched ESA", batched)
+    m = re.search(r"grid replay: (\d+) ESA searches replayed on device SAD grids and equal; (\d+) needed a vector outside the grid", r.stderr)
+    grid = tuple(int(x) for x in m.groups()) if m else None
+    print(tag, "grid replay", grid)
+    if "--me esa" in opts:   # SAD grids (x264_cuda_sad_grid) + host replay with the exact predictors reproduce each full-pel ESA result
+        assert grid is not None and grid[0] > 20 * (n - 1), grid
     if "--me esa" in opts:   # the macroblock-batched kernel searched whole frames of recorded partitions and agreed with every C result
         assert batched is not None and batched[0] > 20 * (n - 1) and batched[1] >= n - 1, batched
     m = re.search(r"intra hooks: (\d+) Intra16x16 decisions, (\d+) chroma mode decisions repeated on the device and equal", r.stderr)
