@@ -20,6 +20,7 @@ CONFIGS = [
     ("hex_8x8dct_b", 96, 64, 4, "--me hex --subme 5 --8x8dct --bframes 1"),
     ("esa", 96, 64, 2, "--me esa --merange 8 --subme 2"),                                                 # config 2's search
     ("esa_refs_b", 96, 64, 5, "--me esa --merange 16 --subme 2 --ref 2 --bframes 1"),                     # config 2 with two refs and B-frames
+    ("cif_esa", 352, 288, 2, "--me esa --merange 16 --subme 2"),                                          # 396 macroblocks per batched launch
     ("esa_p4x4", 64, 48, 2, "--me esa --merange 8 --subme 2 --partitions all"),                           # 4x4 integral plane
     ("umh_rd_weightb", 64, 48, 5, "--me umh --subme 7 --8x8dct --bframes 2 --b-adapt 2 --weightb --mixed-refs --ref 2"),  # config 3
     ("tesa_b3", 64, 48, 5, "--me tesa --merange 8 --subme 6 --bframes 3 --b-adapt 2"),                    # config 4's options
