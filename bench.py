@@ -440,7 +440,7 @@ def run_ours(args):
                                "note": "same 73440 searches as independent x264_cuda_me_search jobs (no SAD sharing)"},
         }
         if world == 1 and not args.no_cpu:
-            rate, kind, cores, sample, _ = cpu_rate(1, 9 * 120 * 8, 2)
+            rate, kind, cores, sample, _ = cpu_rate(1, 9 * 120 * 32, 60)  # ~10 s of the reference's C on one core
             line["cpu_baseline"] = {"value": rate / 1e9, "unit": "Gcand/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
     for f in frames:
