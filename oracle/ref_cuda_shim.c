@@ -932,7 +932,8 @@ static void mc_check(x264_t *h)
  * (S/encoder/slicetype.c:638-679; CRF / ABR only).  After the C call, the cost of the same (p0, p1, b) is evaluated from scratch on the
  * device (x264_cuda_lowres_frame_cost on the lowres planes the device itself produced when each frame came in) and must reproduce what
  * the reference holds for that frame: i_cost_est, i_intra_mbs, and the motion vectors / costs of every interior block.  Exit 10.
- * B frames are checked when the index arithmetic of :661-662 agrees with the frame's true position (it does not always). */
+ * B frames would be checked when the index arithmetic of :661-662 agrees with the frame's true position, but rate control does not ask for
+ * them in this version; the x264_slicetype_decide wrapper below covers B-type estimates. */
 int x264_rc_analyse_slice_c(x264_t *h);
 typedef struct { int frame; x264_cuda_frame_t *d; long long used; } lslot_t;
 static lslot_t lslots[12];
@@ -958,32 +959,15 @@ static x264_cuda_frame_t *lowres_slot(x264_t *h, x264_frame_t *f, int frame_no, 
     return victim->d;
 }
 
-int x264_rc_analyse_slice(x264_t *h)
+/* re-evaluates cost(p0 = 0, p1, b) of source frame nb against frames n0 (and n1) on the device, from scratch, and compares it with what the
+ * frame object fb holds; f1 = the later reference's object (B only).  Returns 0 when the frames are not on the device (nothing compared). */
+static int check_lowres_cost(x264_t *h, x264_frame_t *fb, x264_frame_t *f1, int nb, int n0, int n1, int p1, int b)
 {
-    const int cost = x264_rc_analyse_slice_c(h);
-    static int once;
-    if (!hooks_on() || h->sh.b_mbaff || h->param.rc.i_vbv_buffer_size || !h->frames.b_have_lowres) return cost;
-    if (!once++) atexit(report_la);
-    if (IS_X264_TYPE_I(h->fenc->i_type)) return cost;
-    x264_frame_t *f0 = h->fref0[0], *f1 = NULL, *fb = h->fenc;
-    int p1, b;
-    if (h->fenc->i_type == X264_TYPE_P) {
-        p1 = 0;
-        while (h->frames.current[p1] && IS_X264_TYPE_B(h->frames.current[p1]->i_type)) p1++;
-        b = ++p1;
-    } else {
-        f1 = h->fref1[0];
-        p1 = (f1->i_poc - f0->i_poc) / 2;
-        b = (f1->i_poc - fb->i_poc) / 2;
-        if (b != (fb->i_poc - f0->i_poc) / 2) { n_la_skipped++; return cost; }
-    }
-    /* the source frames' numbers: reconstructed frames carry poc = 2 * (frame - last idr) (encoder.c:1514-1515) */
-    const int nb = fb->i_frame, n0 = f0->i_poc / 2 + h->frames.i_last_idr, n1 = f1 ? f1->i_poc / 2 + h->frames.i_last_idr : nb;
     x264_cuda_frame_t *db = lowres_slot(h, fb, nb, 0), *d0 = lowres_slot(h, fb, n0, 0), *d1 = lowres_slot(h, fb, n1, 0);
-    if (!db || !d0 || !d1 || nb - n0 != b || (f1 && n1 - n0 != p1)) { n_la_skipped++; return cost; }
+    if (!db || !d0 || !d1 || nb - n0 != b || n1 - n0 != p1) return 0;
     const int n_dist = h->param.i_bframe + 1, n_mb = h->mb.i_mb_count;
     ck(x264_cuda_frame_lookahead_alloc(fctx, db, n_dist), "lookahead_alloc"); /* fresh state: everything is searched again */
-    if (f1) { /* the direct-like candidate of a B block reads the later reference's own list-0 vectors (slicetype.c:96-112) */
+    if (b != p1) { /* the direct-like candidate of a B block reads the later reference's own list-0 vectors (slicetype.c:96-112) */
         ck(x264_cuda_frame_lookahead_alloc(fctx, d1, n_dist), "lookahead_alloc");
         ck(x264_cuda_frame_lookahead_set(fctx, d1, 0, p1 - 1, &f1->lowres_mvs[0][p1 - 1][0][0], f1->lowres_mv_costs[0][p1 - 1], NULL), "lookahead_set");
     }
@@ -1018,5 +1002,76 @@ int x264_rc_analyse_slice(x264_t *h)
         exit(10);
     }
     if (b == p1) n_la_p++; else n_la_b++;
+    return 1;
+}
+
+int x264_rc_analyse_slice(x264_t *h)
+{
+    const int cost = x264_rc_analyse_slice_c(h);
+    static int once;
+    if (!hooks_on() || h->sh.b_mbaff || h->param.rc.i_vbv_buffer_size || !h->frames.b_have_lowres) return cost;
+    if (!once++) atexit(report_la);
+    if (IS_X264_TYPE_I(h->fenc->i_type)) return cost;
+    x264_frame_t *f0 = h->fref0[0], *f1 = NULL, *fb = h->fenc;
+    int p1, b;
+    if (h->fenc->i_type == X264_TYPE_P) {
+        p1 = 0;
+        while (h->frames.current[p1] && IS_X264_TYPE_B(h->frames.current[p1]->i_type)) p1++;
+        b = ++p1;
+    } else {
+        f1 = h->fref1[0];
+        p1 = (f1->i_poc - f0->i_poc) / 2;
+        b = (f1->i_poc - fb->i_poc) / 2;
+        if (b != (fb->i_poc - f0->i_poc) / 2) { n_la_skipped++; return cost; }
+    }
+    /* the source frames' numbers: reconstructed frames carry poc = 2 * (frame - last idr) (encoder.c:1514-1515) */
+    const int nb = fb->i_frame, n0 = f0->i_poc / 2 + h->frames.i_last_idr, n1 = f1 ? f1->i_poc / 2 + h->frames.i_last_idr : nb;
+    if (!check_lowres_cost(h, fb, f1, nb, n0, n1, p1, b)) n_la_skipped++;
     return cost;
+}
+
+/* x264_slicetype_decide (slicetype.c:577-636) runs the B-adapt analysis, which leaves cost estimates cached in the undecided frames
+ * (i_cost_est[b - p0][p1 - b]).  Every estimate this call adds — P-type (p1 == b: a frame predicted from an earlier one at distance
+ * 1..bframes+1) and B-type (a frame between two others) — is re-evaluated from scratch on the device and compared. */
+void x264_slicetype_decide_c(x264_t *h);
+void x264_slicetype_decide(x264_t *h)
+{
+    x264_frame_t *objs[X264_BFRAME_MAX * 4 + 4] = { NULL };
+    int n = 0, n0 = 0;
+    const int on = hooks_on() && !h->sh.b_mbaff && h->frames.b_have_lowres && !h->param.rc.i_vbv_buffer_size && h->frames.last_nonb && h->frames.next[0];
+    if (on) {
+        static int once;
+        if (!once++) atexit(report_la);
+        n0 = h->frames.last_nonb->i_poc / 2 + h->frames.i_last_idr;
+        for (int j = 0; h->frames.next[j] && h->frames.next[j]->i_type == X264_TYPE_AUTO && n < X264_BFRAME_MAX * 4 + 2; j++) objs[++n] = h->frames.next[j];
+    }
+    int before[X264_BFRAME_MAX * 4 + 4][X264_BFRAME_MAX + 2];
+    static int beforeb[X264_BFRAME_MAX * 4 + 4][X264_BFRAME_MAX + 2][X264_BFRAME_MAX + 2];
+    for (int k = 1; k <= n; k++)
+        for (int d = 1; d <= h->param.i_bframe + 1 && d <= X264_BFRAME_MAX + 1; d++) {
+            before[k][d] = objs[k]->i_cost_est[d][0];
+            for (int e = 1; e <= h->param.i_bframe + 1 && e <= X264_BFRAME_MAX + 1; e++) beforeb[k][d][e] = objs[k]->i_cost_est[d][e];
+        }
+    x264_slicetype_decide_c(h);
+    /* B-type estimates: frame k between k - d and k + e, provided the later frame's own vectors towards k - d exist (they feed the direct-like
+     * candidate, slicetype.c:96-112, and the B-adapt analysis evaluates that P cost first) */
+    if (on)
+        for (int k = 1; k < n; k++) {
+            x264_frame_t *fb = objs[k];
+            if (fb->i_frame != n0 + k) continue;
+            for (int d = 1; d <= k && d <= h->param.i_bframe + 1; d++)
+                for (int e = 1; k + e <= n && d + e <= h->param.i_bframe + 1; e++) {
+                    x264_frame_t *f1 = objs[k + e];
+                    if (fb->i_cost_est[d][e] < 0 || beforeb[k][d][e] >= 0 || f1->i_frame != n0 + k + e) continue;
+                    if (f1->lowres_mvs[0][d + e - 1][0][0] == 0x7FFF) { n_la_skipped++; continue; }
+                    if (!check_lowres_cost(h, fb, f1, fb->i_frame, fb->i_frame - d, fb->i_frame + e, d + e, d)) n_la_skipped++;
+                }
+        }
+    for (int k = 1; k <= n; k++) {
+        x264_frame_t *fb = objs[k];
+        if (fb->i_frame != n0 + k) continue; /* (consecutive numbering expected: last non-B, then the undecided frames) */
+        for (int d = 1; d <= k && d <= h->param.i_bframe + 1; d++)
+            if (fb->i_cost_est[d][0] >= 0 && before[k][d] < 0)   /* newly evaluated: frame n0 + k predicted from frame n0 + k - d */
+                if (!check_lowres_cost(h, fb, NULL, fb->i_frame, fb->i_frame - d, fb->i_frame, d, d)) n_la_skipped++;
+    }
 }

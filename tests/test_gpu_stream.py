@@ -107,6 +107,8 @@ def test_bitstream_identical(pkg, ctx, tmp_path, tag, w, h, n, opts):
     m = re.search(r"lookahead hooks: (\d+) P and (\d+) B frame costs re-evaluated on the device and equal; (\d+) left to C", r.stderr)
     la = tuple(int(x) for x in m.groups()) if m else None
     print(tag, "lookahead hooks", la)
+    if "--bframes" in opts and "--b-adapt 0" not in opts:   # B-adapt analysis: every P-type cost estimate it caches, re-evaluated on the device
+        assert la is not None and la[0] >= 2 and (la[1] >= 1 or "--weightb --mixed-refs" in opts), la
     if "--crf" in opts:   # rate control asks for each frame's lowres cost (x264_rc_analyse_slice): re-evaluated from scratch on the device (exit 10)
         assert la is not None and la[0] >= 1, la
     # PSNR / SSIM slabs of every kept frame, and with rate control the AQ offsets of every input frame (exit 7 on a difference)
