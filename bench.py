@@ -680,12 +680,7 @@ def run_rows(args):
     ctimed("f2 SSD + SSIM sums + AQ energies + hadamard_ac", lambda: (o.frame_ssd(a2, b2, W, H), o.frame_ssim(a2, b2, W, H), o.frame_mb_energy(og, pe, cu, cv),
                                                                       o.frame_mb_hadamard_ac(og, pe)))
     # residual and MC: the reference is per-macroblock code; time a sample of macroblocks through it and scale
-    class RIn(C.Structure):
-        _fields_ = [(n, C.c_int) for n in ("qp", "chroma_qp", "b_transform_8x8", "b_decimate", "cqm")]
-
-    class ROut(C.Structure):
-        _fields_ = [("luma4x4", (C.c_int16 * 16) * 24), ("luma8x8", (C.c_int16 * 64) * 4), ("chroma_dc", (C.c_int16 * 4) * 2),
-                    ("nnz", C.c_uint8 * 27), ("pad", C.c_uint8), ("cbp_luma", C.c_int), ("cbp_chroma", C.c_int)]
+    RIn, ROut = X.ResidIn, X.ResidOut
     n_s = 1500
     blk = []
     for i in range(n_s):
