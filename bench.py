@@ -363,6 +363,7 @@ def run_ours(args):
     #     lets copies of one frame overlap the search of another.  The headline e2e.value is (b); (a) is reported beside it.
     import threading
     T = max(1, args.e2e_threads)
+    e2e_blocking = args.e2e_blocking if args.e2e_blocking >= 0 else int(T * world > (os.cpu_count() or 1))
     lanes = []
     for t in range(T):
         c = ctx if t == 0 else pkg.Context(local)
@@ -370,6 +371,8 @@ def run_ours(args):
         if t:
             c.set_stream(st.cuda_stream)
             c.set_cost_mv(QP)
+            if e2e_blocking:
+                c.set_blocking_wait(1)
         lanes.append({"ctx": c, "stream": st, "fe": c.frame(W, H, 0), "fr": c.frame(W, H, 0),
                       "res": torch.zeros(n_jobs * pkg.ME_RESULT.itemsize, dtype=torch.uint8).pin_memory()})
     L = pkg.lib()
@@ -455,6 +458,7 @@ def run_ours(args):
                        "l2": "inputs cycle through a %d-pair ring of padded planes (%.0f MB) > 126 MB L2" % (RING_PAIRS, n_frames * g.stride * (g.lines + 64) / 1e6)},
             "e2e": {"value": cands_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "frames_in_flight": T,
+                    "host_wait": "blocking-sync event" if e2e_blocking else "spin",
                     "serial": {"value": cands / (e2e_serial_ms * 1e-3) / 1e9, "ms_per_step": e2e_serial_ms / args.steps,
                                "note": "one host thread, each call waits for its results before the next picture is sent (this rank)"}},
             "gpu_launches": int(launches),
@@ -746,6 +750,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rows", action="store_true", help="per-row device time vs the reference's C on one core (1080p); one JSON line")
+    ap.add_argument("--e2e-blocking", type=int, default=-1, help="frame threads wait for results on a blocking-sync event (sleep) instead of spinning; "
+                    "-1 = automatic: when the ranks' frame threads outnumber the host cores")
     ap.add_argument("--e2e-threads", type=int, default=8, help="frames in flight (host threads, one context each) in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

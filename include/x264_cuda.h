@@ -41,6 +41,9 @@ X264_CUDA_API const char *x264_cuda_error(const x264_cuda_t *ctx); /* ctx may be
 X264_CUDA_API int x264_cuda_set_stream(x264_cuda_t *ctx, void *cuda_stream);
 X264_CUDA_API void *x264_cuda_get_stream(x264_cuda_t *ctx);
 X264_CUDA_API int x264_cuda_synchronize(x264_cuda_t *ctx);
+/* how the host thread waits for results inside the host-array entry points: 0 (default) spins in cudaStreamSynchronize — lowest latency;
+ * 1 sleeps on a blocking-sync event — for many frame threads (S/encoder/encoder.c:1569-1608) sharing fewer host cores */
+X264_CUDA_API int x264_cuda_set_blocking_wait(x264_cuda_t *ctx, int on);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 X264_CUDA_API long long x264_cuda_launch_count(const x264_cuda_t *ctx);
 X264_CUDA_API int x264_cuda_sm_count(const x264_cuda_t *ctx);

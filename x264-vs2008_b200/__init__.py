@@ -99,6 +99,7 @@ def lib():
         L.x264_cuda_get_stream.argtypes = [vp]
         L.x264_cuda_get_stream.restype = vp
         L.x264_cuda_synchronize.argtypes = [vp]
+        L.x264_cuda_set_blocking_wait.argtypes = [vp, ip]
         L.x264_cuda_launch_count.argtypes = [vp]
         L.x264_cuda_launch_count.restype = C.c_longlong
         L.x264_cuda_sm_count.argtypes = [vp]
@@ -293,6 +294,9 @@ class Context:
 
     def synchronize(self):
         self.check(lib().x264_cuda_synchronize(self.h))
+
+    def set_blocking_wait(self, on):
+        self.check(lib().x264_cuda_set_blocking_wait(self.h, int(on)))
 
     def launches(self):
         return lib().x264_cuda_launch_count(self.h)

@@ -15,6 +15,8 @@ struct x264_cuda_t {
     int sm_count;
     cudaStream_t own_stream;
     cudaStream_t stream;          // the stream every launch goes to
+    int blocking_wait;            // wait for results on a blocking-sync event (the host thread sleeps) instead of spinning in cudaStreamSynchronize
+    cudaEvent_t wait_event;
     long long launches;
     char err[256];
     int16_t *d_cost_mv[52];       // device copies of p_cost_mv (base pointers, 4*4*2048+1 entries)
@@ -65,6 +67,7 @@ int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes);
 // pageable memory goes through the pinned stage at `hs`.  results_out also waits for the stream (the call's completion point).
 int x264_cuda_jobs_in(x264_cuda_t *ctx, void *d, const void *h, void *hs, size_t n);
 int x264_cuda_results_out(x264_cuda_t *ctx, void *h, const void *d, void *hs, size_t n);
+int x264_cuda_wait(x264_cuda_t *ctx);
 int x264_cuda_cost_tables(x264_cuda_t *ctx, const int16_t *const **d_ptrs); // device array of 52 table pointers
 
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return x264_cuda_fail((ctx), #call, e_); } while (0)

@@ -54,6 +54,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
     for (int i = 0; i < 52; i++) cudaFree(ctx->d_cost_mv[i]);
     cudaFree(ctx->d_cost_ptrs);
     cudaFree(ctx->d_qt);
@@ -116,11 +117,30 @@ int x264_cuda_jobs_in(x264_cuda_t *ctx, void *d, const void *h, void *hs, size_t
     CUDA_TRY(ctx, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
+// waits for everything queued on the context's stream: spinning (lowest latency, the default) or, with x264_cuda_set_blocking_wait, on a
+// blocking-sync event so that the host thread sleeps — the right choice when more frame threads than host cores wait at once
+int x264_cuda_wait(x264_cuda_t *ctx)
+{
+    if (!ctx->blocking_wait) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    if (!ctx->wait_event) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->wait_event, cudaEventBlockingSync | cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->wait_event, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->wait_event));
+    return 0;
+}
+extern "C" int x264_cuda_set_blocking_wait(x264_cuda_t *ctx, int on)
+{
+    ctx->blocking_wait = on != 0;
+    return 0;
+}
+
 int x264_cuda_results_out(x264_cuda_t *ctx, void *h, const void *d, void *hs, size_t n)
 {
     const bool direct = is_pinned(h);
     CUDA_TRY(ctx, cudaMemcpyAsync(direct ? h : hs, d, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (x264_cuda_wait(ctx)) return -1;
     if (!direct) memcpy(h, hs, n);
     return 0;
 }
