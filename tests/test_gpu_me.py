@@ -140,3 +140,20 @@ def test_mb_search_matches_oracle_and_block_search(pkg, ctx, port, w, h, me_rang
             if not (int(mj["part_mask"]) >> p) & 1:
                 assert int(res[i]["part"][p]["bcost"]) == -1
     fenc.close(); fref.close()
+
+
+def test_blocking_wait_mode_gives_the_same_results(pkg, ctx, port):
+    """x264_cuda_set_blocking_wait: the host thread sleeps on a blocking-sync event instead of spinning; results are those of the default mode"""
+    g, fenc, fref, pe, pr = _setup(pkg, ctx, port, 352, 288, seed=77)
+    mbjobs = make_mb_jobs(pkg, g, seed=5, n=120, qp=(20, 30))
+    want = ctx.me_search_mb(fenc, fref, 16, mbjobs)
+    ctx.set_blocking_wait(1)
+    try:
+        got = ctx.me_search_mb(fenc, fref, 16, mbjobs)
+        bjobs, _ = mb_jobs_to_block_jobs(pkg, mbjobs)
+        blk = ctx.me_search(fenc, fref, 16, bjobs)
+    finally:
+        ctx.set_blocking_wait(0)
+    assert got.tobytes() == want.tobytes()
+    assert np.array_equal(blk, ctx.me_search(fenc, fref, 16, bjobs))
+    fenc.close(); fref.close()
