@@ -193,6 +193,20 @@ X264_CUDA_API int x264_cuda_sad_grid(x264_cuda_t *ctx, const x264_cuda_frame_t *
                                      const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid);
 X264_CUDA_API int x264_cuda_sad_grid_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
                                          const void *d_jobs, int n_jobs, void *d_grid);
+/* Quadrant grids — the form the live encoder uses (integration/x264_b200_hooks.c).  Every partition SAD is a plain sum of the SADs of
+ * the macroblock's four 8x8 quadrants (PIXEL_SAD_C, S/common/pixel.c:40-56), so only those are written, interleaved per position:
+ *   grid[job][j][i][q] (uint16), q = 0 TL | 1 TR | 2 BL | 3 BR, same window, limits and 0xffff marking as above; part_mask is ignored.
+ * 8 bytes per position instead of 18.  async != 0: the call returns once the work is queued on the context's stream; `jobs` and `grid`
+ * must then be page-locked (x264_cuda_host_alloc) and stay untouched until a fence recorded after the call has been waited for. */
+#define X264_CUDA_GRID_QUAD_BYTES(radius) ((size_t)X264_CUDA_GRID_W(radius) * X264_CUDA_GRID_H(radius) * 4 * sizeof(uint16_t))
+X264_CUDA_API int x264_cuda_sad_grid_quad(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                          const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid, int async);
+X264_CUDA_API int x264_cuda_sad_grid_quad_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                              const void *d_jobs, int n_jobs, void *d_grid);
+/* completion markers for asynchronous calls: record returns a fence covering everything queued on the context so far (NULL on failure);
+ * wait blocks until it has completed and releases it */
+X264_CUDA_API void *x264_cuda_fence_record(x264_cuda_t *ctx);
+X264_CUDA_API int x264_cuda_fence_wait(x264_cuda_t *ctx, void *fence);
 /* Host side, no device involved: the full-pel part of x264_me_search_ref for --me esa on one partition's grid plane
  * (grid_part = grid + (job_index * 9 + part) * GW * GH).  job carries mvp, mvc[], i_mvc, qp limits exactly as for
  * x264_cuda_me_search (bx/by are not used); cost_table = p_cost_mv of the qp (x264_cuda_host_cost_mv).  Returns 0 and fills res

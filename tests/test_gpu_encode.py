@@ -1,0 +1,61 @@
+"""gpu: the performance-mode integration (integration/x264_b200_hooks.c linked with the unmodified reference and the real libx264_cuda.so:
+integration/_build/x264_b200) must write byte-identical bitstreams to the plain reference CLI while the exhaustive search reads device
+grids and deblocking / half-pel planes come from the device (BASELINE.json metric "bit-exact encode")."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_integration_host import _clip, _run, REF  # noqa: E402
+
+B200 = os.path.join(ROOT, "integration", "_build", "x264_b200")
+
+CONFIGS = [
+    ("esa_subme2_cif", 352, 288, 5, "--me esa --merange 16 --subme 2", {}),
+    ("esa_subme1_slack2", 96, 64, 3, "--me esa --merange 8 --subme 1", {"X264_B200_GRID_SLACK": "2"}),
+    ("esa_subme5_chroma_me", 176, 144, 4, "--me esa --merange 12 --subme 5 --8x8dct", {}),
+    ("esa_subme7_rd_refs", 176, 144, 5, "--me esa --merange 8 --subme 7 --8x8dct --ref 3 --mixed-refs", {}),
+    ("esa_b_frames", 176, 144, 7, "--me esa --merange 8 --subme 4 --bframes 2 --b-adapt 2 --weightb --ref 2", {}),
+    ("esa_p4x4", 64, 48, 3, "--me esa --merange 8 --subme 2 --partitions all", {}),
+    ("esa_nodeblock", 96, 64, 3, "--me esa --merange 8 --subme 2 --no-deblock", {}),
+    ("esa_cavlc_deblock_offsets", 96, 64, 3, "--me esa --merange 8 --subme 3 --no-cabac --8x8dct --deblock 2:-1", {}),
+    ("esa_crf_aq", 176, 144, 5, "--crf 24 --me esa --merange 8 --subme 6 --bframes 1", {}),
+    ("esa_odd_size", 100, 60, 3, "--me esa --merange 16 --subme 2", {}),
+    ("esa_merange32", 176, 144, 3, "--me esa --merange 32 --subme 2", {}),
+    ("hex_frame_end_only", 176, 144, 4, "--me hex --subme 5 --bframes 1", {}),
+    ("tesa_left_to_reference", 64, 48, 3, "--me tesa --merange 8 --subme 4", {}),
+    ("esa_1080p", 1920, 1080, 3, "--me esa --merange 16 --subme 2", {}),                                   # BASELINE config 2, end to end
+    ("esa_1080p_subme7_8x8dct", 1920, 1080, 2, "--me esa --merange 16 --subme 7 --8x8dct", {}),            # BASELINE config 3
+]
+
+
+@pytest.mark.parametrize("tag,w,h,n,opts,env", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_encode_bitstream_identical(tmp_path, tag, w, h, n, opts, env):
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("oracle/_ref/x264 or integration/_build/x264_b200 not present (they are built where the reference sources exist)")
+    src = str(tmp_path / "in.yuv")
+    _clip(w, h, n, src)
+    a, b = str(tmp_path / "ref.264"), str(tmp_path / "b200.264")
+    r0 = _run(REF, opts, src, a, w, h)
+    assert r0.returncode == 0, r0.stderr[-2000:]
+    e = {"X264_B200_VERBOSE": "1"}
+    e.update(env)
+    r1 = _run(B200, opts, src, b, w, h, e)
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    assert open(a, "rb").read() == open(b, "rb").read(), "bitstreams differ\n" + r1.stderr[-1500:]
+    stat = lambda s: [l for l in s.splitlines() if re.search(r"PSNR Mean|SSIM Mean|x264 \[info\]: slice", l)]
+    assert stat(r0.stderr) == stat(r1.stderr)
+    m = re.search(r"x264_b200: (\d+) ESA searches read device grids", r1.stderr)
+    assert m, r1.stderr[-1500:]
+    if "--me esa" in opts:
+        assert int(m.group(1)) > 0
+        assert "0 searches left to the reference" in r1.stderr
+    k = re.search(r"(\d+) end-of-frame device passes; (\d+) kernel launches", r1.stderr)
+    assert k and int(k.group(1)) > 0 and int(k.group(2)) > 0
+    print(tag, r1.stderr.strip().splitlines()[-2:])

@@ -31,6 +31,9 @@ struct x264_cuda_t {
     void *d_scratch; size_t d_scratch_size; // kernel-private scratch (TESA candidate lists)
     void *d_stage; size_t d_stage_size;
     void *h_stage; size_t h_stage_size; // pinned
+    // asynchronous grid calls: device ring the per-call job copies and grids are carved from, and a pool of fence events
+    uint8_t *d_ring; size_t ring_size, ring_pos;
+    cudaEvent_t fence_pool[256]; int n_fence_pool;
 };
 
 struct QuantTables {
@@ -68,6 +71,7 @@ int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes);
 int x264_cuda_jobs_in(x264_cuda_t *ctx, void *d, const void *h, void *hs, size_t n);
 int x264_cuda_results_out(x264_cuda_t *ctx, void *h, const void *d, void *hs, size_t n);
 int x264_cuda_wait(x264_cuda_t *ctx);
+void *x264_cuda_grid_ring(x264_cuda_t *ctx, size_t bytes); // slice of the device ring for one asynchronous call (nullptr on failure)
 int x264_cuda_cost_tables(x264_cuda_t *ctx, const int16_t *const **d_ptrs); // device array of 52 table pointers
 
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return x264_cuda_fail((ctx), #call, e_); } while (0)

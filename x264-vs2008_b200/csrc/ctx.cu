@@ -64,6 +64,8 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_deblock_recs);
     cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums);
     cudaFreeHost(ctx->h_stage);
+    cudaFree(ctx->d_ring);
+    for (int i = 0; i < ctx->n_fence_pool; i++) cudaEventDestroy(ctx->fence_pool[i]);
     cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
@@ -102,6 +104,49 @@ int x264_cuda_stage(x264_cuda_t *ctx, size_t dev_bytes, size_t host_bytes)
         CUDA_TRY(ctx, cudaMallocHost(&ctx->h_stage, sz));
         ctx->h_stage_size = sz;
     }
+    return 0;
+}
+
+// Device memory for calls that return before their work is done: slices are handed out round-robin from one ring; when the ring wraps,
+// the stream is drained first, so a slice is never reused while an earlier call on this context may still be using it.
+void *x264_cuda_grid_ring(x264_cuda_t *ctx, size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes * 4 > ctx->ring_size) {
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+        cudaFree(ctx->d_ring);
+        ctx->d_ring = nullptr; ctx->ring_size = ctx->ring_pos = 0;
+        const size_t sz = bytes * 4 > ((size_t)64 << 20) ? bytes * 4 : ((size_t)64 << 20);
+        cudaError_t e = cudaMalloc(&ctx->d_ring, sz);
+        if (e != cudaSuccess) { x264_cuda_fail(ctx, "grid ring allocation", e); return nullptr; }
+        ctx->ring_size = sz;
+    }
+    if (ctx->ring_pos + bytes > ctx->ring_size) {
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+        ctx->ring_pos = 0;
+    }
+    void *p = ctx->d_ring + ctx->ring_pos;
+    ctx->ring_pos += bytes;
+    return p;
+}
+
+// Fences: completion markers on the context's stream for the asynchronous entry points.
+extern "C" void *x264_cuda_fence_record(x264_cuda_t *ctx)
+{
+    x264_cuda_enter(ctx);
+    cudaEvent_t ev;
+    if (ctx->n_fence_pool > 0) ev = ctx->fence_pool[--ctx->n_fence_pool];
+    else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { x264_cuda_fail(ctx, "cudaEventCreate", cudaGetLastError()); return nullptr; }
+    if (cudaEventRecord(ev, ctx->stream) != cudaSuccess) { x264_cuda_fail(ctx, "cudaEventRecord", cudaGetLastError()); return nullptr; }
+    return (void *)ev;
+}
+extern "C" int x264_cuda_fence_wait(x264_cuda_t *ctx, void *fence)
+{
+    x264_cuda_enter(ctx);
+    if (!fence) return 0;
+    cudaEvent_t ev = (cudaEvent_t)fence;
+    CUDA_TRY(ctx, cudaEventSynchronize(ev));
+    if (ctx->n_fence_pool < 256) ctx->fence_pool[ctx->n_fence_pool++] = ev; else cudaEventDestroy(ev);
     return 0;
 }
 

@@ -23,6 +23,11 @@ __device__ __forceinline__ void grid_load_row16(uint32_t (&dst)[4], const uint8_
     for (int i = 0; i < 4; i++) dst[i] = __funnelshift_r(w[i], w[i + 1], sh);
 }
 
+// QUAD = false: nine partition planes per job, grid[job][part][GH][GW].
+// QUAD = true : the four 8x8 quadrant SADs (TL, TR, BL, BR) interleaved per position, grid[job][GH][GW][4] — every partition SAD is a
+//               sum of these (PIXEL_SAD_C is a plain sum, S/common/pixel.c:40-56), 8 B instead of 18 B per position and one 8-byte
+//               store per lane (a warp row = 256 contiguous bytes).
+template <bool QUAD>
 __global__ void __launch_bounds__(128, 3)
 sad_grid_kernel(GridGeo geo, const x264_cuda_grid_job_t *__restrict__ jobs, int n_jobs, int radius, uint16_t *__restrict__ grid)
 {
@@ -37,7 +42,7 @@ sad_grid_kernel(GridGeo geo, const x264_cuda_grid_job_t *__restrict__ jobs, int 
     for (int i = lane; i < 64; i += 32) s_F[wid][i >> 2][i & 3] = __ldg((const uint32_t *)(fe + (size_t)(i >> 2) * stride) + (i & 3));
     __syncwarp();
     const uint4 *F4 = (const uint4 *)&s_F[wid][0][0];
-    uint16_t *out = grid + (size_t)jb * 9 * GH * GW;
+    uint16_t *out = grid + (size_t)jb * (QUAD ? 4 : 9) * GH * GW;
     const size_t pstride = (size_t)GH * GW;
     const int ux0 = job.cx - radius, uy0 = job.cy - radius;
     for (int c0 = 0; c0 < GW; c0 += 32) {
@@ -81,6 +86,11 @@ sad_grid_kernel(GridGeo geo, const x264_cuda_grid_job_t *__restrict__ jobs, int 
                 const int row = rbeg + r;
                 if (col_ok && row < GH) {
                     const bool ok = x_ok && r >= ylo && r <= yhi;
+                    if (QUAD) {
+                        uint2 v2 = ok ? make_uint2(tl | (tr << 16), bl | (br << 16)) : make_uint2(0xffffffffu, 0xffffffffu);
+                        *(uint2 *)(out + ((size_t)row * GW + col) * 4) = v2;
+                        continue;
+                    }
                     const uint32_t top = tl + tr, bot = bl + br, lft = tl + bl, rgt = tr + br, all = top + bot;
                     const uint32_t v[9] = { all, top, bot, lft, rgt, tl, tr, bl, br };
                     uint16_t *o = out + (size_t)row * GW + col;
@@ -94,8 +104,8 @@ sad_grid_kernel(GridGeo geo, const x264_cuda_grid_job_t *__restrict__ jobs, int 
 
 } // namespace
 
-extern "C" int x264_cuda_sad_grid_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius, const void *d_jobs,
-                                      int n_jobs, void *d_grid)
+static int sad_grid_launch(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius, const void *d_jobs,
+                           int n_jobs, void *d_grid, bool quad)
 {
     x264_cuda_enter(ctx);
     if (n_jobs <= 0) return 0;
@@ -104,9 +114,22 @@ extern "C" int x264_cuda_sad_grid_dev(x264_cuda_t *ctx, const x264_cuda_frame_t 
         return -1;
     }
     GridGeo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
-    sad_grid_kernel<<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(geo, (const x264_cuda_grid_job_t *)d_jobs, n_jobs, radius, (uint16_t *)d_grid);
+    if (quad)
+        sad_grid_kernel<true><<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(geo, (const x264_cuda_grid_job_t *)d_jobs, n_jobs, radius, (uint16_t *)d_grid);
+    else
+        sad_grid_kernel<false><<<(n_jobs + 3) / 4, 128, 0, ctx->stream>>>(geo, (const x264_cuda_grid_job_t *)d_jobs, n_jobs, radius, (uint16_t *)d_grid);
     LAUNCH_CHECK(ctx, "sad_grid_kernel");
     return 0;
+}
+extern "C" int x264_cuda_sad_grid_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius, const void *d_jobs,
+                                      int n_jobs, void *d_grid)
+{
+    return sad_grid_launch(ctx, fenc, fref, radius, d_jobs, n_jobs, d_grid, false);
+}
+extern "C" int x264_cuda_sad_grid_quad_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius, const void *d_jobs,
+                                           int n_jobs, void *d_grid)
+{
+    return sad_grid_launch(ctx, fenc, fref, radius, d_jobs, n_jobs, d_grid, true);
 }
 
 extern "C" int x264_cuda_sad_grid(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
@@ -122,5 +145,31 @@ extern "C" int x264_cuda_sad_grid(x264_cuda_t *ctx, const x264_cuda_frame_t *fen
     if (x264_cuda_sad_grid_dev(ctx, fenc, fref, radius, ds, n_jobs, ds + jb_al)) return -1;
     CUDA_TRY(ctx, cudaMemcpyAsync(grid, ds + jb_al, gb, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Quadrant grids through host memory.  `async` != 0: nothing is waited for — jobs must stay valid and `grid` must be page-locked
+// (x264_cuda_host_alloc) until x264_cuda_fence_wait() on a fence recorded after this call returns; the device-side job copy and
+// grid live in a per-call slice of the context's grid ring (x264_cuda_grid_ring), so several calls may be in flight.
+extern "C" int x264_cuda_sad_grid_quad(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                       const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid, int async)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_grid_job_t), jb_al = (jb + 255) & ~(size_t)255;
+    const size_t gb = (size_t)n_jobs * X264_CUDA_GRID_QUAD_BYTES(radius);
+    uint8_t *ds;
+    if (async) {
+        ds = (uint8_t *)x264_cuda_grid_ring(ctx, jb_al + gb);
+        if (!ds) return -1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ds, jobs, jb, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if (x264_cuda_stage(ctx, jb_al + gb, jb_al + 256)) return -1;
+        ds = (uint8_t *)ctx->d_stage;
+        if (x264_cuda_jobs_in(ctx, ds, jobs, ctx->h_stage, jb)) return -1;
+    }
+    if (sad_grid_launch(ctx, fenc, fref, radius, ds, n_jobs, ds + jb_al, true)) return -1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(grid, ds + jb_al, gb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!async) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
