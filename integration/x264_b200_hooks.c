@@ -64,7 +64,7 @@ typedef struct {
 
 static struct {
     int state; /* 0: undecided, 1: on, -1: off (plain reference) */
-    int verbose, me_on, frame_on, check; /* X264_B200_ME=0 / X264_B200_FRAME=0 switch one of the two hook groups off (diagnosis) */
+    int verbose, me_on, frame_on, check, avx2; /* X264_B200_ME=0 / X264_B200_FRAME=0 switch one of the two hook groups off (diagnosis) */
     x264_cuda_t *ctx;
     int radius, flags;
     int mb_w, mb_h;
@@ -131,6 +131,7 @@ static int b200_on(x264_t *h)
     if (h->param.analyse.i_me_method == X264_ME_TESA) /* the reference's own TESA reads the integral image on the host */
         B.flags |= X264_CUDA_FRAME_INTEGRAL | (h->frames.b_have_sub8x8_esa ? X264_CUDA_FRAME_INTEGRAL4 : 0);
     B.me_on = !getenv("X264_B200_ME") || atoi(getenv("X264_B200_ME"));
+    B.avx2 = __builtin_cpu_supports("avx2") && !(getenv("X264_B200_AVX2") && !atoi(getenv("X264_B200_AVX2")));
     B.check = getenv("X264_B200_CHECK") && atoi(getenv("X264_B200_CHECK"));
     B.frame_on = !getenv("X264_B200_FRAME") || atoi(getenv("X264_B200_FRAME"));
     for (int i = 0; i < N_GRIDSETS; i++) B.gs[i].enc_frame = -1;
@@ -164,6 +165,20 @@ static dev_slot_t *slot_take(x264_frame_t *f)
     v->f = f; v->i_frame = f->i_frame; v->i_poc = f->i_poc; v->used = ++B.clock;
     return v;
 }
+/* x264 frames live in a small recycled pool (S/common/frame.c:898-975): page-lock each buffer the first time it is seen, so that the
+ * plane copies are DMA'd straight from / to it (a 2-D copy through pageable memory costs ~10 ms per 1080p frame) */
+static void pin_frame(x264_t *h, x264_frame_t *f)
+{
+    static void *seen[256];
+    static int n_seen;
+    for (int i = 0; i < n_seen; i++) if (seen[i] == f->buffer[0]) return;
+    if (n_seen == 256) return;
+    seen[n_seen++] = f->buffer[0];
+    const size_t luma = (size_t)f->i_stride[0] * (f->i_lines[0] + 2 * PADV), chroma = (size_t)f->i_stride[1] * (f->i_lines[1] + 2 * PADV);
+    x264_cuda_host_register(f->buffer[0], (h->param.analyse.i_subpel_refine ? 4 : 1) * luma); /* failure just leaves the slower pageable path */
+    x264_cuda_host_register(f->buffer[1], chroma);
+    x264_cuda_host_register(f->buffer[2], chroma);
+}
 static void upload_picture(x264_cuda_frame_t *d, x264_frame_t *f, int chroma)
 {
     CK(x264_cuda_frame_upload(B.ctx, d, f->plane[0], f->i_stride[0], f->i_width[0], f->i_lines[0]));
@@ -188,6 +203,7 @@ static x264_cuda_frame_t *source_on_device(x264_t *h)
     x264_frame_t *f = h->fenc;
     if (B.denc && B.enc_f == f && B.enc_frame == f->i_frame) return B.denc;
     if (!B.denc && !(B.denc = x264_cuda_frame_new(B.ctx, f->i_width[0], f->i_lines[0], 0))) die("x264_cuda_frame_new");
+    pin_frame(h, f);
     upload_picture(B.denc, f, 0); /* already padded to the macroblock grid by x264_frame_expand_border_mod16 (encoder.c:1411) */
     B.enc_f = f; B.enc_frame = f->i_frame;
     return B.denc;
@@ -199,6 +215,7 @@ static void frame_end(x264_t *h, x264_frame_t *f)
 {
     const double t0 = now_ms();
     dev_slot_t *s = slot_take(f);
+    pin_frame(h, f);
     upload_picture(s->d, f, 1);
     if (B.deblock_pending) {
         x264_cuda_deblock_params_t p = { h->sh.i_alpha_c0_offset, h->sh.i_beta_offset, h->pps->i_chroma_qp_index_offset, h->sh.i_type == SLICE_TYPE_B,
@@ -374,7 +391,7 @@ static gridset_t *gridset_for(x264_t *h, x264_frame_t *ref, int list)
     const size_t per_mb = X264_CUDA_GRID_QUAD_BYTES(R);
     for (int c = 0; c < g->n_chunks; c++) if (g->fence[c]) { CK(x264_cuda_fence_wait(B.ctx, g->fence[c])); g->fence[c] = NULL; }
     if (!g->grid) {
-        g->grid = x264_cuda_host_alloc(per_mb * n_mb);
+        g->grid = x264_cuda_host_alloc(per_mb * n_mb + 64); /* + room for the last 32-byte load of a window's last row */
         g->jobs = x264_cuda_host_alloc(sizeof(x264_cuda_grid_job_t) * n_mb);
         if (!g->grid || !g->jobs) { fprintf(stderr, "x264_b200: cannot page-lock %zu MB for the candidate grids\n", (per_mb * n_mb) >> 20); exit(3); }
     }
@@ -438,6 +455,43 @@ static void view_of(grid_view_t *v, const gridset_t *g, int mb_xy, uint64_t mask
     v->quad = (const uint64_t *)((const uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(R) * mb_xy);
     v->gx0 = g->jobs[mb_xy].cx - R; v->gy0 = g->jobs[mb_xy].cy - R;
     v->mask = mask;
+}
+
+/* Raster argmin of SAD + x cost + y cost over rows [min_y, max_y] x columns [min_x, min_x + width) of a quadrant grid, strict '<', seeded
+ * with (*bcost, *bmx, *bmy) — the loop of me.c:580-598 without the SAD calls.  xc[i] = vector cost of column min_x + i, padded with a huge
+ * value up to a multiple of 8.  Eight positions per step: the 16-bit quadrant sums are selected by the partition mask, added pairwise
+ * (pmaddwd with ones) and across (phaddd); only when some lane beats the best cost so far are the eight positions revisited in raster
+ * order by the scalar code, so ties resolve exactly as in the reference. */
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void scan_window_avx2(const uint64_t *quad, int gw, int gx0, int gy0, uint64_t mask, const int *xc, const int16_t *cost_y,
+                                                             int min_x, int width, int min_y, int max_y, int *pbcost, int *pbmx, int *pbmy)
+{
+    int bcost = *pbcost, bmx = *pbmx, bmy = *pbmy;
+    const __m256i vm = _mm256_set1_epi64x((long long)mask), ones = _mm256_set1_epi16(1);
+    int xcp[48]; /* x costs in the lane order phaddd leaves the sums in: p0 p1 p4 p5 | p2 p3 p6 p7 */
+    static const int order[8] = { 0, 1, 4, 5, 2, 3, 6, 7 };
+    for (int i = 0; i < width; i += 8)
+        for (int k = 0; k < 8; k++) xcp[i + k] = xc[i + order[k]];
+    for (int my = min_y; my <= max_y; my++) {
+        const int ycost = cost_y[my << 2];
+        if (bcost <= ycost) continue;
+        const uint64_t *row = quad + (my - gy0) * gw + (min_x - gx0);
+        __m256i vb = _mm256_set1_epi32(bcost - ycost);
+        for (int i = 0; i < width; i += 8) {
+            const __m256i a = _mm256_and_si256(_mm256_loadu_si256((const __m256i *)(row + i)), vm);
+            const __m256i b = _mm256_and_si256(_mm256_loadu_si256((const __m256i *)(row + i + 4)), vm);
+            const __m256i sums = _mm256_hadd_epi32(_mm256_madd_epi16(a, ones), _mm256_madd_epi16(b, ones));
+            const __m256i c = _mm256_add_epi32(sums, _mm256_loadu_si256((const __m256i *)(xcp + i)));
+            if (_mm256_movemask_epi8(_mm256_cmpgt_epi32(vb, c))) {
+                for (int k = 0; k < 8 && i + k < width; k++) {
+                    const int cc = QUAD_SUM(row[i + k], mask) + xc[i + k] + ycost;
+                    if (cc < bcost) { bcost = cc; bmx = min_x + i + k; bmy = my; }
+                }
+                vb = _mm256_set1_epi32(bcost - ycost);
+            }
+        }
+    }
+    *pbcost = bcost; *pbmx = bmx; *pbmy = bmy;
 }
 
 /* the sub-pel stage of a search: refine_subpel( h, m, hpel, qpel, p_halfpel_thresh, 0 ) of S/encoder/me.c:680-778, through the
@@ -604,17 +658,22 @@ void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, i
             B.n_relaunch++;
             B.t_relaunch += now_ms() - t0;
         }
-        const int16_t *cmx = m->p_cost_mv - m->mvp[0];
-        for (int my = min_y; my <= max_y; my++) {
-            const int ycost = cost_y[my << 2];
-            if (bcost <= ycost) continue; /* nothing in this row can be strictly better (the reference skips it too, me.c:585-587) */
-            const uint64_t *row = gv.quad + (my - gv.gy0) * gv.gw - gv.gx0;
-            const uint64_t mask = gv.mask;
-            for (int mx = min_x; mx < min_x + width; mx++) {
-                const int c = QUAD_SUM(row[mx], mask) + cmx[mx << 2] + ycost;
-                if (c < bcost) { bcost = c; bmx = mx; bmy = my; }
+        int xc[136 + 8];
+        for (int i = 0; i < width; i++) xc[i] = cost_x[(min_x + i) << 2];
+        for (int i = width; i < ((width + 7) & ~7); i++) xc[i] = COST_MAX;
+        if (B.avx2)
+            scan_window_avx2(gv.quad, gv.gw, gv.gx0, gv.gy0, gv.mask, xc, cost_y, min_x, width, min_y, max_y, &bcost, &bmx, &bmy);
+        else
+            for (int my = min_y; my <= max_y; my++) {
+                const int ycost = cost_y[my << 2];
+                if (bcost <= ycost) continue; /* nothing in this row can be strictly better (the reference skips it too, me.c:585-587) */
+                const uint64_t *row = gv.quad + (my - gv.gy0) * gv.gw + (min_x - gv.gx0);
+                const uint64_t mask = gv.mask;
+                for (int i = 0; i < width; i++) {
+                    const int c = QUAD_SUM(row[i], mask) + xc[i] + ycost;
+                    if (c < bcost) { bcost = c; bmx = min_x + i; bmy = my; }
+                }
             }
-        }
         B.n_search++;
     } else { /* sub-8x8 partition or a range beyond the grid: the device searches this block alone, seeded with the predictor stage */
         x264_cuda_me_job_t j;

@@ -125,3 +125,50 @@ def test_lowres_frame_cost_batch(pkg, ctx, port, size):
     assert [a[0] for a in want] == [b[0] for b in got], (want, got)
     for f in frames:
         f.close()
+
+
+def test_lowres_batch_same_frame_two_distances(pkg, ctx, port):
+    """cost(i-1, i, i) and cost(i-2, i, i) search the SAME frame and list at different distances.  The contract allows
+    them in one batch (different (frame, list, distance) states); their hand-over words must not collide (one set per distance), or the
+    persistent warps spin forever.  Also: a batch that does name the same state twice is refused instead of hanging."""
+    from x264_vs2008_b200 import synth
+    w, h = 352, 288
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=53)
+    n_frames = 3
+    planes = lowres_planes(port, g, clip, n_frames)
+    frames = []
+    for i in range(n_frames):
+        f = ctx.frame(w, h, pkg.FRAME_LOWRES)
+        f.upload(clip.luma(i)); f.expand_border(); f.init_lowres(); f.lookahead_alloc(3)
+        frames.append(f)
+    n = g.mb_width * g.mb_height
+    st = [{"mvs": np.zeros((2, 3, n, 2), np.int16), "costs": np.zeros((2, 3, n), np.int32), "intra": np.zeros(n, np.uint16)} for _ in range(n_frames)]
+
+    def oracle_eval(fe, p0, p1, b, ds, bic):
+        d0, d1 = max(b - p0 - 1, 0), max(p1 - b - 1, 0)
+        s = st[fe]
+        state = {"mvs0": s["mvs"][0, d0], "costs0": s["costs"][0, d0], "mvs1": s["mvs"][1, d1], "costs1": s["costs"][1, d1],
+                 "intra": s["intra"], "ref1_mvs": st[p1]["mvs"][0, max(p1 - p0 - 1, 0)].copy()}
+        o = port.lowres_frame_cost(g, planes[b], planes[p0], planes[p1], p0, p1, b, state, do_search=ds, b_intra_calculated=bic)
+        return (o.score, o.intra_mbs if b == p1 else 0, o.intra_cost_sum if b == p1 else 0)
+
+    evals = [(i, i, i, i, (0, 0), 0) for i in range(n_frames)]
+    for e in evals:
+        oracle_eval(*e)
+    ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in evals])
+    evals = [(2, 1, 2, 2, (1, 0), 1), (2, 0, 2, 2, (1, 0), 1), (1, 0, 1, 1, (1, 0), 1)]
+    want = [oracle_eval(*e) for e in evals]
+    got = ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in evals])
+    assert want == got, (want, got)
+    m = np.zeros((g.mb_height, g.mb_width), bool)
+    m[1:-1, 1:-1] = True
+    m = m.ravel()
+    for d0 in (0, 1):
+        mv, cost, _ = frames[2].lookahead_get(0, d0)
+        assert np.array_equal(mv[m], st[2]["mvs"][0, d0][m]) and np.array_equal(cost[m], st[2]["costs"][0, d0][m]), d0
+    dup = [(2, 1, 2, 2, (1, 0), 1), (2, 1, 2, 2, (1, 0), 1)]
+    with pytest.raises(Exception):
+        ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in dup])
+    for f in frames:
+        f.close()

@@ -113,3 +113,33 @@ def test_esa_replay(pkg, ctx, port, qp):
             n_ok += 1
     assert n_ok > 8 * n_out and n_ok > 400, (n_ok, n_out)
     fenc.close(); fref.close()
+
+
+@pytest.mark.parametrize("size,radius", [((208, 144), 24), ((1920, 1080), 24), ((352, 288), 40)])
+def test_quad_grid_equals_partition_grid(pkg, ctx, port, size, radius):
+    """the quadrant grids the live encoder reads (x264_cuda_sad_grid_quad: TL, TR, BL, BR per position, interleaved) against the
+    nine-plane grids checked above: planes 5..8 are the quadrants themselves and every other partition is a sum of them"""
+    w, h = size
+    g, fenc, fref, pe, pr = _frames(pkg, ctx, port, w, h, 13)
+    rng = np.random.default_rng(radius)
+    n_all = g.mb_width * g.mb_height
+    pick = rng.choice(n_all, min(n_all, 160), replace=False)
+    jobs = np.zeros(len(pick), pkg.GRID_JOB)
+    for k, i in enumerate(pick):
+        mbx, mby = int(i % g.mb_width), int(i // g.mb_width)
+        mn, mx, _, _ = X.mv_limits_fpel(g, mbx, mby)
+        jobs[k]["mb_x"], jobs[k]["mb_y"] = mbx, mby
+        jobs[k]["cx"], jobs[k]["cy"] = int(np.clip(rng.integers(-20, 21), mn[0], mx[0])), int(np.clip(rng.integers(-20, 21), mn[1], mx[1]))
+        jobs[k]["mv_min_fpel"], jobs[k]["mv_max_fpel"] = mn, mx
+        jobs[k]["part_mask"] = 511
+    nine = ctx.sad_grid(fenc, fref, radius, jobs).astype(np.int64)
+    quad = ctx.sad_grid_quad(fenc, fref, radius, jobs).astype(np.int64)
+    invalid = nine[:, 5] == 0xffff
+    assert np.array_equal(invalid, quad[..., 0] == 0xffff) and invalid.any() and not invalid.all()
+    for q in range(4):
+        assert np.array_equal(quad[..., q], nine[:, 5 + q])
+    ok = ~invalid
+    sums = {0: quad.sum(-1), 1: quad[..., 0] + quad[..., 1], 2: quad[..., 2] + quad[..., 3], 3: quad[..., 0] + quad[..., 2], 4: quad[..., 1] + quad[..., 3]}
+    for p, v in sums.items():
+        assert np.array_equal(v[ok], nine[:, p][ok]), p
+    fenc.close(); fref.close()

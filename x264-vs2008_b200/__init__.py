@@ -114,6 +114,10 @@ def lib():
         L.x264_cuda_frame_upload_dev.argtypes = [vp, vp, vp, ip, ip, ip]
         L.x264_cuda_frame_upload_chroma.argtypes = [vp, vp, ip, vp, ip, ip, ip]
         L.x264_cuda_set_quant_preset.argtypes = [vp, ip]
+        L.x264_cuda_sad_grid_quad.argtypes = [vp, vp, vp, ip, vp, ip, vp, ip]
+        L.x264_cuda_fence_record.argtypes = [vp]
+        L.x264_cuda_fence_record.restype = vp
+        L.x264_cuda_fence_wait.argtypes = [vp, vp]
         L.x264_cuda_mc_blocks.argtypes = [vp, vp, vp, vp, ip]
         L.x264_cuda_mc_blocks_dev.argtypes = [vp, vp, vp, vp, ip]
         L.x264_cuda_mc_blocks_bi.argtypes = [vp, vp, vp, vp, vp, ip]
@@ -465,6 +469,13 @@ class Context:
         assert jobs.dtype == GRID_JOB
         out = np.zeros((len(jobs), 9, grid_h(radius), grid_w(radius)), np.uint16)
         self.check(lib().x264_cuda_sad_grid(self.h, fenc.h, fref.h, radius, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
+
+    def sad_grid_quad(self, fenc, fref, radius, jobs):
+        """-> uint16 [n_jobs, GH, GW, 4]: SADs of the four 8x8 quadrants (TL, TR, BL, BR) at every integer vector of the window"""
+        assert jobs.dtype == GRID_JOB
+        out = np.zeros((len(jobs), grid_h(radius), grid_w(radius), 4), np.uint16)
+        self.check(lib().x264_cuda_sad_grid_quad(self.h, fenc.h, fref.h, radius, jobs.ctypes.data, len(jobs), out.ctypes.data, 0))
         return out
 
     def me_search_mb_dev(self, fenc, fref, me_range, d_jobs, n, d_results):

@@ -8,6 +8,7 @@
 // shuffles; the selection among candidates is the reference's sequential strict-'<' scan, done uniformly by all lanes.
 // Sub-pel samples follow get_ref (mc.c:181-202): one of the four half-pel planes or the byte average of two.
 #include "pixel_dev.cuh"
+#include <atomic>
 
 namespace {
 
@@ -824,7 +825,7 @@ __global__ void __launch_bounds__(64) lowres_intra_kernel(const uint8_t *__restr
 struct LaArgs {
     const uint8_t *fenc[4], *ref[2][4];
     int stride, W, H;
-    int16_t *mvs[2]; int *costs[2]; const int16_t *ref1_mvs; int *intra; unsigned long long *sync; int n_mb; const int *order; int n_order;
+    int16_t *mvs[2]; int *costs[2]; const int16_t *ref1_mvs; int *intra; unsigned long long *sync[2]; int n_mb; const int *order; int n_order;
     int *ticket, *sums; // sums: score, intra_mbs, intra_cost_sum
     int epoch, b_bidir, b_any_inter, dsf, weight, method, me_range, do_search0, do_search1, mbcmp_satd, fpel_satd;
     const int16_t *tab; // p_cost_mv (qp 12) centre
@@ -941,7 +942,7 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(const LaArgs *__restri
                             const bool inside = small || (nx >= 1 && nx <= a.W - 2 && ny >= 1 && ny <= a.H - 2);
                             if (inside) {
                                 unsigned long long wv;
-                                do wv = ld_relaxed_u64(a.sync + (size_t)l * a.n_mb + nx + ny * a.W); while ((uint32_t)(wv >> 32) != (uint32_t)a.epoch);
+                                do wv = ld_relaxed_u64(a.sync[l] + nx + ny * a.W); while ((uint32_t)(wv >> 32) != (uint32_t)a.epoch);
                                 v = (uint32_t)wv;
                             } else
                                 v = *(const uint32_t *)(a.mvs[l] + 2 * (nx + ny * a.W));
@@ -984,7 +985,7 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(const LaArgs *__restri
                     mvx[l] = fin.mv[0]; mvy[l] = fin.mv[1];
                     if (lane == 0) {
                         const uint32_t mvw = ((uint32_t)(uint16_t)fin.mv[0]) | ((uint32_t)(uint16_t)fin.mv[1] << 16);
-                        st_relaxed_u64(a.sync + (size_t)l * a.n_mb + xy, ((unsigned long long)(uint32_t)a.epoch << 32) | mvw); // hand-over
+                        st_relaxed_u64(a.sync[l] + xy, ((unsigned long long)(uint32_t)a.epoch << 32) | mvw); // hand-over
                         *(uint32_t *)(a.mvs[l] + 2 * xy) = mvw; // the frame's persistent lowres_mvs
                         a.costs[l][xy] = cost;
                     }
@@ -1010,6 +1011,8 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(const LaArgs *__restri
 
 } // namespace
 
+static std::atomic<int> g_la_epoch{0};
+
 extern "C" int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame_t *f, int n_dist)
 {
     x264_cuda_enter(ctx);
@@ -1023,11 +1026,12 @@ extern "C" int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame
     CUDA_TRY(ctx, cudaMalloc(&f->la_mvs, 2 * n_dist * n_mb * 4));
     CUDA_TRY(ctx, cudaMalloc(&f->la_costs, 2 * n_dist * n_mb * 4));
     CUDA_TRY(ctx, cudaMalloc(&f->la_intra, n_mb * 4));
-    CUDA_TRY(ctx, cudaMalloc(&f->la_done, 2 * n_mb * 8)); // hand-over words, per list (see lowres_cost_kernel)
+    CUDA_TRY(ctx, cudaMalloc(&f->la_done, 2 * n_dist * n_mb * 8)); // hand-over words, one set per (list, distance) like the vectors they carry:
+    // two evaluations of one batch that search the same frame and list at different distances never share a word (see lowres_cost_kernel)
     CUDA_TRY(ctx, cudaMemsetAsync(f->la_mvs, 0, 2 * n_dist * n_mb * 4, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(f->la_costs, 0, 2 * n_dist * n_mb * 4, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(f->la_intra, 0, n_mb * 4, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(f->la_done, 0, 2 * n_mb * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->la_done, 0, 2 * n_dist * n_mb * 8, ctx->stream));
     f->la_dist = n_dist;
     return 0;
 }
@@ -1152,9 +1156,12 @@ extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, 
         a.mvs[0] = fenc->la_mvs + 2 * ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb; a.costs[0] = fenc->la_costs + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
         a.mvs[1] = fenc->la_mvs + 2 * ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb; a.costs[1] = fenc->la_costs + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
         a.ref1_mvs = b_bidir ? fref1->la_mvs + 2 * ((size_t)(pm->p1 - pm->p0 - 1)) * n_mb : nullptr;
-        a.intra = fenc->la_intra; a.sync = (unsigned long long *)fenc->la_done; a.n_mb = (int)n_mb; a.order = ctx->d_la_order; a.n_order = ctx->la_n;
+        a.intra = fenc->la_intra; a.n_mb = (int)n_mb;
+        a.sync[0] = (unsigned long long *)fenc->la_done + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
+        a.sync[1] = (unsigned long long *)fenc->la_done + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
+        a.order = ctx->d_la_order; a.n_order = ctx->la_n;
         a.ticket = d_ticket; a.sums = ctx->d_la_sums + 8 * e;
-        a.epoch = ++ctx->la_epoch; a.b_bidir = b_bidir; a.b_any_inter = any;
+        a.epoch = ++g_la_epoch; // process-wide: the hand-over words live in the FRAME, which several contexts may evaluate in turn a.b_bidir = b_bidir; a.b_any_inter = any;
         a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
         a.weight = (pm->flags & X264_CUDA_LOWRES_WEIGHTED_BIPRED) ? 64 - (a.dsf >> 2) : 32;                          // slicetype.c:57
         a.method = pm->me_method < 1 ? X264_CUDA_ME_METHOD_DIA : X264_CUDA_ME_METHOD_HEX;                            // min(HEX, me), slicetype.c:38
@@ -1162,6 +1169,20 @@ extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, 
         a.mbcmp_satd = !!(pm->flags & X264_CUDA_ME_MBCMP_SATD); a.fpel_satd = !!(pm->flags & X264_CUDA_ME_FPEL_SATD);
         a.tab = ctx->d_cost_mv[12] + 2 * 4 * 2048;
     }
+    // the contract of the batch (x264_cuda.h): no two evaluations may search the same (frame, list, distance) state — they would race on
+    // the vectors and on the hand-over words, and a waiter could spin on an epoch that never comes.  Refuse instead of hanging.
+    for (int e = 0; e < n_evals; e++)
+        for (int f = 0; f < e; f++)
+            for (int l = 0; l < 2; l++)
+                for (int k = 0; k < 2; k++) {
+                    const bool se = (l ? h_evals[e].do_search1 && h_evals[e].b_bidir : h_evals[e].do_search0) && h_evals[e].b_any_inter;
+                    const bool sf = (k ? h_evals[f].do_search1 && h_evals[f].b_bidir : h_evals[f].do_search0) && h_evals[f].b_any_inter;
+                    if (se && sf && h_evals[e].mvs[l] == h_evals[f].mvs[k]) {
+                        snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost_batch: evaluations %d and %d search the same (frame, list, distance)", f, e);
+                        free(h_evals);
+                        return -1;
+                    }
+                }
     cudaError_t ce = cudaMemcpyAsync(d_evals, h_evals, (size_t)n_evals * sizeof(LaArgs), cudaMemcpyHostToDevice, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream); // h_evals is pageable and freed below
     free(h_evals);
