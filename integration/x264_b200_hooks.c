@@ -142,6 +142,21 @@ static int b200_on(x264_t *h)
     return 1;
 }
 
+/* GOP-sharded encoding (x264-vs2008_b200/gop_shard.py): a worker that encodes closed GOP k of a longer stream must number its IDR
+ * pictures from k, as the single-process encoder would (S/encoder/encoder.c:1107-1110), and start its count of coded frames where that
+ * encoder would be (h->i_frame selects the signature bit the CABAC flush embeds in every slice, S/common/cabac.c:917); everything else
+ * restarts at an IDR anyway. */
+x264_t *x264_encoder_open_c(x264_param_t *param);
+x264_t *x264_encoder_open(x264_param_t *param)
+{
+    x264_t *h = x264_encoder_open_c(param);
+    const char *e = getenv("X264_B200_IDR_PIC_ID");
+    if (h && e) h->i_idr_pic_id = atoi(e) & 0xffff;
+    e = getenv("X264_B200_CODED_FRAMES");
+    if (h && e) h->i_frame = atoi(e);
+    return h;
+}
+
 /* ------------------------------------------------------------------------------------------------------------------------------
  * device mirrors of frames */
 static dev_slot_t *slot_find(x264_frame_t *f)

@@ -59,3 +59,22 @@ def test_encode_bitstream_identical(tmp_path, tag, w, h, n, opts, env):
     k = re.search(r"(\d+) end-of-frame device passes; (\d+) kernel launches", r1.stderr)
     assert k and int(k.group(1)) > 0 and int(k.group(2)) > 0
     print(tag, r1.stderr.strip().splitlines()[-2:])
+
+
+def test_gop_sharded_on_device(tmp_path):
+    """GOP-sharded encoding with the real library: four worker processes share cuda:0, the stitched stream equals ONE process of the
+    unmodified reference (x264-vs2008_b200/gop_shard.py; the two-rank gloo variant runs on the CPU in tests/test_gop_shard.py)"""
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("builds not present")
+    from test_integration_host import _load_pkg
+    _load_pkg()
+    from x264_vs2008_b200 import gop_shard as G
+    w, h, n, k = 352, 288, 22, 6
+    opts = "--qp 26 --me esa --merange 16 --subme 5 --bframes 2 --b-adapt 2 --ref 2"
+    src = str(tmp_path / "in.yuv")
+    _clip(w, h, n, src)
+    single = str(tmp_path / "single.264")
+    r = _run(REF, opts + " " + " ".join(G.gop_options(k)), src, single, w, h)
+    assert r.returncode == 0, r.stderr[-1500:]
+    parts, wall = G.encode_gops(B200, src, w, h, opts.split(), k, G.plan_gops(n, k), str(tmp_path / "shards"), workers=4)
+    assert G.stitch(parts) == open(single, "rb").read()
