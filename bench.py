@@ -232,7 +232,119 @@ def run_reference(args):
             "cpu_baseline": {"value": rate / 1e9, "unit": "Gcand/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_encode:
+        enc = encode_leg_reference(max(1, min(args.encode_workers, cores)) * 2 * ENC_KEYINT)
+        enc.pop("stream_1thread", None)
+        line["encode"] = enc
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- encode fps (BASELINE metric, 2nd half)
+ENC_OPTS = "--qp 26 --me esa --merange 16 --subme 2 --no-psnr --no-ssim"
+ENC_KEYINT = 24
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "x264")
+B200_CLI = os.path.join(ROOT, "integration", "_build", "x264_b200")
+
+
+def _enc_clip(seed, n_frames):
+    """seeded synthetic 1080p YUV420 clip on local disk (cached between bench invocations of one round)"""
+    import __graft_entry__ as ge
+    ge.load_pkg()
+    from x264_vs2008_b200 import synth
+    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "x264b200_bench_%dx%d_s%d_n%d.yuv" % (W, H, seed, n_frames))
+    if not (os.path.exists(path) and os.path.getsize(path) == n_frames * W * H * 3 // 2):
+        clip = synth.Clip(W, H, seed=seed, motion=(3, 2))   # (3,2) px/frame: the texture field wraps only after 32 frames
+        tmp = path + ".%d.tmp" % os.getpid()
+        with open(tmp, "wb") as f:
+            for i in range(n_frames):
+                for p in clip.yuv420(i % 32):
+                    f.write(np.ascontiguousarray(p).tobytes())
+        os.replace(tmp, path)
+    return path
+
+
+def _cli(exe, opts, src, out, threads=1, env=None):
+    import re
+    cmd = [exe, "--no-asm", "--threads", str(threads)] + opts + ["-o", out, src, "%dx%d" % (W, H)]
+    e = dict(os.environ)
+    e.update(env or {})
+    t = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True, env=e)
+    wall = time.perf_counter() - t
+    if r.returncode != 0:
+        raise SystemExit("bench.py: %s failed: %s" % (exe, r.stderr[-800:]))
+    m = re.search(r"encoded (\d+) frames", r.stderr)
+    return int(m.group(1)) if m else 0, wall, r.stderr
+
+
+def encode_leg_reference(n_frames, seed=1):
+    """the unmodified reference CLI (C only: no yasm/nasm in this image, so its assembly back-end cannot be built) on the host cores"""
+    import __graft_entry__ as ge
+    ge.load_pkg()
+    from x264_vs2008_b200 import gop_shard as G
+    if not os.path.exists(REF_CLI):
+        return {"unavailable": "oracle/_ref/x264 not built"}
+    src = _enc_clip(seed, n_frames)
+    opts = ENC_OPTS.split() + G.gop_options(ENC_KEYINT)
+    cores = os.cpu_count() or 1
+    tmp = os.environ.get("TMPDIR", "/tmp")
+    n1, w1, _ = _cli(REF_CLI, opts, src, os.path.join(tmp, "bench_ref1.264"), 1)
+    nt, wt, _ = _cli(REF_CLI, opts, src, os.path.join(tmp, "bench_reft.264"), cores)
+    # the reference's other way to use all cores bit-exactly: one --threads 1 process per run of closed GOPs (same sharding as ours)
+    runs = G.split_runs(G.plan_gops(n_frames, ENC_KEYINT), cores)
+    _, wg = G.encode_gops(REF_CLI, src, W, H, ENC_OPTS.split(), ENC_KEYINT, runs, os.path.join(tmp, "bench_refshards"), workers=cores)
+    return {"build": "reference C, --no-asm (asm baseline unavailable: no yasm/nasm in the image)", "cores": cores, "frames": n_frames,
+            "fps_1thread": n1 / w1, "fps_threads": nt / wt, "threads": cores, "fps_gop_sharded": n_frames / wg, "gop_sharded_processes": len(runs),
+            "stream_1thread": os.path.join(tmp, "bench_ref1.264")}
+
+
+def encode_leg_ours(local, world, rank, dist, workers):
+    """bit-exact encode fps of the performance-mode build (integration/_build/x264_b200): the unmodified reference encoder whose exhaustive
+    search reads device SAD grids and whose deblocking / half-pel planes come from the device.  One process, and `workers` GOP-sharded
+    processes per GPU (x264-vs2008_b200/gop_shard.py); the stitched stream must equal the reference's --threads 1 stream byte for byte."""
+    import re
+    import __graft_entry__ as ge
+    ge.load_pkg()
+    from x264_vs2008_b200 import gop_shard as G
+    if not (os.path.exists(B200_CLI) and os.path.exists(REF_CLI)):
+        return {"unavailable": "integration/_build/x264_b200 or oracle/_ref/x264 not built"}
+    n_frames = workers * 2 * ENC_KEYINT
+    src = _enc_clip(1 + rank, n_frames)
+    tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), "bench_b200_r%d" % rank)
+    os.makedirs(tmp, exist_ok=True)
+    env = {"X264_B200_DEVICE": str(local), "X264_B200_VERBOSE": "1"}
+    opts = ENC_OPTS.split() + G.gop_options(ENC_KEYINT)
+    # (a) one process, the first 2 GOPs
+    n1, w1, err1 = _cli(B200_CLI, opts + ["--frames", str(2 * ENC_KEYINT)], src, os.path.join(tmp, "single.264"), 1, env)
+    m = re.search(r"open ([0-9.]+) ms", err1)
+    open_ms = float(m.group(1)) if m else 0.0
+    k = re.search(r"(\d+) kernel launches", err1)
+    # (b) `workers` processes on this GPU, each a run of consecutive closed GOPs
+    gops = G.plan_gops(n_frames, ENC_KEYINT)
+    if dist is not None:
+        dist.barrier()
+    parts, wall = G.encode_gops(B200_CLI, src, W, H, ENC_OPTS.split(), ENC_KEYINT, G.split_runs(gops, workers), tmp, workers=workers, env=env)
+    stream = G.stitch(parts)
+    # parity: the reference's own single-process stream of the same clip (rank 0 only: one reference run is enough for the claim)
+    identical = None
+    ref = None
+    if rank == 0:
+        ref = encode_leg_reference(n_frames, seed=1)
+        identical = stream == open(ref.pop("stream_1thread"), "rb").read()
+        if not identical:
+            raise SystemExit("bench.py: GOP-sharded device encode differs from the reference's --threads 1 stream")
+    times, counts = [wall, w1], [n_frames, n1]
+    from x264_vs2008_b200 import shard
+    (wall_max, w1_max), (frames_all, n1_all) = shard.reduce_job(dist, "cuda", times, counts)
+    if rank != 0:
+        return None
+    return {"config": "1080p %s --keyint %d, %d frames per GPU" % (ENC_OPTS, ENC_KEYINT, n_frames),
+            "fps": frames_all / wall_max, "processes_per_gpu": workers, "frames": int(frames_all),
+            "fps_one_process": n1 / w1, "fps_one_process_after_cuda_start": n1 / max(1e-9, w1 - open_ms / 1e3), "cuda_start_ms": open_ms,
+            "kernel_launches_one_process": int(k.group(1)) if k else 0,
+            "identical_to_reference_stream": identical, "reference": ref,
+            "note": "wall-clock of the encoder processes, CUDA context start-up included; the host keeps the sequential macroblock loop, entropy coding "
+                    "and sub-pel refinement (SURVEY 7.3-1: host-bound), the device serves ESA grids, deblocking and half-pel planes"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -434,6 +546,9 @@ def run_ours(args):
 
     # ---- max over ranks
     (total_ms, e2e_ms), (cands_all, sadops_all) = shard.reduce_job(dist if world > 1 else None, "cuda", [total_ms, e2e_ms], [cands, sadops])
+    enc = None
+    if not args.no_encode:
+        enc = encode_leg_ours(local, world, rank, dist if world > 1 else None, max(1, min(args.encode_workers, (os.cpu_count() or 1) // world)))
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -472,6 +587,8 @@ def run_ours(args):
             "per_block_jobs": {"ms_per_step": blockjob_ms, "value": (cands / args.steps) / (blockjob_ms * 1e-3) / 1e9, "unit": "Gcand/s",
                                "note": "same 73440 searches as independent x264_cuda_me_search jobs (no SAD sharing)"},
         }
+        if enc is not None:
+            line["encode"] = enc
         if world == 1 and not args.no_cpu:
             rate, kind, cores, sample, _ = cpu_rate(1, 9 * 120 * 32, 60)  # ~10 s of the reference's C on one core
             line["cpu_baseline"] = {"value": rate / 1e9, "unit": "Gcand/s", "cores": cores, "kind": kind, "sample": sample}
@@ -749,6 +866,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-encode", action="store_true", help="skip the encode-fps leg")
+    ap.add_argument("--encode-workers", type=int, default=4, help="GOP-sharded encoder processes per GPU in the encode-fps leg")
     ap.add_argument("--rows", action="store_true", help="per-row device time vs the reference's C on one core (1080p); one JSON line")
     ap.add_argument("--e2e-blocking", type=int, default=-1, help="frame threads wait for results on a blocking-sync event (sleep) instead of spinning; "
                     "-1 = automatic: when the ranks' frame threads outnumber the host cores")

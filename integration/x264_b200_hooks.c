@@ -45,6 +45,7 @@ extern int16_t *g_cost_mv[52]; /* S/encoder/analyse.c:179 */
 #define N_SLOTS 20 /* device mirrors of reconstructed frames: i_frame_reference <= 16 plus the frames in flight */
 #define N_GRIDSETS 4 /* (source frame, reference frame) pairs with grids in host memory */
 #define MAX_CHUNKS 512
+#define N_EXTRA 8
 
 typedef struct {
     x264_frame_t *f; int i_frame, i_poc; /* which host frame content this mirrors */
@@ -58,8 +59,14 @@ typedef struct {
     long long used;
     uint16_t *grid;                            /* page-locked: n_mb * GW * GH * 4 */
     x264_cuda_grid_job_t *jobs;                /* page-locked: n_mb (centre + limits of every macroblock) */
-    void *fence[MAX_CHUNKS];                   /* completion of each chunk of macroblock rows */
-    int n_chunks, rows_per_chunk;
+    void *fence[MAX_CHUNKS];                   /* completion of each chunk of macroblock rows (NULL: not in flight) */
+    uint8_t issued[MAX_CHUNKS];
+    int n_chunks, rows_per_chunk, list;
+    /* grids recomputed around an exact centre (the guess was off): a few of them are kept beside the frame's grids, because the partitions
+     * of a macroblock on a motion boundary alternate between two centres */
+    uint16_t *extra_grid;                      /* page-locked: N_EXTRA grids */
+    x264_cuda_grid_job_t *extra_job;           /* page-locked: the job (macroblock, centre) each one was computed for */
+    long long extra_used[N_EXTRA];
 } gridset_t;
 
 static struct {
@@ -76,7 +83,7 @@ static struct {
     x264_frame_t *end_done; int end_done_frame; /* fdec whose end-of-frame pass has run */
     int cost_uploaded[52];
     /* statistics */
-    long long n_search, n_relaunch, n_percall, n_outside_pred, n_gridsets, n_frame_end, n_left_to_c;
+    long long n_search, n_extra_hit, n_relaunch, n_percall, n_outside_pred, n_gridsets, n_frame_end, n_left_to_c;
     double t_grid_issue, t_grid_wait, t_frame_end, t_relaunch, t_open;
     /* deferred PSNR / SSIM slabs (see x264_pixel_ssd_wxh below) */
     struct { int y0, h; } ssim_slab[256]; int n_ssim_slab;
@@ -98,9 +105,9 @@ static void die(const char *what)
 static void report(void)
 {
     if (!B.verbose) return;
-    fprintf(stderr, "x264_b200: %lld ESA searches read device grids (%lld macroblock grids recomputed around the exact centre, %lld predictor SADs outside a grid "
+    fprintf(stderr, "x264_b200: %lld ESA searches read device grids (%lld macroblock grids recomputed around the exact centre and %lld reused, %lld predictor SADs outside a grid "
             "taken from the table entry, %lld sub-8x8 searches as one-job device calls, %lld searches left to the reference), %lld frame grid sets, "
-            "%lld end-of-frame device passes; %lld kernel launches\n", B.n_search, B.n_relaunch, B.n_outside_pred, B.n_percall, B.n_left_to_c, B.n_gridsets,
+            "%lld end-of-frame device passes; %lld kernel launches\n", B.n_search, B.n_relaunch, B.n_extra_hit, B.n_outside_pred, B.n_percall, B.n_left_to_c, B.n_gridsets,
             B.n_frame_end, B.ctx ? x264_cuda_launch_count(B.ctx) : 0);
     fprintf(stderr, "x264_b200: host time in device calls: open %.1f ms, grid issue %.1f ms, grid wait %.1f ms, recompute %.1f ms, end of frame %.1f ms\n", B.t_open,
             B.t_grid_issue, B.t_grid_wait, B.t_relaunch, B.t_frame_end);
@@ -111,7 +118,7 @@ static int b200_on(x264_t *h)
 {
     if (B.state) return B.state > 0;
     const char *e = getenv("X264_B200");
-    B.verbose = getenv("X264_B200_VERBOSE") && atoi(getenv("X264_B200_VERBOSE"));
+    B.verbose = getenv("X264_B200_VERBOSE") ? atoi(getenv("X264_B200_VERBOSE")) : 0;
     B.state = -1;
     if (e && !atoi(e)) return 0;
     if (h->param.i_threads > 1 || h->param.b_interlaced) {
@@ -389,6 +396,31 @@ static void guess_centres(x264_t *h, x264_frame_t *ref, int list, gridset_t *g)
     (void)n_mb;
 }
 
+/* Launch chunk c of a grid set.  src_row >= 0: macroblock row src_row of the CURRENT frame is finished — where its macroblocks point into
+ * this reference picture, their vectors replace the guessed centres of the macroblocks below them (h->mb.mv / h->mb.ref are the frame-wide
+ * arrays x264_macroblock_cache_save fills, S/common/macroblock.c:1219-1372). */
+static void issue_chunk(x264_t *h, gridset_t *g, int c, int src_row)
+{
+    const int n_mb = B.mb_w * B.mb_h, mb0 = c * g->rows_per_chunk * B.mb_w, mb1 = X264_MIN(n_mb, mb0 + g->rows_per_chunk * B.mb_w);
+    if (src_row >= 0 && h->mb.mv[g->list] && h->mb.ref[g->list]) {
+        x264_frame_t **fref = g->list ? h->fref1 : h->fref0;
+        const int n_ref = g->list ? h->i_ref1 : h->i_ref0;
+        for (int i = mb0; i < mb1; i++) {
+            const int x = i % B.mb_w;
+            const int r = h->mb.ref[g->list][(2 * src_row + 1) * 2 * B.mb_w + 2 * x];   /* bottom-left 8x8 block of the macroblock above */
+            if (r < 0 || r >= n_ref || fref[r] != g->ref) continue;
+            const int16_t *mv = h->mb.mv[g->list][(4 * src_row + 3) * 4 * B.mb_w + 4 * x];
+            x264_cuda_grid_job_t *j = &g->jobs[i];
+            j->cx = x264_clip3((mv[0] + 2) >> 2, j->mv_min_fpel[0], j->mv_max_fpel[0]);
+            j->cy = x264_clip3((mv[1] + 2) >> 2, j->mv_min_fpel[1], j->mv_max_fpel[1]);
+        }
+    }
+    CK(x264_cuda_sad_grid_quad(B.ctx, source_on_device(h), slot_for_ref(g->ref)->d, B.radius, g->jobs + mb0, mb1 - mb0,
+                               (uint16_t *)((uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(B.radius) * mb0), 1));
+    if (!(g->fence[c] = x264_cuda_fence_record(B.ctx))) die("x264_cuda_fence_record");
+    g->issued[c] = 1;
+}
+
 static gridset_t *gridset_for(x264_t *h, x264_frame_t *ref, int list)
 {
     gridset_t *v = &B.gs[0];
@@ -408,32 +440,41 @@ static gridset_t *gridset_for(x264_t *h, x264_frame_t *ref, int list)
     if (!g->grid) {
         g->grid = x264_cuda_host_alloc(per_mb * n_mb + 64); /* + room for the last 32-byte load of a window's last row */
         g->jobs = x264_cuda_host_alloc(sizeof(x264_cuda_grid_job_t) * n_mb);
-        if (!g->grid || !g->jobs) { fprintf(stderr, "x264_b200: cannot page-lock %zu MB for the candidate grids\n", (per_mb * n_mb) >> 20); exit(3); }
+        g->extra_grid = x264_cuda_host_alloc(per_mb * N_EXTRA + 64);
+        g->extra_job = x264_cuda_host_alloc(sizeof(x264_cuda_grid_job_t) * N_EXTRA);
+        if (!g->grid || !g->jobs || !g->extra_grid || !g->extra_job) { fprintf(stderr, "x264_b200: cannot page-lock %zu MB for the candidate grids\n", (per_mb * n_mb) >> 20); exit(3); }
     }
     g->ref = ref; g->ref_frame = ref->i_frame; g->ref_poc = ref->i_poc; g->enc_frame = h->fenc->i_frame; g->enc_type = h->sh.i_type; g->used = ++B.clock;
     guess_centres(h, ref, list, g);
-    x264_cuda_frame_t *denc = source_on_device(h), *dref = slot_for_ref(ref)->d;
-    /* a few macroblock rows per launch, each followed by its own copy back and fence: the host starts on row 0 while later rows are
-     * still being computed and copied */
-    g->rows_per_chunk = X264_MAX(1, 512 / B.mb_w);
+    /* A few macroblock rows per launch, each followed by its own copy back and fence.  Only the first two chunks are issued now; chunk
+     * c + 1 goes out when the host starts on chunk c (gridset_wait_row), with its centres refreshed from the vectors the rows above have
+     * just been given — the device computes and copies it while the host encodes chunk c. */
+    g->list = list;
+    g->rows_per_chunk = x264_clip3(256 / B.mb_w, 1, 4);
     g->n_chunks = (B.mb_h + g->rows_per_chunk - 1) / g->rows_per_chunk;
     if (g->n_chunks > MAX_CHUNKS) { g->rows_per_chunk = (B.mb_h + MAX_CHUNKS - 1) / MAX_CHUNKS; g->n_chunks = (B.mb_h + g->rows_per_chunk - 1) / g->rows_per_chunk; }
-    for (int c = 0; c < g->n_chunks; c++) {
-        const int mb0 = c * g->rows_per_chunk * B.mb_w, mb1 = X264_MIN(n_mb, mb0 + g->rows_per_chunk * B.mb_w);
-        CK(x264_cuda_sad_grid_quad(B.ctx, denc, dref, R, g->jobs + mb0, mb1 - mb0, (uint16_t *)((uint8_t *)g->grid + per_mb * mb0), 1));
-        if (!(g->fence[c] = x264_cuda_fence_record(B.ctx))) die("x264_cuda_fence_record");
-    }
+    memset(g->issued, 0, sizeof(g->issued));
+    for (int k = 0; k < N_EXTRA; k++) { g->extra_job[k].mb_x = -1; g->extra_used[k] = 0; }
+    issue_chunk(h, g, 0, -1);
+    if (g->n_chunks > 1) issue_chunk(h, g, 1, -1);
     B.n_gridsets++;
     B.t_grid_issue += now_ms() - t0;
     return g;
 }
-static inline void gridset_wait_row(gridset_t *g, int mb_y)
+/* the host is about to search macroblock row mb_y: its chunk must have arrived; the next chunk is sent on its way */
+static inline void gridset_wait_row(x264_t *h, gridset_t *g, int mb_y)
 {
     const int c = mb_y / g->rows_per_chunk;
+    if (!g->issued[c]) issue_chunk(h, g, c, mb_y - 1);
     if (g->fence[c]) {
         const double t0 = now_ms();
         for (int k = 0; k <= c; k++) if (g->fence[k]) { CK(x264_cuda_fence_wait(B.ctx, g->fence[k])); g->fence[k] = NULL; }
         B.t_grid_wait += now_ms() - t0;
+    }
+    if (c + 1 < g->n_chunks && !g->issued[c + 1]) {
+        const double t0 = now_ms();
+        issue_chunk(h, g, c + 1, mb_y - 1);
+        B.t_grid_issue += now_ms() - t0;
     }
 }
 
@@ -615,7 +656,7 @@ void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, i
         const uint64_t mask = i_pixel == PIXEL_16x16 ? ~0ULL : i_pixel == PIXEL_16x8 ? (oy ? Q[2] | Q[3] : Q[0] | Q[1])
                             : i_pixel == PIXEL_8x16 ? (ox ? Q[1] | Q[3] : Q[0] | Q[2]) : Q[(oy >> 3) * 2 + (ox >> 3)];
         g = gridset_for(h, ref, list);
-        gridset_wait_row(g, by >> 4);
+        gridset_wait_row(h, g, by >> 4);
         view_of(&gv, g, mb_xy, mask);
     }
     /* SAD of the block at integer vector (mx, my): from the grid, or — for a predictor candidate the grid does not cover — the table entry */
@@ -662,17 +703,33 @@ void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, i
     const int width = (max_x - min_x + 3) & ~3;
     if (use_grid) {
         if (min_x < gv.gx0 || min_x + width > gv.gx0 + gv.gw || min_y < gv.gy0 || max_y >= gv.gy0 + gv.gh) {
-            /* the guessed centre was off: recompute this macroblock's grid around the exact centre (later partitions of the macroblock
-             * search near it as well) */
-            const double t0 = now_ms();
-            x264_cuda_grid_job_t *j = &g->jobs[mb_xy];
-            j->cx = bmx; j->cy = bmy;
-            CK(x264_cuda_sad_grid_quad(B.ctx, source_on_device(h), slot_for_ref(ref)->d, B.radius, j, 1,
-                                       (uint16_t *)((uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(B.radius) * mb_xy), 0));
-            view_of(&gv, g, mb_xy, gv.mask);
-            B.n_relaunch++;
-            B.t_relaunch += now_ms() - t0;
+            /* the guessed centre was off.  A grid recomputed for this macroblock earlier may cover the window; else recompute one around
+             * the exact centre (one-job launch) into the least recently used spare slot */
+            const int R = B.radius;
+            int slot = -1;
+            for (int k = 0; k < N_EXTRA && slot < 0; k++) {
+                const x264_cuda_grid_job_t *e = &g->extra_job[k];
+                if (e->mb_x == (bx >> 4) && e->mb_y == (by >> 4) && min_x >= e->cx - R && min_x + width <= e->cx - R + gv.gw && min_y >= e->cy - R && max_y <= e->cy + R) slot = k;
+            }
+            if (slot < 0) {
+                const double t0 = now_ms();
+                slot = 0;
+                for (int k = 1; k < N_EXTRA; k++) if (g->extra_used[k] < g->extra_used[slot]) slot = k;
+                x264_cuda_grid_job_t *e = &g->extra_job[slot];
+                *e = g->jobs[mb_xy];
+                e->cx = bmx; e->cy = bmy;
+                if (B.verbose > 1) fprintf(stderr, "x264_b200: miss frame %d mb (%d,%d) pixel %d off (%d,%d): centre (%d,%d), needed (%d,%d), mvp (%d,%d)\n", h->fenc->i_frame, bx >> 4,
+                                           by >> 4, i_pixel, ox, oy, g->jobs[mb_xy].cx, g->jobs[mb_xy].cy, bmx, bmy, m->mvp[0], m->mvp[1]);
+                CK(x264_cuda_sad_grid_quad(B.ctx, source_on_device(h), slot_for_ref(ref)->d, R, e, 1, (uint16_t *)((uint8_t *)g->extra_grid + X264_CUDA_GRID_QUAD_BYTES(R) * slot), 0));
+                B.n_relaunch++;
+                B.t_relaunch += now_ms() - t0;
+            } else
+                B.n_extra_hit++;
+            g->extra_used[slot] = ++B.clock;
+            gv.quad = (const uint64_t *)((const uint8_t *)g->extra_grid + X264_CUDA_GRID_QUAD_BYTES(R) * slot);
+            gv.gx0 = g->extra_job[slot].cx - R; gv.gy0 = g->extra_job[slot].cy - R;
         }
+
         int xc[136 + 8];
         for (int i = 0; i < width; i++) xc[i] = cost_x[(min_x + i) << 2];
         for (int i = width; i < ((width + 7) & ~7); i++) xc[i] = COST_MAX;

@@ -29,7 +29,9 @@ def test_plan_and_fixups():
     from x264_vs2008_b200 import gop_shard as G
     assert G.plan_gops(23, 6) == [(0, 0, 6), (1, 6, 6), (2, 12, 6), (3, 18, 5)]
     assert G.plan_gops(12, 6) == [(0, 0, 6), (1, 6, 6)]
-    assert [G.gops_of_rank(7, 3, r) for r in range(3)] == [[0, 3, 6], [1, 4], [2, 5]]
+    assert [G.gops_of_rank(7, 3, r) for r in range(3)] == [[0, 1, 2], [3, 4], [5, 6]]
+    assert G.split_runs(G.plan_gops(23, 6), 2) == [(0, 0, 12), (2, 12, 11)]
+    assert G.split_runs(G.plan_gops(23, 6), 8) == G.plan_gops(23, 6)
     with pytest.raises(ValueError):
         G.gops_of_rank(4, 2, 2)
     sei = b"\x00\x00\x00\x01\x06\x05\x10abc\x80"
@@ -48,7 +50,9 @@ def _worker(rank, world, port, src, tmp, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         gops = G.plan_gops(N, K)
         mine = [gops[k] for k in G.gops_of_rank(len(gops), world, rank)]
-        parts, _ = G.encode_gops(STUB, src, W, H, OPTS.split(), K, mine, os.path.join(tmp, "r%d" % rank), workers=2)
+        parts, _ = G.encode_gops(STUB, src, W, H, OPTS.split(), K, mine if rank else G.split_runs(mine, 1), os.path.join(tmp, "r%d" % rank), workers=2)
+        if not rank:   # rank 0 encoded its two GOPs as ONE run (one encoder invocation): hand it on under its first GOP's index
+            parts = {0: parts[0], 1: b""}
         stream = G.gather_stream(dist, parts, len(gops))
         dist.barrier()
         dist.destroy_process_group()
@@ -83,9 +87,12 @@ def test_two_ranks_stitch_equals_single_process(tmp_path):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    assert got[0][1] == [0, 2] and got[1][1] == [1, 3]
+    assert got[0][1] == [0, 1] and got[1][1] == [2, 3]
     assert got[1][2] is None
     assert got[0][2] == want, (len(got[0][2]), len(want))
     # and in one process, four workers at once
     parts, _ = G.encode_gops(STUB, src, W, H, OPTS.split(), K, G.plan_gops(N, K), str(tmp_path / "solo"), workers=4)
     assert G.stitch(parts) == want
+    # three workers, runs of 2 + 1 + 1 GOPs
+    parts, _ = G.encode_gops(STUB, src, W, H, OPTS.split(), K, G.split_runs(G.plan_gops(N, K), 3), str(tmp_path / "runs"), workers=3)
+    assert sorted(parts) == [0, 2, 3] and G.stitch(parts) == want

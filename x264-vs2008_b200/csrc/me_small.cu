@@ -1161,7 +1161,7 @@ extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, 
         a.sync[1] = (unsigned long long *)fenc->la_done + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
         a.order = ctx->d_la_order; a.n_order = ctx->la_n;
         a.ticket = d_ticket; a.sums = ctx->d_la_sums + 8 * e;
-        a.epoch = ++g_la_epoch; // process-wide: the hand-over words live in the FRAME, which several contexts may evaluate in turn a.b_bidir = b_bidir; a.b_any_inter = any;
+        a.epoch = ++g_la_epoch; /* process-wide: the hand-over words live in the FRAME, which several contexts may evaluate in turn */ a.b_bidir = b_bidir; a.b_any_inter = any;
         a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
         a.weight = (pm->flags & X264_CUDA_LOWRES_WEIGHTED_BIPRED) ? 64 - (a.dsf >> 2) : 32;                          // slicetype.c:57
         a.method = pm->me_method < 1 ? X264_CUDA_ME_METHOD_DIA : X264_CUDA_ME_METHOD_HEX;                            // min(HEX, me), slicetype.c:38

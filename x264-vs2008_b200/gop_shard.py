@@ -11,8 +11,9 @@ concatenation of the shards in GOP order after two fix-ups:
     S/common/cabac.c:917): the worker starts that count at its first frame number (X264_B200_CODED_FRAMES);
   * every worker starts its stream with the version SEI the reference writes for frame 0 only (encoder.c:1570-1578): dropped from
     every shard but the first.
-Ranks take GOPs round-robin (GOP k -> rank k mod world); within a rank, several worker processes may share the GPU (the per-frame device
-work is ~1 ms, the sequential macroblock loop on the host ~60-100 ms), which is how one B200 feeds all host cores.
+A worker takes a RUN of consecutive GOPs in one encoder invocation (one CUDA context start-up per worker, not per GOP): ranks own
+contiguous runs of the GOP list, and within a rank several worker processes may share the GPU (the per-frame device work is ~1 ms, the
+sequential macroblock loop on the host ~60-100 ms), which is how one B200 feeds all host cores.
 No collective on the data path; rank 0 gathers the NAL bytes.
 """
 import os
@@ -28,10 +29,27 @@ def plan_gops(n_frames, keyint):
     return [(k, s, min(keyint, n_frames - s)) for k, s in enumerate(range(0, n_frames, keyint))]
 
 
+def split_runs(gops, n_parts):
+    """consecutive GOPs -> at most n_parts runs of consecutive GOPs, sizes differing by at most one; a run is (first gop index, first
+    frame, frame count) — the same shape as a GOP, so encode_gop() takes either"""
+    n = len(gops)
+    runs, q, r = [], n // max(1, n_parts), n % max(1, n_parts)
+    lo = 0
+    for p in range(min(n_parts, n)):
+        hi = lo + q + (1 if p < r else 0)
+        if hi > lo:
+            runs.append((gops[lo][0], gops[lo][1], sum(g[2] for g in gops[lo:hi])))
+        lo = hi
+    return runs
+
+
 def gops_of_rank(n_gops, world, rank):
+    """contiguous [lo, hi) of the GOP list for `rank` (sizes differ by at most one)"""
     if not (0 <= rank < world):
         raise ValueError("rank %d outside world %d" % (rank, world))
-    return list(range(rank, n_gops, world))
+    q, r = divmod(n_gops, world)
+    lo = rank * q + min(rank, r)
+    return list(range(lo, lo + q + (1 if rank < r else 0)))
 
 
 def gop_options(keyint):
@@ -48,7 +66,8 @@ def drop_leading_sei(data):
 
 
 def encode_gop(exe, src, width, height, opts, keyint, gop, out_path, env=None, threads=1):
-    """one worker: encode GOP `gop` = (index, first, count) of `src` to out_path; returns (stderr, wall seconds)"""
+    """one worker: encode GOP (or run of GOPs) `gop` = (index of its first GOP, first frame, frame count) of `src` to out_path;
+    returns (stderr, wall seconds)"""
     k, first, count = gop
     cmd = [exe, "--no-asm", "--threads", str(threads)] + list(opts) + gop_options(keyint) + ["--seek", str(first), "--frames", str(count), "-o", out_path, src,
                                                                                               "%dx%d" % (width, height)]
