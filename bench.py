@@ -233,7 +233,7 @@ def run_reference(args):
             "e2e": {"value": rate / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if not args.no_encode:
-        enc = encode_leg_reference(max(1, min(args.encode_workers, cores)) * 2 * ENC_KEYINT)
+        enc = encode_leg_reference(max(1, min(args.encode_workers, cores - (2 if cores > 4 else 0))) * ENC_KEYINT)
         enc.pop("stream_1thread", None)
         line["encode"] = enc
     print(json.dumps(line))
@@ -244,20 +244,24 @@ ENC_OPTS = "--qp 26 --me esa --merange 16 --subme 2 --no-psnr --no-ssim"
 ENC_KEYINT = 24
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "x264")
 B200_CLI = os.path.join(ROOT, "integration", "_build", "x264_b200")
+B200_GOPS = os.path.join(ROOT, "integration", "_build", "x264_b200_gops")
 
 
 def _enc_clip(seed, n_frames):
-    """seeded synthetic 1080p YUV420 clip on local disk (cached between bench invocations of one round)"""
+    """seeded synthetic 1080p YUV420 clip on local disk (cached between bench invocations of one round).  Every closed GOP is its own
+    scene (its own seeded texture and motion), so no P-frame predicts across a content jump"""
     import __graft_entry__ as ge
     ge.load_pkg()
     from x264_vs2008_b200 import synth
-    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "x264b200_bench_%dx%d_s%d_n%d.yuv" % (W, H, seed, n_frames))
+    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "x264b200_bench_%dx%d_s%d_n%d_k%d.yuv" % (W, H, seed, n_frames, ENC_KEYINT))
     if not (os.path.exists(path) and os.path.getsize(path) == n_frames * W * H * 3 // 2):
-        clip = synth.Clip(W, H, seed=seed, motion=(3, 2))   # (3,2) px/frame: the texture field wraps only after 32 frames
         tmp = path + ".%d.tmp" % os.getpid()
         with open(tmp, "wb") as f:
+            clip = None
             for i in range(n_frames):
-                for p in clip.yuv420(i % 32):
+                if i % ENC_KEYINT == 0:
+                    clip = synth.Clip(W, H, seed=1000 * seed + i // ENC_KEYINT, motion=(3 + (i // ENC_KEYINT) % 4, 2))
+                for p in clip.yuv420(i % ENC_KEYINT):
                     f.write(np.ascontiguousarray(p).tobytes())
         os.replace(tmp, path)
     return path
@@ -299,52 +303,64 @@ def encode_leg_reference(n_frames, seed=1):
 
 
 def encode_leg_ours(local, world, rank, dist, workers):
-    """bit-exact encode fps of the performance-mode build (integration/_build/x264_b200): the unmodified reference encoder whose exhaustive
-    search reads device SAD grids and whose deblocking / half-pel planes come from the device.  One process, and `workers` GOP-sharded
-    processes per GPU (x264-vs2008_b200/gop_shard.py); the stitched stream must equal the reference's --threads 1 stream byte for byte."""
+    """bit-exact encode fps of the performance-mode build: the unmodified reference encoder whose exhaustive search reads device SAD grids
+    and whose deblocking / half-pel planes come from the device (integration/x264_b200_hooks.c).
+      fps_one_process : the reference CLI with the hooks (integration/_build/x264_b200), --threads 1;
+      fps             : the GOP-parallel front end (integration/_build/x264_b200_gops): `workers` encoder threads in ONE process per GPU,
+                        each a run of closed GOPs, one device context and stream per thread.
+    The front end's stream must equal the reference's `--threads 1` stream of the same clip byte for byte."""
     import re
     import __graft_entry__ as ge
     ge.load_pkg()
     from x264_vs2008_b200 import gop_shard as G
-    if not (os.path.exists(B200_CLI) and os.path.exists(REF_CLI)):
-        return {"unavailable": "integration/_build/x264_b200 or oracle/_ref/x264 not built"}
-    n_frames = workers * 2 * ENC_KEYINT
+    if not (os.path.exists(B200_CLI) and os.path.exists(B200_GOPS) and os.path.exists(REF_CLI)):
+        return {"unavailable": "integration/_build/x264_b200(_gops) or oracle/_ref/x264 not built"}
+    n_frames = workers * ENC_KEYINT
     src = _enc_clip(1 + rank, n_frames)
     tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), "bench_b200_r%d" % rank)
     os.makedirs(tmp, exist_ok=True)
     env = {"X264_B200_DEVICE": str(local), "X264_B200_VERBOSE": "1"}
     opts = ENC_OPTS.split() + G.gop_options(ENC_KEYINT)
-    # (a) one process, the first 2 GOPs
-    n1, w1, err1 = _cli(B200_CLI, opts + ["--frames", str(2 * ENC_KEYINT)], src, os.path.join(tmp, "single.264"), 1, env)
+    # (a) one process, the first two GOPs
+    n1, w1, err1 = _cli(B200_CLI, opts + ["--frames", str(min(n_frames, 2 * ENC_KEYINT))], src, os.path.join(tmp, "single.264"), 1, env)
     m = re.search(r"open ([0-9.]+) ms", err1)
     open_ms = float(m.group(1)) if m else 0.0
     k = re.search(r"(\d+) kernel launches", err1)
-    # (b) `workers` processes on this GPU, each a run of consecutive closed GOPs
-    gops = G.plan_gops(n_frames, ENC_KEYINT)
+    # (b) the GOP-parallel front end: `workers` encoder threads sharing this GPU
     if dist is not None:
         dist.barrier()
-    parts, wall = G.encode_gops(B200_CLI, src, W, H, ENC_OPTS.split(), ENC_KEYINT, G.split_runs(gops, workers), tmp, workers=workers, env=env)
-    stream = G.stitch(parts)
+    out = os.path.join(tmp, "gops.264")
+    cmd = [B200_GOPS, "--no-asm"] + ENC_OPTS.split() + ["--keyint", str(ENC_KEYINT), "--workers", str(workers), "-o", out, src, "%dx%d" % (W, H)]
+    e = dict(os.environ)
+    e.update(env)
+    t = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True, env=e)
+    wall = time.perf_counter() - t
+    if r.returncode != 0:
+        raise SystemExit("bench.py: x264_b200_gops failed: %s" % r.stderr[-800:])
+    m = re.search(r"encoded (\d+) frames, ([0-9.]+) fps", r.stderr)
+    inner_fps = float(m.group(2)) if m else 0.0
+    launches = sum(int(x) for x in re.findall(r"(\d+) kernel launches", r.stderr))
     # parity: the reference's own single-process stream of the same clip (rank 0 only: one reference run is enough for the claim)
     identical = None
     ref = None
     if rank == 0:
         ref = encode_leg_reference(n_frames, seed=1)
-        identical = stream == open(ref.pop("stream_1thread"), "rb").read()
+        identical = open(out, "rb").read() == open(ref.pop("stream_1thread"), "rb").read()
         if not identical:
-            raise SystemExit("bench.py: GOP-sharded device encode differs from the reference's --threads 1 stream")
-    times, counts = [wall, w1], [n_frames, n1]
+            raise SystemExit("bench.py: GOP-parallel device encode differs from the reference's --threads 1 stream")
     from x264_vs2008_b200 import shard
-    (wall_max, w1_max), (frames_all, n1_all) = shard.reduce_job(dist, "cuda", times, counts)
+    (wall_max, inner_max), (frames_all,) = shard.reduce_job(dist, "cuda", [wall, n_frames / max(inner_fps, 1e-9)], [n_frames])
     if rank != 0:
         return None
     return {"config": "1080p %s --keyint %d, %d frames per GPU" % (ENC_OPTS, ENC_KEYINT, n_frames),
-            "fps": frames_all / wall_max, "processes_per_gpu": workers, "frames": int(frames_all),
+            "fps": frames_all / wall_max, "fps_excluding_process_start": frames_all / inner_max, "encoder_threads_per_gpu": workers, "frames": int(frames_all),
             "fps_one_process": n1 / w1, "fps_one_process_after_cuda_start": n1 / max(1e-9, w1 - open_ms / 1e3), "cuda_start_ms": open_ms,
-            "kernel_launches_one_process": int(k.group(1)) if k else 0,
+            "kernel_launches_one_process": int(k.group(1)) if k else 0, "kernel_launches_front_end": launches,
             "identical_to_reference_stream": identical, "reference": ref,
-            "note": "wall-clock of the encoder processes, CUDA context start-up included; the host keeps the sequential macroblock loop, entropy coding "
-                    "and sub-pel refinement (SURVEY 7.3-1: host-bound), the device serves ESA grids, deblocking and half-pel planes"}
+            "note": "fps = frames / wall-clock of the front-end process (CUDA context start-up, cost-table build and file IO included); the host keeps "
+                    "the sequential macroblock loop, entropy coding and sub-pel refinement of every encoder thread (SURVEY 7.3-1: host-bound), the "
+                    "device serves their ESA grids, deblocking and half-pel planes"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -548,7 +564,8 @@ def run_ours(args):
     (total_ms, e2e_ms), (cands_all, sadops_all) = shard.reduce_job(dist if world > 1 else None, "cuda", [total_ms, e2e_ms], [cands, sadops])
     enc = None
     if not args.no_encode:
-        enc = encode_leg_ours(local, world, rank, dist if world > 1 else None, max(1, min(args.encode_workers, (os.cpu_count() or 1) // world)))
+        cores = os.cpu_count() or 1
+        enc = encode_leg_ours(local, world, rank, dist if world > 1 else None, max(1, min(args.encode_workers, (cores - (2 if world == 1 and cores > 4 else 0)) // world)))
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -867,7 +884,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode-fps leg")
-    ap.add_argument("--encode-workers", type=int, default=4, help="GOP-sharded encoder processes per GPU in the encode-fps leg")
+    ap.add_argument("--encode-workers", type=int, default=12, help="encoder threads per GPU in the encode-fps leg (capped by the host cores per rank)")
     ap.add_argument("--rows", action="store_true", help="per-row device time vs the reference's C on one core (1080p); one JSON line")
     ap.add_argument("--e2e-blocking", type=int, default=-1, help="frame threads wait for results on a blocking-sync event (sleep) instead of spinning; "
                     "-1 = automatic: when the ranks' frame threads outnumber the host cores")

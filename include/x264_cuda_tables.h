@@ -125,6 +125,11 @@ X264_CUDA_API int x264_dct_init_cuda(x264_cuda_dct_function_t *dctf);     /* all
 X264_CUDA_API int x264_quant_init_cuda(x264_cuda_quant_function_t *pf);   /* quant_*, dequant_* */
 X264_CUDA_API int x264_mc_init_cuda(x264_cuda_mc_functions_t *pf);        /* mc_luma, get_ref, mc_chroma, avg[10], hpel_filter, frame_init_lowres_core */
 X264_CUDA_API long long x264_cuda_tables_launches(void);                  /* kernels launched by table entries so far (diagnostic) */
+/* The table signatures cannot report failure (S/common/pixel.h:26-28).  A device error inside an entry is recorded once (sticky), every
+ * later entry returns zeros without touching the device, and this returns the message (NULL while healthy): the encoder-side hook
+ * checks it once per frame and makes x264_encoder_encode() return -1 after x264_log(h, X264_LOG_ERROR, ...) — the reference's own
+ * convention (S/x264.c:759-762).  Entries may be called concurrently from any number of host threads (one context per thread). */
+X264_CUDA_API const char *x264_cuda_tables_error(void);
 X264_CUDA_API void x264_cuda_tables_shutdown(void);                       /* releases the shared context */
 
 #ifdef __cplusplus

@@ -69,9 +69,11 @@ typedef struct {
     long long extra_used[N_EXTRA];
 } gridset_t;
 
-static struct {
+/* all state is per host thread: several encoder instances may run side by side in one process (x264_b200_gops.c), each with its own
+ * device context and stream */
+static __thread struct {
     int state; /* 0: undecided, 1: on, -1: off (plain reference) */
-    int verbose, me_on, frame_on, check, avx2; /* X264_B200_ME=0 / X264_B200_FRAME=0 switch one of the two hook groups off (diagnosis) */
+    int verbose, me_on, frame_on, check, avx2, reported; /* X264_B200_ME=0 / X264_B200_FRAME=0 switch one of the two hook groups off (diagnosis) */
     x264_cuda_t *ctx;
     int radius, flags;
     int mb_w, mb_h;
@@ -104,7 +106,8 @@ static void die(const char *what)
 
 static void report(void)
 {
-    if (!B.verbose) return;
+    if (!B.verbose || B.reported) return;
+    B.reported = 1;
     fprintf(stderr, "x264_b200: %lld ESA searches read device grids (%lld macroblock grids recomputed around the exact centre and %lld reused, %lld predictor SADs outside a grid "
             "taken from the table entry, %lld sub-8x8 searches as one-job device calls, %lld searches left to the reference), %lld frame grid sets, "
             "%lld end-of-frame device passes; %lld kernel launches\n", B.n_search, B.n_relaunch, B.n_extra_hit, B.n_outside_pred, B.n_percall, B.n_left_to_c, B.n_gridsets,
@@ -153,14 +156,24 @@ static int b200_on(x264_t *h)
  * pictures from k, as the single-process encoder would (S/encoder/encoder.c:1107-1110), and start its count of coded frames where that
  * encoder would be (h->i_frame selects the signature bit the CABAC flush embeds in every slice, S/common/cabac.c:917); everything else
  * restarts at an IDR anyway. */
+static __thread int seed_set, seed_idr_pic_id, seed_coded_frames;
+void x264_b200_set_gop_seed(int idr_pic_id, int coded_frames) { seed_set = 1; seed_idr_pic_id = idr_pic_id; seed_coded_frames = coded_frames; }
+void x264_b200_disable_for_this_thread(void) { B.state = -1; }
+void x264_b200_report(void) { report(); }
 x264_t *x264_encoder_open_c(x264_param_t *param);
 x264_t *x264_encoder_open(x264_param_t *param)
 {
     x264_t *h = x264_encoder_open_c(param);
-    const char *e = getenv("X264_B200_IDR_PIC_ID");
-    if (h && e) h->i_idr_pic_id = atoi(e) & 0xffff;
+    if (!h) return h;
+    if (seed_set) { /* an in-process front end (x264_b200_gops.c) */
+        h->i_idr_pic_id = seed_idr_pic_id & 0xffff; h->i_frame = seed_coded_frames;
+        seed_set = 0;
+        return h;
+    }
+    const char *e = getenv("X264_B200_IDR_PIC_ID"); /* a CLI worker started by gop_shard.py */
+    if (e) h->i_idr_pic_id = atoi(e) & 0xffff;
     e = getenv("X264_B200_CODED_FRAMES");
-    if (h && e) h->i_frame = atoi(e);
+    if (e) h->i_frame = atoi(e);
     return h;
 }
 
@@ -267,7 +280,7 @@ static void frame_end(x264_t *h, x264_frame_t *f)
     B.n_frame_end++;
     B.t_frame_end += now_ms() - t0;
 }
-static x264_t *g_h; /* the encoder handle, for the hooks whose reference signature does not carry it (one thread) */
+static __thread x264_t *g_h; /* the encoder handle, for the hooks whose reference signature does not carry it (one thread) */
 static int frame_hooks_on(x264_t *h) { return b200_on(h) && B.frame_on && h->fdec->b_kept_as_ref && !h->sh.b_mbaff; }
 
 void x264_frame_deblock_row(x264_t *h, int mb_y)

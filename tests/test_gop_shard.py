@@ -96,3 +96,26 @@ def test_two_ranks_stitch_equals_single_process(tmp_path):
     # three workers, runs of 2 + 1 + 1 GOPs
     parts, _ = G.encode_gops(STUB, src, W, H, OPTS.split(), K, G.split_runs(G.plan_gops(N, K), 3), str(tmp_path / "runs"), workers=3)
     assert sorted(parts) == [0, 2, 3] and G.stitch(parts) == want
+
+
+GOPS_STUB = os.path.join(ROOT, "oracle", "_ref", "x264_b200_gops_stub")
+
+
+@pytest.mark.parametrize("workers", [1, 3, 4])
+def test_in_process_front_end_equals_single_process(tmp_path, workers):
+    """integration/x264_b200_gops.c — several encoder instances as threads of ONE process (per-thread hook state, cost tables built before
+    the threads start, seeds handed to each instance's x264_encoder_open) — against one process of the unmodified reference"""
+    import subprocess
+    if not (os.path.exists(REF) and os.path.exists(GOPS_STUB)):
+        pytest.skip("oracle/_ref builds not present (they are produced where the reference sources exist)")
+    _load_pkg()
+    from x264_vs2008_b200 import gop_shard as G
+    src = str(tmp_path / "in.yuv")
+    _clip(W, H, N, src)
+    single, out = str(tmp_path / "single.264"), str(tmp_path / "gops.264")
+    r = _run(REF, OPTS + " " + " ".join(G.gop_options(K)), src, single, W, H)
+    assert r.returncode == 0, r.stderr[-1500:]
+    r = subprocess.run([GOPS_STUB, "--no-asm"] + OPTS.split() + ["--keyint", str(K), "--workers", str(workers), "-o", out, src, "%dx%d" % (W, H)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert open(out, "rb").read() == open(single, "rb").read()

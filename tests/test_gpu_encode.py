@@ -78,3 +78,29 @@ def test_gop_sharded_on_device(tmp_path):
     assert r.returncode == 0, r.stderr[-1500:]
     parts, wall = G.encode_gops(B200, src, w, h, opts.split(), k, G.plan_gops(n, k), str(tmp_path / "shards"), workers=4)
     assert G.stitch(parts) == open(single, "rb").read()
+
+
+@pytest.mark.parametrize("size,n,k,workers,opts", [((352, 288), 30, 6, 5, "--qp 26 --me esa --merange 16 --subme 5 --bframes 2 --b-adapt 2 --ref 2"),
+                                                   ((1920, 1080), 12, 4, 3, "--qp 26 --me esa --merange 16 --subme 2 --no-psnr --no-ssim")])
+def test_gop_parallel_front_end_on_device(tmp_path, size, n, k, workers, opts):
+    """integration/x264_b200_gops: encoder threads of one process sharing cuda:0 (one device context and stream per thread) write, stitched,
+    the stream of one reference process"""
+    gops = os.path.join(ROOT, "integration", "_build", "x264_b200_gops")
+    if not (os.path.exists(REF) and os.path.exists(gops)):
+        pytest.skip("builds not present")
+    from test_integration_host import _load_pkg
+    _load_pkg()
+    from x264_vs2008_b200 import gop_shard as G
+    w, h = size
+    src = str(tmp_path / "in.yuv")
+    _clip(w, h, n, src)
+    single, out = str(tmp_path / "single.264"), str(tmp_path / "gops.264")
+    r = _run(REF, opts + " " + " ".join(G.gop_options(k)), src, single, w, h)
+    assert r.returncode == 0, r.stderr[-1500:]
+    e = dict(os.environ)
+    e["X264_B200_VERBOSE"] = "1"
+    r = subprocess.run([gops, "--no-asm"] + opts.split() + ["--keyint", str(k), "--workers", str(workers), "-o", out, src, "%dx%d" % (w, h)],
+                       capture_output=True, text=True, timeout=900, env=e)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert open(out, "rb").read() == open(single, "rb").read()
+    assert len(re.findall(r"ESA searches read device grids", r.stderr)) == workers

@@ -12,6 +12,7 @@
 // Roofline class: integer ALU pipe.  Per candidate position: 64 SAD ops + ~30 ALU ops of bookkeeping serve nine
 // (partition, mv) candidates of the reference's search space.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -208,7 +209,117 @@ __device__ __forceinline__ void scan_union(WarpSmem &S, uint32_t (*cyt)[12], con
     }
 }
 
-__global__ void __launch_bounds__(MB_WARPS * 32, 3)
+// ---------------------------------------------------------------------------------------------------------------------
+// Second lane mapping (the default): TWO LANES PER CANDIDATE COLUMN.  Lane l = (half h = l >> 4, column l & 15): half 0 owns the left
+// eight pixel columns of the macroblock, half 1 the right eight.  A lane keeps an 8-byte reference strip (16-row ring: 32 registers) and
+// its half of the source macroblock (32 registers) instead of 64 + 64, which brings the kernel from 168 to ~100 registers: five CTAs
+// instead of three per SM, i.e. 20 instead of 12 warps to hide the load and fixed-latency stalls the profile showed.  Per position
+// a lane issues 32 VABSDIFF4 into its two quadrant sums (top, bottom of its half), packs them into one word, swaps it with its partner
+// lane (one SHFL) and then owns a share of the nine partitions: half 0 updates {16x16, 16x8 top, 8x16 left, TL, BL}, half 1
+// {-, 16x8 bottom, 8x16 right, TR, BR} — the same five expressions on both halves with per-lane cost terms.
+#define KEY_SHIFT2 11 // key: cost (20 bits) << 11 | row (8 bits) << 3 | 16-column chunk (3 bits)
+__device__ __forceinline__ int half_slot_part(int h, int s) // partition updated by slot s of half h (-1: none)
+{
+    return h ? (s == 0 ? -1 : 2 * s) : (s == 0 ? 0 : 2 * s - 1); // h0: 0,1,3,5,7   h1: -,2,4,6,8
+}
+__device__ __forceinline__ void load_row8(uint32_t (&dst)[2], const uint8_t *p, int sh)
+{
+    const uint32_t w0 = __ldg((const uint32_t *)p), w1 = __ldg((const uint32_t *)p + 1), w2 = __ldg((const uint32_t *)p + 2);
+    dst[0] = __funnelshift_r(w0, w1, sh);
+    dst[1] = __funnelshift_r(w1, w2, sh);
+}
+// cyt2: per union row 2 x 8 words: [h][slot] = (y cost of the slot's partition << KEY_SHIFT2) | row << 3, INVALID outside its row range
+__device__ __forceinline__ void scan_union2(WarpSmem &S, uint32_t (*cyt2)[16], const int16_t *tab, const uint8_t *ref0, int stride, unsigned mask,
+                                            int ux0, int uy0, int uwidth, int urows, int lane, uint32_t (&best)[5])
+{
+    const x264_cuda_me_mb_job_t &job = S.job;
+    const int h = lane >> 4, ci = lane & 15;
+    __syncwarp();
+    if (lane < 30) {
+        const int e = lane % 10, ph = lane / 10, eh = e / 5, es = e % 5;
+        const int p = half_slot_part(eh, es);
+        const bool on = p >= 0 && (mask >> p & 1);
+        const int pp = max(p, 0);
+        const int wy0 = S.win[pp][1] - uy0, wy1 = wy0 + S.win[pp][3];
+        const int16_t *ty = tab + ((uy0 << 2) - job.mvp[pp][1]);
+        for (int r0 = ph; r0 < urows + 3; r0 += 12) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = r0 + 3 * k;
+                v[k] = (on && r >= wy0 && r < wy1) ? (uint32_t)ty[r << 2] : INVALID_COST;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = r0 + 3 * k;
+                if (r < urows + 3) cyt2[r][eh * 8 + es] = (v[k] << KEY_SHIFT2) | ((uint32_t)min(r, 255) << 3);
+            }
+        }
+    }
+    __syncwarp();
+    // this lane's half of the source macroblock
+    uint32_t F[16][2];
+#pragma unroll
+    for (int y = 0; y < 16; y++) { F[y][0] = S.F[y][2 * h]; F[y][1] = S.F[y][2 * h + 1]; }
+    for (int c0 = 0, chunk = 0; c0 < uwidth; c0 += 16, chunk++) {
+        // a full chunk is 16 columns x 1 row segment; the narrow tail chunk is folded to 8 columns x 2 row segments
+        const int rem = uwidth - c0;
+        const int cw = rem > 8 ? 16 : 8, segs = 16 / cw;
+        const int lcol = ci & (cw - 1), seg = ci / cw;
+        const int col = c0 + lcol;
+        const int mx = ux0 + min(col, uwidth - 1);
+        const int seg_rows = (urows + segs - 1) / segs;
+        uint32_t cxp[5];
+#pragma unroll
+        for (int sl = 0; sl < 5; sl++) {
+            const int p = half_slot_part(h, sl), pp = max(p, 0);
+            const int wx0 = S.win[pp][0], ww = S.win[pp][2];
+            const bool in = p >= 0 && (mask >> pp & 1) && col < uwidth && mx >= wx0 && mx < wx0 + ww;
+            cxp[sl] = ((in ? (uint32_t)tab[(mx << 2) - job.mvp[pp][0]] : INVALID_COST) << KEY_SHIFT2) | (uint32_t)chunk;
+        }
+        const uint8_t *t0 = ref0 + (ptrdiff_t)uy0 * stride + ux0 + c0;
+        for (int r = lane; r < seg_rows * segs + 15; r += 32) {
+            prefetch_l1(t0 + (size_t)r * stride);
+            prefetch_l1(t0 + (size_t)r * stride + cw + 16);
+        }
+        const int rbeg = seg * seg_rows;
+        const uint8_t *a = ref0 + (ptrdiff_t)(uy0 + rbeg) * stride + mx + 8 * h;
+        const int sh = ((uintptr_t)a & 3) * 8;
+        const uint8_t *pr = (const uint8_t *)((uintptr_t)a & ~(uintptr_t)3);
+        uint32_t R[16][2];
+#pragma unroll
+        for (int y = 0; y < 15; y++) load_row8(R[y], pr + (size_t)y * stride, sh);
+        for (int base = 0; base < seg_rows; base += 16) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int r = base + j;
+                if (r >= seg_rows) break; // warp-uniform
+                load_row8(R[(j + 15) % 16], pr + (size_t)(r + 15) * stride, sh);
+                const uint4 ca = *(const uint4 *)&cyt2[rbeg + r][h * 8];
+                const uint32_t cb = cyt2[rbeg + r][h * 8 + 4];
+                uint32_t t0a = 0, t1a = 0, b0a = 0, b1a = 0;
+#pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    t0a = sad4_acc(F[y][0], R[(j + y) % 16][0], t0a);
+                    b0a = sad4_acc(F[y + 8][0], R[(j + y + 8) % 16][0], b0a);
+                    t1a = sad4_acc(F[y][1], R[(j + y) % 16][1], t1a);
+                    b1a = sad4_acc(F[y + 8][1], R[(j + y + 8) % 16][1], b1a);
+                }
+                const uint32_t t = t0a + t1a, b = b0a + b1a;
+                const uint32_t o = __shfl_xor_sync(0xffffffffu, t | (b << 16), 16); // the partner half's (top, bottom)
+                const uint32_t ot = o & 0xffffu, ob = o >> 16;
+                const uint32_t own = t + b, tt = t + ot, bb = b + ob, all = tt + bb;
+                const uint32_t s1 = h ? bb : tt;
+#define UPD2(sl, sad, cy) best[sl] = min(best[sl], __umul24((sad), 1u << KEY_SHIFT2) + cxp[sl] + (cy))
+                UPD2(0, all, ca.x); UPD2(1, s1, ca.y); UPD2(2, own, ca.z); UPD2(3, t, ca.w); UPD2(4, b, cb);
+#undef UPD2
+            }
+        }
+    }
+}
+
+template <bool HALF>
+__global__ void __launch_bounds__(MB_WARPS * 32, HALF ? 5 : 3)
 me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int n_jobs,
                     const int16_t *const *__restrict__ cost_tabs, int me_range, int max_ur, int prefetch_dist,
                     x264_cuda_me_mb_result_t *__restrict__ results)
@@ -217,7 +328,8 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
     extern __shared__ __align__(16) uint32_t s_cyt[]; // MB_WARPS x (max_ur + 4) x 12
     const int lane = threadIdx.x & 31;
     WarpSmem &S = s_all[threadIdx.x >> 5];
-    uint32_t (*cyt)[12] = (uint32_t (*)[12])(s_cyt + (size_t)(threadIdx.x >> 5) * (max_ur + 4) * 12);
+    uint32_t (*cyt)[12] = (uint32_t (*)[12])(s_cyt + (size_t)(threadIdx.x >> 5) * (max_ur + 4) * 12);    // full-strip mapping
+    uint32_t (*cyt2)[16] = (uint32_t (*)[16])(s_cyt + (size_t)(threadIdx.x >> 5) * (max_ur + 4) * 16);   // half-strip mapping
     const int stride = geo.stride;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jb < n_jobs; jb += warps_per_grid) {
@@ -357,23 +469,46 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
                 ux0 = S.win[p][0]; uy0 = S.win[p][1]; ux1 = ux0 + S.win[p][2]; uy1 = uy0 + S.win[p][3];
             }
             todo &= ~group;
-            uint32_t best[NP];
-#pragma unroll
-            for (int p = 0; p < NP; p++) best[p] = 0xffffffffu;
-            scan_union(S, cyt, tab, ref0, stride, group, ux0, uy0, ux1 - ux0, uy1 - uy0, lane, best);
-            // warp argmin per partition: min key (cost,row,chunk), then the lowest in-chunk column among its holders
             const int uwidth = ux1 - ux0;
+            if constexpr (HALF) {
+                uint32_t best[5];
 #pragma unroll
-            for (int p = 0; p < NP; p++) {
-                if (!(group >> p & 1)) continue; // warp-uniform
-                const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
-                const int chunk = k & 3, rem = uwidth - chunk * 32;
-                const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8;
-                const uint32_t c = __reduce_min_sync(0xffffffffu, best[p] == k ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
-                if (lane == p) {
-                    my_cost = (int)(k >> KEY_SHIFT);
-                    my_bmy = uy0 + (int)((k >> 2) & 255);
-                    my_bmx = ux0 + chunk * 32 + (int)c;
+                for (int sl = 0; sl < 5; sl++) best[sl] = 0xffffffffu;
+                scan_union2(S, cyt2, tab, ref0, stride, group, ux0, uy0, uwidth, uy1 - uy0, lane, best);
+                // argmin per partition over the 16 lanes of the half that owns it: min key (cost,row,chunk), then the lowest column
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    if (!(group >> p & 1)) continue; // warp-uniform
+                    const int hp = p == 0 ? 0 : ((p - 1) & 1), sp = p == 0 ? 0 : (p + 1) / 2;
+                    const bool mine = (lane >> 4) == hp;
+                    const uint32_t k = __reduce_min_sync(0xffffffffu, mine ? best[sp] : 0xffffffffu);
+                    const int chunk = k & 7, rem = uwidth - chunk * 16;
+                    const int cw = rem > 8 ? 16 : 8;
+                    const uint32_t c = __reduce_min_sync(0xffffffffu, (mine && best[sp] == k) ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
+                    if (lane == p) {
+                        my_cost = (int)(k >> KEY_SHIFT2);
+                        my_bmy = uy0 + (int)((k >> 3) & 255);
+                        my_bmx = ux0 + chunk * 16 + (int)c;
+                    }
+                }
+            } else {
+                uint32_t best[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++) best[p] = 0xffffffffu;
+                scan_union(S, cyt, tab, ref0, stride, group, ux0, uy0, uwidth, uy1 - uy0, lane, best);
+                // warp argmin per partition: min key (cost,row,chunk), then the lowest in-chunk column among its holders
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    if (!(group >> p & 1)) continue; // warp-uniform
+                    const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
+                    const int chunk = k & 3, rem = uwidth - chunk * 32;
+                    const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8;
+                    const uint32_t c = __reduce_min_sync(0xffffffffu, best[p] == k ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
+                    if (lane == p) {
+                        my_cost = (int)(k >> KEY_SHIFT);
+                        my_bmy = uy0 + (int)((k >> 2) & 255);
+                        my_bmx = ux0 + chunk * 32 + (int)c;
+                    }
                 }
             }
         }
@@ -409,11 +544,19 @@ extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_fram
     if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
     Geo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
     const int max_ur = 2 * me_range + 1 + MB_UNION_SLACK;
-    const size_t dyn = (size_t)MB_WARPS * (max_ur + 4) * 12 * sizeof(uint32_t);
+    static const int variant = getenv("X264_CUDA_MB_KERNEL") ? atoi(getenv("X264_CUDA_MB_KERNEL")) : 2; // 1: full-strip lanes, 2: half-strip lanes
     const int blocks = (n_jobs + MB_WARPS - 1) / MB_WARPS;
-    const int prefetch_dist = MB_WARPS * 3 * ctx->sm_count; // warps resident at once (168 registers: three CTAs per SM)
-    me_search_mb_kernel<<<blocks, MB_WARPS * 32, dyn, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
-                                                                     max_ur, prefetch_dist, (x264_cuda_me_mb_result_t *)d_results);
+    if (variant == 1) {
+        const size_t dyn = (size_t)MB_WARPS * (max_ur + 4) * 12 * sizeof(uint32_t);
+        const int prefetch_dist = MB_WARPS * 3 * ctx->sm_count; // warps resident at once (168 registers: three CTAs per SM)
+        me_search_mb_kernel<false><<<blocks, MB_WARPS * 32, dyn, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
+                                                                                max_ur, prefetch_dist, (x264_cuda_me_mb_result_t *)d_results);
+    } else {
+        const size_t dyn = (size_t)MB_WARPS * (max_ur + 4) * 16 * sizeof(uint32_t);
+        const int prefetch_dist = MB_WARPS * 5 * ctx->sm_count; // five CTAs per SM
+        me_search_mb_kernel<true><<<blocks, MB_WARPS * 32, dyn, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
+                                                                               max_ur, prefetch_dist, (x264_cuda_me_mb_result_t *)d_results);
+    }
     LAUNCH_CHECK(ctx, "me_search_mb_kernel");
     return 0;
 }

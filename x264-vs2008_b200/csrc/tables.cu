@@ -4,7 +4,9 @@
 // device functions the frame-batched kernels use (dct_dev.cuh / pixel_dev.cuh), copies the result back and returns it.
 // That is a PCIe round trip per call — fine for tools/checkasm-style verification and for correctness of any caller,
 // not a performance path (the frame-batched x264_cuda_* entry points are).  No CPU arithmetic happens here.
+#include <atomic>
 #include <mutex>
+#include <vector>
 #include <cstdlib>
 #include "dct_dev.cuh"
 #include "pixel_dev.cuh"
@@ -13,42 +15,70 @@
 
 namespace {
 
-std::mutex g_mu;
-x264_cuda_t *g_ctx = nullptr;
+// One context (stream, staging buffers) PER HOST THREAD: the reference copies its tables into every frame thread's x264_t
+// (S/encoder/encoder.c:780) and calls the entries concurrently from up to X264_THREAD_MAX = 128 pthreads (S/common/common.h:50), so
+// the entries must not queue on a process-wide lock.  Contexts are created on a thread's first call and closed when the process exits.
+std::mutex g_reg_mu;                 // guards the registry only (taken once per thread, and by the counters)
+std::vector<x264_cuda_t *> g_all_ctx;
+std::atomic<long long> g_launches{0};
+thread_local x264_cuda_t *t_ctx = nullptr;
+#define g_ctx t_ctx
+
+// The table signatures cannot report failure (S/common/pixel.h:26-28).  A device error is recorded ONCE here (sticky), every later entry
+// returns without touching the device (results zero), and the encoder-side hook turns x264_cuda_tables_error() != NULL into
+// x264_encoder_encode() returning -1 — the reference's own error convention (S/x264.c:759-762) instead of abort().
+std::atomic<bool> g_failed{false};
+char g_fail_msg[512] = "";
+
+void fail(const char *what)
+{
+    bool expected = false;
+    if (g_failed.compare_exchange_strong(expected, true)) {
+        snprintf(g_fail_msg, sizeof(g_fail_msg), "x264_cuda table entry %s: %s", what, g_ctx ? x264_cuda_error(g_ctx) : x264_cuda_error(nullptr));
+        fprintf(stderr, "%s\n", g_fail_msg);
+        if (getenv("X264_CUDA_TABLES_ABORT")) abort(); // opt-in: die at the point of failure (debugging)
+    }
+}
+void close_all() { for (x264_cuda_t *c : g_all_ctx) x264_cuda_close(c); g_all_ctx.clear(); }
 
 int ensure_ctx()
 {
-    if (g_ctx) return 0;
+    if (g_failed.load(std::memory_order_relaxed)) return -1;
+    if (g_ctx) { x264_cuda_enter(g_ctx); return 0; } // this thread may never have selected the device (X264_CUDA_DEVICE != 0)
     const char *e = getenv("X264_CUDA_DEVICE");
-    if (x264_cuda_open(&g_ctx, e ? atoi(e) : 0) != 0) {
-        fprintf(stderr, "%s\n", x264_cuda_error(nullptr));
-        return -1;
-    }
+    if (x264_cuda_open(&g_ctx, e ? atoi(e) : 0) != 0) { g_ctx = nullptr; fail("x264_cuda_open"); return -1; }
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    if (g_all_ctx.empty()) atexit(close_all);
+    g_all_ctx.push_back(g_ctx);
     return 0;
-}
-void die(const char *what)
-{
-    // the table signatures cannot report failure (S/common/pixel.h:26-28): a dead device is fatal, never a silent CPU path
-    fprintf(stderr, "x264_cuda table entry %s: %s\n", what, g_ctx ? x264_cuda_error(g_ctx) : x264_cuda_error(nullptr));
-    abort();
 }
 
 // ---- generic staging: host bytes in -> device -> kernel -> host bytes out
 struct Stage {
     uint8_t *h, *d;
     size_t in_bytes, total;
-    Stage(size_t in_b, size_t out_b) : in_bytes((in_b + 255) & ~(size_t)255), total(((in_b + 255) & ~(size_t)255) + out_b)
+    bool ok;
+    std::vector<uint8_t> dead; // after a failure: host scratch, so that the entries' packing / unpacking code still has memory to touch
+    Stage(size_t in_b, size_t out_b) : in_bytes((in_b + 255) & ~(size_t)255), total(((in_b + 255) & ~(size_t)255) + out_b), ok(true)
     {
-        if (ensure_ctx() || x264_cuda_stage(g_ctx, total, total)) die("staging");
-        h = (uint8_t *)g_ctx->h_stage; d = (uint8_t *)g_ctx->d_stage;
+        if (ensure_ctx()) ok = false;
+        else if (x264_cuda_stage(g_ctx, total, total)) { fail("staging"); ok = false; }
+        if (ok) { h = (uint8_t *)g_ctx->h_stage; d = (uint8_t *)g_ctx->d_stage; }
+        else { dead.assign(total, 0); h = d = dead.data(); }
     }
-    void up() { if (cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, g_ctx->stream) != cudaSuccess) die("H2D"); }
+    cudaStream_t stream() const { return ok ? g_ctx->stream : nullptr; }
+    void up() { if (ok && cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, g_ctx->stream) != cudaSuccess) { fail("H2D"); ok = false; } }
     void down()
     {
+        if (!ok) { memset(h + in_bytes, 0, total - in_bytes); return; }
+        g_launches++;
         g_ctx->launches++;
         if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(h + in_bytes, d + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, g_ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(g_ctx->stream) != cudaSuccess)
-            die("kernel/D2H");
+            cudaStreamSynchronize(g_ctx->stream) != cudaSuccess) {
+            fail("kernel/D2H");
+            ok = false;
+            memset(h + in_bytes, 0, total - in_bytes);
+        }
     }
     uint8_t *hout() { return h + in_bytes; }
     uint8_t *dout() { return d + in_bytes; }
@@ -100,12 +130,11 @@ void pack_tile(uint8_t *dst, const uint8_t *src, int stride, int w, int h)
 // one fenc block against n reference blocks
 void cmp_n(int metric, int ip, const uint8_t *p1, int s1, const uint8_t *const *p2, int s2, int n, int *scores)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     Stage st(256 * (1 + n), n * sizeof(int));
     pack_tile(st.h, p1, s1, kW[ip], kH[ip]);
     for (int i = 0; i < n; i++) pack_tile(st.h + 256 * (1 + i), p2[i], s2, kW[ip], kH[ip]);
     st.up();
-    cmp_tiles_kernel<<<1, 32, 0, g_ctx->stream>>>(metric, kW[ip], kH[ip], n, st.d, st.d + 256, 0, (int *)st.dout());
+    if (st.ok) cmp_tiles_kernel<<<1, 32, 0, st.stream()>>>(metric, kW[ip], kH[ip], n, st.d, st.d + 256, 0, (int *)st.dout());
     st.down();
     memcpy(scores, st.hout(), n * sizeof(int));
 }
@@ -151,7 +180,6 @@ __global__ void ads_kernel(int terms, int dc0, int dc1, int dc2, int dc3, const 
 }
 template <int TERMS> int ads_entry(int enc_dc[4], uint16_t *sums, int delta, uint16_t *cost_mvx, int16_t *mvs, int width, int thresh)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     const int w8 = width + 8;
     const size_t row = (size_t)w8 * 2, in = 3 * ((row + 15) & ~(size_t)15);
     Stage st(in, 16 + (size_t)width * 2);
@@ -160,7 +188,7 @@ template <int TERMS> int ads_entry(int enc_dc[4], uint16_t *sums, int delta, uin
     if (TERMS >= 2) memcpy(st.h + rs, sums + delta, row);      // sums[i+delta], sums[i+delta+8]
     memcpy(st.h + 2 * rs, cost_mvx, (size_t)width * 2);
     st.up();
-    ads_kernel<<<1, 32, 0, g_ctx->stream>>>(TERMS, enc_dc[0], enc_dc[1], TERMS == 4 ? enc_dc[2] : 0, TERMS == 4 ? enc_dc[3] : 0, (const uint16_t *)st.d,
+    if (st.ok) ads_kernel<<<1, 32, 0, st.stream()>>>(TERMS, enc_dc[0], enc_dc[1], TERMS == 4 ? enc_dc[2] : 0, TERMS == 4 ? enc_dc[3] : 0, (const uint16_t *)st.d,
                                             (const uint16_t *)(st.d + rs), (const uint16_t *)(st.d + 2 * rs), width, thresh,
                                             (int16_t *)(st.dout() + 16), (int *)st.dout());
     st.down();
@@ -239,13 +267,12 @@ __global__ void blockop_kernel(int op, int n, int p0, int p1, const uint8_t *a, 
 
 void run_op(int op, int n, int p0, int p1, const void *a, size_t a_bytes, const void *b, size_t b_bytes, void *out, size_t out_bytes)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     const size_t a_al = (a_bytes + 255) & ~(size_t)255;
     Stage st(a_al + b_bytes, out_bytes);
     memcpy(st.h, a, a_bytes);
     if (b_bytes) memcpy(st.h + a_al, b, b_bytes);
     st.up();
-    blockop_kernel<<<1, 32, 0, g_ctx->stream>>>(op, n, p0, p1, st.d, st.d + a_al, st.dout());
+    if (st.ok) blockop_kernel<<<1, 32, 0, st.stream()>>>(op, n, p0, p1, st.d, st.d + a_al, st.dout());
     st.down();
     memcpy(out, st.hout(), out_bytes);
 }
@@ -373,7 +400,6 @@ void qpel_fetch(uint8_t *dst, int dst_stride, uint8_t **src, int i_src, int mvx,
     const ptrdiff_t off = (ptrdiff_t)(mvy >> 2) * i_src + (mvx >> 2);
     const uint8_t *p1 = src[ref0[qidx]] + off + ((mvy & 3) == 3) * i_src;
     const uint8_t *p2 = (qidx & 5) ? src[ref1[qidx]] + off + ((mvx & 3) == 3) : nullptr;
-    std::lock_guard<std::mutex> lk(g_mu);
     const int ts = (w + 15) & ~15;
     Stage st(2 * (size_t)ts * h, (size_t)w * h);
     for (int y = 0; y < h; y++) {
@@ -381,7 +407,7 @@ void qpel_fetch(uint8_t *dst, int dst_stride, uint8_t **src, int i_src, int mvx,
         if (p2) memcpy(st.h + (size_t)(h + y) * ts, p2 + (ptrdiff_t)y * i_src, w);
     }
     st.up();
-    qpel_kernel<<<1, 128, 0, g_ctx->stream>>>(st.d, p2 ? st.d + (size_t)h * ts : nullptr, ts, w, h, st.dout());
+    if (st.ok) qpel_kernel<<<1, 128, 0, st.stream()>>>(st.d, p2 ? st.d + (size_t)h * ts : nullptr, ts, w, h, st.dout());
     st.down();
     for (int y = 0; y < h; y++) memcpy(dst + (ptrdiff_t)y * dst_stride, st.hout() + (size_t)y * w, w);
 }
@@ -416,7 +442,6 @@ __global__ void hpel_rows_kernel(const uint8_t *src, int sstride, int width, int
 void t_hpel_filter(uint8_t *dsth, uint8_t *dstv, uint8_t *dstc, uint8_t *src, int stride, int width, int height, int16_t *buf)
 {
     (void)buf; // the C body's int16 scratch row is not needed on the device
-    std::lock_guard<std::mutex> lk(g_mu);
     const int ts = (width + 11 + 15) & ~15, os = (width + 5 + 15) & ~15;
     const size_t in = (size_t)ts * (height + 5), plane = (size_t)os * height;
     Stage st(in, 3 * plane);
@@ -424,7 +449,7 @@ void t_hpel_filter(uint8_t *dsth, uint8_t *dstv, uint8_t *dstc, uint8_t *src, in
     st.up();
     uint8_t *o = st.dout();
     const int threads = 256, blocks = (height * (width + 5) + threads - 1) / threads;
-    hpel_rows_kernel<<<blocks < 2048 ? blocks : 2048, threads, 0, g_ctx->stream>>>(st.d + 2 * ts + 5, ts, width, height, o, o + plane, o + 2 * plane, os);
+    if (st.ok) hpel_rows_kernel<<<blocks < 2048 ? blocks : 2048, threads, 0, st.stream()>>>(st.d + 2 * ts + 5, ts, width, height, o, o + plane, o + 2 * plane, os);
     st.down();
     const uint8_t *h = st.hout();
     for (int y = 0; y < height; y++) {
@@ -453,14 +478,13 @@ __global__ void lowres_rows_kernel(const uint8_t *src, int sstride, int width, i
 void t_frame_init_lowres_core(uint8_t *src0, uint8_t *dst0, uint8_t *dsth, uint8_t *dstv, uint8_t *dstc, int src_stride, int dst_stride,
                               int width, int height)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     const int ts = (2 * width + 2 + 15) & ~15, os = (width + 15) & ~15;
     const size_t in = (size_t)ts * (2 * height + 1), plane = (size_t)os * height;
     Stage st(in, 4 * plane);
     for (int y = 0; y < 2 * height + 1; y++) memcpy(st.h + (size_t)y * ts, src0 + (ptrdiff_t)y * src_stride, 2 * width + 1);
     st.up();
     const int threads = 256, blocks = (width * height + threads - 1) / threads;
-    lowres_rows_kernel<<<blocks < 4096 ? blocks : 4096, threads, 0, g_ctx->stream>>>(st.d, ts, width, height, st.dout(), plane, os);
+    if (st.ok) lowres_rows_kernel<<<blocks < 4096 ? blocks : 4096, threads, 0, st.stream()>>>(st.d, ts, width, height, st.dout(), plane, os);
     st.down();
     uint8_t *dsts[4] = { dst0, dsth, dstv, dstc };
     for (int p = 0; p < 4; p++)
@@ -543,12 +567,11 @@ __global__ void block_stat_kernel(int op, int w, int h, const uint8_t *a, const 
 }
 unsigned long long block_stat(int op, int w, int h, const uint8_t *p1, int s1, const uint8_t *p2, int s2, int *sums)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     Stage st(512, 32);
     pack_tile(st.h, p1, s1, w, h);
     if (p2) pack_tile(st.h + 256, p2, s2, w, h);
     st.up();
-    block_stat_kernel<<<1, 1, 0, g_ctx->stream>>>(op, w, h, st.d, st.d + 256, (unsigned long long *)st.dout());
+    if (st.ok) block_stat_kernel<<<1, 1, 0, st.stream()>>>(op, w, h, st.d, st.d + 256, (unsigned long long *)st.dout());
     st.down();
     if (sums) memcpy(sums, st.hout(), 32);
     unsigned long long v;
@@ -579,23 +602,21 @@ __global__ void chroma_avg_kernel(int op, int w, int h, int p0, int p1, const ui
 }
 void t_mc_chroma(uint8_t *dst, int i_dst, uint8_t *src, int i_src, int mvx, int mvy, int w, int h)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     Stage st(32 * 17, 256);
     const uint8_t *s = src + (ptrdiff_t)(mvy >> 3) * i_src + (mvx >> 3);
     for (int y = 0; y <= h; y++) memcpy(st.h + 32 * y, s + (ptrdiff_t)y * i_src, w + 1);
     st.up();
-    chroma_avg_kernel<<<1, 256, 0, g_ctx->stream>>>(0, w, h, mvx & 7, mvy & 7, st.d, nullptr, st.dout());
+    if (st.ok) chroma_avg_kernel<<<1, 256, 0, st.stream()>>>(0, w, h, mvx & 7, mvy & 7, st.d, nullptr, st.dout());
     st.down();
     for (int y = 0; y < h; y++) memcpy(dst + (ptrdiff_t)y * i_dst, st.hout() + 16 * y, w);
 }
 template <int W, int H> void t_avg(uint8_t *dst, int i_dst, uint8_t *src1, int i_src1, uint8_t *src2, int i_src2, int weight)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     Stage st(512, 256);
     pack_tile(st.h, src1, i_src1, W, H);
     pack_tile(st.h + 256, src2, i_src2, W, H);
     st.up();
-    chroma_avg_kernel<<<1, 256, 0, g_ctx->stream>>>(1, W, H, weight, 0, st.d, st.d + 256, st.dout());
+    if (st.ok) chroma_avg_kernel<<<1, 256, 0, st.stream()>>>(1, W, H, weight, 0, st.d, st.d + 256, st.dout());
     st.down();
     for (int y = 0; y < H; y++) memcpy(dst + (ptrdiff_t)y * i_dst, st.hout() + 16 * y, W);
 }
@@ -603,14 +624,13 @@ template <int W, int H> void t_avg(uint8_t *dst, int i_dst, uint8_t *src1, int i
 // fenc at FENC_STRIDE, fdec at FDEC_STRIDE with its neighbours in place (row -1, column -1, corner)
 template <int N, bool SATD> void intra_x3(uint8_t *fenc, uint8_t *fdec, int res[3])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     Stage st(256 + 64, 3 * sizeof(int));
     pack_tile(st.h, fenc, 16, N, N);
     uint8_t *e = st.h + 256; // IntraEdges layout: [3] corner, [4..4+N) top, [4+N..4+2N) left
     e[3] = fdec[-32 - 1];
     for (int i = 0; i < N; i++) { e[4 + i] = fdec[-32 + i]; e[4 + N + i] = fdec[i * 32 - 1]; }
     st.up();
-    intra_x3_kernel<N><<<1, 32, 0, g_ctx->stream>>>(SATD, st.d + 256, st.d, (int *)st.dout());
+    if (st.ok) intra_x3_kernel<N><<<1, 32, 0, st.stream()>>>(SATD, st.d + 256, st.d, (int *)st.dout());
     st.down();
     memcpy(res, st.hout(), 3 * sizeof(int));
 }
@@ -619,7 +639,7 @@ template <int N, bool SATD> void intra_x3(uint8_t *fenc, uint8_t *fdec, int res[
 
 extern "C" int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf)
 {
-    { std::lock_guard<std::mutex> lk(g_mu); if (ensure_ctx()) return -1; }
+    if (ensure_ctx()) return -1;
     fill_cmp<0>(pixf->sad); fill_cmp<0>(pixf->sad_aligned); fill_cmp<1>(pixf->ssd); fill_cmp<2>(pixf->satd);
     pixf->sa8d[X264_CUDA_PIXEL_16x16] = cmp1<3, 0>; pixf->sa8d[X264_CUDA_PIXEL_8x8] = cmp1<3, 3>; // the only two the C table has (pixel.c:607-608)
     fill_x3<0>(pixf->sad_x3); fill_x4<0>(pixf->sad_x4); fill_x3<2>(pixf->satd_x3); fill_x4<2>(pixf->satd_x4);
@@ -642,7 +662,7 @@ extern "C" int x264_pixel_init_cuda(x264_cuda_pixel_function_t *pixf)
 
 extern "C" int x264_dct_init_cuda(x264_cuda_dct_function_t *d)
 {
-    { std::lock_guard<std::mutex> lk(g_mu); if (ensure_ctx()) return -1; }
+    if (ensure_ctx()) return -1;
     d->sub4x4_dct = t_sub4x4_dct; d->add4x4_idct = t_add4x4_idct; d->sub8x8_dct = t_sub8x8_dct; d->add8x8_idct = t_add8x8_idct;
     d->add8x8_idct_dc = t_add8x8_idct_dc; d->sub16x16_dct = t_sub16x16_dct; d->add16x16_idct = t_add16x16_idct;
     d->add16x16_idct_dc = t_add16x16_idct_dc; d->sub8x8_dct8 = t_sub8x8_dct8; d->add8x8_idct8 = t_add8x8_idct8;
@@ -652,7 +672,7 @@ extern "C" int x264_dct_init_cuda(x264_cuda_dct_function_t *d)
 
 extern "C" int x264_quant_init_cuda(x264_cuda_quant_function_t *q)
 {
-    { std::lock_guard<std::mutex> lk(g_mu); if (ensure_ctx()) return -1; }
+    if (ensure_ctx()) return -1;
     q->quant_8x8 = t_quant_8x8; q->quant_4x4 = t_quant_4x4; q->quant_4x4_dc = t_quant_4x4_dc; q->quant_2x2_dc = t_quant_2x2_dc;
     q->dequant_8x8 = t_dequant_8x8; q->dequant_4x4 = t_dequant_4x4; q->dequant_4x4_dc = t_dequant_4x4_dc;
     return 0;
@@ -660,7 +680,7 @@ extern "C" int x264_quant_init_cuda(x264_cuda_quant_function_t *q)
 
 extern "C" int x264_mc_init_cuda(x264_cuda_mc_functions_t *m)
 {
-    { std::lock_guard<std::mutex> lk(g_mu); if (ensure_ctx()) return -1; }
+    if (ensure_ctx()) return -1;
     m->mc_luma = t_mc_luma; m->get_ref = t_get_ref; m->hpel_filter = t_hpel_filter; m->frame_init_lowres_core = t_frame_init_lowres_core;
     // chroma MC and the bi-prediction averages, in the table's PIXEL_* order (mc.c:379-389)
     m->mc_chroma = t_mc_chroma;
@@ -669,14 +689,10 @@ extern "C" int x264_mc_init_cuda(x264_cuda_mc_functions_t *m)
     return 0;
 }
 
-extern "C" long long x264_cuda_tables_launches(void)
-{
-    std::lock_guard<std::mutex> lk(g_mu);
-    return g_ctx ? g_ctx->launches : 0;
-}
+extern "C" long long x264_cuda_tables_launches(void) { return g_launches.load(); }
+extern "C" const char *x264_cuda_tables_error(void) { return g_failed.load() ? g_fail_msg : nullptr; }
 
 extern "C" void x264_cuda_tables_shutdown(void)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (g_ctx) { x264_cuda_close(g_ctx); g_ctx = nullptr; }
 }
