@@ -46,6 +46,7 @@ extern int16_t *g_cost_mv[52]; /* S/encoder/analyse.c:179 */
 #define N_GRIDSETS 4 /* (source frame, reference frame) pairs with grids in host memory */
 #define MAX_CHUNKS 512
 #define N_EXTRA 8
+#define N_RING 3   /* chunks of macroblock rows resident in host memory per grid set: the one being read, the next one arriving, one spare */
 
 typedef struct {
     x264_frame_t *f; int i_frame, i_poc; /* which host frame content this mirrors */
@@ -57,7 +58,7 @@ typedef struct {
     x264_frame_t *ref; int ref_frame, ref_poc; /* identity of the reference picture */
     int enc_frame, enc_type;                   /* h->fenc->i_frame / slice type the grids were made for; -1: empty */
     long long used;
-    uint16_t *grid;                            /* page-locked: n_mb * GW * GH * 4 */
+    uint16_t *grid;                            /* page-locked ring of N_RING chunks of rows_per_chunk * mb_w macroblock grids (GW * GH * 4 each) */
     x264_cuda_grid_job_t *jobs;                /* page-locked: n_mb (centre + limits of every macroblock) */
     void *fence[MAX_CHUNKS];                   /* completion of each chunk of macroblock rows (NULL: not in flight) */
     uint8_t issued[MAX_CHUNKS];
@@ -81,12 +82,12 @@ static __thread struct {
     gridset_t gs[N_GRIDSETS];
     long long clock;
     x264_cuda_frame_t *denc; x264_frame_t *enc_f; int enc_frame; /* the source picture on the device */
-    int deblock_pending;   /* x264_frame_deblock_row was asked for rows of the current fdec */
+    double t_pin_pending; int deblock_pending;   /* x264_frame_deblock_row was asked for rows of the current fdec */
     x264_frame_t *end_done; int end_done_frame; /* fdec whose end-of-frame pass has run */
     int cost_uploaded[52];
     /* statistics */
     long long n_search, n_extra_hit, n_relaunch, n_percall, n_outside_pred, n_gridsets, n_frame_end, n_left_to_c;
-    double t_grid_issue, t_grid_wait, t_frame_end, t_relaunch, t_open;
+    double t_grid_issue, t_grid_wait, t_frame_end, t_relaunch, t_open, t_alloc, t_alloc_in_issue, t_alloc_in_end;
     /* deferred PSNR / SSIM slabs (see x264_pixel_ssd_wxh below) */
     struct { int y0, h; } ssim_slab[256]; int n_ssim_slab;
 } B;
@@ -112,8 +113,8 @@ static void report(void)
             "taken from the table entry, %lld sub-8x8 searches as one-job device calls, %lld searches left to the reference), %lld frame grid sets, "
             "%lld end-of-frame device passes; %lld kernel launches\n", B.n_search, B.n_relaunch, B.n_extra_hit, B.n_outside_pred, B.n_percall, B.n_left_to_c, B.n_gridsets,
             B.n_frame_end, B.ctx ? x264_cuda_launch_count(B.ctx) : 0);
-    fprintf(stderr, "x264_b200: host time in device calls: open %.1f ms, grid issue %.1f ms, grid wait %.1f ms, recompute %.1f ms, end of frame %.1f ms\n", B.t_open,
-            B.t_grid_issue, B.t_grid_wait, B.t_relaunch, B.t_frame_end);
+    fprintf(stderr, "x264_b200: host time in device calls: open %.1f ms, page-locking and allocation %.1f ms, grid issue %.1f ms, grid wait %.1f ms, recompute %.1f ms, "
+            "end of frame %.1f ms\n", B.t_open, B.t_alloc, B.t_grid_issue - B.t_alloc_in_issue, B.t_grid_wait, B.t_relaunch, B.t_frame_end - B.t_alloc_in_end);
 }
 
 /* Is the back-end in charge of this encoder?  Decided once. */
@@ -204,15 +205,17 @@ static dev_slot_t *slot_take(x264_frame_t *f)
  * plane copies are DMA'd straight from / to it (a 2-D copy through pageable memory costs ~10 ms per 1080p frame) */
 static void pin_frame(x264_t *h, x264_frame_t *f)
 {
-    static void *seen[256];
-    static int n_seen;
+    static __thread void *seen[256];
+    static __thread int n_seen;
     for (int i = 0; i < n_seen; i++) if (seen[i] == f->buffer[0]) return;
     if (n_seen == 256) return;
+    const double t0 = now_ms();
     seen[n_seen++] = f->buffer[0];
     const size_t luma = (size_t)f->i_stride[0] * (f->i_lines[0] + 2 * PADV), chroma = (size_t)f->i_stride[1] * (f->i_lines[1] + 2 * PADV);
     x264_cuda_host_register(f->buffer[0], (h->param.analyse.i_subpel_refine ? 4 : 1) * luma); /* failure just leaves the slower pageable path */
     x264_cuda_host_register(f->buffer[1], chroma);
     x264_cuda_host_register(f->buffer[2], chroma);
+    B.t_alloc += now_ms() - t0; B.t_pin_pending += now_ms() - t0;
 }
 static void upload_picture(x264_cuda_frame_t *d, x264_frame_t *f, int chroma)
 {
@@ -279,6 +282,7 @@ static void frame_end(x264_t *h, x264_frame_t *f)
     B.end_done = f; B.end_done_frame = f->i_frame;
     B.n_frame_end++;
     B.t_frame_end += now_ms() - t0;
+    B.t_alloc_in_end += B.t_pin_pending; B.t_pin_pending = 0;
 }
 static __thread x264_t *g_h; /* the encoder handle, for the hooks whose reference signature does not carry it (one thread) */
 static int frame_hooks_on(x264_t *h) { return b200_on(h) && B.frame_on && h->fdec->b_kept_as_ref && !h->sh.b_mbaff; }
@@ -428,8 +432,9 @@ static void issue_chunk(x264_t *h, gridset_t *g, int c, int src_row)
             j->cy = x264_clip3((mv[1] + 2) >> 2, j->mv_min_fpel[1], j->mv_max_fpel[1]);
         }
     }
+    if (c >= N_RING && g->fence[c - N_RING]) { CK(x264_cuda_fence_wait(B.ctx, g->fence[c - N_RING])); g->fence[c - N_RING] = NULL; } /* the slot's previous occupant */
     CK(x264_cuda_sad_grid_quad(B.ctx, source_on_device(h), slot_for_ref(g->ref)->d, B.radius, g->jobs + mb0, mb1 - mb0,
-                               (uint16_t *)((uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(B.radius) * mb0), 1));
+                               (uint16_t *)((uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(B.radius) * (size_t)(c % N_RING) * g->rows_per_chunk * B.mb_w), 1));
     if (!(g->fence[c] = x264_cuda_fence_record(B.ctx))) die("x264_cuda_fence_record");
     g->issued[c] = 1;
 }
@@ -450,12 +455,18 @@ static gridset_t *gridset_for(x264_t *h, x264_frame_t *ref, int list)
     const int n_mb = B.mb_w * B.mb_h, R = B.radius;
     const size_t per_mb = X264_CUDA_GRID_QUAD_BYTES(R);
     for (int c = 0; c < g->n_chunks; c++) if (g->fence[c]) { CK(x264_cuda_fence_wait(B.ctx, g->fence[c])); g->fence[c] = NULL; }
+    const int rows_per_chunk = x264_clip3(256 / B.mb_w, 1, 4);
+    B.t_pin_pending = 0;
     if (!g->grid) {
-        g->grid = x264_cuda_host_alloc(per_mb * n_mb + 64); /* + room for the last 32-byte load of a window's last row */
+        const double ta = now_ms();
+        /* the macroblock loop is strictly raster order, so only a short ring of row chunks has to be resident: ~15 MB per grid set at
+         * 1080p instead of the whole frame's 166 MB (+ room for the last 32-byte load of a window's last row) */
+        g->grid = x264_cuda_host_alloc(per_mb * rows_per_chunk * B.mb_w * N_RING + 64);
         g->jobs = x264_cuda_host_alloc(sizeof(x264_cuda_grid_job_t) * n_mb);
         g->extra_grid = x264_cuda_host_alloc(per_mb * N_EXTRA + 64);
         g->extra_job = x264_cuda_host_alloc(sizeof(x264_cuda_grid_job_t) * N_EXTRA);
-        if (!g->grid || !g->jobs || !g->extra_grid || !g->extra_job) { fprintf(stderr, "x264_b200: cannot page-lock %zu MB for the candidate grids\n", (per_mb * n_mb) >> 20); exit(3); }
+        if (!g->grid || !g->jobs || !g->extra_grid || !g->extra_job) { fprintf(stderr, "x264_b200: cannot page-lock %zu MB for the candidate grids\n", (per_mb * rows_per_chunk * B.mb_w * N_RING) >> 20); exit(3); }
+        B.t_alloc += now_ms() - ta; B.t_alloc_in_issue += now_ms() - ta;
     }
     g->ref = ref; g->ref_frame = ref->i_frame; g->ref_poc = ref->i_poc; g->enc_frame = h->fenc->i_frame; g->enc_type = h->sh.i_type; g->used = ++B.clock;
     guess_centres(h, ref, list, g);
@@ -463,15 +474,16 @@ static gridset_t *gridset_for(x264_t *h, x264_frame_t *ref, int list)
      * c + 1 goes out when the host starts on chunk c (gridset_wait_row), with its centres refreshed from the vectors the rows above have
      * just been given — the device computes and copies it while the host encodes chunk c. */
     g->list = list;
-    g->rows_per_chunk = x264_clip3(256 / B.mb_w, 1, 4);
+    g->rows_per_chunk = rows_per_chunk;
     g->n_chunks = (B.mb_h + g->rows_per_chunk - 1) / g->rows_per_chunk;
-    if (g->n_chunks > MAX_CHUNKS) { g->rows_per_chunk = (B.mb_h + MAX_CHUNKS - 1) / MAX_CHUNKS; g->n_chunks = (B.mb_h + g->rows_per_chunk - 1) / g->rows_per_chunk; }
+    if (g->n_chunks > MAX_CHUNKS) { fprintf(stderr, "x264_b200: picture too tall (%d macroblock rows)\n", B.mb_h); exit(3); }
     memset(g->issued, 0, sizeof(g->issued));
     for (int k = 0; k < N_EXTRA; k++) { g->extra_job[k].mb_x = -1; g->extra_used[k] = 0; }
     issue_chunk(h, g, 0, -1);
     if (g->n_chunks > 1) issue_chunk(h, g, 1, -1);
     B.n_gridsets++;
     B.t_grid_issue += now_ms() - t0;
+    B.t_alloc_in_issue += B.t_pin_pending; B.t_pin_pending = 0;
     return g;
 }
 /* the host is about to search macroblock row mb_y: its chunk must have arrived; the next chunk is sent on its way */
@@ -521,7 +533,8 @@ static void view_of(grid_view_t *v, const gridset_t *g, int mb_xy, uint64_t mask
 {
     const int R = B.radius;
     v->gw = X264_CUDA_GRID_W(R); v->gh = X264_CUDA_GRID_H(R);
-    v->quad = (const uint64_t *)((const uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(R) * mb_xy);
+    const int per_chunk = g->rows_per_chunk * B.mb_w, c = mb_xy / per_chunk;
+    v->quad = (const uint64_t *)((const uint8_t *)g->grid + X264_CUDA_GRID_QUAD_BYTES(R) * ((size_t)(c % N_RING) * per_chunk + (mb_xy - c * per_chunk)));
     v->gx0 = g->jobs[mb_xy].cx - R; v->gy0 = g->jobs[mb_xy].cy - R;
     v->mask = mask;
 }
