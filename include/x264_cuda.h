@@ -203,6 +203,13 @@ X264_CUDA_API int x264_cuda_sad_grid_quad(x264_cuda_t *ctx, const x264_cuda_fram
                                           const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid, int async);
 X264_CUDA_API int x264_cuda_sad_grid_quad_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
                                               const void *d_jobs, int n_jobs, void *d_grid);
+/* the latency path: no copies — the kernel reads `jobs` from and writes `grid` to page-locked host memory directly, on a high-priority
+ * stream of its own, and the call returns when the grids are in host memory.  The frames must be complete (nothing pending on them). */
+X264_CUDA_API int x264_cuda_sad_grid_quad_direct(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                                 const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid);
+/* size the device ring the asynchronous calls carve their job copies and grids from (default: 64 MB or four calls' worth); a caller
+ * that knows its working set reserves it once, so that the ring never has to drain the stream in the middle of a frame */
+X264_CUDA_API int x264_cuda_grid_ring_reserve(x264_cuda_t *ctx, size_t bytes);
 /* completion markers for asynchronous calls: record returns a fence covering everything queued on the context so far (NULL on failure);
  * wait blocks until it has completed and releases it */
 X264_CUDA_API void *x264_cuda_fence_record(x264_cuda_t *ctx);

@@ -76,7 +76,7 @@ static __thread struct {
     int state; /* 0: undecided, 1: on, -1: off (plain reference) */
     int verbose, me_on, frame_on, check, avx2, reported; /* X264_B200_ME=0 / X264_B200_FRAME=0 switch one of the two hook groups off (diagnosis) */
     x264_cuda_t *ctx;
-    int radius, flags;
+    int radius, flags, chunk_mbs;
     int mb_w, mb_h;
     dev_slot_t slot[N_SLOTS];
     gridset_t gs[N_GRIDSETS];
@@ -136,6 +136,7 @@ static int b200_on(x264_t *h)
     }
     B.mb_w = h->sps->i_mb_width; B.mb_h = h->sps->i_mb_height;
     const int slack = getenv("X264_B200_GRID_SLACK") ? atoi(getenv("X264_B200_GRID_SLACK")) : 8;
+    B.chunk_mbs = getenv("X264_B200_CHUNK_MBS") ? atoi(getenv("X264_B200_CHUNK_MBS")) : 960; /* macroblocks per grid launch (whole rows) */
     B.radius = h->param.analyse.i_me_range + (slack < 2 ? 2 : slack); /* >= merange + 2: the width rounding of me.c:457 */
     if (B.radius > 64) B.radius = 64;
     B.flags = X264_CUDA_FRAME_CHROMA | (h->param.analyse.i_subpel_refine ? X264_CUDA_FRAME_HPEL : 0);
@@ -455,10 +456,11 @@ static gridset_t *gridset_for(x264_t *h, x264_frame_t *ref, int list)
     const int n_mb = B.mb_w * B.mb_h, R = B.radius;
     const size_t per_mb = X264_CUDA_GRID_QUAD_BYTES(R);
     for (int c = 0; c < g->n_chunks; c++) if (g->fence[c]) { CK(x264_cuda_fence_wait(B.ctx, g->fence[c])); g->fence[c] = NULL; }
-    const int rows_per_chunk = x264_clip3(256 / B.mb_w, 1, 4);
+    const int rows_per_chunk = x264_clip3(B.chunk_mbs / B.mb_w, 1, 16);
     B.t_pin_pending = 0;
     if (!g->grid) {
         const double ta = now_ms();
+        CK(x264_cuda_grid_ring_reserve(B.ctx, (size_t)(2.25 * per_mb * n_mb) + (1 << 20))); /* two frames' worth of grids + job copies */
         /* the macroblock loop is strictly raster order, so only a short ring of row chunks has to be resident: ~15 MB per grid set at
          * 1080p instead of the whole frame's 166 MB (+ room for the last 32-byte load of a window's last row) */
         g->grid = x264_cuda_host_alloc(per_mb * rows_per_chunk * B.mb_w * N_RING + 64);
@@ -746,7 +748,7 @@ void x264_me_search_ref(x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, i
                 e->cx = bmx; e->cy = bmy;
                 if (B.verbose > 1) fprintf(stderr, "x264_b200: miss frame %d mb (%d,%d) pixel %d off (%d,%d): centre (%d,%d), needed (%d,%d), mvp (%d,%d)\n", h->fenc->i_frame, bx >> 4,
                                            by >> 4, i_pixel, ox, oy, g->jobs[mb_xy].cx, g->jobs[mb_xy].cy, bmx, bmy, m->mvp[0], m->mvp[1]);
-                CK(x264_cuda_sad_grid_quad(B.ctx, source_on_device(h), slot_for_ref(ref)->d, R, e, 1, (uint16_t *)((uint8_t *)g->extra_grid + X264_CUDA_GRID_QUAD_BYTES(R) * slot), 0));
+                CK(x264_cuda_sad_grid_quad_direct(B.ctx, source_on_device(h), slot_for_ref(ref)->d, R, e, 1, (uint16_t *)((uint8_t *)g->extra_grid + X264_CUDA_GRID_QUAD_BYTES(R) * slot)));
                 B.n_relaunch++;
                 B.t_relaunch += now_ms() - t0;
             } else

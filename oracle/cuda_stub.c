@@ -165,3 +165,6 @@ int x264_cuda_me_search(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x
     return 0;
 }
 int x264_cuda_host_register(void *p, size_t bytes) { (void)p; (void)bytes; return 0; }
+int x264_cuda_sad_grid_quad_direct(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius, const x264_cuda_grid_job_t *jobs,
+                                   int n_jobs, uint16_t *grid) { return x264_cuda_sad_grid_quad(ctx, fenc, fref, radius, jobs, n_jobs, grid, 0); }
+int x264_cuda_grid_ring_reserve(x264_cuda_t *ctx, size_t bytes) { (void)ctx; (void)bytes; return 0; }

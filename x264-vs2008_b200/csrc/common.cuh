@@ -33,6 +33,7 @@ struct x264_cuda_t {
     void *h_stage; size_t h_stage_size; // pinned
     // asynchronous grid calls: device ring the per-call job copies and grids are carved from, and a pool of fence events
     uint8_t *d_ring; size_t ring_size, ring_pos;
+    cudaStream_t aux_stream;      // high-priority stream of the direct (zero-copy) grid call
     cudaEvent_t fence_pool[256]; int n_fence_pool;
 };
 

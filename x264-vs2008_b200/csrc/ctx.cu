@@ -65,6 +65,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums);
     cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_ring);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     for (int i = 0; i < ctx->n_fence_pool; i++) cudaEventDestroy(ctx->fence_pool[i]);
     cudaStreamDestroy(ctx->own_stream);
     free(ctx);
@@ -128,6 +129,20 @@ void *x264_cuda_grid_ring(x264_cuda_t *ctx, size_t bytes)
     void *p = ctx->d_ring + ctx->ring_pos;
     ctx->ring_pos += bytes;
     return p;
+}
+
+// Callers that know their working set (the live encoder: two frames' worth of grids) size the ring once, so that it wraps about once
+// per frame pair — when everything older has long been consumed — instead of draining the stream in the middle of a frame.
+extern "C" int x264_cuda_grid_ring_reserve(x264_cuda_t *ctx, size_t bytes)
+{
+    x264_cuda_enter(ctx);
+    if (bytes <= ctx->ring_size) return 0;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_ring);
+    ctx->d_ring = nullptr; ctx->ring_size = ctx->ring_pos = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_ring, bytes));
+    ctx->ring_size = bytes;
+    return 0;
 }
 
 // Fences: completion markers on the context's stream for the asynchronous entry points.

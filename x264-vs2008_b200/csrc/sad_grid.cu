@@ -173,3 +173,34 @@ extern "C" int x264_cuda_sad_grid_quad(x264_cuda_t *ctx, const x264_cuda_frame_t
     if (!async) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+// One-shot grids with NO copies: the kernel reads the jobs from and writes the grids to page-locked host memory itself (mapped into the
+// device's address space), on a high-priority stream of its own.  This is the latency path of the live encoder — a macroblock whose
+// guessed centre was off needs its grid NOW, and must neither queue behind the asynchronous chunk traffic of the context's main stream
+// nor behind other encoder threads' copies on the shared copy engines.  20 KB per macroblock cross PCIe as 256-byte posted writes.
+extern "C" int x264_cuda_sad_grid_quad_direct(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref, int radius,
+                                              const x264_cuda_grid_job_t *jobs, int n_jobs, uint16_t *grid)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    if (fenc->g.stride != fref->g.stride || fenc->g.lines != fref->g.lines || radius < 1 || radius > 64) {
+        snprintf(ctx->err, 256, "x264_cuda_sad_grid: fenc/fref geometry mismatch or radius not in 1..64");
+        return -1;
+    }
+    if (!ctx->aux_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi); // hi is the numerically lowest = highest priority
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+    }
+    void *d_jobs = nullptr, *d_grid = nullptr;
+    if (cudaHostGetDevicePointer(&d_jobs, (void *)jobs, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_grid, (void *)grid, 0) != cudaSuccess) {
+        cudaGetLastError();
+        snprintf(ctx->err, 256, "x264_cuda_sad_grid_quad_direct: jobs and grid must be page-locked (x264_cuda_host_alloc)");
+        return -1;
+    }
+    GridGeo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
+    sad_grid_kernel<true><<<(n_jobs + 3) / 4, 128, 0, ctx->aux_stream>>>(geo, (const x264_cuda_grid_job_t *)d_jobs, n_jobs, radius, (uint16_t *)d_grid);
+    LAUNCH_CHECK(ctx, "sad_grid_kernel (direct)");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->aux_stream));
+    return 0;
+}
