@@ -28,6 +28,14 @@ extern "C" int x264_cuda_open(x264_cuda_t **pctx, int device)
         snprintf(g_open_error, 256, "x264_cuda: device %d out of range (0..%d)", device, n - 1);
         return -1;
     }
+    // how host threads wait inside synchronising calls: the CUDA default spins; with many encoder threads per device
+    // (integration/x264_b200_gops.c) yielding or sleeping waiters leave the cores and the driver's locks to the threads that have work.
+    // Must be chosen before the device's context exists, hence an environment switch read by the first open of the process.
+    if (const char *sch = getenv("X264_CUDA_SCHED")) {
+        const unsigned fl = !strcmp(sch, "blocking") ? cudaDeviceScheduleBlockingSync : !strcmp(sch, "yield") ? cudaDeviceScheduleYield
+                          : !strcmp(sch, "spin") ? cudaDeviceScheduleSpin : cudaDeviceScheduleAuto;
+        if (cudaSetDeviceFlags(fl) != cudaSuccess) cudaGetLastError(); // a context that already exists keeps its mode
+    }
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
         return x264_cuda_fail(nullptr, "cudaSetDevice", e);
