@@ -130,7 +130,7 @@ X264_CUDA_API long long x264_cuda_tables_launches(void);                  /* ker
  * checks it once per frame and makes x264_encoder_encode() return -1 after x264_log(h, X264_LOG_ERROR, ...) — the reference's own
  * convention (S/x264.c:759-762).  Entries may be called concurrently from any number of host threads (one context per thread). */
 X264_CUDA_API const char *x264_cuda_tables_error(void);
-X264_CUDA_API void x264_cuda_tables_shutdown(void);                       /* releases the shared context */
+X264_CUDA_API void x264_cuda_tables_shutdown(void);                       /* closes every thread's table context (no entry may be running) */
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,8 @@ std::mutex g_reg_mu;                 // guards the registry only (taken once per
 std::vector<x264_cuda_t *> g_all_ctx;
 std::atomic<long long> g_launches{0};
 thread_local x264_cuda_t *t_ctx = nullptr;
+thread_local int t_gen = 0;          // registry generation t_ctx belongs to (x264_cuda_tables_shutdown starts a new one)
+std::atomic<int> g_gen{0};
 #define g_ctx t_ctx
 
 // The table signatures cannot report failure (S/common/pixel.h:26-28).  A device error is recorded ONCE here (sticky), every later entry
@@ -39,17 +41,19 @@ void fail(const char *what)
         if (getenv("X264_CUDA_TABLES_ABORT")) abort(); // opt-in: die at the point of failure (debugging)
     }
 }
-void close_all() { for (x264_cuda_t *c : g_all_ctx) x264_cuda_close(c); g_all_ctx.clear(); }
 
 int ensure_ctx()
 {
     if (g_failed.load(std::memory_order_relaxed)) return -1;
+    if (g_ctx && t_gen != g_gen.load(std::memory_order_acquire)) g_ctx = nullptr; // closed by x264_cuda_tables_shutdown on another thread
     if (g_ctx) { x264_cuda_enter(g_ctx); return 0; } // this thread may never have selected the device (X264_CUDA_DEVICE != 0)
     const char *e = getenv("X264_CUDA_DEVICE");
     if (x264_cuda_open(&g_ctx, e ? atoi(e) : 0) != 0) { g_ctx = nullptr; fail("x264_cuda_open"); return -1; }
     std::lock_guard<std::mutex> lk(g_reg_mu);
-    if (g_all_ctx.empty()) atexit(close_all);
+    // no atexit hook: by the time exit handlers run the CUDA runtime may already be torn down (a close then faults); the process's
+    // end releases everything, and x264_cuda_tables_shutdown() is there for callers that want an orderly release earlier
     g_all_ctx.push_back(g_ctx);
+    t_gen = g_gen.load(std::memory_order_acquire);
     return 0;
 }
 
@@ -694,5 +698,10 @@ extern "C" const char *x264_cuda_tables_error(void) { return g_failed.load() ? g
 
 extern "C" void x264_cuda_tables_shutdown(void)
 {
-    if (g_ctx) { x264_cuda_close(g_ctx); g_ctx = nullptr; }
+    // closes every thread's context; call it when no thread is inside a table entry (threads that call an entry later open a new one)
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (x264_cuda_t *c : g_all_ctx) x264_cuda_close(c);
+    g_all_ctx.clear();
+    g_gen.fetch_add(1, std::memory_order_release);
+    g_ctx = nullptr;
 }
