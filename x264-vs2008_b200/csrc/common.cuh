@@ -29,6 +29,7 @@ struct x264_cuda_t {
     int *d_deblock_progress; int deblock_rows; void *d_deblock_recs; size_t d_deblock_recs_size;   // per-row progress counters of x264_cuda_frame_deblock
     int resid_no_dct8;   // one-shot hint from x264_cuda_residual_inter to its _dev call
     void *d_scratch; size_t d_scratch_size; // kernel-private scratch (TESA candidate lists)
+    int *d_mb_ticket;    // work counter of the persistent macroblock-batched search kernel
     void *d_stage; size_t d_stage_size;
     void *h_stage; size_t h_stage_size; // pinned
     // asynchronous grid calls: device ring the per-call job copies and grids are carved from, and a pool of fence events

@@ -68,6 +68,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_qt);
     cudaFree(ctx->d_stage);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_mb_ticket);
     cudaFree(ctx->d_deblock_progress);
     cudaFree(ctx->d_deblock_recs);
     cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums);

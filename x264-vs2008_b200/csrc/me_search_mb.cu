@@ -524,6 +524,437 @@ me_search_mb_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int
     }
 }
 
+
+// =====================================================================================================================
+// Third form (the default): WARP-SPECIALISED PERSISTENT KERNEL.  The profile of the one-warp-does-everything kernel shows a warp spending
+// ~60 % of its residency in the short latency-bound phases before and after the scan (job, predictor SADs, cost-table gathers, ring
+// preload) while holding the 168 registers only the scan needs, so the ALU pipe idles half the time at 3 warps per scheduler.  Here one CTA
+// per SM runs 4 PRODUCER warps on 56 registers and 8 SCAN warps on 224 (setmaxnreg moves the registers between the warpgroups):
+//   producer : takes the next macroblock from a global ticket, runs the predictor stage, seeds, windows, pass grouping and builds the
+//              per-pass tables — y-cost word per (row, partition), x-cost word per (chunk, partition, lane) — into a shared-memory slot;
+//   scanner  : waits for a full slot (mbarrier), scans the union window exactly like scan_union above with every table coming from the
+//              slot, reduces, writes the result and hands the slot back.  It never waits on a global-memory dependency chain other than
+//              its own reference rows, which it prefetches into L1 one column chunk / one slot ahead.
+// Each producer feeds two scanners, two slots each (ring).  Results are identical by construction: same windows, same keys.
+#define V3_PROD 8      // producer warps (setmaxnreg works on whole warpgroups of four)
+#define V3_CONS 8      // scan warps: two per scheduler — the scan loop alone saturates the math issue port at that (scratch/scanbench.cu)
+#define V3_FEED 1      // scanners fed by one producer
+#define V3_SLOTS 2
+#define V3_MAX_UW 64   // two 32-column chunks per pass; wider unions are split into per-partition passes
+#define V3_UNION_SLACK 15 // rows a pass's union may exceed 2*me_range+1 by
+#define V3_PROD_REGS 48 // 8 x 32 x 48 + 8 x 32 x 208 = 65536 = the 128 registers x 512 threads the CTA is launched with
+#define V3_CONS_REGS 208
+#define V3_FREG_ROWS 16 // source-macroblock rows a scanner keeps in registers; the others are re-read from the slot (uniform LDS.128)
+
+struct __align__(16) SlotHead {
+    uint32_t F[16][4];   // source macroblock
+    int seed[NP][3];     // bmx, bmy, bcost after the predictor stage
+    int ux0, uy0, uwidth, urows;
+    unsigned group, mask; // partitions of this pass / of the macroblock
+    int jb;              // job index; < 0: no more work for this scanner
+    int first, last;     // first / last pass of the macroblock
+    int mb_x, mb_y, pad;
+};
+#define V3_CXP_BYTES (2 * NP * 32 * 2) // x costs as uint16 (0xffff: outside the partition's window)
+#define V3_TILE_PITCH 112              // bytes per staged reference row: 15 (alignment) + V3_MAX_UW + 19 (16-byte strip + funnel word) rounded up to 16
+#define V3_TILE_EXTRA 18               // rows below the union: 15 of the macroblock + up to 3 from folding a narrow chunk into row segments
+__host__ __device__ inline size_t v3_cyt_bytes(int max_ur) { return (size_t)(max_ur + 4) * 12 * 4; }
+__host__ __device__ inline size_t v3_slot_bytes(int max_ur)
+{
+    return sizeof(SlotHead) + V3_CXP_BYTES + v3_cyt_bytes(max_ur) + (size_t)(max_ur + V3_TILE_EXTRA) * V3_TILE_PITCH;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) { while (!mbar_test(b, parity)) { } }
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *b, uint32_t parity) { while (!mbar_test(b, parity)) __nanosleep(64); } // a waiter that is ahead
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+// a shared-memory read the compiler must repeat where it is written (it would otherwise hoist the 64 source words into registers)
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// the lane tiling of a column chunk (shared by the table builder and the scan): a full chunk is 32 columns x 1 row segment,
+// a narrow tail chunk is folded to 16x2 or 8x4 (columns x row segments)
+__device__ __forceinline__ void chunk_tiling(int uwidth, int c0, int lane, int &cw, int &segs, int &lcol, int &seg)
+{
+    const int rem = uwidth - c0;
+    cw = rem > 16 ? 32 : rem > 8 ? 16 : 8; segs = 32 / cw;
+    lcol = lane & (cw - 1); seg = lane / cw;
+}
+
+// L1 prefetch of a chunk's window tile: (rows + 15) rows x (cw + 15) bytes, at most two 128-byte lines per row
+__device__ __forceinline__ void prefetch_tile(const uint8_t *ref0, int stride, int ux0, int uy0, int uwidth, int urows, int c0, int lane)
+{
+    int cw, segs, lcol, seg;
+    chunk_tiling(uwidth, c0, lane, cw, segs, lcol, seg);
+    const int seg_rows = (urows + segs - 1) / segs;
+    const uint8_t *t0 = ref0 + (ptrdiff_t)uy0 * stride + ux0 + c0;
+    for (int r = lane; r < seg_rows * segs + 15; r += 32) {
+        prefetch_l1(t0 + (size_t)r * stride);
+        prefetch_l1(t0 + (size_t)r * stride + cw + 16);
+    }
+}
+
+// ---- producer: everything of one macroblock up to its per-partition windows (the legacy kernel's first half); returns the partition
+// mask, 0 when the job was rejected (its result is written here)
+__device__ __forceinline__ unsigned v3_setup(WarpSmem &S, const Geo &geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int jb,
+                                             const int16_t *const *__restrict__ cost_tabs, int me_range,
+                                             x264_cuda_me_mb_result_t *__restrict__ results, int lane, const int16_t *&tab, const uint8_t *&ref0)
+{
+    const int stride = geo.stride;
+    __syncwarp();
+    for (int i = lane; i < (int)(sizeof(x264_cuda_me_mb_job_t) / 4); i += 32) ((uint32_t *)&S.job)[i] = __ldg((const uint32_t *)(jobs + jb) + i);
+    __syncwarp();
+    const x264_cuda_me_mb_job_t &job = S.job;
+    tab = cost_tabs[job.qp > 51 ? 51 : job.qp] + 2 * 4 * 2048;
+    const int x_min = job.mv_min_fpel[0], y_min = job.mv_min_fpel[1];
+    const int x_max = job.mv_max_fpel[0], y_max = job.mv_max_fpel[1];
+    const unsigned mask = job.part_mask & ((1u << NP) - 1);
+    int bad = x_min > 0 || x_max < 0 || y_min > 0 || y_max < 0;
+    if (lane < NP && (mask >> lane & 1)) {
+        const int lim = 2 * 4 * 2048 - 8;
+        bad |= max(abs(4 * x_min - job.mvp[lane][0]), abs(4 * x_max - job.mvp[lane][0])) > lim;
+        bad |= max(abs(4 * y_min - job.mvp[lane][1]), abs(4 * y_max - job.mvp[lane][1])) > lim;
+    }
+    const int n_ext = min(max((int)job.i_mvc[0] - X264_CUDA_ME_MB_MVC, 0), X264_CUDA_ME_MB_MVC16_EXTRA);
+    if (lane >= 1 && lane < NP && lane - 1 < n_ext) bad |= job.i_mvc[lane] > X264_CUDA_ME_MB_MVC - 1;
+    if (__any_sync(0xffffffffu, bad) || !mask) {
+        if (lane < NP) { x264_cuda_me_result_t r = { 0, 0, -1, 0, 0, -1 }; results[jb].part[lane] = r; }
+        return 0;
+    }
+    const uint8_t *fe = geo.fenc + (size_t)job.mb_y * 16 * stride + job.mb_x * 16;
+    ref0 = geo.fref + (size_t)job.mb_y * 16 * stride + job.mb_x * 16;
+    for (int i = lane; i < 64; i += 32) S.F[i >> 2][i & 3] = __ldg((const uint32_t *)(fe + (size_t)(i >> 2) * stride) + (i & 3));
+    __syncwarp();
+    if (!(job.flags & X264_CUDA_ME_SEEDED)) {
+        for (int idx = lane; idx < NP * NCAND; idx += 32) {
+            const int p = idx / NCAND, c = idx - p * NCAND;
+            int cx = 0, cy = 0, valid = (mask >> p & 1);
+            const int n_mvc = min((int)job.i_mvc[p], X264_CUDA_ME_MB_MVC);
+            if (c == 0) {
+                cx = (clip3i(job.mvp[p][0], x_min * 4, x_max * 4) + 2) >> 2;
+                cy = (clip3i(job.mvp[p][1], y_min * 4, y_max * 4) + 2) >> 2;
+            } else if (c <= X264_CUDA_ME_MB_MVC) {
+                const int mx = (job.mvc[p][c - 1][0] + 2) >> 2, my = (job.mvc[p][c - 1][1] + 2) >> 2;
+                valid = valid && (c - 1 < n_mvc) && (mx | my) != 0;
+                cx = clip3i(mx, x_min, x_max); cy = clip3i(my, y_min, y_max);
+            }
+            S.pc_x[idx] = cx; S.pc_y[idx] = valid ? cy : (1 << 20);
+        }
+        for (int i = lane; i < NP * NCAND * 4; i += 32) (&S.quad[0][0])[i] = 0;
+        __syncwarp();
+#pragma unroll 1
+        for (int u = 0; u < 3; u++) { // 6 candidates x 16 (partition, quadrant) pairs = 96 uniform 8x8 SADs, three per lane
+            const int t = lane + 32 * u, c = t >> 4;
+            int p, q;
+            pair_pq(t & 15, p, q);
+            const int idx = p * NCAND + c;
+            if (S.pc_y[idx] != (1 << 20))
+                S.quad[idx][q] = sad_quad(S.F, q, ref0 + (ptrdiff_t)((q >> 1) * 8 + S.pc_y[idx]) * stride + (q & 1) * 8 + S.pc_x[idx], stride);
+        }
+        __syncwarp();
+        if (lane < NP) {
+            int mvc_cost[NCAND]; // all the table gathers first (one round trip), then the sequential strict '<' in candidate order
+#pragma unroll
+            for (int c = 0; c < NCAND; c++) {
+                const int idx = lane * NCAND + c;
+                const bool on = c != 0 && S.pc_y[idx] != (1 << 20);
+                mvc_cost[c] = on ? tab[(S.pc_x[idx] << 2) - job.mvp[lane][0]] + tab[(S.pc_y[idx] << 2) - job.mvp[lane][1]] : 0;
+            }
+            int bc = COST_MAX + 1, bx = 0, by = 0;
+#pragma unroll
+            for (int c = 0; c < NCAND; c++) {
+                const int idx = lane * NCAND + c;
+                if (S.pc_y[idx] == (1 << 20)) continue;
+                const int v = S.quad[idx][0] + S.quad[idx][1] + S.quad[idx][2] + S.quad[idx][3] + mvc_cost[c];
+                if (v < bc) { bc = v; bx = S.pc_x[idx]; by = S.pc_y[idx]; }
+            }
+            S.seed[lane][0] = bx; S.seed[lane][1] = by; S.seed[lane][2] = bc;
+        }
+        if (n_ext > 0 && (mask & 1)) seed_p0_wide(S, tab, ref0, stride, n_ext, x_min, x_max, y_min, y_max, lane);
+    } else if (lane < NP) {
+        S.seed[lane][0] = clip3i(job.seed_mv[lane][0], x_min, x_max);
+        S.seed[lane][1] = clip3i(job.seed_mv[lane][1], y_min, y_max);
+        S.seed[lane][2] = job.seed_cost[lane];
+    }
+    __syncwarp();
+    if (lane < NP) {
+        int min_x = 0, min_y = 0, width = 0, rows = 0;
+        if (mask >> lane & 1) {
+            const int bmx = S.seed[lane][0], bmy = S.seed[lane][1];
+            min_x = max(bmx - me_range, x_min); min_y = max(bmy - me_range, y_min);
+            const int max_x = min(bmx + me_range, x_max), max_y = min(bmy + me_range, y_max);
+            width = (max_x - min_x + 3) & ~3; rows = max_y - min_y + 1;
+        }
+        S.win[lane][0] = min_x; S.win[lane][1] = min_y; S.win[lane][2] = width; S.win[lane][3] = rows;
+    }
+    __syncwarp();
+    return mask;
+}
+
+// ---- producer: the tables of one pass into a slot
+__device__ __forceinline__ void v3_fill(SlotHead &H, uint16_t *cxp, uint32_t (*cyt)[12], uint8_t *tile, const WarpSmem &S, const int16_t *tab, const uint8_t *ref0,
+                                        int stride, int jb, unsigned mask, unsigned group, int first, int last, int ux0, int uy0, int uwidth, int urows, int lane)
+{
+    const x264_cuda_me_mb_job_t &job = S.job;
+    for (int i = lane; i < 64; i += 32) (&H.F[0][0])[i] = (&S.F[0][0])[i];
+    if (lane < NP * 3) (&H.seed[0][0])[lane] = (&S.seed[0][0])[lane];
+    if (lane == 0) {
+        H.ux0 = ux0; H.uy0 = uy0; H.uwidth = uwidth; H.urows = urows; H.group = group; H.mask = mask; H.jb = jb; H.first = first; H.last = last;
+        H.mb_x = job.mb_x; H.mb_y = job.mb_y;
+    }
+    {   // stage the pass's reference window in the slot: rows uy0 .. uy0+urows+17, 16-byte units from the aligned-down left edge (cp.async:
+        // global -> shared without registers; the copies fly while the cost tables below are gathered)
+        const int o = ux0 & 15;
+        const uint8_t *g0 = ref0 + (ptrdiff_t)uy0 * stride + (ux0 - o);
+        const int units = (o + uwidth + 19 + 15) >> 4, n = (urows + V3_TILE_EXTRA) * units;
+        const uint32_t t0 = smem_u32(tile);
+        for (int i = lane; i < n; i += 32) {
+            const int r = i / units, u = i - r * units;
+            cp_async16(t0 + r * V3_TILE_PITCH + u * 16, g0 + (size_t)r * stride + u * 16);
+        }
+    }
+    {   // y-cost words, all (row, partition) pairs flattened over the 32 lanes, eight gathers in flight per lane
+        const int n = (urows + 3) * NP;
+        for (int i0 = lane; i0 < n; i0 += 32 * 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = min(i0 + 32 * k, n - 1), r = i / NP, p = i - r * NP;
+                const int wy0 = S.win[p][1] - uy0, wy1 = wy0 + S.win[p][3];
+                const bool in = (group >> p & 1) && r >= wy0 && r < wy1;
+                v[k] = in ? (uint32_t)tab[((uy0 + r) << 2) - job.mvp[p][1]] : INVALID_COST;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = i0 + 32 * k, r = i / NP, p = i - r * NP;
+                if (i < n) cyt[r][p] = (v[k] << KEY_SHIFT) | ((uint32_t)min(r, 255) << 2);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int c0 = 0, chunk = 0; c0 < uwidth; c0 += 32, chunk++) { // x costs per (chunk, partition, lane)
+        int cw, segs, lcol, seg;
+        chunk_tiling(uwidth, c0, lane, cw, segs, lcol, seg);
+        const int col = c0 + lcol;
+        const int mx = ux0 + min(col, uwidth - 1);
+        uint32_t v[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const int wx0 = S.win[p][0], ww = S.win[p][2];
+            const bool in = (group >> p & 1) && col < uwidth && mx >= wx0 && mx < wx0 + ww;
+            v[p] = in ? (uint32_t)(uint16_t)tab[(mx << 2) - job.mvp[p][0]] : 0xffffu;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) cxp[(chunk * NP + p) * 32 + lane] = (uint16_t)v[p];
+    }
+    cp_async_wait_all();
+}
+
+// ---- scanner: the exhaustive pass over one slot's union window (scan_union with the tables in shared memory)
+__device__ __forceinline__ void load_row16_s(uint32_t (&dst)[4], const uint32_t *p, int sh)
+{
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = p[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
+__device__ __forceinline__ void v3_scan(const SlotHead &H, const uint16_t *cxp_tab, const uint32_t (*cyt)[12], const uint8_t *tile, int lane, uint32_t (&best)[NP])
+{
+    const int ux0 = H.ux0, uwidth = H.uwidth, urows = H.urows;
+    const uint4 *F4 = (const uint4 *)&H.F[0][0];
+    const uint32_t F4s = smem_u32(F4);
+    uint4 F[16];
+#pragma unroll
+    for (int y = 0; y < V3_FREG_ROWS; y++) F[y] = F4[y];
+    for (int c0 = 0, chunk = 0; c0 < uwidth; c0 += 32, chunk++) {
+        int cw, segs, lcol, seg;
+        chunk_tiling(uwidth, c0, lane, cw, segs, lcol, seg);
+        const int col = c0 + lcol;
+        const int seg_rows = (urows + segs - 1) / segs;
+        uint32_t cxp[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const uint32_t v = cxp_tab[(chunk * NP + p) * 32 + lane];
+            cxp[p] = ((v == 0xffffu ? INVALID_COST : v) << KEY_SHIFT) | (uint32_t)chunk;
+        }
+        const int rbeg = seg * seg_rows;
+        const int xb = (ux0 & 15) + min(col, uwidth - 1); // byte offset of this lane's strip in a staged row
+        const int sh = (xb & 3) * 8;
+        const uint32_t *pr = (const uint32_t *)(tile + (size_t)rbeg * V3_TILE_PITCH + (xb & ~3));
+        uint32_t R[16][4];
+#pragma unroll
+        for (int y = 0; y < 15; y++) load_row16_s(R[y], pr + y * (V3_TILE_PITCH / 4), sh);
+        for (int base = 0; base < seg_rows; base += 16) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int r = base + j;
+                if (r >= seg_rows) break; // warp-uniform
+                load_row16_s(R[(j + 15) % 16], pr + (r + 15) * (V3_TILE_PITCH / 4), sh);
+                const uint4 *cy4 = (const uint4 *)&cyt[rbeg + r][0];
+                const uint4 ca = cy4[0], cb = cy4[1], cc = cy4[2];
+                uint32_t tl = 0, tr = 0, bl = 0, br = 0, tl2 = 0, tr2 = 0, bl2 = 0, br2 = 0;
+#pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    uint4 f, g;
+                    if (y < V3_FREG_ROWS) f = F[y]; else f = lds128(F4s + 16 * y);
+                    if (y + 8 < V3_FREG_ROWS) g = F[y + 8]; else g = lds128(F4s + 16 * (y + 8));
+                    tl = sad4_acc(f.x, R[(j + y) % 16][0], tl); tr = sad4_acc(f.z, R[(j + y) % 16][2], tr);
+                    bl = sad4_acc(g.x, R[(j + y + 8) % 16][0], bl); br = sad4_acc(g.z, R[(j + y + 8) % 16][2], br);
+                    tl2 = sad4_acc(f.y, R[(j + y) % 16][1], tl2); tr2 = sad4_acc(f.w, R[(j + y) % 16][3], tr2);
+                    bl2 = sad4_acc(g.y, R[(j + y + 8) % 16][1], bl2); br2 = sad4_acc(g.w, R[(j + y + 8) % 16][3], br2);
+                }
+                tl += tl2; tr += tr2; bl += bl2; br += br2;
+                const uint32_t top = tl + tr, bot = bl + br, lft = tl + bl, rgt = tr + br, all = top + bot;
+#define UPD(p, sad, cy) best[p] = min(best[p], __umul24((sad), 1u << KEY_SHIFT) + cxp[p] + (cy))
+                UPD(0, all, ca.x); UPD(1, top, ca.y); UPD(2, bot, ca.z); UPD(3, lft, ca.w); UPD(4, rgt, cb.x);
+                UPD(5, tl, cb.y); UPD(6, tr, cb.z); UPD(7, bl, cb.w); UPD(8, br, cc.x);
+#undef UPD
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__((V3_PROD + V3_CONS) * 32, 1)
+me_search_mb3_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int n_jobs, const int16_t *const *__restrict__ cost_tabs, int me_range,
+                     int max_ur, x264_cuda_me_mb_result_t *__restrict__ results)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[]; // V3_CONS x V3_SLOTS slots | producers' WarpSmem | mbarriers
+    const size_t slot_bytes = v3_slot_bytes(max_ur);
+    WarpSmem *s_prod = (WarpSmem *)(s_dyn + slot_bytes * V3_CONS * V3_SLOTS);
+    uint64_t *s_full = (uint64_t *)(s_prod + V3_CONS / V3_FEED), *s_empty = s_full + V3_CONS * V3_SLOTS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = geo.stride;
+    if (threadIdx.x < V3_CONS * V3_SLOTS) { mbar_init(s_full + threadIdx.x, 1); mbar_init(s_empty + threadIdx.x, 1); }
+    __syncthreads();
+#define SLOT_HEAD(i) (*(SlotHead *)(s_dyn + slot_bytes * (i)))
+#define SLOT_CXP(i) ((uint16_t *)(s_dyn + slot_bytes * (i) + sizeof(SlotHead)))
+#define SLOT_CYT(i) ((uint32_t (*)[12])(s_dyn + slot_bytes * (i) + sizeof(SlotHead) + V3_CXP_BYTES))
+#define SLOT_TILE(i) (s_dyn + slot_bytes * (i) + sizeof(SlotHead) + V3_CXP_BYTES + v3_cyt_bytes(max_ur))
+    if (warp < V3_PROD) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V3_PROD_REGS));
+        if (warp < V3_CONS / V3_FEED) {
+            WarpSmem &S = s_prod[warp];
+            int kf[V3_FEED]; // slots filled so far for each of this producer's scanners (warp * V3_FEED + e)
+#pragma unroll
+            for (int e = 0; e < V3_FEED; e++) kf[e] = 0;
+            // static work split that keeps neighbours together: CTA b takes the batches b, b + grid, ... of V3_CONS consecutive macroblocks,
+            // scanner c the c-th of each — the window tiles in flight on an SM overlap, so the reference rows are shared in L1
+            for (int j0 = blockIdx.x * V3_CONS + warp * V3_FEED; j0 < n_jobs; j0 += gridDim.x * V3_CONS) {
+#pragma unroll
+                for (int e = 0; e < V3_FEED; e++) {
+                    const int jb = j0 + e;
+                    if (jb >= n_jobs) break;
+                    {   // this producer's macroblock after the next: its job record towards L2 now; the next one's source rows (its record
+                        // came in a turn ago)
+                        const int jn = e + 1 < V3_FEED ? jb + 1 : j0 + gridDim.x * V3_CONS;
+                        const int jn2 = e + 2 < V3_FEED ? jb + 2 : j0 + gridDim.x * V3_CONS + (e + 2 - V3_FEED);
+                        if (jn2 < n_jobs && lane < 3) prefetch_l2((const uint8_t *)(jobs + jn2) + 128 * lane);
+                        if (jn < n_jobs) {
+                            const uint32_t pos = __ldg((const uint32_t *)(jobs + jn)); // mb_x | mb_y << 16
+                            if (lane < 16) prefetch_l2(geo.fenc + ((size_t)(pos >> 16) * 16 + lane) * stride + (pos & 0xffff) * 16);
+                        }
+                    }
+                    const int16_t *tab; const uint8_t *ref0;
+                    const unsigned mask = v3_setup(S, geo, jobs, jb, cost_tabs, me_range, results, lane, tab, ref0);
+                    if (!mask) continue;
+                    unsigned todo = mask;
+                    int first = 1;
+                    while (todo) { // pass grouping: all partitions over the union of their windows when it is compact, else one by one
+                        int ux0 = 1 << 20, uy0 = 1 << 20, ux1 = -(1 << 20), uy1 = -(1 << 20);
+                        if (lane < NP && (todo >> lane & 1)) { ux0 = S.win[lane][0]; uy0 = S.win[lane][1]; ux1 = ux0 + S.win[lane][2]; uy1 = uy0 + S.win[lane][3]; }
+                        ux0 = __reduce_min_sync(0xffffffffu, ux0); uy0 = __reduce_min_sync(0xffffffffu, uy0);
+                        ux1 = __reduce_max_sync(0xffffffffu, ux1); uy1 = __reduce_max_sync(0xffffffffu, uy1);
+                        unsigned group = todo;
+                        if (ux1 - ux0 > V3_MAX_UW || uy1 - uy0 > max_ur) {
+                            const int p = __ffs(todo) - 1;
+                            group = 1u << p;
+                            ux0 = S.win[p][0]; uy0 = S.win[p][1]; ux1 = ux0 + S.win[p][2]; uy1 = uy0 + S.win[p][3];
+                        }
+                        todo &= ~group;
+                        const int si = (warp * V3_FEED + e) * V3_SLOTS + kf[e] % V3_SLOTS;
+                        mbar_wait_relaxed(s_empty + si, ((kf[e] / V3_SLOTS) & 1) ^ 1);
+                        v3_fill(SLOT_HEAD(si), SLOT_CXP(si), SLOT_CYT(si), SLOT_TILE(si), S, tab, ref0, stride, jb, mask, group, first, todo == 0, ux0, uy0, ux1 - ux0, uy1 - uy0, lane);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s_full + si);
+                        kf[e]++;
+                        first = 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < V3_FEED; e++) { // no more work: tell the scanners
+                const int si = (warp * V3_FEED + e) * V3_SLOTS + kf[e] % V3_SLOTS;
+                mbar_wait_relaxed(s_empty + si, ((kf[e] / V3_SLOTS) & 1) ^ 1);
+                if (lane == 0) { SLOT_HEAD(si).jb = -1; mbar_arrive(s_full + si); }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V3_CONS_REGS));
+        const int c = (warp - V3_PROD); // scanner index; fed by producer c / V3_FEED
+        int my_bmx = 0, my_bmy = 0, my_cost = INVALID_COST; // lane p keeps partition p's window winner
+        for (int n = 0;; n++) {
+            const int si = c * V3_SLOTS + n % V3_SLOTS;
+            mbar_wait(s_full + si, (n / V3_SLOTS) & 1);
+            const SlotHead &H = SLOT_HEAD(si);
+            const int jb = H.jb;
+            if (jb < 0) break;
+            if (H.first) { my_bmx = my_bmy = 0; my_cost = INVALID_COST; }
+            uint32_t best[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) best[p] = 0xffffffffu;
+            v3_scan(H, SLOT_CXP(si), SLOT_CYT(si), SLOT_TILE(si), lane, best);
+            const unsigned group = H.group;
+            const int ux0 = H.ux0, uy0 = H.uy0, uwidth = H.uwidth;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                if (!(group >> p & 1)) continue; // warp-uniform
+                const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
+                const int chunk = k & 3, rem = uwidth - chunk * 32;
+                const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8;
+                const uint32_t cc = __reduce_min_sync(0xffffffffu, best[p] == k ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
+                if (lane == p) {
+                    my_cost = (int)(k >> KEY_SHIFT);
+                    my_bmy = uy0 + (int)((k >> 2) & 255);
+                    my_bmx = ux0 + chunk * 32 + (int)cc;
+                }
+            }
+            if (H.last && lane < NP) {
+                const unsigned mask = H.mask;
+                x264_cuda_me_result_t r;
+                int bmx = H.seed[lane][0], bmy = H.seed[lane][1], bcost = H.seed[lane][2];
+                r.seed_mx = (int16_t)bmx; r.seed_my = (int16_t)bmy; r.seed_cost = bcost;
+                if ((mask >> lane & 1) && my_cost < INVALID_COST && my_cost < bcost) { bcost = my_cost; bmy = my_bmy; bmx = my_bmx; }
+                if (!(mask >> lane & 1)) { bmx = bmy = 0; bcost = -1; r.seed_mx = r.seed_my = 0; r.seed_cost = -1; }
+                r.bmx = (int16_t)bmx; r.bmy = (int16_t)bmy; r.bcost = bcost;
+                results[jb].part[lane] = r;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + si);
+        }
+    }
+#undef SLOT_HEAD
+#undef SLOT_CXP
+#undef SLOT_CYT
+#undef SLOT_TILE
+}
+
 } // namespace
 
 extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref,
@@ -544,9 +975,20 @@ extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_fram
     if (x264_cuda_cost_tables(ctx, &d_tabs)) return -1;
     Geo geo = { fenc->plane[0], fref->plane[0], fenc->g.stride };
     const int max_ur = 2 * me_range + 1 + MB_UNION_SLACK;
-    static const int variant = getenv("X264_CUDA_MB_KERNEL") ? atoi(getenv("X264_CUDA_MB_KERNEL")) : 2; // 1: full-strip lanes, 2: half-strip lanes
+    static const int variant = getenv("X264_CUDA_MB_KERNEL") ? atoi(getenv("X264_CUDA_MB_KERNEL")) : 3; // 1: full-strip lanes, 2: half-strip lanes, 3: warp-specialised
     const int blocks = (n_jobs + MB_WARPS - 1) / MB_WARPS;
-    if (variant == 1) {
+    const int max_ur3 = 2 * me_range + 1 + V3_UNION_SLACK;
+    const size_t dyn3 = v3_slot_bytes(max_ur3) * V3_CONS * V3_SLOTS + sizeof(WarpSmem) * (V3_CONS / V3_FEED) + 2 * V3_CONS * V3_SLOTS * sizeof(uint64_t);
+    if (variant == 3 && dyn3 <= 200 * 1024 && 2 * me_range + 4 <= V3_MAX_UW) { // a single partition's window must fit one pass
+        static bool attr_set[64];
+        if (!attr_set[ctx->device & 63]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(me_search_mb3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ctx->device & 63] = true;
+        }
+        const int grid = min(ctx->sm_count, (n_jobs + V3_CONS - 1) / V3_CONS);
+        me_search_mb3_kernel<<<grid, (V3_PROD + V3_CONS) * 32, dyn3, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range, max_ur3,
+                                                                                    (x264_cuda_me_mb_result_t *)d_results);
+    } else if (variant == 1) {
         const size_t dyn = (size_t)MB_WARPS * (max_ur + 4) * 12 * sizeof(uint32_t);
         const int prefetch_dist = MB_WARPS * 3 * ctx->sm_count; // warps resident at once (168 registers: three CTAs per SM)
         me_search_mb_kernel<false><<<blocks, MB_WARPS * 32, dyn, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range,
