@@ -557,8 +557,9 @@ struct __align__(16) SlotHead {
 };
 #define V3_CXP_BYTES (2 * NP * 32 * 2) // x costs as uint16 (0xffff: outside the partition's window)
 #define V3_TILE_PITCH 112              // bytes per staged reference row: 15 (alignment) + V3_MAX_UW + 19 (16-byte strip + funnel word) rounded up to 16
-#define V3_TILE_EXTRA 18               // rows below the union: 15 of the macroblock + up to 3 from folding a narrow chunk into row segments
-__host__ __device__ inline size_t v3_cyt_bytes(int max_ur) { return (size_t)(max_ur + 4) * 12 * 4; }
+#define V3_ROW_PAD 4                   // candidate rows past the union a lane may touch: 3 from folding a narrow chunk into row segments + 1 from row pairs
+#define V3_TILE_EXTRA (15 + V3_ROW_PAD) // staged rows below the union: 15 of the macroblock + the pad
+__host__ __device__ inline size_t v3_cyt_bytes(int max_ur) { return (size_t)(max_ur + V3_ROW_PAD) * 12 * 4; }
 __host__ __device__ inline size_t v3_slot_bytes(int max_ur)
 {
     return sizeof(SlotHead) + V3_CXP_BYTES + v3_cyt_bytes(max_ur) + (size_t)(max_ur + V3_TILE_EXTRA) * V3_TILE_PITCH;
@@ -577,7 +578,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity)
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) { while (!mbar_test(b, parity)) { } }
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *b, uint32_t parity) { while (!mbar_test(b, parity)) __nanosleep(64); } // a waiter that is ahead
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *b, uint32_t parity) { while (!mbar_test(b, parity)) __nanosleep(256); } // a waiter that is ahead
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 // a shared-memory read the compiler must repeat where it is written (it would otherwise hoist the 64 source words into registers)
@@ -722,28 +723,28 @@ __device__ __forceinline__ void v3_fill(SlotHead &H, uint16_t *cxp, uint32_t (*c
         // global -> shared without registers; the copies fly while the cost tables below are gathered)
         const int o = ux0 & 15;
         const uint8_t *g0 = ref0 + (ptrdiff_t)uy0 * stride + (ux0 - o);
-        const int units = (o + uwidth + 19 + 15) >> 4, n = (urows + V3_TILE_EXTRA) * units;
+        const int units = (o + uwidth + 19 + 15) >> 4, trows = urows + V3_TILE_EXTRA; // units <= 7
         const uint32_t t0 = smem_u32(tile);
-        for (int i = lane; i < n; i += 32) {
-            const int r = i / units, u = i - r * units;
-            cp_async16(t0 + r * V3_TILE_PITCH + u * 16, g0 + (size_t)r * stride + u * 16);
-        }
+        const int u = lane & 7;
+        if (u < units)
+            for (int r = lane >> 3; r < trows; r += 4) cp_async16(t0 + r * V3_TILE_PITCH + u * 16, g0 + (size_t)r * stride + u * 16);
     }
-    {   // y-cost words, all (row, partition) pairs flattened over the 32 lanes, eight gathers in flight per lane
-        const int n = (urows + 3) * NP;
-        for (int i0 = lane; i0 < n; i0 += 32 * 8) {
+    if (lane < 27) { // y-cost words: lane -> (partition, row phase 0..2); eight gathers in flight per lane
+        const int p = lane % 9, ph = lane / 9;
+        const bool on = group >> p & 1;
+        const int wy0 = S.win[p][1] - uy0, wy1 = wy0 + S.win[p][3];
+        const int16_t *ty = tab + ((uy0 << 2) - job.mvp[p][1]);
+        for (int r0 = ph; r0 < urows + V3_ROW_PAD; r0 += 24) {
             uint32_t v[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const int i = min(i0 + 32 * k, n - 1), r = i / NP, p = i - r * NP;
-                const int wy0 = S.win[p][1] - uy0, wy1 = wy0 + S.win[p][3];
-                const bool in = (group >> p & 1) && r >= wy0 && r < wy1;
-                v[k] = in ? (uint32_t)tab[((uy0 + r) << 2) - job.mvp[p][1]] : INVALID_COST;
+                const int r = r0 + 3 * k;
+                v[k] = (on && r >= wy0 && r < wy1) ? (uint32_t)ty[r << 2] : INVALID_COST;
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const int i = i0 + 32 * k, r = i / NP, p = i - r * NP;
-                if (i < n) cyt[r][p] = (v[k] << KEY_SHIFT) | ((uint32_t)min(r, 255) << 2);
+                const int r = r0 + 3 * k;
+                if (r < urows + V3_ROW_PAD) cyt[r][p] = (v[k] << KEY_SHIFT) | ((uint32_t)min(r, 255) << 2);
             }
         }
     }
@@ -831,9 +832,77 @@ __device__ __forceinline__ void v3_scan(const SlotHead &H, const uint16_t *cxp_t
     }
 }
 
+// The same scan, TWO CANDIDATE ROWS PER STEP: rows r and r+1 meet every source word, so consecutive SADs share that operand (operand
+// reuse: no third register-bank read) and the loop control, table reads and ring loads are paid once per two rows.  18-row ring.
+__device__ __forceinline__ void v3_scan2(const SlotHead &H, const uint16_t *cxp_tab, const uint32_t (*cyt)[12], const uint8_t *tile, int lane, uint32_t (&best)[NP])
+{
+    const int ux0 = H.ux0, uwidth = H.uwidth, urows = H.urows;
+    const uint4 *F4 = (const uint4 *)&H.F[0][0];
+    uint4 F[16];
+#pragma unroll
+    for (int y = 0; y < 16; y++) F[y] = F4[y];
+    for (int c0 = 0, chunk = 0; c0 < uwidth; c0 += 32, chunk++) {
+        int cw, segs, lcol, seg;
+        chunk_tiling(uwidth, c0, lane, cw, segs, lcol, seg);
+        const int col = c0 + lcol;
+        const int seg_rows = (urows + segs - 1) / segs;
+        uint32_t cxp[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const uint32_t v = cxp_tab[(chunk * NP + p) * 32 + lane];
+            cxp[p] = ((v == 0xffffu ? INVALID_COST : v) << KEY_SHIFT) | (uint32_t)chunk;
+        }
+        const int rbeg = seg * seg_rows;
+        const int xb = (ux0 & 15) + min(col, uwidth - 1);
+        const int sh = (xb & 3) * 8;
+        const uint32_t *pr = (const uint32_t *)(tile + (size_t)rbeg * V3_TILE_PITCH + (xb & ~3));
+        uint32_t R[18][4];
+#pragma unroll
+        for (int y = 0; y < 16; y++) load_row16_s(R[y], pr + y * (V3_TILE_PITCH / 4), sh);
+        for (int base = 0; base < seg_rows; base += 18) {
+#pragma unroll
+            for (int j = 0; j < 18; j += 2) {
+                const int r = base + j;
+                if (r >= seg_rows) break; // warp-uniform; an odd last row takes its pair from the pad (another segment's row or an invalid one)
+                load_row16_s(R[(j + 16) % 18], pr + (r + 16) * (V3_TILE_PITCH / 4), sh);
+                load_row16_s(R[(j + 17) % 18], pr + (r + 17) * (V3_TILE_PITCH / 4), sh);
+                uint32_t a[2][8];
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) a[k][i] = 0;
+#pragma unroll
+                for (int y = 0; y < 16; y++) {
+                    const uint4 f = F[y];
+                    const int h = y >> 3; // 0: top quadrants, 1: bottom
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        a[k][4 * h + 0] = sad4_acc(f.x, R[(j + k + y) % 18][0], a[k][4 * h + 0]);
+                        a[k][4 * h + 1] = sad4_acc(f.y, R[(j + k + y) % 18][1], a[k][4 * h + 1]);
+                        a[k][4 * h + 2] = sad4_acc(f.z, R[(j + k + y) % 18][2], a[k][4 * h + 2]);
+                        a[k][4 * h + 3] = sad4_acc(f.w, R[(j + k + y) % 18][3], a[k][4 * h + 3]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const uint4 *cy4 = (const uint4 *)&cyt[rbeg + r + k][0];
+                    const uint4 ca = cy4[0], cb = cy4[1], cc = cy4[2];
+                    const uint32_t tl = a[k][0] + a[k][1], tr = a[k][2] + a[k][3], bl = a[k][4] + a[k][5], br = a[k][6] + a[k][7];
+                    const uint32_t top = tl + tr, bot = bl + br, lft = tl + bl, rgt = tr + br, all = top + bot;
+#define UPD(p, sad, cy) best[p] = min(best[p], __umul24((sad), 1u << KEY_SHIFT) + cxp[p] + (cy))
+                    UPD(0, all, ca.x); UPD(1, top, ca.y); UPD(2, bot, ca.z); UPD(3, lft, ca.w); UPD(4, rgt, cb.x);
+                    UPD(5, tl, cb.y); UPD(6, tr, cb.z); UPD(7, bl, cb.w); UPD(8, br, cc.x);
+#undef UPD
+                }
+            }
+        }
+    }
+}
+
+template <int RS>
 __global__ void __launch_bounds__((V3_PROD + V3_CONS) * 32, 1)
 me_search_mb3_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, int n_jobs, const int16_t *const *__restrict__ cost_tabs, int me_range,
-                     int max_ur, x264_cuda_me_mb_result_t *__restrict__ results)
+                     int max_ur, x264_cuda_me_mb_result_t *__restrict__ results, long long *__restrict__ dbg)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[]; // V3_CONS x V3_SLOTS slots | producers' WarpSmem | mbarriers
     const size_t slot_bytes = v3_slot_bytes(max_ur);
@@ -851,6 +920,7 @@ me_search_mb3_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, in
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V3_PROD_REGS));
         if (warp < V3_CONS / V3_FEED) {
             WarpSmem &S = s_prod[warp];
+            long long t_wait = 0, t_work = 0, t_first = 0; const long long t_begin = dbg ? clock64() : 0; // dbg: cycle accounting (X264_CUDA_MB_DEBUG)
             int kf[V3_FEED]; // slots filled so far for each of this producer's scanners (warp * V3_FEED + e)
 #pragma unroll
             for (int e = 0; e < V3_FEED; e++) kf[e] = 0;
@@ -889,15 +959,19 @@ me_search_mb3_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, in
                         }
                         todo &= ~group;
                         const int si = (warp * V3_FEED + e) * V3_SLOTS + kf[e] % V3_SLOTS;
+                        const long long tw0 = dbg ? clock64() : 0;
                         mbar_wait_relaxed(s_empty + si, ((kf[e] / V3_SLOTS) & 1) ^ 1);
+                        if (dbg) t_wait += clock64() - tw0;
                         v3_fill(SLOT_HEAD(si), SLOT_CXP(si), SLOT_CYT(si), SLOT_TILE(si), S, tab, ref0, stride, jb, mask, group, first, todo == 0, ux0, uy0, ux1 - ux0, uy1 - uy0, lane);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(s_full + si);
+                        if (dbg && !t_first) t_first = clock64() - t_begin;
                         kf[e]++;
                         first = 0;
                     }
                 }
             }
+            if (dbg && lane == 0) { t_work = clock64() - t_begin - t_wait; long long *d = dbg + ((size_t)blockIdx.x * (V3_PROD + V3_CONS) + warp) * 4; d[0] = t_work; d[1] = t_wait; d[2] = t_first; d[3] = kf[0]; }
 #pragma unroll
             for (int e = 0; e < V3_FEED; e++) { // no more work: tell the scanners
                 const int si = (warp * V3_FEED + e) * V3_SLOTS + kf[e] % V3_SLOTS;
@@ -909,31 +983,44 @@ me_search_mb3_kernel(Geo geo, const x264_cuda_me_mb_job_t *__restrict__ jobs, in
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V3_CONS_REGS));
         const int c = (warp - V3_PROD); // scanner index; fed by producer c / V3_FEED
         int my_bmx = 0, my_bmy = 0, my_cost = INVALID_COST; // lane p keeps partition p's window winner
+        long long t_wait = 0, t_first = 0; const long long t_begin = dbg ? clock64() : 0;
         for (int n = 0;; n++) {
             const int si = c * V3_SLOTS + n % V3_SLOTS;
+            const long long tw0 = dbg ? clock64() : 0;
             mbar_wait(s_full + si, (n / V3_SLOTS) & 1);
+            if (dbg) { const long long w = clock64() - tw0; if (n == 0) t_first = w; else t_wait += w; }
             const SlotHead &H = SLOT_HEAD(si);
             const int jb = H.jb;
-            if (jb < 0) break;
+            if (jb < 0) {
+                if (dbg && lane == 0) { long long *d = dbg + ((size_t)blockIdx.x * (V3_PROD + V3_CONS) + warp) * 4; d[0] = clock64() - t_begin - t_wait - t_first; d[1] = t_wait; d[2] = t_first; d[3] = n; }
+                break;
+            }
             if (H.first) { my_bmx = my_bmy = 0; my_cost = INVALID_COST; }
             uint32_t best[NP];
 #pragma unroll
             for (int p = 0; p < NP; p++) best[p] = 0xffffffffu;
-            v3_scan(H, SLOT_CXP(si), SLOT_CYT(si), SLOT_TILE(si), lane, best);
+            if (RS == 2) v3_scan2(H, SLOT_CXP(si), SLOT_CYT(si), SLOT_TILE(si), lane, best);
+            else v3_scan(H, SLOT_CXP(si), SLOT_CYT(si), SLOT_TILE(si), lane, best);
             const unsigned group = H.group;
             const int ux0 = H.ux0, uy0 = H.uy0, uwidth = H.uwidth;
+            {   // warp argmin per partition, branch-free so that the 18 reductions pipeline: min key (cost,row,chunk), then the lowest
+                // in-chunk column among its holders
+                uint32_t kmin[NP], cmin[NP];
 #pragma unroll
-            for (int p = 0; p < NP; p++) {
-                if (!(group >> p & 1)) continue; // warp-uniform
-                const uint32_t k = __reduce_min_sync(0xffffffffu, best[p]);
-                const int chunk = k & 3, rem = uwidth - chunk * 32;
-                const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8;
-                const uint32_t cc = __reduce_min_sync(0xffffffffu, best[p] == k ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
-                if (lane == p) {
-                    my_cost = (int)(k >> KEY_SHIFT);
-                    my_bmy = uy0 + (int)((k >> 2) & 255);
-                    my_bmx = ux0 + chunk * 32 + (int)cc;
+                for (int p = 0; p < NP; p++) kmin[p] = __reduce_min_sync(0xffffffffu, best[p]);
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const int rem = uwidth - (int)(kmin[p] & 3) * 32;
+                    const int cw = rem > 16 ? 32 : rem > 8 ? 16 : 8;
+                    cmin[p] = __reduce_min_sync(0xffffffffu, best[p] == kmin[p] ? (uint32_t)(lane & (cw - 1)) : 0xffffffffu);
                 }
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (lane == p && (group >> p & 1)) {
+                        my_cost = (int)(kmin[p] >> KEY_SHIFT);
+                        my_bmy = uy0 + (int)((kmin[p] >> 2) & 255);
+                        my_bmx = ux0 + (int)(kmin[p] & 3) * 32 + (int)cmin[p];
+                    }
             }
             if (H.last && lane < NP) {
                 const unsigned mask = H.mask;
@@ -979,15 +1066,39 @@ extern "C" int x264_cuda_me_search_mb_dev(x264_cuda_t *ctx, const x264_cuda_fram
     const int blocks = (n_jobs + MB_WARPS - 1) / MB_WARPS;
     const int max_ur3 = 2 * me_range + 1 + V3_UNION_SLACK;
     const size_t dyn3 = v3_slot_bytes(max_ur3) * V3_CONS * V3_SLOTS + sizeof(WarpSmem) * (V3_CONS / V3_FEED) + 2 * V3_CONS * V3_SLOTS * sizeof(uint64_t);
-    if (variant == 3 && dyn3 <= 200 * 1024 && 2 * me_range + 4 <= V3_MAX_UW) { // a single partition's window must fit one pass
+    if (variant == 3 && dyn3 <= 227 * 1024 && 2 * me_range + 4 <= V3_MAX_UW) { // a single partition's window must fit one pass
+        static const int rs = getenv("X264_CUDA_MB_RS") ? atoi(getenv("X264_CUDA_MB_RS")) : 1; // candidate rows per scan step
         static bool attr_set[64];
         if (!attr_set[ctx->device & 63]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(me_search_mb3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(me_search_mb3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(me_search_mb3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set[ctx->device & 63] = true;
         }
         const int grid = min(ctx->sm_count, (n_jobs + V3_CONS - 1) / V3_CONS);
-        me_search_mb3_kernel<<<grid, (V3_PROD + V3_CONS) * 32, dyn3, ctx->stream>>>(geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range, max_ur3,
-                                                                                    (x264_cuda_me_mb_result_t *)d_results);
+        static const bool debug = getenv("X264_CUDA_MB_DEBUG") != nullptr; // cycle accounting of the two roles, printed per launch
+        long long *d_dbg = nullptr;
+        const size_t n_dbg = (size_t)grid * (V3_PROD + V3_CONS) * 4;
+        if (debug) { CUDA_TRY(ctx, cudaMalloc(&d_dbg, n_dbg * 8)); CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, n_dbg * 8, ctx->stream)); }
+        (rs == 2 ? me_search_mb3_kernel<2> : me_search_mb3_kernel<1>)<<<grid, (V3_PROD + V3_CONS) * 32, dyn3, ctx->stream>>>(
+            geo, (const x264_cuda_me_mb_job_t *)d_jobs, n_jobs, d_tabs, me_range, max_ur3, (x264_cuda_me_mb_result_t *)d_results, d_dbg);
+        if (debug) {
+            long long *h = (long long *)malloc(n_dbg * 8);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h, d_dbg, n_dbg * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            double s[2][4] = { { 0 } }, mx[2][4] = { { 0 } };
+            for (int b = 0; b < grid; b++)
+                for (int w = 0; w < V3_PROD + V3_CONS; w++)
+                    for (int k = 0; k < 4; k++) {
+                        const double v = (double)h[((size_t)b * (V3_PROD + V3_CONS) + w) * 4 + k];
+                        s[w >= V3_PROD][k] += v; if (v > mx[w >= V3_PROD][k]) mx[w >= V3_PROD][k] = v;
+                    }
+            const double np = (double)grid * V3_PROD, nc = (double)grid * V3_CONS;
+            fprintf(stderr, "mb3 debug (cycles, mean / max per warp): producer work %.0f / %.0f, wait-empty %.0f / %.0f, first slot ready %.0f / %.0f, slots %.1f | "
+                            "scanner busy %.0f / %.0f, wait-full %.0f / %.0f, first wait %.0f / %.0f, slots %.1f\n",
+                    s[0][0] / np, mx[0][0], s[0][1] / np, mx[0][1], s[0][2] / np, mx[0][2], s[0][3] / np, s[1][0] / nc, mx[1][0], s[1][1] / nc, mx[1][1],
+                    s[1][2] / nc, mx[1][2], s[1][3] / nc);
+            free(h); cudaFree(d_dbg);
+        }
     } else if (variant == 1) {
         const size_t dyn = (size_t)MB_WARPS * (max_ur + 4) * 12 * sizeof(uint32_t);
         const int prefetch_dist = MB_WARPS * 3 * ctx->sm_count; // warps resident at once (168 registers: three CTAs per SM)
