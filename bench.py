@@ -32,6 +32,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, ME_RANGE, QP = 1920, 1080, 16, 26
 RING_PAIRS = 32  # 64 padded planes x 2.36 MB = 151 MB > 126 MB L2
+PAIRS_PER_STEP = 16  # one bench step = 16 consecutive P-frames of the ring (frame q+1 searched in frame q), so that a short driver run
+                     # (--steps 20) times hundreds of launches and the end-to-end leg runs in steady state
 
 
 def build_jobs(pkg, mb_w, mb_h, seed=2024, motion=(5, 3)):
@@ -133,7 +135,8 @@ def ncu_traffic():
     """DRAM bytes per launch of the headline kernel from the committed `ncu --set full` capture (profiles/), or None"""
     try:
         tot, seen = 0.0, 0
-        for line in open(os.path.join(ROOT, "profiles", "r1_ncu_me_search_mb.txt")):
+        name = "r2_ncu_me_search_mb.txt" if os.path.exists(os.path.join(ROOT, "profiles", "r2_ncu_me_search_mb.txt")) else "r1_ncu_me_search_mb.txt"
+        for line in open(os.path.join(ROOT, "profiles", name)):
             f = line.split()
             if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
@@ -411,17 +414,19 @@ def run_ours(args):
     d_mbjobs = h_mbjobs.cuda()
     torch.cuda.synchronize()
 
-    def step_resident(i):
-        p = i % RING_PAIRS
-        ctx.me_search_mb_dev(frames[2 * p + 1], frames[2 * p], ME_RANGE, d_mbjobs.data_ptr(), n_mb, d_res.data_ptr())
+    NQ = n_frames  # pair q: picture (q+1) % n_frames searched in picture q — a chain of P-frames around the ring
 
-    def step_blockjobs(i):
-        p = i % RING_PAIRS
-        ctx.me_search_dev(frames[2 * p + 1], frames[2 * p], ME_RANGE, d_jobs.data_ptr(), n_jobs, d_res.data_ptr())
+    def step_resident(q):
+        q %= NQ
+        ctx.me_search_mb_dev(frames[(q + 1) % n_frames], frames[q], ME_RANGE, d_mbjobs.data_ptr(), n_mb, d_res.data_ptr())
+
+    def step_blockjobs(q):
+        q %= NQ
+        ctx.me_search_dev(frames[(q + 1) % n_frames], frames[q], ME_RANGE, d_jobs.data_ptr(), n_jobs, d_res.data_ptr())
 
     # search-space size (identical for every pair up to the seed positions; count it on pair 0 .. RING_PAIRS-1 exactly)
     cands_per_pair, sadops_per_pair, cands_16x16_per_pair = [], [], []
-    for p in range(RING_PAIRS):
+    for p in range(NQ):
         step_resident(p)
         res = d_res.cpu().numpy().view(pkg.ME_RESULT)
         c, s = count_cands(jobs, res, ME_RANGE)
@@ -446,12 +451,14 @@ def run_ours(args):
     ctx_b.set_cost_mv(QP)
     d_res_b = torch.zeros_like(d_res)
 
+    P = PAIRS_PER_STEP
+
     def step_value(i):
-        p = i % RING_PAIRS
-        if i & 1:
-            ctx_b.me_search_mb_dev(frames[2 * p + 1], frames[2 * p], ME_RANGE, d_mbjobs.data_ptr(), n_mb, d_res_b.data_ptr())
-        else:
-            step_resident(i)
+        for q in range(i * P, (i + 1) * P):
+            if q & 1:
+                ctx_b.me_search_mb_dev(frames[(q + 1) % n_frames], frames[q % NQ], ME_RANGE, d_mbjobs.data_ptr(), n_mb, d_res_b.data_ptr())
+            else:
+                step_resident(q)
 
     for i in range(max(args.warmup, 2)):
         step_value(i)
@@ -472,23 +479,26 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall
     launches = ctx.launches() + ctx_b.launches() - l0
     total_ms = float(e_start.elapsed_time(e_end))  # the whole K-step bracket on the device (gaps included)
-    n_prof = min(args.steps, 50)
+    n_prof = min(args.steps * P, 64)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_prof)]
     for i in range(n_prof):
         evs[i][0].record(stream)
-        step_resident(args.warmup + i)
+        step_resident(args.warmup * P + i)
         evs[i][1].record(stream)
     torch.cuda.synchronize()
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    cands = sum(cands_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
-    sadops = sum(sadops_per_pair[(args.warmup + i) % RING_PAIRS] for i in range(args.steps))
+    timed_pairs = range(args.warmup * P, (args.warmup + args.steps) * P)
+    cands = sum(cands_per_pair[q % NQ] for q in timed_pairs)
+    sadops = sum(sadops_per_pair[q % NQ] for q in timed_pairs)
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  Every step uploads its two pictures from
-    # pinned host memory, expands their borders, uploads the job list, searches, and reads all results back to the host.
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  A lane encodes a chain of P-frames: every pair uploads
+    # ONE new picture from pinned host memory and expands its borders (the reference picture is the previous pair's source picture, still
+    # resident — in the encoder it is the reconstruction the device produced itself), uploads the job list, searches, and reads all results
+    # back to the host.
     # (a) serial: one host thread, one context, each call waits for its results before the next picture is sent;
-    # (b) pipelined: T host threads, each with its own context + stream + frame pair, i.e. T frames in flight — the
-    #     reference's own frame-threading model (one x264_t per frame in flight, S/encoder/encoder.c:1569-1608), which
-    #     lets copies of one frame overlap the search of another.  The headline e2e.value is (b); (a) is reported beside it.
+    # (b) pipelined: T host threads, each with its own context + stream + chain, i.e. T frames in flight — the reference's own
+    #     frame-threading model (one x264_t per frame in flight, S/encoder/encoder.c:1569-1608), which lets copies of one frame overlap the
+    #     search of another.  The headline e2e.value is (b); (a) is reported beside it.
     import threading
     T = max(1, args.e2e_threads)
     e2e_blocking = args.e2e_blocking if args.e2e_blocking >= 0 else int(T * world > (os.cpu_count() or 1))
@@ -501,37 +511,46 @@ def run_ours(args):
             c.set_cost_mv(QP)
             if e2e_blocking:
                 c.set_blocking_wait(1)
-        lanes.append({"ctx": c, "stream": st, "fe": c.frame(W, H, 0), "fr": c.frame(W, H, 0),
+        lanes.append({"ctx": c, "stream": st, "f": [c.frame(W, H, 0), c.frame(W, H, 0)], "have": -1, "last_q": -1,
                       "res": torch.zeros(n_jobs * pkg.ME_RESULT.itemsize, dtype=torch.uint8).pin_memory()})
     L = pkg.lib()
+    n_pairs = args.steps * P
+    per_lane = (n_pairs + T - 1) // T
 
-    def step_e2e(ln, i):
-        p = i % RING_PAIRS
+    def pair_e2e(ln, q):
+        """picture q+1 searched in picture q; the lane's device frame (q & 1) holds picture q from the previous pair of its chain"""
+        q %= NQ
         c = ln["ctx"]
-        ln["fe"].upload(host_pics[2 * p + 1].numpy()); ln["fe"].expand_border_mod16()  # all the reference does to fenc (encoder.c:1413-1416)
-        ln["fr"].upload(host_pics[2 * p].numpy()); ln["fr"].expand_border()
-        c.check(L.x264_cuda_me_search_mb(c.h, ln["fe"].h, ln["fr"].h, ME_RANGE, h_mbjobs.data_ptr(), n_mb, ln["res"].data_ptr()))
+        fr, fe = ln["f"][q & 1], ln["f"][(q + 1) & 1]
+        if ln["have"] != q:  # start of a chain: the reference picture has to come in as well (warm-up only)
+            fr.upload(host_pics[q].numpy()); fr.expand_border()
+        fe.upload(host_pics[(q + 1) % n_frames].numpy()); fe.expand_border()
+        c.check(L.x264_cuda_me_search_mb(c.h, fe.h, fr.h, ME_RANGE, h_mbjobs.data_ptr(), n_mb, ln["res"].data_ptr()))
+        ln["have"], ln["last_q"] = (q + 1) % NQ, q
 
-    for i in range(args.warmup):
-        for ln in lanes:
-            step_e2e(ln, i)
+    def lane_pairs(t, first, count):
+        for q in range(first, first + count):
+            pair_e2e(lanes[t], q)
+
+    for t in range(T):  # warm-up: every lane starts its chain (uploads both pictures of its first pair)
+        lane_pairs(t, t * per_lane - max(args.warmup, 1), max(args.warmup, 1))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_serial = min(n_pairs, 4 * P)
+    lanes[0]["have"] = -1
+    pair_e2e(lanes[0], -1)
     e0.record(stream)
-    for i in range(args.steps):
-        step_e2e(lanes[0], args.warmup + i)
+    lane_pairs(0, 0, n_serial)
     e1.record(stream)
     barrier()
-    e2e_serial_ms = e0.elapsed_time(e1)
-
-    def lane_loop(t):
-        for i in range(t, args.steps, T):
-            step_e2e(lanes[t], args.warmup + i)
+    e2e_serial_ms = e0.elapsed_time(e1) / n_serial * n_pairs  # scaled to the K-step job (the serial leg times at most 4 steps)
+    lanes[0]["have"] = -1
+    lane_pairs(0, -1, 1)
 
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    ths = [threading.Thread(target=lane_loop, args=(t,)) for t in range(T)]
+    ths = [threading.Thread(target=lane_pairs, args=(t, t * per_lane, min(per_lane, max(0, n_pairs - t * per_lane)))) for t in range(T)]
     for th in ths:
         th.start()
     for th in ths:
@@ -539,10 +558,11 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    # the e2e path must return what the resident path computes for the same pair (checked on every lane's last step)
-    for t in range(min(T, args.steps)):
-        i_last = ((args.steps - 1 - t) // T) * T + t
-        step_resident(args.warmup + i_last)
+    # the e2e path must return what the resident path computes for the same pair (checked on every lane's last pair)
+    for t in range(T):
+        if lanes[t]["last_q"] < 0:
+            continue
+        step_resident(lanes[t]["last_q"])
         torch.cuda.synchronize()
         if not np.array_equal(d_res.cpu().numpy(), lanes[t]["res"].numpy()):
             raise SystemExit("bench.py: e2e results differ from the resident-path results (lane %d)" % t)
@@ -557,11 +577,12 @@ def run_ours(args):
     b1.record(stream)
     torch.cuda.synchronize()
     blockjob_ms = b0.elapsed_time(b1) / 5
-    h2d = 2 * W * H + n_mb * pkg.ME_MB_JOB.itemsize
-    d2h = n_jobs * pkg.ME_RESULT.itemsize
+    h2d = P * (W * H + n_mb * pkg.ME_MB_JOB.itemsize)  # per step: 16 pairs x (one new picture + the job list)
+    d2h = P * n_jobs * pkg.ME_RESULT.itemsize
 
     # ---- max over ranks
-    (total_ms, e2e_ms), (cands_all, sadops_all) = shard.reduce_job(dist if world > 1 else None, "cuda", [total_ms, e2e_ms], [cands, sadops])
+    cands_e2e = sum(cands_per_pair[q % NQ] for q in range(n_pairs))
+    (total_ms, e2e_ms), (cands_all, sadops_all, cands_e2e_all) = shard.reduce_job(dist if world > 1 else None, "cuda", [total_ms, e2e_ms], [cands, sadops, cands_e2e])
     enc = None
     if not args.no_encode:
         cores = os.cpu_count() or 1
@@ -575,33 +596,39 @@ def run_ours(args):
         hbm_ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         # SAD work actually needed by the MB-batched kernel: 64 four-byte SADs per position of each MB's union window,
         # bounded below by the largest partition window (1056 positions unclipped) -> use the 16x16 window size
-        mb_sadops = float(np.sum(cands_16x16_per_pair)) / RING_PAIRS * 64
+        mb_sadops = float(np.sum(cands_16x16_per_pair)) / NQ * 64
         int_ach = mb_sadops / (per_launch_ms * 1e-3)
         line = {
             "metric": "1080p ESA ME Gcand/s", "value": cands_all / (total_ms * 1e-3) / 1e9, "unit": "Gcand/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1080p --me esa --merange 16: 8160 MB x 9 partition searches (73440 x264_me_search_ref jobs) per frame pair, macroblock-batched (x264_cuda_me_search_mb)",
-                       "width": W, "height": H, "me_range": ME_RANGE, "qp": QP, "jobs_per_step": n_jobs,
+            "config": {"workload": "1080p --me esa --merange 16: 8160 MB x 9 partition searches (73440 x264_me_search_ref jobs) per P-frame, macroblock-batched "
+                                   "(x264_cuda_me_search_mb); one step = %d consecutive P-frames" % P,
+                       "width": W, "height": H, "me_range": ME_RANGE, "qp": QP, "frames_per_step": P, "jobs_per_step": n_jobs * P,
                        "cands_per_step": cands // args.steps,
-                       "streams": "value leg: consecutive frame pairs alternate between two contexts/streams (independent frames; the tail of one "
+                       "streams": "value leg: consecutive frames alternate between two contexts/streams (their searches are independent; the tail of one "
                                   "launch overlaps the head of the next); one CUDA-event bracket over all K steps; roofline per-launch time from a "
                                   "separate single-stream pass (per_launch_ms)",
                        "l2": "inputs cycle through a %d-pair ring of padded planes (%.0f MB) > 126 MB L2" % (RING_PAIRS, n_frames * g.stride * (g.lines + 64) / 1e6)},
-            "e2e": {"value": cands_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": cands_e2e_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gcand/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "frames_in_flight": T,
                     "host_wait": "blocking-sync event" if e2e_blocking else "spin",
-                    "serial": {"value": cands / (e2e_serial_ms * 1e-3) / 1e9, "ms_per_step": e2e_serial_ms / args.steps,
+                    "serial": {"value": cands_e2e / (e2e_serial_ms * 1e-3) / 1e9, "ms_per_step": e2e_serial_ms / args.steps,
                                "note": "one host thread, each call waits for its results before the next picture is sent (this rank)"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                         "traffic": ncu_traffic(), "algorithmic_bytes": alg_bytes, "kernel": "me_search_mb_kernel", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "note": "this kernel is integer-ALU-pipe bound by design (64 4-byte SADs per 16x16 candidate, ~1 B of HBM traffic per 10k ops); see int_pipe"},
+            "roofline": {"bound": "int_pipe", "op": "VABSDIFF4.U8.ACC (4-byte SAD-accumulate)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
+                         "unit": "Tsad4/s", "frac": int_ach / int_peak, "kernel": "me_search_mb3_kernel", "per_launch_ms": per_launch_ms,
+                         "algorithmic_ops": mb_sadops, "peak_source": "x264_cuda_measure_int_pipe, measured in this run (148 SMs x 64 lanes/clk)",
+                         "traffic": ncu_traffic(), "algorithmic_bytes": alg_bytes,
+                         "note": "the kernel is bound by the integer ALU pipe, not HBM (64 4-byte SADs per 16x16 candidate position, ~1 B of DRAM "
+                                 "traffic per 10k ops: see roofline_hbm); algorithmic ops = 64 x positions of each macroblock's 16x16 window"},
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                             "traffic": ncu_traffic(), "algorithmic_bytes": alg_bytes, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"},
             "int_pipe": {"bound": "int_pipe", "op": "VABSDIFF4.U8.ACC (4-byte SAD-accumulate)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tsad4/s", "frac": int_ach / int_peak, "peak_source": "x264_cuda_measure_int_pipe, measured in this run"},
             "wall_s_timed_region": t_wall, "per_launch_ms": per_launch_ms,
-            "per_block_jobs": {"ms_per_step": blockjob_ms, "value": (cands / args.steps) / (blockjob_ms * 1e-3) / 1e9, "unit": "Gcand/s",
+            "per_block_jobs": {"ms_per_frame": blockjob_ms, "value": (cands / (args.steps * P)) / (blockjob_ms * 1e-3) / 1e9, "unit": "Gcand/s",
                                "note": "same 73440 searches as independent x264_cuda_me_search jobs (no SAD sharing)"},
         }
         if enc is not None:
@@ -614,7 +641,7 @@ def run_ours(args):
         f.close()
     ctx_b.close()
     for ln in lanes:
-        ln["fe"].close(); ln["fr"].close()
+        ln["f"][0].close(); ln["f"][1].close()
         if ln["ctx"] is not ctx:
             ln["ctx"].close()
     ctx.close()
@@ -879,7 +906,7 @@ def run_rows(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
