@@ -36,23 +36,35 @@ PAIRS_PER_STEP = 16  # one bench step = 16 consecutive P-frames of the ring (fra
                      # (--steps 20) times hundreds of launches and the end-to-end leg runs in steady state
 
 
+def mv_limits_fpel_all(mb_w, mb_h, mv_range=512):
+    """h->mb.mv_{min,max}_fpel of every macroblock of a progressive, single-thread encode (S/encoder/analyse.c:258-304), vectorised;
+    the same arithmetic as tests/xo_api.py::mv_limits_fpel (checked against it in tests/test_bench_reference_arm.py)"""
+    fr = 4 * mv_range
+    mbx, mby = np.meshgrid(np.arange(mb_w), np.arange(mb_h))
+    mbx, mby = mbx.reshape(-1), mby.reshape(-1)
+    clip = lambda v: np.clip(v, -fr, fr - 1)
+    mn_x, mn_y = 4 * (-16 * mbx - 24), 4 * (-16 * mby - 24)
+    mx_x, mx_y = 4 * (16 * (mb_w - mbx - 1) + 24), 4 * (16 * (mb_h - mby - 1) + 24)
+    min_spel = np.stack([clip(mn_x), np.minimum(np.maximum(mn_y, max(4 * (-512 + 8), -fr)), fr)], 1)
+    max_spel = np.stack([clip(mx_x), clip(mx_y)], 1)
+    return mbx, mby, (min_spel >> 2) + 5, (max_spel >> 2) - 5
+
+
 def build_jobs(pkg, mb_w, mb_h, seed=2024, motion=(5, 3)):
     """nine searches per macroblock with seeded predictors around the true global motion (qpel units)"""
-    import xo_api as X
     rng = np.random.default_rng(seed)
-    parts = [(0, 0, 0), (1, 0, 0), (1, 0, 8), (2, 0, 0), (2, 8, 0), (3, 0, 0), (3, 8, 0), (3, 0, 8), (3, 8, 8)]
-    n = mb_w * mb_h * len(parts)
+    parts = np.array([(0, 0, 0), (1, 0, 0), (1, 0, 8), (2, 0, 0), (2, 8, 0), (3, 0, 0), (3, 8, 0), (3, 0, 8), (3, 8, 8)])
+    n_mb = mb_w * mb_h
+    n = n_mb * len(parts)
     jobs = np.zeros(n, pkg.ME_JOB)
-    g = type("G", (), dict(mb_width=mb_w, mb_height=mb_h))
-    k = 0
-    for mby in range(mb_h):
-        for mbx in range(mb_w):
-            mnf, mxf, _, _ = X.mv_limits_fpel(g, mbx, mby)
-            for ip, ox, oy in parts:
-                j = jobs[k]
-                j["bx"], j["by"], j["i_pixel"], j["qp"] = mbx * 16 + ox, mby * 16 + oy, ip, QP
-                j["mv_min_fpel"], j["mv_max_fpel"] = mnf, mxf
-                k += 1
+    mbx, mby, mnf, mxf = mv_limits_fpel_all(mb_w, mb_h)
+    j9 = jobs.reshape(n_mb, 9)
+    j9["bx"] = (mbx * 16)[:, None] + parts[None, :, 1]
+    j9["by"] = (mby * 16)[:, None] + parts[None, :, 2]
+    j9["i_pixel"] = parts[None, :, 0]
+    j9["qp"] = QP
+    j9["mv_min_fpel"] = mnf[:, None, :]
+    j9["mv_max_fpel"] = mxf[:, None, :]
     jit = lambda s, size: rng.integers(-s, s + 1, size)
     jobs["mvp"][:, 0] = -4 * motion[0] + jit(6, n)
     jobs["mvp"][:, 1] = -4 * motion[1] + jit(6, n)
@@ -649,6 +661,158 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+CONFIGS = {
+    # BASELINE.json configs[2..4]: per-frame device pipelines of the other named configurations (one JSON line each; the headline
+    # metric and its driver contract stay with configs[1], the default run)
+    "1080p_subme7": dict(w=1920, h=1080, me="esa", subme=7, dct8=True, lookahead=False,
+                         what="1080p --me esa --subme 7 --8x8dct: hpel filter + ESA + sub-pel refinement + MC + batched DCT/quant/dequant/idct + deblock"),
+    "4k_tesa": dict(w=3840, h=2160, me="tesa", subme=2, dct8=False, lookahead=True,
+                    what="3840x2160 --me tesa --b-adapt 2: lowres planes + lookahead frame costs (2 evaluations per launch) + TESA full search of every 16x16 block"),
+    "8k_bulk": dict(w=7680, h=4320, me="esa", subme=0, dct8=False, lookahead=False,
+                    what="7680x4320 bulk: ESA (9 partitions per macroblock) + transform/quant of every macroblock"),
+}
+
+
+def run_config(args):
+    """`--config NAME`: one frame of a named BASELINE configuration through the frame-batched entry points, host arrays in and out
+    (every stage time includes the H2D/D2H of its job and result arrays), CUDA events per stage; rank 0 of each GPU runs its own frames
+    (frames are independent: --gpus N = N replicas, aggregate = sum)."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_pkg()
+    from x264_vs2008_b200 import synth, shard
+    from helpers import make_deblock_info
+    cfg = CONFIGS[args.config]
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pkg.Context(local)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    w, h = cfg["w"], cfg["h"]
+    clip = synth.Clip(w, h, seed=3 + rank)
+    flags = pkg.FRAME_HPEL | pkg.FRAME_INTEGRAL | pkg.FRAME_LOWRES | pkg.FRAME_CHROMA
+    fenc, fref, fdec = ctx.frame(w, h, flags), ctx.frame(w, h, flags), ctx.frame(w, h, flags)
+    (y1, u1, v1), (y0, u0, v0) = clip.yuv420(1), clip.yuv420(0)
+    pics = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p in (y1, u1, v1)]  # the incoming picture sits in page-locked memory
+    y1, u1, v1 = (p.numpy() for p in pics)
+    g = fenc.g
+    n_mb = g.mb_width * g.mb_height
+    jobs = build_jobs(pkg, g.mb_width, g.mb_height)
+    mbjobs = to_mb_jobs(pkg, jobs, g.mb_width, g.mb_height)
+    j16 = jobs[0::9].copy()
+    j16["mv_min_spel"] = (j16["mv_min_fpel"].astype(np.int32) - 5) * 4
+    j16["mv_max_spel"] = (j16["mv_max_fpel"].astype(np.int32) + 5) * 4
+    ctx.set_cost_mv(QP); ctx.set_quant_preset(0)
+    rj = np.zeros(n_mb, pkg.RESID_JOB)
+    rj["mb_x"], rj["mb_y"] = np.tile(np.arange(g.mb_width), g.mb_height), np.repeat(np.arange(g.mb_height), g.mb_width)
+    rj["qp"], rj["chroma_qp"], rj["flags"] = 26, 26, pkg.RESID_DECIMATE | (pkg.RESID_8x8DCT if cfg["dct8"] else 0)
+    dinfo = make_deblock_info(g, seed=7) if cfg["subme"] == 7 else None
+    fref.upload(y0); fref.upload_chroma(u0, v0); fref.expand_border(); fref.filter(); fref.init_lowres()
+    fdec.upload(y0); fdec.upload_chroma(u0, v0)
+    if cfg["lookahead"]:
+        for f in (fenc, fref):
+            f.lookahead_alloc(2)
+    stages, state = {}, {}
+    # job lists and result arrays of the three large stages live in page-locked memory (x264_cuda_host_alloc in a C caller): DMA'd directly
+    L = pkg.lib()
+    keep = []
+
+    def pinned(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).pin_memory()
+        keep.append(t)
+        return t
+
+    def pinned_out(dtype, n):
+        t = torch.zeros(n * dtype.itemsize, dtype=torch.uint8).pin_memory()
+        keep.append(t)
+        return t, t.numpy().view(dtype)
+
+    p_mbjobs = pinned(mbjobs)
+    p_mbres, mbres = pinned_out(pkg.ME_MB_RESULT, n_mb)
+    p_js, js_view = pinned_out(pkg.ME_JOB, n_mb)
+    p_fin, fin = pinned_out(pkg.ME_FINAL, n_mb)
+    p_rj = pinned(rj)
+    p_coef, _ = pinned_out(pkg.MB_COEFFS, n_mb)
+
+    def timed(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); r = fn(); e1.record(stream); torch.cuda.synchronize()
+        stages.setdefault(name, []).append(e0.elapsed_time(e1))
+        return r
+
+    def one_frame():
+        timed("upload + borders", lambda: (fenc.upload(y1), fenc.upload_chroma(u1, v1), fenc.expand_border()))
+        timed("hpel + integral (reference frame)", fref.filter)
+        if cfg["lookahead"]:
+            timed("lowres planes", fenc.init_lowres)
+            # two independent P-type frame costs (each frame searched in the other) in ONE launch, the way the B-adapt analysis batches
+            # the costs of a lookahead window (x264_cuda_lowres_frame_cost_batch)
+            ev = [(fenc, fref, fenc, 0, 1, 1, (1, 0), 0), (fref, fenc, fref, 0, 1, 1, (1, 0), 0)]
+            timed("lookahead: 2 frame costs in one launch", lambda: ctx.lowres_frame_cost_batch(ev))
+        if cfg["me"] == "tesa":
+            js_view[:] = j16
+            js_view["flags"] = pkg.ME_MBCMP_SATD | pkg.ME_FPEL_SATD
+            timed("ME: TESA + subme %d, every 16x16 block" % cfg["subme"],
+                  lambda: ctx.check(L.x264_cuda_me_search_small(ctx.h, fenc.h, fref.h, pkg.ME_METHOD_TESA, ME_RANGE, cfg["subme"], p_js.data_ptr(), n_mb, p_fin.data_ptr())))
+            state["fin"] = fin
+        else:
+            timed("ME: ESA, 9 partitions per macroblock",
+                  lambda: ctx.check(L.x264_cuda_me_search_mb(ctx.h, fenc.h, fref.h, ME_RANGE, p_mbjobs.data_ptr(), n_mb, p_mbres.data_ptr())))
+            state["res"] = mbres
+            if cfg["subme"]:
+                r = mbres["part"][:, 0]
+                js_view[:] = j16
+                js_view["seed_mv"][:, 0], js_view["seed_mv"][:, 1], js_view["seed_cost"] = r["bmx"], r["bmy"], r["bcost"]
+                js_view["flags"] = pkg.ME_MBCMP_SATD
+                timed("sub-pel refinement subme %d (16x16)" % cfg["subme"],
+                      lambda: ctx.check(L.x264_cuda_me_search_small(ctx.h, fenc.h, fref.h, pkg.ME_METHOD_SEEDED, ME_RANGE, cfg["subme"], p_js.data_ptr(), n_mb, p_fin.data_ptr())))
+                state["fin"] = fin
+        if "fin" in state:
+            mc = np.zeros(n_mb, pkg.MC_JOB)
+            mc["bx"], mc["by"], mc["mvx"], mc["mvy"], mc["w"], mc["h"] = j16["bx"], j16["by"], state["fin"]["mv"][:, 0], state["fin"]["mv"][:, 1], 16, 16
+            timed("motion compensation", lambda: ctx.mc_blocks(fref, fdec, mc))
+        timed("residual: dct/quant/dequant/idct of every macroblock",
+              lambda: ctx.check(L.x264_cuda_residual_inter(ctx.h, fenc.h, fdec.h, p_rj.data_ptr(), n_mb, p_coef.data_ptr())))
+        if dinfo is not None:
+            timed("deblock", lambda: ctx.frame_deblock(fdec, dinfo))
+
+    for _ in range(max(1, args.warmup)):
+        one_frame()
+    stages.clear()
+    n_frames = max(2, min(args.steps, 8))
+    for _ in range(n_frames):
+        one_frame()
+    # search-space size: the window of every search is the ESA/TESA one (S/encoder/me.c:449-457), counted from the seeds
+    if cfg["me"] == "tesa":
+        seeds = ctx.me_search(fenc, fref, ME_RANGE, j16)
+        cands, _ = count_cands(j16, seeds, ME_RANGE)
+        me_key = [k for k in stages if k.startswith("ME:")][0]
+    else:
+        cands, _ = count_cands(jobs, state["res"]["part"].reshape(-1), ME_RANGE)
+        me_key = "ME: ESA, 9 partitions per macroblock"
+    med = {k: float(np.median(v)) for k, v in stages.items()}
+    frame_ms = sum(med.values())
+    (frame_ms_max,), (cands_all,) = shard.reduce_job(dist if world > 1 else None, "cuda", [frame_ms], [cands])
+    (me_ms_max,), _ = shard.reduce_job(dist if world > 1 else None, "cuda", [med[me_key]], [0])
+    if rank == 0:
+        print(json.dumps({"metric": "%s ME Gcand/s" % args.config, "value": cands_all / (me_ms_max * 1e-3) / 1e9, "unit": "Gcand/s", "n_gpus": world,
+                          "steps": n_frames, "warmup": max(1, args.warmup), "ms_per_step": frame_ms_max, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": cfg["what"], "width": w, "height": h, "macroblocks": n_mb, "me_range": ME_RANGE, "qp": QP,
+                                     "cands_per_frame": int(cands)},
+                          "pipeline_fps": world * 1e3 / frame_ms_max, "stages_ms": med,
+                          "note": "value = search positions of the ME stage / its time; every stage is one frame-batched C-ABI call with host arrays "
+                                  "(page-locked job / result arrays; their H2D and D2H are inside the stage time); pipeline_fps = frames / sum of the stage times, stages "
+                                  "run back to back on one stream (no overlap between frames)", "gpu_launches": int(ctx.launches())}))
+    for f in (fenc, fref, fdec):
+        f.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_rows(args):
     """`--rows`: every SURVEY 8 row on one 1080p frame — device time of the frame-batched entry point (CUDA events, host arrays in,
     results out where the entry point takes host arrays) beside the reference's own C for the same work on ONE host core
@@ -912,6 +1076,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode-fps leg")
     ap.add_argument("--encode-workers", type=int, default=12, help="encoder threads per GPU in the encode-fps leg (capped by the host cores per rank)")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="one frame pipeline of another BASELINE configuration (one JSON line)")
     ap.add_argument("--rows", action="store_true", help="per-row device time vs the reference's C on one core (1080p); one JSON line")
     ap.add_argument("--e2e-blocking", type=int, default=-1, help="frame threads wait for results on a blocking-sync event (sleep) instead of spinning; "
                     "-1 = automatic: when the ranks' frame threads outnumber the host cores")
@@ -920,6 +1085,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.rows:
         run_rows(args)
+    elif args.config and args.impl == "ours":
+        run_config(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

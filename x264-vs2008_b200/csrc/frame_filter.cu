@@ -48,113 +48,167 @@ __global__ void __launch_bounds__(256) replicate_border_kernel(BorderArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Half-pel planes.  One thread = 4 adjacent output columns (one 32-bit store per plane) walking down R rows.
-// It keeps the last 6 source rows of its 9-byte neighbourhood (columns x-2..x+6) in registers, so each new
-// row costs 3 aligned word loads; the vertical 6-tap (int, |v| <= 10710 fits the reference's int16 buf) is
-// evaluated for those 9 columns and feeds both the V plane and the horizontal pass of the centre plane.
-__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a + f - 5 * (b + e) + 20 * (c + d); }
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
+// Half-pel planes (hpel_filter, S/common/mc.c:133-155).  One thread = 8 adjacent output columns (one 64-bit store per plane) walking
+// down R rows.  The arithmetic is packed so that the kernel is bound by HBM rather than by the integer pipe:
+//   * the source rows are unpacked ONCE into pairs of 16-bit lanes (7 registers = columns x-2 .. x+11) and kept in a 6-row register ring;
+//   * the vertical 6-tap runs on both lanes of a register at a time: Vb = (a+f) + 20(c+d) - 5(b+e) + 2560 per lane — the bias keeps every
+//     lane non-negative, so the 32-bit multiply-adds never borrow across lanes (|v| <= 10710 is the reference's int16 `buf`);
+//   * V plane: ((Vb+16)>>5) - 80 == (v+16)>>5, clamped with the packed 16-bit min/max instructions;
+//   * centre plane: horizontal 6-tap over the 16-bit vertical sums as three DP2A per pixel (pairs (1,-5) (20,20) (-5,1));
+//   * H plane: horizontal 6-tap over the source bytes as two DP4A per pixel ((1,-5,20,20) and (-5,1,0,0));
+//   * clamp-and-pack of four results = two I2IP (cvt.pack.sat.u8.s32).
+__device__ __forceinline__ int dp2a_lo_ss(uint32_t a, uint32_t b, int c)
 {
-    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// bytes (sat(p0), sat(p1), sat(p2), sat(p3)), low byte first
+__device__ __forceinline__ uint32_t pack4_sat(int p0, int p1, int p2, int p3)
+{
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(p1), "r"(p0), "r"(t));
+    return d;
 }
 
 template <int R>
 __global__ void __launch_bounds__(128) hpel_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dh,
                                                    uint8_t *__restrict__ dv, uint8_t *__restrict__ dc, int stride,
-                                                   int x_begin, int n_words, int y_begin, int y_end)
+                                                   int x_begin, int n_cols, int y_begin, int y_end)
 {
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= n_words) return;
-    const int x = x_begin + wi * 4; // multiple of 4 relative to pixel 0 => aligned words (PADH, stride % 4 == 0)
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= n_cols) return;
+    const int x = x_begin + ti * 8; // multiple of 8 relative to pixel 0 => 8-byte aligned (PADH = 32, stride % 128 == 0)
     const int y0 = y_begin + blockIdx.y * R;
-    // ring of 6 rows x 12 bytes (x-4 .. x+7), kept as the 9 needed byte values x-2..x+6
-    int px[6][9];
-    auto load = [&](int (&dst)[9], int y) {
-        const uint32_t *p = (const uint32_t *)(src + (ptrdiff_t)y * stride + x - 4);
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        dst[0] = (w0 >> 16) & 255; dst[1] = w0 >> 24;
-        dst[2] = w1 & 255; dst[3] = (w1 >> 8) & 255; dst[4] = (w1 >> 16) & 255; dst[5] = w1 >> 24;
-        dst[6] = w2 & 255; dst[7] = (w2 >> 8) & 255; dst[8] = (w2 >> 16) & 255;
+    uint32_t U[6][7]; // rows y-2 .. y+3; U[.][k] = (p[x-2+2k], p[x-1+2k]) as two 16-bit lanes
+    auto load_unpack = [&](uint32_t (&u)[7], int y) {
+        const uint8_t *p = src + (ptrdiff_t)y * stride + x;
+        const uint2 m = __ldg((const uint2 *)p);
+        const uint32_t w0 = __ldg((const uint32_t *)(p - 4)), w3 = __ldg((const uint32_t *)(p + 8));
+        u[0] = __byte_perm(w0, 0, 0x4342);
+        u[1] = __byte_perm(m.x, 0, 0x4140); u[2] = __byte_perm(m.x, 0, 0x4342);
+        u[3] = __byte_perm(m.y, 0, 0x4140); u[4] = __byte_perm(m.y, 0, 0x4342);
+        u[5] = __byte_perm(w3, 0, 0x4140); u[6] = __byte_perm(w3, 0, 0x4342);
     };
 #pragma unroll
-    for (int k = 0; k < 5; k++) load(px[k], y0 - 2 + k);
+    for (int k = 0; k < 5; k++) load_unpack(U[k], y0 - 2 + k);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int y = y0 + r;
         if (y >= y_end) break;
-        // rows y-2..y+3 live in px[(r+k)%6], k=0..5 (static after unrolling)
-        load(px[(r + 5) % 6], y + 3);
-        int v[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++)
-            v[i] = tap6(px[r % 6][i], px[(r + 1) % 6][i], px[(r + 2) % 6][i], px[(r + 3) % 6][i], px[(r + 4) % 6][i],
-                        px[(r + 5) % 6][i]);
-        const int(&s)[9] = px[(r + 2) % 6]; // source row y
-        int oh[4], ov[4], oc[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            // output column x+i sits at neighbourhood index i+2
-            oh[i] = clip_u8((tap6(s[i], s[i + 1], s[i + 2], s[i + 3], s[i + 4], s[i + 5]) + 16) >> 5);
-            ov[i] = clip_u8((v[i + 2] + 16) >> 5);
-            oc[i] = clip_u8((tap6(v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5]) + 512) >> 10);
-        }
+        load_unpack(U[(r + 5) % 6], y + 3);
         const ptrdiff_t o = (ptrdiff_t)y * stride + x;
-        *(uint32_t *)(dh + o) = pack4(oh[0], oh[1], oh[2], oh[3]);
-        *(uint32_t *)(dv + o) = pack4(ov[0], ov[1], ov[2], ov[3]);
-        *(uint32_t *)(dc + o) = pack4(oc[0], oc[1], oc[2], oc[3]);
+        // ---- vertical 6-tap, two columns per register, biased by 2560
+        uint32_t Vb[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const uint32_t af = U[r % 6][k] + U[(r + 5) % 6][k] + 0x0a000a00u;
+            const uint32_t be = U[(r + 1) % 6][k] + U[(r + 4) % 6][k], cd = U[(r + 2) % 6][k] + U[(r + 3) % 6][k];
+            Vb[k] = af + cd * 20u + be * 0xfffffffbu;
+        }
+        {   // ---- V plane: columns x .. x+7 are pairs 1..4
+            uint32_t m[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t s = ((Vb[k + 1] + 0x00100010u) >> 5) & 0x07ff07ffu;
+                m[k] = __viaddmin_s16x2_relu(s, 0xffb0ffb0u, 0x00ff00ffu); // max(min(s - 80, 255), 0) per lane
+            }
+            *(uint2 *)(dv + o) = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
+        }
+        {   // ---- centre plane: 6-tap over the vertical sums; S[k] = (Vb[k].hi, Vb[k+1].lo) serves the odd columns
+            uint32_t S[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) S[k] = __byte_perm(Vb[k], Vb[k + 1], 0x5432);
+            int c[8];
+            const int K = 512 - 32 * 2560; // rounding, minus the bias seen through coefficients that sum to 32
+#pragma unroll
+            for (int mm = 0; mm < 4; mm++) {
+                c[2 * mm] = dp2a_lo_ss(Vb[mm + 2], 0x01fbu, dp2a_lo_ss(Vb[mm + 1], 0x1414u, dp2a_lo_ss(Vb[mm], 0xfb01u, K))) >> 10;
+                c[2 * mm + 1] = dp2a_lo_ss(S[mm + 2], 0x01fbu, dp2a_lo_ss(S[mm + 1], 0x1414u, dp2a_lo_ss(S[mm], 0xfb01u, K))) >> 10;
+            }
+            *(uint2 *)(dc + o) = make_uint2(pack4_sat(c[0], c[1], c[2], c[3]), pack4_sat(c[4], c[5], c[6], c[7]));
+        }
+        {   // ---- H plane: 6-tap over the bytes of row y (re-read: an L1 hit, and cheaper than carrying the raw words through the ring)
+            const uint8_t *p = src + o;
+            const uint2 m = __ldg((const uint2 *)p);
+            const uint32_t w[5] = { __ldg((const uint32_t *)(p - 4)), m.x, m.y, __ldg((const uint32_t *)(p + 8)), 0 };
+            uint32_t A[12]; // A[j] = bytes x+j-2 .. x+j+1
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const int q = (j + 2) >> 2, sh = ((j + 2) & 3) * 8;
+                A[j] = sh ? __funnelshift_r(w[q], w[q + 1], sh) : w[q];
+            }
+            int h[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) h[i] = dp4a_us(A[i + 4], 0x000001fbu, dp4a_us(A[i], 0x1414fb01u, 16)) >> 5;
+            *(uint2 *)(dh + o) = make_uint2(pack4_sat(h[0], h[1], h[2], h[3]), pack4_sat(h[4], h[5], h[6], h[7]));
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Integral image: sum8[y][x] = sum of the 8x8 pixel box with top-left (x,y), sum4 likewise for 4x4, both
-// mod 2^16 like the reference's uint16 arithmetic.  One thread = 2 adjacent columns walking down R rows with a
+// mod 2^16 like the reference's uint16 arithmetic.  One thread = 4 adjacent columns (64-bit stores) walking down R rows with a
 // running vertical sum (add the entering row's horizontal sum, subtract the leaving one).
 template <int R, bool SUB4>
 __global__ void __launch_bounds__(128) integral_kernel(const uint8_t *__restrict__ src, uint16_t *__restrict__ sum8,
-                                                       uint16_t *__restrict__ sum4, int stride, int x_begin, int n_pairs,
+                                                       uint16_t *__restrict__ sum4, int stride, int x_begin, int n_quads,
                                                        int y_begin, int y_end)
 {
-    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= n_pairs) return;
-    const int x = x_begin + pi * 2; // even; loads below use the enclosing aligned words
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n_quads) return;
+    const int x = x_begin + qi * 4; // multiple of 4: the twelve bytes x .. x+11 a row contributes are three aligned words
     const int y0 = y_begin + blockIdx.y * R;
-    // horizontal sums of row y for columns x and x+1: h8 = 8 pixels, h4 = 4 pixels
-    auto hsum = [&](int y, uint32_t &h8, uint32_t &h4) {
-        const uint8_t *a = src + (ptrdiff_t)y * stride + x;
-        const int sh = ((uintptr_t)a & 3) * 8; // 0 or 16
-        const uint32_t *p = (const uint32_t *)((uintptr_t)a & ~(uintptr_t)3);
+    // horizontal sums of row y for columns x .. x+3, packed two columns per register: h8 = 8 pixels, h4 = 4 pixels
+    auto hsum = [&](int y, uint32_t (&h8)[2], uint32_t (&h4)[2]) {
+        const uint32_t *p = (const uint32_t *)(src + (ptrdiff_t)y * stride + x);
         const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);         // bytes x..x+7
-        const uint32_t b0 = __funnelshift_r(w0, w1, sh + 8), b1 = __funnelshift_r(w1, w2, sh + 8); // bytes x+1..x+8
-        const uint32_t l0 = sad4_acc(a0, 0, 0), l1 = sad4_acc(b0, 0, 0);
-        h4 = l0 | (l1 << 16);
-        h8 = sad4_acc(a1, 0, l0) | (sad4_acc(b1, 0, l1) << 16);
+        uint32_t l[4], h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t lo = k ? __funnelshift_r(w0, w1, 8 * k) : w0, hi = k ? __funnelshift_r(w1, w2, 8 * k) : w1;
+            l[k] = sad4_acc(lo, 0, 0);
+            h[k] = sad4_acc(hi, 0, l[k]);
+        }
+        h4[0] = l[0] | (l[1] << 16); h4[1] = l[2] | (l[3] << 16);
+        h8[0] = h[0] | (h[1] << 16); h8[1] = h[2] | (h[3] << 16);
     };
-    // running sums hold two 16-bit lanes (columns x, x+1); lanes never carry into each other because every
-    // true value is < 2^16 (8x8 box <= 16320) and we only add/subtract whole lane-pairs of equal structure:
-    // keep the lanes in separate registers to stay safe.
-    uint32_t s8a = 0, s8b = 0, s4a = 0, s4b = 0;
-    uint32_t ring8[8], ring4[8]; // horizontal 8- and 4-pixel sums of rows y..y+7 (slot (r+k)%8 <-> row y+k)
+    // running vertical sums, one register per column (the uint16 wrap of the reference is applied when storing)
+    uint32_t s8[4] = { 0, 0, 0, 0 }, s4[4] = { 0, 0, 0, 0 };
+    uint32_t ring8[8][2], ring4[8][2]; // horizontal sums of rows y..y+7 (slot (r+k)%8 <-> row y+k)
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         hsum(y0 + k, ring8[k], ring4[k]);
-        s8a += ring8[k] & 0xffff; s8b += ring8[k] >> 16;
-        if (SUB4 && k < 4) { s4a += ring4[k] & 0xffff; s4b += ring4[k] >> 16; }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            s8[c] += (ring8[k][c >> 1] >> (16 * (c & 1))) & 0xffff;
+            if (SUB4 && k < 4) s4[c] += (ring4[k][c >> 1] >> (16 * (c & 1))) & 0xffff;
+        }
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int y = y0 + r;
         if (y >= y_end) break;
         const ptrdiff_t o = (ptrdiff_t)y * stride + x;
-        *(uint32_t *)(sum8 + o) = (s8a & 0xffff) | (s8b << 16);
-        if (SUB4) *(uint32_t *)(sum4 + o) = (s4a & 0xffff) | (s4b << 16);
+        *(uint2 *)(sum8 + o) = make_uint2((s8[0] & 0xffff) | (s8[1] << 16), (s8[2] & 0xffff) | (s8[3] << 16));
+        if (SUB4) *(uint2 *)(sum4 + o) = make_uint2((s4[0] & 0xffff) | (s4[1] << 16), (s4[2] & 0xffff) | (s4[3] << 16));
         if (r + 1 < R) {
-            uint32_t h8, h4;
+            uint32_t h8[2], h4[2];
             hsum(y + 8, h8, h4);
-            const uint32_t old8 = ring8[r % 8], old4 = ring4[r % 8], in4 = ring4[(r + 4) % 8];
-            s8a += (h8 & 0xffff) - (old8 & 0xffff); s8b += (h8 >> 16) - (old8 >> 16);
-            if (SUB4) { s4a += (in4 & 0xffff) - (old4 & 0xffff); s4b += (in4 >> 16) - (old4 >> 16); }
-            ring8[r % 8] = h8; ring4[r % 8] = h4;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int sh = 16 * (c & 1);
+                s8[c] += ((h8[c >> 1] >> sh) & 0xffff) - ((ring8[r % 8][c >> 1] >> sh) & 0xffff);
+                if (SUB4) s4[c] += ((ring4[(r + 4) % 8][c >> 1] >> sh) & 0xffff) - ((ring4[r % 8][c >> 1] >> sh) & 0xffff);
+            }
+            ring8[r % 8][0] = h8[0]; ring8[r % 8][1] = h8[1]; ring4[r % 8][0] = h4[0]; ring4[r % 8][1] = h4[1];
         }
     }
 }
@@ -163,32 +217,46 @@ __global__ void __launch_bounds__(128) integral_kernel(const uint8_t *__restrict
 // Half-resolution planes: per output pixel the nested rounding average of a 2x2 source neighbourhood
 // (mc.c:343-349).  (a+b+1)>>1 per byte is exactly __vavgu4, so one thread produces 4 output pixels of all four
 // planes from 3 rows x 9 source bytes.
+template <int RL>
 __global__ void __launch_bounds__(128) lowres_kernel(const uint8_t *__restrict__ src, int src_stride, uint8_t *__restrict__ l0,
                                                      uint8_t *__restrict__ lh, uint8_t *__restrict__ lv, uint8_t *__restrict__ lc,
-                                                     int dst_stride, int n_words, int lines_lowres)
+                                                     int dst_stride, int n_cols, int lines_lowres)
 {
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (wi >= n_words || y >= lines_lowres) return;
-    const uint8_t *r0 = src + (ptrdiff_t)(2 * y) * src_stride + 8 * wi;
-    uint32_t w[3][3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const uint32_t *p = (const uint32_t *)(r0 + (ptrdiff_t)k * src_stride);
-        w[k][0] = __ldg(p); w[k][1] = __ldg(p + 1); w[k][2] = __ldg(p + 2);
-    }
-    uint32_t a01[3], a12[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { a01[i] = __vavgu4(w[0][i], w[1][i]); a12[i] = __vavgu4(w[1][i], w[2][i]); }
-    auto emit = [&](const uint32_t (&a)[3], uint8_t *d0, uint8_t *d1) {
-        const uint32_t even = __byte_perm(a[0], a[1], 0x6420), odd = __byte_perm(a[0], a[1], 0x7531);
-        const uint32_t even1 = __byte_perm(even, a[2], 0x4321);
-        const ptrdiff_t o = (ptrdiff_t)y * dst_stride + 4 * wi;
-        *(uint32_t *)(d0 + o) = __vavgu4(even, odd);
-        *(uint32_t *)(d1 + o) = __vavgu4(odd, even1);
+    // one thread = 8 output pixels (16 source bytes + one word) x RL output rows; a source row serves two output rows
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_cols) return;
+    const int y0 = blockIdx.y * RL;
+    const uint8_t *r0 = src + (ptrdiff_t)(2 * y0) * src_stride + 16 * ci;
+    auto load = [&](uint32_t (&w)[5], int k) {
+        const uint8_t *p = r0 + (ptrdiff_t)k * src_stride;
+        const uint4 q = __ldg((const uint4 *)p);
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; w[4] = __ldg((const uint32_t *)(p + 16));
     };
-    emit(a01, l0, lh);
-    emit(a12, lv, lc);
+    uint32_t w[2 * RL + 1][5]; // every source row of the tile first: the loads are independent, so one memory round trip serves all
+#pragma unroll
+    for (int k = 0; k < 2 * RL + 1; k++) load(w[k], k);
+#pragma unroll
+    for (int r = 0; r < RL; r++) {
+        const int y = y0 + r;
+        if (y >= lines_lowres) break;
+        uint32_t a01[5], a12[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) { a01[i] = __vavgu4(w[2 * r][i], w[2 * r + 1][i]); a12[i] = __vavgu4(w[2 * r + 1][i], w[2 * r + 2][i]); }
+        const ptrdiff_t o = (ptrdiff_t)y * dst_stride + 8 * ci;
+        auto emit = [&](const uint32_t (&a)[5], uint8_t *d0, uint8_t *d1) {
+            uint32_t e[2], f[2];
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                const uint32_t even = __byte_perm(a[2 * g], a[2 * g + 1], 0x6420), odd = __byte_perm(a[2 * g], a[2 * g + 1], 0x7531);
+                const uint32_t even1 = __byte_perm(even, a[2 * g + 2], 0x4321);
+                e[g] = __vavgu4(even, odd); f[g] = __vavgu4(odd, even1);
+            }
+            *(uint2 *)(d0 + o) = make_uint2(e[0], e[1]);
+            *(uint2 *)(d1 + o) = make_uint2(f[0], f[1]);
+        };
+        emit(a01, l0, lh);
+        emit(a12, lv, lc);
+    }
 }
 
 int launch_border(x264_cuda_t *ctx, uint8_t *const planes[], int n_planes, int stride, int cx0, int cx1, int cy0, int cy1,
@@ -253,11 +321,17 @@ extern "C" int x264_cuda_frame_filter(x264_cuda_t *ctx, x264_cuda_frame_t *f)
     {
         // hpel_filter covers columns [-8, w16+8) and rows [-8, lines+8) (mc.c:409-426); expand_border_filtered
         // then keeps only columns [-4, w16+4) of it (frame.c:278-281), which is all we compute.
-        constexpr int R = 8;
-        const int x_begin = -4, n_words = (w16 + 8) / 4, y_begin = -8, y_end = g.lines + 8;
-        dim3 grid((n_words + 127) / 128, (y_end - y_begin + R - 1) / R);
-        hpel_kernel<R><<<grid, 128, 0, ctx->stream>>>(f->plane[0], f->plane[1], f->plane[2], f->plane[3], g.stride, x_begin,
-                                                       n_words, y_begin, y_end);
+        // (the kernel computes [-8, w16+8); the border pass below overwrites the outer four columns on each side with the replication)
+        const int x_begin = -8, n_cols = (w16 + 16) / 8, y_begin = -8, y_end = g.lines + 8;
+        if (g.lines >= 1440) { // rows per thread: 12 where the frame has enough threads to fill the machine, else 6
+            constexpr int R = 12;
+            dim3 grid((n_cols + 127) / 128, (y_end - y_begin + R - 1) / R);
+            hpel_kernel<R><<<grid, 128, 0, ctx->stream>>>(f->plane[0], f->plane[1], f->plane[2], f->plane[3], g.stride, x_begin, n_cols, y_begin, y_end);
+        } else {
+            constexpr int R = 6;
+            dim3 grid((n_cols + 127) / 128, (y_end - y_begin + R - 1) / R);
+            hpel_kernel<R><<<grid, 128, 0, ctx->stream>>>(f->plane[0], f->plane[1], f->plane[2], f->plane[3], g.stride, x_begin, n_cols, y_begin, y_end);
+        }
         LAUNCH_CHECK(ctx, "hpel_kernel");
         uint8_t *planes[3] = { f->plane[1], f->plane[2], f->plane[3] };
         if (launch_border(ctx, planes, 3, g.stride, -4, w16 + 3, -8, g.lines + 7, -PADH, w16 + PADH, -PADV, g.lines + PADV))
@@ -267,13 +341,13 @@ extern "C" int x264_cuda_frame_filter(x264_cuda_t *ctx, x264_cuda_frame_t *f)
         // valid region of the reference's integral planes: rows [-31, lines+23], columns [-32, w16+24)
         // (mc.c:428-461 with stride_ref = w16+64; the h pass stops 8 short of the row end)
         constexpr int R = 16;
-        const int x_begin = -PADH, n_pairs = (w16 + 24 + PADH) / 2, y_begin = -PADV + 1, y_end = g.lines + 24;
-        dim3 grid((n_pairs + 127) / 128, (y_end - y_begin + R - 1) / R);
+        const int x_begin = -PADH, n_quads = (w16 + 24 + PADH) / 4, y_begin = -PADV + 1, y_end = g.lines + 24;
+        dim3 grid((n_quads + 127) / 128, (y_end - y_begin + R - 1) / R);
         if (g.flags & X264_CUDA_FRAME_INTEGRAL4)
             integral_kernel<R, true><<<grid, 128, 0, ctx->stream>>>(f->plane[0], f->integral, f->integral + f->plane_size, g.stride,
-                                                                     x_begin, n_pairs, y_begin, y_end);
+                                                                     x_begin, n_quads, y_begin, y_end);
         else
-            integral_kernel<R, false><<<grid, 128, 0, ctx->stream>>>(f->plane[0], f->integral, nullptr, g.stride, x_begin, n_pairs,
+            integral_kernel<R, false><<<grid, 128, 0, ctx->stream>>>(f->plane[0], f->integral, nullptr, g.stride, x_begin, n_quads,
                                                                       y_begin, y_end);
         LAUNCH_CHECK(ctx, "integral_kernel");
     }
@@ -290,10 +364,11 @@ extern "C" int x264_cuda_frame_init_lowres(x264_cuda_t *ctx, x264_cuda_frame_t *
     }
     // The reference first duplicates the last column/row of the source (mc.c:315-317); on a border-expanded
     // device plane those bytes already hold exactly that replication, so the core reads them as they are.
-    const int n_words = g.width_lowres / 4;
-    dim3 grid((n_words + 127) / 128, g.lines_lowres);
-    lowres_kernel<<<grid, 128, 0, ctx->stream>>>(f->plane[0], g.stride, f->lowres[0], f->lowres[1], f->lowres[2], f->lowres[3],
-                                                  g.stride_lowres, n_words, g.lines_lowres);
+    constexpr int RL = 2;
+    const int n_cols = g.width_lowres / 8; // width_lowres = 8 * mb_width
+    dim3 grid((n_cols + 127) / 128, (g.lines_lowres + RL - 1) / RL);
+    lowres_kernel<RL><<<grid, 128, 0, ctx->stream>>>(f->plane[0], g.stride, f->lowres[0], f->lowres[1], f->lowres[2], f->lowres[3],
+                                                      g.stride_lowres, n_cols, g.lines_lowres);
     LAUNCH_CHECK(ctx, "lowres_kernel");
     // x264_frame_expand_border_lowres passes width = i_stride_lowres - 2*PADH of the REFERENCE layout
     // (frame.c:301), which exceeds width_lowres when mb_width is odd; those extra columns are never written by
