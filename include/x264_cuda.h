@@ -261,8 +261,8 @@ X264_CUDA_API int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel,
                                       int *out);
 
 /* ------------------------------------------------------------------ lowres lookahead ------------------ */
-/* One call == one x264_slicetype_frame_cost(h, a, frames, p0, p1, b) evaluation (S/encoder/slicetype.c:256-355) in its
- * default (non-VBV, non-AQ) form: every interior 8x8 block of the half-resolution frame b gets
+/* One call == one x264_slicetype_frame_cost(h, a, frames, p0, p1, b) evaluation (S/encoder/slicetype.c:256-355).  Default
+ * form (:318-330): every interior 8x8 block of the half-resolution frame b gets
  * x264_slicetype_mb_cost (:43-248) — bidirectional direct-like try, one DIA/HEX + subme-4 search per list with the
  * reverse-raster neighbour predictors, bidirectional retry, intra (ten 8x8 predictions) — and the block costs are
  * summed.  Blocks run as an anti-diagonal wavefront (x+2y descending) inside one launch; the per-frame
@@ -271,6 +271,8 @@ X264_CUDA_API int x264_cuda_block_cmp(x264_cuda_t *ctx, int metric, int i_pixel,
  * fenc = frames[b], fref0 = frames[p0], fref1 = frames[p1] (may equal fref0 when b == p1); all three need
  * X264_CUDA_FRAME_LOWRES + x264_cuda_frame_init_lowres. */
 #define X264_CUDA_LOWRES_WEIGHTED_BIPRED 16 /* param.analyse.b_weighted_bipred; other flag bits: X264_CUDA_ME_MBCMP_SATD / _FPEL_SATD */
+#define X264_CUDA_LOWRES_VBV 32             /* h->param.rc.i_vbv_buffer_size != 0: the all-blocks form of slicetype.c:300-316 (the frame-edge
+                                             * blocks are searched too, and i_row_satds[b-p0][p1-b][] is produced); only through the _rc entries */
 typedef struct x264_cuda_lowres_params_t {
     int p0, p1, b;
     int me_method;          /* the user's --me (X264_ME_*: 0 dia, 1 hex, ...); the lookahead uses min(HEX, me) */
@@ -283,7 +285,8 @@ typedef struct x264_cuda_lowres_result_t {
     int score;              /* sum of block costs BEFORE the B-frame scaling of slicetype.c:338-339 */
     int intra_mbs;          /* i_intra_mbs[b-p0]   (b == p1 only) */
     int intra_cost_sum;     /* i_cost_est[0][0]    (b == p1 only) */
-    int reserved;
+    int score_aq;           /* i_cost_est_aq[b-p0][p1-b]: the interior sum of (cost * i_inv_qscale_factor + 128) >> 8 (slicetype.c:307-315, :324-329);
+                             * equals score without an inv_qscale array, 0 for frames of at most 2 macroblocks in a dimension (:293-298) */
 } x264_cuda_lowres_result_t;
 /* (re)allocates the lookahead state of a frame: n_dist = i_bframe + 1 distances per list, zero-filled like frame.c:92-98 */
 X264_CUDA_API int x264_cuda_frame_lookahead_alloc(x264_cuda_t *ctx, x264_cuda_frame_t *frame, int n_dist);
@@ -304,6 +307,17 @@ X264_CUDA_API int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_
 X264_CUDA_API int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs,
                                                     const x264_cuda_frame_t *const *fref0s, const x264_cuda_frame_t *const *fref1s,
                                                     const x264_cuda_lowres_params_t *params, x264_cuda_lowres_result_t *results);
+/* The rate-control forms: inv_qscale = frames[b]->i_inv_qscale_factor (uint16[mb_width*mb_height], host; NULL when rc.i_aq_mode is off)
+ * weights every block cost into result->score_aq; with X264_CUDA_LOWRES_VBV in params->flags the evaluation covers EVERY block in
+ * the reference's reverse-raster dependency order and row_satd[mb_height] (host) receives frames[b]->i_row_satds[b-p0][p1-b][] —
+ * what x264_rc_analyse_slice hands to the VBV row predictor (slicetype.c:638-679, ratecontrol.c).  A batch is either all-VBV or all-default. */
+X264_CUDA_API int x264_cuda_lowres_frame_cost_rc(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
+                                                 const x264_cuda_frame_t *fref1, const x264_cuda_lowres_params_t *params,
+                                                 const uint16_t *inv_qscale, x264_cuda_lowres_result_t *result, int *row_satd);
+X264_CUDA_API int x264_cuda_lowres_frame_cost_batch_rc(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs,
+                                                       const x264_cuda_frame_t *const *fref0s, const x264_cuda_frame_t *const *fref1s,
+                                                       const x264_cuda_lowres_params_t *params, const uint16_t *const *inv_qscales,
+                                                       x264_cuda_lowres_result_t *results, int *const *row_satds);
 
 /* ------------------------------------------------------------------ in-loop deblocking ---------------- */
 /* x264_frame_deblock (S/common/frame.c:794-799 -> x264_frame_deblock_row :621-792) of one progressive frame, in place on the

@@ -534,9 +534,10 @@ static x264_frame_t *g_la_frames[3];
 static x264_t *g_la_h;
 static int g_la_key[6];
 
-void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
-                          const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
-                          const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out)
+static void ref_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                                  const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                                  const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out, int b_vbv, const uint16_t *inv_qscale,
+                                  int *row_satd)
 {
     int key[6] = { g->width, g->height, in->me_method, in->mbcmp_satd, in->fpel_satd, in->b_weighted_bipred };
     if (!g_la_h || memcmp(key, g_la_key, sizeof(key))) {
@@ -557,6 +558,14 @@ void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_
     h->param.analyse.i_me_range = in->me_range;
     const int n_mb = g->mb_width * g->mb_height;
     x264_frame_t *f0 = g_la_frames[0], *f1 = g_la_frames[1], *fb = g_la_frames[2];
+    /* the VBV form of x264_slicetype_frame_cost is selected by these two parameters alone (slicetype.c:300-309) */
+    h->param.rc.i_vbv_buffer_size = b_vbv ? 1000 : 0;
+    h->param.rc.i_aq_mode = inv_qscale ? X264_AQ_VARIANCE : X264_AQ_NONE;
+    if (inv_qscale) {
+        if (!fb->i_inv_qscale_factor) fb->i_inv_qscale_factor = x264_malloc(n_mb * sizeof(uint16_t));
+        memcpy(fb->i_inv_qscale_factor, inv_qscale, n_mb * sizeof(uint16_t));
+    }
+    fb->i_row_satds[in->b - in->p0][in->p1 - in->b][0] = -1; /* "row sums not calculated yet" (slicetype.c:270) */
     const int b_bidir = in->b < in->p1;
     const uint8_t *const *src[3] = { fref0, fref1, fenc };
     x264_frame_t *dst[3] = { f0, f1, fb };
@@ -606,6 +615,22 @@ void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_
     out->score_aq = fb->i_cost_est_aq[in->b - in->p0][in->p1 - in->b];
     out->intra_mbs = fb->i_intra_mbs[in->b - in->p0];
     out->intra_cost_sum = fb->i_cost_est[0][0];
+    if (b_vbv && row_satd) memcpy(row_satd, fb->i_row_satds[in->b - in->p0][in->p1 - in->b], g->mb_height * sizeof(int));
+    h->param.rc.i_vbv_buffer_size = 0; h->param.rc.i_aq_mode = X264_AQ_NONE;
+}
+
+void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                          const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                          const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out)
+{
+    ref_lowres_frame_cost(g, in, fenc, fref0, fref1, mvs0, costs0, mvs1, costs1, ref1_mvs, intra_cost, out, 0, NULL, NULL);
+}
+
+void xo_lowres_frame_cost_vbv(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                              const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                              const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out, const uint16_t *inv_qscale, int *row_satd)
+{
+    ref_lowres_frame_cost(g, in, fenc, fref0, fref1, mvs0, costs0, mvs1, costs1, ref1_mvs, intra_cost, out, row_satd != NULL, inv_qscale, row_satd);
 }
 
 void xo_lowres_intra_pred(int mode, const uint8_t *l0, int stride, int bx, int by, uint8_t out[64])

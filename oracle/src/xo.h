@@ -201,7 +201,7 @@ void xo_me_refine_qpel(const xo_geom *g, const uint8_t *fenc_plane, const uint8_
 int xo_me_refine_bidir_satd(const xo_geom *g, const uint8_t *fenc_plane, const uint8_t *const fref0[4], const uint8_t *const fref1[4],
                             const xo_me_in *in, const int16_t mvp0[2], const int16_t mvp1[2], int weight, int mbcmp_satd, int16_t mv0[2], int16_t mv1[2]);
 
-/* ---------------- lowres lookahead: S/encoder/slicetype.c:43-355 (non-VBV, no AQ) ----------------
+/* ---------------- lowres lookahead: S/encoder/slicetype.c:43-355 ----------------
  * Planes are the four half-resolution planes (pixel 0,0 pointers, stride g->stride_lowres).  mvs/costs are the frame's
  * lowres_mvs[l][dist-1] / lowres_mv_costs[l][dist-1] arrays (mb_width*mb_height entries, updated in place when
  * do_search[l]); ref1_mvs = frames[p1]->lowres_mvs[0][p1-p0-1] (B evaluations only); intra_cost = i_intra_cost.
@@ -220,6 +220,12 @@ typedef struct { int score, score_aq, intra_mbs, intra_cost_sum; } xo_lowres_out
 void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
                           const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
                           const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out);
+/* the VBV form (h->param.rc.i_vbv_buffer_size, slicetype.c:300-316): every block evaluated, row_satd[mb_height] = per-row sums of the
+ * block costs weighted by inv_qscale (frames[b]->i_inv_qscale_factor; NULL = rc.i_aq_mode off), out->score_aq the weighted interior sum.
+ * row_satd == NULL: the default (interior-only) form with the AQ weights (:318-330) */
+void xo_lowres_frame_cost_vbv(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                              const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                              const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out, const uint16_t *inv_qscale, int *row_satd);
 /* one of the ten 8x8 predictions used by the lookahead (0..3: predict_8x8c DC,H,V,P; 4..9: predict_8x8 DDL,DDR,VR,HD,VL,HU
  * on the filtered edge), S/common/predict.c:234-336, :499-748 */
 void xo_lowres_intra_pred(int mode, const uint8_t *l0, int stride, int bx, int by, uint8_t out[64]);

@@ -1,6 +1,6 @@
 /* xo_lookahead.c — ORACLE (test infrastructure only): the half-resolution lookahead cost of one (p0,p1,b) frame
- * triple, i.e. x264_slicetype_frame_cost + x264_slicetype_mb_cost (S/encoder/slicetype.c:43-355) for the non-VBV,
- * non-AQ case, with the 8x8 intra predictors it uses (S/common/predict.c:234-336, :499-748). */
+ * triple, i.e. x264_slicetype_frame_cost + x264_slicetype_mb_cost (S/encoder/slicetype.c:43-355): the default form
+ * (interior blocks, :318-330) and the VBV form (every block, per-row sums, AQ-weighted costs, :300-316), with the 8x8 intra predictors it uses (S/common/predict.c:234-336, :499-748). */
 #include <stdlib.h>
 #include <string.h>
 #include "xo.h"
@@ -144,9 +144,12 @@ static int bidir_cost(const la_ctx *c, int bx, int by, const int *mv0, const int
     return penalty + xo_pixel_cmp(c->in->mbcmp_satd ? XO_SATD : XO_SAD, XO_8x8, fe, 16, a, 16);
 }
 
-void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
-                          const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
-                          const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out)
+/* b_vbv: h->param.rc.i_vbv_buffer_size != 0 (slicetype.c:300-316): every block is evaluated, row_satd[mb_height] receives the per-row
+ * sums of the (AQ-weighted when inv_qscale != NULL, i.e. rc.i_aq_mode) block costs, out->score_aq the weighted interior sum */
+static void lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                              const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                              const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out, int b_vbv, const uint16_t *inv_qscale,
+                              int *row_satd)
 {
     const int W = g->mb_width, H = g->mb_height, stride = g->stride_lowres;
     const int b_bidir = in->b < in->p1;
@@ -158,8 +161,10 @@ void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_
     int *costs[2] = { costs0, costs1 };
     memset(out, 0, sizeof(*out));
     const int small = W <= 2 || H <= 2;
-    for (int my = small ? H - 1 : H - 2; my >= (small ? 0 : 1); my--)
-        for (int mx = small ? W - 1 : W - 2; mx >= (small ? 0 : 1); mx--) {
+    const int all = small || b_vbv;
+    if (b_vbv && !small) memset(row_satd, 0, H * sizeof(int));
+    for (int my = all ? H - 1 : H - 2; my >= (all ? 0 : 1); my--)
+        for (int mx = all ? W - 1 : W - 2; mx >= (all ? 0 : 1); mx--) {
             const int xy = mx + my * W, bx = 8 * mx, by = 8 * my;
             int bcost = XO_COST_MAX;
             if (in->p0 != in->p1 || in->p0 != in->b) {
@@ -225,7 +230,27 @@ void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_
                 if (b_intra) bcost = icost;
                 if (mx > 0 && mx < W - 1 && my > 0 && my < H - 1) { out->intra_mbs += b_intra; out->intra_cost_sum += icost; }
             }
-            out->score += bcost;
+            if (b_vbv && !small) { /* slicetype.c:305-316 */
+                const int aq = inv_qscale ? (bcost * inv_qscale[xy] + 128) >> 8 : bcost;
+                row_satd[my] += aq;
+                if (mx > 0 && mx < W - 1 && my > 0 && my < H - 1) { out->score += bcost; out->score_aq += aq; }
+            } else {
+                out->score += bcost;
+                out->score_aq += (!small && inv_qscale) ? (bcost * inv_qscale[xy] + 128) >> 8 : small ? 0 : bcost; /* :318-330; tiny frames leave it 0 (:293-298) */
+            }
         }
-    out->score_aq = out->score;
+}
+
+void xo_lowres_frame_cost(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                          const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                          const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out)
+{
+    lowres_frame_cost(g, in, fenc, fref0, fref1, mvs0, costs0, mvs1, costs1, ref1_mvs, intra_cost, out, 0, NULL, NULL);
+}
+
+void xo_lowres_frame_cost_vbv(const xo_geom *g, const xo_lowres_in *in, const uint8_t *const fenc[4], const uint8_t *const fref0[4],
+                              const uint8_t *const fref1[4], int16_t (*mvs0)[2], int *costs0, int16_t (*mvs1)[2], int *costs1,
+                              const int16_t (*ref1_mvs)[2], uint16_t *intra_cost, xo_lowres_out *out, const uint16_t *inv_qscale, int *row_satd)
+{
+    lowres_frame_cost(g, in, fenc, fref0, fref1, mvs0, costs0, mvs1, costs1, ref1_mvs, intra_cost, out, row_satd != NULL, inv_qscale, row_satd);
 }

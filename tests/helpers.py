@@ -156,9 +156,10 @@ def lowres_planes(o, g, clip, n_frames):
     return out
 
 
-def oracle_lookahead(o, g, planes, me_method=X.ME_HEX, me_range=16, mbcmp_satd=1, weighted=0, is_ref=False):
-    """runs LOOKAHEAD_SCHEDULE on oracle `o`; returns list of (name, score, intra_mbs, intra_cost_sum, mvs0, costs0, mvs1, costs1, intra).
-    Frame state: per frame, per (list, dist) arrays, as x264_frame_t keeps them (S/common/frame.h:65-74)."""
+def oracle_lookahead(o, g, planes, me_method=X.ME_HEX, me_range=16, mbcmp_satd=1, weighted=0, is_ref=False, vbv=False, inv_qscale=None):
+    """runs LOOKAHEAD_SCHEDULE on oracle `o`; returns list of (name, score, intra_mbs, intra_cost_sum, mvs0, costs0, mvs1, costs1, intra,
+    row_satd, score_aq).  Frame state: per frame, per (list, dist) arrays, as x264_frame_t keeps them (S/common/frame.h:65-74).
+    vbv: the rc.i_vbv_buffer_size form (slicetype.c:300-316); inv_qscale: per-frame list of uint16[n_mb] (AQ on) or None."""
     n = g.mb_width * g.mb_height
     st = [{"mvs": np.zeros((2, 3, n, 2), np.int16), "costs": np.zeros((2, 3, n), np.int32), "intra": np.zeros(n, np.uint16)} for _ in planes]
     res = []
@@ -167,21 +168,23 @@ def oracle_lookahead(o, g, planes, me_method=X.ME_HEX, me_range=16, mbcmp_satd=1
         s = st[fe]
         state = {"mvs0": s["mvs"][0, d0], "costs0": s["costs"][0, d0], "mvs1": s["mvs"][1, d1], "costs1": s["costs"][1, d1],
                  "intra": s["intra"], "ref1_mvs": st[p1]["mvs"][0, max(p1 - p0 - 1, 0)].copy()}
+        row_satd = np.zeros(g.mb_height, np.int32)
         out = o.lowres_frame_cost(g, planes[b], planes[p0], planes[p1], p0, p1, b, state, me_method=me_method, me_range=me_range,
-                                  mbcmp_satd=mbcmp_satd, weighted=weighted, do_search=ds, b_intra_calculated=bic)
+                                  mbcmp_satd=mbcmp_satd, weighted=weighted, do_search=ds, b_intra_calculated=bic, vbv=vbv,
+                                  inv_qscale=inv_qscale[fe] if inv_qscale is not None else None, row_satd=row_satd)
         score = out.score
         if not is_ref and b < p1:
             score = score * 100 // 120   # the reference stores B scores scaled (slicetype.c:338-339, i_bframe_bias 0)
         res.append((name, score, out.intra_mbs if b == p1 else 0, out.intra_cost_sum if (b == p1 and p0 != p1) else 0,  # for I the reference overwrites i_cost_est[0][0] with the score
-                   
-                    state["mvs0"].copy(), state["costs0"].copy(), state["mvs1"].copy(), state["costs1"].copy(), s["intra"].copy()))
+                    state["mvs0"].copy(), state["costs0"].copy(), state["mvs1"].copy(), state["costs1"].copy(), s["intra"].copy(),
+                    row_satd, out.score_aq))
     return res
 
 
-def lookahead_digest(res, g):
-    """compact, comparable form: scores + interior arrays"""
+def lookahead_digest(res, g, all_blocks=False):
+    """compact, comparable form: scores + interior arrays (all_blocks: every block — the VBV form evaluates the frame edge too)"""
     W, H = g.mb_width, g.mb_height
-    small = W <= 2 or H <= 2
+    small = W <= 2 or H <= 2 or all_blocks
     m = np.zeros((H, W), bool)
     if small:
         m[:] = True

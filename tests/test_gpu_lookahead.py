@@ -8,7 +8,7 @@ from helpers import LOOKAHEAD_SCHEDULE, lowres_planes, oracle_lookahead, lookahe
 pytestmark = pytest.mark.gpu
 
 
-def device_lookahead(pkg, ctx, g, clip, me_method, me_range, satd, weighted, n_frames=3):
+def device_lookahead(pkg, ctx, g, clip, me_method, me_range, satd, weighted, n_frames=3, vbv=False, inv_qscale=None):
     frames = []
     for i in range(n_frames):
         f = ctx.frame(g.width, g.height, pkg.FRAME_LOWRES)
@@ -20,17 +20,49 @@ def device_lookahead(pkg, ctx, g, clip, me_method, me_range, satd, weighted, n_f
     flags = (pkg.ME_MBCMP_SATD if satd else 0) | (pkg.LOWRES_WEIGHTED_BIPRED if weighted else 0)
     res = []
     for name, fe, p0, p1, b, ds, bic in LOOKAHEAD_SCHEDULE:
-        score, imbs, isum = ctx.lowres_frame_cost(frames[b], frames[p0], frames[p1], p0, p1, b, me_method=me_method, me_range=me_range,
-                                                  flags=flags, do_search=ds, b_intra_calculated=bic)
+        rows, aq = None, None
+        if vbv or inv_qscale is not None:
+            score, imbs, isum, aq, rows = ctx.lowres_frame_cost_rc(frames[b], frames[p0], frames[p1], p0, p1, b, vbv=vbv,
+                                                                   inv_qscale=inv_qscale[fe] if inv_qscale is not None else None,
+                                                                   me_method=me_method, me_range=me_range, flags=flags, do_search=ds,
+                                                                   b_intra_calculated=bic)
+        else:
+            score, imbs, isum = ctx.lowres_frame_cost(frames[b], frames[p0], frames[p1], p0, p1, b, me_method=me_method, me_range=me_range,
+                                                      flags=flags, do_search=ds, b_intra_calculated=bic)
         if b < p1:
             score = score * 100 // 120
         d0, d1 = max(b - p0 - 1, 0), max(p1 - b - 1, 0)
         m0, c0, intra = frames[fe].lookahead_get(0, d0)
         m1, c1, _ = frames[fe].lookahead_get(1, d1)
-        res.append((name, score, imbs if b == p1 else 0, isum if (b == p1 and p0 != p1) else 0, m0, c0, m1, c1, intra))
+        res.append((name, score, imbs if b == p1 else 0, isum if (b == p1 and p0 != p1) else 0, m0, c0, m1, c1, intra, rows, aq))
     for f in frames:
         f.close()
     return res
+
+
+@pytest.mark.parametrize("size,aq,vbv", [((176, 144), True, True), ((208, 112), False, True), ((32, 64), True, True), ((176, 144), True, False),
+                                         ((1920, 1080), True, True)])
+def test_lowres_frame_cost_rc(pkg, ctx, port, size, aq, vbv):
+    """the rate-control forms (slicetype.c:300-330): all blocks + per-row sums (VBV), AQ-weighted score"""
+    from x264_vs2008_b200 import synth
+    w, h = size
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=33)
+    planes = lowres_planes(port, g, clip, 3)
+    rng = np.random.default_rng(5)
+    inv = [rng.integers(128, 512, g.mb_width * g.mb_height).astype(np.uint16) for _ in range(3)] if aq else None
+    want = oracle_lookahead(port, g, planes, X.ME_HEX, 16, 1, 0, vbv=vbv, inv_qscale=inv)
+    got = device_lookahead(pkg, ctx, g, clip, X.ME_HEX, 16, 1, 0, vbv=vbv, inv_qscale=inv)
+    sa, xa = lookahead_digest(want, g, all_blocks=vbv)
+    sb, xb = lookahead_digest(got, g, all_blocks=vbv)
+    small = g.mb_width <= 2 or g.mb_height <= 2
+    for i, (name, *_r) in enumerate(LOOKAHEAD_SCHEDULE):
+        bad = np.nonzero(xa[i] != xb[i])[0]
+        assert len(bad) == 0, (name, len(bad), bad[:8], xa[i][bad[:8]], xb[i][bad[:8]])
+        assert np.array_equal(sa[i], sb[i]), (name, sa[i], sb[i])
+        assert want[i][10] == got[i][10], (name, "score_aq", want[i][10], got[i][10])
+        if vbv and not small:
+            assert np.array_equal(want[i][9], got[i][9]), (name, "row_satd")
 
 
 @pytest.mark.parametrize("size,method,satd,weighted", [((176, 144), X.ME_HEX, 1, 0), ((176, 144), X.ME_DIA, 0, 0), ((208, 112), X.ME_HEX, 1, 1),

@@ -145,6 +145,29 @@ def test_lowres_lookahead(pkg, port, ref, size, method, satd, weighted):
     assert np.array_equal(xa, xb)
 
 
+@pytest.mark.parametrize("size,aq,vbv", [((176, 144), True, True), ((208, 112), False, True), ((32, 64), True, True), ((176, 144), True, False)])
+def test_lowres_lookahead_vbv(pkg, port, ref, size, aq, vbv):
+    """the VBV form of x264_slicetype_frame_cost (slicetype.c:300-316): every block evaluated, per-row sums, AQ-weighted costs"""
+    from x264_vs2008_b200 import synth
+    from helpers import lowres_planes, oracle_lookahead, lookahead_digest
+    w, h = size
+    g = port.geometry(w, h)
+    planes = lowres_planes(ref, g, synth.Clip(w, h, seed=33), 3)
+    rng = np.random.default_rng(5)
+    inv = [rng.integers(128, 512, g.mb_width * g.mb_height).astype(np.uint16) for _ in range(3)] if aq else None
+    a = oracle_lookahead(port, g, planes, X.ME_HEX, 16, 1, 0, vbv=vbv, inv_qscale=inv)
+    b = oracle_lookahead(ref, g, planes, X.ME_HEX, 16, 1, 0, is_ref=True, vbv=vbv, inv_qscale=inv)
+    sa, xa = lookahead_digest(a, g, all_blocks=vbv)
+    sb, xb = lookahead_digest(b, g, all_blocks=vbv)
+    assert np.array_equal(sa, sb), (sa, sb)
+    assert np.array_equal(xa, xb)
+    small = g.mb_width <= 2 or g.mb_height <= 2
+    for ra, rb in zip(a, b):
+        if vbv and not small:  # tiny frames take the first branch of slicetype.c:293-298: no row sums
+            assert np.array_equal(ra[9], rb[9]), (ra[0], ra[9], rb[9])
+        assert ra[10] == rb[10], (ra[0], ra[10], rb[10])
+
+
 @pytest.mark.parametrize("size,kw", [((176, 144), dict()), ((176, 144), dict(slice_b=1)), ((208, 112), dict(cavlc_8x8dct=1, alpha=-2, beta=2, chroma_off=3)),
                                      ((64, 48), dict(chaos=True)), ((96, 80), dict(chaos=True, slice_b=1, cavlc_8x8dct=1, alpha=6, beta=-4, chroma_off=-5)),
                                      ((176, 144), dict(psub8x8=0, qp_centre=18, alpha=-6, beta=-6)), ((32, 16), dict(qp_centre=45, alpha=12, beta=12))])

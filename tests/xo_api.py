@@ -137,6 +137,7 @@ class Oracle:
             getattr(L, n).argtypes = [i16p, i32p, C.c_int]
         L.xo_lowres_frame_cost.argtypes = [C.POINTER(Geom), C.POINTER(LowresIn), C.POINTER(u8p), C.POINTER(u8p), C.POINTER(u8p),
                                            i16p, i32p, i16p, i32p, i16p, u16p, C.POINTER(LowresOut)]
+        L.xo_lowres_frame_cost_vbv.argtypes = list(L.xo_lowres_frame_cost.argtypes) + [u16p, i32p]
         L.xo_lowres_intra_pred.argtypes = [C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
         L.xo_lowres_intra_cost.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.xo_me_search_subpel_chroma.argtypes = [C.POINTER(Geom), u8p, C.POINTER(u8p), u16p, C.POINTER(Chroma), C.POINTER(MeIn), C.c_int,
@@ -310,16 +311,21 @@ class Oracle:
         self.lib.xo_frame_deblock(C.byref(g), C.byref(d), _ptr(y, u8p, g.origin), _ptr(u), _ptr(v), u.shape[1])
 
     def lowres_frame_cost(self, g, fenc4, fref0_4, fref1_4, p0, p1, b, state, me_method=ME_HEX, me_range=16, mbcmp_satd=1,
-                          fpel_satd=0, weighted=0, do_search=(1, 1), b_intra_calculated=0):
+                          fpel_satd=0, weighted=0, do_search=(1, 1), b_intra_calculated=0, vbv=False, inv_qscale=None, row_satd=None):
         """x264_slicetype_frame_cost on lowres planes.  state: dict of per-frame lookahead arrays that persist between calls —
         'mvs0','mvs1' int16[n_mb,2]; 'costs0','costs1' int32[n_mb]; 'intra' uint16[n_mb]; 'ref1_mvs' int16[n_mb,2] (B only).
-        Updated in place.  Returns LowresOut (score is the raw sum for the port; the reference scales B scores, see xo.h)."""
+        Updated in place.  Returns LowresOut (score is the raw sum for the port; the reference scales B scores, see xo.h).
+        vbv: the rc.i_vbv_buffer_size form (every block, row_satd int32[mb_height] filled, inv_qscale uint16[n_mb] or None = AQ off)."""
         li = LowresIn(p0, p1, b, me_method, me_range, mbcmp_satd, fpel_satd, weighted, (C.c_int * 2)(*do_search), b_intra_calculated)
         mk = lambda planes: (u8p * 4)(*[_ptr(p, u8p, g.origin_lowres) for p in planes])
         out = LowresOut()
-        self.lib.xo_lowres_frame_cost(C.byref(g), C.byref(li), mk(fenc4), mk(fref0_4), mk(fref1_4),
-                                      _ptr(state["mvs0"], i16p), _ptr(state["costs0"], i32p), _ptr(state["mvs1"], i16p),
-                                      _ptr(state["costs1"], i32p), _ptr(state["ref1_mvs"], i16p), _ptr(state["intra"], u16p), C.byref(out))
+        args = (C.byref(g), C.byref(li), mk(fenc4), mk(fref0_4), mk(fref1_4),
+                _ptr(state["mvs0"], i16p), _ptr(state["costs0"], i32p), _ptr(state["mvs1"], i16p),
+                _ptr(state["costs1"], i32p), _ptr(state["ref1_mvs"], i16p), _ptr(state["intra"], u16p), C.byref(out))
+        if vbv or inv_qscale is not None:
+            self.lib.xo_lowres_frame_cost_vbv(*args, _ptr(inv_qscale, u16p) if inv_qscale is not None else None, _ptr(row_satd, i32p) if vbv else None)
+        else:
+            self.lib.xo_lowres_frame_cost(*args)
         return out
 
 

@@ -68,6 +68,7 @@ ME_METHOD_DIA, ME_METHOD_HEX, ME_METHOD_UMH, ME_METHOD_TESA, ME_METHOD_SEEDED, M
 ME_MBCMP_SATD = 8
 ME_CHROMA = 32
 LOWRES_WEIGHTED_BIPRED = 16
+LOWRES_VBV = 32
 ME_RESULT = np.dtype([("bmx", "<i2"), ("bmy", "<i2"), ("bcost", "<i4"), ("seed_mx", "<i2"), ("seed_my", "<i2"),
                       ("seed_cost", "<i4")], align=True)
 ME_MB_PARTS, ME_MB_MVC = 9, 4
@@ -157,6 +158,8 @@ def lib():
         L.x264_cuda_frame_lookahead_set.argtypes = [vp, vp, ip, ip, vp, vp, vp]
         L.x264_cuda_lowres_frame_cost.argtypes = [vp, vp, vp, vp, vp, vp]
         L.x264_cuda_lowres_frame_cost_batch.argtypes = [vp, ip, vp, vp, vp, vp, vp]
+        L.x264_cuda_lowres_frame_cost_rc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+        L.x264_cuda_lowres_frame_cost_batch_rc.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_deblock_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_frame_ssd.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
@@ -422,6 +425,18 @@ class Context:
         res = np.zeros(4, np.int32)
         self.check(lib().x264_cuda_lowres_frame_cost(self.h, fenc.h, fref0.h, fref1.h, pm.ctypes.data, res.ctypes.data))
         return int(res[0]), int(res[1]), int(res[2])
+
+    def lowres_frame_cost_rc(self, fenc, fref0, fref1, p0, p1, b, inv_qscale=None, vbv=True, me_method=1, me_range=16, flags=ME_MBCMP_SATD,
+                             do_search=(1, 1), b_intra_calculated=0):
+        """the rate-control forms of x264_slicetype_frame_cost (S/encoder/slicetype.c:300-316): -> (score, intra_mbs, intra_cost_sum,
+        score_aq, row_satd int32[mb_height] or None).  inv_qscale: uint16[n_mb] (rc.i_aq_mode) or None; vbv: evaluate every block."""
+        pm = np.array([p0, p1, b, me_method, me_range, flags | (LOWRES_VBV if vbv else 0), do_search[0], do_search[1], b_intra_calculated], np.int32)
+        res = np.zeros(4, np.int32)
+        rows = np.zeros(fenc.g.mb_height, np.int32) if vbv else None
+        iq = np.ascontiguousarray(inv_qscale, np.uint16) if inv_qscale is not None else None
+        self.check(lib().x264_cuda_lowres_frame_cost_rc(self.h, fenc.h, fref0.h, fref1.h, pm.ctypes.data, iq.ctypes.data if iq is not None else None,
+                                                        res.ctypes.data, rows.ctypes.data if vbv else None))
+        return int(res[0]), int(res[1]), int(res[2]), int(res[3]), rows
 
     def frame_deblock(self, fdec, info):
         """x264_frame_deblock (S/common/frame.c:621-799) in place on fdec's luma + chroma planes.  info: dict with the reference's

@@ -71,7 +71,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_mb_ticket);
     cudaFree(ctx->d_deblock_progress);
     cudaFree(ctx->d_deblock_recs);
-    cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums);
+    cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums); cudaFree(ctx->d_la_vbv);
     cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_ring);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

@@ -826,7 +826,8 @@ struct LaArgs {
     const uint8_t *fenc[4], *ref[2][4];
     int stride, W, H;
     int16_t *mvs[2]; int *costs[2]; const int16_t *ref1_mvs; int *intra; unsigned long long *sync[2]; int n_mb; const int *order; int n_order;
-    int *ticket, *sums; // sums: score, intra_mbs, intra_cost_sum
+    int *ticket, *sums; // sums: score, intra_mbs, intra_cost_sum, score_aq
+    const uint16_t *inv_q; int *row_satd; int all; // the VBV form (slicetype.c:300-316): every block evaluated, AQ-weighted per-row sums
     int epoch, b_bidir, b_any_inter, dsf, weight, method, me_range, do_search0, do_search1, mbcmp_satd, fpel_satd;
     const int16_t *tab; // p_cost_mv (qp 12) centre
 };
@@ -938,7 +939,7 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(const LaArgs *__restri
                         const bool ex = lane < 4 && nx >= 0 && nx < a.W && ny < a.H;
                         uint32_t v = 0;
                         if (ex) {
-                            const bool small = a.W <= 2 || a.H <= 2;
+                            const bool small = a.W <= 2 || a.H <= 2 || a.all;
                             const bool inside = small || (nx >= 1 && nx <= a.W - 2 && ny >= 1 && ny <= a.H - 2);
                             if (inside) {
                                 unsigned long long wv;
@@ -1003,8 +1004,15 @@ __global__ void __launch_bounds__(128) lowres_cost_kernel(const LaArgs *__restri
             if (b_intra) bcost = icost;
         }
         if (lane == 0) {
-            atomicAdd(a.sums + 0, bcost);
-            if (!a.b_bidir && mx > 0 && mx < a.W - 1 && my > 0 && my < a.H - 1) { atomicAdd(a.sums + 1, b_intra); atomicAdd(a.sums + 2, icost); }
+            const bool interior = mx > 0 && mx < a.W - 1 && my > 0 && my < a.H - 1;
+            const bool tiny = a.W <= 2 || a.H <= 2;
+            const int aq = a.inv_q ? (bcost * a.inv_q[xy] + 128) >> 8 : bcost; // slicetype.c:307-309, :324-326
+            if (tiny) atomicAdd(a.sums + 0, bcost);                            // :293-298: plain sum, no weighted score
+            else {
+                if (a.all) atomicAdd(a.row_satd + my, aq);                     // :310
+                if (interior) { atomicAdd(a.sums + 0, bcost); atomicAdd(a.sums + 3, aq); }
+            }
+            if (!a.b_bidir && interior) { atomicAdd(a.sums + 1, b_intra); atomicAdd(a.sums + 2, icost); }
         }
     }
 }
@@ -1085,9 +1093,10 @@ extern "C" int x264_cuda_frame_lookahead_set(x264_cuda_t *ctx, x264_cuda_frame_t
 
 #define LA_MAX_BATCH 64
 
-extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs, const x264_cuda_frame_t *const *fref0s,
-                                                 const x264_cuda_frame_t *const *fref1s, const x264_cuda_lowres_params_t *pms,
-                                                 x264_cuda_lowres_result_t *results)
+// inv_qscales / row_satds: NULL, or one pointer per evaluation (host arrays: uint16[n_mb] / int[mb_height]; entries may be NULL)
+static int lowres_frame_cost_core(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs, const x264_cuda_frame_t *const *fref0s,
+                                  const x264_cuda_frame_t *const *fref1s, const x264_cuda_lowres_params_t *pms,
+                                  const uint16_t *const *inv_qscales, x264_cuda_lowres_result_t *results, int *const *row_satds)
 {
     x264_cuda_enter(ctx);
     if (n_evals < 1 || n_evals > LA_MAX_BATCH) { snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost_batch: 1..%d evaluations per call", LA_MAX_BATCH); return -1; }
@@ -1105,23 +1114,52 @@ extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, 
     // wavefront order: interior blocks (all blocks for tiny frames) by x + 2y descending
     if (ctx->la_w != W || ctx->la_h != H) {
         const bool small = W <= 2 || H <= 2;
-        int *ord = (int *)malloc((size_t)W * H * sizeof(int)), n = 0;
-        for (int v = (W - 1) + 2 * (H - 1); v >= 0; v--)
-            for (int y = H - 1; y >= 0; y--) {
-                const int x = v - 2 * y;
-                if (x < 0 || x >= W) continue;
-                if (!small && (x < 1 || x > W - 2 || y < 1 || y > H - 2)) continue;
-                ord[n++] = x + y * W;
-            }
+        // two lists in one allocation: the interior blocks (default form), then every block (VBV form, slicetype.c:300-316)
+        int *ord = (int *)malloc((size_t)2 * W * H * sizeof(int)), n = 0, n_all = 0;
+        for (int pass = 0; pass < 2; pass++)
+            for (int v = (W - 1) + 2 * (H - 1); v >= 0; v--)
+                for (int y = H - 1; y >= 0; y--) {
+                    const int x = v - 2 * y;
+                    if (x < 0 || x >= W) continue;
+                    if (pass == 0) {
+                        if (!small && (x < 1 || x > W - 2 || y < 1 || y > H - 2)) continue;
+                        ord[n++] = x + y * W;
+                    } else
+                        ord[n + n_all++] = x + y * W;
+                }
         cudaFree(ctx->d_la_order); ctx->d_la_order = nullptr;
+        cudaFree(ctx->d_la_vbv); ctx->d_la_vbv = nullptr;
         // per evaluation 8 ints of sums; then the ticket counter; then the LaArgs array
         if (!ctx->d_la_sums) CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_sums, (8 * LA_MAX_BATCH + 8) * sizeof(int) + LA_MAX_BATCH * sizeof(LaArgs)));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_order, (size_t)W * H * sizeof(int)));
-        CUDA_TRY(ctx, cudaMemcpy(ctx->d_la_order, ord, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_order, (size_t)(n + n_all) * sizeof(int)));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_la_order, ord, (size_t)(n + n_all) * sizeof(int), cudaMemcpyHostToDevice));
         free(ord);
         ctx->la_w = W; ctx->la_h = H; ctx->la_n = n;
     }
     const size_t n_mb = (size_t)W * H;
+    // VBV / AQ side arrays, per evaluation: row sums int[H_al] | inverse qscale uint16[n_mb_al]
+    const size_t vbv_rows = ((size_t)H + 3) & ~(size_t)3, vbv_stride = vbv_rows * sizeof(int) + ((n_mb * sizeof(uint16_t) + 15) & ~(size_t)15);
+    bool any_vbv = false, any_all = false;
+    for (int e = 0; e < n_evals; e++) {
+        const bool all = (pms[e].flags & X264_CUDA_LOWRES_VBV) != 0;
+        if (all && !(row_satds && row_satds[e])) { snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost: X264_CUDA_LOWRES_VBV needs a row_satd array"); return -1; }
+        any_all |= all;
+        any_vbv |= all || (inv_qscales && inv_qscales[e]);
+    }
+    if (any_all && n_evals > 1) {
+        // one ticket space per launch: evaluations of a batch must all walk the same block list
+        for (int e = 0; e < n_evals; e++)
+            if (!(pms[e].flags & X264_CUDA_LOWRES_VBV)) { snprintf(ctx->err, 256, "x264_cuda_lowres_frame_cost_batch: VBV and default evaluations cannot share a batch"); return -1; }
+    }
+    if (any_vbv) {
+        if (!ctx->d_la_vbv) CUDA_TRY(ctx, cudaMalloc(&ctx->d_la_vbv, vbv_stride * LA_MAX_BATCH));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_la_vbv, 0, vbv_stride * n_evals, ctx->stream));
+        for (int e = 0; e < n_evals; e++)
+            if (inv_qscales && inv_qscales[e])
+                CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_la_vbv + vbv_stride * e + vbv_rows * sizeof(int), inv_qscales[e], n_mb * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int n_order = any_all && !(W <= 2 || H <= 2) ? (int)n_mb : ctx->la_n;
+    const int *d_order = any_all && !(W <= 2 || H <= 2) ? ctx->d_la_order + ctx->la_n : ctx->d_la_order;
     int *d_ticket = ctx->d_la_sums + 8 * LA_MAX_BATCH;
     LaArgs *d_evals = (LaArgs *)(ctx->d_la_sums + 8 * LA_MAX_BATCH + 8);
     static_assert(sizeof(LaArgs) % 8 == 0, "LaArgs array follows an 8-int header");
@@ -1159,8 +1197,11 @@ extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, 
         a.intra = fenc->la_intra; a.n_mb = (int)n_mb;
         a.sync[0] = (unsigned long long *)fenc->la_done + ((size_t)0 * fenc->la_dist + (d0 < 0 ? 0 : d0)) * n_mb;
         a.sync[1] = (unsigned long long *)fenc->la_done + ((size_t)1 * fenc->la_dist + (d1 < 0 ? 0 : d1)) * n_mb;
-        a.order = ctx->d_la_order; a.n_order = ctx->la_n;
+        a.order = d_order; a.n_order = n_order;
         a.ticket = d_ticket; a.sums = ctx->d_la_sums + 8 * e;
+        a.all = any_all;
+        a.row_satd = any_vbv ? (int *)((uint8_t *)ctx->d_la_vbv + vbv_stride * e) : nullptr;
+        a.inv_q = (inv_qscales && inv_qscales[e]) ? (const uint16_t *)((uint8_t *)ctx->d_la_vbv + vbv_stride * e + vbv_rows * sizeof(int)) : nullptr;
         a.epoch = ++g_la_epoch; /* process-wide: the hand-over words live in the FRAME, which several contexts may evaluate in turn */ a.b_bidir = b_bidir; a.b_any_inter = any;
         a.dsf = pm->p1 != pm->p0 ? (((pm->b - pm->p0) << 8) + ((pm->p1 - pm->p0) >> 1)) / (pm->p1 - pm->p0) : 128; // slicetype.c:289-290
         a.weight = (pm->flags & X264_CUDA_LOWRES_WEIGHTED_BIPRED) ? 64 - (a.dsf >> 2) : 32;                          // slicetype.c:57
@@ -1190,17 +1231,40 @@ extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, 
     // persistent warps pulling tickets in wavefront order: every ticket's dependencies hold smaller tickets, so a waiting
     // warp only ever waits for warps that are already running.  A diagonal of one wavefront holds at most ~W/2 blocks; twice
     // that many warps per evaluation keep the next diagonals prefetching while leaving the rest of the GPU to other kernels.
-    const int blocks = min((ctx->la_n * n_evals + 3) / 4, min(max(8, (W + 3) / 4) * n_evals, ctx->sm_count * 4));
-    lowres_cost_kernel<<<blocks, 128, 0, ctx->stream>>>(d_evals, n_evals, d_ticket, ctx->la_n);
+    const int blocks = min((n_order * n_evals + 3) / 4, min(max(8, (W + 3) / 4) * n_evals, ctx->sm_count * 4));
+    lowres_cost_kernel<<<blocks, 128, 0, ctx->stream>>>(d_evals, n_evals, d_ticket, n_order);
     LAUNCH_CHECK(ctx, "lowres_cost_kernel");
     int *sums = (int *)malloc((size_t)n_evals * 8 * sizeof(int));
     ce = cudaMemcpyAsync(sums, ctx->d_la_sums, (size_t)n_evals * 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    for (int e = 0; e < n_evals && ce == cudaSuccess; e++)
+        if (any_all && row_satds && row_satds[e])
+            ce = cudaMemcpyAsync(row_satds[e], (uint8_t *)ctx->d_la_vbv + vbv_stride * e, (size_t)H * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     if (ce == cudaSuccess)
-        for (int e = 0; e < n_evals; e++) { results[e].score = sums[8 * e]; results[e].intra_mbs = sums[8 * e + 1]; results[e].intra_cost_sum = sums[8 * e + 2]; results[e].reserved = 0; }
+        for (int e = 0; e < n_evals; e++) { results[e].score = sums[8 * e]; results[e].intra_mbs = sums[8 * e + 1]; results[e].intra_cost_sum = sums[8 * e + 2]; results[e].score_aq = sums[8 * e + 3]; }
     free(sums);
     if (ce != cudaSuccess) return x264_cuda_fail(ctx, "lowres_frame_cost", ce);
     return 0;
+}
+
+extern "C" int x264_cuda_lowres_frame_cost_batch(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs, const x264_cuda_frame_t *const *fref0s,
+                                                 const x264_cuda_frame_t *const *fref1s, const x264_cuda_lowres_params_t *pms,
+                                                 x264_cuda_lowres_result_t *results)
+{
+    return lowres_frame_cost_core(ctx, n_evals, fencs, fref0s, fref1s, pms, nullptr, results, nullptr);
+}
+
+extern "C" int x264_cuda_lowres_frame_cost_batch_rc(x264_cuda_t *ctx, int n_evals, x264_cuda_frame_t *const *fencs, const x264_cuda_frame_t *const *fref0s,
+                                                    const x264_cuda_frame_t *const *fref1s, const x264_cuda_lowres_params_t *pms,
+                                                    const uint16_t *const *inv_qscales, x264_cuda_lowres_result_t *results, int *const *row_satds)
+{
+    return lowres_frame_cost_core(ctx, n_evals, fencs, fref0s, fref1s, pms, inv_qscales, results, row_satds);
+}
+
+extern "C" int x264_cuda_lowres_frame_cost_rc(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0, const x264_cuda_frame_t *fref1,
+                                              const x264_cuda_lowres_params_t *pm, const uint16_t *inv_qscale, x264_cuda_lowres_result_t *result, int *row_satd)
+{
+    return lowres_frame_cost_core(ctx, 1, &fenc, &fref0, &fref1, pm, &inv_qscale, result, &row_satd);
 }
 
 extern "C" int x264_cuda_lowres_frame_cost(x264_cuda_t *ctx, x264_cuda_frame_t *fenc, const x264_cuda_frame_t *fref0,
