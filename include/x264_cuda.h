@@ -13,6 +13,10 @@
  *
  * Threading (S/common/common.h:50, S/encoder/encoder.c:780): one x264_cuda_t per x264_t thread context; a
  * context owns one CUDA stream and is not re-entrant; different contexts may be used concurrently.
+ * Device frames may be shared between contexts (one thread's fdec is the next thread's reference), but every call is
+ * asynchronous on its own context's stream and NOTHING orders two contexts' streams: before another context reads a frame,
+ * the producing context must have been waited for — x264_cuda_fence_wait(x264_cuda_fence_record(producer)) or
+ * x264_cuda_synchronize(producer) — exactly where the reference waits on x264_frame_cond_wait (S/encoder/encoder.c:1176-1180).
  */
 #ifndef X264_CUDA_H
 #define X264_CUDA_H
@@ -441,6 +445,30 @@ X264_CUDA_API int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_fra
                                            const x264_cuda_resid_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_t *coeffs);
 X264_CUDA_API int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
                                                const void *d_jobs, int n_jobs, void *d_coeffs);
+
+/* Frame-batched residual coding of I_16x16 macroblocks: what x264_macroblock_encode does for h->mb.i_type == I_16x16 (S/encoder/macroblock.c:512-530
+ * predict_16x16[mode] + x264_mb_encode_i16x16 :184-270; :744-760 predict_8x8c[mode] + x264_mb_encode_8x8_chroma with b_inter = 0, :272-363), non-trellis,
+ * non-lossless.  The prediction reads the UNFILTERED reconstruction of the left / top / top-left neighbours in fdec, so the listed macroblocks run
+ * as a wavefront inside one launch: a macroblock must be listed AFTER any of those three neighbours that is also in the list (raster order always
+ * qualifies); neighbours that are not listed must already be final in fdec.  On return fdec holds the reconstruction of the listed macroblocks
+ * (luma + chroma).  Modes are the reference's enums: mode16 = enum intra16x16_pred_e (V H DC P DC_LEFT DC_TOP DC_128), mode_chroma =
+ * enum intra_chroma_pred_e (DC H V P DC_LEFT DC_TOP DC_128) — e.g. what x264_cuda_intra_mb_costs picked.  flags: X264_CUDA_RESID_DECIMATE =
+ * slice B || (b_dct_decimate && slice P) (:193).  Coefficient record: c.luma[16*i + 1..15] = AC levels of block i (slot 0 zero), luma_dc =
+ * h->dct.luma16x16_dc, c.nnz[24] its flag; levels of blocks whose nnz is 0 read as zero. */
+typedef struct x264_cuda_intra16_job_t {
+    int16_t mb_x, mb_y;
+    uint8_t qp, chroma_qp;     /* h->mb.i_qp, h->mb.i_chroma_qp */
+    uint8_t mode16, mode_chroma;
+    uint8_t flags, reserved[3];
+} x264_cuda_intra16_job_t;     /* 12 bytes */
+typedef struct x264_cuda_mb_coeffs_i16_t {
+    x264_cuda_mb_coeffs_t c;
+    int16_t luma_dc[16];       /* h->dct.luma16x16_dc */
+} x264_cuda_mb_coeffs_i16_t;   /* 848 bytes */
+X264_CUDA_API int x264_cuda_residual_intra16(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
+                                             const x264_cuda_intra16_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_i16_t *coeffs);
+X264_CUDA_API int x264_cuda_residual_intra16_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
+                                                 const void *d_jobs, int n_jobs, void *d_coeffs);
 
 /* x264_macroblock_probe_skip (S/encoder/macroblock.c:797-883), frame-batched: skip[i] = 1 when macroblock i quantises to nothing
  * against its skip prediction — luma decimation total < 6 (:822-840) and, for each chroma plane whose SSD reaches

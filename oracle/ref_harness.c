@@ -444,6 +444,47 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
     }
 }
 
+/* one I_16x16 macroblock through the reference's own x264_macroblock_encode: neighbour pixels hand-loaded around p_fdec (the row above,
+ * the left column and the corner are inside the fdec buffer, common/macroblock.c:990-1004), slice type picked so that b_decimate matches */
+void xo_residual_intra16_mb(const xo_resid_in *in, int mode16, int mode_chroma, const uint8_t fenc_y[256], const uint8_t fenc_u[64],
+                            const uint8_t fenc_v[64], const uint8_t nb_y[33], const uint8_t nb_u[17], const uint8_t nb_v[17],
+                            uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out, int16_t luma_dc[16])
+{
+    xo_resid_in tmp = *in;
+    tmp.b_transform_8x8 = 0;
+    memset(rec_y, 0, 256); memset(rec_u, 0, 64); memset(rec_v, 0, 64);
+    x264_t *h = res_handle(&tmp, fenc_y, fenc_u, fenc_v, rec_y, rec_u, rec_v);
+    h->sh.i_type = in->b_decimate ? SLICE_TYPE_P : SLICE_TYPE_I; /* macroblock.c:193: B || (b_dct_decimate && P) */
+    h->param.analyse.b_dct_decimate = in->b_decimate;
+    h->mb.i_type = I_16x16;
+    h->mb.i_intra16x16_pred_mode = mode16;
+    h->mb.i_chroma_pred_mode = mode_chroma;
+    const uint8_t *nb[3] = { nb_y, nb_u, nb_v };
+    for (int p = 0; p < 3; p++) {
+        const int n = p ? 8 : 16;
+        uint8_t *d = h->mb.pic.p_fdec[p];
+        d[-FDEC_STRIDE - 1] = nb[p][0];
+        memcpy(d - FDEC_STRIDE, nb[p] + 1, n);
+        for (int y = 0; y < n; y++) d[y * FDEC_STRIDE - 1] = nb[p][1 + n + y];
+    }
+    x264_macroblock_encode(h);
+    memset(out, 0, sizeof(*out));
+    memcpy(out->luma4x4, h->dct.luma4x4, sizeof(out->luma4x4));
+    memcpy(out->chroma_dc, h->dct.chroma_dc, sizeof(out->chroma_dc));
+    for (int i = 0; i < 27; i++) out->nnz[i] = h->mb.cache.non_zero_count[x264_scan8[i]];
+    /* blocks the reference did not code keep stale levels in h->dct (it never reads them): report them as zero, like the port */
+    for (int i = 0; i < 24; i++) if (!out->nnz[i]) memset(out->luma4x4[i], 0, sizeof(out->luma4x4[i]));
+    for (int ch = 0; ch < 2; ch++) if (!out->nnz[25 + ch]) memset(out->chroma_dc[ch], 0, sizeof(out->chroma_dc[ch]));
+    memset(luma_dc, 0, 16 * sizeof(int16_t));
+    if (out->nnz[24]) memcpy(luma_dc, h->dct.luma16x16_dc, 16 * sizeof(int16_t));
+    out->cbp_luma = h->mb.i_cbp_luma; out->cbp_chroma = h->mb.i_cbp_chroma;
+    for (int y = 0; y < 16; y++) memcpy(rec_y + 16 * y, h->mb.pic.p_fdec[0] + FDEC_STRIDE * y, 16);
+    for (int y = 0; y < 8; y++) {
+        memcpy(rec_u + 8 * y, h->mb.pic.p_fdec[1] + FDEC_STRIDE * y, 8);
+        memcpy(rec_v + 8 * y, h->mb.pic.p_fdec[2] + FDEC_STRIDE * y, 8);
+    }
+}
+
 /* intra mode costs with the reference's own predictors (x264_predict_16x16_init / x264_predict_8x8c_init tables) and mbcmp functions,
  * on an FDEC_STRIDE tile loaded with the neighbour pixels; the candidate lists and the lambda terms are the few lines of glue around
  * them in x264_mb_analyse_intra / _intra_chroma (static there), followed literally */

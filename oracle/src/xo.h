@@ -160,6 +160,15 @@ typedef struct {
 void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
                           uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out);
 
+/* One I_16x16 macroblock through x264_macroblock_encode: predict_16x16[mode16] + x264_mb_encode_i16x16 (S/encoder/macroblock.c:512-530,
+ * :184-270), predict_8x8c[mode_chroma] + x264_mb_encode_8x8_chroma(b_inter = 0) (:744-760, :272-363).  nb_y[33] / nb_u,nb_v[17] = corner,
+ * row above, left column of the neighbouring reconstruction; in->b_decimate = slice B || (b_dct_decimate && slice P) (:193);
+ * out->luma4x4[0..15] = AC levels (DC slot 0), luma_dc = h->dct.luma16x16_dc (zero unless out->nnz[24]); rec_* = reconstruction.
+ * Levels of uncoded blocks are reported as zero. */
+void xo_residual_intra16_mb(const xo_resid_in *in, int mode16, int mode_chroma, const uint8_t fenc_y[256], const uint8_t fenc_u[64],
+                            const uint8_t fenc_v[64], const uint8_t nb_y[33], const uint8_t nb_u[17], const uint8_t nb_v[17],
+                            uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out, int16_t luma_dc[16]);
+
 /* x264_macroblock_probe_skip (S/encoder/macroblock.c:797-883) with the prediction supplied (b_bidir = 1); 1 = skippable.
  * in->b_transform_8x8 / b_decimate are ignored (the probe always uses the 4x4 transform and the decimation scores). */
 int xo_probe_skip_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],

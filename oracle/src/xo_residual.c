@@ -66,6 +66,71 @@ static void to_tiles(uint8_t fe[16 * 16], uint8_t fd[32 * 16], const uint8_t *sr
     }
 }
 
+/* x264_mb_encode_8x8_chroma(h, b_inter, chroma_qp), macroblock.c:272-363; b_decimate as computed there (:275: only inter macroblocks decimate) */
+static void encode_chroma(const xo_resid_in *in, int b_inter, int b_decimate, const uint8_t fenc_u[64], const uint8_t fenc_v[64],
+                          uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out)
+{
+    uint8_t fe[16 * 16], fd[32 * 16];
+    int cbp_chroma = 0;
+    const int cqp = in->chroma_qp;
+    uint16_t mf[16], bias[16];
+    int dq[6][16];
+    xo_quant4_tables(in->cqm, 2 + b_inter, cqp, mf, bias); /* CQM_4IC + b_inter */
+    xo_dequant4_table(in->cqm, 2 + b_inter, dq);
+    for (int ch = 0; ch < 2; ch++) {
+        int16_t dct4[4][16], dc[4];
+        int score = 0, nz_ac = 0;
+        to_tiles(fe, fd, ch ? fenc_v : fenc_u, ch ? rec_v : rec_u, 8);
+        for (int i = 0; i < 4; i++)
+            xo_sub4x4_dct(dct4[i], fe + 4 * (i & 1) + 4 * (i >> 1) * 16, fd + 4 * (i & 1) + 4 * (i >> 1) * 32);
+        { /* dct2x2dc, macroblock.c:72-85 */
+            int d0 = dct4[0][0] + dct4[1][0], d1 = dct4[2][0] + dct4[3][0];
+            int d2 = dct4[0][0] - dct4[1][0], d3 = dct4[2][0] - dct4[3][0];
+            dc[0] = d0 + d1; dc[2] = d2 + d3; dc[1] = d0 - d1; dc[3] = d2 - d3; /* d[0][0], d[1][0], d[0][1], d[1][1] */
+            for (int i = 0; i < 4; i++) dct4[i][0] = 0;
+        }
+        for (int i = 0; i < 4; i++) {
+            int nz = xo_quant_4x4(dct4[i], mf, bias);
+            out->nnz[16 + i + ch * 4] = nz;
+            if (nz) {
+                nz_ac = 1;
+                xo_zigzag_scan_4x4(out->luma4x4[16 + i + ch * 4], dct4[i]);
+                xo_dequant_4x4(dct4[i], (const int(*)[16])dq, cqp);
+                if (b_decimate) score += xo_decimate_score(out->luma4x4[16 + i + ch * 4], 15);
+            }
+        }
+        int nz_dc = xo_quant_2x2_dc(dc, mf[0] >> 1, bias[0] << 1);
+        out->nnz[25 + ch] = nz_dc;
+        /* IDCT_DEQUANT_START, macroblock.c:42-53 */
+        int e0 = dc[0] + dc[1], e1 = dc[2] + dc[3], e2 = dc[0] - dc[1], e3 = dc[2] - dc[3];
+        int dmf = dq[cqp % 6][0], qbits = cqp / 6 - 5;
+        if (qbits > 0) { dmf <<= qbits; qbits = 0; }
+        if ((b_decimate && score < 7) || !nz_ac) {
+            for (int i = 0; i < 4; i++) out->nnz[16 + i + ch * 4] = 0;
+            if (nz_dc) {
+                int16_t o[4];
+                for (int i = 0; i < 4; i++) out->chroma_dc[ch][i] = dc[(i & 1) * 2 + (i >> 1)]; /* zigzag_scan_2x2_dc: level[i] = dct[x][y] */
+                o[0] = (int16_t)((e0 + e1) * dmf >> -qbits); o[1] = (int16_t)((e0 - e1) * dmf >> -qbits);
+                o[2] = (int16_t)((e2 + e3) * dmf >> -qbits); o[3] = (int16_t)((e2 - e3) * dmf >> -qbits);
+                xo_add_idct_dc(fd, o, 4);
+            }
+        } else {
+            cbp_chroma = 1;
+            if (nz_dc) {
+                for (int i = 0; i < 4; i++) out->chroma_dc[ch][i] = dc[(i & 1) * 2 + (i >> 1)];
+                dct4[0][0] = (int16_t)((e0 + e1) * dmf >> -qbits); dct4[1][0] = (int16_t)((e0 - e1) * dmf >> -qbits);
+                dct4[2][0] = (int16_t)((e2 + e3) * dmf >> -qbits); dct4[3][0] = (int16_t)((e2 - e3) * dmf >> -qbits);
+            }
+            for (int i = 0; i < 4; i++) xo_add4x4_idct(fd + 4 * (i & 1) + 4 * (i >> 1) * 32, dct4[i]);
+        }
+        uint8_t *rec = ch ? rec_v : rec_u;
+        for (int y = 0; y < 8; y++) memcpy(rec + 8 * y, fd + 32 * y, 8);
+    }
+    if (cbp_chroma) cbp_chroma = 2;
+    else if (out->nnz[25] | out->nnz[26]) cbp_chroma = 1;
+    out->cbp_chroma = cbp_chroma;
+}
+
 void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], const uint8_t fenc_u[64], const uint8_t fenc_v[64],
                           uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out)
 {
@@ -145,65 +210,61 @@ void xo_residual_inter_mb(const xo_resid_in *in, const uint8_t fenc_y[256], cons
     for (int y = 0; y < 16; y++) memcpy(rec_y + 16 * y, fd + 32 * y, 16);
     out->cbp_luma = cbp_luma;
 
-    /* ---- chroma: x264_mb_encode_8x8_chroma(h, b_inter=1, chroma_qp), macroblock.c:272-363 ---- */
-    int cbp_chroma = 0;
-    const int cqp = in->chroma_qp;
+    encode_chroma(in, 1, b_decimate, fenc_u, fenc_v, rec_u, rec_v, out);
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * One I_16x16 macroblock through x264_macroblock_encode (S/encoder/macroblock.c:512-530 predict + x264_mb_encode_i16x16 :184-270,
+ * then :744-760 chroma predict + x264_mb_encode_8x8_chroma with b_inter = 0).  nb_* = corner, row above, left column (as for
+ * xo_predict_*); in->b_decimate = (slice B) || (b_dct_decimate && slice P) (:193); in->b_transform_8x8 is ignored (:520).
+ * out->luma4x4[0..15] hold the AC levels (DC slot zero), luma_dc the zigzagged 4x4 DC levels (h->dct.luma16x16_dc), nnz[24] its flag. */
+void xo_residual_intra16_mb(const xo_resid_in *in, int mode16, int mode_chroma, const uint8_t fenc_y[256], const uint8_t fenc_u[64],
+                            const uint8_t fenc_v[64], const uint8_t nb_y[33], const uint8_t nb_u[17], const uint8_t nb_v[17],
+                            uint8_t rec_y[256], uint8_t rec_u[64], uint8_t rec_v[64], xo_resid_out *out, int16_t luma_dc[16])
+{
+    uint8_t fe[16 * 16], fd[32 * 16];
+    int16_t dct4[16][16], dc[16];
     uint16_t mf[16], bias[16];
     int dq[6][16];
-    xo_quant4_tables(in->cqm, 3, cqp, mf, bias); /* CQM_4PC */
-    xo_dequant4_table(in->cqm, 3, dq);
-    for (int ch = 0; ch < 2; ch++) {
-        int16_t dct4[4][16], dc[4];
-        int score = 0, nz_ac = 0;
-        to_tiles(fe, fd, ch ? fenc_v : fenc_u, ch ? rec_v : rec_u, 8);
-        for (int i = 0; i < 4; i++)
-            xo_sub4x4_dct(dct4[i], fe + 4 * (i & 1) + 4 * (i >> 1) * 16, fd + 4 * (i & 1) + 4 * (i >> 1) * 32);
-        { /* dct2x2dc, macroblock.c:72-85 */
-            int d0 = dct4[0][0] + dct4[1][0], d1 = dct4[2][0] + dct4[3][0];
-            int d2 = dct4[0][0] - dct4[1][0], d3 = dct4[2][0] - dct4[3][0];
-            dc[0] = d0 + d1; dc[2] = d2 + d3; dc[1] = d0 - d1; dc[3] = d2 - d3; /* d[0][0], d[1][0], d[0][1], d[1][1] */
-            for (int i = 0; i < 4; i++) dct4[i][0] = 0;
+    const int qp = in->qp;
+    memset(out, 0, sizeof(*out));
+    memset(luma_dc, 0, 16 * sizeof(int16_t));
+    xo_predict_16x16(mode16, nb_y, rec_y);
+    to_tiles(fe, fd, fenc_y, rec_y, 16);
+    xo_quant4_tables(in->cqm, 0, qp, mf, bias); /* CQM_4IY */
+    xo_dequant4_table(in->cqm, 0, dq);
+    int decimate_score = in->b_decimate ? 0 : 9, cbp_luma = 0;
+    for (int i = 0; i < 16; i++) {
+        xo_sub4x4_dct(dct4[i], fe + 4 * bx4[i] + 4 * by4[i] * 16, fd + 4 * bx4[i] + 4 * by4[i] * 32);
+        dc[bx4[i] + 4 * by4[i]] = dct4[i][0]; /* block_idx_xy_1d, macroblock.c:219 */
+        dct4[i][0] = 0;
+        int nz = xo_quant_4x4(dct4[i], mf, bias);
+        out->nnz[i] = nz;
+        if (nz) {
+            xo_zigzag_scan_4x4(out->luma4x4[i], dct4[i]);
+            xo_dequant_4x4(dct4[i], (const int(*)[16])dq, qp);
+            if (decimate_score < 6) decimate_score += xo_decimate_score(out->luma4x4[i], 15);
+            cbp_luma = 0xf;
         }
-        for (int i = 0; i < 4; i++) {
-            int nz = xo_quant_4x4(dct4[i], mf, bias);
-            out->nnz[16 + i + ch * 4] = nz;
-            if (nz) {
-                nz_ac = 1;
-                xo_zigzag_scan_4x4(out->luma4x4[16 + i + ch * 4], dct4[i]);
-                xo_dequant_4x4(dct4[i], (const int(*)[16])dq, cqp);
-                if (b_decimate) score += xo_decimate_score(out->luma4x4[16 + i + ch * 4], 15);
-            }
-        }
-        int nz_dc = xo_quant_2x2_dc(dc, mf[0] >> 1, bias[0] << 1);
-        out->nnz[25 + ch] = nz_dc;
-        /* IDCT_DEQUANT_START, macroblock.c:42-53 */
-        int e0 = dc[0] + dc[1], e1 = dc[2] + dc[3], e2 = dc[0] - dc[1], e3 = dc[2] - dc[3];
-        int dmf = dq[cqp % 6][0], qbits = cqp / 6 - 5;
-        if (qbits > 0) { dmf <<= qbits; qbits = 0; }
-        if ((b_decimate && score < 7) || !nz_ac) {
-            for (int i = 0; i < 4; i++) out->nnz[16 + i + ch * 4] = 0;
-            if (nz_dc) {
-                int16_t o[4];
-                for (int i = 0; i < 4; i++) out->chroma_dc[ch][i] = dc[(i & 1) * 2 + (i >> 1)]; /* zigzag_scan_2x2_dc: level[i] = dct[x][y] */
-                o[0] = (int16_t)((e0 + e1) * dmf >> -qbits); o[1] = (int16_t)((e0 - e1) * dmf >> -qbits);
-                o[2] = (int16_t)((e2 + e3) * dmf >> -qbits); o[3] = (int16_t)((e2 - e3) * dmf >> -qbits);
-                xo_add_idct_dc(fd, o, 4);
-            }
-        } else {
-            cbp_chroma = 1;
-            if (nz_dc) {
-                for (int i = 0; i < 4; i++) out->chroma_dc[ch][i] = dc[(i & 1) * 2 + (i >> 1)];
-                dct4[0][0] = (int16_t)((e0 + e1) * dmf >> -qbits); dct4[1][0] = (int16_t)((e0 - e1) * dmf >> -qbits);
-                dct4[2][0] = (int16_t)((e2 + e3) * dmf >> -qbits); dct4[3][0] = (int16_t)((e2 - e3) * dmf >> -qbits);
-            }
-            for (int i = 0; i < 4; i++) xo_add4x4_idct(fd + 4 * (i & 1) + 4 * (i >> 1) * 32, dct4[i]);
-        }
-        uint8_t *rec = ch ? rec_v : rec_u;
-        for (int y = 0; y < 8; y++) memcpy(rec + 8 * y, fd + 32 * y, 8);
     }
-    if (cbp_chroma) cbp_chroma = 2;
-    else if (out->nnz[25] | out->nnz[26]) cbp_chroma = 1;
-    out->cbp_chroma = cbp_chroma;
+    if (decimate_score < 6) { cbp_luma = 0; memset(out->nnz, 0, 16); }
+    xo_dct4x4dc(dc);
+    int nz = xo_quant_4x4_dc(dc, mf[0] >> 1, bias[0] << 1);
+    out->nnz[24] = nz;
+    if (nz) {
+        xo_zigzag_scan_4x4(luma_dc, dc);
+        xo_idct4x4dc(dc);
+        xo_dequant_4x4_dc(dc, (const int(*)[16])dq, qp);
+        if (cbp_luma) for (int i = 0; i < 16; i++) dct4[i][0] = dc[bx4[i] + 4 * by4[i]];
+    }
+    if (cbp_luma) for (int i = 0; i < 16; i++) xo_add4x4_idct(fd + 4 * bx4[i] + 4 * by4[i] * 32, dct4[i]);
+    else if (nz) xo_add_idct_dc(fd, dc, 16);
+    for (int y = 0; y < 16; y++) memcpy(rec_y + 16 * y, fd + 32 * y, 16);
+    out->cbp_luma = cbp_luma;
+    xo_predict_8x8c(mode_chroma, nb_u, rec_u);
+    xo_predict_8x8c(mode_chroma, nb_v, rec_v);
+    encode_chroma(in, 0, 0, fenc_u, fenc_v, rec_u, rec_v, out);
+    for (int i = 0; i < 24; i++) if (!out->nnz[i]) memset(out->luma4x4[i], 0, sizeof(out->luma4x4[i])); /* uncoded blocks read as zero */
 }
 
 /* ---------------------------------------------------------------------------------------------------------

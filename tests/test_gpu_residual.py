@@ -127,6 +127,86 @@ def test_residual_inter_frame(pkg, ctx, port, cqm):
     fenc.close(); fdec.close()
 
 
+def _intra16_modes(rng, mx, my):
+    """a valid (mode16, mode_chroma) pair for the neighbours a macroblock has (analyse.c:372-440)"""
+    if mx and my:
+        return int(rng.integers(0, 4)), int(rng.integers(0, 4))
+    if mx:
+        return int(rng.choice([4, 1])), int(rng.choice([4, 1]))      # DC_LEFT, H
+    if my:
+        return int(rng.choice([5, 0])), int(rng.choice([5, 2]))      # DC_TOP, V (luma 0, chroma 2)
+    return 6, 6
+
+
+def _intra16_reference(port, jobs, cqm, y1, u1, v1, ry, ru, rv):
+    """the listed macroblocks one after the other through the oracle, reading neighbours from / writing into the running reconstruction"""
+    outs = []
+    pads = [np.pad(a, 1) for a in (ry, ru, rv)]  # row above / column left of the frame edge: never used by a valid mode
+    for j in jobs:
+        mx, my = int(j["mb_x"]), int(j["mb_y"])
+        f = [np.ascontiguousarray(a[my * n:my * n + n, mx * n:mx * n + n]) for a, n in ((y1, 16), (u1, 8), (v1, 8))]
+        nb = []
+        for a, n in zip(pads, (16, 8, 8)):
+            x0, y0 = mx * n + 1, my * n + 1
+            nb.append(np.concatenate([[a[y0 - 1, x0 - 1]], a[y0 - 1, x0:x0 + n], a[y0:y0 + n, x0 - 1]]).astype(np.uint8))
+        rin = RIn(int(j["qp"]), int(j["chroma_qp"]), 0, (int(j["flags"]) >> 1) & 1, cqm)
+        o, dc, qy, qu, qv = port.residual_intra16_mb(rin, int(j["mode16"]), int(j["mode_chroma"]), f[0], f[1], f[2], nb[0], nb[1], nb[2])
+        for a, q, n in zip(pads, (qy, qu, qv), (16, 8, 8)):
+            a[my * n + 1:my * n + n + 1, mx * n + 1:mx * n + n + 1] = q.reshape(n, n)
+        outs.append((o, dc))
+    return outs, [a[1:-1, 1:-1] for a in pads]
+
+
+@pytest.mark.parametrize("size,cqm,subset", [((352, 288), 0, False), ((352, 288), 1, True), ((64, 48), 0, False), ((1920, 1080), 0, False),
+                                             ((1920, 1080), 1, True)])
+def test_residual_intra16_frame(pkg, ctx, port, size, cqm, subset):
+    """I_16x16 macroblocks of a frame as one wavefront launch (x264_mb_encode_i16x16 + intra chroma): coefficients and reconstruction
+    against the oracle run macroblock by macroblock in list order; subset: scattered intra macroblocks among final (inter) neighbours"""
+    from x264_vs2008_b200 import synth
+    w, h = size
+    clip = synth.Clip(w, h, seed=37, noise=3)
+    y1, u1, v1 = clip.yuv420(1)
+    y0, u0, v0 = clip.yuv420(0)
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    hp, wp = mbh * 16, mbw * 16
+    padto = lambda a, hh, ww: np.pad(a, ((0, hh - a.shape[0]), (0, ww - a.shape[1])), mode="edge")
+    y1, y0 = padto(y1, hp, wp), padto(y0, hp, wp)
+    u1, v1, u0, v0 = (padto(a, hp // 2, wp // 2) for a in (u1, v1, u0, v0))
+    fenc, fdec = ctx.frame(w, h, pkg.FRAME_CHROMA), ctx.frame(w, h, pkg.FRAME_CHROMA)
+    ctx.set_quant_preset(cqm)
+    rng = np.random.default_rng(17 + cqm)
+    for rep in range(2):
+        sel = [i for i in range(mbw * mbh) if not subset or rng.random() < 0.3]
+        jobs = np.zeros(len(sel), pkg.INTRA16_JOB)
+        for k, i in enumerate(sel):
+            mx, my = i % mbw, i // mbw
+            jobs[k]["mb_x"], jobs[k]["mb_y"] = mx, my
+            jobs[k]["qp"] = int(rng.integers(12, 46)) if rep else 26
+            jobs[k]["chroma_qp"] = int(rng.integers(12, 40)) if rep else 26
+            jobs[k]["mode16"], jobs[k]["mode_chroma"] = _intra16_modes(rng, mx, my)
+            jobs[k]["flags"] = pkg.RESID_DECIMATE if (rep and rng.random() < 0.5) else 0
+        fenc.upload(y1[:h, :w]); fenc.upload_chroma(u1[:h // 2, :w // 2], v1[:h // 2, :w // 2]); fenc.expand_border_mod16()
+        fdec.upload(y0[:h, :w]); fdec.upload_chroma(u0[:h // 2, :w // 2], v0[:h // 2, :w // 2]); fdec.expand_border_mod16()
+        want, recon = _intra16_reference(port, jobs, cqm, y1, u1, v1, y0.copy(), u0.copy(), v0.copy())
+        out = ctx.residual_intra16(fenc, fdec, jobs)
+        gy = fdec.download(pkg.PLANE_FULL)[32:32 + hp, 32:32 + wp]
+        gu, gv = (fdec.download(pl)[16:16 + hp // 2, 16:16 + wp // 2] for pl in (pkg.PLANE_CB, pkg.PLANE_CR))
+        for k, j in enumerate(jobs):
+            o, dc = want[k]
+            g = out[k]
+            mx, my = int(j["mb_x"]), int(j["mb_y"])
+            tag = (rep, k, mx, my, int(j["qp"]), int(j["chroma_qp"]), int(j["mode16"]), int(j["mode_chroma"]), int(j["flags"]))
+            assert (int(g["c"]["cbp_luma"]), int(g["c"]["cbp_chroma"])) == (o.cbp_luma, o.cbp_chroma), tag
+            assert list(g["c"]["nnz"]) == list(o.nnz), tag
+            assert np.array_equal(g["c"]["luma"], np.array(o.luma4x4)[:16].reshape(-1)), tag
+            assert np.array_equal(g["luma_dc"], dc), tag
+            assert np.array_equal(g["c"]["chroma_ac"], np.array(o.luma4x4)[16:24]), tag
+            assert np.array_equal(g["c"]["chroma_dc"], np.array(o.chroma_dc)), tag
+            assert np.array_equal(gy[my * 16:my * 16 + 16, mx * 16:mx * 16 + 16], recon[0][my * 16:my * 16 + 16, mx * 16:mx * 16 + 16]), tag
+        assert np.array_equal(gy, recon[0]) and np.array_equal(gu, recon[1]) and np.array_equal(gv, recon[2])
+    fenc.close(); fdec.close()
+
+
 @pytest.mark.parametrize("cqm", [0, 1])
 def test_probe_skip_pred_in_fdec(pkg, ctx, port, cqm):
     """x264_macroblock_probe_skip, b_bidir form: tiles around the skip decision laid out as the macroblocks of a CIF frame pair"""

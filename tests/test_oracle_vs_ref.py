@@ -403,6 +403,43 @@ def test_residual_inter_mb(port, ref, cqm):
                 assert np.array_equal(a[k], b[k]), tag
 
 
+def intra16_neighbours(rng, fy, fu, fv, flat):
+    """neighbour pixels (corner, row above, left column) resembling the source block (so that the residual is small) or random"""
+    out = []
+    for t, n in ((fy, 16), (fu, 8), (fv, 8)):
+        t2 = t.reshape(n, n).astype(np.int32)
+        nb = np.concatenate([[t2[0, 0]], t2[0], t2[:, 0]]) + rng.integers(-6, 7, 2 * n + 1)
+        if not flat:
+            nb = rng.integers(0, 256, 2 * n + 1)
+        out.append(np.clip(nb, 0, 255).astype(np.uint8))
+    return out
+
+
+@pytest.mark.parametrize("cqm", [0, 1])
+def test_residual_intra16_mb(port, ref, cqm):
+    """I_16x16 macroblocks through x264_macroblock_encode (predict + x264_mb_encode_i16x16 + intra chroma): port vs the reference"""
+    import helpers
+    rng = np.random.default_rng(70 + cqm)
+    seen_dc_only = seen_decimated = 0
+    for i, (qp, cqp, fy, fu, fv, py, pu, pv) in enumerate(helpers.skip_probe_cases(70 + cqm, 300)):
+        nby, nbu, nbv = intra16_neighbours(rng, fy, fu, fv, flat=i % 3 != 0)
+        mode16, modec, dec = int(rng.integers(0, 7)), int(rng.integers(0, 7)), int(rng.integers(0, 2))
+        rin = X.ResidIn(qp, min(cqp, 51), 0, dec, cqm)
+        a = port.residual_intra16_mb(rin, mode16, modec, fy, fu, fv, nby, nbu, nbv)
+        b = ref.residual_intra16_mb(rin, mode16, modec, fy, fu, fv, nby, nbu, nbv)
+        tag = (i, qp, cqp, mode16, modec, dec)
+        assert (a[0].cbp_luma, a[0].cbp_chroma) == (b[0].cbp_luma, b[0].cbp_chroma), tag
+        assert bytes(a[0].nnz) == bytes(b[0].nnz), tag
+        assert np.array_equal(np.array(a[0].luma4x4), np.array(b[0].luma4x4)), tag
+        assert np.array_equal(np.array(a[0].chroma_dc), np.array(b[0].chroma_dc)), tag
+        assert np.array_equal(a[1], b[1]), tag
+        for k in (2, 3, 4):
+            assert np.array_equal(a[k], b[k]), tag
+        seen_dc_only += a[0].cbp_luma == 0 and a[0].nnz[24] != 0
+        seen_decimated += dec and a[0].cbp_luma == 0
+    assert seen_dc_only and seen_decimated  # both reconstruction branches of macroblock.c:264-269 were exercised
+
+
 @pytest.mark.parametrize("cqm", [0, 1])
 def test_probe_skip(port, ref, cqm):
     """x264_macroblock_probe_skip (b_bidir form) + the lambda2 table its chroma gate reads"""

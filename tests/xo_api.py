@@ -301,6 +301,15 @@ class Oracle:
         (self.lib.xo_predict_8x8c if chroma else self.lib.xo_predict_16x16)(mode, _ptr(nb), _ptr(out))
         return out
 
+    def residual_intra16_mb(self, rin, mode16, mode_chroma, fy, fu, fv, nby, nbu, nbv):
+        """one I_16x16 macroblock through x264_macroblock_encode -> (ResidOut, luma_dc int16[16], rec_y, rec_u, rec_v)"""
+        ry, ru, rv = np.zeros(256, np.uint8), np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        dc = np.zeros(16, np.int16)
+        o = ResidOut()
+        self.lib.xo_residual_intra16_mb(C.byref(rin), mode16, mode_chroma, _ptr(fy), _ptr(fu), _ptr(fv), _ptr(nby), _ptr(nbu), _ptr(nbv),
+                                        _ptr(ry), _ptr(ru), _ptr(rv), C.byref(o), _ptr(dc, i16p))
+        return o, dc, ry, ru, rv
+
     def probe_skip_mb(self, rin, fy, fu, fv, py, pu, pv):
         """x264_macroblock_probe_skip with the prediction supplied -> 0/1"""
         return int(self.lib.xo_probe_skip_mb(C.byref(rin), _ptr(fy), _ptr(fu), _ptr(fv), _ptr(py), _ptr(pu), _ptr(pv)))

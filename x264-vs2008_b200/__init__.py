@@ -19,6 +19,10 @@ RESID_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("qp", "u1"), ("chroma_q
 MB_COEFFS = np.dtype([("luma", "<i2", (256,)), ("chroma_ac", "<i2", (8, 16)), ("chroma_dc", "<i2", (2, 4)), ("nnz", "u1", (27,)),
                       ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("reserved", "u1", (3,))], align=True)
 assert RESID_JOB.itemsize == 8 and MB_COEFFS.itemsize == 816
+INTRA16_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("qp", "u1"), ("chroma_qp", "u1"), ("mode16", "u1"), ("mode_chroma", "u1"), ("flags", "u1"),
+                        ("reserved", "u1", (3,))], align=True)
+MB_COEFFS_I16 = np.dtype([("c", MB_COEFFS), ("luma_dc", "<i2", (16,))], align=True)
+assert INTRA16_JOB.itemsize == 12 and MB_COEFFS_I16.itemsize == 848
 SKIP_JOB = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("mvx", "<i2"), ("mvy", "<i2"), ("qp", "u1"), ("chroma_qp", "u1"), ("flags", "u1"),
                      ("reserved", "u1")], align=True)
 assert SKIP_JOB.itemsize == 12
@@ -127,6 +131,8 @@ def lib():
         L.x264_cuda_block_dc.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp]
         L.x264_cuda_residual_inter.argtypes = [vp, vp, vp, vp, ip, vp]
         L.x264_cuda_residual_inter_dev.argtypes = [vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_residual_intra16.argtypes = [vp, vp, vp, vp, ip, vp]
+        L.x264_cuda_residual_intra16_dev.argtypes = [vp, vp, vp, vp, ip, vp]
         L.x264_cuda_frame_download.argtypes = [vp, vp, ip, vp, ip]
         for n in ("x264_cuda_frame_expand_border", "x264_cuda_frame_expand_border_mod16", "x264_cuda_frame_filter", "x264_cuda_frame_init_lowres"):
             if hasattr(L, n):
@@ -389,6 +395,13 @@ class Context:
         jobs = np.ascontiguousarray(jobs, RESID_JOB)
         out = np.zeros(len(jobs), MB_COEFFS)
         self.check(lib().x264_cuda_residual_inter(self.h, fenc.h, fdec.h, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
+
+    def residual_intra16(self, fenc, fdec, jobs):
+        """I_16x16 macroblocks through x264_macroblock_encode, wavefront in list order (S/encoder/macroblock.c:184-270, :272-363)"""
+        jobs = np.ascontiguousarray(jobs, INTRA16_JOB)
+        out = np.zeros(len(jobs), MB_COEFFS_I16)
+        self.check(lib().x264_cuda_residual_intra16(self.h, fenc.h, fdec.h, jobs.ctypes.data, len(jobs), out.ctypes.data))
         return out
 
     def me_search_small(self, fenc, fref, method, me_range, subme, jobs):

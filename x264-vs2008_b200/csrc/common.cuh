@@ -26,6 +26,7 @@ struct x264_cuda_t {
     int cost_ptrs_dirty;
     // staging for the host-pointer entry points
     int *d_la_order; int la_w, la_h, la_n; int la_epoch; int *d_la_sums; // lookahead wavefront order (interior list, then all blocks) + result cells
+    void *d_i16_state; int i16_state_n; unsigned i16_epoch;              // intra 16x16 encode wavefront: per-macroblock state words + ticket
     void *d_la_vbv;                                                      // per-evaluation row sums + inverse qscale factors (VBV / AQ form)
     int *d_deblock_progress; int deblock_rows; void *d_deblock_recs; size_t d_deblock_recs_size;   // per-row progress counters of x264_cuda_frame_deblock
     int resid_no_dct8;   // one-shot hint from x264_cuda_residual_inter to its _dev call

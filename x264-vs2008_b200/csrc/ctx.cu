@@ -71,7 +71,7 @@ extern "C" void x264_cuda_close(x264_cuda_t *ctx)
     cudaFree(ctx->d_mb_ticket);
     cudaFree(ctx->d_deblock_progress);
     cudaFree(ctx->d_deblock_recs);
-    cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums); cudaFree(ctx->d_la_vbv);
+    cudaFree(ctx->d_la_order); cudaFree(ctx->d_la_sums); cudaFree(ctx->d_la_vbv); cudaFree(ctx->d_i16_state);
     cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_ring);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -314,10 +314,21 @@ extern "C" void *x264_cuda_frame_plane(const x264_cuda_frame_t *f, int plane)
     return nullptr;
 }
 
+// a picture larger than the frame's macroblock-padded area would overwrite the neighbouring planes of the allocation
+static int upload_bounds(x264_cuda_t *ctx, const char *who, int cols, int rows, int max_cols, int max_rows)
+{
+    if (cols < 0 || rows < 0 || cols > max_cols || rows > max_rows) {
+        snprintf(ctx->err, 256, "%s: %d x %d does not fit the frame's %d x %d plane", who, cols, rows, max_cols, max_rows);
+        return -1;
+    }
+    return 0;
+}
+
 extern "C" int x264_cuda_frame_upload(x264_cuda_t *ctx, x264_cuda_frame_t *f, const uint8_t *src, int src_stride,
                                       int cols, int rows)
 {
     x264_cuda_enter(ctx);
+    if (upload_bounds(ctx, "x264_cuda_frame_upload", cols, rows, f->g.mb_width * 16, f->g.lines)) return -1;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, src, src_stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
@@ -329,6 +340,7 @@ extern "C" int x264_cuda_frame_upload_chroma(x264_cuda_t *ctx, x264_cuda_frame_t
         snprintf(ctx->err, 256, "x264_cuda_frame_upload_chroma: frame has no chroma plane %d", plane);
         return -1;
     }
+    if (upload_bounds(ctx, "x264_cuda_frame_upload_chroma", cols, rows, f->g.mb_width * 8, f->g.lines / 2)) return -1;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(f->chroma[plane - X264_CUDA_PLANE_CB], f->stride_c, src, src_stride, cols, rows,
                                     cudaMemcpyHostToDevice, ctx->stream));
     return 0;
@@ -337,6 +349,7 @@ extern "C" int x264_cuda_frame_upload_dev(x264_cuda_t *ctx, x264_cuda_frame_t *f
                                           int cols, int rows)
 {
     x264_cuda_enter(ctx);
+    if (upload_bounds(ctx, "x264_cuda_frame_upload_dev", cols, rows, f->g.mb_width * 16, f->g.lines)) return -1;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(f->plane[0], f->g.stride, dsrc, src_stride, cols, rows, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }

@@ -776,6 +776,8 @@ __device__ __forceinline__ void load_row16_s(uint32_t (&dst)[4], const uint32_t 
 #pragma unroll
     for (int i = 0; i < 4; i++) dst[i] = __funnelshift_r(w[i], w[i + 1], sh);
 }
+// (measured and rejected: the same extraction on the FMA pipe, hi32(w[i] * 2^(32-sh)) + lo32(w[i+1] * 2^(32-sh)) as IMAD.HI + IMAD, to take the
+// four SHF per row off the ALU pipe that VABSDIFF4 saturates — 0.111 ms per 1080p launch against 0.101: IMAD.HI issues at a quarter rate)
 __device__ __forceinline__ void v3_scan(const SlotHead &H, const uint16_t *cxp_tab, const uint32_t (*cyt)[12], const uint8_t *tile, int lane, uint32_t (&best)[NP])
 {
     const int ux0 = H.ux0, uwidth = H.uwidth, urows = H.urows;

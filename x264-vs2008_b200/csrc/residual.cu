@@ -165,6 +165,97 @@ __device__ __forceinline__ void store4x4(uint8_t *p, int stride, const int (&v)[
                                                 ((uint32_t)v[y * 4 + 3] << 24);
 }
 
+// x264_mb_encode_8x8_chroma (macroblock.c:272-363) on the chroma lanes 16..23 of a macroblock's warp (U0..3, V0..3): f = source block,
+// p = prediction (both valid on those lanes), dst = where the lane's reconstructed 4x4 goes (always stored when store_pred: the intra
+// caller has the prediction in registers only).  list = CQM_4IC + b_inter; decim as computed at :275.  zero_uncoded: AC levels of blocks
+// whose nnz ends up 0 (DC-only planes) are left zero in the record.  Returns i_cbp_chroma on every lane.
+__device__ __forceinline__ int chroma_blocks(const QuantTables *__restrict__ qt, int list, int cqp, bool decim, bool intra, int lane, const int (&f)[16],
+                                             int (&p)[16], uint8_t *dst, int stride_c, x264_cuda_mb_coeffs_t *out)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int cl = lane - 16;
+    const bool mine = lane >= 16 && lane < 24;
+    const int ch = (cl >> 2) & 1, bi = cl & 3;
+    int c[16], nz = 0, score = 0, dc0 = 0;
+    int16_t lv[16];
+    if (mine) {
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
+        fwd4x4(d, c);
+        dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
+        const uint16_t *mf = qt->q4mf[list][cqp], *bias = qt->q4bias[list][cqp];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+        nz = nz != 0;
+        if (nz) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
+            if (decim) score = decimate_score(lv, 1, 16);
+            const int *dmf = qt->dq4[list][cqp % 6];
+            const int qbits = cqp / 6 - 4;
+#pragma unroll
+            for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+        }
+    }
+    // gather the four DCs / scores / nz of this lane's channel
+    const int cb = 16 + ch * 4;
+    const int b0 = __shfl_sync(FULL, dc0, cb), b1 = __shfl_sync(FULL, dc0, cb + 1), b2 = __shfl_sync(FULL, dc0, cb + 2),
+              b3 = __shfl_sync(FULL, dc0, cb + 3);
+    int tot = 0, nz_ac = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { tot += __shfl_sync(FULL, score, cb + k); nz_ac |= __shfl_sync(FULL, nz, cb + k); }
+    // dct2x2dc: d[0][0], d[1][0], d[0][1], d[1][1] (macroblock.c:72-80), flat order d[0][0],d[0][1],d[1][0],d[1][1]
+    const int e0 = b0 + b1, e1 = b2 + b3, e2 = b0 - b1, e3 = b2 - b3;
+    int dc[4] = { s16(e0 + e1), s16(e0 - e1), s16(e2 + e3), s16(e2 - e3) };
+    const int mf0 = qt->q4mf[list][cqp][0] >> 1, bias0 = qt->q4bias[list][cqp][0] << 1;
+    int nz_dc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { dc[k] = quant1(dc[k], mf0, bias0); nz_dc |= dc[k]; }
+    nz_dc = nz_dc != 0;
+    // IDCT_DEQUANT_START (macroblock.c:42-53)
+    const int g0 = dc[0] + dc[1], g1 = dc[2] + dc[3], g2 = dc[0] - dc[1], g3 = dc[2] - dc[3];
+    int dmf = qt->dq4[list][cqp % 6][0], qbits = cqp / 6 - 5;
+    if (qbits > 0) { dmf <<= qbits; qbits = 0; }
+    const int o4[4] = { s16((g0 + g1) * dmf >> -qbits), s16((g0 - g1) * dmf >> -qbits), s16((g2 + g3) * dmf >> -qbits),
+                        s16((g2 - g3) * dmf >> -qbits) };
+    const bool dc_only = (decim && tot < 7) || !nz_ac;
+    if (mine) {
+        if (nz && !(intra && dc_only)) {
+#pragma unroll
+            for (int k = 0; k < 16; k += 2)
+                *(uint32_t *)&out->chroma_ac[cl][k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
+        }
+        out->nnz[16 + cl] = (uint8_t)(dc_only ? 0 : nz);
+        if (bi == 0) {
+            out->nnz[25 + ch] = (uint8_t)nz_dc;
+            if (nz_dc) { // zigzag_scan_2x2_dc: level[i] = dct[x][y]
+                out->chroma_dc[ch][0] = (int16_t)dc[0]; out->chroma_dc[ch][1] = (int16_t)dc[2];
+                out->chroma_dc[ch][2] = (int16_t)dc[1]; out->chroma_dc[ch][3] = (int16_t)dc[3];
+            }
+        }
+        if (dc_only) {
+            if (nz_dc) { // add8x8_idct_dc: block bi gets dct[bi>>1][bi&1] == o4[bi]
+                const int v = s16((o4[bi] + 32) >> 6);
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + v);
+                store4x4(dst, stride_c, p);
+            } else if (intra)
+                store4x4(dst, stride_c, p);
+        } else {
+            if (nz_dc) c[0] = o4[bi]; // idct_dequant_2x2_dc -> dct4x4[bi][0][0]
+            int r[16];
+            inv4x4(c, r);
+#pragma unroll
+            for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + r[k]);
+            store4x4(dst, stride_c, p);
+        }
+    }
+    const int ac_u = __shfl_sync(FULL, (int)!dc_only, 16), ac_v = __shfl_sync(FULL, (int)!dc_only, 20);
+    const int dcn_u = __shfl_sync(FULL, nz_dc, 16), dcn_v = __shfl_sync(FULL, nz_dc, 20);
+    return (ac_u | ac_v) ? 2 : (dcn_u | dcn_v) ? 1 : 0;
+}
+
 // ALLOW8 = false is the variant for batches without 8x8-transform macroblocks: without the 64-coefficient path it needs half the
 // registers, i.e. twice the resident warps for a kernel that is bound by instruction latency
 template <bool ALLOW8>
@@ -291,87 +382,14 @@ __global__ void __launch_bounds__(128) residual_inter_kernel(const QuantTables *
         const int cl = lane - 16;                 // 0..7 on the chroma lanes
         const bool mine = lane >= 16 && lane < 24;
         const int ch = (cl >> 2) & 1, bi = cl & 3;
-        int c[16], p[16], nz = 0, score = 0, dc0 = 0;
+        int f[16], p[16];
         const uint8_t *fe = (ch ? fr.fe_v : fr.fe_u) + ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * fr.stride_c + job.mb_x * 8 + (bi & 1) * 4;
         uint8_t *dst = (ch ? fr.fd_v : fr.fd_u) + ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * fr.stride_c + job.mb_x * 8 + (bi & 1) * 4;
-        if (mine) {
-            int f[16], d[16];
-            load4x4(fe, fr.stride_c, f);
-            load4x4(dst, fr.stride_c, p);
-#pragma unroll
-            for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
-            fwd4x4(d, c);
-            dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
-            const uint16_t *mf = qt->q4mf[3][cqp], *bias = qt->q4bias[3][cqp]; // CQM_4PC
-#pragma unroll
-            for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
-            nz = nz != 0;
-            if (nz) {
-                int16_t lv[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
-#pragma unroll
-                for (int k = 0; k < 16; k += 2)
-                    *(uint32_t *)&out->chroma_ac[cl][k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
-                if (decim) score = decimate_score(lv, 1, 16);
-                const int *dmf = qt->dq4[3][cqp % 6];
-                const int qbits = cqp / 6 - 4;
-#pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
-            }
-        }
-        // gather the four DCs / scores / nz of this lane's channel
-        const int cb = 16 + ch * 4;
-        const int b0 = __shfl_sync(FULL, dc0, cb), b1 = __shfl_sync(FULL, dc0, cb + 1), b2 = __shfl_sync(FULL, dc0, cb + 2),
-                  b3 = __shfl_sync(FULL, dc0, cb + 3);
-        int tot = 0, nz_ac = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { tot += __shfl_sync(FULL, score, cb + k); nz_ac |= __shfl_sync(FULL, nz, cb + k); }
-        // dct2x2dc: d[0][0], d[1][0], d[0][1], d[1][1] (macroblock.c:72-80), flat order d[0][0],d[0][1],d[1][0],d[1][1]
-        const int e0 = b0 + b1, e1 = b2 + b3, e2 = b0 - b1, e3 = b2 - b3;
-        int dc[4] = { s16(e0 + e1), s16(e0 - e1), s16(e2 + e3), s16(e2 - e3) };
-        const int mf0 = qt->q4mf[3][cqp][0] >> 1, bias0 = qt->q4bias[3][cqp][0] << 1;
-        int nz_dc = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { dc[k] = quant1(dc[k], mf0, bias0); nz_dc |= dc[k]; }
-        nz_dc = nz_dc != 0;
-        // IDCT_DEQUANT_START (macroblock.c:42-53)
-        const int g0 = dc[0] + dc[1], g1 = dc[2] + dc[3], g2 = dc[0] - dc[1], g3 = dc[2] - dc[3];
-        int dmf = qt->dq4[3][cqp % 6][0], qbits = cqp / 6 - 5;
-        if (qbits > 0) { dmf <<= qbits; qbits = 0; }
-        const int o4[4] = { s16((g0 + g1) * dmf >> -qbits), s16((g0 - g1) * dmf >> -qbits), s16((g2 + g3) * dmf >> -qbits),
-                            s16((g2 - g3) * dmf >> -qbits) };
-        const bool dc_only = (decim && tot < 7) || !nz_ac;
-        if (mine) {
-            out->nnz[16 + cl] = (uint8_t)(dc_only ? 0 : nz);
-            if (bi == 0) {
-                out->nnz[25 + ch] = (uint8_t)nz_dc;
-                if (nz_dc) { // zigzag_scan_2x2_dc: level[i] = dct[x][y]
-                    out->chroma_dc[ch][0] = (int16_t)dc[0]; out->chroma_dc[ch][1] = (int16_t)dc[2];
-                    out->chroma_dc[ch][2] = (int16_t)dc[1]; out->chroma_dc[ch][3] = (int16_t)dc[3];
-                }
-            }
-            if (dc_only) {
-                if (nz_dc) { // add8x8_idct_dc: block bi gets dct[bi>>1][bi&1] == o4[bi]
-                    const int v = s16((o4[bi] + 32) >> 6);
-#pragma unroll
-                    for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + v);
-                    store4x4(dst, fr.stride_c, p);
-                }
-            } else {
-                if (nz_dc) c[0] = o4[bi]; // idct_dequant_2x2_dc -> dct4x4[bi][0][0]
-                int r[16];
-                inv4x4(c, r);
-#pragma unroll
-                for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + r[k]);
-                store4x4(dst, fr.stride_c, p);
-            }
-        }
-        const int ac_u = __shfl_sync(FULL, (int)!dc_only, 16), ac_v = __shfl_sync(FULL, (int)!dc_only, 20);
-        const int dcn_u = __shfl_sync(FULL, nz_dc, 16), dcn_v = __shfl_sync(FULL, nz_dc, 20);
+        if (mine) { load4x4(fe, fr.stride_c, f); load4x4(dst, fr.stride_c, p); }
+        const int cbp_chroma = chroma_blocks(qt, 3 /* CQM_4PC */, cqp, decim, false, lane, f, p, dst, fr.stride_c, out);
         if (lane == 0) {
             out->cbp_luma = (uint8_t)cbp_luma;
-            out->cbp_chroma = (uint8_t)((ac_u | ac_v) ? 2 : (dcn_u | dcn_v) ? 1 : 0);
+            out->cbp_chroma = (uint8_t)cbp_chroma;
         }
     }
 }
@@ -522,6 +540,301 @@ extern "C" int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_
     for (int i = 0; i < n_jobs && !any8; i++) any8 = jobs[i].flags & X264_CUDA_RESID_8x8DCT;
     ctx->resid_no_dct8 = !any8;
     if (x264_cuda_residual_inter_dev(ctx, fenc, fdec, ds, n_jobs, ds + jb_al)) return -1;
+    if (x264_cuda_results_out(ctx, coeffs, ds + jb_al, hs + jb_al, rb)) return -1;
+    return 0;
+}
+
+// =========================================================================================================
+// I_16x16 macroblocks through x264_macroblock_encode: predict_16x16[mode] + x264_mb_encode_i16x16 (S/encoder/macroblock.c:512-530,
+// :184-270), predict_8x8c[mode] + x264_mb_encode_8x8_chroma(b_inter = 0) (:744-760, :272-363).  The prediction of a macroblock reads the
+// RECONSTRUCTION of its left / top / top-left neighbours, so the macroblocks of a call form a wavefront: ONE WARP PER MACROBLOCK, persistent
+// warps pull jobs by ticket in list order (the list must name a macroblock after the neighbours it depends on: raster order does), and a
+// per-macroblock state word (epoch-stamped: pending / done) tells a warp which neighbours belong to this call and when they are final.
+// A waiting warp only ever waits for smaller tickets, which running warps hold, so the scheme cannot deadlock whatever the grid size.
+// Lane roles as in residual_inter_kernel: lanes 0..15 the luma 4x4 blocks (block_idx order), lanes 16..23 the chroma blocks; the 4x4 luma
+// DC transform (dct4x4dc / quant_4x4_dc / idct4x4dc / dequant_4x4_dc) runs on lane 0 over values gathered by shuffles.
+namespace {
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void intra16_mark_kernel(const x264_cuda_intra16_job_t *__restrict__ jobs, int n_jobs, int mb_width, unsigned *state, unsigned epoch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_jobs) state[jobs[i].mb_y * mb_width + jobs[i].mb_x] = epoch << 1;
+}
+
+// predictor kinds of a mode number: luma enum intra16x16_pred_e (V H DC P DC_LEFT DC_TOP DC_128), chroma enum intra_chroma_pred_e
+// (DC H V P DC_LEFT DC_TOP DC_128) -> 0 V, 1 H, 2 DC-like, 3 plane
+__device__ __forceinline__ int pred_kind(int mode, bool chroma) { return mode == 1 ? 1 : mode == 3 ? 3 : mode == (chroma ? 2 : 0) ? 0 : 2; }
+
+struct Intra16Edges { uint8_t y[40], u[24], v[24]; }; // [3] corner, [4..4+n) row above, [4+n..4+2n) left column
+
+__global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables *__restrict__ qt, FrameRefs fr, int mb_width,
+                                                               const x264_cuda_intra16_job_t *__restrict__ jobs, int n_jobs,
+                                                               x264_cuda_mb_coeffs_i16_t *__restrict__ outs, unsigned *state, unsigned epoch,
+                                                               int *ticket)
+{
+    __shared__ __align__(4) Intra16Edges s_edges[4];
+    __shared__ int s_dc[4][16];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    Intra16Edges &E = s_edges[wid];
+    for (;;) {
+        int jb = 0;
+        if (lane == 0) jb = atomicAdd(ticket, 1);
+        jb = __shfl_sync(FULL, jb, 0);
+        if (jb >= n_jobs) return;
+        const x264_cuda_intra16_job_t job = jobs[jb];
+        x264_cuda_mb_coeffs_i16_t *out = outs + jb;
+        const int qp = min((int)job.qp, 51), cqp = min((int)job.chroma_qp, 51);
+        const bool decim = job.flags & X264_CUDA_RESID_DECIMATE;
+        const int kind_y = pred_kind(job.mode16, false), kind_c = pred_kind(job.mode_chroma, true);
+        for (int i = lane; i < (int)(sizeof(x264_cuda_mb_coeffs_i16_t) / 4); i += 32) ((uint32_t *)out)[i] = 0;
+        // source blocks first: they do not depend on anybody
+        const int bx = (lane & 1) + ((lane >> 2) & 1) * 2, by = ((lane >> 1) & 1) + ((lane >> 3) & 1) * 2; // block_idx_x/y
+        const int cl = lane - 16, ch = (cl >> 2) & 1, bi = cl & 3;
+        int f[16];
+        if (lane < 16) load4x4(fr.fe_y + ((size_t)job.mb_y * 16 + by * 4) * fr.stride + job.mb_x * 16 + bx * 4, fr.stride, f);
+        else if (lane < 24) load4x4((ch ? fr.fe_v : fr.fe_u) + ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * fr.stride_c + job.mb_x * 8 + (bi & 1) * 4, fr.stride_c, f);
+        // ---- wait for the neighbours that belong to this call: left, top, top-left (lanes 0..2)
+        if (lane < 3) {
+            const int nx = job.mb_x - (lane != 1), ny = job.mb_y - (lane != 0);
+            if (nx >= 0 && ny >= 0) {
+                const unsigned *w = state + ny * mb_width + nx;
+                unsigned v = ld_acquire_u32(w);
+                while ((v >> 1) == epoch && !(v & 1)) v = ld_acquire_u32(w);
+            }
+        }
+        __syncwarp();
+        // ---- neighbour pixels straight from L2 (another SM wrote them a moment ago)
+        {
+            const uint8_t *py = fr.fd_y + (size_t)job.mb_y * 16 * fr.stride + job.mb_x * 16;
+            if (lane < 16) { E.y[4 + lane] = __ldcg(py - (ptrdiff_t)fr.stride + lane); E.y[20 + lane] = __ldcg(py + (ptrdiff_t)lane * fr.stride - 1); }
+            if (lane == 16) E.y[3] = __ldcg(py - (ptrdiff_t)fr.stride - 1);
+            const size_t co = (size_t)job.mb_y * 8 * fr.stride_c + job.mb_x * 8;
+            if (lane >= 16) {
+                const int k = lane & 7;
+                const uint8_t *pc = ((lane & 8) ? fr.fd_v : fr.fd_u) + co;
+                uint8_t *e = (lane & 8) ? E.v : E.u;
+                e[4 + k] = __ldcg(pc - (ptrdiff_t)fr.stride_c + k); e[12 + k] = __ldcg(pc + (ptrdiff_t)k * fr.stride_c - 1);
+                if (k == 0) e[3] = __ldcg(pc - (ptrdiff_t)fr.stride_c - 1);
+            }
+        }
+        __syncwarp();
+        // ---- prediction of this lane's 4x4 block
+        int p[16];
+        if (lane < 16) { // predict.c:40-170
+            const uint8_t *e = E.y;
+            const int x0 = bx * 4, y0 = by * 4;
+            if (kind_y == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = e[4 + x0 + (k & 3)];
+            } else if (kind_y == 1) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = e[20 + y0 + (k >> 2)];
+            } else if (kind_y == 2) {
+                int st = 0, sl = 0;
+#pragma unroll
+                for (int i = 0; i < 16; i++) { st += e[4 + i]; sl += e[20 + i]; }
+                const int m = job.mode16;
+                const int dc = m == 2 ? (st + sl + 16) >> 5 : m == 4 ? (sl + 8) >> 4 : m == 5 ? (st + 8) >> 4 : 128;
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = dc;
+            } else {
+                int H = 0, V = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    H += (i + 1) * ((int)e[4 + 8 + i] - (int)(6 - i >= 0 ? e[4 + 6 - i] : e[3]));
+                    V += (i + 1) * ((int)e[20 + 8 + i] - (int)(6 - i >= 0 ? e[20 + 6 - i] : e[3]));
+                }
+                const int a = 16 * (e[20 + 15] + e[4 + 15]), b = (5 * H + 32) >> 6, c = (5 * V + 32) >> 6, i00 = a - 7 * (b + c) + 16;
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8((i00 + b * (x0 + (k & 3)) + c * (y0 + (k >> 2))) >> 5);
+            }
+        } else if (lane < 24) { // predict.c:172-336
+            const uint8_t *e = ch ? E.v : E.u;
+            const int x0 = (bi & 1) * 4, y0 = (bi >> 1) * 4;
+            if (kind_c == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = e[4 + x0 + (k & 3)];
+            } else if (kind_c == 1) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = e[12 + y0 + (k >> 2)];
+            } else if (kind_c == 2) {
+                int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { s0 += e[4 + i]; s1 += e[8 + i]; s2 += e[12 + i]; s3 += e[16 + i]; }
+                int dcq[4] = { 128, 128, 128, 128 };
+                const int m = job.mode_chroma;
+                if (m == 0) { dcq[0] = (s0 + s2 + 4) >> 3; dcq[1] = (s1 + 2) >> 2; dcq[2] = (s3 + 2) >> 2; dcq[3] = (s1 + s3 + 4) >> 3; } // predict.c:234-277
+                else if (m == 4) { dcq[0] = dcq[1] = (s2 + 2) >> 2; dcq[2] = dcq[3] = (s3 + 2) >> 2; }                                // :184-212
+                else if (m == 5) { dcq[0] = dcq[2] = (s0 + 2) >> 2; dcq[1] = dcq[3] = (s1 + 2) >> 2; }                                // :213-233
+                const int dc = dcq[bi];
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = dc;
+            } else {
+                int H = 0, V = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    H += (i + 1) * ((int)e[4 + 4 + i] - (int)(2 - i >= 0 ? e[4 + 2 - i] : e[3]));
+                    V += (i + 1) * ((int)e[12 + 4 + i] - (int)(2 - i >= 0 ? e[12 + 2 - i] : e[3]));
+                }
+                const int a = 16 * (e[12 + 7] + e[4 + 7]), b = (17 * H + 16) >> 5, c = (17 * V + 16) >> 5, i00 = a - 3 * (b + c) + 16;
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8((i00 + b * (x0 + (k & 3)) + c * (y0 + (k >> 2))) >> 5);
+            }
+        }
+        // ---- luma: x264_mb_encode_i16x16
+        int c[16], nz = 0, score = 0, dc0 = 0;
+        int16_t lv[16];
+        uint8_t *dst = fr.fd_y + ((size_t)job.mb_y * 16 + by * 4) * fr.stride + job.mb_x * 16 + bx * 4;
+        if (lane < 16) {
+            int d[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
+            fwd4x4(d, c);
+            dc0 = c[0]; c[0] = 0;                                                   // :218-220
+            const uint16_t *mf = qt->q4mf[0][qp], *bias = qt->q4bias[0][qp];        // CQM_4IY
+#pragma unroll
+            for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
+            nz = nz != 0;
+            if (nz) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
+                if (decim) score = decimate_score(lv, 1, 16);                       // decimate_score15, :230
+                const int *dmf = qt->dq4[0][qp % 6];
+                const int qbits = qp / 6 - 4;
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
+            }
+        }
+        // the running "if (decimate_score < 6) decimate_score += ..." of :230 ends below 6 exactly when the total does (scores are >= 0)
+        int tot = lane < 16 ? score : 0, any = lane < 16 ? nz : 0;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { tot += __shfl_xor_sync(FULL, tot, o); any |= __shfl_xor_sync(FULL, any, o); }
+        tot = __shfl_sync(FULL, tot, 0); any = __shfl_sync(FULL, any, 0);
+        const int cbp_luma = (any && !(decim && tot < 6)) ? 0xf : 0;                 // :232, :238-245
+        // 4x4 DC block on lane 0: dct_dc4x4[0][block_idx_xy_1d[i]] = dct4x4[i][0][0]
+        int dcs[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int v = __shfl_sync(FULL, dc0, i);
+            dcs[((i & 1) + ((i >> 2) & 1) * 2) + 4 * (((i >> 1) & 1) + ((i >> 3) & 1) * 2)] = v;
+        }
+        int nz_dc = 0;
+        if (lane == 0) {
+            hadamard_dc(dcs, true);                                                 // dct4x4dc, :247
+            const int mf0 = qt->q4mf[0][qp][0] >> 1, bias0 = qt->q4bias[0][qp][0] << 1; // :251
+#pragma unroll
+            for (int k = 0; k < 16; k++) { dcs[k] = quant1(dcs[k], mf0, bias0); nz_dc |= dcs[k]; }
+            nz_dc = nz_dc != 0;
+            if (nz_dc) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) out->luma_dc[k] = (int16_t)dcs[c_zz4[k]]; // zigzag scan_4x4, :256
+                hadamard_dc(dcs, false);                                            // idct4x4dc, :259
+                const int qbits = qp / 6 - 6, dmf0 = qt->dq4[0][qp % 6][0];         // dequant_4x4_dc, quant.c:148-178
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    dcs[k] = qbits >= 0 ? s16(dcs[k] * (dmf0 << qbits)) : s16((dcs[k] * dmf0 + (1 << (-qbits - 1))) >> (-qbits));
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) s_dc[wid][k] = dcs[k];
+        }
+        nz_dc = __shfl_sync(FULL, nz_dc, 0);
+        __syncwarp();
+        if (lane < 16) {
+            const int my_dc = s_dc[wid][bx + 4 * by];
+            if (cbp_luma) {
+                if (nz) {
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2) *(uint32_t *)&out->c.luma[lane * 16 + k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
+                }
+                out->c.nnz[lane] = (uint8_t)nz;
+                if (nz_dc) c[0] = my_dc;                                            // :261-263
+                int r[16];
+                inv4x4(c, r);                                                       // add16x16_idct, :267
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + r[k]);
+            } else if (nz_dc) {                                                     // add16x16_idct_dc, :269
+                const int v = s16((my_dc + 32) >> 6);
+#pragma unroll
+                for (int k = 0; k < 16; k++) p[k] = clip_u8(p[k] + v);
+            }
+            store4x4(dst, fr.stride, p);
+        }
+        if (lane == 0) out->c.nnz[24] = (uint8_t)nz_dc;
+        // ---- chroma: x264_mb_encode_8x8_chroma(h, 0, chroma_qp): CQM_4IC, no decimation (:275)
+        uint8_t *dstc = (ch ? fr.fd_v : fr.fd_u) + ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * fr.stride_c + job.mb_x * 8 + (bi & 1) * 4;
+        const int cbp_chroma = chroma_blocks(qt, 2, cqp, false, true, lane, f, p, dstc, fr.stride_c, &out->c);
+        if (lane == 0) { out->c.cbp_luma = (uint8_t)cbp_luma; out->c.cbp_chroma = (uint8_t)cbp_chroma; }
+        // ---- publish: every lane's pixel stores, then the state word
+        __syncwarp();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(state + job.mb_y * mb_width + job.mb_x, (epoch << 1) | 1);
+    }
+}
+
+} // namespace
+
+extern "C" int x264_cuda_residual_intra16_dev(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec, const void *d_jobs,
+                                              int n_jobs, void *d_coeffs)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    if (need_tables(ctx, false)) return -1;
+    if (!fenc->buf_chroma || !fdec->buf_chroma || fenc->g.stride != fdec->g.stride) {
+        snprintf(ctx->err, 256, "x264_cuda_residual_intra16: frames need X264_CUDA_FRAME_CHROMA and equal geometry");
+        return -1;
+    }
+    const int n_mb = fenc->g.mb_width * fenc->g.mb_height;
+    if (ctx->i16_state_n < n_mb + 1) { // state words of every macroblock + the ticket counter
+        cudaFree(ctx->d_i16_state); ctx->d_i16_state = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_i16_state, (size_t)(n_mb + 1) * sizeof(unsigned)));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_i16_state, 0, (size_t)(n_mb + 1) * sizeof(unsigned), ctx->stream));
+        ctx->i16_state_n = n_mb + 1; ctx->i16_epoch = 0;
+    }
+    const unsigned epoch = ++ctx->i16_epoch & 0x7fffffffu; // 31 bits: bit 0 of the word is the done flag
+    if (epoch == 0) { CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_i16_state, 0, (size_t)n_mb * sizeof(unsigned), ctx->stream)); return x264_cuda_residual_intra16_dev(ctx, fenc, fdec, d_jobs, n_jobs, d_coeffs); }
+    unsigned *state = (unsigned *)ctx->d_i16_state;
+    int *ticket = (int *)(state + ctx->i16_state_n - 1);
+    CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, sizeof(int), ctx->stream));
+    FrameRefs fr = { fenc->plane[0], fenc->chroma[0], fenc->chroma[1], fdec->plane[0], fdec->chroma[0], fdec->chroma[1], fenc->g.stride,
+                     fenc->stride_c };
+    intra16_mark_kernel<<<(n_jobs + 255) / 256, 256, 0, ctx->stream>>>((const x264_cuda_intra16_job_t *)d_jobs, n_jobs, fenc->g.mb_width, state, epoch);
+    ctx->launches++;
+    // a wavefront of a W x H frame holds at most ~min(W, H) macroblocks: a few warps per SM are plenty
+    const int blocks = min((n_jobs + 3) / 4, ctx->sm_count * 2);
+    residual_intra16_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_qt, fr, fenc->g.mb_width, (const x264_cuda_intra16_job_t *)d_jobs, n_jobs,
+                                                             (x264_cuda_mb_coeffs_i16_t *)d_coeffs, state, epoch, ticket);
+    LAUNCH_CHECK(ctx, "residual_intra16_kernel");
+    return 0;
+}
+
+extern "C" int x264_cuda_residual_intra16(x264_cuda_t *ctx, const x264_cuda_frame_t *fenc, x264_cuda_frame_t *fdec,
+                                          const x264_cuda_intra16_job_t *jobs, int n_jobs, x264_cuda_mb_coeffs_i16_t *coeffs)
+{
+    x264_cuda_enter(ctx);
+    if (n_jobs <= 0) return 0;
+    for (int i = 0; i < n_jobs; i++)
+        if (jobs[i].mb_x < 0 || jobs[i].mb_x >= fenc->g.mb_width || jobs[i].mb_y < 0 || jobs[i].mb_y >= fenc->g.mb_height || jobs[i].mode16 > 6 ||
+            jobs[i].mode_chroma > 6) {
+            snprintf(ctx->err, 256, "x264_cuda_residual_intra16: job %d: macroblock (%d,%d) / modes (%d,%d) out of range", i, jobs[i].mb_x, jobs[i].mb_y,
+                     jobs[i].mode16, jobs[i].mode_chroma);
+            return -1;
+        }
+    const size_t jb = (size_t)n_jobs * sizeof(x264_cuda_intra16_job_t), rb = (size_t)n_jobs * sizeof(x264_cuda_mb_coeffs_i16_t);
+    const size_t jb_al = (jb + 255) & ~(size_t)255;
+    if (x264_cuda_stage(ctx, jb_al + rb, jb_al + rb)) return -1;
+    uint8_t *hs = (uint8_t *)ctx->h_stage, *ds = (uint8_t *)ctx->d_stage;
+    if (x264_cuda_jobs_in(ctx, ds, jobs, hs, jb)) return -1;
+    if (x264_cuda_residual_intra16_dev(ctx, fenc, fdec, ds, n_jobs, ds + jb_al)) return -1;
     if (x264_cuda_results_out(ctx, coeffs, ds + jb_al, hs + jb_al, rb)) return -1;
     return 0;
 }

@@ -1,6 +1,7 @@
 /* x264_cuda_host.c — host-side C companions of the CUDA back-end: things the reference computes on the host
  * and hands to the device as data.  Compiled with the reference's own flags (-O4 -ffast-math). */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include "../../include/x264_cuda.h"
 
@@ -128,18 +129,19 @@ float x264_cuda_host_ssim_end(const int (*sums)[4], int w4, int h4)
  * functions and are rebuilt here rather than transcribed. */
 static float aq_log2[128];
 static uint8_t aq_exp2[64];
-static void aq_init(void)
+static pthread_once_t aq_once = PTHREAD_ONCE_INIT; /* several frame threads may arrive together */
+static void aq_build(void)
 {
-    if (aq_exp2[63]) return;
     for (int i = 0; i < 128; i++) aq_log2[i] = (float)(floor(log2(1.0 + i / 128.0) * 1e5 + 0.5) / 1e5);
     for (int i = 0; i < 64; i++) aq_exp2[i] = (uint8_t)floor((pow(2.0, (i + 0.5) / 64.0) - 1.0) * 256.0 + 0.5);
 }
+static void aq_init(void) { pthread_once(&aq_once, aq_build); }
 void x264_cuda_host_aq(const uint32_t *energy, int n_mb, float aq_strength, float *qp_offset, uint16_t *inv_qscale)
 {
     aq_init();
     const float strength = aq_strength * 1.0397;
     for (int k = 0; k < n_mb; k++) {
-        const uint32_t e = energy[k];
+        const uint32_t e = energy[k] ? energy[k] : 1; /* ac_energy_mb never returns 0 (ratecontrol.c:188: var clamped to >= 1); clz(0) is undefined */
         const int lz = __builtin_clz(e);
         const float adj = strength * (aq_log2[(e << lz >> 24) & 0x7f] - lz + 16.573f);
         qp_offset[k] = adj;
