@@ -10,7 +10,6 @@
 namespace {
 
 // ---- zig-zag (frame) orders as flat indices into the reference's transposed blocks (dct.c:488-560)
-__constant__ uint8_t c_zz4[16] = { 0, 4, 1, 2, 5, 8, 12, 9, 6, 3, 7, 10, 13, 14, 11, 15 };
 __constant__ uint8_t c_zz8[64] = { 0,  8,  1,  2,  9,  16, 24, 17, 10, 3,  4,  11, 18, 25, 32, 40, 33, 26, 19, 12, 5,  6,
                                    13, 20, 27, 34, 41, 48, 56, 49, 42, 35, 28, 21, 14, 7,  15, 22, 29, 36, 43, 50, 57, 58,
                                    51, 44, 37, 30, 23, 31, 38, 45, 52, 59, 60, 53, 46, 39, 47, 54, 61, 62, 55, 63 };
@@ -30,6 +29,71 @@ __device__ int decimate_score(const int16_t *lv, int first, int n)
         score += tab[run];
     }
     return score;
+}
+
+// zig-zag position k of a 4x4 block as a compile-time constant (the loops that use it are fully unrolled, so level k is a plain
+// register move instead of an indexed read of the coefficient array in local memory)
+__host__ __device__ constexpr int zz4(int k)
+{
+    return k == 0 ? 0 : k == 1 ? 4 : k == 2 ? 1 : k == 3 ? 2 : k == 4 ? 5 : k == 5 ? 8 : k == 6 ? 12 : k == 7 ? 9 : k == 8 ? 6 : k == 9 ? 3 : k == 10 ? 7 :
+           k == 11 ? 10 : k == 12 ? 13 : k == 13 ? 14 : k == 14 ? 11 : 15;
+}
+
+// x264_decimate_score15 / 16 (quant.c:219-252) from two bit masks over the zig-zag levels: nzm = level != 0, big = |level| > 1.
+// Walks the non-zero levels from the last one down; each scores by the run of zeros below it (down to `first`).
+__device__ __forceinline__ int decimate_score4(unsigned nzm, unsigned big, int first)
+{
+    if (first) { nzm &= ~1u; big &= ~1u; }
+    if (big) return 9;
+    int score = 0;
+    while (nzm) {
+        const int pos = 31 - __clz(nzm);
+        nzm ^= 1u << pos;
+        const int next = nzm ? 31 - __clz(nzm) : first - 1;
+        const int run = pos - next - 1;
+        score += run < 1 ? 3 : run < 3 ? 2 : run < 6 ? 1 : 0; // x264_decimate_table4
+    }
+    return score;
+}
+
+// quant_4x4 of the transposed coefficient block c[] (quant.c:33-58) with the list's tables fetched as four 16-byte loads, then — when
+// something survives — the zig-zag levels packed two per word (lvw), the decimation score (want_score; first = 1 for the AC-only
+// score15) and dequant_4x4 in place (quant.c:82-109).  lvw is all zero when nothing survives.  Returns nz (0/1).
+__device__ __forceinline__ int quant_block4(const QuantTables *__restrict__ qt, int list, int qp, int (&c)[16], bool want_score, int first,
+                                            uint32_t (&lvw)[8], int &score)
+{
+    const uint4 *mf4 = (const uint4 *)qt->q4mf[list][qp], *bs4 = (const uint4 *)qt->q4bias[list][qp];
+    const uint4 m0 = __ldg(mf4), m1 = __ldg(mf4 + 1), b0 = __ldg(bs4), b1 = __ldg(bs4 + 1);
+    const uint32_t mw[8] = { m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w }, bw[8] = { b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w };
+    int nz = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int sh = 16 * (k & 1);
+        c[k] = quant1(c[k], (int)((mw[k >> 1] >> sh) & 0xffff), (int)((bw[k >> 1] >> sh) & 0xffff));
+        nz |= c[k];
+    }
+    score = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) lvw[k] = 0;
+    if (!nz) return 0;
+    unsigned nzm = 0, big = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int v = c[zz4(k)];
+        lvw[k >> 1] |= (uint32_t)(uint16_t)v << (16 * (k & 1));
+        nzm |= (unsigned)(v != 0) << k;
+        big |= (unsigned)((unsigned)(v + 1) > 2u) << k;
+    }
+    if (want_score) score = decimate_score4(nzm, big, first);
+    const int4 *dq = (const int4 *)qt->dq4[list][qp % 6];
+    const int qbits = qp / 6 - 4;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const int4 d = __ldg(dq + g);
+        c[4 * g] = dequant1(c[4 * g], d.x, qbits); c[4 * g + 1] = dequant1(c[4 * g + 1], d.y, qbits);
+        c[4 * g + 2] = dequant1(c[4 * g + 2], d.z, qbits); c[4 * g + 3] = dequant1(c[4 * g + 3], d.w, qbits);
+    }
+    return 1;
 }
 
 // =========================================================================================================
@@ -177,26 +241,14 @@ __device__ __forceinline__ int chroma_blocks(const QuantTables *__restrict__ qt,
     const bool mine = lane >= 16 && lane < 24;
     const int ch = (cl >> 2) & 1, bi = cl & 3;
     int c[16], nz = 0, score = 0, dc0 = 0;
-    int16_t lv[16];
+    uint32_t lvw[8];
     if (mine) {
         int d[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
         fwd4x4(d, c);
         dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
-        const uint16_t *mf = qt->q4mf[list][cqp], *bias = qt->q4bias[list][cqp];
-#pragma unroll
-        for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
-        nz = nz != 0;
-        if (nz) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
-            if (decim) score = decimate_score(lv, 1, 16);
-            const int *dmf = qt->dq4[list][cqp % 6];
-            const int qbits = cqp / 6 - 4;
-#pragma unroll
-            for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
-        }
+        nz = quant_block4(qt, list, cqp, c, decim, 1, lvw, score);
     }
     // gather the four DCs / scores / nz of this lane's channel
     const int cb = 16 + ch * 4;
@@ -221,10 +273,11 @@ __device__ __forceinline__ int chroma_blocks(const QuantTables *__restrict__ qt,
                         s16((g2 - g3) * dmf >> -qbits) };
     const bool dc_only = (decim && tot < 7) || !nz_ac;
     if (mine) {
-        if (nz && !(intra && dc_only)) {
-#pragma unroll
-            for (int k = 0; k < 16; k += 2)
-                *(uint32_t *)&out->chroma_ac[cl][k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
+        {   // every chroma block's 32 bytes are written exactly once: the levels, or zeros (nothing survived / intra plane that stays DC-only)
+            const bool keep = nz && !(intra && dc_only);
+            uint4 *o4 = (uint4 *)&out->chroma_ac[cl][0];
+            o4[0] = keep ? make_uint4(lvw[0], lvw[1], lvw[2], lvw[3]) : make_uint4(0, 0, 0, 0);
+            o4[1] = keep ? make_uint4(lvw[4], lvw[5], lvw[6], lvw[7]) : make_uint4(0, 0, 0, 0);
         }
         out->nnz[16 + cl] = (uint8_t)(dc_only ? 0 : nz);
         if (bi == 0) {
@@ -272,8 +325,13 @@ __global__ void __launch_bounds__(128) residual_inter_kernel(const QuantTables *
     const bool dct8 = ALLOW8 && (job.flags & X264_CUDA_RESID_8x8DCT), decim = job.flags & X264_CUDA_RESID_DECIMATE;
     const unsigned FULL = 0xffffffffu;
 
-    // zero the coefficient record first (uncoded blocks read as zero, like a cleared h->dct)
-    for (int i = lane; i < (int)(sizeof(x264_cuda_mb_coeffs_t) / 4); i += 32) ((uint32_t *)out)[i] = 0;
+    // Uncoded blocks read as zero, like a cleared h->dct.  The 4x4 paths write every block's 32 bytes exactly once (levels or zeros), so only
+    // the tail of the record (chroma_dc, nnz, cbp: 48 bytes of scattered byte stores) is cleared up front; the 8x8 path clears the luma too.
+    {
+        constexpr int tail0 = offsetof(x264_cuda_mb_coeffs_t, chroma_dc) / 4, words = sizeof(x264_cuda_mb_coeffs_t) / 4;
+        for (int i = (dct8 ? 0 : tail0) + lane; i < words; i += 32)
+            if (i < (int)(offsetof(x264_cuda_mb_coeffs_t, chroma_ac) / 4) || i >= tail0) ((uint32_t *)out)[i] = 0;
+    }
     __syncwarp();
 
     int cbp_luma = 0;
@@ -290,22 +348,10 @@ __global__ void __launch_bounds__(128) residual_inter_kernel(const QuantTables *
 #pragma unroll
             for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
             fwd4x4(d, c);
-            const uint16_t *mf = qt->q4mf[1][qp], *bias = qt->q4bias[1][qp]; // CQM_4PY
-#pragma unroll
-            for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
-            nz = nz != 0;
-            if (nz) {
-                int16_t lv[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) *(uint32_t *)&out->luma[lane * 16 + k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
-                if (decim) score = decimate_score(lv, 0, 16);
-                const int *dmf = qt->dq4[1][qp % 6];
-                const int qbits = qp / 6 - 4;
-#pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
-            }
+            uint32_t lvw[8];
+            nz = quant_block4(qt, 1 /* CQM_4PY */, qp, c, decim, 0, lvw, score);
+            uint4 *o4 = (uint4 *)&out->luma[lane * 16]; // all zero when nothing survived
+            o4[0] = make_uint4(lvw[0], lvw[1], lvw[2], lvw[3]); o4[1] = make_uint4(lvw[4], lvw[5], lvw[6], lvw[7]);
         }
         // per 8x8: i_decimate_8x8 accumulates the scores of its blocks in order while it is still < 6 (macroblock.c:704-705)
         const int base = lane & ~3;
@@ -595,7 +641,8 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
         const int qp = min((int)job.qp, 51), cqp = min((int)job.chroma_qp, 51);
         const bool decim = job.flags & X264_CUDA_RESID_DECIMATE;
         const int kind_y = pred_kind(job.mode16, false), kind_c = pred_kind(job.mode_chroma, true);
-        for (int i = lane; i < (int)(sizeof(x264_cuda_mb_coeffs_i16_t) / 4); i += 32) ((uint32_t *)out)[i] = 0;
+        // every 4x4 block's levels are written exactly once below (levels or zeros); the tail (chroma_dc, nnz, cbp, luma_dc) is cleared here
+        for (int i = (int)(offsetof(x264_cuda_mb_coeffs_t, chroma_dc) / 4) + lane; i < (int)(sizeof(x264_cuda_mb_coeffs_i16_t) / 4); i += 32) ((uint32_t *)out)[i] = 0;
         // source blocks first: they do not depend on anybody
         const int bx = (lane & 1) + ((lane >> 2) & 1) * 2, by = ((lane >> 1) & 1) + ((lane >> 3) & 1) * 2; // block_idx_x/y
         const int cl = lane - 16, ch = (cl >> 2) & 1, bi = cl & 3;
@@ -692,7 +739,7 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
         }
         // ---- luma: x264_mb_encode_i16x16
         int c[16], nz = 0, score = 0, dc0 = 0;
-        int16_t lv[16];
+        uint32_t lvw[8];
         uint8_t *dst = fr.fd_y + ((size_t)job.mb_y * 16 + by * 4) * fr.stride + job.mb_x * 16 + bx * 4;
         if (lane < 16) {
             int d[16];
@@ -700,19 +747,7 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
             for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
             fwd4x4(d, c);
             dc0 = c[0]; c[0] = 0;                                                   // :218-220
-            const uint16_t *mf = qt->q4mf[0][qp], *bias = qt->q4bias[0][qp];        // CQM_4IY
-#pragma unroll
-            for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
-            nz = nz != 0;
-            if (nz) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
-                if (decim) score = decimate_score(lv, 1, 16);                       // decimate_score15, :230
-                const int *dmf = qt->dq4[0][qp % 6];
-                const int qbits = qp / 6 - 4;
-#pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = dequant1(c[k], dmf[k], qbits);
-            }
+            nz = quant_block4(qt, 0 /* CQM_4IY */, qp, c, decim, 1, lvw, score);       // quant, zigzag, decimate_score15 (:230), dequant
         }
         // the running "if (decimate_score < 6) decimate_score += ..." of :230 ends below 6 exactly when the total does (scores are >= 0)
         int tot = lane < 16 ? score : 0, any = lane < 16 ? nz : 0;
@@ -736,7 +771,7 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
             nz_dc = nz_dc != 0;
             if (nz_dc) {
 #pragma unroll
-                for (int k = 0; k < 16; k++) out->luma_dc[k] = (int16_t)dcs[c_zz4[k]]; // zigzag scan_4x4, :256
+                for (int k = 0; k < 16; k++) out->luma_dc[k] = (int16_t)dcs[zz4(k)]; // zigzag scan_4x4, :256
                 hadamard_dc(dcs, false);                                            // idct4x4dc, :259
                 const int qbits = qp / 6 - 6, dmf0 = qt->dq4[0][qp % 6][0];         // dequant_4x4_dc, quant.c:148-178
 #pragma unroll
@@ -750,11 +785,13 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
         __syncwarp();
         if (lane < 16) {
             const int my_dc = s_dc[wid][bx + 4 * by];
+            {
+                const bool keep = cbp_luma && nz;
+                uint4 *o4 = (uint4 *)&out->c.luma[lane * 16];
+                o4[0] = keep ? make_uint4(lvw[0], lvw[1], lvw[2], lvw[3]) : make_uint4(0, 0, 0, 0);
+                o4[1] = keep ? make_uint4(lvw[4], lvw[5], lvw[6], lvw[7]) : make_uint4(0, 0, 0, 0);
+            }
             if (cbp_luma) {
-                if (nz) {
-#pragma unroll
-                    for (int k = 0; k < 16; k += 2) *(uint32_t *)&out->c.luma[lane * 16 + k] = (uint16_t)lv[k] | ((uint32_t)(uint16_t)lv[k + 1] << 16);
-                }
                 out->c.nnz[lane] = (uint8_t)nz;
                 if (nz_dc) c[0] = my_dc;                                            // :261-263
                 int r[16];
@@ -889,16 +926,8 @@ __global__ void __launch_bounds__(128) probe_skip_kernel(const QuantTables *__re
 #pragma unroll
         for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
         fwd4x4(d, c);
-        const uint16_t *mf = qt->q4mf[1][qp], *bias = qt->q4bias[1][qp]; // CQM_4PY
-        int nz = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
-        if (nz) {
-            int16_t lv[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
-            score = decimate_score(lv, 0, 16);
-        }
+        uint32_t lvw[8];
+        quant_block4(qt, 1 /* CQM_4PY */, qp, c, true, 0, lvw, score);
     } else if (lane < 24) { // chroma, macroblock.c:845-879
         const int cl = lane - 16, ch = cl >> 2, bi = cl & 3;
         const size_t off = ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * pl.stride_c + job.mb_x * 8 + (bi & 1) * 4;
@@ -930,16 +959,8 @@ __global__ void __launch_bounds__(128) probe_skip_kernel(const QuantTables *__re
         for (int k = 0; k < 16; k++) { d[k] = f[k] - p[k]; ssd += d[k] * d[k]; }
         fwd4x4(d, c);
         dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
-        const uint16_t *mf = qt->q4mf[3][cqp], *bias = qt->q4bias[3][cqp]; // CQM_4PC
-        int nz = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) { c[k] = quant1(c[k], mf[k], bias[k]); nz |= c[k]; }
-        if (nz) {
-            int16_t lv[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) lv[k] = (int16_t)c[c_zz4[k]];
-            score = decimate_score(lv, 1, 16);
-        }
+        uint32_t lvw[8];
+        quant_block4(qt, 3 /* CQM_4PC */, cqp, c, true, 1, lvw, score);
     }
 
     // luma total over lanes 0..15, per-plane chroma totals over lanes 16..19 / 20..23
