@@ -819,7 +819,25 @@ def run_config(args):
     (frame_ms_max,), (cands_all,) = shard.reduce_job(dist if world > 1 else None, "cuda", [frame_ms], [cands])
     (me_ms_max,), _ = shard.reduce_job(dist if world > 1 else None, "cuda", [med[me_key]], [0])
     if rank == 0:
-        print(json.dumps({"metric": "%s ME Gcand/s" % args.config, "value": cands_all / (me_ms_max * 1e-3) / 1e9, "unit": "Gcand/s", "n_gpus": world,
+        # bytes that cross PCIe per frame: the picture, every stage's job list in, every stage's results out
+        h2d = int(y1.nbytes + u1.nbytes + v1.nbytes + rj.nbytes + (j16.nbytes if (cfg["me"] == "tesa" or cfg["subme"]) else 0)
+                  + (mbjobs.nbytes if cfg["me"] != "tesa" else 0) + (n_mb * pkg.MC_JOB.itemsize if "fin" in state else 0))
+        d2h = int(n_mb * pkg.MB_COEFFS.itemsize + (n_mb * pkg.ME_FINAL.itemsize if "fin" in state else 0)
+                  + (n_mb * pkg.ME_MB_RESULT.itemsize if cfg["me"] != "tesa" else 0))
+        extra = {"e2e": {"value": world * 1e3 / frame_ms_max, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "note": "the whole pipeline through the host-array C ABI: one step = one frame, its picture upload and every stage's job / result copies inside the timed stages"}}
+        if cfg["me"] != "tesa":
+            # the ME stage's kernel against the integer-pipe roofline, as in the headline line (the stage time includes its job / result copies)
+            c16, _ = count_cands(jobs[0::9], state["res"]["part"][:, 0], ME_RANGE)
+            int_peak = ctx.measure_int_pipe()
+            ach = 64.0 * c16 / (med[me_key] * 1e-3)
+            extra["roofline"] = {"bound": "int_pipe", "op": "VABSDIFF4.U8.ACC", "kernel": "me_search_mb3_kernel", "achieved": ach / 1e12, "peak": int_peak / 1e12,
+                                 "unit": "Tsad4/s", "frac": ach / int_peak, "traffic": None,
+                                 "note": "64 x positions of each macroblock's 16x16 window / the ME stage time (H2D of the job list and D2H of the results included)"}
+        else:
+            extra["roofline"] = {"bound": "latency", "note": "this configuration's frame time is the lookahead wavefront (x264_slicetype_frame_cost: W + 2H dependent 8x8-block "
+                                                             "searches) and the warp-per-search TESA kernel; neither has a bandwidth or issue-rate roofline worth quoting"}
+        print(json.dumps({"metric": "%s ME Gcand/s" % args.config, "value": cands_all / (me_ms_max * 1e-3) / 1e9, "unit": "Gcand/s", "n_gpus": world, **extra,
                           "steps": n_frames, "warmup": max(1, args.warmup), "ms_per_step": frame_ms_max, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": {"workload": cfg["what"], "width": w, "height": h, "macroblocks": n_mb, "me_range": ME_RANGE, "qp": QP,

@@ -454,7 +454,10 @@ X264_CUDA_API int x264_cuda_residual_inter_dev(x264_cuda_t *ctx, const x264_cuda
  * (luma + chroma).  Modes are the reference's enums: mode16 = enum intra16x16_pred_e (V H DC P DC_LEFT DC_TOP DC_128), mode_chroma =
  * enum intra_chroma_pred_e (DC H V P DC_LEFT DC_TOP DC_128) — e.g. what x264_cuda_intra_mb_costs picked.  flags: X264_CUDA_RESID_DECIMATE =
  * slice B || (b_dct_decimate && slice P) (:193).  Coefficient record: c.luma[16*i + 1..15] = AC levels of block i (slot 0 zero), luma_dc =
- * h->dct.luma16x16_dc, c.nnz[24] its flag; levels of blocks whose nnz is 0 read as zero. */
+ * h->dct.luma16x16_dc, c.nnz[24] its flag; levels of blocks whose nnz is 0 read as zero.
+ * The host-array entry takes the list in any dependency-respecting order and works through it by anti-diagonals (x + y ascending: a whole
+ * diagonal is independent), returning results in list order; the _dev entry takes its tickets in LIST order, so a device-resident list
+ * should itself be sorted by x + y — in raster order only a few macroblock rows are ever in flight. */
 typedef struct x264_cuda_intra16_job_t {
     int16_t mb_x, mb_y;
     uint8_t qp, chroma_qp;     /* h->mb.i_qp, h->mb.i_chroma_qp */

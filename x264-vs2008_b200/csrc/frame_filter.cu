@@ -99,12 +99,29 @@ __global__ void __launch_bounds__(128) hpel_kernel(const uint8_t *__restrict__ s
     };
 #pragma unroll
     for (int k = 0; k < 5; k++) load_unpack(U[k], y0 - 2 + k);
+    // The row loop has no early exit (rows past y_end are computed from clamped addresses and not stored) and the raw words of the
+    // rows two and three iterations ahead are already in flight: with a `break` per row the compiler cannot move a row's loads above
+    // the previous row's stores, and every row then pays a full memory round trip.
+    uint32_t raw[2][4];
+    auto fetch = [&](uint32_t (&w)[4], int y) {
+        const uint8_t *p = src + (ptrdiff_t)min(y, y_end + 2) * stride + x;
+        const uint2 m = __ldg((const uint2 *)p);
+        w[0] = __ldg((const uint32_t *)(p - 4)); w[1] = m.x; w[2] = m.y; w[3] = __ldg((const uint32_t *)(p + 8));
+    };
+    auto unpack = [&](uint32_t (&u)[7], const uint32_t (&w)[4]) {
+        u[0] = __byte_perm(w[0], 0, 0x4342);
+        u[1] = __byte_perm(w[1], 0, 0x4140); u[2] = __byte_perm(w[1], 0, 0x4342);
+        u[3] = __byte_perm(w[2], 0, 0x4140); u[4] = __byte_perm(w[2], 0, 0x4342);
+        u[5] = __byte_perm(w[3], 0, 0x4140); u[6] = __byte_perm(w[3], 0, 0x4342);
+    };
+    fetch(raw[0], y0 + 3); fetch(raw[1], y0 + 4);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int y = y0 + r;
-        if (y >= y_end) break;
-        load_unpack(U[(r + 5) % 6], y + 3);
-        const ptrdiff_t o = (ptrdiff_t)y * stride + x;
+        const bool live = y < y_end;
+        unpack(U[(r + 5) % 6], raw[r % 2]);
+        if (r + 2 < R) fetch(raw[r % 2], y + 5);
+        const ptrdiff_t o = (ptrdiff_t)min(y, y_end - 1) * stride + x;
         // ---- vertical 6-tap, two columns per register, biased by 2560
         uint32_t Vb[7];
 #pragma unroll
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(128) hpel_kernel(const uint8_t *__restrict__ s
                 const uint32_t s = ((Vb[k + 1] + 0x00100010u) >> 5) & 0x07ff07ffu;
                 m[k] = __viaddmin_s16x2_relu(s, 0xffb0ffb0u, 0x00ff00ffu); // max(min(s - 80, 255), 0) per lane
             }
-            *(uint2 *)(dv + o) = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
+            if (live) *(uint2 *)(dv + o) = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
         }
         {   // ---- centre plane: 6-tap over the vertical sums; S[k] = (Vb[k].hi, Vb[k+1].lo) serves the odd columns
             uint32_t S[6];
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(128) hpel_kernel(const uint8_t *__restrict__ s
                 c[2 * mm] = dp2a_lo_ss(Vb[mm + 2], 0x01fbu, dp2a_lo_ss(Vb[mm + 1], 0x1414u, dp2a_lo_ss(Vb[mm], 0xfb01u, K))) >> 10;
                 c[2 * mm + 1] = dp2a_lo_ss(S[mm + 2], 0x01fbu, dp2a_lo_ss(S[mm + 1], 0x1414u, dp2a_lo_ss(S[mm], 0xfb01u, K))) >> 10;
             }
-            *(uint2 *)(dc + o) = make_uint2(pack4_sat(c[0], c[1], c[2], c[3]), pack4_sat(c[4], c[5], c[6], c[7]));
+            if (live) *(uint2 *)(dc + o) = make_uint2(pack4_sat(c[0], c[1], c[2], c[3]), pack4_sat(c[4], c[5], c[6], c[7]));
         }
         {   // ---- H plane: 6-tap over the bytes of row y (re-read: an L1 hit, and cheaper than carrying the raw words through the ring)
             const uint8_t *p = src + o;
@@ -148,7 +165,7 @@ __global__ void __launch_bounds__(128) hpel_kernel(const uint8_t *__restrict__ s
             int h[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) h[i] = dp4a_us(A[i + 4], 0x000001fbu, dp4a_us(A[i], 0x1414fb01u, 16)) >> 5;
-            *(uint2 *)(dh + o) = make_uint2(pack4_sat(h[0], h[1], h[2], h[3]), pack4_sat(h[4], h[5], h[6], h[7]));
+            if (live) *(uint2 *)(dh + o) = make_uint2(pack4_sat(h[0], h[1], h[2], h[3]), pack4_sat(h[4], h[5], h[6], h[7]));
         }
     }
 }
@@ -166,14 +183,16 @@ __global__ void __launch_bounds__(128) integral_kernel(const uint8_t *__restrict
     if (qi >= n_quads) return;
     const int x = x_begin + qi * 4; // multiple of 4: the twelve bytes x .. x+11 a row contributes are three aligned words
     const int y0 = y_begin + blockIdx.y * R;
-    // horizontal sums of row y for columns x .. x+3, packed two columns per register: h8 = 8 pixels, h4 = 4 pixels
-    auto hsum = [&](int y, uint32_t (&h8)[2], uint32_t (&h4)[2]) {
-        const uint32_t *p = (const uint32_t *)(src + (ptrdiff_t)y * stride + x);
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    // horizontal sums of one row for columns x .. x+3 from its three words, packed two columns per register: h8 = 8 pixels, h4 = 4 pixels
+    auto fetch = [&](uint32_t (&w)[3], int y) {
+        const uint32_t *p = (const uint32_t *)(src + (ptrdiff_t)min(y, y_end + 7) * stride + x); // y_end + 7: the last row any stored sum needs
+        w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2);
+    };
+    auto hsum = [&](const uint32_t (&w)[3], uint32_t (&h8)[2], uint32_t (&h4)[2]) {
         uint32_t l[4], h[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint32_t lo = k ? __funnelshift_r(w0, w1, 8 * k) : w0, hi = k ? __funnelshift_r(w1, w2, 8 * k) : w1;
+            const uint32_t lo = k ? __funnelshift_r(w[0], w[1], 8 * k) : w[0], hi = k ? __funnelshift_r(w[1], w[2], 8 * k) : w[1];
             l[k] = sad4_acc(lo, 0, 0);
             h[k] = sad4_acc(hi, 0, l[k]);
         }
@@ -183,25 +202,34 @@ __global__ void __launch_bounds__(128) integral_kernel(const uint8_t *__restrict
     // running vertical sums, one register per column (the uint16 wrap of the reference is applied when storing)
     uint32_t s8[4] = { 0, 0, 0, 0 }, s4[4] = { 0, 0, 0, 0 };
     uint32_t ring8[8][2], ring4[8][2]; // horizontal sums of rows y..y+7 (slot (r+k)%8 <-> row y+k)
+    uint32_t pre[8][3], pf[4][3];      // the first eight rows and the next four are requested before anything is computed
+#pragma unroll
+    for (int k = 0; k < 8; k++) fetch(pre[k], y0 + k);
+#pragma unroll
+    for (int k = 0; k < 4; k++) fetch(pf[k], y0 + 8 + k);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        hsum(y0 + k, ring8[k], ring4[k]);
+        hsum(pre[k], ring8[k], ring4[k]);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             s8[c] += (ring8[k][c >> 1] >> (16 * (c & 1))) & 0xffff;
             if (SUB4 && k < 4) s4[c] += (ring4[k][c >> 1] >> (16 * (c & 1))) & 0xffff;
         }
     }
+    // No early exit in the row loop (rows past y_end are computed from clamped addresses and not stored) and a row's words are requested
+    // four iterations before they are summed: with a `break` per row every row paid a full memory round trip.
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int y = y0 + r;
-        if (y >= y_end) break;
-        const ptrdiff_t o = (ptrdiff_t)y * stride + x;
-        *(uint2 *)(sum8 + o) = make_uint2((s8[0] & 0xffff) | (s8[1] << 16), (s8[2] & 0xffff) | (s8[3] << 16));
-        if (SUB4) *(uint2 *)(sum4 + o) = make_uint2((s4[0] & 0xffff) | (s4[1] << 16), (s4[2] & 0xffff) | (s4[3] << 16));
+        if (y < y_end) {
+            const ptrdiff_t o = (ptrdiff_t)y * stride + x;
+            *(uint2 *)(sum8 + o) = make_uint2((s8[0] & 0xffff) | (s8[1] << 16), (s8[2] & 0xffff) | (s8[3] << 16));
+            if (SUB4) *(uint2 *)(sum4 + o) = make_uint2((s4[0] & 0xffff) | (s4[1] << 16), (s4[2] & 0xffff) | (s4[3] << 16));
+        }
         if (r + 1 < R) {
             uint32_t h8[2], h4[2];
-            hsum(y + 8, h8, h4);
+            hsum(pf[r % 4], h8, h4); // row y + 8
+            if (r + 5 < R) fetch(pf[r % 4], y + 12);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int sh = 16 * (c & 1);
