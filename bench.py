@@ -196,12 +196,16 @@ def _cpu_worker(args):
         outs = o.me_search_fpel_batch(g, pe, pr, integ, arr)
     dt = time.perf_counter() - t0
     res = np.zeros(len(jobs), pkg.ME_RESULT)
-    if use_ref:  # the harness hides the seed: recompute it with the port to count the search space
+    chained = True
+    if use_ref:  # the harness cannot see the reference's internal full-pel state: the port supplies it, chained to the reference through (mv, cost)
+        ref_final = np.array([(r.mv[0], r.mv[1], r.cost) for r in outs], np.int64)
         outs = X.port().me_search_fpel_batch(g, pe, pr, integ, arr)
+        chained = bool(np.array_equal(ref_final, np.array([(r.mv[0], r.mv[1], r.cost) for r in outs], np.int64)))
     for i, r in enumerate(outs):
         res[i]["seed_mx"], res[i]["seed_my"] = r.seed_mx, r.seed_my
     cands, _ = count_cands(jobs, res, ME_RANGE)
-    return cands * reps, dt
+    best = np.array([(r.bmx, r.bmy, r.bcost) for r in outs], np.int64) if chained else None
+    return cands * reps, dt, best
 
 
 def cpu_rate(n_procs, jobs_per_proc, reps, stride_start=0):
@@ -223,6 +227,7 @@ def cpu_rate(n_procs, jobs_per_proc, reps, stride_start=0):
     wall = max(o[1] for o in outs)
     kind = "reference" if use_ref else "port"
     sample = "%d jobs x %d passes per process (ESA merange 16, 1080p, same job list as the GPU arm)" % (jobs_per_proc, reps)
+    cpu_rate.last_best = [(sl[0], sl[1], o[2]) for sl, o in zip(slices, outs)]  # (first job, end, (bmx, bmy, bcost) of each) for the parity check
     return cands / wall, kind, n_procs, sample, wall
 
 
@@ -258,7 +263,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------- encode fps (BASELINE metric, 2nd half)
 ENC_OPTS = "--qp 26 --me esa --merange 16 --subme 2 --no-psnr --no-ssim"
 ENC_KEYINT = 24
-ENC_GOPS_PER_WORKER = 3  # closed GOPs per encoder thread: the front end's start-up (CUDA context, page-locking) is paid once per run
+ENC_GOPS_PER_WORKER = 4  # closed GOPs per encoder thread: the front end's start-up (CUDA context, page-locking) is paid once per run
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "x264")
 B200_CLI = os.path.join(ROOT, "integration", "_build", "x264_b200")
 B200_GOPS = os.path.join(ROOT, "integration", "_build", "x264_b200_gops")
@@ -670,6 +675,22 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             rate, kind, cores, sample, _ = cpu_rate(1, 9 * 120 * 32, 60)  # ~10 s of the reference's C on one core
             line["cpu_baseline"] = {"value": rate / 1e9, "unit": "Gcand/s", "cores": cores, "kind": kind, "sample": sample}
+            # the same jobs on the same frame pair (ring pair 0 = pictures 1 and 0 of the seeded clip) through the kernel the timed region ran:
+            # every (mv, cost) must equal what the reference's C returned
+            step_resident(0)
+            torch.cuda.synchronize()
+            got = d_res.cpu().numpy().view(pkg.ME_RESULT)
+            n_chk = 0
+            for lo, hi, best in cpu_rate.last_best:
+                if best is None:
+                    raise SystemExit("bench.py: the oracle port and the reference's C disagree on (mv, cost) of jobs %d..%d" % (lo, hi))
+                mine = np.stack([got["bmx"][lo:hi], got["bmy"][lo:hi], got["bcost"][lo:hi]], 1).astype(np.int64)
+                if not np.array_equal(mine, best):
+                    bad = int(np.nonzero((mine != best).any(1))[0][0])
+                    raise SystemExit("bench.py: job %d: device (%s) != %s C (%s)" % (lo + bad, mine[bad], kind, best[bad]))
+                n_chk += hi - lo
+            line["parity"] = {"checked_jobs": n_chk, "against": "oracle port's full-pel (mv, cost)" + (", itself equal to the reference's x264_me_search_ref in final (mv, cost) on the same jobs" if kind == "reference" else ""),
+                              "result": "bit-exact"}
         print(json.dumps(line))
     for f in frames:
         f.close()
