@@ -31,6 +31,7 @@
 void x264_b200_set_gop_seed(int idr_pic_id, int coded_frames); /* x264_b200_hooks.c: per-thread seeds of the next x264_encoder_open */
 void x264_b200_disable_for_this_thread(void);
 void x264_b200_report(void);
+void x264_b200_warm_device(void);
 
 typedef struct {
     int index, first_gop, first_frame, n_frames;
@@ -130,6 +131,8 @@ static void build_cost_tables(const x264_param_t *base)
     }
 }
 
+static void *warm_main(void *arg) { (void)arg; x264_b200_warm_device(); return NULL; }
+
 static int is_flag(const char *name)
 {
     static const char *flags[] = { "8x8dct", "weightb", "mixed-refs", "b-pyramid", "interlaced", "aud", "progress", "quiet", "verbose", "non-deterministic",
@@ -176,7 +179,11 @@ int main(int argc, char **argv)
     if (workers > n_gops) workers = n_gops;
     if (workers < 1) { fprintf(stderr, "x264_b200_gops: no frames\n"); return 2; }
 
+    /* the device's context comes up on a helper thread while this one builds the cost tables */
+    pthread_t warm;
+    const int warming = pthread_create(&warm, NULL, warm_main, NULL) == 0;
     build_cost_tables(&param);
+    if (warming) pthread_join(warm, NULL);
     worker_t *w = calloc(workers, sizeof(*w));
     const double t0 = now_s();
     for (int k = 0, gop = 0; k < workers; k++) { /* consecutive runs, sizes differing by at most one GOP */

@@ -162,6 +162,15 @@ static __thread int seed_set, seed_idr_pic_id, seed_coded_frames;
 void x264_b200_set_gop_seed(int idr_pic_id, int coded_frames) { seed_set = 1; seed_idr_pic_id = idr_pic_id; seed_coded_frames = coded_frames; }
 void x264_b200_disable_for_this_thread(void) { B.state = -1; }
 void x264_b200_report(void) { report(); }
+/* creates the process's CUDA context (1-3 s on a freshly started box) from a helper thread, so that a front end can overlap it with its own
+ * start-up work; the encoder threads' x264_cuda_open calls then find the context in place */
+void x264_b200_warm_device(void)
+{
+    const char *e = getenv("X264_B200");
+    if (e && !atoi(e)) return;
+    x264_cuda_t *c = NULL;
+    if (x264_cuda_open(&c, getenv("X264_B200_DEVICE") ? atoi(getenv("X264_B200_DEVICE")) : 0) == 0 && c) { x264_cuda_synchronize(c); x264_cuda_close(c); }
+}
 x264_t *x264_encoder_open_c(x264_param_t *param);
 x264_t *x264_encoder_open(x264_param_t *param)
 {

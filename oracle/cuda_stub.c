@@ -19,6 +19,7 @@ struct x264_cuda_frame_t {
 
 int x264_cuda_open(x264_cuda_t **ctx, int device) { (void)device; *ctx = calloc(1, sizeof(**ctx)); return 0; }
 void x264_cuda_close(x264_cuda_t *ctx) { free(ctx); }
+int x264_cuda_synchronize(x264_cuda_t *ctx) { (void)ctx; return 0; }
 const char *x264_cuda_error(const x264_cuda_t *ctx) { return ctx ? ctx->err : "stub"; }
 long long x264_cuda_launch_count(const x264_cuda_t *ctx) { return ctx->launches; }
 void *x264_cuda_host_alloc(size_t bytes) { return malloc(bytes); }
