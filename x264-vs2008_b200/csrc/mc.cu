@@ -12,6 +12,31 @@ struct McPlanes {
     int stride, stride_c;
 };
 
+// Four horizontally adjacent pixels of mc_chroma (mc.c:205-236) at once: s = top-left source byte of the first pixel (any alignment),
+// coef = cA | cB << 8 | cC << 16 | cD << 24 (each <= 64).  Every output pixel is ONE dp4a over (s[x], s[x+1], t[x], t[x+1]) — the same sum
+// of four products, + 32, >> 6 as the reference's expression.
+__device__ __forceinline__ uint32_t chroma4(const uint8_t *s, int stride, uint32_t coef)
+{
+    uint32_t lo[2], hi[2]; // per source row: bytes 0..3 and bytes 1..4
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uintptr_t a = (uintptr_t)(s + (ptrdiff_t)r * stride);
+        const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+        lo[r] = __funnelshift_r(w0, w1, sh);
+        hi[r] = sh == 24 ? w1 : __funnelshift_r(w0, w1, sh + 8);
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t sel = (uint32_t)j | (uint32_t)(4 + j) << 4;
+        const uint32_t quad = __byte_perm(__byte_perm(lo[0], hi[0], sel), __byte_perm(lo[1], hi[1], sel), 0x5410);
+        out |= (__dp4a(quad, coef, 32u) >> 6) << (8 * j);
+    }
+    return out;
+}
+
 __global__ void __launch_bounds__(128) mc_blocks_kernel(McPlanes pl, const x264_cuda_mc_job_t *__restrict__ jobs, int n_jobs, int do_chroma)
 {
     const int lane = threadIdx.x & 31;
@@ -35,6 +60,15 @@ __global__ void __launch_bounds__(128) mc_blocks_kernel(McPlanes pl, const x264_
         const int cw = w >> 1, ch = h >> 1;
         const size_t off = (size_t)(job.by >> 1) * pl.stride_c + (job.bx >> 1);
         const ptrdiff_t so = (ptrdiff_t)(job.mvy >> 3) * pl.stride_c + (job.mvx >> 3);
+        if (cw >= 4 && !((job.bx >> 1) & 3)) { // word-aligned destination rows: four pixels per lane and step (chroma4), 32-bit stores
+            const uint32_t coef = (uint32_t)cA | (uint32_t)cB << 8 | (uint32_t)cC << 16 | (uint32_t)cD << 24;
+            const int two = cw >> 3, per = (cw >> 2) * ch; // 4-pixel units per row - 1 (cw is 4 or 8), units per plane
+            for (int i = lane; i < 2 * per; i += 32) {
+                const int p = i >= per, k = i - p * per, y = k >> two, x = (k & two) * 4;
+                const ptrdiff_t o = (ptrdiff_t)y * pl.stride_c + x;
+                *(uint32_t *)((p ? pl.dst_cr : pl.dst_cb) + off + o) = chroma4((p ? pl.ref_cr : pl.ref_cb) + off + so + o, pl.stride_c, coef);
+            }
+        } else
         for (int i = lane; i < 2 * cw * ch; i += 32) {
             const int p = i / (cw * ch), k = i - p * cw * ch, y = k / cw, x = k - y * cw;
             const uint8_t *s = (p ? pl.ref_cr : pl.ref_cb) + off + so + (ptrdiff_t)y * pl.stride_c + x;
@@ -95,6 +129,19 @@ __global__ void __launch_bounds__(128) mc_blocks_bi_kernel(McBiPlanes pl, const 
             cA[l] = (8 - d8x) * (8 - d8y); cB[l] = d8x * (8 - d8y); cC[l] = (8 - d8x) * d8y; cD[l] = d8x * d8y;
             so[l] = (ptrdiff_t)(mvy >> 3) * pl.stride_c + (mvx >> 3);
         }
+        if (cw >= 4 && !((job.bx >> 1) & 3)) { // four pixels per lane and step: both lists' chroma4, blended per byte like the luma words
+            uint32_t coef[2];
+#pragma unroll
+            for (int l = 0; l < 2; l++) coef[l] = (uint32_t)cA[l] | (uint32_t)cB[l] << 8 | (uint32_t)cC[l] << 16 | (uint32_t)cD[l] << 24;
+            const int two = cw >> 3, per = (cw >> 2) * ch;
+            for (int i = lane; i < 2 * per; i += 32) {
+                const int p = i >= per, k = i - p * per, y = k >> two, x = (k & two) * 4;
+                const ptrdiff_t o = (ptrdiff_t)y * pl.stride_c + x;
+                const uint32_t a = chroma4((p ? pl.ref_cr[0] : pl.ref_cb[0]) + off + so[0] + o, pl.stride_c, coef[0]);
+                const uint32_t b = chroma4((p ? pl.ref_cr[1] : pl.ref_cb[1]) + off + so[1] + o, pl.stride_c, coef[1]);
+                *(uint32_t *)((p ? pl.dst_cr : pl.dst_cb) + off + o) = blend4(a, b, weight);
+            }
+        } else
         for (int i = lane; i < 2 * cw * ch; i += 32) {
             const int p = i / (cw * ch), k = i - p * cw * ch, y = k / cw, x = k - y * cw;
             int v[2];

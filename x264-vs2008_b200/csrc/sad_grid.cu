@@ -28,7 +28,7 @@ __device__ __forceinline__ void grid_load_row16(uint32_t (&dst)[4], const uint8_
 //               sum of these (PIXEL_SAD_C is a plain sum, S/common/pixel.c:40-56), 8 B instead of 18 B per position and one 8-byte
 //               store per lane (a warp row = 256 contiguous bytes).
 template <bool QUAD>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, QUAD ? 3 : 2) // the nine-plane form keeps nine running sums per position: two CTAs per SM, no spills
 sad_grid_kernel(GridGeo geo, const x264_cuda_grid_job_t *__restrict__ jobs, int n_jobs, int radius, uint16_t *__restrict__ grid)
 {
     __shared__ __align__(16) uint32_t s_F[4][16][4];
