@@ -661,10 +661,12 @@ extern "C" int x264_cuda_residual_inter(x264_cuda_t *ctx, const x264_cuda_frame_
 // DC transform (dct4x4dc / quant_4x4_dc / idct4x4dc / dequant_4x4_dc) runs on lane 0 over values gathered by shuffles.
 namespace {
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+// polling load: relaxed (an acquire load invalidates the SM's whole L1 on every poll — CCTL.IVALL — and the warps that are working on the
+// same SM then miss on every quantiser-table read: measured 12.5 us per wavefront step).  The acquire is ONE fence after the flag is seen.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
 {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -687,7 +689,8 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
                                                                int *ticket, const int *__restrict__ order)
 {
     __shared__ __align__(4) Intra16Edges s_edges[4];
-    __shared__ int s_dc[4][16];
+    __shared__ __align__(16) int s_dc[4][20];   // dequantised luma DCs + [16] the DC block's nz flag
+    __shared__ __align__(16) int s_dcin[4][32]; // every block's DC coefficient, by lane
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     Intra16Edges &E = s_edges[wid];
@@ -715,9 +718,10 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
             const int nx = job.mb_x - (lane != 1), ny = job.mb_y - (lane != 0);
             if (nx >= 0 && ny >= 0) {
                 const unsigned *w = state + ny * mb_width + nx;
-                unsigned v = ld_acquire_u32(w);
-                while ((v >> 1) == epoch && !(v & 1)) v = ld_acquire_u32(w);
+                unsigned v = ld_relaxed_u32(w);
+                while ((v >> 1) == epoch && !(v & 1)) { __nanosleep(64); v = ld_relaxed_u32(w); }
             }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory"); // acquire side of the neighbours' release stores (not __threadfence(): that is fence.sc)
         }
         __syncwarp();
         // ---- neighbour pixels straight from L2 (another SM wrote them a moment ago)
@@ -812,29 +816,30 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
             dc0 = c[0]; c[0] = 0;                                                   // :218-220 / dct2x2dc :72-85
             nz = quant_block4(qt, isl ? 0 /* CQM_4IY */ : 2 /* CQM_4IC */, isl ? qp : cqp, c, isl && decim, 1, lvw, score); // decimate_score15, :230
         }
+        // Cross-lane traffic goes through one vote, one REDUX and shared memory: inside this persistent loop every __shfl_sync compiles to a
+        // convergence call + SHFL, and the ~40 of them were half of a step's working time in the ncu source view.
+        const unsigned nzb = __ballot_sync(FULL, act && nz);                        // bit l: lane l's block kept coefficients
+        if (act) s_dcin[wid][lane] = dc0;
         // luma: the running "if (decimate_score < 6) decimate_score += ..." of :230 ends below 6 exactly when the total does (scores are >= 0)
-        int tot = isl ? score : 0, any = isl ? nz : 0;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) { tot += __shfl_xor_sync(FULL, tot, o); any |= __shfl_xor_sync(FULL, any, o); }
-        tot = __shfl_sync(FULL, tot, 0); any = __shfl_sync(FULL, any, 0);
-        const int cbp_luma = (any && !(decim && tot < 6)) ? 0xf : 0;                 // :232, :238-245
+        const int tot = __reduce_add_sync(FULL, isl ? score : 0);
+        const int cbp_luma = ((nzb & 0xffffu) && !(decim && tot < 6)) ? 0xf : 0;     // :232, :238-245
+        __syncwarp();
         // luma 4x4 DC block on lane 0: dct_dc4x4[0][block_idx_xy_1d[i]] = dct4x4[i][0][0]
-        int dcs[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int v = __shfl_sync(FULL, dc0, i);
-            dcs[((i & 1) + ((i >> 2) & 1) * 2) + 4 * (((i >> 1) & 1) + ((i >> 3) & 1) * 2)] = v;
-        }
-        int nz_dc = 0;
         if (lane == 0) {
+            int dcs[16], nzd = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) dcs[((i & 1) + ((i >> 2) & 1) * 2) + 4 * (((i >> 1) & 1) + ((i >> 3) & 1) * 2)] = s_dcin[wid][i];
             hadamard_dc(dcs, true);                                                 // dct4x4dc, :247
             const int mf0 = qt->q4mf[0][qp][0] >> 1, bias0 = qt->q4bias[0][qp][0] << 1; // :251
 #pragma unroll
-            for (int k = 0; k < 16; k++) { dcs[k] = quant1(dcs[k], mf0, bias0); nz_dc |= dcs[k]; }
-            nz_dc = nz_dc != 0;
-            if (nz_dc) {
+            for (int k = 0; k < 16; k++) { dcs[k] = quant1(dcs[k], mf0, bias0); nzd |= dcs[k]; }
+            nzd = nzd != 0;
+            if (nzd) {
+                uint32_t w[8];
 #pragma unroll
-                for (int k = 0; k < 16; k++) out->luma_dc[k] = (int16_t)dcs[zz4(k)]; // zigzag scan_4x4, :256
+                for (int k = 0; k < 8; k++) w[k] = (uint32_t)(uint16_t)dcs[zz4(2 * k)] | (uint32_t)(uint16_t)dcs[zz4(2 * k + 1)] << 16; // zigzag scan_4x4, :256
+                uint4 *o4 = (uint4 *)out->luma_dc;
+                o4[0] = make_uint4(w[0], w[1], w[2], w[3]); o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 hadamard_dc(dcs, false);                                            // idct4x4dc, :259
                 const int qbits = qp / 6 - 6, dmf0 = qt->dq4[0][qp % 6][0];         // dequant_4x4_dc, quant.c:148-178
 #pragma unroll
@@ -843,14 +848,13 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
             }
 #pragma unroll
             for (int k = 0; k < 16; k++) s_dc[wid][k] = dcs[k];
+            s_dc[wid][16] = nzd;
         }
-        nz_dc = __shfl_sync(FULL, nz_dc, 0);
         // chroma 2x2 DC of this lane's plane (every lane computes it; only lanes 16..23 use it): dct2x2dc, quant_2x2_dc, IDCT_DEQUANT_START
         const int cb = 16 + ch * 4;
-        const int b0 = __shfl_sync(FULL, dc0, cb), b1 = __shfl_sync(FULL, dc0, cb + 1), b2 = __shfl_sync(FULL, dc0, cb + 2), b3 = __shfl_sync(FULL, dc0, cb + 3);
-        int nz_ac = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) nz_ac |= __shfl_sync(FULL, nz, cb + k);
+        const int4 bq = *(const int4 *)&s_dcin[wid][cb];
+        const int b0 = bq.x, b1 = bq.y, b2 = bq.z, b3 = bq.w;
+        const int nz_ac = (nzb >> cb) & 0xf;
         const int e0 = b0 + b1, e1 = b2 + b3, e2 = b0 - b1, e3 = b2 - b3;
         int cdc[4] = { s16(e0 + e1), s16(e0 - e1), s16(e2 + e3), s16(e2 - e3) };
         const int cmf0 = qt->q4mf[2][cqp][0] >> 1, cbias0 = qt->q4bias[2][cqp][0] << 1;
@@ -864,6 +868,7 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
         const int o4v[4] = { s16((g0 + g1) * cdmf >> -cqbits), s16((g0 - g1) * cdmf >> -cqbits), s16((g2 + g3) * cdmf >> -cqbits), s16((g2 - g3) * cdmf >> -cqbits) };
         const bool dc_only = !nz_ac;                                                // :334 with b_decimate = 0
         __syncwarp();
+        const int nz_dc = s_dc[wid][16];
         // ---- levels (each block's 32 bytes once: lanes 16..23 land in chroma_ac), bookkeeping bytes, reconstruction — one stream again
         bool inv = false;
         int dcv = 0;
@@ -903,17 +908,16 @@ __global__ void __launch_bounds__(128) residual_intra16_kernel(const QuantTables
             store4x4(dst, isl ? fr.stride : fr.stride_c, p);
         }
         {
-            const int ac_u = __shfl_sync(FULL, (int)!dc_only, 16), ac_v = __shfl_sync(FULL, (int)!dc_only, 20);
-            const int dcn_u = __shfl_sync(FULL, nz_cdc, 16), dcn_v = __shfl_sync(FULL, nz_cdc, 20);
+            const unsigned ac = __ballot_sync(FULL, act && !isl && !dc_only), dcn = __ballot_sync(FULL, act && !isl && nz_cdc);
             if (lane == 0) {
                 out->c.nnz[24] = (uint8_t)nz_dc;
                 out->c.cbp_luma = (uint8_t)cbp_luma;
-                out->c.cbp_chroma = (uint8_t)((ac_u | ac_v) ? 2 : (dcn_u | dcn_v) ? 1 : 0);
+                out->c.cbp_chroma = (uint8_t)(ac ? 2 : dcn ? 1 : 0);
             }
         }
-        // ---- publish: every lane's pixel stores, then the state word
-        __syncwarp();
-        __threadfence();
+        // ---- publish: every lane's pixel stores happen before lane 0's release store through the warp barrier (causality order is cumulative
+        // across bar.warp.sync), so ONE st.release.gpu publishes the macroblock.  A __threadfence() on all lanes here (fence.sc.gpu) was two
+        // thirds of the working time of a step in the ncu source view.
         __syncwarp();
         if (lane == 0) st_release_u32(state + job.mb_y * mb_width + job.mb_x, (epoch << 1) | 1);
     }
