@@ -968,6 +968,15 @@ def run_rows(args):
     p_ij, p_ires = pinned(ij), pinned_out(n_mb * pkg.INTRA_RESULT.itemsize)
     key_i = "f4 Intra16x16 + chroma 8x8 candidate costs (predict + SATD, up to 4 + 4 modes), 8160 MB"
     timed(key_i, lambda: ctx.check(L.x264_cuda_intra_mb_costs(ctx.h, fenc.h, fdec.h, p_ij.data_ptr(), n_mb, p_ires.data_ptr())))
+    # every macroblock as I_16x16 (one wavefront launch; the host entry deals the raster list by anti-diagonals)
+    i16 = np.zeros(n_mb, pkg.INTRA16_JOB)
+    i16["mb_x"], i16["mb_y"], i16["qp"], i16["chroma_qp"] = rj["mb_x"], rj["mb_y"], 26, 26
+    inner = (i16["mb_x"] > 0) & (i16["mb_y"] > 0)
+    i16["mode16"] = np.where(inner, (i16["mb_x"] + i16["mb_y"]) % 4, np.where(i16["mb_x"] > 0, 4, np.where(i16["mb_y"] > 0, 5, 6)))
+    i16["mode_chroma"] = np.where(inner, (i16["mb_x"] + 2 * i16["mb_y"]) % 4, np.where(i16["mb_x"] > 0, 4, np.where(i16["mb_y"] > 0, 5, 6)))
+    p_i16, p_i16res = pinned(i16), pinned_out(n_mb * pkg.MB_COEFFS_I16.itemsize)
+    key_i16 = "a14 I_16x16 macroblock encode (predict, dct, DC transform, quant, dequant, idct; luma + chroma), 8160 MB, one wavefront"
+    timed(key_i16, lambda: ctx.check(L.x264_cuda_residual_intra16(ctx.h, fenc.h, fdec.h, p_i16.data_ptr(), n_mb, p_i16res.data_ptr())), reps=3)
     timed("f1 deblocking", lambda: ctx.frame_deblock(fdec, dinfo), reps=3)
     timed("a11 lowres P frame cost (intra + HEX/subme 4 search)", lambda: ctx.lowres_frame_cost(fenc, fref, fenc, 0, 1, 1, do_search=(1, 0)), reps=3)
     # candidate grids for the sequential-predictor use (host replay): all 9 partitions x 33 x 36 vectors per macroblock
@@ -1093,6 +1102,13 @@ def run_rows(args):
     for (fy, fu, fv, _, _, _), (ny, nu, nv) in zip(blk, nbs):
         o.lib.xo_intra_mb_costs(C.byref(iin), X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(ny), X._ptr(nu), X._ptr(nv), C.byref(iout))
     cpu[key_i] = (time.perf_counter() - t0) / n_s * n_mb * 1e3
+    if hasattr(o.lib, "xo_residual_intra16_mb"):
+        ry, ru, rv, dcv = np.zeros(256, np.uint8), np.zeros(64, np.uint8), np.zeros(64, np.uint8), np.zeros(16, np.int16)
+        t0 = time.perf_counter()
+        for i, ((fy, fu, fv, _, _, _), (ny, nu, nv)) in enumerate(zip(blk, nbs)):
+            o.lib.xo_residual_intra16_mb(C.byref(rin), i % 4, (i // 4) % 4, X._ptr(fy), X._ptr(fu), X._ptr(fv), X._ptr(ny), X._ptr(nu), X._ptr(nv),
+                                         X._ptr(ry), X._ptr(ru), X._ptr(rv), C.byref(rout), X._ptr(dcv, X.i16p))
+        cpu[key_i16] = max((time.perf_counter() - t0) / n_s * n_mb * 1e3 - 0.0, 0.0)
     planes4 = (X.u8p * 4)(*[X._ptr(p_, X.u8p, og.origin + 64 * og.stride + 64) for p_ in (pr, fh, fv, fc)])
     dst, dstc = np.zeros((16, 16), np.uint8), np.zeros((8, 8), np.uint8)
     cup = np.ascontiguousarray(np.pad(u0, 16, mode="edge"))
