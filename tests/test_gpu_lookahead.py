@@ -204,3 +204,48 @@ def test_lowres_batch_same_frame_two_distances(pkg, ctx, port):
         ctx.lowres_frame_cost_batch([(frames[fe], frames[p0], frames[p1], p0, p1, b, ds, bic) for fe, p0, p1, b, ds, bic in dup])
     for f in frames:
         f.close()
+
+
+def test_lowres_batch_rc_and_refusals(pkg, ctx, port):
+    """x264_cuda_lowres_frame_cost_batch_rc: two VBV evaluations (P costs of two frames) in ONE launch against the oracle, and the calls the
+    contract refuses: the VBV flag without a row array, VBV and default evaluations in one batch"""
+    from x264_vs2008_b200 import synth
+    w, h = 352, 288
+    g = port.geometry(w, h)
+    clip = synth.Clip(w, h, seed=57)
+    planes = lowres_planes(port, g, clip, 3)
+    frames = []
+    for i in range(3):
+        f = ctx.frame(w, h, pkg.FRAME_LOWRES)
+        f.upload(clip.luma(i)); f.expand_border(); f.init_lowres(); f.lookahead_alloc(3)
+        frames.append(f)
+    n = g.mb_width * g.mb_height
+    rng = np.random.default_rng(9)
+    inv = [rng.integers(100, 600, n).astype(np.uint16) for _ in range(3)]
+    want = []
+    for b in (1, 2):  # cost(b-1, b, b), every block, AQ-weighted
+        state = X.lowres_state(g)
+        rows = np.zeros(g.mb_height, np.int32)
+        o = port.lowres_frame_cost(g, planes[b], planes[b - 1], planes[b], b - 1, b, b, state, do_search=(1, 0), vbv=True, inv_qscale=inv[b], row_satd=rows)
+        want.append((o.score, o.intra_mbs, o.intra_cost_sum, o.score_aq, rows, state["mvs0"].copy()))
+    got = ctx.lowres_frame_cost_batch_rc([(frames[b], frames[b - 1], frames[b], b - 1, b, b, (1, 0), 0) for b in (1, 2)], inv_qscales=[inv[1], inv[2]])
+    for k, b in enumerate((1, 2)):
+        assert got[k][:4] == want[k][:4], (b, got[k][:4], want[k][:4])
+        assert np.array_equal(got[k][4], want[k][4]), b
+        mv, _, _ = frames[b].lookahead_get(0, 0)
+        assert np.array_equal(mv, want[k][5]), b  # every block, the frame edge included
+    # refusals
+    pm = np.array([0, 1, 1, 1, 16, pkg.ME_MBCMP_SATD | pkg.LOWRES_VBV, 1, 0, 1], np.int32)
+    res = np.zeros(4, np.int32)
+    assert pkg.lib().x264_cuda_lowres_frame_cost_rc(ctx.h, frames[1].h, frames[0].h, frames[1].h, pm.ctypes.data, None, res.ctypes.data, None) == -1
+    assert "row_satd" in ctx.error()
+    import ctypes as C
+    ptrs = [(C.c_void_p * 2)(frames[1].h, frames[2].h), (C.c_void_p * 2)(frames[0].h, frames[1].h), (C.c_void_p * 2)(frames[1].h, frames[2].h)]
+    pm2 = np.array([[0, 1, 1, 1, 16, pkg.ME_MBCMP_SATD | pkg.LOWRES_VBV, 1, 0, 1], [1, 2, 2, 1, 16, pkg.ME_MBCMP_SATD, 1, 0, 1]], np.int32)
+    res2 = np.zeros((2, 4), np.int32)
+    rows = [np.zeros(g.mb_height, np.int32) for _ in range(2)]
+    row_p = (C.c_void_p * 2)(rows[0].ctypes.data, rows[1].ctypes.data)
+    assert pkg.lib().x264_cuda_lowres_frame_cost_batch_rc(ctx.h, 2, ptrs[0], ptrs[1], ptrs[2], pm2.ctypes.data, None, res2.ctypes.data, row_p) == -1
+    assert "cannot share a batch" in ctx.error()
+    for f in frames:
+        f.close()

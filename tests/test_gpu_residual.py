@@ -297,3 +297,26 @@ def test_probe_skip_mc(pkg, ctx, port):
         assert len(jobs) // 8 < n1 < 7 * len(jobs) // 8, n1
     for f in (fref, fenc, fdec):
         f.close()
+
+
+def test_intra16_and_upload_refusals(pkg, ctx):
+    """out-of-range input is refused with -1 and a message instead of being written somewhere: a macroblock outside the frame or a mode
+    number outside the reference's enums (x264_cuda_residual_intra16), a picture larger than the frame's planes (x264_cuda_frame_upload*)"""
+    w, h = 64, 48
+    fenc, fdec = ctx.frame(w, h, pkg.FRAME_CHROMA), ctx.frame(w, h, pkg.FRAME_CHROMA)
+    ctx.set_quant_preset(0)
+    for bad in (dict(mb_x=4), dict(mb_y=3), dict(mode16=7), dict(mode_chroma=9), dict(mb_x=-1)):
+        jobs = np.zeros(1, pkg.INTRA16_JOB)
+        jobs[0]["qp"], jobs[0]["chroma_qp"], jobs[0]["mode16"], jobs[0]["mode_chroma"] = 26, 26, 6, 6
+        for k, v in bad.items():
+            jobs[0][k] = v
+        with pytest.raises(pkg.CudaError, match="out of range"):
+            ctx.residual_intra16(fenc, fdec, jobs)
+    big = np.zeros((h + 17, w), np.uint8)
+    with pytest.raises(pkg.CudaError, match="does not fit"):
+        fenc.upload(big)
+    with pytest.raises(pkg.CudaError, match="does not fit"):
+        fenc.upload_chroma(np.zeros((h // 2, w // 2 + 9), np.uint8), np.zeros((h // 2, w // 2), np.uint8))
+    ok = np.zeros((h, w), np.uint8)
+    fenc.upload(ok)  # the frame itself still works
+    fenc.close(); fdec.close()

@@ -492,6 +492,20 @@ class Context:
         self.check(lib().x264_cuda_lowres_frame_cost_batch(self.h, n, ptrs[0], ptrs[1], ptrs[2], pm.ctypes.data, res.ctypes.data))
         return [(int(r[0]), int(r[1]), int(r[2])) for r in res]
 
+    def lowres_frame_cost_batch_rc(self, evals, inv_qscales=None, vbv=True, me_method=1, me_range=16, flags=ME_MBCMP_SATD):
+        """the rate-control forms for a batch (all VBV or all default): evals as for lowres_frame_cost_batch, inv_qscales: list of uint16[n_mb]
+        or None.  -> list of (score, intra_mbs, intra_cost_sum, score_aq, row_satd or None)"""
+        n = len(evals)
+        ptrs = [(C.c_void_p * n)(*[e[k].h for e in evals]) for k in range(3)]
+        pm = np.array([[e[3], e[4], e[5], me_method, me_range, flags | (LOWRES_VBV if vbv else 0), e[6][0], e[6][1], e[7]] for e in evals], np.int32)
+        res = np.zeros((n, 4), np.int32)
+        rows = [np.zeros(evals[i][0].g.mb_height, np.int32) for i in range(n)] if vbv else None
+        iqs = [np.ascontiguousarray(q, np.uint16) for q in inv_qscales] if inv_qscales is not None else None
+        iq_p = (C.c_void_p * n)(*[q.ctypes.data for q in iqs]) if iqs is not None else None
+        row_p = (C.c_void_p * n)(*[r.ctypes.data for r in rows]) if vbv else None
+        self.check(lib().x264_cuda_lowres_frame_cost_batch_rc(self.h, n, ptrs[0], ptrs[1], ptrs[2], pm.ctypes.data, iq_p, res.ctypes.data, row_p))
+        return [(int(r[0]), int(r[1]), int(r[2]), int(r[3]), rows[i] if vbv else None) for i, r in enumerate(res)]
+
     def sad_grid(self, fenc, fref, radius, jobs):
         """-> uint16 [n_jobs, 9, GH, GW]: SAD of every partition at every integer vector of the window (0xffff = not available)"""
         assert jobs.dtype == GRID_JOB
