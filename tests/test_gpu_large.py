@@ -205,7 +205,7 @@ def test_probe_skip_large(pkg, ctx, port, size, n_sample):
     want = np.array(want, np.uint8)
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, (len(bad), bad[:8])
-    assert len(jobs) // 8 < int(want.sum()) < 7 * len(jobs) // 8, int(want.sum())
+    assert len(jobs) // 16 < int(want.sum()) < 15 * len(jobs) // 16, int(want.sum())  # both outcomes well represented (content-dependent: a wide band)
     fenc.close(); fdec.close()
 
 
