@@ -322,6 +322,7 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
     if (method == X264_CUDA_ME_METHOD_SEEDED || refine_only) {
         bmx = job.seed_mv[0]; bmy = job.seed_mv[1]; bcost = job.seed_cost;
     } else {
+        bool zero_done = false;
         if (subme >= 3) { // me.c:189-205: predictors at quarter-pel precision
             const uint32_t bmv = ((uint32_t)bmx & 0xffff) | ((uint32_t)bmy << 16);
             const int n = 1 + n_mvc;
@@ -342,8 +343,13 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
                 }
             }
             bmx = (bpred_mx + 2) >> 2; bmy = (bpred_my + 2) >> 2;
-            const int cost = eval_round(c, c.fpel_satd, lane, true, bmx << 2, bmy << 2);
-            if (cost < bcost) bcost = cost; // COST_MV(bmx,bmy) with bcost == COST_MAX
+            // COST_MV(bmx,bmy) with bcost == COST_MAX, then COST_MV(0,0) (me.c:229): two candidates of ONE round, folded in that order
+            const int kk = lane / c.U;
+            const int cost = eval_round(c, c.fpel_satd, lane, kk < 2, kk == 0 ? bmx << 2 : 0, kk == 0 ? bmy << 2 : 0);
+            const int c0 = cand_cost(c, cost, 0), c1 = cand_cost(c, cost, 1);
+            if (c0 < bcost) bcost = c0;
+            if (c1 < bcost) { bcost = c1; bmx = 0; bmy = 0; }
+            zero_done = true;
         } else { // me.c:207-227
             const int n = 1 + n_mvc;
             int cur_x = pmx, cur_y = pmy;
@@ -364,7 +370,7 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
             }
             bmx = cur_x; bmy = cur_y;
         }
-        { // COST_MV(0,0), me.c:229
+        if (!zero_done) { // COST_MV(0,0), me.c:229
             const int cost = eval_round(c, c.fpel_satd, lane, true, 0, 0);
             if (cost < bcost) { bcost = cost; bmx = 0; bmy = 0; }
         }
@@ -503,17 +509,23 @@ __device__ void warp_search(const SearchCtx &c, const x264_cuda_me_job_t &job, i
             if (v3 < sc) { sc = v3; sx = ox + 2; sy = oy; }
             if (sx == ox && sy == oy) break;
         }
-        if (!refine_only) { // !b_refine_qpel, me.c:729-736
+        // !b_refine_qpel (me.c:729-736): the centre is costed again with mbcmp.  Where a round has room for five candidates (U <= 4) that
+        // evaluation rides along with the first quarter-pel diamond instead of being a round of its own (the lookahead's searches are a chain
+        // of such rounds on the wavefront's critical path)
+        bool centre_pending = false;
+        if (!refine_only) {
             if (sy > spel_ymax) sy = spel_ymax;
-            sc = eval_round_satd(c, lane, true, sx, sy);
+            if (qpel_iters > 0 && 32 / c.U >= 5) centre_pending = true;
+            else sc = eval_round_satd(c, lane, true, sx, sy);
         }
         int bdir = -1;
         for (int i = qpel_iters; i > 0; i--) { // quarter-pel diamond with mbcmp, me.c:755-767
             const int odir = bdir, ox = sx, oy = sy;
             const int k = lane / c.U;
-            const int dx = k == 2 ? -1 : k == 3 ? 1 : 0, dy = k == 0 ? -1 : k == 1 ? 1 : 0;
-            const bool valid = k < 4 && (refine_only || (k ^ 1) != odir); // COST_MV_SATD: if( b_refine_qpel || (dir^1) != odir )
+            const int dx = k == 2 ? -1 : k == 3 ? 1 : 0, dy = k == 0 ? -1 : k == 1 ? 1 : 0; // k == 4: the centre itself
+            const bool valid = (k < 4 && (refine_only || (k ^ 1) != odir)) || (centre_pending && k == 4); // COST_MV_SATD: if( b_refine_qpel || (dir^1) != odir )
             const int v = eval_round_satd(c, lane, valid, ox + dx, oy + dy);
+            if (centre_pending) { sc = cand_cost(c, v, 4); centre_pending = false; }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int vj = cand_cost(c, v, j);

@@ -1030,11 +1030,14 @@ __global__ void __launch_bounds__(128) probe_skip_kernel(const QuantTables *__re
     const bool store = !in_fdec && (job.flags & X264_CUDA_SKIP_STORE_PRED) && pl.fd_y;
     const unsigned FULL = 0xffffffffu;
 
+    // Lanes 0..15 form the luma predictions (qpel fetch), lanes 16..23 the chroma ones (1/8-pel bilinear); the residual, transform,
+    // quantisation and decimation score of all 24 blocks then run as ONE instruction stream with a per-lane table list and qp.
     int score = 0, ssd = 0, dc0 = 0;
-    if (lane < 16) { // luma, macroblock.c:822-840
+    int f[16], p[16];
+    const bool isl = lane < 16, act = lane < 24;
+    if (isl) { // luma, macroblock.c:822-840
         const int bx = (lane & 1) + ((lane >> 2) & 1) * 2, by = ((lane >> 1) & 1) + ((lane >> 3) & 1) * 2;
         const size_t off = ((size_t)job.mb_y * 16 + by * 4) * pl.stride + job.mb_x * 16 + bx * 4;
-        int f[16], p[16], d[16], c[16];
         load4x4(pl.fe_y + off, pl.stride, f);
         if (in_fdec)
             load4x4(pl.fd_y + off, pl.stride, p);
@@ -1049,15 +1052,9 @@ __global__ void __launch_bounds__(128) probe_skip_kernel(const QuantTables *__re
                 if (store) *(uint32_t *)(pl.fd_y + off + (size_t)y * pl.stride) = w;
             }
         }
-#pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = f[k] - p[k];
-        fwd4x4(d, c);
-        uint32_t lvw[8];
-        quant_block4(qt, 1 /* CQM_4PY */, qp, c, true, 0, lvw, score);
-    } else if (lane < 24) { // chroma, macroblock.c:845-879
+    } else if (act) { // chroma, macroblock.c:845-879
         const int cl = lane - 16, ch = cl >> 2, bi = cl & 3;
         const size_t off = ((size_t)job.mb_y * 8 + (bi >> 1) * 4) * pl.stride_c + job.mb_x * 8 + (bi & 1) * 4;
-        int f[16], p[16], d[16], c[16];
         load4x4((ch ? pl.fe_v : pl.fe_u) + off, pl.stride_c, f);
         uint8_t *fd = (ch ? pl.fd_v : pl.fd_u);
         if (in_fdec)
@@ -1081,13 +1078,17 @@ __global__ void __launch_bounds__(128) probe_skip_kernel(const QuantTables *__re
             }
             if (store) store4x4(fd + off, pl.stride_c, p);
         }
-#pragma unroll
-        for (int k = 0; k < 16; k++) { d[k] = f[k] - p[k]; ssd += d[k] * d[k]; }
-        fwd4x4(d, c);
-        dc0 = c[0]; c[0] = 0; // dct2x2dc takes the DCs out (macroblock.c:72-85)
-        uint32_t lvw[8];
-        quant_block4(qt, 3 /* CQM_4PC */, cqp, c, true, 1, lvw, score);
     }
+    if (act) {
+        int d[16], c[16];
+        uint32_t lvw[8];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { d[k] = f[k] - p[k]; ssd += d[k] * d[k]; } // the SSD only matters on the chroma lanes (:843)
+        fwd4x4(d, c);
+        if (!isl) { dc0 = c[0]; c[0] = 0; } // dct2x2dc takes the chroma DCs out (macroblock.c:72-85)
+        quant_block4(qt, isl ? 1 /* CQM_4PY */ : 3 /* CQM_4PC */, isl ? qp : cqp, c, true, isl ? 0 : 1, lvw, score);
+    }
+    if (isl) ssd = 0;
 
     // luma total over lanes 0..15, per-plane chroma totals over lanes 16..19 / 20..23
     int luma = lane < 16 ? score : 0;
